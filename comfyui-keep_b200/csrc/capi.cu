@@ -1,0 +1,237 @@
+// keep_b200 — the C-ABI boundary (include/keep_b200.h): exceptions -> error codes, no torch types.
+#include <mutex>
+#include <vector>
+
+#include "engine.h"
+
+using namespace keep;
+
+struct keep_engine_s {
+    Engine* e;
+    std::mutex mu;
+};
+
+static thread_local std::string g_err;
+
+#define KEEP_API_BEGIN try {
+#define KEEP_API_END                                   \
+    }                                                  \
+    catch (const std::exception& ex) {                 \
+        g_err = ex.what();                             \
+        cudaGetLastError();                            \
+        return -1;                                     \
+    }                                                  \
+    catch (...) {                                      \
+        g_err = "keep_b200: unknown error";            \
+        return -2;                                     \
+    }
+
+int keepop_conv2d_tc(const ConvArgs& a, cudaStream_t s);   // conv_tcgen05.cu
+
+extern "C" {
+
+const char* keep_last_error(void) { return g_err.c_str(); }
+
+int keep_create(keep_handle* out, int device, const keep_weight_desc* weights, int n_weights, int flags) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(out && weights && n_weights > 0, "keep_create: null argument");
+    *out = nullptr;
+    keep_engine_s* h = new keep_engine_s();
+    try {
+        h->e = new Engine(device, weights, n_weights, flags);
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    *out = h;
+    return 0;
+    KEEP_API_END
+}
+
+size_t keep_workspace_bytes(keep_handle h, int b, int T) {
+    try {
+        if (!h) throw Error("keep_workspace_bytes: null handle");
+        std::lock_guard<std::mutex> lk(h->mu);
+        return h->e->workspace_bytes(b, T);
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return 0;
+    }
+}
+
+int keep_forward(keep_handle h, const float* x_dev, int b, int T, void* out_dev, int out_dtype, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h, "keep_forward: null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->e->forward(x_dev, b, T, out_dev, out_dtype, workspace, workspace_bytes, (cudaStream_t)stream);
+    return 0;
+    KEEP_API_END
+}
+
+int keep_destroy(keep_handle h) {
+    KEEP_API_BEGIN
+    if (h) {
+        delete h->e;
+        delete h;
+    }
+    return 0;
+    KEEP_API_END
+}
+
+long long keep_launch_count(keep_handle h) { return h ? h->e->launches() : 0; }
+
+int keep_debug_capture(keep_handle h, int enable) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h, "null handle");
+    h->e->set_capture(enable != 0);
+    return 0;
+    KEEP_API_END
+}
+
+int keep_debug_force(keep_handle h, const char* what, const void* host_data, size_t bytes) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h && what, "null argument");
+    h->e->force(what, host_data, bytes);
+    return 0;
+    KEEP_API_END
+}
+
+long long keep_debug_read(keep_handle h, const char* what, void* host_data, size_t bytes) {
+    try {
+        if (!h || !what) throw Error("null argument");
+        return (long long)h->e->read(what, host_data, bytes);
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// op-level hooks: a tiny weight-less Engine-free harness around the launchers
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    explicit DevBuf(size_t bytes) { CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 256)); }
+    ~DevBuf() { cudaFree(p); }
+};
+}  // namespace
+
+int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, const float* weight_host, const float* bias_host,
+                  int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
+                  const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
+                  float* out_dev, void* stream) {
+    KEEP_API_BEGIN
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<float> packed((size_t)cout * cin * kh * kw);
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i)
+            for (int y = 0; y < kh; ++y)
+                for (int x = 0; x < kw; ++x)
+                    packed[((size_t)(y * kw + x) * cin + i) * cout + o] = weight_host[(((size_t)o * cin + i) * kh + y) * kw + x];
+    DevBuf wd(packed.size() * 4), bd((size_t)cout * 4);
+    CUDA_CHECK(cudaMemcpy(wd.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    if (bias_host) CUDA_CHECK(cudaMemcpy(bd.p, bias_host, (size_t)cout * 4, cudaMemcpyHostToDevice));
+    ConvArgs a;
+    a.in0 = x_dev; a.c0 = cin; a.n = n; a.h = h; a.w = w; a.up = up;
+    a.pre_scale = pre_scale_dev; a.pre_shift = pre_shift_dev; a.pre_act = pre_act;
+    a.wt = (const float*)wd.p; a.bias = bias_host ? (const float*)bd.p : nullptr;
+    a.kh = kh; a.kw = kw; a.stride = stride; a.pad_t = pad_t; a.pad_l = pad_l; a.cout = cout;
+    a.ho = (h * up + pad_t + pad_b - kh) / stride + 1;
+    a.wo = (w * up + pad_l + pad_r - kw) / stride + 1;
+    a.act = act; a.res = res_dev; a.out = out_dev;
+    if (use_tc) {
+        int rc = keepop_conv2d_tc(a, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        return rc;
+    }
+    a.splitk = conv_pick_splitk(a);
+    DevBuf part(a.splitk > 1 ? (size_t)a.splitk * n * a.ho * a.wo * cout * 4 : 0);
+    a.partial = (float*)part.p;
+    conv2d_simt(a, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+    KEEP_API_END
+}
+
+int keepop_groupnorm_affine(const float* x_dev, int n, int hw, int c, int groups, float eps, const float* gamma_dev,
+                            const float* beta_dev, float* scale_dev, float* shift_dev, void* stream) {
+    KEEP_API_BEGIN
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf scratch(gn_scratch_doubles(n, hw, c) * 8);
+    groupnorm_affine(x_dev, F32, n, hw, c, c / groups, eps, gamma_dev, beta_dev, scale_dev, shift_dev, c, 0, (double*)scratch.p, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+    KEEP_API_END
+}
+
+int keepop_layernorm(const float* x_dev, int rows, int c, const float* g_dev, const float* b_dev, float eps, float* out_dev,
+                     void* stream) {
+    KEEP_API_BEGIN
+    layernorm(x_dev, rows, c, g_dev, b_dev, eps, nullptr, out_dev, nullptr, 0, nullptr, (cudaStream_t)stream);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+    KEEP_API_END
+}
+
+int keepop_attention(const float* q, const float* k, const float* v, int nb, int Lq, int Lk, int heads, int dh, float scale,
+                     float* out_dev, void* stream) {
+    KEEP_API_BEGIN
+    cudaStream_t s = (cudaStream_t)stream;
+    const int D = heads * dh;
+    DevBuf S((size_t)nb * heads * Lq * Lk * 4);
+    BGemmArgs g;
+    g.A = q; g.B = k; g.C = (float*)S.p;
+    g.M = Lq; g.N = Lk; g.K = dh; g.lda = D; g.ldb = D; g.ldc = Lk; g.transB = 1; g.alpha = scale;
+    g.nz0 = nb; g.nz1 = heads;
+    g.sA[0] = (long long)Lq * D; g.sA[1] = dh; g.sB[0] = (long long)Lk * D; g.sB[1] = dh;
+    g.sC[0] = (long long)heads * Lq * Lk; g.sC[1] = (long long)Lq * Lk;
+    bgemm_simt(g, s);
+    softmax_rows((float*)S.p, (long long)nb * heads * Lq, Lk, nullptr, 1, Lq, s);
+    BGemmArgs m;
+    m.A = (float*)S.p; m.B = v; m.C = out_dev;
+    m.M = Lq; m.N = dh; m.K = Lk; m.lda = Lk; m.ldb = D; m.ldc = D; m.transB = 0;
+    m.nz0 = nb; m.nz1 = heads;
+    m.sA[0] = (long long)heads * Lq * Lk; m.sA[1] = (long long)Lq * Lk;
+    m.sB[0] = (long long)Lk * D; m.sB[1] = dh; m.sC[0] = (long long)Lq * D; m.sC[1] = dh;
+    bgemm_simt(m, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+    KEEP_API_END
+}
+
+int keepop_flow_warp(const float* img, const float* flow, float* out, int n, int h, int w, int c, void* stream) {
+    KEEP_API_BEGIN
+    flow_warp(img, F32, flow, out, F32, n, h, w, c, (cudaStream_t)stream);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+    KEEP_API_END
+}
+
+int keepop_convex_upsample8(const float* mask, const float* flow, float* out, int n, int h, int w, void* stream) {
+    KEEP_API_BEGIN
+    convex_upsample8(mask, flow, out, n, h, w, (cudaStream_t)stream);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+    KEEP_API_END
+}
+
+int keepop_window_sine_pos(float* x, int n, int h, int w, int c, int splits, void* stream) {
+    KEEP_API_BEGIN
+    add_window_sine_pos(x, n, h, w, c, splits, (cudaStream_t)stream);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+    KEEP_API_END
+}
+
+int keepop_argmax_gather(const float* logits, int tokens, int ncodes, const float* codebook, int cdim, int* idx, float* quant,
+                         void* stream) {
+    KEEP_API_BEGIN
+    argmax_gather(logits, tokens, ncodes, codebook, cdim, nullptr, idx, quant, F32, (cudaStream_t)stream);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+    KEEP_API_END
+}
+
+}  // extern "C"

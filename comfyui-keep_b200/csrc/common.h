@@ -1,0 +1,119 @@
+// keep_b200 — shared host/device helpers for the sm_100a KEEP engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+
+namespace keep {
+
+// ------------------------------------------------------------------------------------------
+// errors: everything throws; the C-ABI layer converts to an error code + thread-local message
+// (the reference's nodes rely on catching exceptions, nodes.py:83-88 — never abort()).
+// ------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    explicit Error(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define KEEP_CHECK(cond, ...)                                                         \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            char _b[512];                                                             \
+            snprintf(_b, sizeof(_b), __VA_ARGS__);                                    \
+            char _c[768];                                                             \
+            snprintf(_c, sizeof(_c), "%s:%d: %s", __FILE__, __LINE__, _b);            \
+            throw ::keep::Error(_c);                                                  \
+        }                                                                             \
+    } while (0)
+
+#define CUDA_CHECK(expr)                                                              \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            char _c[768];                                                             \
+            snprintf(_c, sizeof(_c), "%s:%d: CUDA error %s: %s", __FILE__, __LINE__,  \
+                     cudaGetErrorName(_e), cudaGetErrorString(_e));                   \
+            throw ::keep::Error(_c);                                                  \
+        }                                                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// tensors: feature maps are NHWC; token matrices are (rows, C) == NHWC with h=rows, w=1
+// ------------------------------------------------------------------------------------------
+enum DType : int { F32 = 0, F16 = 1 };
+
+static inline size_t dtype_size(DType d) { return d == F32 ? 4 : 2; }
+
+struct Tensor {
+    void* p = nullptr;
+    int n = 0, h = 0, w = 0, c = 0;
+    DType dt = F32;
+    size_t numel() const { return (size_t)n * h * w * c; }
+    size_t bytes() const { return numel() * dtype_size(dt); }
+    size_t rows() const { return (size_t)n * h * w; }
+    float* f() const { return (float*)p; }
+    __half* hf() const { return (__half*)p; }
+};
+
+// activation applied in an epilogue / prologue
+enum Act : int { ACT_NONE = 0, ACT_SWISH = 1, ACT_RELU = 2, ACT_LRELU02 = 3, ACT_GELU = 4, ACT_SIGMOID = 5 };
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float ldf(const float* p, size_t i) { return p[i]; }
+__device__ __forceinline__ float ldf(const __half* p, size_t i) { return __half2float(p[i]); }
+__device__ __forceinline__ void stf(float* p, size_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void stf(__half* p, size_t i, float v) { p[i] = __float2half_rn(v); }
+
+// 4 consecutive elements (i must be a multiple of 4 and the row 16B/8B aligned)
+__device__ __forceinline__ float4 ld4(const float* p, size_t i) { return *reinterpret_cast<const float4*>(p + i); }
+__device__ __forceinline__ float4 ld4(const __half* p, size_t i) {
+    uint2 u = *reinterpret_cast<const uint2*>(p + i);
+    __half2 a = *reinterpret_cast<__half2*>(&u.x), b = *reinterpret_cast<__half2*>(&u.y);
+    float2 fa = __half22float2(a), fb = __half22float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, size_t i, float4 v) { *reinterpret_cast<float4*>(p + i) = v; }
+__device__ __forceinline__ void st4(__half* p, size_t i, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p + i) = u;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case ACT_SWISH: return v / (1.0f + expf(-v));                       // x * sigmoid(x)
+        case ACT_RELU: return fmaxf(v, 0.0f);
+        case ACT_LRELU02: return v > 0.0f ? v : 0.2f * v;
+        case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact (erf) GELU
+        case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace keep

@@ -1,0 +1,248 @@
+// keep_b200 — exact-fp32 implicit-GEMM convolution / linear on CUDA cores (NHWC).
+//
+// This is the precision-reference compute path of the engine ("fp32" mode) and the fallback for
+// shapes the tcgen05 kernel does not take (Cin = 3 stems, Cin = 130 upsampler, Cout = 3 / 1 heads).
+// Replaces every nn.Conv2d / nn.Linear the reference dispatches to cuDNN / cuBLAS on this path
+// (vqgan_arch.py:161-181,260-286,311-335; keep_arch.py:445-455,766-772,78-87,391-393,929,936-938;
+//  gmflow/backbone.py:11-14,50,64; gmflow/gmflow.py:46-48; gmflow/transformer.py:128-143,336-337).
+//
+// Fusions: nearest-x2 upsample and channel concat in the im2col gather, GroupNorm/InstanceNorm
+// apply + activation in the A-operand prologue, bias + activation + residual in the epilogue,
+// deterministic split-K for the small-M (16^2 / 32^2) layers of the serial per-frame chain.
+#include "ops.h"
+
+namespace keep {
+
+namespace {
+constexpr int BM = 128, BN = 64, BK = 16, NTHREADS = 256;
+
+__device__ __forceinline__ void load8(const void* src, int dt, size_t off, float* v) {
+    if (dt == F32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
+        float4 a = p[0], b = p[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + off);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(h[j]);
+            v[2 * j] = f.x; v[2 * j + 1] = f.y;
+        }
+    }
+}
+__device__ __forceinline__ float load1(const void* src, int dt, size_t off) {
+    return dt == F32 ? reinterpret_cast<const float*>(src)[off] : __half2float(reinterpret_cast<const __half*>(src)[off]);
+}
+__device__ __forceinline__ void store1(void* dst, int dt, size_t off, float v) {
+    if (dt == F32) reinterpret_cast<float*>(dst)[off] = v;
+    else reinterpret_cast<__half*>(dst)[off] = __float2half_rn(v);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(NTHREADS) conv_igemm_simt_kernel(const ConvArgs a) {
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int cin = a.c0 + a.c1;
+    const int HoWo = a.ho * a.wo;
+    const int M = a.n * HoWo;
+    const int K = a.kh * a.kw * cin;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nchunks = (K + BK - 1) / BK;
+    const int per = (nchunks + a.splitk - 1) / a.splitk;
+    const int ck0 = blockIdx.z * per;
+    const int ck1 = min(nchunks, ck0 + per);
+
+    // ---- loader coordinates: one output pixel per thread, 8 consecutive k per thread
+    const int lp = tid & (BM - 1);
+    const int lk = (tid >> 7) * 8;
+    const int m = m0 + lp;
+    const bool mvalid = m < M;
+    int pn = 0, oy = 0, ox = 0;
+    if (mvalid) {
+        pn = m / HoWo;
+        int r = m - pn * HoWo;
+        oy = r / a.wo;
+        ox = r - oy * a.wo;
+    }
+    const int iy0 = oy * a.stride - a.pad_t, ix0 = ox * a.stride - a.pad_l;
+    const int Hl = a.h * a.up, Wl = a.w * a.up;
+    const int bk = tid >> 4, bn4 = (tid & 15) * 4;  // B loader: row k, 4 consecutive n
+
+    float av[8];
+    float bv[4];
+
+    auto load_chunk = [&](int ck) {
+        const int k0 = ck * BK;
+        // ---------------- A (im2col gather + prologue) ----------------
+        if (FAST) {
+            const int kk = k0 + lk;
+            const int tap = kk / cin;
+            const int ci = kk - tap * cin;
+            const int ky = tap / a.kw, kx = tap - ky * a.kw;
+            const int iy = iy0 + ky, ix = ix0 + kx;
+            const bool ok = mvalid && iy >= 0 && iy < Hl && ix >= 0 && ix < Wl;
+            if (ok) {
+                const size_t pix = ((size_t)pn * a.h + iy / a.up) * a.w + ix / a.up;
+                if (ci < a.c0) load8(a.in0, a.in0_dt, pix * a.c0 + ci, av);
+                else load8(a.in1, a.in1_dt, pix * a.c1 + (ci - a.c0), av);
+                if (a.pre_scale) {
+                    const float* sc = a.pre_scale + (size_t)pn * cin + ci;
+                    const float* sh = a.pre_shift + (size_t)pn * cin + ci;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) av[j] = apply_act(fmaf(av[j], sc[j], sh[j]), a.pre_act);
+                } else if (a.pre_act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) av[j] = apply_act(av[j], a.pre_act);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) av[j] = 0.0f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kk = k0 + lk + j;
+                float v = 0.0f;
+                if (mvalid && kk < K) {
+                    const int tap = kk / cin;
+                    const int ci = kk - tap * cin;
+                    const int ky = tap / a.kw, kx = tap - ky * a.kw;
+                    const int iy = iy0 + ky, ix = ix0 + kx;
+                    if (iy >= 0 && iy < Hl && ix >= 0 && ix < Wl) {
+                        const size_t pix = ((size_t)pn * a.h + iy / a.up) * a.w + ix / a.up;
+                        v = ci < a.c0 ? load1(a.in0, a.in0_dt, pix * a.c0 + ci)
+                                      : load1(a.in1, a.in1_dt, pix * a.c1 + (ci - a.c0));
+                        if (a.pre_scale) v = fmaf(v, a.pre_scale[(size_t)pn * cin + ci], a.pre_shift[(size_t)pn * cin + ci]);
+                        v = apply_act(v, a.pre_act);
+                    }
+                }
+                av[j] = v;
+            }
+        }
+        // ---------------- B (weights [K][cout]) ----------------
+        const int kb = k0 + bk;
+        if (FAST) {
+            if (n0 + bn4 < a.cout) {  // kb < K always (K % 16 == 0), cout % 4 == 0
+                float4 t = *reinterpret_cast<const float4*>(a.wt + (size_t)kb * a.cout + n0 + bn4);
+                bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+            } else {
+                bv[0] = bv[1] = bv[2] = bv[3] = 0.0f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int nn = n0 + bn4 + j;
+                bv[j] = (kb < K && nn < a.cout) ? a.wt[(size_t)kb * a.cout + nn] : 0.0f;
+            }
+        }
+    };
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    const int ty = tid >> 4, tx = tid & 15;
+    if (ck0 < ck1) load_chunk(ck0);
+    for (int ck = ck0; ck < ck1; ++ck) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) As[lk + j][lp] = av[j];
+        *reinterpret_cast<float4*>(&Bs[bk][bn4]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+        __syncthreads();
+        if (ck + 1 < ck1) load_chunk(ck + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+    }
+
+    // ---------------- epilogue ----------------
+    const int nb = n0 + tx * 4;
+    if (a.splitk > 1) {
+        float* part = a.partial + (size_t)blockIdx.z * M * a.cout;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int mm = m0 + ty * 8 + i;
+            if (mm >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (nb + j < a.cout) part[(size_t)mm * a.cout + nb + j] = acc[i][j];
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int mm = m0 + ty * 8 + i;
+        if (mm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nn = nb + j;
+            if (nn >= a.cout) continue;
+            float v = acc[i][j] + (a.bias ? a.bias[nn] : 0.0f);
+            v = apply_act(v, a.act);
+            const size_t o = (size_t)mm * a.cout + nn;
+            if (a.res) v += load1(a.res, a.res_dt, o);
+            store1(a.out, a.out_dt, o, v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
+                                                            const float* __restrict__ bias, int act, const void* res,
+                                                            int res_dt, void* out, int out_dt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MN) return;
+    float v = 0.0f;
+    for (int z = 0; z < splitk; ++z) v += part[(size_t)z * MN + i];
+    if (bias) v += bias[i % cout];
+    v = apply_act(v, act);
+    if (res) v += load1(res, res_dt, i);
+    store1(out, out_dt, i, v);
+}
+}  // namespace
+
+int conv_pick_splitk(const ConvArgs& a) {
+    const long long M = (long long)a.n * a.ho * a.wo;
+    const int K = a.kh * a.kw * (a.c0 + a.c1);
+    const long long ctas = (long long)cdiv(M, BM) * cdiv(a.cout, BN);
+    const int nchunks = cdiv(K, BK);
+    if (ctas >= 120 || nchunks < 16) return 1;
+    long long s = (296 + ctas - 1) / ctas;
+    if (s > nchunks / 4) s = nchunks / 4;
+    if (s > 32) s = 32;
+    return s < 1 ? 1 : (int)s;
+}
+
+void conv2d_simt(const ConvArgs& a, cudaStream_t s) {
+    const int cin = a.c0 + a.c1;
+    const long long M = (long long)a.n * a.ho * a.wo;
+    KEEP_CHECK(M > 0 && a.cout > 0 && cin > 0, "conv2d_simt: empty problem");
+    KEEP_CHECK(a.up == 1 || a.up == 2, "conv2d_simt: up must be 1 or 2");
+    KEEP_CHECK(a.splitk == 1 || a.partial != nullptr, "conv2d_simt: split-K needs a partial buffer");
+    const bool fast = (a.c0 % 16 == 0) && (a.c1 % 16 == 0) && (a.cout % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.in0) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.in1) & 15) == 0);
+    dim3 grid(cdiv(M, BM), cdiv(a.cout, BN), a.splitk);
+    if (fast) conv_igemm_simt_kernel<true><<<grid, NTHREADS, 0, s>>>(a);
+    else conv_igemm_simt_kernel<false><<<grid, NTHREADS, 0, s>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    if (a.splitk > 1) {
+        const long long MN = M * a.cout;
+        splitk_reduce_kernel<<<cdiv(MN, 256), 256, 0, s>>>(a.partial, a.splitk, MN, a.cout, a.bias, a.act, a.res, a.res_dt,
+                                                            a.out, a.out_dt);
+        CUDA_CHECK(cudaGetLastError());
+    }
+}
+
+}  // namespace keep

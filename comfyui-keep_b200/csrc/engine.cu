@@ -1,0 +1,1071 @@
+// keep_b200 — KEEP forward orchestration: reference call graph (keep_arch.py:1008-1145) re-expressed
+// as a stream of hand-written sm_100a kernels over NHWC activations.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace keep {
+
+// =============================================================================================
+// Arena
+// =============================================================================================
+void Arena::reset(char* base, size_t cap, bool dry) {
+    base_ = base; cap_ = cap; dry_ = dry; peak_ = 0;
+    blocks_.clear();
+    blocks_.push_back({0, cap, false});
+}
+
+void* Arena::alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    for (size_t i = 0; i < blocks_.size(); ++i) {
+        Block& b = blocks_[i];
+        if (!b.used && b.size >= bytes) {
+            if (b.size > bytes) {
+                Block rest{b.off + bytes, b.size - bytes, false};
+                b.size = bytes;
+                b.used = true;
+                const size_t off = b.off;
+                blocks_.insert(blocks_.begin() + i + 1, rest);
+                peak_ = std::max(peak_, off + bytes);
+                return base_ + off;
+            }
+            b.used = true;
+            peak_ = std::max(peak_, b.off + bytes);
+            return base_ + b.off;
+        }
+    }
+    throw Error("keep_b200: workspace exhausted (need " + std::to_string(bytes) + " more bytes, capacity " + std::to_string(cap_) +
+                "); size it with keep_workspace_bytes(b, T)");
+}
+
+void Arena::free(void* p) {
+    if (!p) return;
+    const size_t off = (size_t)((char*)p - base_);
+    for (size_t i = 0; i < blocks_.size(); ++i) {
+        if (blocks_[i].off == off && blocks_[i].used) {
+            blocks_[i].used = false;
+            if (i + 1 < blocks_.size() && !blocks_[i + 1].used) {
+                blocks_[i].size += blocks_[i + 1].size;
+                blocks_.erase(blocks_.begin() + i + 1);
+            }
+            if (i > 0 && !blocks_[i - 1].used) {
+                blocks_[i - 1].size += blocks_[i].size;
+                blocks_.erase(blocks_.begin() + i);
+            }
+            return;
+        }
+    }
+    throw Error("keep_b200: arena free of unknown pointer");
+}
+
+// =============================================================================================
+// weights
+// =============================================================================================
+static bool ends_with(const std::string& s, const std::string& suf) {
+    return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+void Engine::add_arr(const std::string& key, const std::vector<float>& host, int d0, int d1, int d2, int d3) {
+    staging_.push_back({key, host});
+    DevArr a;
+    a.numel = (long long)host.size();
+    a.d[0] = d0; a.d[1] = d1; a.d[2] = d2; a.d[3] = d3;
+    W_[key] = a;
+}
+
+// conv OIHW -> [(ky*kw + kx)*I + i][o]; linear (O, I) is the 1x1 case
+static std::vector<float> pack_oihw(const float* w, int O, int I, int kh, int kw) {
+    std::vector<float> out((size_t)O * I * kh * kw);
+    for (int o = 0; o < O; ++o)
+        for (int i = 0; i < I; ++i)
+            for (int y = 0; y < kh; ++y)
+                for (int x = 0; x < kw; ++x)
+                    out[((size_t)(y * kw + x) * I + i) * O + o] = w[(((size_t)o * I + i) * kh + y) * kw + x];
+    return out;
+}
+
+void Engine::pack_weights(const keep_weight_desc* w, int n_w) {
+    std::unordered_map<std::string, const keep_weight_desc*> by_name;
+    for (int i = 0; i < n_w; ++i) {
+        KEEP_CHECK(w[i].name && w[i].data && w[i].ndim >= 1 && w[i].ndim <= 4, "bad weight descriptor %d", i);
+        by_name[w[i].name] = &w[i];
+    }
+    auto numel = [](const keep_weight_desc* d) { long long n = 1; for (int i = 0; i < d->ndim; ++i) n *= d->shape[i]; return n; };
+    for (int i = 0; i < n_w; ++i) {
+        const keep_weight_desc* d = &w[i];
+        const std::string key = d->name;
+        const long long ne = numel(d);
+        if (key == "position_emb" || key == "quantize.embedding.weight") {
+            add_arr(key, std::vector<float>(d->data, d->data + ne), (int)d->shape[0], (int)d->shape[1]);
+        } else if (ends_with(key, "in_proj_weight")) {  // nn.MultiheadAttention packed (3E, E): q | k | v
+            const int E = (int)d->shape[1];
+            KEEP_CHECK(d->ndim == 2 && d->shape[0] == 3 * E, "in_proj_weight shape");
+            const std::string base = key.substr(0, key.size() - strlen("in_proj_weight"));
+            add_arr(base + "in_proj_qk.weight", pack_oihw(d->data, 2 * E, E, 1, 1), E, 2 * E, 1, 1);
+            add_arr(base + "in_proj_v.weight", pack_oihw(d->data + (size_t)2 * E * E, E, E, 1, 1), E, E, 1, 1);
+        } else if (ends_with(key, "in_proj_bias")) {
+            const int E = (int)(d->shape[0] / 3);
+            const std::string base = key.substr(0, key.size() - strlen("in_proj_bias"));
+            add_arr(base + "in_proj_qk.bias", std::vector<float>(d->data, d->data + 2 * E), 2 * E);
+            add_arr(base + "in_proj_v.bias", std::vector<float>(d->data + 2 * E, d->data + 3 * E), E);
+        } else if (d->ndim == 4) {
+            add_arr(key, pack_oihw(d->data, (int)d->shape[0], (int)d->shape[1], (int)d->shape[2], (int)d->shape[3]),
+                    (int)d->shape[1], (int)d->shape[0], (int)d->shape[2], (int)d->shape[3]);
+            // AttnBlock q|k|v 1x1 convs fused into one N = 3C GEMM (vqgan_arch.py:222-224)
+            if (ends_with(key, ".q.weight")) {
+                const std::string base = key.substr(0, key.size() - strlen("q.weight"));
+                auto kq = by_name.find(base + "k.weight"), vq = by_name.find(base + "v.weight");
+                auto bq = by_name.find(base + "q.bias"), bk = by_name.find(base + "k.bias"), bv = by_name.find(base + "v.bias");
+                if (kq != by_name.end() && vq != by_name.end() && bq != by_name.end() && bk != by_name.end() && bv != by_name.end()) {
+                    const int C = (int)d->shape[1], O = (int)d->shape[0];
+                    std::vector<float> cat((size_t)C * 3 * O), bias(3 * O);
+                    const float* src[3] = {d->data, kq->second->data, vq->second->data};
+                    const float* bsrc[3] = {bq->second->data, bk->second->data, bv->second->data};
+                    for (int t = 0; t < 3; ++t) {
+                        for (int o = 0; o < O; ++o) {
+                            for (int c = 0; c < C; ++c) cat[(size_t)c * 3 * O + t * O + o] = src[t][(size_t)o * C + c];
+                            bias[t * O + o] = bsrc[t][o];
+                        }
+                    }
+                    add_arr(base + "qkv.weight", cat, C, 3 * O, 1, 1);
+                    add_arr(base + "qkv.bias", bias, 3 * O);
+                }
+            }
+        } else if (d->ndim == 2) {
+            add_arr(key, pack_oihw(d->data, (int)d->shape[0], (int)d->shape[1], 1, 1), (int)d->shape[1], (int)d->shape[0], 1, 1);
+        } else {
+            add_arr(key, std::vector<float>(d->data, d->data + ne), (int)d->shape[0]);
+        }
+    }
+    // one pool, one upload
+    size_t total = 0;
+    for (auto& kv : staging_) total += (kv.second.size() + 63) & ~(size_t)63;
+    if (!dry_only_) CUDA_CHECK(cudaMalloc((void**)&wpool_, total * sizeof(float)));
+    size_t off = 0;
+    for (auto& kv : staging_) {
+        if (!dry_only_)
+            CUDA_CHECK(cudaMemcpy(wpool_ + off, kv.second.data(), kv.second.size() * sizeof(float), cudaMemcpyHostToDevice));
+        W_[kv.first].p = (dry_only_ ? (float*)(uintptr_t)4096 : wpool_) + off;
+        off += (kv.second.size() + 63) & ~(size_t)63;
+    }
+    staging_.clear();
+    staging_.shrink_to_fit();
+}
+
+const float* Engine::warr(const std::string& key) const {
+    auto it = W_.find(key);
+    KEEP_CHECK(it != W_.end(), "missing weight '%s' (state dict must match the reference's KEEP keys)", key.c_str());
+    return it->second.p;
+}
+
+ConvW Engine::convw(const std::string& prefix) const {
+    auto it = W_.find(prefix + ".weight");
+    KEEP_CHECK(it != W_.end(), "missing weight '%s.weight'", prefix.c_str());
+    ConvW c;
+    c.w = it->second.p;
+    c.cin = it->second.d[0]; c.cout = it->second.d[1]; c.kh = it->second.d[2]; c.kw = it->second.d[3];
+    KEEP_CHECK(c.kh >= 1 && c.kw >= 1, "'%s.weight' is not a conv/linear weight", prefix.c_str());
+    auto ib = W_.find(prefix + ".bias");
+    c.b = ib == W_.end() ? nullptr : ib->second.p;
+    return c;
+}
+
+// =============================================================================================
+// construction
+// =============================================================================================
+Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : device_(device), flags_(flags) {
+    dry_only_ = (flags & KEEP_FLAG_PLAN_ONLY) != 0;
+    if (!dry_only_) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        KEEP_CHECK(e == cudaSuccess && ndev > 0, "keep_b200 needs a CUDA device (no CPU fallback): %s", cudaGetErrorString(e));
+        KEEP_CHECK(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        KEEP_CHECK(prop.major == 10, "keep_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device,
+                   prop.major, prop.minor);
+    }
+    adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
+    pack_weights(w, n_w);
+    // required keys (strict load, like load_state_dict(strict=True))
+    const char* must[] = {"position_emb", "quantize.embedding.weight", "feat_emb.weight", "idx_pred_layer.1.weight",
+                          "encoder.blocks.0.weight", "hq_encoder.blocks.24.weight", "generator.blocks.24.weight",
+                          "flownet.model.backbone.conv1.weight", "kalman_filter.kalman_gain_calculator.3.weight",
+                          "cft.16.scale.0.weight", "cfa.32.attn.to_q.weight", "ft_layers.8.linear2.weight"};
+    for (const char* k : must) KEEP_CHECK(has(k), "state dict is missing '%s'", k);
+
+    // GMFlow shifted-window region ids (gmflow/transformer.py:19-43) for a 64x64 map, 2x2 windows, shift 16
+    if (!dry_only_) {
+        const int H = 64, Wd = 64, wh = 32, ww = 32, sh = 16, sw = 16;
+        std::vector<int> reg(4 * 1024);
+        for (int win = 0; win < 4; ++win)
+            for (int t = 0; t < 1024; ++t) {
+                const int y = (win / 2) * wh + t / ww, x = (win % 2) * ww + t % ww;
+                const int ry = y < H - wh ? 0 : (y < H - sh ? 1 : 2);
+                const int rx = x < Wd - ww ? 0 : (x < Wd - sw ? 1 : 2);
+                reg[win * 1024 + t] = ry * 3 + rx;
+            }
+        CUDA_CHECK(cudaMalloc((void**)&region_, reg.size() * sizeof(int)));
+        CUDA_CHECK(cudaMemcpy(region_, reg.data(), reg.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<float> grid(4096 * 2);
+        for (int t = 0; t < 4096; ++t) { grid[2 * t] = (float)(t % 64); grid[2 * t + 1] = (float)(t / 64); }
+        CUDA_CHECK(cudaMalloc((void**)&grid64_, grid.size() * sizeof(float)));
+        CUDA_CHECK(cudaMemcpy(grid64_, grid.data(), grid.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+}
+
+Engine::~Engine() {
+    if (dry_only_) return;
+    cudaSetDevice(device_);
+    cudaFree(wpool_);
+    cudaFree(region_);
+    cudaFree(grid64_);
+    cudaFree(own_ws_);
+    for (auto& kv : cap_) cudaFree(kv.second.p);
+    for (auto& kv : forced_) cudaFree(kv.second.p);
+}
+
+// =============================================================================================
+// building blocks
+// =============================================================================================
+void Engine::begin(void* ws, size_t ws_bytes, cudaStream_t s, bool dry) {
+    s_ = s;
+    if (dry) arena_.reset((char*)(uintptr_t)4096, (size_t)1 << 46, true);
+    else arena_.reset((char*)ws, ws_bytes, false);
+}
+
+Tensor Engine::talloc(int n, int h, int w, int c, int dt) {
+    Tensor t;
+    t.n = n; t.h = h; t.w = w; t.c = c; t.dt = (DType)dt;
+    t.p = arena_.alloc(t.bytes());
+    return t;
+}
+void Engine::tfree(Tensor& t) { arena_.free(t.p); t.p = nullptr; }
+void Engine::afree(Aff& a) { arena_.free(a.scale); a.scale = a.shift = nullptr; }
+
+void Engine::capture(const std::string& name, const void* dev, size_t bytes) {
+    if (!capture_ || arena_.dry()) return;
+    Cap& c = cap_[name];
+    if (c.bytes < bytes) {
+        cudaFree(c.p);
+        CUDA_CHECK(cudaMalloc(&c.p, bytes));
+        c.bytes = bytes;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(c.p, dev, bytes, cudaMemcpyDeviceToDevice, s_));
+}
+
+Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
+    const int c1 = o.in1 ? o.in1->c : 0;
+    KEEP_CHECK(cw.cin == x.c + c1, "conv: weight expects %d input channels, got %d", cw.cin, x.c + c1);
+    ConvArgs a;
+    a.in0 = x.p; a.in0_dt = x.dt; a.c0 = x.c;
+    if (o.in1) {
+        KEEP_CHECK(o.in1->n == x.n && o.in1->h == x.h && o.in1->w == x.w, "conv: concat sources differ in shape");
+        a.in1 = o.in1->p; a.in1_dt = o.in1->dt; a.c1 = c1;
+    }
+    a.n = x.n; a.h = x.h; a.w = x.w; a.up = o.up;
+    if (o.pre) { a.pre_scale = o.pre->scale; a.pre_shift = o.pre->shift; }
+    a.pre_act = o.pre_act;
+    a.wt = cw.w; a.bias = cw.b;
+    a.kh = cw.kh; a.kw = cw.kw; a.stride = o.stride; a.pad_t = o.pad_t; a.pad_l = o.pad_l; a.cout = cw.cout;
+    a.ho = (x.h * o.up + o.pad_t + o.pad_b - cw.kh) / o.stride + 1;
+    a.wo = (x.w * o.up + o.pad_l + o.pad_r - cw.kw) / o.stride + 1;
+    a.act = o.act;
+    Tensor out = talloc(x.n, a.ho, a.wo, cw.cout, o.out_dt < 0 ? adt_ : o.out_dt);
+    if (o.res) {
+        KEEP_CHECK(o.res->numel() == out.numel(), "conv: residual shape mismatch");
+        a.res = o.res->p; a.res_dt = o.res->dt;
+    }
+    a.out = out.p; a.out_dt = out.dt;
+    a.splitk = conv_pick_splitk(a);
+    void* part = nullptr;
+    if (a.splitk > 1) {
+        part = arena_.alloc((size_t)a.splitk * out.numel() * sizeof(float));
+        a.partial = (float*)part;
+    }
+    if (!arena_.dry()) {
+        conv2d_simt(a, s_);
+        launches_ += a.splitk > 1 ? 2 : 1;
+    }
+    if (part) arena_.free(part);
+    return out;
+}
+
+Tensor Engine::linear(const Tensor& x, const std::string& prefix, int act, const Tensor* res) {
+    ConvOpt o;
+    o.act = act; o.res = res; o.out_dt = F32;
+    return conv(x, convw(prefix), o);
+}
+
+Aff Engine::gn(const Tensor& x, const std::string& prefix, const Tensor* x2) {
+    const int ct = x.c + (x2 ? x2->c : 0);
+    KEEP_CHECK(ct % 32 == 0, "GroupNorm(32): %d channels", ct);
+    const int cpg = ct / 32;
+    Aff a;
+    a.scale = (float*)arena_.alloc((size_t)2 * x.n * ct * sizeof(float));
+    a.shift = a.scale + (size_t)x.n * ct;
+    const float* g = warr(prefix + ".weight");
+    const float* b = warr(prefix + ".bias");
+    const int hw = x.h * x.w;
+    double* scratch = (double*)arena_.alloc(gn_scratch_doubles(x.n, hw, std::max(x.c, x2 ? x2->c : 0)) * sizeof(double));
+    if (!arena_.dry()) {
+        groupnorm_affine(x.p, x.dt, x.n, hw, x.c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, 0, scratch, s_);
+        launches_ += 2;
+        if (x2) {
+            KEEP_CHECK(x.c % cpg == 0, "GroupNorm over concat: group straddles the sources");
+            groupnorm_affine(x2->p, x2->dt, x2->n, hw, x2->c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, x.c, scratch, s_);
+            launches_ += 2;
+        }
+    }
+    arena_.free(scratch);
+    return a;
+}
+
+Aff Engine::inorm(const Tensor& x) {
+    Aff a;
+    a.scale = (float*)arena_.alloc((size_t)2 * x.n * x.c * sizeof(float));
+    a.shift = a.scale + (size_t)x.n * x.c;
+    const int hw = x.h * x.w;
+    double* scratch = (double*)arena_.alloc(gn_scratch_doubles(x.n, hw, x.c) * sizeof(double));
+    if (!arena_.dry()) {
+        groupnorm_affine(x.p, x.dt, x.n, hw, x.c, 1, 1e-5f, nullptr, nullptr, a.scale, a.shift, x.c, 0, scratch, s_);
+        launches_ += 2;
+    }
+    arena_.free(scratch);
+    return a;
+}
+
+Tensor Engine::ln(const Tensor& x, const std::string& prefix, const Tensor* res, const float* add2, int add2_rows, Tensor* out2) {
+    KEEP_CHECK(x.dt == F32, "layernorm expects fp32 tokens");
+    Tensor out = talloc(x.n, x.h, x.w, x.c, F32);
+    if (out2) *out2 = talloc(x.n, x.h, x.w, x.c, F32);
+    if (!arena_.dry()) {
+        layernorm(x.f(), (int)x.rows(), x.c, warr(prefix + ".weight"), warr(prefix + ".bias"), 1e-5f, res ? res->f() : nullptr,
+                  out.f(), add2, add2_rows, out2 ? out2->f() : nullptr, s_);
+        launches_ += 1;
+    }
+    return out;
+}
+
+// vqgan_arch.py:170-181
+Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2) {
+    Aff a1 = gn(x, p + ".norm1", x2);
+    ConvOpt o1;
+    o1.pad(1); o1.pre = &a1; o1.pre_act = ACT_SWISH; o1.in1 = x2;
+    Tensor h = conv(x, p + ".conv1", o1);
+    afree(a1);
+    Aff a2 = gn(h, p + ".norm2");
+    Tensor skip = x;
+    const bool own_skip = has(p + ".conv_out.weight");
+    if (own_skip) {
+        ConvOpt os;
+        os.in1 = x2;
+        skip = conv(x, p + ".conv_out", os);
+    } else {
+        KEEP_CHECK(!x2, "res_block: concat input needs conv_out");
+    }
+    ConvOpt o2;
+    o2.pad(1); o2.pre = &a2; o2.pre_act = ACT_SWISH; o2.res = &skip;
+    Tensor out = conv(h, p + ".conv2", o2);
+    afree(a2);
+    tfree(h);
+    if (own_skip) tfree(skip);
+    return out;
+}
+
+// generic multi-head attention: scores -> softmax -> PV, all fp32
+Tensor Engine::mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv,
+                   long long sv, int nb, int Lq, int Lk, int heads, int dh, float scale) {
+    Tensor S = talloc(nb * heads, Lq, 1, Lk, F32);
+    Tensor O = talloc(nb, Lq, 1, heads * dh, F32);
+    if (!arena_.dry()) {
+        BGemmArgs g;
+        g.A = q; g.B = k; g.C = S.f();
+        g.M = Lq; g.N = Lk; g.K = dh; g.lda = ldq; g.ldb = ldk; g.ldc = Lk; g.transB = 1; g.alpha = scale;
+        g.nz0 = nb; g.nz1 = heads;
+        g.sA[0] = sq; g.sA[1] = dh; g.sB[0] = sk; g.sB[1] = dh;
+        g.sC[0] = (long long)heads * Lq * Lk; g.sC[1] = (long long)Lq * Lk;
+        bgemm_simt(g, s_);
+        softmax_rows(S.f(), (long long)nb * heads * Lq, Lk, nullptr, 1, Lq, s_);
+        BGemmArgs h;
+        h.A = S.f(); h.B = v; h.C = O.f();
+        h.M = Lq; h.N = dh; h.K = Lk; h.lda = Lk; h.ldb = ldv; h.ldc = heads * dh; h.transB = 0;
+        h.nz0 = nb; h.nz1 = heads;
+        h.sA[0] = (long long)heads * Lq * Lk; h.sA[1] = (long long)Lq * Lk;
+        h.sB[0] = sv; h.sB[1] = dh;
+        h.sC[0] = (long long)Lq * heads * dh; h.sC[1] = dh;
+        bgemm_simt(h, s_);
+        launches_ += 3;
+    }
+    tfree(S);
+    return O;
+}
+
+// vqgan_arch.py:219-243
+Tensor Engine::attn_block(const Tensor& x, const std::string& p) {
+    Aff a = gn(x, p + ".norm");
+    ConvOpt o;
+    o.pre = &a; o.out_dt = F32;
+    Tensor qkv = conv(x, p + ".qkv", o);
+    afree(a);
+    const int L = x.h * x.w, C = x.c;
+    Tensor O = mha(qkv.f(), 3 * C, (long long)L * 3 * C, qkv.f() + C, 3 * C, (long long)L * 3 * C, qkv.f() + 2 * C, 3 * C,
+                   (long long)L * 3 * C, x.n, L, L, 1, C, 1.0f / sqrtf((float)C));
+    tfree(qkv);
+    O.h = x.h; O.w = x.w;
+    ConvOpt po;
+    po.res = &x;
+    Tensor out = conv(O, p + ".proj_out", po);
+    tfree(O);
+    return out;
+}
+
+// Encoder programme (vqgan_arch.py:246-292) for nf 64, ch_mult [1,2,2,4,4,8], 2 res blocks, attention at 16
+static const char* kEncProg[25] = {"conv", "res", "res", "down", "res", "res", "down", "res", "res", "down", "res", "res", "down",
+                                   "res", "res", "down", "res", "attn", "res", "attn", "res", "attn", "res", "norm", "conv"};
+static const char* kGenProg[25] = {"conv", "res", "attn", "res", "res", "attn", "res", "attn", "up", "res", "res", "up", "res",
+                                   "res", "up", "res", "res", "up", "res", "res", "up", "res", "res", "norm", "conv"};
+
+Tensor Engine::encoder(const Tensor& img, const std::string& p, const std::function<void(int, const Tensor&)>& tap) {
+    Tensor x = img;
+    bool own = false;
+    Aff pend;  // pending GroupNorm (norm_out) to fuse into the last conv
+    for (int i = 0; i < 25; ++i) {
+        const std::string bp = p + ".blocks." + std::to_string(i);
+        const std::string kind = kEncProg[i];
+        Tensor y;
+        if (kind == "conv") {
+            ConvOpt o;
+            o.pad(1);
+            if (i == 24) { o.pre = &pend; o.out_dt = F32; }
+            y = conv(x, bp, o);
+            if (i == 24) afree(pend);
+        } else if (kind == "res") {
+            y = res_block(x, bp);
+        } else if (kind == "attn") {
+            y = attn_block(x, bp);
+        } else if (kind == "down") {  // vqgan_arch.py:135-139
+            ConvOpt o;
+            o.stride = 2; o.pad_b = 1; o.pad_r = 1;
+            y = conv(x, bp + ".conv", o);
+        } else {  // norm_out: statistics only; apply is fused into the next conv
+            pend = gn(x, bp);
+            if (tap) tap(i, x);
+            continue;
+        }
+        if (own) tfree(x);
+        x = y;
+        own = true;
+        if (tap) tap(i, x);
+    }
+    return x;
+}
+
+// =============================================================================================
+// GMFlow (gmflow/*.py; 1 scale, swin splits 2, global correlation + global propagation)
+// =============================================================================================
+// gmflow/backbone.py:8-36.  x_aff != null: x is a raw conv output with a pending InstanceNorm+ReLU.
+void Engine::gm_resblock(Tensor& x, Aff* x_aff, const std::string& p, int stride) {
+    ConvOpt o1;
+    o1.pad(1); o1.stride = stride; o1.pre = x_aff; o1.pre_act = x_aff ? ACT_RELU : ACT_NONE; o1.out_dt = F32;
+    Tensor y1 = conv(x, p + ".conv1", o1);
+    Aff a1 = inorm(y1);
+    ConvOpt o2;
+    o2.pad(1); o2.pre = &a1; o2.pre_act = ACT_RELU; o2.out_dt = F32;
+    Tensor y2 = conv(y1, p + ".conv2", o2);
+    afree(a1);
+    tfree(y1);
+    Aff a2 = inorm(y2);
+    Tensor out = talloc(y2.n, y2.h, y2.w, y2.c, F32);
+    EwArgs e;
+    Tensor d;
+    Aff a3;
+    const bool ds = has(p + ".downsample.0.weight");
+    if (ds) {
+        ConvOpt od;
+        od.stride = stride; od.pre = x_aff; od.pre_act = x_aff ? ACT_RELU : ACT_NONE; od.out_dt = F32;
+        d = conv(x, p + ".downsample.0", od);
+        a3 = inorm(d);
+        e.A = d.p; e.a_dt = d.dt; e.sa = a3.scale; e.ba = a3.shift; e.act_a = ACT_NONE;
+    } else {
+        e.A = x.p; e.a_dt = x.dt;
+        if (x_aff) { e.sa = x_aff->scale; e.ba = x_aff->shift; e.act_a = ACT_RELU; }
+    }
+    e.B = y2.p; e.b_dt = y2.dt; e.sb = a2.scale; e.bb = a2.shift; e.act_b = ACT_RELU;
+    e.act_o = ACT_RELU;
+    e.out = out.p; e.o_dt = out.dt; e.n = out.n; e.hw = out.h * out.w; e.c = out.c;
+    if (!arena_.dry()) { elementwise(e, s_); launches_ += 1; }
+    if (ds) { afree(a3); tfree(d); }
+    afree(a2);
+    tfree(y2);
+    tfree(x);
+    x = out;
+}
+
+// gmflow/transformer.py:147-185 on tokens (nimg, 4096, 128); windows 2x2, optional half-window shift
+void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int nimg, bool shift, bool ffn) {
+    const int C = 128, H = 64, Wd = 64, k = 2, L = 1024;
+    Tensor q = linear(src, p + ".q_proj"), kk = linear(tgt, p + ".k_proj"), v = linear(tgt, p + ".v_proj");
+    Tensor qw = talloc(nimg * 4, L, 1, C, F32), kw = talloc(nimg * 4, L, 1, C, F32), vw = talloc(nimg * 4, L, 1, C, F32);
+    const int sh = shift ? 16 : 0;
+    if (!arena_.dry()) {
+        window_partition(q.f(), qw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
+        window_partition(kk.f(), kw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
+        window_partition(v.f(), vw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
+        launches_ += 3;
+    }
+    tfree(q); tfree(kk); tfree(v);
+    Tensor S = talloc(nimg * 4, L, 1, L, F32);
+    Tensor Ow = talloc(nimg * 4, L, 1, C, F32);
+    if (!arena_.dry()) {
+        BGemmArgs g;
+        g.A = qw.f(); g.B = kw.f(); g.C = S.f();
+        g.M = L; g.N = L; g.K = C; g.lda = C; g.ldb = C; g.ldc = L; g.transB = 1; g.alpha = 1.0f / sqrtf((float)C);
+        g.nz0 = nimg * 4;
+        g.sA[0] = (long long)L * C; g.sB[0] = (long long)L * C; g.sC[0] = (long long)L * L;
+        bgemm_simt(g, s_);
+        softmax_rows(S.f(), (long long)nimg * 4 * L, L, shift ? region_ : nullptr, 4, L, s_);
+        BGemmArgs h;
+        h.A = S.f(); h.B = vw.f(); h.C = Ow.f();
+        h.M = L; h.N = C; h.K = L; h.lda = L; h.ldb = C; h.ldc = C; h.transB = 0;
+        h.nz0 = nimg * 4;
+        h.sA[0] = (long long)L * L; h.sB[0] = (long long)L * C; h.sC[0] = (long long)L * C;
+        bgemm_simt(h, s_);
+        launches_ += 3;
+    }
+    tfree(S); tfree(qw); tfree(kw); tfree(vw);
+    Tensor O = talloc(nimg, H * Wd, 1, C, F32);
+    if (!arena_.dry()) { window_merge(Ow.f(), O.f(), nimg, H, Wd, C, k, sh, sh, s_); launches_ += 1; }
+    tfree(Ow);
+    Tensor m = linear(O, p + ".merge");
+    tfree(O);
+    Tensor out;
+    if (!ffn) {
+        out = ln(m, p + ".norm1", &src);
+        tfree(m);
+    } else {
+        Tensor m1 = ln(m, p + ".norm1");
+        tfree(m);
+        ConvOpt o;
+        o.in1 = &m1; o.act = ACT_GELU; o.out_dt = F32;   // mlp.0 on cat([source, message]) without materialising the concat
+        Tensor h = conv(src, convw(p + ".mlp.0"), o);
+        tfree(m1);
+        Tensor m2 = linear(h, p + ".mlp.2");
+        tfree(h);
+        out = ln(m2, p + ".norm2", &src);
+        tfree(m2);
+    }
+    tfree(src);
+    src = out;
+}
+
+// x_nchw: (T,3,512,512) fp32 in [-1,1]; flows: (T-1,512,512,2), pair i = flow(frame i+1 -> frame i)  (keep_arch.py:976-986)
+void Engine::gmflow(const float* x_nchw, int T, float* flows) {
+    const std::string P = "flownet.model";
+    const int HW = 512 * 512;
+    const int chunk = 4;
+    for (int p0 = 0; p0 < T - 1; p0 += chunk) {
+        const int np = std::min(chunk, T - 1 - p0);
+        // images: [img0 = frames p0+1 .. p0+np | img1 = frames p0 .. p0+np-1], ImageNet-normalised NHWC
+        Tensor img = talloc(2 * np, 512, 512, 3, F32);
+        if (!arena_.dry()) {
+            nchw_to_nhwc(x_nchw + (size_t)(p0 + 1) * 3 * HW, img.p, F32, np, 3, 512, 512, 1, s_);
+            nchw_to_nhwc(x_nchw + (size_t)p0 * 3 * HW, (float*)img.p + (size_t)np * HW * 3, F32, np, 3, 512, 512, 1, s_);
+            launches_ += 2;
+        }
+        // backbone (gmflow/backbone.py:101-117)
+        ConvOpt o;
+        o.stride = 2; o.pad(3); o.out_dt = F32;
+        Tensor x = conv(img, P + ".backbone.conv1", o);
+        tfree(img);
+        Aff a = inorm(x);
+        gm_resblock(x, &a, P + ".backbone.layer1.0", 1);
+        afree(a);
+        gm_resblock(x, nullptr, P + ".backbone.layer1.1", 1);
+        gm_resblock(x, nullptr, P + ".backbone.layer2.0", 2);
+        gm_resblock(x, nullptr, P + ".backbone.layer2.1", 1);
+        gm_resblock(x, nullptr, P + ".backbone.layer3.0", 2);
+        gm_resblock(x, nullptr, P + ".backbone.layer3.1", 1);
+        ConvOpt oc;
+        oc.out_dt = F32;
+        Tensor feat = conv(x, P + ".backbone.conv2", oc);   // (2np, 64, 64, 128)
+        tfree(x);
+        if (!arena_.dry()) { add_window_sine_pos(feat.f(), 2 * np, 64, 64, 128, 2, s_); launches_ += 1; }
+        // transformer (gmflow/transformer.py:273-322): c0 = [f0; f1], c1 = [f1; f0]
+        Tensor c0 = feat;
+        c0.h = 4096; c0.w = 1;
+        Tensor c1 = talloc(2 * np, 4096, 1, 128, F32);
+        const size_t half = (size_t)np * 4096 * 128;
+        auto swap_into_c1 = [&]() {
+            if (arena_.dry()) return;
+            CUDA_CHECK(cudaMemcpyAsync(c1.f(), c0.f() + half, half * sizeof(float), cudaMemcpyDeviceToDevice, s_));
+            CUDA_CHECK(cudaMemcpyAsync(c1.f() + half, c0.f(), half * sizeof(float), cudaMemcpyDeviceToDevice, s_));
+        };
+        swap_into_c1();
+        for (int l = 0; l < 6; ++l) {
+            const std::string lp = P + ".transformer.layers." + std::to_string(l);
+            const bool shift = (l % 2) == 1;
+            gm_layer(c0, c0, lp + ".self_attn", 2 * np, shift, false);
+            gm_layer(c0, c1, lp + ".cross_attn_ffn", 2 * np, shift, true);
+            swap_into_c1();
+        }
+        tfree(c1);
+        Tensor f0 = c0;  // view: first np images
+        f0.n = np;
+        const float* f1 = c0.f() + half;
+        // global correlation softmax (gmflow/matching.py:7-36)
+        Tensor S = talloc(np, 4096, 1, 4096, F32);
+        Tensor flow = talloc(np, 64, 64, 2, F32);
+        if (!arena_.dry()) {
+            BGemmArgs g;
+            g.A = f0.f(); g.B = f1; g.C = S.f();
+            g.M = 4096; g.N = 4096; g.K = 128; g.lda = 128; g.ldb = 128; g.ldc = 4096; g.transB = 1;
+            g.alpha = 1.0f / sqrtf(128.0f);
+            g.nz0 = np;
+            g.sA[0] = 4096LL * 128; g.sB[0] = 4096LL * 128; g.sC[0] = 4096LL * 4096;
+            bgemm_simt(g, s_);
+            softmax_expect2(S.f(), (long long)np * 4096, 4096, 4096, grid64_, 0, grid64_, flow.f(), s_);
+            launches_ += 2;
+        }
+        // flow propagation (gmflow/transformer.py:343-374): q = q_proj(f0), k = k_proj(q)
+        Tensor q = linear(f0, P + ".feature_flow_attn.q_proj");
+        Tensor kq = linear(q, P + ".feature_flow_attn.k_proj");
+        Tensor flow2 = talloc(np, 64, 64, 2, F32);
+        if (!arena_.dry()) {
+            BGemmArgs g;
+            g.A = q.f(); g.B = kq.f(); g.C = S.f();
+            g.M = 4096; g.N = 4096; g.K = 128; g.lda = 128; g.ldb = 128; g.ldc = 4096; g.transB = 1;
+            g.alpha = 1.0f / sqrtf(128.0f);
+            g.nz0 = np;
+            g.sA[0] = 4096LL * 128; g.sB[0] = 4096LL * 128; g.sC[0] = 4096LL * 4096;
+            bgemm_simt(g, s_);
+            softmax_expect2(S.f(), (long long)np * 4096, 4096, 4096, flow.f(), 4096LL * 2, nullptr, flow2.f(), s_);
+            launches_ += 2;
+        }
+        tfree(S); tfree(q); tfree(kq); tfree(flow);
+        // convex x8 upsampling (gmflow/gmflow.py:74-88): conv3x3 on cat(flow, feature0) -> ReLU -> 1x1 -> 576 logits
+        Tensor f0m = f0;
+        f0m.h = 64; f0m.w = 64;
+        ConvOpt ou;
+        ou.pad(1); ou.in1 = &f0m; ou.act = ACT_RELU; ou.out_dt = F32;
+        Tensor u = conv(flow2, convw(P + ".upsampler.0"), ou);
+        ConvOpt om;
+        om.out_dt = F32;
+        Tensor mask = conv(u, P + ".upsampler.2", om);
+        tfree(u);
+        if (!arena_.dry()) {
+            convex_upsample8(mask.f(), flow2.f(), flows + (size_t)p0 * HW * 2, np, 64, 64, s_);
+            launches_ += 1;
+        }
+        tfree(mask); tfree(flow2); tfree(c0);
+    }
+}
+
+// =============================================================================================
+// Kalman gain estimator (keep_arch.py:801-821, BasicTransformerBlock :640-682)
+// =============================================================================================
+Tensor Engine::kalman_gains(const Tensor& z_codes, int T) {
+    const int L = 256, C = 256, heads = 8, dh = 48, inner = heads * dh;
+    const float scale = 1.0f / sqrtf((float)dh);
+    Tensor h = talloc(1, T * L, 1, C, F32);
+    if (!arena_.dry()) CUDA_CHECK(cudaMemcpyAsync(h.p, z_codes.p, h.bytes(), cudaMemcpyDeviceToDevice, s_));
+    for (int blk = 0; blk < 3; ++blk) {
+        const std::string p = "kalman_filter.uncertainty_estimator." + std::to_string(blk);
+        // sparse-causal attention: keys/values = [frame 0 || frame i-1]
+        Tensor hn = ln(h, p + ".norm1");
+        Tensor q = linear(hn, p + ".attn1.to_q"), k = linear(hn, p + ".attn1.to_k"), v = linear(hn, p + ".attn1.to_v");
+        tfree(hn);
+        Tensor k2 = talloc(1, T * 2 * L, 1, inner, F32), v2 = talloc(1, T * 2 * L, 1, inner, F32);
+        if (!arena_.dry()) {
+            sparse_causal_gather(k.f(), k2.f(), 1, T, L, inner, s_);
+            sparse_causal_gather(v.f(), v2.f(), 1, T, L, inner, s_);
+            launches_ += 2;
+        }
+        tfree(k); tfree(v);
+        Tensor o = mha(q.f(), inner, (long long)L * inner, k2.f(), inner, 2LL * L * inner, v2.f(), inner, 2LL * L * inner, T, L,
+                       2 * L, heads, dh, scale);
+        tfree(q); tfree(k2); tfree(v2);
+        Tensor h1 = linear(o, p + ".attn1.to_out.0", ACT_NONE, &h);
+        tfree(o); tfree(h);
+        // GEGLU feed-forward
+        Tensor n3 = ln(h1, p + ".norm3");
+        Tensor pr = linear(n3, p + ".ff.net.0.proj");
+        tfree(n3);
+        Tensor gg = talloc(1, T * L, 1, 4 * C, F32);
+        if (!arena_.dry()) { geglu(pr.f(), gg.f(), T * L, 4 * C, s_); launches_ += 1; }
+        tfree(pr);
+        Tensor h2 = linear(gg, p + ".ff.net.2", ACT_NONE, &h1);
+        tfree(gg); tfree(h1);
+        // temporal attention over frames for every spatial token: batch = token, sequence = frame
+        Tensor nt = ln(h2, p + ".norm_temp");
+        Tensor qt = linear(nt, p + ".attn_temp.to_q"), kt = linear(nt, p + ".attn_temp.to_k"), vt = linear(nt, p + ".attn_temp.to_v");
+        tfree(nt);
+        Tensor St = talloc(L * heads, T, 1, T, F32);
+        Tensor ot = talloc(1, T * L, 1, inner, F32);
+        if (!arena_.dry()) {
+            BGemmArgs g;
+            g.A = qt.f(); g.B = kt.f(); g.C = St.f();
+            g.M = T; g.N = T; g.K = dh; g.lda = L * inner; g.ldb = L * inner; g.ldc = T; g.transB = 1; g.alpha = scale;
+            g.nz0 = L; g.nz1 = heads;
+            g.sA[0] = inner; g.sA[1] = dh; g.sB[0] = inner; g.sB[1] = dh;
+            g.sC[0] = (long long)heads * T * T; g.sC[1] = (long long)T * T;
+            bgemm_simt(g, s_);
+            softmax_rows(St.f(), (long long)L * heads * T, T, nullptr, 1, T, s_);
+            BGemmArgs m;
+            m.A = St.f(); m.B = vt.f(); m.C = ot.f();
+            m.M = T; m.N = dh; m.K = T; m.lda = T; m.ldb = L * inner; m.ldc = L * inner; m.transB = 0;
+            m.nz0 = L; m.nz1 = heads;
+            m.sA[0] = (long long)heads * T * T; m.sA[1] = (long long)T * T;
+            m.sB[0] = inner; m.sB[1] = dh; m.sC[0] = inner; m.sC[1] = dh;
+            bgemm_simt(m, s_);
+            launches_ += 3;
+        }
+        tfree(St); tfree(qt); tfree(kt); tfree(vt);
+        h = linear(ot, p + ".attn_temp.to_out.0", ACT_NONE, &h2);
+        tfree(ot); tfree(h2);
+    }
+    // kalman_gain_calculator: 3 ResBlocks, conv1x1 -> 1, sigmoid (keep_arch.py:766-772)
+    Tensor x = h;
+    x.n = T; x.h = 16; x.w = 16;
+    const int save = adt_;
+    adt_ = F32;
+    for (int i = 0; i < 3; ++i) {
+        Tensor y = res_block(x, "kalman_filter.kalman_gain_calculator." + std::to_string(i));
+        tfree(x);
+        x = y;
+    }
+    ConvOpt o;
+    o.act = ACT_SIGMOID; o.out_dt = F32;
+    Tensor g = conv(x, "kalman_filter.kalman_gain_calculator.3", o);   // (T,16,16,1)
+    adt_ = save;
+    tfree(x);
+    return g;
+}
+
+// =============================================================================================
+// code-prediction transformer (keep_arch.py:1073-1089) -> quantised latent (1,16,16,256)
+// =============================================================================================
+Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
+    const int L = 256, E = 512, heads = 8, dh = 64;
+    Tensor zt = z_hat;
+    zt.n = 1; zt.h = L; zt.w = 1;
+    Tensor t = linear(zt, "feat_emb");
+    const float* pos = warr("position_emb");
+    for (int l = 0; l < 9; ++l) {
+        const std::string p = "ft_layers." + std::to_string(l);
+        Tensor qk_in;
+        Tensor tn = ln(t, p + ".norm1", nullptr, pos, L, &qk_in);
+        Tensor qk = linear(qk_in, p + ".self_attn.in_proj_qk");
+        Tensor v = linear(tn, p + ".self_attn.in_proj_v");
+        tfree(qk_in); tfree(tn);
+        Tensor o = mha(qk.f(), 2 * E, 0, qk.f() + E, 2 * E, 0, v.f(), E, 0, 1, L, L, heads, dh, 1.0f / sqrtf((float)dh));
+        tfree(qk); tfree(v);
+        Tensor t1 = linear(o, p + ".self_attn.out_proj", ACT_NONE, &t);
+        tfree(o); tfree(t);
+        Tensor n2 = ln(t1, p + ".norm2");
+        Tensor hdn = linear(n2, p + ".linear1", ACT_GELU);
+        tfree(n2);
+        t = linear(hdn, p + ".linear2", ACT_NONE, &t1);
+        tfree(hdn); tfree(t1);
+    }
+    Tensor tn = ln(t, "idx_pred_layer.0");
+    tfree(t);
+    Tensor logits = linear(tn, "idx_pred_layer.1");
+    tfree(tn);
+    Tensor quant = talloc(1, 16, 16, 256, adt_);
+    int* idx = (int*)arena_.alloc(L * sizeof(int));
+    if (!arena_.dry()) {
+        const int* forced = nullptr;
+        auto it = forced_.find("codes");
+        if (it != forced_.end() && it->second.p) forced = (const int*)it->second.p + (size_t)frame * L;
+        argmax_gather(logits.f(), L, 1024, warr("quantize.embedding.weight"), 256, forced, idx, quant.p, quant.dt, s_);
+        launches_ += 1;
+        if (capture_) {
+            Cap& cl = cap_["logits"];
+            Cap& cc = cap_["codes"];
+            if (cl.p && (size_t)(frame + 1) * L * 1024 * 4 <= cl.bytes)
+                CUDA_CHECK(cudaMemcpyAsync((float*)cl.p + (size_t)frame * L * 1024, logits.p, (size_t)L * 1024 * 4,
+                                           cudaMemcpyDeviceToDevice, s_));
+            if (cc.p && (size_t)(frame + 1) * L * 4 <= cc.bytes)
+                CUDA_CHECK(cudaMemcpyAsync((int*)cc.p + (size_t)frame * L, idx, (size_t)L * 4, cudaMemcpyDeviceToDevice, s_));
+        }
+    }
+    arena_.free(idx);
+    tfree(logits);
+    return quant;
+}
+
+// Fuse_sft_block.forward (keep_arch.py:465-472)
+Tensor Engine::cft(const Tensor& enc, const Tensor& dec, const std::string& p) {
+    Tensor f = res_block(enc, p + ".encode_enc", &dec);
+    ConvOpt o1;
+    o1.pad(1); o1.act = ACT_LRELU02;
+    ConvOpt o2;
+    o2.pad(1);
+    Tensor s1 = conv(f, p + ".scale.0", o1);
+    Tensor sc = conv(s1, p + ".scale.2", o2);
+    tfree(s1);
+    Tensor t1 = conv(f, p + ".shift.0", o1);
+    Tensor sh = conv(t1, p + ".shift.2", o2);
+    tfree(t1); tfree(f);
+    Tensor out = talloc(dec.n, dec.h, dec.w, dec.c, dec.dt);
+    if (!arena_.dry()) { cft_combine(dec.p, dec.dt, sc.p, sh.p, sc.dt, 1.0f, out.p, out.dt, out.numel(), s_); launches_ += 1; }
+    tfree(sc); tfree(sh);
+    return out;
+}
+
+// CrossFrameFusionLayer.forward, residual=True (keep_arch.py:519-541); 4 heads x 256
+Tensor Engine::cfa(const Tensor& cur, const Tensor& prev, const std::string& p) {
+    KEEP_CHECK(cur.dt == F32 && prev.dt == F32, "cfa expects fp32 feature maps");
+    const int L = cur.h * cur.w, C = cur.c, heads = 4, dh = 256, inner = heads * dh;
+    Tensor x = cur, pv = prev;
+    x.n = 1; x.h = L; x.w = 1;
+    pv.n = 1; pv.h = L; pv.w = 1;
+    Tensor q = linear(x, p + ".attn.to_q"), k = linear(pv, p + ".attn.to_k"), v = linear(pv, p + ".attn.to_v");
+    Tensor o = mha(q.f(), inner, 0, k.f(), inner, 0, v.f(), inner, 0, 1, L, L, heads, dh, 1.0f / sqrtf((float)dh));
+    tfree(q); tfree(k); tfree(v);
+    Tensor y = linear(o, p + ".attn.to_out.0");
+    tfree(o);
+    Tensor x1 = ln(y, p + ".norm1", &x);
+    tfree(y);
+    Tensor pr = linear(x1, p + ".ff.net.0.proj");
+    Tensor gg = talloc(1, L, 1, 4 * C, F32);
+    if (!arena_.dry()) { geglu(pr.f(), gg.f(), L, 4 * C, s_); launches_ += 1; }
+    tfree(pr);
+    Tensor y2 = linear(gg, p + ".ff.net.2");
+    tfree(gg);
+    Tensor x2 = ln(y2, p + ".norm2", &x1);
+    tfree(y2); tfree(x1);
+    x2.n = cur.n; x2.h = cur.h; x2.w = cur.w;
+    return x2;
+}
+
+// Generator programme with CFT / CFA hooks (keep_arch.py:1101-1125)
+Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[3], Tensor cfa_prev[2]) {
+    Tensor x = quant;
+    bool own = false;
+    Aff pend;
+    for (int j = 0; j < 25; ++j) {
+        const std::string bp = "generator.blocks." + std::to_string(j);
+        const std::string kind = kGenProg[j];
+        Tensor y;
+        if (kind == "conv") {
+            ConvOpt o;
+            o.pad(1);
+            if (j == 24) { o.pre = &pend; o.out_dt = F32; }
+            y = conv(x, bp, o);
+            if (j == 24) afree(pend);
+        } else if (kind == "res") {
+            y = res_block(x, bp);
+        } else if (kind == "attn") {
+            y = attn_block(x, bp);
+        } else if (kind == "up") {  // vqgan_arch.py:148-152: nearest x2 fused into the conv's gather
+            ConvOpt o;
+            o.pad(1); o.up = 2;
+            y = conv(x, bp + ".conv", o);
+        } else {
+            pend = gn(x, bp);
+            continue;
+        }
+        if (own) tfree(x);
+        x = y;
+        own = true;
+        const int ti = j == 6 ? 0 : (j == 9 ? 1 : (j == 12 ? 2 : -1));   // sizes 16 / 32 / 64
+        if (ti >= 0) {
+            static const char* sz[3] = {"16", "32", "64"};
+            Tensor enc = taps[ti];   // (T, s, s, C): slice frame
+            enc.n = 1;
+            enc.p = (char*)enc.p + (size_t)frame * enc.h * enc.w * enc.c * dtype_size(enc.dt);
+            Tensor z = cft(enc, x, std::string("cft.") + sz[ti]);
+            tfree(x);
+            x = z;
+            if (ti < 2) {  // CFA at 16 and 32
+                if (frame > 0) {
+                    Tensor z2 = cfa(x, cfa_prev[ti], std::string("cfa.") + sz[ti]);
+                    tfree(x);
+                    x = z2;
+                }
+                if (!arena_.dry())
+                    CUDA_CHECK(cudaMemcpyAsync(cfa_prev[ti].p, x.p, x.bytes(), cudaMemcpyDeviceToDevice, s_));
+            }
+        }
+    }
+    return x;   // (1,512,512,3) fp32
+}
+
+// =============================================================================================
+// full forward for one clip (b = 1)
+// =============================================================================================
+void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtype) {
+    const int HW = 512 * 512;
+    const bool dry = arena_.dry();
+    // ---- persistent per-clip tensors
+    Tensor flows = talloc(T - 1, 512, 512, 2, F32);
+    Tensor taps[3] = {talloc(T, 16, 16, 512, adt_), talloc(T, 32, 32, 256, adt_), talloc(T, 64, 64, 256, adt_)};
+    Tensor z_codes = talloc(T, 16, 16, 256, F32);
+    Tensor cfa_prev[2] = {talloc(1, 16, 16, 512, F32), talloc(1, 32, 32, 256, F32)};
+
+    // ---- optical flow (batched over pairs)
+    auto ff = forced_.find("flows");
+    if (!dry && ff != forced_.end() && ff->second.p) {
+        KEEP_CHECK(ff->second.bytes == flows.bytes(), "forced flows have the wrong size");
+        CUDA_CHECK(cudaMemcpyAsync(flows.p, ff->second.p, flows.bytes(), cudaMemcpyDeviceToDevice, s_));
+    } else {
+        gmflow(x_dev, T, flows.f());
+    }
+    capture("flows", flows.p, flows.bytes());
+
+    // ---- LQ encoder, batched over frames in chunks (keep_arch.py:1034-1037)
+    const int chunk = 4;
+    for (int f0 = 0; f0 < T; f0 += chunk) {
+        const int nf = std::min(chunk, T - f0);
+        Tensor img = talloc(nf, 512, 512, 3, adt_);
+        if (!dry) { nchw_to_nhwc(x_dev + (size_t)f0 * 3 * HW, img.p, img.dt, nf, 3, 512, 512, 0, s_); launches_ += 1; }
+        auto tap = [&](int i, const Tensor& t) {
+            const int ti = i == 18 ? 0 : (i == 14 ? 1 : (i == 11 ? 2 : -1));
+            if (ti < 0 || dry) return;
+            const size_t per = (size_t)t.h * t.w * t.c * dtype_size(t.dt);
+            CUDA_CHECK(cudaMemcpyAsync((char*)taps[ti].p + (size_t)f0 * per, t.p, per * nf, cudaMemcpyDeviceToDevice, s_));
+        };
+        Tensor z = encoder(img, "encoder", tap);
+        if (!dry)
+            CUDA_CHECK(cudaMemcpyAsync(z_codes.f() + (size_t)f0 * 256 * 256, z.p, z.bytes(), cudaMemcpyDeviceToDevice, s_));
+        tfree(z);
+        tfree(img);
+    }
+    capture("z_codes", z_codes.p, z_codes.bytes());
+
+    // ---- Kalman gains (batched over T)
+    Tensor gains = kalman_gains(z_codes, T);
+    capture("gains", gains.p, gains.bytes());
+    if (capture_ && !dry) {
+        for (const char* nm : {"logits", "codes"}) {
+            Cap& c = cap_[nm];
+            const size_t need = std::string(nm) == "logits" ? (size_t)T * 256 * 1024 * 4 : (size_t)T * 256 * 4;
+            if (c.bytes < need) { cudaFree(c.p); CUDA_CHECK(cudaMalloc(&c.p, need)); c.bytes = need; }
+        }
+    }
+
+    // ---- serial per-frame recurrence (keep_arch.py:1062-1128)
+    Tensor prev_out;  // (1,512,512,3) fp32 NHWC
+    auto fp = forced_.find("prev");
+    const bool force_prev = dry || (fp != forced_.end() && fp->second.p);
+    for (int i = 0; i < T; ++i) {
+        Tensor z_hat;
+        bool own_z = false;
+        if (i == 0) {
+            z_hat = z_codes;
+            z_hat.n = 1;
+        } else {
+            Tensor src = prev_out;
+            bool own_src = false;
+            if (force_prev) {
+                src = talloc(1, 512, 512, 3, F32);
+                own_src = true;
+                if (!dry) { nchw_to_nhwc((const float*)fp->second.p + (size_t)(i - 1) * 3 * HW, src.p, F32, 1, 3, 512, 512, 0, s_); launches_ += 1; }
+            }
+            Tensor warped = talloc(1, 512, 512, 3, adt_);
+            if (!dry) {
+                flow_warp(src.p, src.dt, flows.f() + (size_t)(i - 1) * HW * 2, warped.p, warped.dt, 1, 512, 512, 3, s_);
+                launches_ += 1;
+            }
+            if (own_src) tfree(src);
+            Tensor zp = encoder(warped, "hq_encoder", nullptr);
+            tfree(warped);
+            z_hat = talloc(1, 16, 16, 256, F32);
+            own_z = true;
+            if (!dry) {
+                kalman_update(z_codes.f() + (size_t)i * 256 * 256, zp.f(), gains.f() + (size_t)i * 256, z_hat.f(), 256, 256, s_);
+                launches_ += 1;
+            }
+            tfree(zp);
+        }
+        Tensor zh = z_hat;
+        if (i == 0) zh.p = z_codes.p;
+        Tensor quant = code_transformer(zh, i);
+        if (own_z) tfree(z_hat);
+        Tensor img = generator(quant, i, taps, cfa_prev);
+        tfree(quant);
+        if (!dry) {
+            nhwc_to_nchw(img.p, img.dt, (char*)out_dev + (size_t)i * 3 * HW * (out_dtype == KEEP_OUT_F16 ? 2 : 4),
+                         out_dtype == KEEP_OUT_F16 ? F16 : F32, 1, 3, 512, 512, s_);
+            launches_ += 1;
+        }
+        if (prev_out.p) tfree(prev_out);
+        prev_out = img;
+    }
+    if (prev_out.p) tfree(prev_out);
+    tfree(gains);
+    tfree(cfa_prev[0]); tfree(cfa_prev[1]);
+    tfree(z_codes);
+    for (int i = 0; i < 3; ++i) tfree(taps[i]);
+    tfree(flows);
+}
+
+size_t Engine::workspace_bytes(int b, int T) {
+    KEEP_CHECK(b >= 1 && T >= 2 && T <= 100, "keep_workspace_bytes: need b >= 1 and 2 <= T <= 100 (got b=%d T=%d)", b, T);
+    auto it = ws_cache_.find(T);
+    if (it != ws_cache_.end()) return it->second;
+    begin(nullptr, 0, nullptr, true);
+    forward_clip(nullptr, T, nullptr, KEEP_OUT_F32);
+    const size_t need = arena_.peak() + 4096;
+    ws_cache_[T] = need;
+    return need;
+}
+
+void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t s) {
+    KEEP_CHECK(!dry_only_, "keep_forward: engine was created with KEEP_FLAG_PLAN_ONLY (no device)");
+    KEEP_CHECK(x_dev && out_dev, "keep_forward: null tensor");
+    KEEP_CHECK(b >= 1 && T >= 2 && T <= 100, "keep_forward: need b >= 1 and 2 <= T <= 100 (got b=%d T=%d)", b, T);
+    KEEP_CHECK(out_dtype == KEEP_OUT_F32 || out_dtype == KEEP_OUT_F16, "keep_forward: bad out_dtype %d", out_dtype);
+    CUDA_CHECK(cudaSetDevice(device_));
+    const size_t need = workspace_bytes(1, T);
+    if (!ws) {
+        if (own_ws_bytes_ < need) {
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            cudaFree(own_ws_);
+            own_ws_ = nullptr; own_ws_bytes_ = 0;
+            CUDA_CHECK(cudaMalloc(&own_ws_, need));
+            own_ws_bytes_ = need;
+        }
+        ws = own_ws_; ws_bytes = own_ws_bytes_;
+    }
+    KEEP_CHECK(ws_bytes >= need, "keep_forward: workspace too small (%zu < %zu)", ws_bytes, need);
+    KEEP_CHECK(((uintptr_t)ws & 255) == 0, "keep_forward: workspace must be 256-byte aligned");
+    const size_t per_clip = (size_t)T * 3 * 512 * 512;
+    for (int bi = 0; bi < b; ++bi) {   // clips are independent (keep_processor.py:263-270)
+        begin(ws, ws_bytes, s, false);
+        forward_clip(x_dev + bi * per_clip, T, (char*)out_dev + bi * per_clip * (out_dtype == KEEP_OUT_F16 ? 2 : 4), out_dtype);
+    }
+}
+
+// =============================================================================================
+// test hooks
+// =============================================================================================
+void Engine::force(const std::string& what, const void* host, size_t bytes) {
+    CUDA_CHECK(cudaSetDevice(device_));
+    Cap& c = forced_[what];
+    cudaFree(c.p);
+    c.p = nullptr; c.bytes = 0;
+    if (!host || bytes == 0) return;
+    CUDA_CHECK(cudaMalloc(&c.p, bytes));
+    CUDA_CHECK(cudaMemcpy(c.p, host, bytes, cudaMemcpyHostToDevice));
+    c.bytes = bytes;
+}
+
+size_t Engine::read(const std::string& what, void* host, size_t bytes) {
+    CUDA_CHECK(cudaSetDevice(device_));
+    auto it = cap_.find(what);
+    KEEP_CHECK(it != cap_.end() && it->second.p, "no captured tensor '%s' (enable capture and run forward first)", what.c_str());
+    const size_t n = std::min(bytes, it->second.bytes);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(host, it->second.p, n, cudaMemcpyDeviceToHost));
+    return it->second.bytes;
+}
+
+}  // namespace keep

@@ -1,0 +1,117 @@
+// keep_b200 — the KEEP inference engine (host orchestration of the sm_100a kernels).
+#pragma once
+#include <functional>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/keep_b200.h"
+#include "ops.h"
+
+namespace keep {
+
+// first-fit free-list allocator over one contiguous device workspace.  All work is enqueued on a
+// single stream, so a block may be reused as soon as its last consumer has been *enqueued*.
+class Arena {
+   public:
+    void reset(char* base, size_t cap, bool dry);
+    void* alloc(size_t bytes);
+    void free(void* p);
+    size_t peak() const { return peak_; }
+    bool dry() const { return dry_; }
+
+   private:
+    struct Block { size_t off, size; bool used; };
+    std::vector<Block> blocks_;
+    char* base_ = nullptr;
+    size_t cap_ = 0, peak_ = 0;
+    bool dry_ = false;
+};
+
+struct DevArr { float* p = nullptr; long long numel = 0; int d[4] = {0, 0, 0, 0}; };
+struct ConvW { const float* w = nullptr; const float* b = nullptr; int cin = 0, cout = 0, kh = 1, kw = 1; };
+struct Aff { float* scale = nullptr; float* shift = nullptr; };
+
+struct ConvOpt {
+    int stride = 1, pad_t = 0, pad_l = 0, pad_b = 0, pad_r = 0, up = 1;
+    const Aff* pre = nullptr; int pre_act = ACT_NONE;
+    int act = ACT_NONE;
+    const Tensor* res = nullptr;
+    const Tensor* in1 = nullptr;
+    int out_dt = -1;  // -1: engine feature-map dtype
+    ConvOpt& pad(int p) { pad_t = pad_l = pad_b = pad_r = p; return *this; }
+};
+
+class Engine {
+   public:
+    Engine(int device, const keep_weight_desc* w, int n_w, int flags);
+    ~Engine();
+    size_t workspace_bytes(int b, int T);
+    void forward(const float* x_dev, int b, int T, void* out_dev, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t s);
+    // test hooks (stage-wise teacher forcing / intermediate capture)
+    void force(const std::string& what, const void* host, size_t bytes);
+    size_t read(const std::string& what, void* host, size_t bytes);
+    void set_capture(bool on) { capture_ = on; }
+    int device() const { return device_; }
+    long long launches() const { return launches_; }
+
+    // building blocks are public so the op-level C-ABI test hooks can drive them
+    Tensor talloc(int n, int h, int w, int c, int dt);
+    void tfree(Tensor& t);
+    void afree(Aff& a);
+    Tensor conv(const Tensor& x, const ConvW& cw, const ConvOpt& o);
+    Tensor conv(const Tensor& x, const std::string& prefix, const ConvOpt& o) { return conv(x, convw(prefix), o); }
+    Tensor linear(const Tensor& x, const std::string& prefix, int act = ACT_NONE, const Tensor* res = nullptr);
+    Aff gn(const Tensor& x, const std::string& prefix, const Tensor* x2 = nullptr);
+    Aff inorm(const Tensor& x);
+    Tensor ln(const Tensor& x, const std::string& prefix, const Tensor* res = nullptr, const float* add2 = nullptr,
+              int add2_rows = 0, Tensor* out2 = nullptr);
+    Tensor res_block(const Tensor& x, const std::string& p, const Tensor* x2 = nullptr);
+    Tensor attn_block(const Tensor& x, const std::string& p);
+    Tensor encoder(const Tensor& img, const std::string& p, const std::function<void(int, const Tensor&)>& tap);
+    // multi-head attention on (rows, ld) matrices; writes (nb*Lq, heads*dh)
+    Tensor mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv, long long sv,
+               int nb, int Lq, int Lk, int heads, int dh, float scale);
+    ConvW convw(const std::string& prefix) const;
+    const float* warr(const std::string& key) const;
+    bool has(const std::string& key) const { return W_.count(key) != 0; }
+    void begin(void* ws, size_t ws_bytes, cudaStream_t s, bool dry);
+    cudaStream_t stream() const { return s_; }
+    Arena& arena() { return arena_; }
+
+   private:
+    void forward_clip(const float* x_dev, int T, void* out_dev, int out_dtype);
+    void gmflow(const float* x_nchw, int T, float* flows);
+    void gm_resblock(Tensor& x, Aff* x_aff, const std::string& p, int stride);
+    void gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int nimg, bool shift, bool ffn);
+    Tensor kalman_gains(const Tensor& z_codes, int T);
+    Tensor code_transformer(const Tensor& z_hat, int frame);
+    Tensor cft(const Tensor& enc, const Tensor& dec, const std::string& p);
+    Tensor cfa(const Tensor& cur, const Tensor& prev, const std::string& p);
+    Tensor generator(const Tensor& quant, int frame, Tensor taps[3], Tensor cfa_prev[2]);
+    void pack_weights(const keep_weight_desc* w, int n_w);
+    void add_arr(const std::string& key, const std::vector<float>& host, int d0, int d1 = 0, int d2 = 0, int d3 = 0);
+
+    int device_ = 0, flags_ = 0;
+    bool dry_only_ = false;  // KEEP_FLAG_PLAN_ONLY: host-side planning only (workspace sizing, key checks), no device
+    int adt_ = F32;  // feature-map storage dtype
+    std::unordered_map<std::string, DevArr> W_;
+    std::vector<std::pair<std::string, std::vector<float>>> staging_;
+    float* wpool_ = nullptr;
+    int* region_ = nullptr;      // GMFlow shifted-window region ids [4][1024]
+    float* grid64_ = nullptr;    // GMFlow coordinate grid (4096, 2)
+    Arena arena_;
+    cudaStream_t s_ = nullptr;
+    long long launches_ = 0;
+    // engine-owned workspace (used when the caller passes none)
+    void* own_ws_ = nullptr; size_t own_ws_bytes_ = 0;
+    std::unordered_map<int, size_t> ws_cache_;
+    // debug capture / forcing
+    struct Cap { void* p = nullptr; size_t bytes = 0; };
+    std::unordered_map<std::string, Cap> cap_;      // device buffers holding last forward's intermediates
+    std::unordered_map<std::string, Cap> forced_;   // device buffers with forced values
+    bool capture_ = false;
+    void capture(const std::string& name, const void* dev, size_t bytes);
+};
+
+}  // namespace keep

@@ -1,0 +1,462 @@
+// keep_b200 — memory-bound kernels of the KEEP path: elementwise merges, softmax, warp, Kalman
+// update, logits->argmax->codebook gather, GMFlow geometry (windows, sine position, convex x8).
+#include "ops.h"
+
+namespace keep {
+namespace {
+
+__device__ __forceinline__ float4 ld4_any(const void* p, int dt, size_t i) {
+    return dt == F32 ? ld4(reinterpret_cast<const float*>(p), i) : ld4(reinterpret_cast<const __half*>(p), i);
+}
+__device__ __forceinline__ void st4_any(void* p, int dt, size_t i, float4 v) {
+    if (dt == F32) st4(reinterpret_cast<float*>(p), i, v);
+    else st4(reinterpret_cast<__half*>(p), i, v);
+}
+__device__ __forceinline__ float ld1_any(const void* p, int dt, size_t i) {
+    return dt == F32 ? reinterpret_cast<const float*>(p)[i] : __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+__device__ __forceinline__ void st1_any(void* p, int dt, size_t i, float v) {
+    if (dt == F32) reinterpret_cast<float*>(p)[i] = v;
+    else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) elementwise_kernel(const EwArgs a, size_t n4) {
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const size_t i = i4 * 4;
+    const int c = (int)(i % a.c);
+    const size_t nidx = i / ((size_t)a.hw * a.c);
+    float4 va = ld4_any(a.A, a.a_dt, i);
+    float x[4] = {va.x, va.y, va.z, va.w};
+    if (a.sa) {
+        const float4 s = *reinterpret_cast<const float4*>(a.sa + nidx * a.c + c);
+        const float4 b = *reinterpret_cast<const float4*>(a.ba + nidx * a.c + c);
+        x[0] = fmaf(x[0], s.x, b.x); x[1] = fmaf(x[1], s.y, b.y); x[2] = fmaf(x[2], s.z, b.z); x[3] = fmaf(x[3], s.w, b.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = apply_act(x[j], a.act_a);
+    if (a.B) {
+        float4 vb = ld4_any(a.B, a.b_dt, i);
+        float y[4] = {vb.x, vb.y, vb.z, vb.w};
+        if (a.sb) {
+            const float4 s = *reinterpret_cast<const float4*>(a.sb + nidx * a.c + c);
+            const float4 b = *reinterpret_cast<const float4*>(a.bb + nidx * a.c + c);
+            y[0] = fmaf(y[0], s.x, b.x); y[1] = fmaf(y[1], s.y, b.y); y[2] = fmaf(y[2], s.z, b.z); y[3] = fmaf(y[3], s.w, b.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] += apply_act(y[j], a.act_b);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = apply_act(x[j], a.act_o);
+    st4_any(a.out, a.o_dt, i, make_float4(x[0], x[1], x[2], x[3]));
+}
+
+__global__ void __launch_bounds__(256) cft_combine_kernel(const void* dec, int dec_dt, const void* scale, const void* shift,
+                                                          int ss_dt, float cond, void* out, int o_dt, size_t n4) {
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const size_t i = i4 * 4;
+    const float4 d = ld4_any(dec, dec_dt, i), sc = ld4_any(scale, ss_dt, i), sh = ld4_any(shift, ss_dt, i);
+    float4 o;
+    o.x = d.x + cond * (d.x * sc.x + sh.x);
+    o.y = d.y + cond * (d.y * sc.y + sh.y);
+    o.z = d.z + cond * (d.z * sc.z + sh.z);
+    o.w = d.w + cond * (d.w * sc.w + sh.w);
+    st4_any(out, o_dt, i, o);
+}
+
+__global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ in, float* __restrict__ out, size_t total4,
+                                                    int inner) {
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const size_t i = i4 * 4;
+    const size_t row = i / inner;
+    const int col = (int)(i % inner);
+    const float4 h = *reinterpret_cast<const float4*>(in + row * 2 * inner + col);
+    const float4 g = *reinterpret_cast<const float4*>(in + row * 2 * inner + inner + col);
+    float4 o;
+    o.x = h.x * apply_act(g.x, ACT_GELU);
+    o.y = h.y * apply_act(g.y, ACT_GELU);
+    o.z = h.z * apply_act(g.z, ACT_GELU);
+    o.w = h.w * apply_act(g.w, ACT_GELU);
+    *reinterpret_cast<float4*>(out + i) = o;
+}
+
+// one warp per row, L <= 1024
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, long long rows, int L,
+                                                           const int* __restrict__ region, int n_win, int Lq) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* r = s + (size_t)row * L;
+    float v[32];
+    float mx = -INFINITY;
+    const int* reg = nullptr;
+    int myreg = 0;
+    if (region) {
+        const long long batch = row / Lq;
+        reg = region + (size_t)(batch % n_win) * L;   // self-attention windows: Lq == L
+        myreg = reg[row % Lq];
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int k = lane + i * 32;
+        float x = -INFINITY;
+        if (k < L) {
+            x = r[k];
+            if (reg && reg[k] != myreg) x += -100.0f;
+        }
+        v[i] = x;
+        mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int k = lane + i * 32;
+        v[i] = k < L ? expf(v[i] - mx) : 0.0f;
+        sum += v[i];
+    }
+    const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int k = lane + i * 32;
+        if (k < L) r[k] = v[i] * inv;
+    }
+}
+
+// one block (256 threads) per row; V has two columns
+__global__ void __launch_bounds__(256) softmax_expect2_kernel(const float* __restrict__ s, int L, int Lq,
+                                                              const float* __restrict__ v, long long v_bstride,
+                                                              const float* __restrict__ sub, float* __restrict__ out) {
+    __shared__ float red[3][8];
+    const long long row = blockIdx.x;
+    const float* r = s + (size_t)row * L;
+    const float* vv = v + (row / Lq) * v_bstride;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float mx = -INFINITY;
+    for (int k = tid; k < L; k += 256) mx = fmaxf(mx, r[k]);
+    mx = warp_max(mx);
+    if (lane == 0) red[0][wid] = mx;
+    __syncthreads();
+    mx = red[0][0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[0][i]);
+    __syncthreads();
+    float se = 0.0f, sx = 0.0f, sy = 0.0f;
+    for (int k = tid; k < L; k += 256) {
+        const float e = expf(r[k] - mx);
+        const float2 val = *reinterpret_cast<const float2*>(vv + 2 * (size_t)k);
+        se += e;
+        sx = fmaf(e, val.x, sx);
+        sy = fmaf(e, val.y, sy);
+    }
+    se = warp_sum(se); sx = warp_sum(sx); sy = warp_sum(sy);
+    if (lane == 0) { red[0][wid] = se; red[1][wid] = sx; red[2][wid] = sy; }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0, b = 0, c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; c += red[2][i]; }
+        float ox = b / a, oy = c / a;
+        if (sub) { ox -= sub[2 * (row % Lq)]; oy -= sub[2 * (row % Lq) + 1]; }
+        out[2 * row] = ox;
+        out[2 * row + 1] = oy;
+    }
+}
+
+__global__ void __launch_bounds__(256) kalman_update_kernel(const float* __restrict__ z, const float* __restrict__ zp,
+                                                            const float* __restrict__ gain, float* __restrict__ out,
+                                                            size_t total, int c) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float g = gain[i / c];
+    out[i] = (1.0f - g) * z[i] + g * zp[i];   // keep_arch.py:798
+}
+
+// one warp per token; ties resolve to the lowest index
+__global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restrict__ logits, int tokens, int ncodes,
+                                                            const float* __restrict__ codebook, int cdim,
+                                                            const int* __restrict__ forced, int* __restrict__ idx_out,
+                                                            void* quant, int q_dt) {
+    const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tok >= tokens) return;
+    const float* r = logits + (size_t)tok * ncodes;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < ncodes; k += 32) {
+        const float x = r[k];
+        if (x > best) { best = x; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) idx_out[tok] = bi;
+    const int use = forced ? forced[tok] : bi;
+    for (int ch = lane; ch < cdim; ch += 32) st1_any(quant, q_dt, (size_t)tok * cdim + ch, codebook[(size_t)use * cdim + ch]);
+}
+
+__global__ void __launch_bounds__(256) sparse_causal_gather_kernel(const float* __restrict__ kv, float* __restrict__ out,
+                                                                   int T, int L, int c4, size_t total4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int cc = (int)(i % c4);
+    size_t r = i / c4;
+    const int j = (int)(r % (2 * L)); r /= (2 * L);
+    const int f = (int)(r % T);
+    const size_t b = r / T;
+    const int srcf = j < L ? 0 : (f > 0 ? f - 1 : 0);
+    const int tok = j < L ? j : j - L;
+    reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(kv)[((b * T + srcf) * L + tok) * c4 + cc];
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, void* out, int o_dt, int c, int hw,
+                                                           size_t total, int mode) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
+    if (i >= total) return;
+    const size_t n = i / hw, p = i % hw;
+    for (int ch = 0; ch < c; ++ch) {
+        float v = x[(n * c + ch) * hw + p];
+        if (mode == 1) {  // gmflow_arch.py:53-54 then gmflow/utils.py:55-63
+            const float mean = ch == 0 ? 0.485f : (ch == 1 ? 0.456f : 0.406f);
+            const float sd = ch == 0 ? 0.229f : (ch == 1 ? 0.224f : 0.225f);
+            v = (v + 1.0f) / 2.0f * 255.0f;
+            v = (v / 255.0f - mean) / sd;
+        }
+        st1_any(out, o_dt, i * c + ch, v);
+    }
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const void* x, int dt, void* out, int o_dt, int c, int hw,
+                                                           size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
+    if (i >= total) return;
+    const size_t n = i / hw, p = i % hw;
+    for (int ch = 0; ch < c; ++ch) st1_any(out, o_dt, (n * c + ch) * hw + p, ld1_any(x, dt, i * c + ch));
+}
+
+// arch_util.py:113-144 -> F.grid_sample(bilinear, zeros, align_corners=True)
+__global__ void __launch_bounds__(256) flow_warp_kernel(const void* img, int dt, const float* __restrict__ flow, void* out,
+                                                        int o_dt, int h, int w, int c, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*h*w
+    if (i >= total) return;
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const size_t n = i / ((size_t)w * h);
+    const float vx = (float)x + flow[2 * i], vy = (float)y + flow[2 * i + 1];
+    const float wm = (float)max(w - 1, 1), hm = (float)max(h - 1, 1);
+    const float gx = 2.0f * vx / wm - 1.0f, gy = 2.0f * vy / hm - 1.0f;
+    const float ix = ((gx + 1.0f) / 2.0f) * (float)(w - 1), iy = ((gy + 1.0f) / 2.0f) * (float)(h - 1);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy;
+    const float w_nw = wx0 * wy0, w_ne = wx1 * wy0, w_sw = wx0 * wy1, w_se = wx1 * wy1;
+    // guard the float->int conversion against huge flows
+    const bool finite_ok = (ix > -4.0f) && (ix < (float)w + 4.0f) && (iy > -4.0f) && (iy < (float)h + 4.0f);
+    const int x0 = finite_ok ? (int)fx : -8, y0 = finite_ok ? (int)fy : -8;
+    const size_t base = n * (size_t)h * w;
+    for (int ch = 0; ch < c; ++ch) {
+        float acc = 0.0f;
+        if (y0 >= 0 && y0 < h) {
+            if (x0 >= 0 && x0 < w) acc += ld1_any(img, dt, (base + (size_t)y0 * w + x0) * c + ch) * w_nw;
+            if (x0 + 1 >= 0 && x0 + 1 < w) acc += ld1_any(img, dt, (base + (size_t)y0 * w + x0 + 1) * c + ch) * w_ne;
+        }
+        if (y0 + 1 >= 0 && y0 + 1 < h) {
+            if (x0 >= 0 && x0 < w) acc += ld1_any(img, dt, (base + (size_t)(y0 + 1) * w + x0) * c + ch) * w_sw;
+            if (x0 + 1 >= 0 && x0 + 1 < w) acc += ld1_any(img, dt, (base + (size_t)(y0 + 1) * w + x0 + 1) * c + ch) * w_se;
+        }
+        st1_any(out, o_dt, i * c + ch, acc);
+    }
+}
+
+// gmflow/position.py:26-46 on (h/splits, w/splits) windows, tiled over the map (gmflow/utils.py:66-86)
+__global__ void __launch_bounds__(256) add_window_sine_pos_kernel(float* __restrict__ x, int h, int w, int c, int splits,
+                                                                  size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ch = (int)(i % c);
+    const size_t p = i / c;
+    const int xx = (int)(p % w), yy = (int)((p / w) % h);
+    const int wh = h / splits, ww = w / splits;
+    const int half = c / 2;
+    const bool is_y = ch < half;
+    const int k = is_y ? ch : ch - half;
+    const float pos = is_y ? (float)(yy % wh + 1) : (float)(xx % ww + 1);
+    const float den = (is_y ? (float)wh : (float)ww) + 1e-6f;
+    const float e = pos / den * 6.283185307179586f;
+    const float dim_t = powf(10000.0f, (float)(2 * (k / 2)) / (float)half);
+    const float arg = e / dim_t;
+    x[i] += (k & 1) ? cosf(arg) : sinf(arg);
+}
+
+__global__ void __launch_bounds__(256) window_partition_kernel(const float* __restrict__ x, float* __restrict__ out, int h, int w,
+                                                               int c4, int k, int sh, int sw, int ldx4, size_t total4,
+                                                               int merge) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over windowed layout (n*k*k, wh*ww, c4)
+    if (i >= total4) return;
+    const int wh = h / k, ww = w / k;
+    const int cc = (int)(i % c4);
+    size_t r = i / c4;
+    const int t = (int)(r % (wh * ww)); r /= (wh * ww);
+    const int win = (int)(r % (k * k));
+    const size_t n = r / (k * k);
+    const int yy = t / ww, xx = t % ww;
+    const int wy = win / k, wx = win % k;
+    const int y = (wy * wh + yy + sh) % h, xcol = (wx * ww + xx + sw) % w;   // roll by -shift == read at +shift
+    const size_t full = ((n * h + y) * w + xcol);
+    if (!merge) reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(x)[full * ldx4 + cc];
+    else reinterpret_cast<float4*>(out)[full * c4 + cc] = reinterpret_cast<const float4*>(x)[i];
+}
+
+__global__ void __launch_bounds__(256) convex_upsample8_kernel(const float* __restrict__ mask, const float* __restrict__ flow,
+                                                               float* __restrict__ out, int h, int w, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n * 8h * 8w
+    if (i >= total) return;
+    const int W8 = 8 * w, H8 = 8 * h;
+    const int X = (int)(i % W8), Y = (int)((i / W8) % H8);
+    const size_t n = i / ((size_t)W8 * H8);
+    const int x = X >> 3, j = X & 7, y = Y >> 3, ii = Y & 7;
+    const float* m = mask + ((n * h + y) * w + x) * 576 + ii * 8 + j;
+    float lg[9], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { lg[k] = m[k * 64]; mx = fmaxf(mx, lg[k]); }
+    float se = 0.0f, ax = 0.0f, ay = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float e = expf(lg[k] - mx);
+        se += e;
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            const float2 f = *reinterpret_cast<const float2*>(flow + 2 * ((n * h + yy) * w + xx));
+            ax = fmaf(e, 8.0f * f.x, ax);
+            ay = fmaf(e, 8.0f * f.y, ay);
+        }
+    }
+    out[2 * i] = ax / se;
+    out[2 * i + 1] = ay / se;
+}
+
+__global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+                                                      float* __restrict__ out, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ct = ca + cb;
+    const size_t row = i / ct;
+    const int col = (int)(i % ct);
+    out[i] = col < ca ? a[row * ca + col] : b[row * cb + (col - ca)];
+}
+
+static inline unsigned blocks_for(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+void elementwise(const EwArgs& a, cudaStream_t s) {
+    KEEP_CHECK(a.c % 4 == 0, "elementwise: c %% 4 != 0");
+    const size_t n4 = (size_t)a.n * a.hw * a.c / 4;
+    elementwise_kernel<<<blocks_for(n4), 256, 0, s>>>(a, n4);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void cft_combine(const void* dec, int dec_dt, const void* scale, const void* shift, int ss_dt, float cond, void* out, int o_dt,
+                 size_t numel, cudaStream_t s) {
+    KEEP_CHECK(numel % 4 == 0, "cft_combine: numel %% 4 != 0");
+    cft_combine_kernel<<<blocks_for(numel / 4), 256, 0, s>>>(dec, dec_dt, scale, shift, ss_dt, cond, out, o_dt, numel / 4);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void geglu(const float* in, float* out, int rows, int inner, cudaStream_t s) {
+    KEEP_CHECK(inner % 4 == 0, "geglu: inner %% 4 != 0");
+    const size_t t4 = (size_t)rows * inner / 4;
+    geglu_kernel<<<blocks_for(t4), 256, 0, s>>>(in, out, t4, inner);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void softmax_rows(float* sc, long long rows, int L, const int* region, int n_win, int Lq, cudaStream_t s) {
+    KEEP_CHECK(L <= 1024, "softmax_rows: L=%d > 1024", L);
+    KEEP_CHECK(!region || Lq == L, "softmax_rows: region mask needs square windows");
+    softmax_rows_kernel<<<blocks_for((size_t)rows, 8), 256, 0, s>>>(sc, rows, L, region, n_win > 0 ? n_win : 1, Lq > 0 ? Lq : 1);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void softmax_expect2(const float* sc, long long rows, int L, int Lq, const float* v, long long v_bstride, const float* sub,
+                     float* out, cudaStream_t s) {
+    softmax_expect2_kernel<<<(unsigned)rows, 256, 0, s>>>(sc, L, Lq, v, v_bstride, sub, out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void kalman_update(const float* z, const float* zp, const float* gain, float* out, int pixels, int c, cudaStream_t s) {
+    const size_t total = (size_t)pixels * c;
+    kalman_update_kernel<<<blocks_for(total), 256, 0, s>>>(z, zp, gain, out, total, c);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void argmax_gather(const float* logits, int tokens, int ncodes, const float* codebook, int cdim, const int* forced_idx,
+                   int* idx_out, void* quant, int q_dt, cudaStream_t s) {
+    argmax_gather_kernel<<<blocks_for((size_t)tokens, 8), 256, 0, s>>>(logits, tokens, ncodes, codebook, cdim, forced_idx,
+                                                                      idx_out, quant, q_dt);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void sparse_causal_gather(const float* kv, float* out, int b, int T, int L, int c, cudaStream_t s) {
+    KEEP_CHECK(c % 4 == 0, "sparse_causal_gather: c %% 4");
+    const size_t t4 = (size_t)b * T * 2 * L * (c / 4);
+    sparse_causal_gather_kernel<<<blocks_for(t4), 256, 0, s>>>(kv, out, T, L, c / 4, t4);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void nchw_to_nhwc(const float* x, void* out, int o_dt, int n, int c, int h, int w, int mode, cudaStream_t s) {
+    const size_t total = (size_t)n * h * w;
+    nchw_to_nhwc_kernel<<<blocks_for(total), 256, 0, s>>>(x, out, o_dt, c, h * w, total, mode);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s) {
+    const size_t total = (size_t)n * h * w;
+    nhwc_to_nchw_kernel<<<blocks_for(total), 256, 0, s>>>(x, dt, out, out_dt, c, h * w, total);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void flow_warp(const void* img, int dt, const float* flow, void* out, int o_dt, int n, int h, int w, int c, cudaStream_t s) {
+    const size_t total = (size_t)n * h * w;
+    flow_warp_kernel<<<blocks_for(total), 256, 0, s>>>(img, dt, flow, out, o_dt, h, w, c, total);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void add_window_sine_pos(float* x, int n, int h, int w, int c, int splits, cudaStream_t s) {
+    const size_t total = (size_t)n * h * w * c;
+    add_window_sine_pos_kernel<<<blocks_for(total), 256, 0, s>>>(x, h, w, c, splits, total);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void window_partition(const float* x, float* out, int n, int h, int w, int c, int k, int shift_h, int shift_w, int ldx,
+                      cudaStream_t s) {
+    KEEP_CHECK(c % 4 == 0 && ldx % 4 == 0 && h % k == 0 && w % k == 0, "window_partition: bad shape");
+    const size_t t4 = (size_t)n * h * w * (c / 4);
+    window_partition_kernel<<<blocks_for(t4), 256, 0, s>>>(x, out, h, w, c / 4, k, shift_h, shift_w, ldx / 4, t4, 0);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void window_merge(const float* x, float* out, int n, int h, int w, int c, int k, int shift_h, int shift_w, cudaStream_t s) {
+    KEEP_CHECK(c % 4 == 0 && h % k == 0 && w % k == 0, "window_merge: bad shape");
+    const size_t t4 = (size_t)n * h * w * (c / 4);
+    window_partition_kernel<<<blocks_for(t4), 256, 0, s>>>(x, out, h, w, c / 4, k, shift_h, shift_w, c / 4, t4, 1);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void convex_upsample8(const float* mask, const float* flow, float* out, int n, int h, int w, cudaStream_t s) {
+    const size_t total = (size_t)n * 64 * h * w;
+    convex_upsample8_kernel<<<blocks_for(total), 256, 0, s>>>(mask, flow, out, h, w, total);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void concat2(const float* a, int ca, const float* b, int cb, float* out, long long rows, cudaStream_t s) {
+    const size_t total = (size_t)rows * (ca + cb);
+    concat2_kernel<<<blocks_for(total), 256, 0, s>>>(a, ca, b, cb, out, total);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace keep

@@ -1,0 +1,154 @@
+// keep_b200 — GroupNorm / InstanceNorm statistics -> per-(n, channel) affine, and LayerNorm.
+//
+// GroupNorm(32, eps 1e-6) (vqgan_arch.py:16-17) and GMFlow's affine-free InstanceNorm2d (eps 1e-5,
+// gmflow/backbone.py:17-36) are both "statistics over H*W*cpg, then y = x*scale[n][c] + shift[n][c]".
+// Statistics are reduced here (double accumulation, two deterministic stages); the *apply* (and the
+// swish / ReLU that follows) is fused into the consuming convolution's A-operand prologue or into
+// the residual-merge elementwise kernel, so normalised activations never round-trip HBM.
+#include "ops.h"
+
+namespace keep {
+namespace {
+
+constexpr int GN_MAX_CHUNKS = 128;
+
+static inline int gn_num_chunks(int hw) {
+    int s = cdiv(hw, 512);
+    return s < 1 ? 1 : (s > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : s);
+}
+
+// partial[n][chunk][c][2] doubles
+template <typename T>
+__global__ void gn_partial_kernel(const T* __restrict__ x, int hw, int c, int nchunks, double* __restrict__ partial) {
+    extern __shared__ double sm[];  // [lanes][c][2]
+    const int c4 = c >> 2;
+    const int lanes = blockDim.x / c4;
+    const int cv = threadIdx.x % c4, lane = threadIdx.x / c4;
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int per = (hw + nchunks - 1) / nchunks;
+    const int p0 = chunk * per, p1 = min(hw, p0 + per);
+    double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    const T* base = x + (size_t)n * hw * c;
+    for (int p = p0 + lane; p < p1; p += lanes) {
+        const float4 v = ld4(base, (size_t)p * c + cv * 4);
+        s[0] += v.x; q[0] += (double)v.x * v.x;
+        s[1] += v.y; q[1] += (double)v.y * v.y;
+        s[2] += v.z; q[2] += (double)v.z * v.z;
+        s[3] += v.w; q[3] += (double)v.w * v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sm[((size_t)lane * c + cv * 4 + j) * 2 + 0] = s[j];
+        sm[((size_t)lane * c + cv * 4 + j) * 2 + 1] = q[j];
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        double ss = 0, qq = 0;
+        for (int l = 0; l < lanes; ++l) {
+            ss += sm[((size_t)l * c + ch) * 2 + 0];
+            qq += sm[((size_t)l * c + ch) * 2 + 1];
+        }
+        double* o = partial + (((size_t)n * nchunks + chunk) * c + ch) * 2;
+        o[0] = ss;
+        o[1] = qq;
+    }
+}
+
+// one warp per (n, group)
+__global__ void gn_finalize_kernel(const double* __restrict__ partial, int n, int hw, int c, int cpg, int nchunks, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ scale, float* __restrict__ shift, int c_total, int c_off) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int groups = c / cpg;
+    if (warp >= n * groups) return;
+    const int in = warp / groups, g = warp % groups;
+    double s = 0, q = 0;
+    const int total = nchunks * cpg;
+    for (int i = lane; i < total; i += 32) {
+        const int chunk = i / cpg, ch = g * cpg + i % cpg;
+        const double* o = partial + (((size_t)in * nchunks + chunk) * c + ch) * 2;
+        s += o[0];
+        q += o[1];
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    const double cnt = (double)hw * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    for (int i = lane; i < cpg; i += 32) {
+        const int ch = g * cpg + i;
+        const float ga = gamma ? gamma[c_off + ch] : 1.0f;
+        const float be = beta ? beta[c_off + ch] : 0.0f;
+        const float sc = ga * rstd;
+        scale[(size_t)in * c_total + c_off + ch] = sc;
+        shift[(size_t)in * c_total + c_off + ch] = be - (float)mean * sc;
+    }
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int rows, int c, const float* __restrict__ g,
+                                                        const float* __restrict__ b, float eps, const float* __restrict__ res,
+                                                        float* __restrict__ out, const float* __restrict__ add2, int add2_rows,
+                                                        float* __restrict__ out2) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * c;
+    float v[32];  // c <= 1024
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int ch = lane + i * 32;
+        v[i] = ch < c ? xr[ch] : 0.0f;
+        s += v[i];
+    }
+    const float mean = warp_sum(s) / (float)c;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int ch = lane + i * 32;
+        const float d = ch < c ? v[i] - mean : 0.0f;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)c + eps);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int ch = lane + i * 32;
+        if (ch < c) {
+            float y = (v[i] - mean) * rstd * g[ch] + b[ch];
+            if (res) y += res[(size_t)row * c + ch];
+            out[(size_t)row * c + ch] = y;
+            if (out2) out2[(size_t)row * c + ch] = y + add2[(size_t)(row % add2_rows) * c + ch];
+        }
+    }
+}
+}  // namespace
+
+size_t gn_scratch_doubles(int n, int hw, int c) { return (size_t)n * gn_num_chunks(hw) * c * 2; }
+
+void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, float eps, const float* gamma, const float* beta,
+                      float* scale, float* shift, int c_total, int c_off, double* scratch, cudaStream_t s) {
+    KEEP_CHECK(c % 4 == 0 && c / 4 <= 256 && c % cpg == 0, "groupnorm: unsupported channels %d (cpg %d)", c, cpg);
+    const int nchunks = gn_num_chunks(hw);
+    const int c4 = c / 4;
+    const int lanes = 256 / c4 > 0 ? 256 / c4 : 1;
+    const int threads = lanes * c4;
+    const size_t smem = (size_t)lanes * c * 2 * sizeof(double);
+    dim3 grid(nchunks, n);
+    if (dt == F32) gn_partial_kernel<float><<<grid, threads, smem, s>>>((const float*)x, hw, c, nchunks, scratch);
+    else gn_partial_kernel<__half><<<grid, threads, smem, s>>>((const __half*)x, hw, c, nchunks, scratch);
+    CUDA_CHECK(cudaGetLastError());
+    const int warps = n * (c / cpg);
+    gn_finalize_kernel<<<cdiv(warps, 8), 256, 0, s>>>(scratch, n, hw, c, cpg, nchunks, eps, gamma, beta, scale, shift, c_total,
+                                                      c_off);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void layernorm(const float* x, int rows, int c, const float* g, const float* b, float eps, const float* res, float* out,
+               const float* add2, int add2_rows, float* out2, cudaStream_t s) {
+    KEEP_CHECK(c <= 1024, "layernorm: c=%d > 1024", c);
+    layernorm_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, rows, c, g, b, eps, res, out, add2, add2_rows > 0 ? add2_rows : 1, out2);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace keep

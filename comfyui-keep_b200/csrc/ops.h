@@ -1,0 +1,115 @@
+// keep_b200 — host-side launchers for the hand-written kernels (all on one stream).
+#pragma once
+#include "common.h"
+
+namespace keep {
+
+// ------------------------------------------------------------------------------------------
+// convolution / linear as implicit GEMM over NHWC:  M = n*ho*wo pixels, N = cout, K = kh*kw*cin
+// ------------------------------------------------------------------------------------------
+struct ConvArgs {
+    // input: up to two NHWC sources concatenated along channels (torch.cat([enc, dec], 1) of the
+    // CFT block, keep_arch.py:467, is never materialised)
+    const void* in0 = nullptr; int in0_dt = F32; int c0 = 0;
+    const void* in1 = nullptr; int in1_dt = F32; int c1 = 0;
+    int n = 0, h = 0, w = 0;     // physical input size
+    int up = 1;                  // nearest-neighbour upsample factor applied on the fly (vqgan_arch.py:149)
+    // prologue: per-(n, channel) affine (GroupNorm / InstanceNorm apply) then activation
+    const float* pre_scale = nullptr; const float* pre_shift = nullptr; int pre_act = ACT_NONE;
+    // weights packed [kh*kw*cin][cout] fp32 (k = (ky*kw + kx)*cin + ci), bias [cout] or null
+    const float* wt = nullptr; const float* bias = nullptr;
+    int kh = 1, kw = 1, stride = 1, pad_t = 0, pad_l = 0, cout = 0;
+    int ho = 0, wo = 0;
+    // epilogue: v = act(acc + bias) ; v += res
+    int act = ACT_NONE;
+    const void* res = nullptr; int res_dt = F32;
+    void* out = nullptr; int out_dt = F32;
+    // split-K (deterministic: partials to workspace, fixed-order reduce)
+    int splitk = 1; float* partial = nullptr;
+};
+void conv2d_simt(const ConvArgs& a, cudaStream_t s);
+// picks split-K for small-M layers; `scratch` must hold conv_splitk_scratch_floats(a) floats when splitk>1
+int conv_pick_splitk(const ConvArgs& a);
+
+// ------------------------------------------------------------------------------------------
+// batched strided GEMM (fp32), used for attention scores / PV
+//   C[z][m][n] = alpha * sum_k A[z][m][k] * (transB ? B[z][n][k] : B[z][k][n])  (+ C if accumulate)
+//   z = (z0, z1, z2) with per-operand strides (elements)
+// ------------------------------------------------------------------------------------------
+struct BGemmArgs {
+    const float* A = nullptr; const float* B = nullptr; float* C = nullptr;
+    int M = 0, N = 0, K = 0;
+    int lda = 0, ldb = 0, ldc = 0;
+    int transB = 1;
+    float alpha = 1.0f; int accumulate = 0;
+    int nz0 = 1, nz1 = 1, nz2 = 1;
+    long long sA[3] = {0, 0, 0}, sB[3] = {0, 0, 0}, sC[3] = {0, 0, 0};
+};
+void bgemm_simt(const BGemmArgs& a, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------
+// normalisation
+// ------------------------------------------------------------------------------------------
+// per-(n, group) statistics over an NHWC tensor -> per-(n, channel) affine  y = x*scale + shift
+//   groups of `cpg` consecutive channels; gamma/beta may be null (InstanceNorm, affine-free)
+//   writes scale/shift at [n][c_total] + c_off  (c_total >= c, for concatenated inputs)
+//   scratch: gn_scratch_doubles(...) doubles
+size_t gn_scratch_doubles(int n, int hw, int c);
+void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, float eps,
+                      const float* gamma, const float* beta, float* scale, float* shift,
+                      int c_total, int c_off, double* scratch, cudaStream_t s);
+// LayerNorm over the last dim of (rows, c) fp32; out = LN(x)*g+b (+ res) ; out2 = out + add2[row % add2_rows]
+void layernorm(const float* x, int rows, int c, const float* g, const float* b, float eps,
+               const float* res, float* out, const float* add2, int add2_rows, float* out2, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------
+// elementwise
+// ------------------------------------------------------------------------------------------
+// out = act_o( act_a(A*sa+ba) + act_b(B*sb+bb) ), per-(n,c) affines optional, B optional
+struct EwArgs {
+    const void* A = nullptr; int a_dt = F32; const float* sa = nullptr; const float* ba = nullptr; int act_a = ACT_NONE;
+    const void* B = nullptr; int b_dt = F32; const float* sb = nullptr; const float* bb = nullptr; int act_b = ACT_NONE;
+    int act_o = ACT_NONE;
+    void* out = nullptr; int o_dt = F32;
+    int n = 0, hw = 0, c = 0;
+};
+void elementwise(const EwArgs& a, cudaStream_t s);
+// CFT combine: out = dec + cond*(dec*scale + shift)          keep_arch.py:470-471
+void cft_combine(const void* dec, int dec_dt, const void* scale, const void* shift, int ss_dt, float cond,
+                 void* out, int o_dt, size_t numel, cudaStream_t s);
+// GEGLU: in (rows, 2*inner) -> out (rows, inner) = in[:, :inner] * gelu(in[:, inner:])
+void geglu(const float* in, float* out, int rows, int inner, cudaStream_t s);
+// softmax over rows of length L (in place), optional swin region mask: add -100 where region[q] != region[k]
+//   rows are organised as (batch, Lq); region ids indexed [(batch % n_win)][token]
+void softmax_rows(float* s, long long rows, int L, const int* region, int n_win, int Lq, cudaStream_t s_);
+// out[row][0:2] = sum_k softmax(s[row])[k] * v[(row / Lq)][k][0:2]   (- sub[row % Lq][0:2] if sub)
+//   v is indexed [(row / Lq) * v_bstride + 2*k]  (v_bstride = 0 shares one value table across batches)
+void softmax_expect2(const float* s, long long rows, int L, int Lq, const float* v, long long v_bstride, const float* sub,
+                     float* out, cudaStream_t s_);
+void kalman_update(const float* z, const float* zp, const float* gain, float* out, int pixels, int c, cudaStream_t s);
+// logits (tokens, ncodes) -> idx (tokens) int32, quant (tokens, cdim) = codebook[idx]; forced idx optional
+void argmax_gather(const float* logits, int tokens, int ncodes, const float* codebook, int cdim,
+                   const int* forced_idx, int* idx_out, void* quant, int q_dt, cudaStream_t s);
+// sparse-causal K/V gather: out[(b,f)][0:L] = kv[(b,0)], out[(b,f)][L:2L] = kv[(b,max(f-1,0))]  keep_arch.py:704-716
+void sparse_causal_gather(const float* kv, float* out, int b, int T, int L, int c, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------
+// layout / geometry
+// ------------------------------------------------------------------------------------------
+// x NCHW fp32 [-1,1] -> NHWC (dt): mode 0 copy ; mode 1 GMFlow normalisation ((x+1)/2 - mean)/std
+void nchw_to_nhwc(const float* x, void* out, int o_dt, int n, int c, int h, int w, int mode, cudaStream_t s);
+void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s);
+// bilinear warp (grid_sample bilinear / zeros / align_corners=True), img NHWC c channels, flow (n,h,w,2) px
+void flow_warp(const void* img, int dt, const float* flow, void* out, int o_dt, int n, int h, int w, int c, cudaStream_t s);
+// GMFlow: add windowed sine position embedding in place on (n, h, w, c) fp32  (utils.py:66-86)
+void add_window_sine_pos(float* x, int n, int h, int w, int c, int splits, cudaStream_t s);
+// GMFlow window partition with optional cyclic shift: (n, h, w, c) -> (n*k*k, h/k*w/k, c) and back
+void window_partition(const float* x, float* out, int n, int h, int w, int c, int k, int shift_h, int shift_w,
+                      int ldx, cudaStream_t s);
+void window_merge(const float* x, float* out, int n, int h, int w, int c, int k, int shift_h, int shift_w, cudaStream_t s);
+// convex x8 upsampling (gmflow.py:74-88): mask (n,h,w,576), flow (n,h,w,2) -> (n,8h,8w,2)
+void convex_upsample8(const float* mask, const float* flow, float* out, int n, int h, int w, cudaStream_t s);
+// concat along channels of two (rows, c) fp32 matrices / generic strided copy
+void concat2(const float* a, int ca, const float* b, int cb, float* out, long long rows, cudaStream_t s);
+
+}  // namespace keep

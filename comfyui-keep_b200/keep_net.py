@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference's KEEP module for the one hot path `keep_net(x, need_upscale=False)`.
+
+Reference interface being mirrored (same names, argument meaning and error behaviour):
+  construction   ARCH_REGISTRY.get('KEEP')(**cfg)            modules/keep_model_loader.py:93-97
+  weights        .load_state_dict(sd, strict=True); .eval()  modules/keep_model_loader.py:120-121
+  residency      .to(device) / .to(offload_device)           modules/keep_model_loader.py:28-48
+  call           keep_net(x, need_upscale=False)             modules/keep_processor.py:174,177,268,270
+                 KEEP.forward                                modules/deps/wm_basicsr/archs/keep_arch.py:1008-1145
+
+Everything inside the call runs in libkeep_b200.so (hand-written sm_100a CUDA) through the C-ABI of
+include/keep_b200.h, bound here with ctypes; torch is used only for device memory and the stream.
+There is NO CPU / PyTorch fallback: without the built library or without a CUDA device this raises.
+"""
+import ctypes
+import json
+import os
+
+import torch
+import torch.nn as nn
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+KEEP_GENERAL_CFG = dict(  # modules/utils.py:42-57 (+ defaults :76-90): the config this engine implements
+    img_size=512, emb_dim=256, dim_embd=512, n_head=8, n_layers=9, codebook_size=1024,
+    cft_list=['16', '32', '64'], kalman_attn_head_dim=48, num_uncertainty_layers=3,
+    cfa_list=['16', '32'], cfa_nhead=4, cfa_dim=256, cond=1, nf=64, ch_mult=[1, 2, 2, 4, 4, 8],
+    attn_resolutions=[16], res_blocks=2, quantizer_type='nearest', latent_size=256, cross_residual=True)
+
+FLAG_FP16_FEATURES = 1
+FLAG_TCGEN05 = 2
+FLAG_PLAN_ONLY = 256
+
+
+def lib_path():
+    return os.path.join(_HERE, "libkeep_b200.so")
+
+
+class _WeightDesc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.POINTER(ctypes.c_float)),
+                ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * 4)]
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen libkeep_b200.so and declare the C-ABI (include/keep_b200.h). Raises if it is not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "keep_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU/PyTorch fallback for the KEEP hot path." % path)
+    lib = ctypes.CDLL(path)
+    vp, ci, cf, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+    lib.keep_last_error.restype = ctypes.c_char_p
+    lib.keep_create.argtypes = [ctypes.POINTER(vp), ci, ctypes.POINTER(_WeightDesc), ci, ci]
+    lib.keep_workspace_bytes.argtypes = [vp, ci, ci]
+    lib.keep_workspace_bytes.restype = cs
+    lib.keep_forward.argtypes = [vp, vp, ci, ci, vp, ci, vp, cs, vp]
+    lib.keep_destroy.argtypes = [vp]
+    lib.keep_launch_count.argtypes = [vp]
+    lib.keep_launch_count.restype = ctypes.c_longlong
+    lib.keep_debug_capture.argtypes = [vp, ci]
+    lib.keep_debug_force.argtypes = [vp, ctypes.c_char_p, vp, cs]
+    lib.keep_debug_read.argtypes = [vp, ctypes.c_char_p, vp, cs]
+    lib.keep_debug_read.restype = ctypes.c_longlong
+    lib.keepop_conv2d.argtypes = [ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp, vp]
+    lib.keepop_groupnorm_affine.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp]
+    lib.keepop_layernorm.argtypes = [vp, ci, ci, vp, vp, cf, vp, vp]
+    lib.keepop_attention.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp]
+    lib.keepop_flow_warp.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.keepop_convex_upsample8.argtypes = [vp, vp, vp, ci, ci, ci, vp]
+    lib.keepop_window_sine_pos.argtypes = [vp, ci, ci, ci, ci, ci, vp]
+    lib.keepop_argmax_gather.argtypes = [vp, ci, ci, vp, ci, vp, vp, vp]
+    _LIB = lib
+    return lib
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise RuntimeError("keep_b200: %s failed: %s" % (what, lib.keep_last_error().decode("utf-8", "replace")))
+
+
+def expected_shapes():
+    with open(os.path.join(_HERE, "keep_state_shapes.json")) as f:
+        return json.load(f)
+
+
+class KeepNetB200(nn.Module):
+    """Drop-in replacement for the reference `KEEP` module on the inference path."""
+
+    def __init__(self, flags=0, **cfg):
+        super().__init__()
+        for k, v in cfg.items():
+            if k in KEEP_GENERAL_CFG and KEEP_GENERAL_CFG[k] != v:
+                raise ValueError("KeepNetB200 implements the 'KEEP' (general) config only: %s=%r != %r"
+                                 % (k, v, KEEP_GENERAL_CFG[k]))
+        self._flags = int(flags)
+        self._shapes = expected_shapes()
+        self._weights = None          # CPU fp32 tensors, reference key names
+        self._engine = None           # keep_handle (c_void_p)
+        self._device = torch.device("cpu")
+        self.training = False
+
+    # ---- state dict (strict, reference key set) ------------------------------------------------
+    def state_dict(self, *args, **kwargs):
+        if self._weights is None:
+            return {k: torch.zeros(s) for k, s in self._shapes.items()}
+        return dict(self._weights)
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        missing = [k for k in self._shapes if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._shapes]
+        if strict and (missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict for KeepNetB200:\n\tMissing key(s): %s\n\tUnexpected key(s): %s"
+                               % (missing[:8], unexpected[:8]))
+        w = {}
+        for k, shp in self._shapes.items():
+            if k not in state_dict:
+                continue
+            t = state_dict[k]
+            if list(t.shape) != list(shp):
+                raise RuntimeError("size mismatch for %s: got %s, expected %s" % (k, list(t.shape), list(shp)))
+            w[k] = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        self._weights = w
+        self._drop_engine()
+        if self._device.type == "cuda":
+            self._make_engine()
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    # ---- residency -----------------------------------------------------------------------------
+    def _drop_engine(self):
+        if self._engine is not None:
+            lib = load_library()
+            lib.keep_destroy(self._engine)
+            self._engine = None
+
+    def _make_engine(self, flags=None):
+        if self._weights is None:
+            raise RuntimeError("KeepNetB200: load_state_dict() before moving to a CUDA device")
+        lib = load_library()
+        flags = self._flags if flags is None else flags
+        names = list(self._weights.keys())
+        descs = (_WeightDesc * len(names))()
+        keep = []
+        for i, k in enumerate(names):
+            t = self._weights[k]
+            nb = k.encode()
+            keep.append(nb)
+            descs[i].name = nb
+            descs[i].data = ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
+            descs[i].ndim = t.dim()
+            for j in range(4):
+                descs[i].shape[j] = t.shape[j] if j < t.dim() else 1
+        h = ctypes.c_void_p()
+        dev = self._device.index if self._device.type == "cuda" and self._device.index is not None else (
+            torch.cuda.current_device() if self._device.type == "cuda" else 0)
+        _check(lib, lib.keep_create(ctypes.byref(h), int(dev), descs, len(names), int(flags)), "keep_create")
+        self._engine = h
+        return h
+
+    def to(self, *args, **kwargs):
+        device = kwargs.get("device", None)
+        for a in args:
+            if isinstance(a, (str, torch.device)):
+                device = a
+            elif isinstance(a, int):
+                device = torch.device("cuda", a)
+        if device is None:
+            return self
+        device = torch.device(device)
+        if device.type == "cuda":
+            if not torch.cuda.is_available():
+                raise RuntimeError("KeepNetB200.to(cuda): no CUDA device (no CPU fallback for the KEEP hot path)")
+            if device.index is None:
+                device = torch.device("cuda", torch.cuda.current_device())
+            if self._engine is None or device != self._device:
+                self._drop_engine()
+                self._device = device
+                if self._weights is not None:
+                    self._make_engine()
+        else:  # offload: free packed device weights + workspace (keep_model_loader.py:45-61)
+            self._drop_engine()
+            self._device = device
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if device is not None else torch.cuda.current_device()))
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise RuntimeError("KeepNetB200 is inference-only")
+        return self
+
+    def __del__(self):
+        try:
+            self._drop_engine()
+        except Exception:
+            pass
+
+    # ---- the hot path --------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, detach_16=True, early_feat=True, need_upscale=True, out_dtype=torch.float32):
+        """x: (b, T>=2, 3, 512, 512) fp32 in [-1, 1] on the engine's device -> (b, T, 3, 512, 512), unclamped."""
+        if self._engine is None:
+            raise RuntimeError("KeepNetB200: no device engine — call .load_state_dict(...) and .to('cuda') first "
+                               "(there is no CPU fallback)")
+        if need_upscale:  # keep_arch.py:1020-1023; never used by the nodes (they pass need_upscale=False)
+            b, t = x.shape[:2]
+            x = torch.nn.functional.interpolate(x.flatten(0, 1), scale_factor=4, mode="bilinear").unflatten(0, (b, t))
+        if x.dim() != 5 or x.shape[2] != 3 or x.shape[3] != 512 or x.shape[4] != 512:
+            raise RuntimeError("KeepNetB200: expected (b, T, 3, 512, 512), got %s" % (tuple(x.shape),))
+        if x.shape[1] < 2:
+            raise RuntimeError("KeepNetB200: T must be >= 2 (the reference duplicates single frames, keep_processor.py:173-175)")
+        if not x.is_cuda or x.device != self._device:
+            raise RuntimeError("KeepNetB200: input on %s but the engine lives on %s" % (x.device, self._device))
+        x = x.to(torch.float32).contiguous()
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        lib = load_library()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            rc = lib.keep_forward(self._engine, x.data_ptr(), int(x.shape[0]), int(x.shape[1]), out.data_ptr(),
+                                  1 if out_dtype == torch.float16 else 0, None, 0, ctypes.c_void_p(stream))
+        _check(lib, rc, "keep_forward")
+        return out
+
+    # ---- test hooks ----------------------------------------------------------------------------
+    def launch_count(self):
+        return int(load_library().keep_launch_count(self._engine)) if self._engine is not None else 0
+
+    def debug_capture(self, on=True):
+        lib = load_library()
+        _check(lib, lib.keep_debug_capture(self._engine, 1 if on else 0), "keep_debug_capture")
+
+    def debug_force(self, what, tensor):
+        lib = load_library()
+        if tensor is None:
+            _check(lib, lib.keep_debug_force(self._engine, what.encode(), None, 0), "keep_debug_force")
+            return
+        t = tensor.detach().cpu().contiguous()
+        _check(lib, lib.keep_debug_force(self._engine, what.encode(), t.data_ptr(), t.numel() * t.element_size()),
+               "keep_debug_force")
+
+    def debug_read(self, what, shape, dtype=torch.float32):
+        lib = load_library()
+        t = torch.empty(shape, dtype=dtype)
+        n = lib.keep_debug_read(self._engine, what.encode(), t.data_ptr(), t.numel() * t.element_size())
+        if n < 0:
+            raise RuntimeError("keep_b200: debug_read(%s): %s" % (what, lib.keep_last_error().decode()))
+        return t
+
+
+def install_into_model_pack(model_pack, flags=0):
+    """Swap `model_pack.keep_net` (reference KEEP module) for the B200 engine, keeping its weights.
+
+    `model_pack` is the reference's KEEPModelPack (modules/keep_model_loader.py:12-61); everything else in
+    the pack (face helper, detector, parser) is left untouched."""
+    ref = model_pack.keep_net
+    net = KeepNetB200(flags=flags)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.eval()
+    model_pack.keep_net = net
+    return net

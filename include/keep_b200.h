@@ -1,0 +1,102 @@
+/* keep_b200 — C-ABI of the Blackwell-native KEEP inference path (libkeep_b200.so).
+ *
+ * One call replaces the reference's `keep_net(clip, need_upscale=False)`:
+ *   caller      modules/keep_processor.py:174,177,268,270   (self.keep_net(...))
+ *   callee      modules/deps/wm_basicsr/archs/keep_arch.py:1008-1145 (KEEP.forward)
+ *   lifecycle   modules/keep_model_loader.py:93-97 (construct), :120-121 (load_state_dict, eval),
+ *               :28-48 (KEEPModelPack.load_device / offload -> .to(device))
+ *
+ * Plain pointers and sizes only; no torch types.  The Python shim (comfyui-keep_b200/keep_net.py)
+ * binds these with ctypes and passes `tensor.data_ptr()` and the current CUDA stream handle.
+ * Every function returns 0 on success or a negative error code and never aborts the process;
+ * `keep_last_error()` returns the thread-local message (the reference's nodes catch exceptions
+ * and return (None,), nodes.py:83-88,131-136).  There is no CPU fallback: without a CUDA device
+ * `keep_create` fails.
+ */
+#ifndef KEEP_B200_H
+#define KEEP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct keep_engine_s* keep_handle;
+
+/* one entry of the reference state dict (after the loader's key renames, keep_model_loader.py:110-118):
+ * `data` is HOST memory, fp32, contiguous, in the reference's own layout (conv OIHW, linear (out,in)). */
+typedef struct {
+    const char* name;
+    const float* data;
+    int32_t ndim;
+    int64_t shape[4];
+} keep_weight_desc;
+
+enum { KEEP_OUT_F32 = 0, KEEP_OUT_F16 = 1 };
+enum {
+    KEEP_FLAG_DEFAULT = 0,
+    KEEP_FLAG_FP16_FEATURES = 1, /* store conv feature maps as fp16 in HBM */
+    KEEP_FLAG_TCGEN05 = 2,       /* run eligible convolutions / GEMMs on the tcgen05 tensor-core kernel */
+    KEEP_FLAG_PLAN_ONLY = 256    /* host-side planning only (strict key check + workspace sizing); keep_forward fails */
+};
+
+/* Build an engine on CUDA device `device` from the 896-tensor KEEP state dict: packs the weights
+ * into kernel layouts and uploads them.  Replaces ARCH_REGISTRY.get('KEEP')(**cfg) +
+ * load_state_dict(strict=True) + .to(device): missing or mis-shaped keys are an error. */
+int keep_create(keep_handle* out, int device, const keep_weight_desc* weights, int n_weights, int flags);
+
+/* Bytes of device workspace `keep_forward` needs for a (b, T) call (activations only; weights are
+ * owned by the engine). */
+size_t keep_workspace_bytes(keep_handle h, int b, int T);
+
+/* The hot path.  x_dev: (b, T, 3, 512, 512) fp32 NCHW in [-1, 1] on the engine's device, not
+ * mutated.  out_dev: (b, T, 3, 512, 512), fp32 or fp16 per `out_dtype`, unclamped — exactly what
+ * KEEP.forward returns in eval mode (keep_arch.py:1138,1145).  T >= 2 (the reference duplicates a
+ * single frame, keep_processor.py:173-175,266-268).  workspace may be NULL (the engine then owns
+ * and grows its own); `stream` is a cudaStream_t (NULL = default stream).  Asynchronous: no host
+ * synchronisation inside. */
+int keep_forward(keep_handle h, const float* x_dev, int b, int T, void* out_dev, int out_dtype, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* Free packed weights and any engine-owned workspace (KEEPModelPack.offload, keep_model_loader.py:45-61). */
+int keep_destroy(keep_handle h);
+
+const char* keep_last_error(void);
+
+/* Number of kernels the engine launched since creation (bench.py `gpu_launches`). */
+long long keep_launch_count(keep_handle h);
+
+/* ---- test hooks (stage-wise teacher forcing and intermediate capture; tests/ only) -------------
+ * what ∈ {"flows" (T-1,512,512,2) f32, "z_codes" (T,16,16,256) f32 NHWC, "gains" (T,256) f32,
+ *         "logits" (T,256,1024) f32, "codes" (T,256) i32, "prev" (T,3,512,512) f32 NCHW (force only)}.
+ * keep_debug_force with bytes == 0 clears the forcing.  Data is host memory. */
+int keep_debug_capture(keep_handle h, int enable);
+int keep_debug_force(keep_handle h, const char* what, const void* host_data, size_t bytes);
+long long keep_debug_read(keep_handle h, const char* what, void* host_data, size_t bytes);
+
+/* ---- op-level entry points (tests/ only): each runs ONE kernel family on device pointers --------
+ * conv: x (n,h,w,cin) NHWC fp32, weight OIHW host fp32, bias host or NULL; pads (t,l,b,r); `up` nearest
+ * factor; pre_scale/pre_shift (n,cin) device or NULL; res (n,ho,wo,cout) device or NULL; out device fp32. */
+int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, const float* weight_host, const float* bias_host,
+                  int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
+                  const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
+                  float* out_dev, void* stream);
+int keepop_groupnorm_affine(const float* x_dev, int n, int hw, int c, int groups, float eps, const float* gamma_dev,
+                            const float* beta_dev, float* scale_dev, float* shift_dev, void* stream);
+int keepop_layernorm(const float* x_dev, int rows, int c, const float* g_dev, const float* b_dev, float eps, float* out_dev,
+                     void* stream);
+/* multi-head attention on packed (nb*L, heads*dh) fp32 matrices */
+int keepop_attention(const float* q_dev, const float* k_dev, const float* v_dev, int nb, int Lq, int Lk, int heads, int dh,
+                     float scale, float* out_dev, void* stream);
+int keepop_flow_warp(const float* img_dev, const float* flow_dev, float* out_dev, int n, int h, int w, int c, void* stream);
+int keepop_convex_upsample8(const float* mask_dev, const float* flow_dev, float* out_dev, int n, int h, int w, void* stream);
+int keepop_window_sine_pos(float* x_dev, int n, int h, int w, int c, int splits, void* stream);
+int keepop_argmax_gather(const float* logits_dev, int tokens, int ncodes, const float* codebook_dev, int cdim, int* idx_dev,
+                         float* quant_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEEP_B200_H */

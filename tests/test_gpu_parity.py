@@ -1,0 +1,144 @@
+"""GPU tier, stage and end-to-end parity of `keep_net(clip)` against the oracle / reference fixtures.
+
+Protocol: the discrete argmax makes free-running parity fragile, so besides the
+free-running comparison every stage is also checked teacher-forced (reference flows / code indices /
+previous outputs fed in), where a single flipped code cannot mask everything else.
+
+Tolerances (fp32 engine mode): north_star's bar is max-abs <= 1e-2 on decoded pixels and PSNR >= 50 dB."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def psnr(a, b):
+    a, b = a.double().clamp(-1, 1), b.double().clamp(-1, 1)
+    mse = float(((a - b) ** 2).mean()) / 4.0
+    return 999.0 if mse == 0 else 10 * np.log10(1.0 / mse)
+
+
+@pytest.fixture(scope="module")
+def net(keep_mod, state_dict):
+    n = keep_mod.KeepNetB200()
+    n.load_state_dict(state_dict, strict=True)
+    n.eval().to("cuda")
+    n.debug_capture(True)
+    yield n
+    n.to("cpu")
+
+
+@pytest.fixture(scope="module")
+def oracle_T2(state_dict):
+    from oracle import keep_oracle, weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = weights.make_clip(2, seed=4321, coherent=True)
+    out, cap = keep_oracle.keep_forward(state_dict, x, capture=True)
+    return x, out, cap
+
+
+def _report(tag, **kw):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.txt"), "a") as f:
+        f.write(tag + " " + " ".join("%s=%s" % (k, v) for k, v in kw.items()) + "\n")
+
+
+def test_free_running_T3_matches_reference_fixture(net):
+    """Engine vs the REAL reference's outputs (fixture written by oracle/make_golden.py)."""
+    from oracle import weights
+    g = np.load(os.path.join(GOLD, "ref_T3_coherent.npz"))
+    x = weights.make_clip(3, seed=1234, coherent=True).cuda()
+    out = net(x, need_upscale=False)
+    torch.cuda.synchronize()
+    assert out.shape == x.shape and out.dtype == torch.float32
+    T = 3
+    flows = net.debug_read("flows", (T - 1, 512, 512, 2)).permute(0, 3, 1, 2)[None]
+    z = net.debug_read("z_codes", (T, 16, 16, 256)).permute(0, 3, 1, 2)
+    gains = net.debug_read("gains", (T, 16, 16))
+    codes = net.debug_read("codes", (T, 256), torch.int32)
+    logits = net.debug_read("logits", (T, 256, 1024))
+    e_flow = float((flows[:, :, :, ::8, ::8] - torch.from_numpy(g["flows_sub8"])).abs().max())
+    e_z = float((z - torch.from_numpy(g["z_codes"])).abs().max())
+    e_g = float((gains - torch.from_numpy(g["gains"]).reshape(T, 16, 16)).abs().max())
+    agree = [(codes[i].numpy() == g["codes"][0, i]).mean() for i in range(T)]
+    top2 = torch.from_numpy(g["logit_top2"])[0]
+    e_logit = float((logits.topk(2, dim=2).values - top2).abs().max())
+    ref_sub = torch.from_numpy(g["out_sub4"])
+    got_sub = out.cpu()[:, :, :, ::4, ::4]
+    e_out = float((got_sub.clamp(-1, 1) - ref_sub.clamp(-1, 1)).abs().max())
+    p = [psnr(got_sub[:, i], ref_sub[:, i]) for i in range(T)]
+    _report("free_T3", flow=e_flow, z=e_z, gain=e_g, logit=e_logit, agree=agree, out=e_out, psnr=p)
+    assert e_flow < 5e-2 and e_z < 2e-3 and e_g < 2e-4 and e_logit < 5e-3
+    assert min(agree) == 1.0, "code indices differ from the reference: %s" % agree
+    assert e_out <= 1e-2 and min(p) >= 50.0
+    crop = out.cpu()[:, :, :, 192:320, 192:320]
+    assert float((crop.clamp(-1, 1) - torch.from_numpy(g["out_crop"]).clamp(-1, 1)).abs().max()) <= 1e-2
+
+
+def test_stagewise_teacher_forced_T2(net, oracle_T2):
+    x, ref_out, cap = oracle_T2
+    T = 2
+    try:
+        net.debug_force("flows", cap["flows"][0].permute(0, 2, 3, 1).contiguous())
+        net.debug_force("codes", cap["codes"][0].to(torch.int32))
+        net.debug_force("prev", ref_out[0])
+        out = net(x.cuda(), need_upscale=False).cpu()
+    finally:
+        for w in ("flows", "codes", "prev"):
+            net.debug_force(w, None)
+    z = net.debug_read("z_codes", (T, 16, 16, 256)).permute(0, 3, 1, 2)
+    gains = net.debug_read("gains", (T, 16, 16))
+    logits = net.debug_read("logits", (T, 256, 1024))
+    e_z = float((z - cap["z_codes"][0]).abs().max())
+    e_g = float((gains - cap["gains"][0, :, 0]).abs().max())
+    e_l = float((logits - cap["logits"][0]).abs().max())
+    e_o = float((out - ref_out).abs().max())
+    _report("forced_T2", z=e_z, gain=e_g, logit=e_l, out=e_o, psnr=psnr(out, ref_out))
+    assert e_z < 2e-3 and e_g < 2e-4 and e_l < 5e-3
+    assert e_o < 5e-3 and psnr(out, ref_out) > 70.0
+
+
+def test_free_running_T2_full_resolution(net, oracle_T2):
+    x, ref_out, cap = oracle_T2
+    out = net(x.cuda(), need_upscale=False).cpu()
+    flows = net.debug_read("flows", (1, 512, 512, 2)).permute(0, 3, 1, 2)
+    codes = net.debug_read("codes", (2, 256), torch.int32)
+    e_f = float((flows - cap["flows"][0]).abs().max())
+    agree = float((codes.long() == cap["codes"][0]).float().mean())
+    e_o = float((out.clamp(-1, 1) - ref_out.clamp(-1, 1)).abs().max())
+    _report("free_T2", flow=e_f, agree=agree, out=e_o, psnr=psnr(out, ref_out))
+    assert e_f < 5e-2
+    assert agree == 1.0
+    assert e_o <= 1e-2 and psnr(out, ref_out) >= 50.0
+
+
+def test_deterministic_and_input_not_mutated(net):
+    from oracle import weights
+    x = weights.make_clip(2, seed=77, coherent=True).cuda()
+    x0 = x.clone()
+    a = net(x, need_upscale=False)
+    b = net(x, need_upscale=False)
+    assert torch.equal(x, x0)
+    assert torch.equal(a, b), "two runs on the same clip must be bitwise identical"
+
+
+def test_batch_of_clips_equals_clip_by_clip(net):
+    from oracle import weights
+    x = torch.cat([weights.make_clip(2, seed=5, coherent=True), weights.make_clip(2, seed=6, coherent=True)], 0).cuda()
+    both = net(x, need_upscale=False)
+    one = net(x[1:2].contiguous(), need_upscale=False)
+    assert torch.equal(both[1:2], one)
+
+
+def test_shape_and_device_errors_raise(net):
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 3, 512, 512, device="cuda"), need_upscale=False)   # T < 2
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 3, 256, 256, device="cuda"), need_upscale=False)   # wrong size
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 3, 512, 512), need_upscale=False)                  # CPU tensor: no fallback
