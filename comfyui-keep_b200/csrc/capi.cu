@@ -81,6 +81,22 @@ int keep_destroy(keep_handle h) {
 
 long long keep_launch_count(keep_handle h) { return h ? h->e->launches() : 0; }
 
+int keep_profile_enable(keep_handle h, int enable) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h, "null handle");
+    h->e->set_profile(enable != 0);
+    return 0;
+    KEEP_API_END
+}
+
+int keep_profile_read(keep_handle h, double* out8) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h && out8, "null argument");
+    h->e->profile_read(out8);
+    return 0;
+    KEEP_API_END
+}
+
 int keep_debug_capture(keep_handle h, int enable) {
     KEEP_API_BEGIN
     KEEP_CHECK(h, "null handle");

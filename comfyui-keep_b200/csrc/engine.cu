@@ -228,6 +228,8 @@ Engine::~Engine() {
     cudaFree(own_ws_);
     for (auto& kv : cap_) cudaFree(kv.second.p);
     for (auto& kv : forced_) cudaFree(kv.second.p);
+    for (auto& p : prof_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto& e : ev_pool_) cudaEventDestroy(e);
 }
 
 // =============================================================================================
@@ -289,8 +291,21 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         a.partial = (float*)part;
     }
     if (!arena_.dry()) {
+        Prof pr;
+        if (profile_) {
+            pr.a = get_event(); pr.b = get_event();
+            pr.flops = 2.0 * (double)out.rows() * cw.cout * cw.kh * cw.kw * cw.cin;
+            pr.bytes = (double)x.bytes() + (o.in1 ? (double)o.in1->bytes() : 0.0) + (double)out.bytes() +
+                       (o.res ? (double)o.res->bytes() : 0.0) + 4.0 * cw.cout * cw.kh * cw.kw * cw.cin;
+            pr.tag = 0;
+            CUDA_CHECK(cudaEventRecord(pr.a, s_));
+        }
         conv2d_simt(a, s_);
         launches_ += a.splitk > 1 ? 2 : 1;
+        if (profile_) {
+            CUDA_CHECK(cudaEventRecord(pr.b, s_));
+            prof_.push_back(pr);
+        }
     }
     if (part) arena_.free(part);
     return out;
@@ -1041,6 +1056,38 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
     for (int bi = 0; bi < b; ++bi) {   // clips are independent (keep_processor.py:263-270)
         begin(ws, ws_bytes, s, false);
         forward_clip(x_dev + bi * per_clip, T, (char*)out_dev + bi * per_clip * (out_dtype == KEEP_OUT_F16 ? 2 : 4), out_dtype);
+    }
+}
+
+// =============================================================================================
+// profiling (bench.py): CUDA events around every conv/GEMM launch on the launching stream
+// =============================================================================================
+cudaEvent_t Engine::get_event() {
+    if (!ev_pool_.empty()) {
+        cudaEvent_t e = ev_pool_.back();
+        ev_pool_.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+}
+
+void Engine::set_profile(bool on) {
+    profile_ = on;
+    for (auto& p : prof_) { ev_pool_.push_back(p.a); ev_pool_.push_back(p.b); }
+    prof_.clear();
+}
+
+// out8: [0] launches, [1] ms, [2] GFLOP, [3] GB (algorithmic) for tag 0 (CUDA-core path); [4..7] same for tag 1 (tcgen05)
+void Engine::profile_read(double* out8) {
+    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto& p : prof_) {
+        float ms = 0.0f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, p.a, p.b));
+        double* o = out8 + (p.tag ? 4 : 0);
+        o[0] += 1.0; o[1] += ms; o[2] += p.flops * 1e-9; o[3] += p.bytes * 1e-9;
     }
 }
 

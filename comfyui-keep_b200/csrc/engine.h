@@ -52,6 +52,9 @@ class Engine {
     void force(const std::string& what, const void* host, size_t bytes);
     size_t read(const std::string& what, void* host, size_t bytes);
     void set_capture(bool on) { capture_ = on; }
+    // per-launch CUDA-event timing of the conv/GEMM kernel family (bench.py roofline)
+    void set_profile(bool on);
+    void profile_read(double* out8);
     int device() const { return device_; }
     long long launches() const { return launches_; }
 
@@ -111,6 +114,11 @@ class Engine {
     std::unordered_map<std::string, Cap> cap_;      // device buffers holding last forward's intermediates
     std::unordered_map<std::string, Cap> forced_;   // device buffers with forced values
     bool capture_ = false;
+    bool profile_ = false;
+    struct Prof { cudaEvent_t a, b; double flops, bytes; int tag; };
+    std::vector<Prof> prof_;
+    std::vector<cudaEvent_t> ev_pool_;
+    cudaEvent_t get_event();
     void capture(const std::string& name, const void* dev, size_t bytes);
 };
 

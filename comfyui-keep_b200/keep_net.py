@@ -63,6 +63,8 @@ def load_library():
     lib.keep_destroy.argtypes = [vp]
     lib.keep_launch_count.argtypes = [vp]
     lib.keep_launch_count.restype = ctypes.c_longlong
+    lib.keep_profile_enable.argtypes = [vp, ci]
+    lib.keep_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.keep_debug_capture.argtypes = [vp, ci]
     lib.keep_debug_force.argtypes = [vp, ctypes.c_char_p, vp, cs]
     lib.keep_debug_read.argtypes = [vp, ctypes.c_char_p, vp, cs]
@@ -237,6 +239,17 @@ class KeepNetB200(nn.Module):
     # ---- test hooks ----------------------------------------------------------------------------
     def launch_count(self):
         return int(load_library().keep_launch_count(self._engine)) if self._engine is not None else 0
+
+    def profile(self, on=True):
+        lib = load_library()
+        _check(lib, lib.keep_profile_enable(self._engine, 1 if on else 0), "keep_profile_enable")
+
+    def profile_read(self):
+        lib = load_library()
+        buf = (ctypes.c_double * 8)()
+        _check(lib, lib.keep_profile_read(self._engine, buf), "keep_profile_read")
+        keys = ("launches", "ms", "gflop", "gbytes")
+        return {"cuda_core": dict(zip(keys, buf[0:4])), "tcgen05": dict(zip(keys, buf[4:8]))}
 
     def debug_capture(self, on=True):
         lib = load_library()

@@ -68,6 +68,12 @@ const char* keep_last_error(void);
 /* Number of kernels the engine launched since creation (bench.py `gpu_launches`). */
 long long keep_launch_count(keep_handle h);
 
+/* Per-launch CUDA-event timing of the conv/GEMM kernel family (bench.py's roofline leg): enable, run
+ * keep_forward, then read out8 = {launches, ms, GFLOP, algorithmic GB} for the CUDA-core path followed by the
+ * same four numbers for the tcgen05 path.  Reading synchronises the device and keeps the samples. */
+int keep_profile_enable(keep_handle h, int enable);
+int keep_profile_read(keep_handle h, double* out8);
+
 /* ---- test hooks (stage-wise teacher forcing and intermediate capture; tests/ only) -------------
  * what ∈ {"flows" (T-1,512,512,2) f32, "z_codes" (T,16,16,256) f32 NHWC, "gains" (T,256) f32,
  *         "logits" (T,256,1024) f32, "codes" (T,256) i32, "prev" (T,3,512,512) f32 NCHW (force only)}.

