@@ -10,6 +10,7 @@
 // apply + activation in the A-operand prologue, bias + activation + residual in the epilogue,
 // deterministic split-K for the small-M (16^2 / 32^2) layers of the serial per-frame chain.
 #include "ops.h"
+#include "tc.h"
 
 namespace keep {
 
@@ -223,6 +224,12 @@ int conv_pick_splitk(const ConvArgs& a) {
     if (s > nchunks / 4) s = nchunks / 4;
     if (s > 32) s = 32;
     return s < 1 ? 1 : (int)s;
+}
+
+void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
+                   int res_dt, void* out, int out_dt, cudaStream_t s) {
+    splitk_reduce_kernel<<<cdiv(MN, 256), 256, 0, s>>>(partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
+    CUDA_CHECK(cudaGetLastError());
 }
 
 void conv2d_simt(const ConvArgs& a, cudaStream_t s) {

@@ -1,4 +1,567 @@
-// placeholder until the tcgen05 kernel lands
+// keep_b200 — tcgen05 implicit-GEMM convolution / linear for sm_100a (NHWC, fp16 operands, fp32 accumulate in TMEM).
+//
+// One persistent, warp-specialised kernel covers every 3x3 stride-1 convolution (optionally with the
+// generator's nearest-x2 upsample and the CFT channel concat folded into the gather) and every 1x1
+// convolution / nn.Linear on the KEEP path whose Cout is a multiple of 16:
+//
+//   warps 0-3   epilogue      tcgen05.ld TMEM -> registers -> {bias, activation, +residual, cast} -> HBM
+//   warp  4     MMA issuer    one thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and tcgen05.commit
+//   warp  5     weight loader one thread streams pre-packed fp16 weight panels with 1-D TMA (cp.async.bulk)
+//   warps 6-13  A producers   coalesced NHWC loads of the (16+2)x(8+2) input halo, GroupNorm/InstanceNorm
+//                             apply + swish/ReLU in registers, fp16 pack, st.shared into the UMMA
+//                             "interleaved" (no-swizzle, K-major) core-matrix layout
+//
+// Implicit GEMM without im2col traffic: the halo tile of 64 input channels is staged ONCE in shared
+// memory; the nine filter taps are nine *shifted views* of it, expressed purely through the UMMA
+// shared-memory descriptor (start address + SBO = one halo row), so each activation byte is read from
+// L2/HBM once per CTA tile instead of nine times.  Accumulators are double-buffered in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  Small-M layers (16^2..64^2 maps of the serial
+// per-frame chain) are split over K (channel blocks) across CTAs with a deterministic fixed-order reduce.
+//
+// Replaces the cuDNN / cuBLAS dispatch behind nn.Conv2d / nn.Linear in vqgan_arch.py:161-181,219-243,
+// 260-286,311-335 and keep_arch.py:78-87,391-393,445-455,929,936-938.
+#include <vector>
+
 #include "ops.h"
-using namespace keep;
-int keepop_conv2d_tc(const ConvArgs& a, cudaStream_t s) { (void)a; (void)s; throw Error("tcgen05 conv not built yet"); }
+#include "tc.h"
+
+namespace keep {
+namespace {
+
+constexpr int kThreads = 448;
+constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 5, kProdWarp0 = 6, kProdThreads = 256;
+constexpr int SA = 3, SB = 4;          // A / B pipeline depth
+constexpr int CB = 64;                 // channels per A stage (4 MMA K-steps of 16)
+constexpr int PLANE3 = 2960;           // bytes per 8-channel plane of a 18x10 halo (2880 padded to 16 mod 128: conflict-free stores)
+constexpr int PLANE1 = 2064;           // bytes per plane of a 128-pixel 1x1 tile (2048 padded likewise)
+constexpr int A_STAGE_BYTES = 8 * PLANE3;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major: core matrix = 8 rows x 16 B (contiguous 128 B);
+// LBO = byte distance between the two K-halves of one K=16 step, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ float fast_act(float v, int act) {
+    switch (act) {
+        case ACT_SWISH: {   // x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU op
+            float t;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+            return 0.5f * v * (1.0f + t);
+        }
+        case ACT_RELU: return fmaxf(v, 0.0f);
+        case ACT_LRELU02: return v > 0.0f ? v : 0.2f * v;
+        default: return apply_act(v, act);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_stage_bytes = a.bn * 128;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + SA * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SB * b_stage_bytes);
+    // barrier map: a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2]
+    const uint32_t bar0 = smem_u32(bars);
+    auto A_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (SA + s); };
+    auto B_FULL = [&](int s) { return bar0 + 8u * (2 * SA + s); };
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 * SA + SB + s); };
+    auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * SA + 2 * SB + s); };
+    auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * SA + 2 * SB + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SA; ++s) { mbar_init(A_FULL(s), kProdThreads); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(ACC_FULL(s), 1); mbar_init(ACC_EMPTY(s), kEpiWarps * 32); }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const bool conv3 = a.taps == 9;
+    const int plane = conv3 ? PLANE3 : PLANE1;
+    const int hw10 = conv3 ? 10 : 8;                 // halo row pitch in pixels
+    const int mt_per_img = a.tiles_y * a.tiles_x;
+    const int m_tiles = a.n * mt_per_img;
+    const long long total = (long long)m_tiles * a.ntile_n * a.splitk;
+    const int cb_per = (a.ncb + a.splitk - 1) / a.splitk;
+
+    // work item w -> (n-tile fastest, then m-tile, then k-split)
+    auto decode = [&](long long w, int& nt, int& img, int& ty, int& tx, int& ks) {
+        nt = (int)(w % a.ntile_n);
+        long long r = w / a.ntile_n;
+        const int mt = (int)(r % m_tiles);
+        ks = (int)(r / m_tiles);
+        img = mt / mt_per_img;
+        const int t2 = mt - img * mt_per_img;
+        ty = t2 / a.tiles_x;
+        tx = t2 - ty * a.tiles_x;
+    };
+
+    if (warp >= kProdWarp0) {
+        // =========================== A producers ===========================
+        const int pt = threadIdx.x - kProdWarp0 * 32;       // 0..255
+        const int pl = pt & 7;                              // 8-channel plane handled by this thread
+        const int Hl = a.h * a.up, Wl = a.w * a.up;
+        const int npix = conv3 ? 180 : 128;
+        const int cin = a.c0 + a.c1;
+        int stage = 0, phase = 0;
+        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            int nt, img, ty, tx, ks;
+            decode(w, nt, img, ty, tx, ks);
+            const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
+            for (int cb = cb0; cb < cb1; ++cb) {
+                const int ch = cb * CB + pl * 8;            // first of this thread's 8 channels (global, concat space)
+                const bool ch_ok = ch < cin;
+                float sc[8], sh[8];
+                if (a.pre_scale && ch_ok) {
+                    const float4* ps = reinterpret_cast<const float4*>(a.pre_scale + (size_t)img * cin + ch);
+                    const float4* pb = reinterpret_cast<const float4*>(a.pre_shift + (size_t)img * cin + ch);
+                    float4 s0 = ps[0], s1 = ps[1], b0 = pb[0], b1 = pb[1];
+                    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+                }
+                const void* src; int sdt, sc_ch, cc;
+                if (ch < a.c0) { src = a.in0; sdt = a.in0_dt; sc_ch = a.c0; cc = ch; }
+                else { src = a.in1; sdt = a.in1_dt; sc_ch = a.c1; cc = ch - a.c0; }
+                mbar_wait(A_EMPTY(stage), phase ^ 1);
+                uint8_t* dst = sA + stage * A_STAGE_BYTES + pl * plane;
+                for (int p = pt >> 3; p < npix; p += kProdThreads / 8) {
+                    bool ok = ch_ok;
+                    size_t pix = 0;
+                    if (conv3) {
+                        const int hy = p / 10, hx = p - hy * 10;
+                        const int iy = ty * 16 + hy - 1, ix = tx * 8 + hx - 1;
+                        ok = ok && iy >= 0 && iy < Hl && ix >= 0 && ix < Wl;
+                        pix = ((size_t)img * a.h + (iy >> (a.up - 1))) * a.w + (ix >> (a.up - 1));
+                    } else {
+                        const long long q = ((long long)ty * 16) * 8 + p;     // pixel index within the image
+                        ok = ok && q < (long long)a.h * a.w;
+                        pix = (size_t)img * a.h * a.w + (size_t)q;
+                    }
+                    float v[8];
+                    if (ok) {
+                        if (sdt == F32) {
+                            const float4* g = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + pix * sc_ch + cc);
+                            const float4 x0 = g[0], x1 = g[1];
+                            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+                        } else {
+                            const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + pix * sc_ch + cc);
+                            const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hh[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+                        }
+                        if (a.pre_scale) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+                        }
+                        if (a.pre_act != ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fast_act(v[j], a.pre_act);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+                    }
+                    uint4 o;
+                    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+                    o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                    o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(dst + p * 16) = o;
+                }
+                fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
+                mbar_arrive(A_FULL(stage));
+                if (++stage == SA) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == kLoadWarp) {
+        // =========================== weight loader (1-D TMA) ===========================
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+                int nt, img, ty, tx, ks;
+                decode(w, nt, img, ty, tx, ks);
+                const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
+                for (int cb = cb0; cb < cb1; ++cb) {
+                    for (int tap = 0; tap < a.taps; ++tap) {
+                        mbar_wait(B_EMPTY(stage), phase ^ 1);
+                        mbar_arrive_expect_tx(B_FULL(stage), (uint32_t)b_stage_bytes);
+                        const uint8_t* g = reinterpret_cast<const uint8_t*>(a.wt) +
+                                           ((size_t)((size_t)nt * a.ncb + cb) * a.taps + tap) * (size_t)b_stage_bytes;
+                        tma_bulk_g2s(smem_u32(sB + stage * b_stage_bytes), g, (uint32_t)b_stage_bytes, B_FULL(stage));
+                        if (++stage == SB) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, K-major A/B
+            const uint32_t a_lbo = a.swap_lbo_sbo ? (uint32_t)(hw10 * 16) : (uint32_t)plane;
+            const uint32_t a_sbo = a.swap_lbo_sbo ? (uint32_t)plane : (uint32_t)(hw10 * 16);
+            const uint32_t b_lbo = a.swap_lbo_sbo ? 256u : 128u;
+            const uint32_t b_sbo = a.swap_lbo_sbo ? 128u : 256u;
+            int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+                int nt, img, ty, tx, ks;
+                decode(w, nt, img, ty, tx, ks);
+                const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
+                mbar_wait(ACC_EMPTY(as), pacc ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
+                uint32_t acc = 0;
+                for (int cb = cb0; cb < cb1; ++cb) {
+                    mbar_wait(A_FULL(sa), pa);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(sA + sa * A_STAGE_BYTES);
+                    for (int tap = 0; tap < a.taps; ++tap) {
+                        mbar_wait(B_FULL(sb), pb);
+                        tc_fence_after();
+                        const uint32_t b_base = smem_u32(sB + sb * b_stage_bytes);
+                        const uint32_t tap_off = conv3 ? (uint32_t)(((tap / 3) * 10 + (tap % 3)) * 16) : 0u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = make_desc(a_base + (uint32_t)(2 * k * plane) + tap_off, a_lbo, a_sbo);
+                            const uint64_t bd = make_desc(b_base + (uint32_t)(k * a.bn * 32), b_lbo, b_sbo);
+                            umma_f16(d_tmem, ad, bd, idesc, acc);
+                            acc = 1;
+                        }
+                        umma_commit(B_EMPTY(sb));            // frees the weight stage when these MMAs retire
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                    umma_commit(A_EMPTY(sa));
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(ACC_FULL(as));
+                if (++as == 2) { as = 0; pacc ^= 1; }
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 0-3 <-> TMEM lane quarters) ===========================
+        int as = 0, pacc = 0;
+        const int row = warp * 32 + lane;          // accumulator row = output pixel within the tile
+        const int r = row >> 3, c = row & 7;
+        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            int nt, img, ty, tx, ks;
+            decode(w, nt, img, ty, tx, ks);
+            mbar_wait(ACC_FULL(as), pacc);
+            tc_fence_after();
+            long long pixel;
+            bool ok;
+            if (conv3) {
+                const int oy = ty * 16 + r, ox = tx * 8 + c;
+                ok = oy < a.ho && ox < a.wo;
+                pixel = ((long long)img * a.ho + oy) * a.wo + ox;
+            } else {
+                const long long q = (long long)ty * 128 + row;
+                ok = q < (long long)a.h * a.w;
+                pixel = (long long)img * a.h * a.w + q;
+            }
+            const int n0 = nt * a.bn;
+            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * a.bn);
+            for (int j = 0; j < a.bn; j += 16) {
+                uint32_t rr[16];
+                tmem_ld16(t0 + (uint32_t)j, rr);
+                tmem_ld_wait();
+                const int nn = n0 + j;
+                if (ok && nn < a.cout) {       // cout % 16 == 0
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
+                    const size_t off = (size_t)pixel * a.cout + nn;
+                    if (a.splitk > 1) {
+                        float4* o = reinterpret_cast<float4*>(a.partial + (size_t)ks * a.M * a.cout + off);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                    } else {
+                        if (a.bias) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 b = *reinterpret_cast<const float4*>(a.bias + nn + 4 * e);
+                                v[4 * e] += b.x; v[4 * e + 1] += b.y; v[4 * e + 2] += b.z; v[4 * e + 3] += b.w;
+                            }
+                        }
+                        if (a.act != ACT_NONE) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], a.act);
+                        }
+                        if (a.res) {
+                            if (a.res_dt == F32) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float4 q4 = ld4(reinterpret_cast<const float*>(a.res), off + 4 * e);
+                                    v[4 * e] += q4.x; v[4 * e + 1] += q4.y; v[4 * e + 2] += q4.z; v[4 * e + 3] += q4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float4 q4 = ld4(reinterpret_cast<const __half*>(a.res), off + 4 * e);
+                                    v[4 * e] += q4.x; v[4 * e + 1] += q4.y; v[4 * e + 2] += q4.z; v[4 * e + 3] += q4.w;
+                                }
+                            }
+                        }
+                        if (a.out_dt == F32) {
+                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                st4(reinterpret_cast<__half*>(a.out), off + 4 * e, make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(ACC_EMPTY(as));
+            if (++as == 2) { as = 0; pacc ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int tc_pick_bn(int cout, long long m_tiles) {
+    // N tile: a multiple of 16 up to 256.  Wider tiles amortise the A-operand transform; narrower ones give
+    // more CTAs when the layer is small.
+    if (cout <= 64) return (cout + 15) / 16 * 16;
+    if (cout == 96 || cout == 192) return cout;
+    if (cout % 256 == 0 && m_tiles * (cout / 256) >= 148) return 256;
+    return 128;
+}
+
+bool tc_eligible(const ConvArgs& a) {
+    const int cin = a.c0 + a.c1;
+    const bool k3 = a.kh == 3 && a.kw == 3 && a.stride == 1 && a.pad_t == 1 && a.pad_l == 1 && a.ho == a.h * a.up && a.wo == a.w * a.up;
+    const bool k1 = a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad_t == 0 && a.pad_l == 0 && a.up == 1;
+    if (!k3 && !k1) return false;
+    if (a.cout % 16 != 0 || cin % 8 != 0 || cin < 32) return false;
+    if (a.c1 > 0 && a.c0 % 8 != 0) return false;
+    if (k1 && ((long long)a.h * a.w) % 8 != 0) return false;
+    if (a.up != 1 && a.up != 2) return false;
+    return true;
+}
+
+size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn) {
+    const int ncb = (cin + CB - 1) / CB, ntile = (cout + bn - 1) / bn;
+    return (size_t)ntile * ncb * taps * bn * 64;
+}
+
+// OIHW fp32 (host) -> [ntile][cb][tap][k16][n8][khalf][8 n][8 k] fp16
+void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, __half* out) {
+    const int taps = kh * kw, ncb = (cin + CB - 1) / CB, ntile = (cout + bn - 1) / bn;
+    size_t idx = 0;
+    for (int nt = 0; nt < ntile; ++nt)
+        for (int cb = 0; cb < ncb; ++cb)
+            for (int tap = 0; tap < taps; ++tap)
+                for (int k16 = 0; k16 < 4; ++k16)
+                    for (int g = 0; g < bn / 8; ++g)
+                        for (int kh2 = 0; kh2 < 2; ++kh2)
+                            for (int r = 0; r < 8; ++r)
+                                for (int e = 0; e < 8; ++e) {
+                                    const int o = nt * bn + g * 8 + r, i = cb * CB + k16 * 16 + kh2 * 8 + e;
+                                    float v = 0.0f;
+                                    if (o < cout && i < cin) v = w_oihw[(((size_t)o * cin + i) * kh + tap / kw) * kw + tap % kw];
+                                    out[idx++] = __float2half_rn(v);
+                                }
+}
+
+namespace {
+// device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 panel layout
+__global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, size_t total,
+                                 __half* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    size_t r = idx;
+    const int e = (int)(r % 8); r /= 8;
+    const int row = (int)(r % 8); r /= 8;
+    const int kh2 = (int)(r % 2); r /= 2;
+    const int g = (int)(r % (bn / 8)); r /= (bn / 8);
+    const int k16 = (int)(r % 4); r /= 4;
+    const int tap = (int)(r % taps); r /= taps;
+    const int cb = (int)(r % ncb); r /= ncb;
+    const int nt = (int)r;
+    const int o = nt * bn + g * 8 + row, i = cb * CB + k16 * 16 + kh2 * 8 + e;
+    float v = 0.0f;
+    if (o < cout && i < cin) v = w[((size_t)tap * cin + i) * cout + o];
+    out[idx] = __float2half_rn(v);
+}
+}  // namespace
+
+void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, __half* out, cudaStream_t s) {
+    const int ncb = (cin + CB - 1) / CB;
+    const size_t total = tc_packed_weight_halfs(cin, cout, taps, bn);
+    tc_repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_kc, cin, cout, taps, bn, ncb, total, out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb) {
+    const long long ctas = m_tiles * ntile_n;
+    if (ctas >= 96 || ncb < 2) return 1;
+    long long s = (148 + ctas - 1) / ctas;
+    if (s > ncb) s = ncb;
+    return (int)(s < 1 ? 1 : s);
+}
+
+static int env_swap() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KEEP_TC_SWAP_LBO_SBO"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+
+void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int splitk, float* partial, int num_sms, cudaStream_t s) {
+    KEEP_CHECK(tc_eligible(a), "conv2d_tc: layer not eligible for the tcgen05 kernel");
+    TcConvArgs t;
+    t.in0 = a.in0; t.in1 = a.in1; t.in0_dt = a.in0_dt; t.in1_dt = a.in1_dt; t.c0 = a.c0; t.c1 = a.c1;
+    t.n = a.n; t.h = a.h; t.w = a.w; t.up = a.up;
+    t.pre_scale = a.pre_scale; t.pre_shift = a.pre_shift; t.pre_act = a.pre_act;
+    t.wt = packed; t.bias = a.bias;
+    t.taps = a.kh * a.kw; t.cout = a.cout; t.bn = bn;
+    t.ho = a.ho; t.wo = a.wo;
+    t.ncb = (a.c0 + a.c1 + CB - 1) / CB;
+    if (t.taps == 9) { t.tiles_y = cdiv(a.ho, 16); t.tiles_x = cdiv(a.wo, 8); }
+    else { t.tiles_y = cdiv((long long)a.h * a.w, 128); t.tiles_x = 1; }
+    t.ntile_n = cdiv(a.cout, bn);
+    {   // every K-split must own at least one channel block
+        const int cb_per = cdiv(t.ncb, splitk < 1 ? 1 : splitk);
+        splitk = cdiv(t.ncb, cb_per);
+    }
+    t.splitk = splitk; t.partial = partial;
+    t.act = a.act; t.res = a.res; t.res_dt = a.res_dt; t.out = a.out; t.out_dt = a.out_dt;
+    t.M = (long long)a.n * a.ho * a.wo;
+    int cols = 32;
+    while (cols < 2 * bn) cols *= 2;
+    KEEP_CHECK(cols <= 512, "conv2d_tc: BN %d needs more than 512 TMEM columns", bn);
+    t.tmem_cols = cols;
+    t.swap_lbo_sbo = env_swap();
+    KEEP_CHECK(splitk == 1 || partial, "conv2d_tc: split-K needs a partial buffer");
+    const size_t smem = 128 + (size_t)SA * A_STAGE_BYTES + (size_t)SB * bn * 128 + 8 * (2 * SA + 2 * SB + 4) + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+        configured = 220 * 1024;
+    }
+    const long long total = (long long)t.n * t.tiles_y * t.tiles_x * t.ntile_n * splitk;
+    const int grid = (int)std::min<long long>(total, num_sms);
+    conv_tc_kernel<<<grid, kThreads, smem, s>>>(t);
+    CUDA_CHECK(cudaGetLastError());
+    if (splitk > 1) splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);
+}
+
+}  // namespace keep
+
+// op-level test hook (capi.cu): pack on the fly, run, free
+int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, cudaStream_t s) {
+    using namespace keep;
+    const int cin = a.c0 + a.c1;
+    KEEP_CHECK(tc_eligible(a), "keepop_conv2d(use_tc=1): layer not eligible for the tcgen05 kernel");
+    const long long m_tiles = a.kh == 3 ? (long long)a.n * cdiv(a.ho, 16) * cdiv(a.wo, 8) : (long long)a.n * cdiv((long long)a.h * a.w, 128);
+    const int bn = tc_pick_bn(a.cout, m_tiles);
+    std::vector<__half> packed(tc_packed_weight_halfs(cin, a.cout, a.kh * a.kw, bn));
+    tc_pack_weights(w_oihw_host, a.cout, cin, a.kh, a.kw, bn, packed.data());
+    __half* dw = nullptr;
+    float* part = nullptr;
+    CUDA_CHECK(cudaMalloc((void**)&dw, packed.size() * sizeof(__half)));
+    CUDA_CHECK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    const int splitk = tc_pick_splitk(m_tiles, cdiv(a.cout, bn), (cin + 63) / 64);
+    if (splitk > 1) CUDA_CHECK(cudaMalloc((void**)&part, (size_t)splitk * a.n * a.ho * a.wo * a.cout * sizeof(float)));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    try {
+        conv2d_tc(a, dw, bn, splitk, part, sms, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    } catch (...) {
+        cudaFree(dw);
+        cudaFree(part);
+        throw;
+    }
+    cudaFree(dw);
+    cudaFree(part);
+    return 0;
+}

@@ -189,6 +189,7 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         KEEP_CHECK(prop.major == 10, "keep_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device,
                    prop.major, prop.minor);
+        num_sms_ = prop.multiProcessorCount;
     }
     adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
     pack_weights(w, n_w);
@@ -228,6 +229,7 @@ Engine::~Engine() {
     cudaFree(own_ws_);
     for (auto& kv : cap_) cudaFree(kv.second.p);
     for (auto& kv : forced_) cudaFree(kv.second.p);
+    for (auto& kv : tcw_) cudaFree(kv.second.p);
     for (auto& p : prof_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& e : ev_pool_) cudaEventDestroy(e);
 }
@@ -284,8 +286,17 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         a.res = o.res->p; a.res_dt = o.res->dt;
     }
     a.out = out.p; a.out_dt = out.dt;
-    a.splitk = conv_pick_splitk(a);
+    const bool use_tc = (flags_ & KEEP_FLAG_TCGEN05) && !o.exact && tc_eligible(a);
+    int bn = 0;
     void* part = nullptr;
+    if (use_tc) {
+        const long long m_tiles = cw.kh == 3 ? (long long)x.n * cdiv(a.ho, 16) * cdiv(a.wo, 8)
+                                             : (long long)x.n * cdiv((long long)x.h * x.w, 128);
+        bn = tc_pick_bn(cw.cout, m_tiles);
+        a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), (cw.cin + 63) / 64);
+    } else {
+        a.splitk = conv_pick_splitk(a);
+    }
     if (a.splitk > 1) {
         part = arena_.alloc((size_t)a.splitk * out.numel() * sizeof(float));
         a.partial = (float*)part;
@@ -296,11 +307,12 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             pr.a = get_event(); pr.b = get_event();
             pr.flops = 2.0 * (double)out.rows() * cw.cout * cw.kh * cw.kw * cw.cin;
             pr.bytes = (double)x.bytes() + (o.in1 ? (double)o.in1->bytes() : 0.0) + (double)out.bytes() +
-                       (o.res ? (double)o.res->bytes() : 0.0) + 4.0 * cw.cout * cw.kh * cw.kw * cw.cin;
-            pr.tag = 0;
+                       (o.res ? (double)o.res->bytes() : 0.0) + (use_tc ? 2.0 : 4.0) * cw.cout * cw.kh * cw.kw * cw.cin;
+            pr.tag = use_tc ? 1 : 0;
             CUDA_CHECK(cudaEventRecord(pr.a, s_));
         }
-        conv2d_simt(a, s_);
+        if (use_tc) conv2d_tc(a, tc_weights(cw, bn), bn, a.splitk, a.partial, num_sms_, s_);
+        else conv2d_simt(a, s_);
         launches_ += a.splitk > 1 ? 2 : 1;
         if (profile_) {
             CUDA_CHECK(cudaEventRecord(pr.b, s_));
@@ -309,6 +321,21 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     }
     if (part) arena_.free(part);
     return out;
+}
+
+const __half* Engine::tc_weights(const ConvW& cw, int bn) {
+    auto it = tcw_.find(cw.w);
+    if (it != tcw_.end() && it->second.bn == bn) return it->second.p;
+    TcW t;
+    t.bn = bn;
+    CUDA_CHECK(cudaMalloc((void**)&t.p, tc_packed_weight_halfs(cw.cin, cw.cout, cw.kh * cw.kw, bn) * sizeof(__half)));
+    tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, t.p, s_);
+    if (it != tcw_.end()) {
+        CUDA_CHECK(cudaStreamSynchronize(s_));
+        cudaFree(it->second.p);
+    }
+    tcw_[cw.w] = t;
+    return t.p;
 }
 
 Tensor Engine::linear(const Tensor& x, const std::string& prefix, int act, const Tensor* res) {

@@ -7,6 +7,7 @@
 
 #include "../../include/keep_b200.h"
 #include "ops.h"
+#include "tc.h"
 
 namespace keep {
 
@@ -39,6 +40,7 @@ struct ConvOpt {
     const Tensor* res = nullptr;
     const Tensor* in1 = nullptr;
     int out_dt = -1;  // -1: engine feature-map dtype
+    bool exact = false;  // force the exact-fp32 CUDA-core kernel even when the tcgen05 path is enabled
     ConvOpt& pad(int p) { pad_t = pad_l = pad_b = pad_r = p; return *this; }
 };
 
@@ -109,6 +111,11 @@ class Engine {
     // engine-owned workspace (used when the caller passes none)
     void* own_ws_ = nullptr; size_t own_ws_bytes_ = 0;
     std::unordered_map<int, size_t> ws_cache_;
+    // tcgen05 path: fp16 weight panels, packed on first use, keyed by (fp32 weight pointer, N tile)
+    struct TcW { __half* p = nullptr; int bn = 0; };
+    std::unordered_map<const float*, TcW> tcw_;
+    const __half* tc_weights(const ConvW& cw, int bn);
+    int num_sms_ = 148;
     // debug capture / forcing
     struct Cap { void* p = nullptr; size_t bytes = 0; };
     std::unordered_map<std::string, Cap> cap_;      // device buffers holding last forward's intermediates

@@ -1,0 +1,33 @@
+// keep_b200 — tcgen05 convolution kernel: shared declarations
+#pragma once
+#include "ops.h"
+
+namespace keep {
+
+struct TcConvArgs {
+    const void* in0; const void* in1; int in0_dt, in1_dt; int c0, c1;
+    int n, h, w, up;
+    const float* pre_scale; const float* pre_shift; int pre_act;
+    const __half* wt; const float* bias;
+    int taps, cout, bn, ho, wo, ncb;
+    int tiles_y, tiles_x, ntile_n;
+    int splitk; float* partial;
+    int act; const void* res; int res_dt; void* out; int out_dt;
+    long long M;
+    int tmem_cols;
+    int swap_lbo_sbo;   // debug: KEEP_TC_SWAP_LBO_SBO=1
+};
+
+bool tc_eligible(const ConvArgs& a);
+int tc_pick_bn(int cout, long long m_tiles);
+int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb);
+size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn);
+void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, __half* out);
+void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, __half* out, cudaStream_t s);
+// partial: splitk * M * cout floats when splitk > 1
+void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int splitk, float* partial, int num_sms, cudaStream_t s);
+// fixed-order split-K reduce + epilogue (conv_simt.cu)
+void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
+                   int res_dt, void* out, int out_dt, cudaStream_t s);
+
+}  // namespace keep

@@ -1,0 +1,84 @@
+"""GPU tier: the tcgen05 (tensor-core, fp16 operands / fp32 TMEM accumulate) convolution kernel.
+
+Op level: vs torch fp32 conv on operands rounded to fp16 exactly as the kernel rounds them (so the only
+differences are fp32 summation order and, with a swish prologue, tanh.approx) — tolerance 2e-4 (3e-3 with swish)
+relative to max|y|.  Engine level: whole keep_net in tensor-core mode vs the oracle, reported and bounded."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_gpu_ops import _act, ref_conv, run_conv
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+TC_CASES = [
+    # name, n, cin, h, w, cout, k, up, pre, pre_act, act, res, bias
+    ("3x3_64_64", 2, 64, 32, 32, 64, 3, 1, False, "none", "none", False, True),
+    ("3x3_gn_swish_res_ragged", 1, 64, 40, 24, 128, 3, 1, True, "swish", "none", True, True),
+    ("up2_128", 1, 128, 16, 16, 128, 3, 2, False, "none", "none", False, True),
+    ("linear_splitk", 1, 512, 256, 1, 1024, 1, 1, False, "none", "gelu", False, True),
+    ("c16_512_splitk_res", 1, 512, 16, 16, 512, 3, 1, True, "swish", "none", True, True),
+    ("lrelu_256", 1, 256, 32, 32, 256, 3, 1, False, "none", "lrelu", False, True),
+    ("ragged_37x29", 1, 64, 37, 29, 64, 3, 1, False, "none", "none", False, True),
+    ("gm_96_96_relu", 2, 96, 32, 32, 96, 3, 1, True, "relu", "none", False, False),
+    ("mask_1x1_576", 2, 256, 16, 16, 576, 1, 1, False, "none", "none", False, True),
+    ("qkv_1x1_pre_n2", 2, 512, 16, 16, 1536, 1, 1, True, "none", "none", False, True),
+    ("persistent_64_64_256sq", 1, 64, 256, 256, 64, 3, 1, True, "swish", "none", True, True),
+    ("persistent_128_128_n3", 3, 128, 128, 64, 128, 3, 1, False, "none", "none", False, True),
+    ("wide_256_256_128sq", 1, 256, 128, 128, 256, 3, 1, False, "none", "none", False, True),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tcgen05_matches_torch(lib, case):
+    name, n, cin, h, w, cout, k, up, pre, pre_act, act, res, bias = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) & 0xFFFF)
+    x = torch.randn((n, cin, h, w), generator=g).cuda()
+    wt = (torch.randn((cout, cin, k, k), generator=g) / math.sqrt(cin * k * k)).cuda()
+    b = torch.randn((cout,), generator=g).cuda() if bias else None
+    prep = None
+    if pre:
+        prep = (1.0 + 0.2 * torch.randn((n, cin), generator=g)).cuda(), (0.2 * torch.randn((n, cin), generator=g)).cuda()
+    pads = (1, 1, 1, 1) if k == 3 else (0, 0, 0, 0)
+    # reference with the kernel's operand rounding: A = fp16(act(affine(x))), W = fp16(w), fp32 accumulate
+    xa = x
+    if prep is not None:
+        xa = xa * prep[0][:, :, None, None] + prep[1][:, :, None, None]
+    xa = _act(xa, pre_act).half().float()
+    want0 = ref_conv(xa, wt.half().float(), b, 1, pads, up, None, "none", act, None)
+    r = torch.randn(want0.shape, generator=g).cuda() if res else None
+    want = want0 + r if res else want0
+    got = run_conv(lib, x, wt, b, 1, pads, up, prep, pre_act, act, r, use_tc=1)
+    torch.cuda.synchronize()
+    err = float((got - want).abs().max())
+    tol = (3e-3 if pre_act == "swish" else 2e-4) * max(1.0, float(want.abs().max()))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "tc_op_report.txt"), "a") as f:
+        f.write("%s swap=%s err=%.3e tol=%.3e max=%.3f\n" % (name, os.environ.get("KEEP_TC_SWAP_LBO_SBO", "0"), err, tol,
+                                                              float(want.abs().max())))
+    assert err <= tol, "%s: max abs err %g > %g" % (name, err, tol)
+
+
+def test_conv_tcgen05_vs_fp32_kernel_is_fp16_close(lib):
+    """Same layer through both kernels: the tensor-core result must sit within fp16 operand rounding of exact fp32."""
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn((1, 128, 64, 64), generator=g).cuda()
+    wt = (torch.randn((128, 128, 3, 3), generator=g) / math.sqrt(128 * 9)).cuda()
+    b = torch.randn((128,), generator=g).cuda()
+    a = run_conv(lib, x, wt, b, 1, (1, 1, 1, 1), use_tc=0)
+    c = run_conv(lib, x, wt, b, 1, (1, 1, 1, 1), use_tc=1)
+    rel = float((a - c).abs().max() / a.abs().max())
+    assert rel < 3e-3, rel

@@ -1,0 +1,88 @@
+"""GPU tier: keep_net in tensor-core mode (KEEP_FLAG_TCGEN05) vs the oracle.
+
+fp16 operand rounding perturbs the logits by ~1e-2, so a few code indices flip at near-ties of the oracle's own
+logits.  The checks are therefore: (1) teacher-forced (oracle flows / codes / previous outputs
+fed in) pixels within fp16 tolerance, (2) free-running code flips only where the oracle's top1-top2 margin is small."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def psnr(a, b):
+    a, b = a.double().clamp(-1, 1), b.double().clamp(-1, 1)
+    mse = float(((a - b) ** 2).mean()) / 4.0
+    return 999.0 if mse == 0 else 10 * np.log10(1.0 / mse)
+
+
+@pytest.fixture(scope="module")
+def net_tc(keep_mod, state_dict):
+    n = keep_mod.KeepNetB200(flags=keep_mod.keep_net.FLAG_TCGEN05)
+    n.load_state_dict(state_dict, strict=True)
+    n.eval().to("cuda")
+    n.debug_capture(True)
+    yield n
+    n.to("cpu")
+
+
+@pytest.fixture(scope="module")
+def oracle_T2(state_dict):
+    from oracle import keep_oracle, weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = weights.make_clip(2, seed=4321, coherent=True)
+    out, cap = keep_oracle.keep_forward(state_dict, x, capture=True)
+    return x, out, cap
+
+
+def _report(tag, **kw):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report_tc.txt"), "a") as f:
+        f.write(tag + " " + " ".join("%s=%s" % (k, v) for k, v in kw.items()) + "\n")
+
+
+def test_tc_teacher_forced_T2(net_tc, oracle_T2):
+    x, ref_out, cap = oracle_T2
+    T = 2
+    try:
+        net_tc.debug_force("flows", cap["flows"][0].permute(0, 2, 3, 1).contiguous())
+        net_tc.debug_force("codes", cap["codes"][0].to(torch.int32))
+        net_tc.debug_force("prev", ref_out[0])
+        out = net_tc(x.cuda(), need_upscale=False).cpu()
+    finally:
+        for w in ("flows", "codes", "prev"):
+            net_tc.debug_force(w, None)
+    z = net_tc.debug_read("z_codes", (T, 16, 16, 256)).permute(0, 3, 1, 2)
+    gains = net_tc.debug_read("gains", (T, 16, 16))
+    logits = net_tc.debug_read("logits", (T, 256, 1024))
+    codes = net_tc.debug_read("codes", (T, 256), torch.int32).long()
+    e_z = float((z - cap["z_codes"][0]).abs().max())
+    e_g = float((gains - cap["gains"][0, :, 0]).abs().max())
+    e_l = float((logits - cap["logits"][0]).abs().max())
+    agree = float((codes == cap["codes"][0]).float().mean())
+    e_o = float((out.clamp(-1, 1) - ref_out.clamp(-1, 1)).abs().max())
+    p = psnr(out, ref_out)
+    _report("tc_forced_T2", z=e_z, gain=e_g, logit=e_l, own_argmax_agree=agree, out=e_o, psnr=p,
+            zmax=float(cap["z_codes"].abs().max()), lmax=float(cap["logits"].abs().max()))
+    assert e_z < 5e-2 * float(cap["z_codes"].abs().max())
+    assert e_l < 5e-2 * float(cap["logits"].abs().max())
+    assert p >= 40.0, p
+
+
+def test_tc_free_running_T2_flips_only_at_near_ties(net_tc, oracle_T2):
+    x, ref_out, cap = oracle_T2
+    out = net_tc(x.cuda(), need_upscale=False).cpu()
+    codes = net_tc.debug_read("codes", (2, 256), torch.int32).long()
+    flows = net_tc.debug_read("flows", (1, 512, 512, 2)).permute(0, 3, 1, 2)
+    flips = codes != cap["codes"][0]
+    top2 = cap["logits"][0].topk(2, dim=2).values
+    margin = top2[..., 0] - top2[..., 1]
+    worst = float(margin[flips].max()) if bool(flips.any()) else 0.0
+    _report("tc_free_T2", flips=int(flips.sum()), flips_frame0=int(flips[0].sum()), worst_margin=worst,
+            flow_err=float((flows - cap["flows"][0]).abs().max()), out=float((out.clamp(-1, 1) - ref_out.clamp(-1, 1)).abs().max()),
+            psnr=psnr(out, ref_out))
+    assert int(flips[0].sum()) <= 8, "too many code flips on frame 0: %d" % int(flips[0].sum())
+    assert float(margin[0][flips[0]].max() if bool(flips[0].any()) else 0.0) < 0.1
