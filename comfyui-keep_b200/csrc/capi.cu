@@ -26,7 +26,7 @@ static thread_local std::string g_err;
         return -2;                                     \
     }
 
-int keepop_conv2d_tc(const ConvArgs& a, const float* w_oihw_host, cudaStream_t s);   // conv_tcgen05.cu
+int keepop_conv2d_tc(const ConvArgs& a, const float* w_oihw_host, int passes, cudaStream_t s);   // conv_tcgen05.cu
 
 extern "C" {
 
@@ -158,7 +158,7 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
     a.wo = (w * up + pad_l + pad_r - kw) / stride + 1;
     a.act = act; a.res = res_dev; a.out = out_dev;
     if (use_tc) {
-        int rc = keepop_conv2d_tc(a, weight_host, s);
+        int rc = keepop_conv2d_tc(a, weight_host, use_tc == 3 ? 3 : 1, s);
         CUDA_CHECK(cudaStreamSynchronize(s));
         return rc;
     }

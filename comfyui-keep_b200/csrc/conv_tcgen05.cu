@@ -30,11 +30,12 @@ namespace {
 
 constexpr int kThreads = 448;
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 5, kProdWarp0 = 6, kProdThreads = 256;
-constexpr int SA = 3, SB = 4;          // A / B pipeline depth
+constexpr int MAX_SA = 4, MAX_SB = 6;  // barrier slots (actual pipeline depths come from the launch arguments)
 constexpr int CB = 64;                 // channels per A stage (4 MMA K-steps of 16)
 constexpr int PLANE3 = 2960;           // bytes per 8-channel plane of a 18x10 halo (2880 padded to 16 mod 128: conflict-free stores)
 constexpr int PLANE1 = 2064;           // bytes per plane of a 128-pixel 1x1 tile (2048 padded likewise)
-constexpr int A_STAGE_BYTES = 8 * PLANE3;
+constexpr int A_SUB_BYTES = 8 * PLANE3;   // one operand tile (hi); the split-precision mode appends a second (lo) tile
+constexpr int MAXIT = 6;               // ceil(180 * 8 / 256) halo units per producer thread
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -121,27 +122,36 @@ __device__ __forceinline__ float fast_act(float v, int act) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+// PASSES = 1: fp16 operands (10-bit mantissa, the precision class of cuDNN's default TF32 convolutions).
+// PASSES = 3: split-precision: A = Ah + Al, W = Wh + Wl (fp16 pairs, ~22 mantissa bits), D += Ah*Wh + Ah*Wl + Al*Wh
+//             with fp32 accumulation in TMEM -> fp32-grade results on the tensor cores (the "decision path" needs
+//             this: one flipped argmax over the 1024 code logits changes a 32x32-pixel block).
+template <int PASSES>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b_stage_bytes = a.bn * 128;
+    constexpr int NOP = PASSES == 3 ? 2 : 1;             // operand tiles per stage (hi [, lo])
+    constexpr int A_STAGE_BYTES = NOP * A_SUB_BYTES;
+    const int SA = a.sa_stages, SB = a.sb_stages;
+    const int b_panel_bytes = a.bn * 128;
+    const int b_stage_bytes = NOP * b_panel_bytes;
     uint8_t* sA = smem;
     uint8_t* sB = smem + SA * A_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SB * b_stage_bytes);
-    // barrier map: a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2]
+    // barrier map: a_full[MAX_SA] a_empty[MAX_SA] b_full[MAX_SB] b_empty[MAX_SB] acc_full[2] acc_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto A_FULL = [&](int s) { return bar0 + 8u * s; };
-    auto A_EMPTY = [&](int s) { return bar0 + 8u * (SA + s); };
-    auto B_FULL = [&](int s) { return bar0 + 8u * (2 * SA + s); };
-    auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 * SA + SB + s); };
-    auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * SA + 2 * SB + s); };
-    auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * SA + 2 * SB + 2 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (MAX_SA + s); };
+    auto B_FULL = [&](int s) { return bar0 + 8u * (2 * MAX_SA + s); };
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_SA + MAX_SB + s); };
+    auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + s); };
+    auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SA + 2 * MAX_SB + 4);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < SA; ++s) { mbar_init(A_FULL(s), kProdThreads); mbar_init(A_EMPTY(s), 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+        for (int s = 0; s < MAX_SA; ++s) { mbar_init(A_FULL(s), kProdThreads); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < MAX_SB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(ACC_FULL(s), 1); mbar_init(ACC_EMPTY(s), kEpiWarps * 32); }
         fence_barrier_init();
     }
@@ -197,10 +207,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 const void* src; int sdt, sc_ch, cc;
                 if (ch < a.c0) { src = a.in0; sdt = a.in0_dt; sc_ch = a.c0; cc = ch; }
                 else { src = a.in1; sdt = a.in1_dt; sc_ch = a.c1; cc = ch - a.c0; }
-                mbar_wait(A_EMPTY(stage), phase ^ 1);
-                uint8_t* dst = sA + stage * A_STAGE_BYTES + pl * plane;
-                for (int p = pt >> 3; p < npix; p += kProdThreads / 8) {
-                    bool ok = ch_ok;
+                // ---- issue every global load of this stage first (memory-level parallelism), then transform
+                uint4 raw[MAXIT][2];
+                bool okv[MAXIT];
+                const int p_first = pt >> 3;
+#pragma unroll
+                for (int it = 0; it < MAXIT; ++it) {
+                    const int p = p_first + it * (kProdThreads / 8);
+                    bool ok = ch_ok && p < npix;
                     size_t pix = 0;
                     if (conv3) {
                         const int hy = p / 10, hx = p - hy * 10;
@@ -212,15 +226,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         ok = ok && q < (long long)a.h * a.w;
                         pix = (size_t)img * a.h * a.w + (size_t)q;
                     }
-                    float v[8];
+                    okv[it] = ok;
                     if (ok) {
                         if (sdt == F32) {
-                            const float4* g = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + pix * sc_ch + cc);
-                            const float4 x0 = g[0], x1 = g[1];
-                            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+                            const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(src) + pix * sc_ch + cc);
+                            raw[it][0] = g[0];
+                            raw[it][1] = g[1];
                         } else {
-                            const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + pix * sc_ch + cc);
-                            const __half2* hh = reinterpret_cast<const __half2*>(&u);
+                            raw[it][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + pix * sc_ch + cc);
+                        }
+                    }
+                }
+                mbar_wait(A_EMPTY(stage), phase ^ 1);
+                uint8_t* dst = sA + stage * A_STAGE_BYTES + pl * plane;
+#pragma unroll
+                for (int it = 0; it < MAXIT; ++it) {
+                    const int p = p_first + it * (kProdThreads / 8);
+                    if (p >= npix) continue;
+                    float v[8];
+                    if (okv[it]) {
+                        if (sdt == F32) {
+                            const float* f0 = reinterpret_cast<const float*>(&raw[it][0]);
+                            const float* f1 = reinterpret_cast<const float*>(&raw[it][1]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { v[j] = f0[j]; v[4 + j] = f1[j]; }
+                        } else {
+                            const __half2* hh = reinterpret_cast<const __half2*>(&raw[it][0]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hh[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
                         }
@@ -230,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         }
                         if (a.pre_act != ACT_NONE) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = fast_act(v[j], a.pre_act);
+                            for (int j = 0; j < 8; ++j) v[j] = PASSES == 3 ? apply_act(v[j], a.pre_act) : fast_act(v[j], a.pre_act);
                         }
                     } else {
 #pragma unroll
@@ -242,6 +273,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
                     o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
                     *reinterpret_cast<uint4*>(dst + p * 16) = o;
+                    if (PASSES == 3) {   // residual (lo) tile: v - float(fp16(v))
+                        const float2 r0 = __half22float2(h0), r1 = __half22float2(h1), r2 = __half22float2(h2), r3 = __half22float2(h3);
+                        __half2 l0 = __floats2half2_rn(v[0] - r0.x, v[1] - r0.y), l1 = __floats2half2_rn(v[2] - r1.x, v[3] - r1.y);
+                        __half2 l2 = __floats2half2_rn(v[4] - r2.x, v[5] - r2.y), l3 = __floats2half2_rn(v[6] - r3.x, v[7] - r3.y);
+                        uint4 ol;
+                        ol.x = *reinterpret_cast<uint32_t*>(&l0); ol.y = *reinterpret_cast<uint32_t*>(&l1);
+                        ol.z = *reinterpret_cast<uint32_t*>(&l2); ol.w = *reinterpret_cast<uint32_t*>(&l3);
+                        *reinterpret_cast<uint4*>(dst + A_SUB_BYTES + p * 16) = ol;
+                    }
                 }
                 fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
                 mbar_arrive(A_FULL(stage));
@@ -298,7 +338,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t ad = make_desc(a_base + (uint32_t)(2 * k * plane) + tap_off, a_lbo, a_sbo);
                             const uint64_t bd = make_desc(b_base + (uint32_t)(k * a.bn * 32), b_lbo, b_sbo);
-                            umma_f16(d_tmem, ad, bd, idesc, acc);
+                            if (PASSES == 3) {   // small cross terms first, then the leading term
+                                const uint64_t adl = make_desc(a_base + A_SUB_BYTES + (uint32_t)(2 * k * plane) + tap_off, a_lbo, a_sbo);
+                                const uint64_t bdl = make_desc(b_base + (uint32_t)b_panel_bytes + (uint32_t)(k * a.bn * 32), b_lbo, b_sbo);
+                                umma_f16(d_tmem, adl, bd, idesc, acc);
+                                umma_f16(d_tmem, ad, bdl, idesc, 1u);
+                                umma_f16(d_tmem, ad, bd, idesc, 1u);
+                            } else {
+                                umma_f16(d_tmem, ad, bd, idesc, acc);
+                            }
                             acc = 1;
                         }
                         umma_commit(B_EMPTY(sb));            // frees the weight stage when these MMAs retire
@@ -406,12 +454,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-int tc_pick_bn(int cout, long long m_tiles) {
+int tc_pick_bn(int cout, long long m_tiles, int passes) {
     // N tile: a multiple of 16 up to 256.  Wider tiles amortise the A-operand transform; narrower ones give
-    // more CTAs when the layer is small.
+    // more CTAs when the layer is small.  The split-precision mode doubles the smem per stage -> BN <= 128.
     if (cout <= 64) return (cout + 15) / 16 * 16;
-    if (cout == 96 || cout == 192) return cout;
-    if (cout % 256 == 0 && m_tiles * (cout / 256) >= 148) return 256;
+    if (cout == 96) return 96;
+    if (cout == 192 && passes == 1) return 192;
+    if (passes == 1 && cout % 256 == 0 && m_tiles * (cout / 256) >= 148) return 256;
+    if (cout % 128 != 0 && cout % 96 == 0) return 96;
     return 128;
 }
 
@@ -427,33 +477,35 @@ bool tc_eligible(const ConvArgs& a) {
     return true;
 }
 
-size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn) {
+size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn, int passes) {
     const int ncb = (cin + CB - 1) / CB, ntile = (cout + bn - 1) / bn;
-    return (size_t)ntile * ncb * taps * bn * 64;
+    return (size_t)ntile * ncb * taps * bn * 64 * (passes == 3 ? 2 : 1);
 }
 
-// OIHW fp32 (host) -> [ntile][cb][tap][k16][n8][khalf][8 n][8 k] fp16
-void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, __half* out) {
-    const int taps = kh * kw, ncb = (cin + CB - 1) / CB, ntile = (cout + bn - 1) / bn;
+// OIHW fp32 (host) -> [ntile][cb][tap][hi|lo][k16][n8][khalf][8 n][8 k] fp16
+void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out) {
+    const int taps = kh * kw, ncb = (cin + CB - 1) / CB, ntile = (cout + bn - 1) / bn, nop = passes == 3 ? 2 : 1;
     size_t idx = 0;
     for (int nt = 0; nt < ntile; ++nt)
         for (int cb = 0; cb < ncb; ++cb)
             for (int tap = 0; tap < taps; ++tap)
-                for (int k16 = 0; k16 < 4; ++k16)
-                    for (int g = 0; g < bn / 8; ++g)
-                        for (int kh2 = 0; kh2 < 2; ++kh2)
-                            for (int r = 0; r < 8; ++r)
-                                for (int e = 0; e < 8; ++e) {
-                                    const int o = nt * bn + g * 8 + r, i = cb * CB + k16 * 16 + kh2 * 8 + e;
-                                    float v = 0.0f;
-                                    if (o < cout && i < cin) v = w_oihw[(((size_t)o * cin + i) * kh + tap / kw) * kw + tap % kw];
-                                    out[idx++] = __float2half_rn(v);
-                                }
+                for (int part = 0; part < nop; ++part)
+                    for (int k16 = 0; k16 < 4; ++k16)
+                        for (int g = 0; g < bn / 8; ++g)
+                            for (int kh2 = 0; kh2 < 2; ++kh2)
+                                for (int r = 0; r < 8; ++r)
+                                    for (int e = 0; e < 8; ++e) {
+                                        const int o = nt * bn + g * 8 + r, i = cb * CB + k16 * 16 + kh2 * 8 + e;
+                                        float v = 0.0f;
+                                        if (o < cout && i < cin) v = w_oihw[(((size_t)o * cin + i) * kh + tap / kw) * kw + tap % kw];
+                                        const __half hi = __float2half_rn(v);
+                                        out[idx++] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+                                    }
 }
 
 namespace {
 // device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 panel layout
-__global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, size_t total,
+__global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int nop, size_t total,
                                  __half* __restrict__ out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -463,20 +515,22 @@ __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout,
     const int kh2 = (int)(r % 2); r /= 2;
     const int g = (int)(r % (bn / 8)); r /= (bn / 8);
     const int k16 = (int)(r % 4); r /= 4;
+    const int part = (int)(r % nop); r /= nop;
     const int tap = (int)(r % taps); r /= taps;
     const int cb = (int)(r % ncb); r /= ncb;
     const int nt = (int)r;
     const int o = nt * bn + g * 8 + row, i = cb * CB + k16 * 16 + kh2 * 8 + e;
     float v = 0.0f;
     if (o < cout && i < cin) v = w[((size_t)tap * cin + i) * cout + o];
-    out[idx] = __float2half_rn(v);
+    const __half hi = __float2half_rn(v);
+    out[idx] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
 }
 }  // namespace
 
-void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, __half* out, cudaStream_t s) {
+void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, __half* out, cudaStream_t s) {
     const int ncb = (cin + CB - 1) / CB;
-    const size_t total = tc_packed_weight_halfs(cin, cout, taps, bn);
-    tc_repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_kc, cin, cout, taps, bn, ncb, total, out);
+    const size_t total = tc_packed_weight_halfs(cin, cout, taps, bn, passes);
+    tc_repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_kc, cin, cout, taps, bn, ncb, passes == 3 ? 2 : 1, total, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -494,8 +548,20 @@ static int env_swap() {
     return v;
 }
 
-void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int splitk, float* partial, int num_sms, cudaStream_t s) {
+static void pick_stages(int passes, int bn, int& sa, int& sb) {
+    const int a_stage = (passes == 3 ? 2 : 1) * A_SUB_BYTES, b_stage = (passes == 3 ? 2 : 1) * bn * 128;
+    const int budget = 222 * 1024;
+    sa = passes == 3 ? 2 : 3;
+    sb = 3;
+    // grow the weight pipeline first (9 weight stages are consumed per activation stage), then the activation one
+    while (sb < MAX_SB && sa * a_stage + (sb + 1) * b_stage <= budget) ++sb;
+    while (sa < MAX_SA && (sa + 1) * a_stage + sb * b_stage <= budget) ++sa;
+}
+
+void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
+               cudaStream_t s) {
     KEEP_CHECK(tc_eligible(a), "conv2d_tc: layer not eligible for the tcgen05 kernel");
+    KEEP_CHECK(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3");
     TcConvArgs t;
     t.in0 = a.in0; t.in1 = a.in1; t.in0_dt = a.in0_dt; t.in1_dt = a.in1_dt; t.c0 = a.c0; t.c1 = a.c1;
     t.n = a.n; t.h = a.h; t.w = a.w; t.up = a.up;
@@ -519,31 +585,37 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int splitk, floa
     KEEP_CHECK(cols <= 512, "conv2d_tc: BN %d needs more than 512 TMEM columns", bn);
     t.tmem_cols = cols;
     t.swap_lbo_sbo = env_swap();
+    pick_stages(passes, bn, t.sa_stages, t.sb_stages);
     KEEP_CHECK(splitk == 1 || partial, "conv2d_tc: split-K needs a partial buffer");
-    const size_t smem = 128 + (size_t)SA * A_STAGE_BYTES + (size_t)SB * bn * 128 + 8 * (2 * SA + 2 * SB + 4) + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-        configured = 220 * 1024;
+    const int nop = passes == 3 ? 2 : 1;
+    const size_t smem = 128 + (size_t)t.sa_stages * nop * A_SUB_BYTES + (size_t)t.sb_stages * nop * bn * 128 +
+                        8 * (2 * MAX_SA + 2 * MAX_SB + 4) + 16;
+    KEEP_CHECK(smem <= 227 * 1024, "conv2d_tc: %zu bytes of shared memory", smem);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
     }
     const long long total = (long long)t.n * t.tiles_y * t.tiles_x * t.ntile_n * splitk;
     const int grid = (int)std::min<long long>(total, num_sms);
-    conv_tc_kernel<<<grid, kThreads, smem, s>>>(t);
+    if (passes == 3) conv_tc_kernel<3><<<grid, kThreads, smem, s>>>(t);
+    else conv_tc_kernel<1><<<grid, kThreads, smem, s>>>(t);
     CUDA_CHECK(cudaGetLastError());
     if (splitk > 1) splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);
 }
 
 }  // namespace keep
 
-// op-level test hook (capi.cu): pack on the fly, run, free
-int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, cudaStream_t s) {
+// op-level test hook (capi.cu): pack on the fly, run, free.  use_tc: 1 = fp16 operands, 3 = split precision
+int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, int passes, cudaStream_t s) {
     using namespace keep;
     const int cin = a.c0 + a.c1;
-    KEEP_CHECK(tc_eligible(a), "keepop_conv2d(use_tc=1): layer not eligible for the tcgen05 kernel");
+    KEEP_CHECK(tc_eligible(a), "keepop_conv2d(use_tc): layer not eligible for the tcgen05 kernel");
     const long long m_tiles = a.kh == 3 ? (long long)a.n * cdiv(a.ho, 16) * cdiv(a.wo, 8) : (long long)a.n * cdiv((long long)a.h * a.w, 128);
-    const int bn = tc_pick_bn(a.cout, m_tiles);
-    std::vector<__half> packed(tc_packed_weight_halfs(cin, a.cout, a.kh * a.kw, bn));
-    tc_pack_weights(w_oihw_host, a.cout, cin, a.kh, a.kw, bn, packed.data());
+    const int bn = tc_pick_bn(a.cout, m_tiles, passes);
+    std::vector<__half> packed(tc_packed_weight_halfs(cin, a.cout, a.kh * a.kw, bn, passes));
+    tc_pack_weights(w_oihw_host, a.cout, cin, a.kh, a.kw, bn, passes, packed.data());
     __half* dw = nullptr;
     float* part = nullptr;
     CUDA_CHECK(cudaMalloc((void**)&dw, packed.size() * sizeof(__half)));
@@ -554,7 +626,7 @@ int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, cudaStre
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     try {
-        conv2d_tc(a, dw, bn, splitk, part, sms, s);
+        conv2d_tc(a, dw, bn, passes, splitk, part, sms, s);
         CUDA_CHECK(cudaStreamSynchronize(s));
     } catch (...) {
         cudaFree(dw);

@@ -192,6 +192,7 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         num_sms_ = prop.multiProcessorCount;
     }
     adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
+    tc_passes_ = (flags & KEEP_FLAG_TC_SPLIT3) ? 3 : 1;
     pack_weights(w, n_w);
     // required keys (strict load, like load_state_dict(strict=True))
     const char* must[] = {"position_emb", "quantize.embedding.weight", "feat_emb.weight", "idx_pred_layer.1.weight",
@@ -292,7 +293,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     if (use_tc) {
         const long long m_tiles = cw.kh == 3 ? (long long)x.n * cdiv(a.ho, 16) * cdiv(a.wo, 8)
                                              : (long long)x.n * cdiv((long long)x.h * x.w, 128);
-        bn = tc_pick_bn(cw.cout, m_tiles);
+        bn = tc_pick_bn(cw.cout, m_tiles, tc_passes_);
         a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), (cw.cin + 63) / 64);
     } else {
         a.splitk = conv_pick_splitk(a);
@@ -307,11 +308,11 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             pr.a = get_event(); pr.b = get_event();
             pr.flops = 2.0 * (double)out.rows() * cw.cout * cw.kh * cw.kw * cw.cin;
             pr.bytes = (double)x.bytes() + (o.in1 ? (double)o.in1->bytes() : 0.0) + (double)out.bytes() +
-                       (o.res ? (double)o.res->bytes() : 0.0) + (use_tc ? 2.0 : 4.0) * cw.cout * cw.kh * cw.kw * cw.cin;
+                       (o.res ? (double)o.res->bytes() : 0.0) + (use_tc ? 2.0 * (tc_passes_ == 3 ? 2 : 1) : 4.0) * cw.cout * cw.kh * cw.kw * cw.cin;
             pr.tag = use_tc ? 1 : 0;
             CUDA_CHECK(cudaEventRecord(pr.a, s_));
         }
-        if (use_tc) conv2d_tc(a, tc_weights(cw, bn), bn, a.splitk, a.partial, num_sms_, s_);
+        if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_), bn, tc_passes_, a.splitk, a.partial, num_sms_, s_);
         else conv2d_simt(a, s_);
         launches_ += a.splitk > 1 ? 2 : 1;
         if (profile_) {
@@ -323,13 +324,13 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     return out;
 }
 
-const __half* Engine::tc_weights(const ConvW& cw, int bn) {
+const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes) {
     auto it = tcw_.find(cw.w);
-    if (it != tcw_.end() && it->second.bn == bn) return it->second.p;
+    if (it != tcw_.end() && it->second.bn == bn && it->second.passes == passes) return it->second.p;
     TcW t;
-    t.bn = bn;
-    CUDA_CHECK(cudaMalloc((void**)&t.p, tc_packed_weight_halfs(cw.cin, cw.cout, cw.kh * cw.kw, bn) * sizeof(__half)));
-    tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, t.p, s_);
+    t.bn = bn; t.passes = passes;
+    CUDA_CHECK(cudaMalloc((void**)&t.p, tc_packed_weight_halfs(cw.cin, cw.cout, cw.kh * cw.kw, bn, passes) * sizeof(__half)));
+    tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, passes, t.p, s_);
     if (it != tcw_.end()) {
         CUDA_CHECK(cudaStreamSynchronize(s_));
         cudaFree(it->second.p);

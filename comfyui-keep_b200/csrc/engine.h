@@ -112,9 +112,10 @@ class Engine {
     void* own_ws_ = nullptr; size_t own_ws_bytes_ = 0;
     std::unordered_map<int, size_t> ws_cache_;
     // tcgen05 path: fp16 weight panels, packed on first use, keyed by (fp32 weight pointer, N tile)
-    struct TcW { __half* p = nullptr; int bn = 0; };
+    struct TcW { __half* p = nullptr; int bn = 0, passes = 0; };
     std::unordered_map<const float*, TcW> tcw_;
-    const __half* tc_weights(const ConvW& cw, int bn);
+    const __half* tc_weights(const ConvW& cw, int bn, int passes);
+    int tc_passes_ = 1;   // 1: fp16 operands; 3: split-precision (fp32-grade) tensor-core mode
     int num_sms_ = 148;
     // debug capture / forcing
     struct Cap { void* p = nullptr; size_t bytes = 0; };

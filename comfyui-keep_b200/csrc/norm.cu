@@ -10,10 +10,11 @@
 namespace keep {
 namespace {
 
-constexpr int GN_MAX_CHUNKS = 128;
+constexpr int GN_MAX_CHUNKS = 1024;
 
-static inline int gn_num_chunks(int hw) {
-    int s = cdiv(hw, 512);
+// ~32K elements per block: 512^2 x 64 -> 512 blocks per image (several waves over 148 SMs)
+static inline int gn_num_chunks(int hw, int c) {
+    int s = cdiv((long long)hw * c, 32768);
     return s < 1 ? 1 : (s > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : s);
 }
 
@@ -124,12 +125,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 }  // namespace
 
-size_t gn_scratch_doubles(int n, int hw, int c) { return (size_t)n * gn_num_chunks(hw) * c * 2; }
+size_t gn_scratch_doubles(int n, int hw, int c) { return (size_t)n * GN_MAX_CHUNKS * c * 2 < (size_t)n * gn_num_chunks(hw, c) * c * 2 ? 0 : (size_t)n * gn_num_chunks(hw, c) * c * 2; }
 
 void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, float eps, const float* gamma, const float* beta,
                       float* scale, float* shift, int c_total, int c_off, double* scratch, cudaStream_t s) {
     KEEP_CHECK(c % 4 == 0 && c / 4 <= 256 && c % cpg == 0, "groupnorm: unsupported channels %d (cpg %d)", c, cpg);
-    const int nchunks = gn_num_chunks(hw);
+    const int nchunks = gn_num_chunks(hw, c);
     const int c4 = c / 4;
     const int lanes = 256 / c4 > 0 ? 256 / c4 : 1;
     const int threads = lanes * c4;

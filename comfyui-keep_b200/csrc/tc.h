@@ -15,17 +15,19 @@ struct TcConvArgs {
     int act; const void* res; int res_dt; void* out; int out_dt;
     long long M;
     int tmem_cols;
+    int sa_stages, sb_stages;
     int swap_lbo_sbo;   // debug: KEEP_TC_SWAP_LBO_SBO=1
 };
 
 bool tc_eligible(const ConvArgs& a);
-int tc_pick_bn(int cout, long long m_tiles);
+int tc_pick_bn(int cout, long long m_tiles, int passes);
 int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb);
-size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn);
-void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, __half* out);
-void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, __half* out, cudaStream_t s);
+size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn, int passes);
+void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out);
+void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, __half* out, cudaStream_t s);
 // partial: splitk * M * cout floats when splitk > 1
-void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int splitk, float* partial, int num_sms, cudaStream_t s);
+void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
+               cudaStream_t s);
 // fixed-order split-K reduce + epilogue (conv_simt.cu)
 void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
                    int res_dt, void* out, int out_dt, cudaStream_t s);

@@ -23,9 +23,14 @@ def psnr(a, b):
     return 999.0 if mse == 0 else 10 * np.log10(1.0 / mse)
 
 
-@pytest.fixture(scope="module")
-def net(keep_mod, state_dict):
-    n = keep_mod.KeepNetB200()
+# fp32: exact CUDA-core kernels.  tc3: tcgen05 tensor cores with split-precision operands (fp32-grade) — both must meet
+# the same parity bar.
+@pytest.fixture(scope="module", params=["fp32", "tc3"])
+def net(request, keep_mod, state_dict):
+    kn = keep_mod.keep_net
+    flags = 0 if request.param == "fp32" else (kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3)
+    n = keep_mod.KeepNetB200(flags=flags)
+    n.mode_name = request.param
     n.load_state_dict(state_dict, strict=True)
     n.eval().to("cuda")
     n.debug_capture(True)
@@ -72,7 +77,7 @@ def test_free_running_T3_matches_reference_fixture(net):
     got_sub = out.cpu()[:, :, :, ::4, ::4]
     e_out = float((got_sub.clamp(-1, 1) - ref_sub.clamp(-1, 1)).abs().max())
     p = [psnr(got_sub[:, i], ref_sub[:, i]) for i in range(T)]
-    _report("free_T3", flow=e_flow, z=e_z, gain=e_g, logit=e_logit, agree=agree, out=e_out, psnr=p)
+    _report("free_T3[%s]" % net.mode_name, flow=e_flow, z=e_z, gain=e_g, logit=e_logit, agree=agree, out=e_out, psnr=p)
     # flows: random GMFlow weights give |flow| up to ~450 px (softmax expectations over 4096 positions);
     # tolerance is relative to that range (fp32 summation-order noise), 2e-4 * max|flow|.
     # logits of frames >= 1 inherit that noise through warp -> hq_encoder: the reference's own fp32-vs-fp64
@@ -103,7 +108,7 @@ def test_stagewise_teacher_forced_T2(net, oracle_T2):
     e_g = float((gains - cap["gains"][0, :, 0]).abs().max())
     e_l = float((logits - cap["logits"][0]).abs().max())
     e_o = float((out - ref_out).abs().max())
-    _report("forced_T2", z=e_z, gain=e_g, logit=e_l, out=e_o, psnr=psnr(out, ref_out))
+    _report("forced_T2[%s]" % net.mode_name, z=e_z, gain=e_g, logit=e_l, out=e_o, psnr=psnr(out, ref_out))
     assert e_z < 2e-3 and e_g < 2e-4 and e_l < 5e-3
     assert e_o < 5e-3 and psnr(out, ref_out) > 70.0
 
@@ -116,7 +121,7 @@ def test_free_running_T2_full_resolution(net, oracle_T2):
     e_f = float((flows - cap["flows"][0]).abs().max())
     agree = float((codes.long() == cap["codes"][0]).float().mean())
     e_o = float((out.clamp(-1, 1) - ref_out.clamp(-1, 1)).abs().max())
-    _report("free_T2", flow=e_f, agree=agree, out=e_o, psnr=psnr(out, ref_out))
+    _report("free_T2[%s]" % net.mode_name, flow=e_f, agree=agree, out=e_o, psnr=psnr(out, ref_out))
     assert e_f < 2e-4 * float(cap["flows"].abs().max())
     assert agree == 1.0
     assert e_o <= 1e-2 and psnr(out, ref_out) >= 50.0

@@ -82,3 +82,31 @@ def test_conv_tcgen05_vs_fp32_kernel_is_fp16_close(lib):
     c = run_conv(lib, x, wt, b, 1, (1, 1, 1, 1), use_tc=1)
     rel = float((a - c).abs().max() / a.abs().max())
     assert rel < 3e-3, rel
+
+
+SPLIT_CASES = [c for c in TC_CASES if c[0] in ("3x3_64_64", "3x3_gn_swish_res_ragged", "up2_128", "linear_splitk", "c16_512_splitk_res",
+                                                "gm_96_96_relu", "qkv_1x1_pre_n2", "persistent_64_64_256sq", "wide_256_256_128sq")]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES, ids=[c[0] for c in SPLIT_CASES])
+def test_conv_tcgen05_split_precision_matches_fp32(lib, case):
+    """use_tc=3: A = Ah + Al, W = Wh + Wl, three MMAs per K step -> must match the *unrounded* fp32 convolution."""
+    name, n, cin, h, w, cout, k, up, pre, pre_act, act, res, bias = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) & 0xFFFF)
+    x = torch.randn((n, cin, h, w), generator=g).cuda()
+    wt = (torch.randn((cout, cin, k, k), generator=g) / math.sqrt(cin * k * k)).cuda()
+    b = torch.randn((cout,), generator=g).cuda() if bias else None
+    prep = None
+    if pre:
+        prep = (1.0 + 0.2 * torch.randn((n, cin), generator=g)).cuda(), (0.2 * torch.randn((n, cin), generator=g)).cuda()
+    pads = (1, 1, 1, 1) if k == 3 else (0, 0, 0, 0)
+    want0 = ref_conv(x.double(), wt.double(), b.double() if b is not None else None, 1, pads, up,
+                     (prep[0].double(), prep[1].double()) if prep else None, pre_act, act, None).float()
+    r = torch.randn(want0.shape, generator=g).cuda() if res else None
+    want = want0 + r if res else want0
+    got = run_conv(lib, x, wt, b, 1, pads, up, prep, pre_act, act, r, use_tc=3)
+    torch.cuda.synchronize()
+    err = float((got - want).abs().max())
+    with open(os.path.join(ROOT, "gpurun_out", "tc_op_report.txt"), "a") as f:
+        f.write("split3 %s err=%.3e max=%.3f\n" % (name, err, float(want.abs().max())))
+    assert err <= 2e-5 * max(1.0, float(want.abs().max())), "%s: max abs err %g" % (name, err)
