@@ -29,6 +29,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 T_CLIP = 20
+# Engine mode benchmarked by default: the fastest one that meets the parity bar (tests/test_gpu_parity.py):
+#   fp32 = exact CUDA-core kernels; tc3 = tcgen05 with split-precision operands (fp32-grade); tc = tcgen05 fp16 operands
+DEFAULT_MODE = "tc3"
+DTYPE_OF = {"fp32": "f32", "tc3": "f16x2 split operands, fp32 accumulate (fp32-grade)", "tc": "f16 operands, fp32 accumulate"}
 
 
 def clip_flops(T):
@@ -137,7 +141,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=T_CLIP)
-    ap.add_argument("--mode", default=os.environ.get("KEEP_BENCH_MODE", "auto"), choices=["auto", "fp32", "tc"])
+    ap.add_argument("--mode", default=os.environ.get("KEEP_BENCH_MODE", "auto"), choices=["auto", "fp32", "tc", "tc3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -163,9 +167,11 @@ def main():
     flags = 0
     mode = args.mode
     if mode == "auto":
-        mode = os.environ.get("KEEP_DEFAULT_MODE", "fp32")
+        mode = os.environ.get("KEEP_DEFAULT_MODE", DEFAULT_MODE)
     if mode == "tc":
         flags |= keep_b200.keep_net.FLAG_TCGEN05
+    elif mode == "tc3":
+        flags |= keep_b200.keep_net.FLAG_TCGEN05 | keep_b200.keep_net.FLAG_TC_SPLIT3
     net = keep_b200.KeepNetB200(flags=flags)
     net.load_state_dict(keep_b200.synth.make_state_dict(seed=0), strict=True)
     net.eval().to(dev)
@@ -272,7 +278,7 @@ def main():
         line = {
             "metric": "512x512 aligned-face frames/sec through keep_net (20-frame clips)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if mode == "fp32" else "f16 (fp32 accumulate)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[mode], "data": "synthetic",
             "config": {"workload": "KEEP general model, %d-frame aligned 512x512 synthetic clip, one clip per GPU per step" % T,
                        "weights": "seeded synthetic (no checkpoint offline)", "engine_mode": mode,
                        "l2": "256 MiB buffer zeroed between timed steps; per-step working set >> 126 MB L2",

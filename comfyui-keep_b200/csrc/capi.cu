@@ -97,6 +97,14 @@ int keep_profile_read(keep_handle h, double* out8) {
     KEEP_API_END
 }
 
+int keep_profile_dump(keep_handle h, const char* path) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h && path, "null argument");
+    h->e->profile_dump(path);
+    return 0;
+    KEEP_API_END
+}
+
 int keep_debug_capture(keep_handle h, int enable) {
     KEEP_API_BEGIN
     KEEP_CHECK(h, "null handle");

@@ -7,7 +7,7 @@
 //   warps 0-3   epilogue      tcgen05.ld TMEM -> registers -> {bias, activation, +residual, cast} -> HBM
 //   warp  4     MMA issuer    one thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and tcgen05.commit
 //   warp  5     weight loader one thread streams pre-packed fp16 weight panels with 1-D TMA (cp.async.bulk)
-//   warps 6-13  A producers   coalesced NHWC loads of the (16+2)x(8+2) input halo, GroupNorm/InstanceNorm
+//   warps 6-21  A producers   coalesced NHWC loads of the (16+2)x(8+2) input halo, GroupNorm/InstanceNorm
 //                             apply + swish/ReLU in registers, fp16 pack, st.shared into the UMMA
 //                             "interleaved" (no-swizzle, K-major) core-matrix layout
 //
@@ -28,14 +28,14 @@
 namespace keep {
 namespace {
 
-constexpr int kThreads = 448;
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 5, kProdWarp0 = 6, kProdThreads = 256;
+constexpr int kThreads = 704;
+constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 5, kProdWarp0 = 6, kProdThreads = 512;   // 16 producer warps
 constexpr int MAX_SA = 4, MAX_SB = 6;  // barrier slots (actual pipeline depths come from the launch arguments)
 constexpr int CB = 64;                 // channels per A stage (4 MMA K-steps of 16)
 constexpr int PLANE3 = 2960;           // bytes per 8-channel plane of a 18x10 halo (2880 padded to 16 mod 128: conflict-free stores)
 constexpr int PLANE1 = 2064;           // bytes per plane of a 128-pixel 1x1 tile (2048 padded likewise)
 constexpr int A_SUB_BYTES = 8 * PLANE3;   // one operand tile (hi); the split-precision mode appends a second (lo) tile
-constexpr int MAXIT = 6;               // ceil(180 * 8 / 256) halo units per producer thread
+constexpr int MAXIT = 3;               // ceil(180 * 8 / 512) halo units per producer thread
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -106,18 +106,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
            ((uint64_t)1 << 46);
 }
 
-__device__ __forceinline__ float fast_act(float v, int act) {
-    switch (act) {
-        case ACT_SWISH: {   // x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU op
-            float t;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
-            return 0.5f * v * (1.0f + t);
-        }
-        case ACT_RELU: return fmaxf(v, 0.0f);
-        case ACT_LRELU02: return v > 0.0f ? v : 0.2f * v;
-        default: return apply_act(v, act);
-    }
+// The kernel's code footprint matters: five warp roles run different code at once and the SM's instruction cache
+// is small (a first version that inlined the generic activation switch 48x ran 10x slower, stalled on fetch).
+// Producer prologue activations are only ever swish (VQGAN) or ReLU (GMFlow); everything else is out of line.
+template <bool EXACT>
+__device__ __forceinline__ float swish_f(float v) {
+    if (EXACT) return v / (1.0f + __expf(-v));
+    float t;   // x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU op
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+    return 0.5f * v * (1.0f + t);
 }
+__device__ __noinline__ float act_slow(float v, int act) { return apply_act(v, act); }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
@@ -126,7 +125,7 @@ __device__ __forceinline__ float fast_act(float v, int act) {
 // PASSES = 3: split-precision: A = Ah + Al, W = Wh + Wl (fp16 pairs, ~22 mantissa bits), D += Ah*Wh + Ah*Wl + Al*Wh
 //             with fp32 accumulation in TMEM -> fp32-grade results on the tensor cores (the "decision path" needs
 //             this: one flipped argmax over the 1024 code logits changes a 32x32-pixel block).
-template <int PASSES>
+template <int PASSES, bool IN_F16>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -183,16 +182,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 
     if (warp >= kProdWarp0) {
         // =========================== A producers ===========================
-        const int pt = threadIdx.x - kProdWarp0 * 32;       // 0..255
+        const int pt = threadIdx.x - kProdWarp0 * 32;       // 0..511
         const int pl = pt & 7;                              // 8-channel plane handled by this thread
         const int Hl = a.h * a.up, Wl = a.w * a.up;
         const int npix = conv3 ? 180 : 128;
         const int cin = a.c0 + a.c1;
+        const int ushift = a.up - 1;
+        // halo units of this thread: pixel p = p_first + it*64 -> (row, col) within the 18x10 halo; tile independent
+        const int p_first = pt >> 3;
+        int hy[MAXIT], hx[MAXIT];
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int p = p_first + it * (kProdThreads / 8);
+            hy[it] = p / 10;
+            hx[it] = p - hy[it] * 10;
+        }
         int stage = 0, phase = 0;
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
             int nt, img, ty, tx, ks;
             decode(w, nt, img, ty, tx, ks);
             const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
+            const int oy0 = ty * 16 - 1, ox0 = tx * 8 - 1;
             for (int cb = cb0; cb < cb1; ++cb) {
                 const int ch = cb * CB + pl * 8;            // first of this thread's 8 channels (global, concat space)
                 const bool ch_ok = ch < cin;
@@ -204,37 +214,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
                     sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
                 }
-                const void* src; int sdt, sc_ch, cc;
-                if (ch < a.c0) { src = a.in0; sdt = a.in0_dt; sc_ch = a.c0; cc = ch; }
-                else { src = a.in1; sdt = a.in1_dt; sc_ch = a.c1; cc = ch - a.c0; }
+                const uint8_t* src; int sc_ch, cc;
+                if (ch < a.c0) { src = reinterpret_cast<const uint8_t*>(a.in0); sc_ch = a.c0; cc = ch; }
+                else { src = reinterpret_cast<const uint8_t*>(a.in1); sc_ch = a.c1; cc = ch - a.c0; }
+                constexpr int ESZ = IN_F16 ? 2 : 4;
                 // ---- issue every global load of this stage first (memory-level parallelism), then transform
-                uint4 raw[MAXIT][2];
+                uint4 raw[MAXIT][IN_F16 ? 1 : 2];
                 bool okv[MAXIT];
-                const int p_first = pt >> 3;
 #pragma unroll
                 for (int it = 0; it < MAXIT; ++it) {
                     const int p = p_first + it * (kProdThreads / 8);
                     bool ok = ch_ok && p < npix;
-                    size_t pix = 0;
+                    size_t pix;
                     if (conv3) {
-                        const int hy = p / 10, hx = p - hy * 10;
-                        const int iy = ty * 16 + hy - 1, ix = tx * 8 + hx - 1;
+                        const int iy = oy0 + hy[it], ix = ox0 + hx[it];
                         ok = ok && iy >= 0 && iy < Hl && ix >= 0 && ix < Wl;
-                        pix = ((size_t)img * a.h + (iy >> (a.up - 1))) * a.w + (ix >> (a.up - 1));
+                        pix = ((size_t)img * a.h + (iy >> ushift)) * a.w + (ix >> ushift);
                     } else {
-                        const long long q = ((long long)ty * 16) * 8 + p;     // pixel index within the image
+                        const long long q = (long long)ty * 128 + p;     // pixel index within the image
                         ok = ok && q < (long long)a.h * a.w;
                         pix = (size_t)img * a.h * a.w + (size_t)q;
                     }
                     okv[it] = ok;
                     if (ok) {
-                        if (sdt == F32) {
-                            const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(src) + pix * sc_ch + cc);
-                            raw[it][0] = g[0];
-                            raw[it][1] = g[1];
-                        } else {
-                            raw[it][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + pix * sc_ch + cc);
-                        }
+                        const uint4* g = reinterpret_cast<const uint4*>(src + (pix * sc_ch + cc) * ESZ);
+                        raw[it][0] = g[0];
+                        if (!IN_F16) raw[it][1] = g[1];
                     }
                 }
                 mbar_wait(A_EMPTY(stage), phase ^ 1);
@@ -243,11 +248,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 for (int it = 0; it < MAXIT; ++it) {
                     const int p = p_first + it * (kProdThreads / 8);
                     if (p >= npix) continue;
-                    float v[8];
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = make_uint4(0u, 0u, 0u, 0u);
                     if (okv[it]) {
-                        if (sdt == F32) {
+                        float v[8];
+                        if (!IN_F16) {
                             const float* f0 = reinterpret_cast<const float*>(&raw[it][0]);
-                            const float* f1 = reinterpret_cast<const float*>(&raw[it][1]);
+                            const float* f1 = reinterpret_cast<const float*>(&raw[it][IN_F16 ? 0 : 1]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) { v[j] = f0[j]; v[4 + j] = f1[j]; }
                         } else {
@@ -259,29 +265,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
                         }
-                        if (a.pre_act != ACT_NONE) {
+                        __half2 hq[4];
+                        if (PASSES == 3) {
+                            if (a.pre_act == ACT_SWISH) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = PASSES == 3 ? apply_act(v[j], a.pre_act) : fast_act(v[j], a.pre_act);
+                                for (int j = 0; j < 8; ++j) v[j] = swish_f<true>(v[j]);
+                            } else if (a.pre_act == ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                            __half2 lq[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {   // residual (lo) tile: v - float(fp16(v))
+                                const float2 r = __half22float2(hq[j]);
+                                lq[j] = __floats2half2_rn(v[2 * j] - r.x, v[2 * j + 1] - r.y);
+                            }
+                            ol.x = *reinterpret_cast<uint32_t*>(&lq[0]); ol.y = *reinterpret_cast<uint32_t*>(&lq[1]);
+                            ol.z = *reinterpret_cast<uint32_t*>(&lq[2]); ol.w = *reinterpret_cast<uint32_t*>(&lq[3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                            if (a.pre_act == ACT_SWISH) {   // packed: x*sigmoid(x) = h + h*tanh(h), h = x/2 (one MUFU per 2 elements)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const __half2 hh = __hmul2(hq[j], __float2half2_rn(0.5f));
+                                    uint32_t t, hi = *reinterpret_cast<const uint32_t*>(&hh);
+                                    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(hi));
+                                    hq[j] = __hfma2(hh, *reinterpret_cast<__half2*>(&t), hh);
+                                }
+                            } else if (a.pre_act == ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) hq[j] = __hmax2(hq[j], __float2half2_rn(0.0f));
+                            }
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+                        o.x = *reinterpret_cast<uint32_t*>(&hq[0]); o.y = *reinterpret_cast<uint32_t*>(&hq[1]);
+                        o.z = *reinterpret_cast<uint32_t*>(&hq[2]); o.w = *reinterpret_cast<uint32_t*>(&hq[3]);
                     }
-                    uint4 o;
-                    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-                    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
-                    o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-                    o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
                     *reinterpret_cast<uint4*>(dst + p * 16) = o;
-                    if (PASSES == 3) {   // residual (lo) tile: v - float(fp16(v))
-                        const float2 r0 = __half22float2(h0), r1 = __half22float2(h1), r2 = __half22float2(h2), r3 = __half22float2(h3);
-                        __half2 l0 = __floats2half2_rn(v[0] - r0.x, v[1] - r0.y), l1 = __floats2half2_rn(v[2] - r1.x, v[3] - r1.y);
-                        __half2 l2 = __floats2half2_rn(v[4] - r2.x, v[5] - r2.y), l3 = __floats2half2_rn(v[6] - r3.x, v[7] - r3.y);
-                        uint4 ol;
-                        ol.x = *reinterpret_cast<uint32_t*>(&l0); ol.y = *reinterpret_cast<uint32_t*>(&l1);
-                        ol.z = *reinterpret_cast<uint32_t*>(&l2); ol.w = *reinterpret_cast<uint32_t*>(&l3);
-                        *reinterpret_cast<uint4*>(dst + A_SUB_BYTES + p * 16) = ol;
-                    }
+                    if (PASSES == 3) *reinterpret_cast<uint4*>(dst + A_SUB_BYTES + p * 16) = ol;
                 }
                 fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
                 mbar_arrive(A_FULL(stage));
@@ -404,9 +427,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                                 v[4 * e] += b.x; v[4 * e + 1] += b.y; v[4 * e + 2] += b.z; v[4 * e + 3] += b.w;
                             }
                         }
-                        if (a.act != ACT_NONE) {
+                        if (a.act == ACT_RELU) {
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], a.act);
+                            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
+                        } else if (a.act != ACT_NONE) {
+#pragma unroll 1
+                            for (int e = 0; e < 16; ++e) v[e] = act_slow(v[e], a.act);
                         }
                         if (a.res) {
                             if (a.res_dt == F32) {
@@ -591,16 +617,25 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     const size_t smem = 128 + (size_t)t.sa_stages * nop * A_SUB_BYTES + (size_t)t.sb_stages * nop * bn * 128 +
                         8 * (2 * MAX_SA + 2 * MAX_SB + 4) + 16;
     KEEP_CHECK(smem <= 227 * 1024, "conv2d_tc: %zu bytes of shared memory", smem);
+    KEEP_CHECK(a.c1 == 0 || a.in0_dt == a.in1_dt, "conv2d_tc: concatenated sources must share a dtype");
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     const long long total = (long long)t.n * t.tiles_y * t.tiles_x * t.ntile_n * splitk;
     const int grid = (int)std::min<long long>(total, num_sms);
-    if (passes == 3) conv_tc_kernel<3><<<grid, kThreads, smem, s>>>(t);
-    else conv_tc_kernel<1><<<grid, kThreads, smem, s>>>(t);
+    const bool f16 = a.in0_dt == F16;
+    if (passes == 3) {
+        if (f16) conv_tc_kernel<3, true><<<grid, kThreads, smem, s>>>(t);
+        else conv_tc_kernel<3, false><<<grid, kThreads, smem, s>>>(t);
+    } else {
+        if (f16) conv_tc_kernel<1, true><<<grid, kThreads, smem, s>>>(t);
+        else conv_tc_kernel<1, false><<<grid, kThreads, smem, s>>>(t);
+    }
     CUDA_CHECK(cudaGetLastError());
     if (splitk > 1) splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);
 }

@@ -310,6 +310,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             pr.bytes = (double)x.bytes() + (o.in1 ? (double)o.in1->bytes() : 0.0) + (double)out.bytes() +
                        (o.res ? (double)o.res->bytes() : 0.0) + (use_tc ? 2.0 * (tc_passes_ == 3 ? 2 : 1) : 4.0) * cw.cout * cw.kh * cw.kw * cw.cin;
             pr.tag = use_tc ? 1 : 0;
+            pr.m = (int)out.rows(); pr.k = cw.kh * cw.kw * cw.cin; pr.n = cw.cout; pr.kh = cw.kh * 10 + o.stride; pr.splitk = a.splitk; pr.bn = bn;
             CUDA_CHECK(cudaEventRecord(pr.a, s_));
         }
         if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_), bn, tc_passes_, a.splitk, a.partial, num_sms_, s_);
@@ -1117,6 +1118,19 @@ void Engine::profile_read(double* out8) {
         double* o = out8 + (p.tag ? 4 : 0);
         o[0] += 1.0; o[1] += ms; o[2] += p.flops * 1e-9; o[3] += p.bytes * 1e-9;
     }
+}
+
+void Engine::profile_dump(const char* path) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    FILE* f = fopen(path, "w");
+    KEEP_CHECK(f, "cannot open %s", path);
+    fprintf(f, "tag,M,K,N,kh_stride,splitk,bn,ms,gflop\n");
+    for (auto& p : prof_) {
+        float ms = 0.0f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, p.a, p.b));
+        fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%.6f,%.4f\n", p.tag, p.m, p.k, p.n, p.kh, p.splitk, p.bn, ms, p.flops * 1e-9);
+    }
+    fclose(f);
 }
 
 // =============================================================================================

@@ -57,6 +57,7 @@ class Engine {
     // per-launch CUDA-event timing of the conv/GEMM kernel family (bench.py roofline)
     void set_profile(bool on);
     void profile_read(double* out8);
+    void profile_dump(const char* path);
     int device() const { return device_; }
     long long launches() const { return launches_; }
 
@@ -123,7 +124,7 @@ class Engine {
     std::unordered_map<std::string, Cap> forced_;   // device buffers with forced values
     bool capture_ = false;
     bool profile_ = false;
-    struct Prof { cudaEvent_t a, b; double flops, bytes; int tag; };
+    struct Prof { cudaEvent_t a, b; double flops, bytes; int tag; int m, k, n, kh, splitk, bn; };
     std::vector<Prof> prof_;
     std::vector<cudaEvent_t> ev_pool_;
     cudaEvent_t get_event();

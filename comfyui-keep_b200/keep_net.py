@@ -66,6 +66,7 @@ def load_library():
     lib.keep_launch_count.restype = ctypes.c_longlong
     lib.keep_profile_enable.argtypes = [vp, ci]
     lib.keep_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    lib.keep_profile_dump.argtypes = [vp, ctypes.c_char_p]
     lib.keep_debug_capture.argtypes = [vp, ci]
     lib.keep_debug_force.argtypes = [vp, ctypes.c_char_p, vp, cs]
     lib.keep_debug_read.argtypes = [vp, ctypes.c_char_p, vp, cs]
@@ -251,6 +252,10 @@ class KeepNetB200(nn.Module):
         _check(lib, lib.keep_profile_read(self._engine, buf), "keep_profile_read")
         keys = ("launches", "ms", "gflop", "gbytes")
         return {"cuda_core": dict(zip(keys, buf[0:4])), "tcgen05": dict(zip(keys, buf[4:8]))}
+
+    def profile_dump(self, path):
+        lib = load_library()
+        _check(lib, lib.keep_profile_dump(self._engine, path.encode()), "keep_profile_dump")
 
     def debug_capture(self, on=True):
         lib = load_library()

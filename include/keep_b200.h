@@ -74,6 +74,7 @@ long long keep_launch_count(keep_handle h);
  * same four numbers for the tcgen05 path.  Reading synchronises the device and keeps the samples. */
 int keep_profile_enable(keep_handle h, int enable);
 int keep_profile_read(keep_handle h, double* out8);
+int keep_profile_dump(keep_handle h, const char* csv_path); /* one row per conv/GEMM launch: shape, ms */
 
 /* ---- test hooks (stage-wise teacher forcing and intermediate capture; tests/ only) -------------
  * what ∈ {"flows" (T-1,512,512,2) f32, "z_codes" (T,16,16,256) f32 NHWC, "gains" (T,256) f32,
