@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--frames", type=int, default=T_CLIP)
     ap.add_argument("--mode", default=os.environ.get("KEEP_BENCH_MODE", "auto"), choices=["auto", "fp32", "tc", "tc3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying the per-clip CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,6 +173,8 @@ def main():
         flags |= keep_b200.keep_net.FLAG_TCGEN05
     elif mode == "tc3":
         flags |= keep_b200.keep_net.FLAG_TCGEN05 | keep_b200.keep_net.FLAG_TC_SPLIT3
+    if not args.no_graph:
+        flags |= keep_b200.keep_net.FLAG_CUDA_GRAPH
     net = keep_b200.KeepNetB200(flags=flags)
     net.load_state_dict(keep_b200.synth.make_state_dict(seed=0), strict=True)
     net.eval().to(dev)
@@ -281,6 +284,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[mode], "data": "synthetic",
             "config": {"workload": "KEEP general model, %d-frame aligned 512x512 synthetic clip, one clip per GPU per step" % T,
                        "weights": "seeded synthetic (no checkpoint offline)", "engine_mode": mode,
+                       "cuda_graph": not args.no_graph,
                        "l2": "256 MiB buffer zeroed between timed steps; per-step working set >> 126 MB L2",
                        "collective": "NCCL gather of fp16 decoded frames to rank 0" if world > 1 else "none"},
             "clocks": clocks, "gpu_launches": int(launches),

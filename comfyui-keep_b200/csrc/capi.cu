@@ -165,6 +165,11 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
     a.ho = (h * up + pad_t + pad_b - kh) / stride + 1;
     a.wo = (w * up + pad_l + pad_r - kw) / stride + 1;
     a.act = act; a.res = res_dev; a.out = out_dev;
+    if (use_tc == 4) {   // bandwidth-bound stem / head kernels
+        conv2d_small(a, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        return 0;
+    }
     if (use_tc) {
         int rc = keepop_conv2d_tc(a, weight_host, use_tc == 3 ? 3 : 1, s);
         CUDA_CHECK(cudaStreamSynchronize(s));

@@ -1,0 +1,166 @@
+// keep_b200 — the two memory-bound ends of the VQGAN / GMFlow stacks, which have no tensor-core shape:
+//   * stems:  Cin = 3  -> 64  (3x3 s1 p1: vqgan_arch.py:260-261 ; 7x7 s2 p3: gmflow/backbone.py:50)
+//   * heads:  Cin = 64 -> 3   (3x3 s1 p1 after GroupNorm: vqgan_arch.py:333-335)
+// Both are bandwidth problems (K = 27 / 147, or N = 3): one pass over the big 512x512 tensor, fp32 math.
+#include "ops.h"
+
+namespace keep {
+namespace {
+
+__device__ __forceinline__ float ld1(const void* p, int dt, size_t i) {
+    return dt == F32 ? reinterpret_cast<const float*>(p)[i] : __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+
+// ---- stem: thread = (output pixel, group of 16 output channels); weights [KS*KS*3][64] in shared memory
+template <int KS, int STRIDE>
+__global__ void __launch_bounds__(256) conv_cin3_kernel(const void* __restrict__ in, int in_dt, int n, int h, int w, int pad,
+                                                        const float* __restrict__ wt, const float* __restrict__ bias, int ho, int wo,
+                                                        void* __restrict__ out, int out_dt) {
+    constexpr int K = KS * KS * 3;
+    __shared__ __align__(16) float sw[K * 64];
+    for (int i = threadIdx.x; i < K * 64; i += 256) sw[i] = wt[i];
+    __syncthreads();
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long pix = gid >> 2;
+    const int grp = (int)(gid & 3);
+    if (pix >= (long long)n * ho * wo) return;
+    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), img = (int)(pix / ((long long)wo * ho));
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = bias ? bias[grp * 16 + j] : 0.0f;
+    const int iy0 = oy * STRIDE - pad, ix0 = ox * STRIDE - pad;
+#pragma unroll 1
+    for (int ky = 0; ky < KS; ++ky) {
+        const int iy = iy0 + ky;
+        if (iy < 0 || iy >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+            const int ix = ix0 + kx;
+            if (ix < 0 || ix >= w) continue;
+            const size_t base = (((size_t)img * h + iy) * w + ix) * 3;
+            const float x0 = ld1(in, in_dt, base), x1 = ld1(in, in_dt, base + 1), x2 = ld1(in, in_dt, base + 2);
+            const float4* w0 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 0) * 64 + grp * 16);
+            const float4* w1 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 1) * 64 + grp * 16);
+            const float4* w2 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 2) * 64 + grp * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 a = w0[q], b = w1[q], c = w2[q];
+                acc[4 * q + 0] = fmaf(x0, a.x, fmaf(x1, b.x, fmaf(x2, c.x, acc[4 * q + 0])));
+                acc[4 * q + 1] = fmaf(x0, a.y, fmaf(x1, b.y, fmaf(x2, c.y, acc[4 * q + 1])));
+                acc[4 * q + 2] = fmaf(x0, a.z, fmaf(x1, b.z, fmaf(x2, c.z, acc[4 * q + 2])));
+                acc[4 * q + 3] = fmaf(x0, a.w, fmaf(x1, b.w, fmaf(x2, c.w, acc[4 * q + 3])));
+            }
+        }
+    }
+    const size_t o = (size_t)pix * 64 + grp * 16;
+    if (out_dt == F32) {
+        float4* po = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) po[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            st4(reinterpret_cast<__half*>(out), o + 4 * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+    }
+}
+
+// ---- head: 3x3 s1 p1, Cin % 16 == 0, Cout <= 4.  Block = 32x8 output pixels, one thread per pixel; the input halo is
+// staged through shared memory 16 channels at a time with the GroupNorm affine applied; weights [9][cin][4] in smem.
+constexpr int HT_W = 32, HT_H = 8, HC = 16, HPITCH = 20;   // channel pitch 20 floats: conflict-free float4 reads
+__global__ void __launch_bounds__(256) conv_cout4_kernel(const void* __restrict__ in, int in_dt, int n, int h, int w, int cin,
+                                                         const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
+                                                         const float* __restrict__ wt /*[9*cin][cout]*/, const float* __restrict__ bias,
+                                                         int cout, float* __restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    float* sw = sm;                                   // [9][cin][4]
+    float* sx = sm + 9 * cin * 4;                     // [(HT_H+2)*(HT_W+2)][HPITCH]
+    for (int i = threadIdx.x; i < 9 * cin * 4; i += 256) {
+        const int c = i & 3, k = i >> 2;
+        sw[i] = c < cout ? wt[(size_t)k * cout + c] : 0.0f;
+    }
+    const int tiles_x = (w + HT_W - 1) / HT_W, tiles_y = (h + HT_H - 1) / HT_H;
+    const int img = blockIdx.x / (tiles_x * tiles_y);
+    const int t = blockIdx.x - img * tiles_x * tiles_y;
+    const int ty0 = (t / tiles_x) * HT_H, tx0 = (t % tiles_x) * HT_W;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int HALO = (HT_H + 2) * (HT_W + 2);
+    for (int c0 = 0; c0 < cin; c0 += HC) {
+        __syncthreads();
+        for (int u = threadIdx.x; u < HALO * (HC / 4); u += 256) {
+            const int p = u >> 2, q = u & 3;
+            const int hy = p / (HT_W + 2), hx = p - hy * (HT_W + 2);
+            const int iy = ty0 + hy - 1, ix = tx0 + hx - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+                const size_t off = (((size_t)img * h + iy) * w + ix) * cin + c0 + q * 4;
+                v = in_dt == F32 ? ld4(reinterpret_cast<const float*>(in), off) : ld4(reinterpret_cast<const __half*>(in), off);
+                if (pre_scale) {
+                    const float4 s = *reinterpret_cast<const float4*>(pre_scale + (size_t)img * cin + c0 + q * 4);
+                    const float4 b = *reinterpret_cast<const float4*>(pre_shift + (size_t)img * cin + c0 + q * 4);
+                    v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+                }
+            }
+            *reinterpret_cast<float4*>(sx + p * HPITCH + q * 4) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const float* xp = sx + ((ly + tap / 3) * (HT_W + 2) + lx + tap % 3) * HPITCH;
+            const float4* wp = reinterpret_cast<const float4*>(sw + (tap * cin + c0) * 4);
+#pragma unroll
+            for (int q = 0; q < HC / 4; ++q) {
+                const float4 x = *reinterpret_cast<const float4*>(xp + q * 4);
+                const float4 w0 = wp[q * 4 + 0], w1 = wp[q * 4 + 1], w2 = wp[q * 4 + 2], w3 = wp[q * 4 + 3];
+                acc[0] = fmaf(x.x, w0.x, fmaf(x.y, w1.x, fmaf(x.z, w2.x, fmaf(x.w, w3.x, acc[0]))));
+                acc[1] = fmaf(x.x, w0.y, fmaf(x.y, w1.y, fmaf(x.z, w2.y, fmaf(x.w, w3.y, acc[1]))));
+                acc[2] = fmaf(x.x, w0.z, fmaf(x.y, w1.z, fmaf(x.z, w2.z, fmaf(x.w, w3.z, acc[2]))));
+                acc[3] = fmaf(x.x, w0.w, fmaf(x.y, w1.w, fmaf(x.z, w2.w, fmaf(x.w, w3.w, acc[3]))));
+            }
+        }
+    }
+    const int oy = ty0 + ly, ox = tx0 + lx;
+    if (oy < h && ox < w) {
+        const size_t o = (((size_t)img * h + oy) * w + ox) * cout;
+        for (int c = 0; c < cout; ++c) out[o + c] = acc[c] + (bias ? bias[c] : 0.0f);
+    }
+}
+}  // namespace
+
+bool conv_small_eligible(const ConvArgs& a) {
+    const int cin = a.c0 + a.c1;
+    if (a.c1 != 0 || a.up != 1 || a.res != nullptr || a.act != ACT_NONE) return false;
+    if (cin == 3 && a.cout == 64 && a.pre_scale == nullptr && a.pre_act == ACT_NONE) {
+        if (a.kh == 3 && a.kw == 3 && a.stride == 1 && a.pad_t == 1 && a.pad_l == 1) return true;
+        if (a.kh == 7 && a.kw == 7 && a.stride == 2 && a.pad_t == 3 && a.pad_l == 3) return true;
+        return false;
+    }
+    if (a.cout <= 4 && cin % 16 == 0 && cin <= 128 && a.kh == 3 && a.kw == 3 && a.stride == 1 && a.pad_t == 1 && a.pad_l == 1 &&
+        a.pre_act == ACT_NONE && a.out_dt == F32 && a.ho == a.h && a.wo == a.w)
+        return true;
+    return false;
+}
+
+void conv2d_small(const ConvArgs& a, cudaStream_t s) {
+    KEEP_CHECK(conv_small_eligible(a), "conv2d_small: not eligible");
+    const int cin = a.c0 + a.c1;
+    if (cin == 3) {
+        const long long threads = (long long)a.n * a.ho * a.wo * 4;
+        const unsigned grid = (unsigned)((threads + 255) / 256);
+        if (a.kh == 3) conv_cin3_kernel<3, 1><<<grid, 256, 0, s>>>(a.in0, a.in0_dt, a.n, a.h, a.w, 1, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);
+        else conv_cin3_kernel<7, 2><<<grid, 256, 0, s>>>(a.in0, a.in0_dt, a.n, a.h, a.w, 3, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);
+    } else {
+        const int tiles = ((a.w + HT_W - 1) / HT_W) * ((a.h + HT_H - 1) / HT_H);
+        const size_t smem = (size_t)(9 * cin * 4 + (HT_H + 2) * (HT_W + 2) * HPITCH) * sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(conv_cout4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            configured = true;
+        }
+        conv_cout4_kernel<<<a.n * tiles, 256, smem, s>>>(a.in0, a.in0_dt, a.n, a.h, a.w, cin, a.pre_scale, a.pre_shift, a.wt, a.bias,
+                                                         a.cout, (float*)a.out);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace keep

@@ -231,6 +231,10 @@ Engine::~Engine() {
     for (auto& kv : cap_) cudaFree(kv.second.p);
     for (auto& kv : forced_) cudaFree(kv.second.p);
     for (auto& kv : tcw_) cudaFree(kv.second.p);
+    for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
+    cudaFree(gx_);
+    cudaFree(gout_);
+    if (gs_) { cudaStreamDestroy(gs_); cudaEventDestroy(ev_in_); cudaEventDestroy(ev_out_); }
     for (auto& p : prof_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& e : ev_pool_) cudaEventDestroy(e);
 }
@@ -287,7 +291,8 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         a.res = o.res->p; a.res_dt = o.res->dt;
     }
     a.out = out.p; a.out_dt = out.dt;
-    const bool use_tc = (flags_ & KEEP_FLAG_TCGEN05) && !o.exact && tc_eligible(a);
+    const bool use_small = conv_small_eligible(a);
+    const bool use_tc = !use_small && (flags_ & KEEP_FLAG_TCGEN05) && !o.exact && tc_eligible(a);
     int bn = 0;
     void* part = nullptr;
     if (use_tc) {
@@ -296,7 +301,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         bn = tc_pick_bn(cw.cout, m_tiles, tc_passes_);
         a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), (cw.cin + 63) / 64);
     } else {
-        a.splitk = conv_pick_splitk(a);
+        a.splitk = use_small ? 1 : conv_pick_splitk(a);
     }
     if (a.splitk > 1) {
         part = arena_.alloc((size_t)a.splitk * out.numel() * sizeof(float));
@@ -314,6 +319,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             CUDA_CHECK(cudaEventRecord(pr.a, s_));
         }
         if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_), bn, tc_passes_, a.splitk, a.partial, num_sms_, s_);
+        else if (use_small) conv2d_small(a, s_);
         else conv2d_simt(a, s_);
         launches_ += a.splitk > 1 ? 2 : 1;
         if (profile_) {
@@ -1074,6 +1080,8 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
             CUDA_CHECK(cudaStreamSynchronize(s));
             cudaFree(own_ws_);
             own_ws_ = nullptr; own_ws_bytes_ = 0;
+            for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
+            graphs_.clear();
             CUDA_CHECK(cudaMalloc(&own_ws_, need));
             own_ws_bytes_ = need;
         }
@@ -1082,9 +1090,65 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
     KEEP_CHECK(ws_bytes >= need, "keep_forward: workspace too small (%zu < %zu)", ws_bytes, need);
     KEEP_CHECK(((uintptr_t)ws & 255) == 0, "keep_forward: workspace must be 256-byte aligned");
     const size_t per_clip = (size_t)T * 3 * 512 * 512;
+    const size_t osz = out_dtype == KEEP_OUT_F16 ? 2 : 4;
+    bool forcing = false;
+    for (auto& kv : forced_) forcing = forcing || kv.second.p != nullptr;
+    const bool want_graph = (flags_ & KEEP_FLAG_CUDA_GRAPH) && !capture_ && !profile_ && !forcing && ws == own_ws_;
     for (int bi = 0; bi < b; ++bi) {   // clips are independent (keep_processor.py:263-270)
-        begin(ws, ws_bytes, s, false);
-        forward_clip(x_dev + bi * per_clip, T, (char*)out_dev + bi * per_clip * (out_dtype == KEEP_OUT_F16 ? 2 : 4), out_dtype);
+        const float* xin = x_dev + bi * per_clip;
+        char* xout = (char*)out_dev + bi * per_clip * osz;
+        if (want_graph && eager_runs_[T] >= 1) {
+            // static staging buffers so the captured graph's pointers stay valid across calls
+            if (gx_bytes_ < per_clip * 4 || gout_bytes_ < per_clip * 4) {
+                CUDA_CHECK(cudaStreamSynchronize(s));
+                cudaFree(gx_); cudaFree(gout_);
+                for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
+                graphs_.clear();
+                CUDA_CHECK(cudaMalloc((void**)&gx_, per_clip * 4));
+                CUDA_CHECK(cudaMalloc(&gout_, per_clip * 4));
+                gx_bytes_ = gout_bytes_ = per_clip * 4;
+            }
+            // the caller's stream may be the legacy default stream, which cannot be captured: the graph lives on an
+            // engine-owned non-blocking stream, ordered against the caller's stream with events
+            if (!gs_) {
+                CUDA_CHECK(cudaStreamCreateWithFlags(&gs_, cudaStreamNonBlocking));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ev_out_, cudaEventDisableTiming));
+            }
+            ClipGraph& g = graphs_[T];
+            if (g.exec && (g.ws != ws || g.out_dtype != out_dtype)) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            CUDA_CHECK(cudaEventRecord(ev_in_, s));
+            CUDA_CHECK(cudaStreamWaitEvent(gs_, ev_in_, 0));
+            if (!g.exec) {
+                cudaGraph_t graph = nullptr;
+                CUDA_CHECK(cudaStreamBeginCapture(gs_, cudaStreamCaptureModeThreadLocal));
+                try {
+                    begin(ws, ws_bytes, gs_, false);
+                    forward_clip(gx_, T, gout_, out_dtype);
+                } catch (...) {
+                    cudaStreamEndCapture(gs_, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                CUDA_CHECK(cudaStreamEndCapture(gs_, &graph));
+                cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                CUDA_CHECK(e);
+                g.ws = ws; g.out_dtype = out_dtype;
+            }
+            CUDA_CHECK(cudaMemcpyAsync(gx_, xin, per_clip * 4, cudaMemcpyDeviceToDevice, gs_));
+            CUDA_CHECK(cudaGraphLaunch(g.exec, gs_));
+            CUDA_CHECK(cudaMemcpyAsync(xout, gout_, per_clip * osz, cudaMemcpyDeviceToDevice, gs_));
+            CUDA_CHECK(cudaEventRecord(ev_out_, gs_));
+            CUDA_CHECK(cudaStreamWaitEvent(s, ev_out_, 0));
+            launches_ += launches_per_clip_[T];
+        } else {
+            const long long l0 = launches_;
+            begin(ws, ws_bytes, s, false);
+            forward_clip(xin, T, xout, out_dtype);
+            launches_per_clip_[T] = launches_ - l0;
+            eager_runs_[T] += 1;
+        }
     }
 }
 

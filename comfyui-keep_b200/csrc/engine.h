@@ -118,6 +118,13 @@ class Engine {
     const __half* tc_weights(const ConvW& cw, int bn, int passes);
     int tc_passes_ = 1;   // 1: fp16 operands; 3: split-precision (fp32-grade) tensor-core mode
     int num_sms_ = 148;
+    // CUDA graph of one clip forward (KEEP_FLAG_CUDA_GRAPH): ~1800 launches per frame collapse into one graph launch
+    struct ClipGraph { cudaGraphExec_t exec = nullptr; void* ws = nullptr; int out_dtype = 0; };
+    std::unordered_map<int, ClipGraph> graphs_;   // keyed by T
+    float* gx_ = nullptr; void* gout_ = nullptr; size_t gx_bytes_ = 0, gout_bytes_ = 0;   // static in/out staging for replays
+    cudaStream_t gs_ = nullptr; cudaEvent_t ev_in_ = nullptr, ev_out_ = nullptr;
+    std::unordered_map<int, long long> launches_per_clip_;
+    std::unordered_map<int, int> eager_runs_;     // per T: eager forwards done (weights packed, allocations warmed)
     // debug capture / forcing
     struct Cap { void* p = nullptr; size_t bytes = 0; };
     std::unordered_map<std::string, Cap> cap_;      // device buffers holding last forward's intermediates

@@ -30,6 +30,9 @@ struct ConvArgs {
 void conv2d_simt(const ConvArgs& a, cudaStream_t s);
 // picks split-K for small-M layers; `scratch` must hold conv_splitk_scratch_floats(a) floats when splitk>1
 int conv_pick_splitk(const ConvArgs& a);
+// bandwidth-bound ends of the conv stacks: Cin = 3 stems (3x3 s1, 7x7 s2) and Cout <= 4 heads (3x3 s1)
+bool conv_small_eligible(const ConvArgs& a);
+void conv2d_small(const ConvArgs& a, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------
 // batched strided GEMM (fp32), used for attention scores / PV

@@ -29,6 +29,7 @@ KEEP_GENERAL_CFG = dict(  # modules/utils.py:42-57 (+ defaults :76-90): the conf
 FLAG_FP16_FEATURES = 1
 FLAG_TCGEN05 = 2
 FLAG_TC_SPLIT3 = 4
+FLAG_CUDA_GRAPH = 8
 FLAG_PLAN_ONLY = 256
 
 

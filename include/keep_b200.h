@@ -40,6 +40,7 @@ enum {
     KEEP_FLAG_FP16_FEATURES = 1, /* store conv feature maps as fp16 in HBM */
     KEEP_FLAG_TCGEN05 = 2,       /* run eligible convolutions / GEMMs on the tcgen05 tensor-core kernel */
     KEEP_FLAG_TC_SPLIT3 = 4,     /* with TCGEN05: split-precision operands (A=Ah+Al, W=Wh+Wl, 3 MMAs) -> fp32-grade results */
+    KEEP_FLAG_CUDA_GRAPH = 8,    /* capture one clip forward per T into a CUDA graph after the first (eager) call and replay it */
     KEEP_FLAG_PLAN_ONLY = 256    /* host-side planning only (strict key check + workspace sizing); keep_forward fails */
 };
 

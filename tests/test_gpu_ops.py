@@ -198,3 +198,29 @@ def test_argmax_gather_matches_torch(lib):
     mask = torch.ones(256, dtype=torch.bool, device="cuda"); mask[5] = False
     assert torch.equal(idx.long()[mask], want[mask])
     assert torch.equal(quant, cb[idx.long()])
+
+
+SMALL_CASES = [
+    # name, n, cin, h, w, cout, k, stride, pad, pre
+    ("stem_3x3", 2, 3, 96, 80, 64, 3, 1, 1, False),
+    ("gm_stem_7x7_s2", 2, 3, 96, 64, 64, 7, 2, 3, False),
+    ("head_64_3_gn", 2, 64, 72, 50, 3, 3, 1, 1, True),
+    ("head_64_3_full", 1, 64, 512, 512, 3, 3, 1, 1, True),
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=[c[0] for c in SMALL_CASES])
+def test_conv_small_kernels_match_torch(lib, case):
+    name, n, cin, h, w, cout, k, stride, pad, pre = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) & 0xFFFF)
+    x = torch.randn((n, cin, h, w), generator=g).cuda()
+    wt = (torch.randn((cout, cin, k, k), generator=g) / math.sqrt(cin * k * k)).cuda()
+    b = torch.randn((cout,), generator=g).cuda() if name != "gm_stem_7x7_s2" else None
+    prep = None
+    if pre:
+        prep = (1.0 + 0.2 * torch.randn((n, cin), generator=g)).cuda(), (0.2 * torch.randn((n, cin), generator=g)).cuda()
+    pads = (pad, pad, pad, pad)
+    want = ref_conv(x, wt, b, stride, pads, 1, prep, "none", "none", None)
+    got = run_conv(lib, x, wt, b, stride, pads, 1, prep, "none", "none", None, use_tc=4)
+    err = float((got - want).abs().max())
+    assert got.shape == want.shape and err <= 2e-4 * max(1.0, float(want.abs().max())), "%s: %g" % (name, err)

@@ -189,3 +189,30 @@ def test_shape_and_device_errors_raise(net):
         net(torch.zeros(1, 2, 3, 256, 256, device="cuda"), need_upscale=False)   # wrong size
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 2, 3, 512, 512), need_upscale=False)                  # CPU tensor: no fallback
+
+
+def test_cuda_graph_replay_is_bitwise_identical_to_eager(keep_mod, state_dict):
+    """KEEP_FLAG_CUDA_GRAPH: call 1 runs eagerly, call 2 captures, call 3+ replay; every call must return the eager
+    engine's bits, including on a different clip after capture (static staging buffers, no stale pointers)."""
+    from oracle import weights
+    kn = keep_mod.keep_net
+    base = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3
+    eager = keep_mod.KeepNetB200(flags=base)
+    eager.load_state_dict(state_dict, strict=True)
+    eager.eval().to("cuda")
+    graph = keep_mod.KeepNetB200(flags=base | kn.FLAG_CUDA_GRAPH)
+    graph.load_state_dict(state_dict, strict=True)
+    graph.eval().to("cuda")
+    xa = weights.make_clip(2, seed=11, coherent=True).cuda()
+    xb = weights.make_clip(2, seed=12, coherent=True).cuda()
+    ra, rb = eager(xa, need_upscale=False), eager(xb, need_upscale=False)
+    for i, (x, r) in enumerate([(xa, ra), (xa, ra), (xa, ra), (xb, rb), (xa, ra)]):
+        y = graph(x, need_upscale=False)
+        assert torch.equal(y, r), "call %d differs from the eager engine" % i
+    # a stream other than the default one
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        y = graph(xb, need_upscale=False)
+    st.synchronize()
+    assert torch.equal(y, rb)
+    eager.to("cpu"); graph.to("cpu")
