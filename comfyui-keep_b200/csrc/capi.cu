@@ -184,6 +184,12 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
     KEEP_API_END
 }
 
+// debug: point the tcgen05 kernel's role timeline at a device buffer of 160 int64 (null = off)
+int keepop_tc_trace(long long* dev_buf) {
+    keep::g_tc_trace = dev_buf;
+    return 0;
+}
+
 int keepop_groupnorm_affine(const float* x_dev, int n, int hw, int c, int groups, float eps, const float* gamma_dev,
                             const float* beta_dev, float* scale_dev, float* shift_dev, void* stream) {
     KEEP_API_BEGIN

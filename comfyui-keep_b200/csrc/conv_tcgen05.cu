@@ -22,6 +22,10 @@
 // 260-286,311-335 and keep_arch.py:78-87,391-393,445-455,929,936-938.
 #include <vector>
 
+#ifndef KEEP_TC_HPITCH
+#define KEEP_TC_HPITCH 10
+#endif
+
 #include "ops.h"
 #include "tc.h"
 
@@ -32,9 +36,14 @@ constexpr int kThreads = 704;
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 5, kProdWarp0 = 6, kProdThreads = 512;   // 16 producer warps
 constexpr int MAX_SA = 4, MAX_SB = 6;  // barrier slots (actual pipeline depths come from the launch arguments)
 constexpr int CB = 64;                 // channels per A stage (4 MMA K-steps of 16)
-constexpr int PLANE3 = 2960;           // bytes per 8-channel plane of a 18x10 halo (2880 padded to 16 mod 128: conflict-free stores)
-constexpr int PLANE1 = 2064;           // bytes per plane of a 128-pixel 1x1 tile (2048 padded likewise)
-constexpr int A_SUB_BYTES = 8 * PLANE3;   // one operand tile (hi); the split-precision mode appends a second (lo) tile
+// A stage = halo tile in the UMMA SWIZZLE_128B K-major layout: one 128-byte row (64 channels, fp16) per halo pixel,
+// 16-byte chunks XOR-swizzled by (row & 7).  The halo is 18 rows x 10 columns but rows are PITCHED at 16 pixels, so
+// that (a) every 8-pixel group of an MMA operand view starts SBO = 16*128 = 2048 B after the previous one (a multiple
+// of the 1024-byte swizzle atom: all groups share one swizzle phase) and (b) a filter tap (dy, dx) is just the start
+// address base + (dy*16 + dx)*128 with descriptor base_offset = dx.  (The first version used the no-swizzle
+// "interleaved" core-matrix layout: correct, but the tensor core fetched it 16 bytes per cycle, ~300 cycles per MMA.)
+constexpr int HPITCH_PX = KEEP_TC_HPITCH;
+constexpr int A_SUB_BYTES = (18 * HPITCH_PX * 128 + 1023) / 1024 * 1024;   // one operand tile (hi); split precision appends a lo tile
 constexpr int MAXIT = 3;               // ceil(180 * 8 / 512) halo units per producer thread
 
 // ------------------------------------------------------------------------------------------------
@@ -97,14 +106,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major: core matrix = 8 rows x 16 B (contiguous 128 B);
-// LBO = byte distance between the two K-halves of one K=16 step, SBO = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
-           ((uint64_t)1 << 46);
-}
+// UMMA shared-memory descriptor, SWIZZLE_128B, K-major (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30)
+// (unused for swizzled K-major: 1), SBO>>4 [32,46) = distance between 8-row groups, version 1 [46,48),
+// base_offset [49,52) = (start >> 7) & 7 when the start is not 1024-byte aligned, layout type 2 = SWIZZLE_128B [61,64).
 
 // The kernel's code footprint matters: five warp roles run different code at once and the SM's instruction cache
 // is small (a first version that inlined the generic activation switch 48x ran 10x slower, stalled on fetch).
@@ -125,10 +136,16 @@ __device__ __noinline__ float act_slow(float v, int act) { return apply_act(v, a
 // PASSES = 3: split-precision: A = Ah + Al, W = Wh + Wl (fp16 pairs, ~22 mantissa bits), D += Ah*Wh + Ah*Wl + Al*Wh
 //             with fp32 accumulation in TMEM -> fp32-grade results on the tensor cores (the "decision path" needs
 //             this: one flipped argmax over the 1024 code logits changes a 32x32-pixel block).
+// optional per-role timeline (debug): a.trace != null -> CTA 0 stamps clock64() at role milestones of its first tiles
+#define TC_TRACE(slot, idx)                                                                        \
+    do {                                                                                           \
+        if (a.trace && blockIdx.x == 0 && (idx) < 16) a.trace[(slot) * 16 + (idx)] = clock64();    \
+    } while (0)
+
 template <int PASSES, bool IN_F16>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms are 1024-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NOP = PASSES == 3 ? 2 : 1;             // operand tiles per stage (hi [, lo])
     constexpr int A_STAGE_BYTES = NOP * A_SUB_BYTES;
@@ -147,6 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + s); };
     auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + 2 + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SA + 2 * MAX_SB + 4);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [256] bias of the current N tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_SA; ++s) { mbar_init(A_FULL(s), kProdThreads); mbar_init(A_EMPTY(s), 1); }
@@ -161,8 +179,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     const uint32_t tmem_base = *tmem_slot;
 
     const bool conv3 = a.taps == 9;
-    const int plane = conv3 ? PLANE3 : PLANE1;
-    const int hw10 = conv3 ? 10 : 8;                 // halo row pitch in pixels
     const int mt_per_img = a.tiles_y * a.tiles_x;
     const int m_tiles = a.n * mt_per_img;
     const long long total = (long long)m_tiles * a.ntile_n * a.splitk;
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             hy[it] = p / 10;
             hx[it] = p - hy[it] * 10;
         }
-        int stage = 0, phase = 0;
+        int stage = 0, phase = 0, trace_i = 0;
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
             int nt, img, ty, tx, ks;
             decode(w, nt, img, ty, tx, ks);
@@ -242,8 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         if (!IN_F16) raw[it][1] = g[1];
                     }
                 }
+                if (pt == 0) TC_TRACE(0, trace_i);
                 mbar_wait(A_EMPTY(stage), phase ^ 1);
-                uint8_t* dst = sA + stage * A_STAGE_BYTES + pl * plane;
+                if (pt == 0) TC_TRACE(1, trace_i);
+                uint8_t* dst = sA + stage * A_STAGE_BYTES;
 #pragma unroll
                 for (int it = 0; it < MAXIT; ++it) {
                     const int p = p_first + it * (kProdThreads / 8);
@@ -303,18 +321,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         o.x = *reinterpret_cast<uint32_t*>(&hq[0]); o.y = *reinterpret_cast<uint32_t*>(&hq[1]);
                         o.z = *reinterpret_cast<uint32_t*>(&hq[2]); o.w = *reinterpret_cast<uint32_t*>(&hq[3]);
                     }
-                    *reinterpret_cast<uint4*>(dst + p * 16) = o;
-                    if (PASSES == 3) *reinterpret_cast<uint4*>(dst + A_SUB_BYTES + p * 16) = ol;
+                    // row = halo pixel (pitch 16) or tile pixel; 16-byte chunk `pl` lands at chunk (pl ^ (row & 7))
+                    const int row = conv3 ? hy[it] * HPITCH_PX + hx[it] : p;
+                    const int soff = row * 128 + ((pl ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst + soff) = o;
+                    if (PASSES == 3) *reinterpret_cast<uint4*>(dst + A_SUB_BYTES + soff) = ol;
                 }
                 fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
                 mbar_arrive(A_FULL(stage));
+                if (pt == 0) { TC_TRACE(2, trace_i); ++trace_i; }
                 if (++stage == SA) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kLoadWarp) {
         // =========================== weight loader (1-D TMA) ===========================
         if (lane == 0) {
-            int stage = 0, phase = 0;
+            int stage = 0, phase = 0, trace_l = 0;
             for (long long w = blockIdx.x; w < total; w += gridDim.x) {
                 int nt, img, ty, tx, ks;
                 decode(w, nt, img, ty, tx, ks);
@@ -326,6 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         const uint8_t* g = reinterpret_cast<const uint8_t*>(a.wt) +
                                            ((size_t)((size_t)nt * a.ncb + cb) * a.taps + tap) * (size_t)b_stage_bytes;
                         tma_bulk_g2s(smem_u32(sB + stage * b_stage_bytes), g, (uint32_t)b_stage_bytes, B_FULL(stage));
+                        if (cb == cb0 && tap == 0) TC_TRACE(8, trace_l);
+                        if (cb == cb1 - 1 && tap == a.taps - 1) { TC_TRACE(9, trace_l); ++trace_l; }
                         if (++stage == SB) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -333,39 +357,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         }
     } else if (warp == kMmaWarp) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, K-major A/B
-            const uint32_t a_lbo = a.swap_lbo_sbo ? (uint32_t)(hw10 * 16) : (uint32_t)plane;
-            const uint32_t a_sbo = a.swap_lbo_sbo ? (uint32_t)plane : (uint32_t)(hw10 * 16);
-            const uint32_t b_lbo = a.swap_lbo_sbo ? 256u : 128u;
-            const uint32_t b_sbo = a.swap_lbo_sbo ? 128u : 256u;
-            int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-                int nt, img, ty, tx, ks;
-                decode(w, nt, img, ty, tx, ks);
-                const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
-                mbar_wait(ACC_EMPTY(as), pacc ^ 1);
+        // The whole warp runs the (warp-uniform) control flow so that stage counters, shared-memory addresses and
+        // descriptors live in the uniform datapath; one elected lane issues the tcgen05 instructions.  A first version
+        // ran this loop on a single divergent lane with per-MMA 64-bit descriptor construction: ~150 instructions per
+        // filter tap on one thread made *instruction issue of this warp* the bottleneck of the whole kernel.
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, K-major A/B
+        // descriptor = {lo: start>>4 | LBO(1)<<16, hi: SBO>>4 | version 1<<14 | base_offset<<17 | SWIZZLE_128B(2)<<29}
+        const uint32_t a_sbo = conv3 ? (uint32_t)(HPITCH_PX * 128) : 1024u;
+        const uint32_t a_hi0 = ((a_sbo >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+        const uint32_t b_hi = ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+        const uint32_t a_lo0 = 1u << 16, b_lo0 = 1u << 16;
+        const uint32_t a_kstep = 32u >> 4, b_kstep = 32u >> 4;                 // K=16 halfs = 32 bytes inside the 128-byte row
+        const uint32_t a_lo_off = (uint32_t)A_SUB_BYTES >> 4, b_lo_off = (uint32_t)b_panel_bytes >> 4;
+        // Measured on B200: with a 128-byte-row-shifted start address the swizzle XOR is applied on the absolute shared
+        // memory address bits, so base_offset stays 0 (setting it to dx double-counts the phase and corrupts the tile).
+        const uint32_t use_bo = a.swap_lbo_sbo ? 1u : 0u;                       // debug knob: KEEP_TC_BASE_OFFSET=1
+        const bool leader = elect_one();
+        int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0, trace_m = 0;
+        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            int nt, img, ty, tx, ks;
+            decode(w, nt, img, ty, tx, ks);
+            const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
+            mbar_wait(ACC_EMPTY(as), pacc ^ 1);
+            tc_fence_after();
+            if (lane == 0) TC_TRACE(3, trace_m);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
+            uint32_t acc = 0;
+            for (int cb = cb0; cb < cb1; ++cb) {
+                mbar_wait(A_FULL(sa), pa);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
-                uint32_t acc = 0;
-                for (int cb = cb0; cb < cb1; ++cb) {
-                    mbar_wait(A_FULL(sa), pa);
+                if (lane == 0 && cb == cb0) TC_TRACE(4, trace_m);
+                uint32_t a_lo = a_lo0 | (smem_u32(sA + sa * A_STAGE_BYTES) >> 4);
+                int dx = 0;
+                for (int tap = 0; tap < a.taps; ++tap) {
+                    mbar_wait(B_FULL(sb), pb);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(sA + sa * A_STAGE_BYTES);
-                    for (int tap = 0; tap < a.taps; ++tap) {
-                        mbar_wait(B_FULL(sb), pb);
-                        tc_fence_after();
-                        const uint32_t b_base = smem_u32(sB + sb * b_stage_bytes);
-                        const uint32_t tap_off = conv3 ? (uint32_t)(((tap / 3) * 10 + (tap % 3)) * 16) : 0u;
+                    const uint32_t b_lo = b_lo0 | (smem_u32(sB + sb * b_stage_bytes) >> 4);
+                    const uint32_t a_hi = a_hi0 | ((use_bo * (uint32_t)dx) << 17);   // tap dx shifts the start by dx rows of 128 B
+                    if (leader) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = make_desc(a_base + (uint32_t)(2 * k * plane) + tap_off, a_lbo, a_sbo);
-                            const uint64_t bd = make_desc(b_base + (uint32_t)(k * a.bn * 32), b_lbo, b_sbo);
+                            const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + k * a_kstep);
+                            const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + k * b_kstep);
                             if (PASSES == 3) {   // small cross terms first, then the leading term
-                                const uint64_t adl = make_desc(a_base + A_SUB_BYTES + (uint32_t)(2 * k * plane) + tap_off, a_lbo, a_sbo);
-                                const uint64_t bdl = make_desc(b_base + (uint32_t)b_panel_bytes + (uint32_t)(k * a.bn * 32), b_lbo, b_sbo);
-                                umma_f16(d_tmem, adl, bd, idesc, acc);
-                                umma_f16(d_tmem, ad, bdl, idesc, 1u);
+                                umma_f16(d_tmem, ad + a_lo_off, bd, idesc, acc);
+                                umma_f16(d_tmem, ad, bd + b_lo_off, idesc, 1u);
                                 umma_f16(d_tmem, ad, bd, idesc, 1u);
                             } else {
                                 umma_f16(d_tmem, ad, bd, idesc, acc);
@@ -373,25 +409,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                             acc = 1;
                         }
                         umma_commit(B_EMPTY(sb));            // frees the weight stage when these MMAs retire
-                        if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
-                    umma_commit(A_EMPTY(sa));
-                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    __syncwarp();
+                    // next tap = shifted view of the same halo tile: +1 pixel (128 B), or to the next halo row
+                    if (++dx == 3) { dx = 0; a_lo += (uint32_t)((HPITCH_PX - 2) * 128) >> 4; } else { a_lo += 128u >> 4; }
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
                 }
-                umma_commit(ACC_FULL(as));
-                if (++as == 2) { as = 0; pacc ^= 1; }
+                if (leader) umma_commit(A_EMPTY(sa));
+                __syncwarp();
+                if (++sa == SA) { sa = 0; pa ^= 1; }
             }
+            if (leader) umma_commit(ACC_FULL(as));
+            __syncwarp();
+            if (lane == 0) { TC_TRACE(5, trace_m); ++trace_m; }
+            if (++as == 2) { as = 0; pacc ^= 1; }
         }
     } else {
         // =========================== epilogue (warps 0-3 <-> TMEM lane quarters) ===========================
-        int as = 0, pacc = 0;
+        // Each thread owns one accumulator row (= one output pixel) and walks its BN columns 16 at a time:
+        // tcgen05.ld -> (+bias from shared memory) -> activation -> (+residual, loaded while the TMEM load is in
+        // flight) -> 64 contiguous bytes to HBM.  Everything stays in registers (a first version spilled the row to
+        // local memory and re-fetched the bias from L2 every 16 columns: 8K cycles per tile, the kernel's bottleneck).
+        int as = 0, pacc = 0, trace_e = 0, bias_nt = -1;
         const int row = warp * 32 + lane;          // accumulator row = output pixel within the tile
         const int r = row >> 3, c = row & 7;
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
             int nt, img, ty, tx, ks;
             decode(w, nt, img, ty, tx, ks);
-            mbar_wait(ACC_FULL(as), pacc);
-            tc_fence_after();
+            if (nt != bias_nt) {   // stage this N tile's bias (zeros when absent / beyond cout) in shared memory
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x; i < a.bn; i += kEpiWarps * 32) {
+                    const int nn = nt * a.bn + i;
+                    s_bias[i] = (a.bias && a.splitk == 1 && nn < a.cout) ? a.bias[nn] : 0.0f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                bias_nt = nt;
+            }
             long long pixel;
             bool ok;
             if (conv3) {
@@ -404,65 +457,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 pixel = (long long)img * a.h * a.w + q;
             }
             const int n0 = nt * a.bn;
+            mbar_wait(ACC_FULL(as), pacc);
+            tc_fence_after();
+            if (threadIdx.x == 0) TC_TRACE(6, trace_e);
             const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * a.bn);
+            const bool partial_out = a.splitk > 1;
             for (int j = 0; j < a.bn; j += 16) {
                 uint32_t rr[16];
+                __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge after divergent stores
                 tmem_ld16(t0 + (uint32_t)j, rr);
-                tmem_ld_wait();
                 const int nn = n0 + j;
-                if (ok && nn < a.cout) {       // cout % 16 == 0
-                    float v[16];
+                const bool live = ok && nn < a.cout;       // cout % 16 == 0
+                const size_t off = (size_t)pixel * a.cout + nn;
+                float4 rs[4];
+                const bool has_res = live && !partial_out && a.res != nullptr;
+                if (has_res) {
+                    if (a.res_dt == F32) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
-                    const size_t off = (size_t)pixel * a.cout + nn;
-                    if (a.splitk > 1) {
-                        float4* o = reinterpret_cast<float4*>(a.partial + (size_t)ks * a.M * a.cout + off);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                        for (int e = 0; e < 4; ++e) rs[e] = ld4(reinterpret_cast<const float*>(a.res), off + 4 * e);
                     } else {
-                        if (a.bias) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float4 b = *reinterpret_cast<const float4*>(a.bias + nn + 4 * e);
-                                v[4 * e] += b.x; v[4 * e + 1] += b.y; v[4 * e + 2] += b.z; v[4 * e + 3] += b.w;
-                            }
-                        }
-                        if (a.act == ACT_RELU) {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
-                        } else if (a.act != ACT_NONE) {
-#pragma unroll 1
-                            for (int e = 0; e < 16; ++e) v[e] = act_slow(v[e], a.act);
-                        }
-                        if (a.res) {
-                            if (a.res_dt == F32) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float4 q4 = ld4(reinterpret_cast<const float*>(a.res), off + 4 * e);
-                                    v[4 * e] += q4.x; v[4 * e + 1] += q4.y; v[4 * e + 2] += q4.z; v[4 * e + 3] += q4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float4 q4 = ld4(reinterpret_cast<const __half*>(a.res), off + 4 * e);
-                                    v[4 * e] += q4.x; v[4 * e + 1] += q4.y; v[4 * e + 2] += q4.z; v[4 * e + 3] += q4.w;
-                                }
-                            }
-                        }
-                        if (a.out_dt == F32) {
-                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                st4(reinterpret_cast<__half*>(a.out), off + 4 * e, make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]));
-                        }
+                        for (int e = 0; e < 4; ++e) rs[e] = ld4(reinterpret_cast<const __half*>(a.res), off + 4 * e);
                     }
+                }
+                tmem_ld_wait();
+                if (!live) continue;
+                float v[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
+                if (partial_out) {
+                    float4* o = reinterpret_cast<float4*>(a.partial + (size_t)ks * a.M * a.cout + off);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                    continue;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 b = *reinterpret_cast<const float4*>(s_bias + j + 4 * e);
+                    v[4 * e] += b.x; v[4 * e + 1] += b.y; v[4 * e + 2] += b.z; v[4 * e + 3] += b.w;
+                }
+                if (a.act == ACT_RELU) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
+                } else if (a.act != ACT_NONE) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = act_slow(v[e], a.act);
+                }
+                if (has_res) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { v[4 * e] += rs[e].x; v[4 * e + 1] += rs[e].y; v[4 * e + 2] += rs[e].z; v[4 * e + 3] += rs[e].w; }
+                }
+                if (a.out_dt == F32) {
+                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        st4(reinterpret_cast<__half*>(a.out), off + 4 * e, make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]));
                 }
             }
             tc_fence_before();
             mbar_arrive(ACC_EMPTY(as));
+            if (threadIdx.x == 0) { TC_TRACE(7, trace_e); ++trace_e; }
             if (++as == 2) { as = 0; pacc ^= 1; }
         }
     }
@@ -508,44 +565,42 @@ size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn, int passes) {
     return (size_t)ntile * ncb * taps * bn * 64 * (passes == 3 ? 2 : 1);
 }
 
-// OIHW fp32 (host) -> [ntile][cb][tap][hi|lo][k16][n8][khalf][8 n][8 k] fp16
+// OIHW fp32 (host) -> [ntile][cb][tap][hi|lo] panels; a panel is the SWIZZLE_128B K-major image of the (bn x 64) tile:
+// row n = 128 bytes (64 input channels), 16-byte chunk j stored at chunk position j ^ (n & 7)
 void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out) {
     const int taps = kh * kw, ncb = (cin + CB - 1) / CB, ntile = (cout + bn - 1) / bn, nop = passes == 3 ? 2 : 1;
-    size_t idx = 0;
+    size_t base = 0;
     for (int nt = 0; nt < ntile; ++nt)
         for (int cb = 0; cb < ncb; ++cb)
             for (int tap = 0; tap < taps; ++tap)
-                for (int part = 0; part < nop; ++part)
-                    for (int k16 = 0; k16 < 4; ++k16)
-                        for (int g = 0; g < bn / 8; ++g)
-                            for (int kh2 = 0; kh2 < 2; ++kh2)
-                                for (int r = 0; r < 8; ++r)
-                                    for (int e = 0; e < 8; ++e) {
-                                        const int o = nt * bn + g * 8 + r, i = cb * CB + k16 * 16 + kh2 * 8 + e;
-                                        float v = 0.0f;
-                                        if (o < cout && i < cin) v = w_oihw[(((size_t)o * cin + i) * kh + tap / kw) * kw + tap % kw];
-                                        const __half hi = __float2half_rn(v);
-                                        out[idx++] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
-                                    }
+                for (int part = 0; part < nop; ++part, base += (size_t)bn * 64)
+                    for (int r = 0; r < bn; ++r)
+                        for (int k = 0; k < 64; ++k) {
+                            const int o = nt * bn + r, i = cb * CB + k;
+                            float v = 0.0f;
+                            if (o < cout && i < cin) v = w_oihw[(((size_t)o * cin + i) * kh + tap / kw) * kw + tap % kw];
+                            const __half hi = __float2half_rn(v);
+                            const int chunk = (k >> 3) ^ (r & 7);
+                            out[base + (size_t)r * 64 + chunk * 8 + (k & 7)] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+                        }
 }
 
 namespace {
-// device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 panel layout
+// device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 swizzled panels
 __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int nop, size_t total,
                                  __half* __restrict__ out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     size_t r = idx;
     const int e = (int)(r % 8); r /= 8;
-    const int row = (int)(r % 8); r /= 8;
-    const int kh2 = (int)(r % 2); r /= 2;
-    const int g = (int)(r % (bn / 8)); r /= (bn / 8);
-    const int k16 = (int)(r % 4); r /= 4;
+    const int chunk = (int)(r % 8); r /= 8;
+    const int row = (int)(r % bn); r /= bn;
     const int part = (int)(r % nop); r /= nop;
     const int tap = (int)(r % taps); r /= taps;
     const int cb = (int)(r % ncb); r /= ncb;
     const int nt = (int)r;
-    const int o = nt * bn + g * 8 + row, i = cb * CB + k16 * 16 + kh2 * 8 + e;
+    const int k = ((chunk ^ (row & 7)) << 3) + e;      // logical input channel within the 64-channel block
+    const int o = nt * bn + row, i = cb * CB + k;
     float v = 0.0f;
     if (o < cout && i < cin) v = w[((size_t)tap * cin + i) * cout + o];
     const __half hi = __float2half_rn(v);
@@ -570,15 +625,17 @@ int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb) {
 
 static int env_swap() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("KEEP_TC_SWAP_LBO_SBO"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("KEEP_TC_BASE_OFFSET"); v = (e && e[0] == '1') ? 1 : 0; }
     return v;
 }
 
+long long* g_tc_trace = nullptr;   // debug: device buffer of 10*16 clock64 stamps (keepop_tc_trace)
+
 static void pick_stages(int passes, int bn, int& sa, int& sb) {
     const int a_stage = (passes == 3 ? 2 : 1) * A_SUB_BYTES, b_stage = (passes == 3 ? 2 : 1) * bn * 128;
-    const int budget = 222 * 1024;
-    sa = passes == 3 ? 2 : 3;
-    sb = 3;
+    const int budget = 224 * 1024;
+    sa = 2;
+    sb = 2;
     // grow the weight pipeline first (9 weight stages are consumed per activation stage), then the activation one
     while (sb < MAX_SB && sa * a_stage + (sb + 1) * b_stage <= budget) ++sb;
     while (sa < MAX_SA && (sa + 1) * a_stage + sb * b_stage <= budget) ++sa;
@@ -612,10 +669,11 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     t.tmem_cols = cols;
     t.swap_lbo_sbo = env_swap();
     pick_stages(passes, bn, t.sa_stages, t.sb_stages);
+    t.trace = g_tc_trace;
     KEEP_CHECK(splitk == 1 || partial, "conv2d_tc: split-K needs a partial buffer");
     const int nop = passes == 3 ? 2 : 1;
-    const size_t smem = 128 + (size_t)t.sa_stages * nop * A_SUB_BYTES + (size_t)t.sb_stages * nop * bn * 128 +
-                        8 * (2 * MAX_SA + 2 * MAX_SB + 4) + 16;
+    const size_t smem = 1024 + (size_t)t.sa_stages * nop * A_SUB_BYTES + (size_t)t.sb_stages * nop * bn * 128 +
+                        8 * (2 * MAX_SA + 2 * MAX_SB + 4) + 16 + 256 * sizeof(float);
     KEEP_CHECK(smem <= 227 * 1024, "conv2d_tc: %zu bytes of shared memory", smem);
     KEEP_CHECK(a.c1 == 0 || a.in0_dt == a.in1_dt, "conv2d_tc: concatenated sources must share a dtype");
     static bool configured = false;

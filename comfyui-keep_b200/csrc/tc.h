@@ -16,9 +16,11 @@ struct TcConvArgs {
     long long M;
     int tmem_cols;
     int sa_stages, sb_stages;
+    long long* trace;   // debug timeline (null = off)
     int swap_lbo_sbo;   // debug: KEEP_TC_SWAP_LBO_SBO=1
 };
 
+extern long long* g_tc_trace;
 bool tc_eligible(const ConvArgs& a);
 int tc_pick_bn(int cout, long long m_tiles, int passes);
 int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb);

@@ -92,6 +92,7 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
                   int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
                   const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
                   float* out_dev, void* stream);
+int keepop_tc_trace(long long* dev_buf_160_i64); /* debug: per-role clock64 timeline of CTA 0 of the tcgen05 kernel */
 int keepop_groupnorm_affine(const float* x_dev, int n, int hw, int c, int groups, float eps, const float* gamma_dev,
                             const float* beta_dev, float* scale_dev, float* shift_dev, void* stream);
 int keepop_layernorm(const float* x_dev, int rows, int c, const float* g_dev, const float* b_dev, float eps, float* out_dev,

@@ -1,0 +1,20 @@
+"""Per-role timeline (clock64) of CTA 0 of the tcgen05 conv kernel for one layer shape."""
+import ctypes, math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch, keep_b200
+from test_gpu_ops import run_conv
+lib = keep_b200.keep_net.load_library()
+n, cin, h, w, cout = [int(v) for v in (sys.argv[1:6] if len(sys.argv) > 5 else (1, 64, 512, 512, 64))]
+mode = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+x = torch.randn((n, cin, h, w), device="cuda"); wt = torch.randn((cout, cin, 3, 3), device="cuda") / math.sqrt(cin * 9); b = torch.randn(cout, device="cuda")
+pre = (torch.ones((n, cin), device="cuda"), torch.zeros((n, cin), device="cuda"))
+run_conv(lib, x, wt, b, 1, (1, 1, 1, 1), 1, pre, "swish", "none", None, use_tc=mode)
+buf = torch.zeros(160, dtype=torch.int64, device="cuda")
+lib.keepop_tc_trace(ctypes.c_void_p(buf.data_ptr()))
+run_conv(lib, x, wt, b, 1, (1, 1, 1, 1), 1, pre, "swish", "none", None, use_tc=mode)
+lib.keepop_tc_trace(None)
+t = buf.cpu().reshape(10, 16); t0 = int(t[t > 0].min())
+names = ["prod:loads_issued", "prod:got_A_EMPTY", "prod:A_FULL_arrive", "mma:got_ACC_EMPTY", "mma:got_A_FULL", "mma:issued_all", "epi:got_ACC_FULL", "epi:done", "load:first_tap", "load:last_tap"]
+for i, nm in enumerate(names):
+    print("%-20s" % nm, " ".join("%7d" % (int(v) - t0 if v > 0 else -1) for v in t[i][:10]))
