@@ -6,3 +6,4 @@ shim:  `import keep_b200`  (see /keep_b200.py) or `importlib` with this file's p
 from .keep_net import KeepNetB200, KEEP_GENERAL_CFG, install_into_model_pack, lib_path  # noqa: F401
 from .build import build  # noqa: F401
 from . import synth  # noqa: F401,E402
+from . import sharding  # noqa: F401,E402

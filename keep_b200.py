@@ -23,3 +23,4 @@ build = pkg.build
 lib_path = pkg.lib_path
 keep_net = sys.modules[_NAME + ".keep_net"]
 synth = pkg.synth
+sharding = pkg.sharding

@@ -1,0 +1,63 @@
+"""CPU tier: clip splitting / round-robin assignment / gather order of the N>1 path, world_size-2 gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_split_matches_reference_loop(keep_mod):
+    sh = keep_mod.sharding
+    assert sh.split_clips(100, 20) == [(0, 20, 20), (20, 40, 20), (40, 60, 20), (60, 80, 20), (80, 100, 20)]
+    c = sh.split_clips(512, 20)            # BASELINE.json config 5: 25 x 20 + 1 x 12
+    assert len(c) == 26 and c[-1] == (500, 512, 12)
+    assert sh.split_clips(21, 20)[-1] == (20, 21, 1)   # 1-frame tail (duplicated to T=2 by the runner)
+    assert sh.split_clips(0, 20) == []
+    with pytest.raises(ValueError):
+        sh.split_clips(5, 0)
+    owner = sh.assign_round_robin(26, 8)
+    assert [owner.count(r) for r in range(8)] == [4, 4, 3, 3, 3, 3, 3, 3]
+
+
+class _FakeNet:
+    """Stands in for keep_net on CPU: marks every frame with (clip length, frame position) so order/ownership show."""
+
+    def __call__(self, x, need_upscale=False):
+        assert x.shape[1] >= 2 and not need_upscale
+        t = torch.arange(x.shape[1], dtype=x.dtype).view(1, -1, 1, 1, 1)
+        return x * 2.0 + t * 1e-3
+
+
+def _worker(rank, world, port, n_frames, clip_len, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import keep_b200
+    g = torch.Generator().manual_seed(0)
+    frames = torch.rand((1, n_frames, 3, 512, 512), generator=g)[:, :, :, :8, :8].repeat(1, 1, 1, 64, 64)
+    out = keep_b200.sharding.run_clips_sharded(_FakeNet(), frames, clip_len, gather_dtype=torch.float32)
+    if rank == 0:
+        ref = keep_b200.sharding.run_clips(_FakeNet(), frames, clip_len)
+        q.put((tuple(out.shape), bool(torch.equal(out, ref))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames,clip_len", [(7, 3), (5, 2), (4, 4)])
+def test_sharded_equals_single_process_gloo_world2(n_frames, clip_len):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, clip_len, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    shape, same = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert shape == (1, n_frames, 3, 512, 512) and same
