@@ -178,7 +178,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const bool conv3 = a.taps == 9;
+    const int win = a.win;                 // 3: 3x3 s1 | 2: 3x3 stride-2 as a 2x2 window over the virtual space-to-depth input | 1: 1x1
+    const bool conv3 = win > 1;            // halo-tile modes
+    const int hcols = 8 + win - 1;         // halo columns (rows are pitched at HPITCH_PX pixels)
+    // stride-2 mode: virtual channel block cb = parity p * ncbr + real block; tap (a,b) x parity (py,px) maps to filter
+    // position ky = 2a + py - pad_t, kx = 2b + px - pad_l; combinations outside the 3x3 filter are skipped entirely
+    auto stage_live = [&](int cb, int tap) -> bool {
+        if (!a.s2d) return true;
+        const int p = cb / a.ncbr;
+        const int ky = 2 * (tap >> 1) + (p >> 1) - a.pad_t, kx = 2 * (tap & 1) + (p & 1) - a.pad_l;
+        return ky >= 0 && ky <= 2 && kx >= 0 && kx <= 2;
+    };
     const int mt_per_img = a.tiles_y * a.tiles_x;
     const int m_tiles = a.n * mt_per_img;
     const long long total = (long long)m_tiles * a.ntile_n * a.splitk;
@@ -201,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         const int pt = threadIdx.x - kProdWarp0 * 32;       // 0..511
         const int pl = pt & 7;                              // 8-channel plane handled by this thread
         const int Hl = a.h * a.up, Wl = a.w * a.up;
-        const int npix = conv3 ? 180 : 128;
+        const int npix = conv3 ? (16 + win - 1) * hcols : 128;
         const int cin = a.c0 + a.c1;
         const int ushift = a.up - 1;
         // halo units of this thread: pixel p = p_first + it*64 -> (row, col) within the 18x10 halo; tile independent
@@ -210,17 +220,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 #pragma unroll
         for (int it = 0; it < MAXIT; ++it) {
             const int p = p_first + it * (kProdThreads / 8);
-            hy[it] = p / 10;
-            hx[it] = p - hy[it] * 10;
+            hy[it] = p / hcols;
+            hx[it] = p - hy[it] * hcols;
         }
         int stage = 0, phase = 0, trace_i = 0;
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
             int nt, img, ty, tx, ks;
             decode(w, nt, img, ty, tx, ks);
             const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
-            const int oy0 = ty * 16 - 1, ox0 = tx * 8 - 1;
+            const int oy0 = ty * 16 - (a.s2d ? a.pad_t : 1), ox0 = tx * 8 - (a.s2d ? a.pad_l : 1);
             for (int cb = cb0; cb < cb1; ++cb) {
-                const int ch = cb * CB + pl * 8;            // first of this thread's 8 channels (global, concat space)
+                const int par = a.s2d ? cb / a.ncbr : 0;    // stride-2 mode: input parity (py, px) of this virtual block
+                const int py = par >> 1, px = par & 1;
+                const int ch = (a.s2d ? (cb - par * a.ncbr) : cb) * CB + pl * 8;   // first of this thread's 8 real channels
                 const bool ch_ok = ch < cin;
                 float sc[8], sh[8];
                 if (a.pre_scale && ch_ok) {
@@ -243,7 +255,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     bool ok = ch_ok && p < npix;
                     size_t pix;
                     if (conv3) {
-                        const int iy = oy0 + hy[it], ix = ox0 + hx[it];
+                        int iy = oy0 + hy[it], ix = ox0 + hx[it];
+                        if (a.s2d) { iy = 2 * iy + py; ix = 2 * ix + px; }
                         ok = ok && iy >= 0 && iy < Hl && ix >= 0 && ix < Wl;
                         pix = ((size_t)img * a.h + (iy >> ushift)) * a.w + (ix >> ushift);
                     } else {
@@ -343,13 +356,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
                 for (int cb = cb0; cb < cb1; ++cb) {
                     for (int tap = 0; tap < a.taps; ++tap) {
+                        if (!stage_live(cb, tap)) continue;
                         mbar_wait(B_EMPTY(stage), phase ^ 1);
                         mbar_arrive_expect_tx(B_FULL(stage), (uint32_t)b_stage_bytes);
                         const uint8_t* g = reinterpret_cast<const uint8_t*>(a.wt) +
                                            ((size_t)((size_t)nt * a.ncb + cb) * a.taps + tap) * (size_t)b_stage_bytes;
                         tma_bulk_g2s(smem_u32(sB + stage * b_stage_bytes), g, (uint32_t)b_stage_bytes, B_FULL(stage));
                         if (cb == cb0 && tap == 0) TC_TRACE(8, trace_l);
-                        if (cb == cb1 - 1 && tap == a.taps - 1) { TC_TRACE(9, trace_l); ++trace_l; }
                         if (++stage == SB) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -390,6 +403,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 uint32_t a_lo = a_lo0 | (smem_u32(sA + sa * A_STAGE_BYTES) >> 4);
                 int dx = 0;
                 for (int tap = 0; tap < a.taps; ++tap) {
+                    if (!stage_live(cb, tap)) {   // keep the shifted-view cursor in step, issue nothing
+                        if (++dx == win) { dx = 0; a_lo += (uint32_t)((HPITCH_PX - (win - 1)) * 128) >> 4; } else { a_lo += 128u >> 4; }
+                        continue;
+                    }
                     mbar_wait(B_FULL(sb), pb);
                     tc_fence_after();
                     const uint32_t b_lo = b_lo0 | (smem_u32(sB + sb * b_stage_bytes) >> 4);
@@ -412,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     }
                     __syncwarp();
                     // next tap = shifted view of the same halo tile: +1 pixel (128 B), or to the next halo row
-                    if (++dx == 3) { dx = 0; a_lo += (uint32_t)((HPITCH_PX - 2) * 128) >> 4; } else { a_lo += 128u >> 4; }
+                    if (++dx == win) { dx = 0; a_lo += (uint32_t)((HPITCH_PX - (win - 1)) * 128) >> 4; } else { a_lo += 128u >> 4; }
                     if (++sb == SB) { sb = 0; pb ^= 1; }
                 }
                 if (leader) umma_commit(A_EMPTY(sa));
@@ -548,8 +565,19 @@ int tc_pick_bn(int cout, long long m_tiles, int passes) {
     return 128;
 }
 
+bool tc_is_s2d(const ConvArgs& a) {
+    return a.kh == 3 && a.kw == 3 && a.stride == 2 && a.up == 1 && a.c1 == 0 && a.pad_t == a.pad_l && (a.pad_t == 0 || a.pad_t == 1) &&
+           a.h % 2 == 0 && a.w % 2 == 0 && a.ho == a.h / 2 && a.wo == a.w / 2;
+}
+
+int tc_virtual_cin(const ConvArgs& a) {
+    const int cin = a.c0 + a.c1;
+    return tc_is_s2d(a) ? 4 * ((cin + CB - 1) / CB) * CB : cin;
+}
+
 bool tc_eligible(const ConvArgs& a) {
     const int cin = a.c0 + a.c1;
+    if (tc_is_s2d(a)) return a.cout % 16 == 0 && cin % 8 == 0 && cin >= 32;
     const bool k3 = a.kh == 3 && a.kw == 3 && a.stride == 1 && a.pad_t == 1 && a.pad_l == 1 && a.ho == a.h * a.up && a.wo == a.w * a.up;
     const bool k1 = a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad_t == 0 && a.pad_l == 0 && a.up == 1;
     if (!k3 && !k1) return false;
@@ -587,8 +615,8 @@ void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int
 
 namespace {
 // device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 swizzled panels
-__global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int nop, size_t total,
-                                 __half* __restrict__ out) {
+__global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int nop, int s2d_pad,
+                                 size_t total, __half* __restrict__ out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     size_t r = idx;
@@ -600,18 +628,28 @@ __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout,
     const int cb = (int)(r % ncb); r /= ncb;
     const int nt = (int)r;
     const int k = ((chunk ^ (row & 7)) << 3) + e;      // logical input channel within the 64-channel block
-    const int o = nt * bn + row, i = cb * CB + k;
+    const int o = nt * bn + row;
     float v = 0.0f;
-    if (o < cout && i < cin) v = w[((size_t)tap * cin + i) * cout + o];
+    if (s2d_pad < 0) {
+        const int i = cb * CB + k;
+        if (o < cout && i < cin) v = w[((size_t)tap * cin + i) * cout + o];
+    } else {   // virtual space-to-depth: block cb = parity * ncbr + real block; tap = (a, b) of the 2x2 cell window
+        const int ncbr = ncb / 4, par = cb / ncbr, i = (cb - par * ncbr) * CB + k;
+        const int ky = 2 * (tap >> 1) + (par >> 1) - s2d_pad, kx = 2 * (tap & 1) + (par & 1) - s2d_pad;
+        if (o < cout && i < cin && ky >= 0 && ky <= 2 && kx >= 0 && kx <= 2) v = w[((size_t)(ky * 3 + kx) * cin + i) * cout + o];
+    }
     const __half hi = __float2half_rn(v);
     out[idx] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
 }
 }  // namespace
 
-void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, __half* out, cudaStream_t s) {
-    const int ncb = (cin + CB - 1) / CB;
-    const size_t total = tc_packed_weight_halfs(cin, cout, taps, bn, passes);
-    tc_repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_kc, cin, cout, taps, bn, ncb, passes == 3 ? 2 : 1, total, out);
+void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s) {
+    // stride-2 mode: `cin` real channels are seen as 4 * ceil(cin/64) * 64 virtual channels with a 2x2 (taps = 4) window
+    const int vcin = s2d_pad >= 0 ? 4 * ((cin + CB - 1) / CB) * CB : cin;
+    const int vtaps = s2d_pad >= 0 ? 4 : taps;
+    const int ncb = (vcin + CB - 1) / CB;
+    const size_t total = tc_packed_weight_halfs(vcin, cout, vtaps, bn, passes);
+    tc_repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_kc, cin, cout, vtaps, bn, ncb, passes == 3 ? 2 : 1, s2d_pad, total, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -650,10 +688,15 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     t.n = a.n; t.h = a.h; t.w = a.w; t.up = a.up;
     t.pre_scale = a.pre_scale; t.pre_shift = a.pre_shift; t.pre_act = a.pre_act;
     t.wt = packed; t.bias = a.bias;
-    t.taps = a.kh * a.kw; t.cout = a.cout; t.bn = bn;
+    const bool s2d = tc_is_s2d(a);
+    t.s2d = s2d ? 1 : 0;
+    t.win = s2d ? 2 : (a.kh == 3 ? 3 : 1);
+    t.taps = t.win * t.win; t.cout = a.cout; t.bn = bn;
     t.ho = a.ho; t.wo = a.wo;
-    t.ncb = (a.c0 + a.c1 + CB - 1) / CB;
-    if (t.taps == 9) { t.tiles_y = cdiv(a.ho, 16); t.tiles_x = cdiv(a.wo, 8); }
+    t.ncbr = (a.c0 + a.c1 + CB - 1) / CB;
+    t.ncb = s2d ? 4 * t.ncbr : t.ncbr;
+    t.pad_t = a.pad_t; t.pad_l = a.pad_l;
+    if (t.win > 1) { t.tiles_y = cdiv(a.ho, 16); t.tiles_x = cdiv(a.wo, 8); }
     else { t.tiles_y = cdiv((long long)a.h * a.w, 128); t.tiles_x = 1; }
     t.ntile_n = cdiv(a.cout, bn);
     {   // every K-split must own at least one channel block
@@ -707,13 +750,20 @@ int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, int pass
     KEEP_CHECK(tc_eligible(a), "keepop_conv2d(use_tc): layer not eligible for the tcgen05 kernel");
     const long long m_tiles = a.kh == 3 ? (long long)a.n * cdiv(a.ho, 16) * cdiv(a.wo, 8) : (long long)a.n * cdiv((long long)a.h * a.w, 128);
     const int bn = tc_pick_bn(a.cout, m_tiles, passes);
-    std::vector<__half> packed(tc_packed_weight_halfs(cin, a.cout, a.kh * a.kw, bn, passes));
-    tc_pack_weights(w_oihw_host, a.cout, cin, a.kh, a.kw, bn, passes, packed.data());
+    const bool s2d = tc_is_s2d(a);
+    const int vcin = tc_virtual_cin(a);
     __half* dw = nullptr;
     float* part = nullptr;
-    CUDA_CHECK(cudaMalloc((void**)&dw, packed.size() * sizeof(__half)));
-    CUDA_CHECK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    const int splitk = tc_pick_splitk(m_tiles, cdiv(a.cout, bn), (cin + 63) / 64);
+    if (!s2d) {
+        std::vector<__half> packed(tc_packed_weight_halfs(cin, a.cout, a.kh * a.kw, bn, passes));
+        tc_pack_weights(w_oihw_host, a.cout, cin, a.kh, a.kw, bn, passes, packed.data());
+        CUDA_CHECK(cudaMalloc((void**)&dw, packed.size() * sizeof(__half)));
+        CUDA_CHECK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    } else {   // a.wt already holds the [9*cin][cout] fp32 layout on the device
+        CUDA_CHECK(cudaMalloc((void**)&dw, tc_packed_weight_halfs(vcin, a.cout, 4, bn, passes) * sizeof(__half)));
+        tc_repack_device(a.wt, cin, a.cout, 9, bn, passes, a.pad_t, dw, s);
+    }
+    const int splitk = tc_pick_splitk(m_tiles, cdiv(a.cout, bn), (vcin + 63) / 64);
     if (splitk > 1) CUDA_CHECK(cudaMalloc((void**)&part, (size_t)splitk * a.n * a.ho * a.wo * a.cout * sizeof(float)));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

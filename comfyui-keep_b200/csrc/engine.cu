@@ -190,6 +190,7 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         KEEP_CHECK(prop.major == 10, "keep_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device,
                    prop.major, prop.minor);
         num_sms_ = prop.multiProcessorCount;
+        gn_warmup();
     }
     adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
     tc_passes_ = (flags & KEEP_FLAG_TC_SPLIT3) ? 3 : 1;
@@ -299,7 +300,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         const long long m_tiles = cw.kh == 3 ? (long long)x.n * cdiv(a.ho, 16) * cdiv(a.wo, 8)
                                              : (long long)x.n * cdiv((long long)x.h * x.w, 128);
         bn = tc_pick_bn(cw.cout, m_tiles, tc_passes_);
-        a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), (cw.cin + 63) / 64);
+        a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), (tc_virtual_cin(a) + 63) / 64);
     } else {
         a.splitk = use_small ? 1 : conv_pick_splitk(a);
     }
@@ -318,7 +319,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             pr.m = (int)out.rows(); pr.k = cw.kh * cw.kw * cw.cin; pr.n = cw.cout; pr.kh = cw.kh * 10 + o.stride; pr.splitk = a.splitk; pr.bn = bn;
             CUDA_CHECK(cudaEventRecord(pr.a, s_));
         }
-        if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_), bn, tc_passes_, a.splitk, a.partial, num_sms_, s_);
+        if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_, tc_is_s2d(a) ? a.pad_t : -1), bn, tc_passes_, a.splitk, a.partial, num_sms_, s_);
         else if (use_small) conv2d_small(a, s_);
         else conv2d_simt(a, s_);
         launches_ += a.splitk > 1 ? 2 : 1;
@@ -331,13 +332,15 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     return out;
 }
 
-const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes) {
+const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad) {
     auto it = tcw_.find(cw.w);
     if (it != tcw_.end() && it->second.bn == bn && it->second.passes == passes) return it->second.p;
     TcW t;
     t.bn = bn; t.passes = passes;
-    CUDA_CHECK(cudaMalloc((void**)&t.p, tc_packed_weight_halfs(cw.cin, cw.cout, cw.kh * cw.kw, bn, passes) * sizeof(__half)));
-    tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, passes, t.p, s_);
+    const int vcin = s2d_pad >= 0 ? 4 * ((cw.cin + 63) / 64) * 64 : cw.cin;
+    const int vtaps = s2d_pad >= 0 ? 4 : cw.kh * cw.kw;
+    CUDA_CHECK(cudaMalloc((void**)&t.p, tc_packed_weight_halfs(vcin, cw.cout, vtaps, bn, passes) * sizeof(__half)));
+    tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, passes, s2d_pad, t.p, s_);
     if (it != tcw_.end()) {
         CUDA_CHECK(cudaStreamSynchronize(s_));
         cudaFree(it->second.p);
@@ -365,11 +368,11 @@ Aff Engine::gn(const Tensor& x, const std::string& prefix, const Tensor* x2) {
     double* scratch = (double*)arena_.alloc(gn_scratch_doubles(x.n, hw, std::max(x.c, x2 ? x2->c : 0)) * sizeof(double));
     if (!arena_.dry()) {
         groupnorm_affine(x.p, x.dt, x.n, hw, x.c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, 0, scratch, s_);
-        launches_ += 2;
+        launches_ += 1;
         if (x2) {
             KEEP_CHECK(x.c % cpg == 0, "GroupNorm over concat: group straddles the sources");
             groupnorm_affine(x2->p, x2->dt, x2->n, hw, x2->c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, x.c, scratch, s_);
-            launches_ += 2;
+            launches_ += 1;
         }
     }
     arena_.free(scratch);

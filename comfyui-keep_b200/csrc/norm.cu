@@ -10,17 +10,18 @@
 namespace keep {
 namespace {
 
-constexpr int GN_MAX_CHUNKS = 1024;
+constexpr int GN_MAX_CHUNKS = 2048;
 
-// ~32K elements per block: 512^2 x 64 -> 512 blocks per image (several waves over 148 SMs)
+// ~16K elements per block (16 float4 per thread): 512^2 x 64 -> 1024 blocks per image = ~7 resident blocks per SM
 static inline int gn_num_chunks(int hw, int c) {
-    int s = cdiv((long long)hw * c, 32768);
+    int s = cdiv((long long)hw * c, 16384);
     return s < 1 ? 1 : (s > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : s);
 }
 
-// partial[n][chunk][c][2] doubles
+// Stage 1: per-(image, chunk, channel) partial sums -> partial[n][chunk][c][2] (double).  Pure streaming read.
 template <typename T>
-__global__ void gn_partial_kernel(const T* __restrict__ x, int hw, int c, int nchunks, double* __restrict__ partial) {
+__global__ void __launch_bounds__(256) gn_partial_kernel(const T* __restrict__ x, int hw, int c, int nchunks,
+                                                         double* __restrict__ partial) {
     extern __shared__ double sm[];  // [lanes][c][2]
     const int c4 = c >> 2;
     const int lanes = blockDim.x / c4;
@@ -30,17 +31,31 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, int hw, int c, int nc
     const int p0 = chunk * per, p1 = min(hw, p0 + per);
     double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     const T* base = x + (size_t)n * hw * c;
-    for (int p = p0 + lane; p < p1; p += lanes) {
-        const float4 v = ld4(base, (size_t)p * c + cv * 4);
-        s[0] += v.x; q[0] += (double)v.x * v.x;
-        s[1] += v.y; q[1] += (double)v.y * v.y;
-        s[2] += v.z; q[2] += (double)v.z * v.z;
-        s[3] += v.w; q[3] += (double)v.w * v.w;
-    }
+    if (lane < lanes) {
+        int p = p0 + lane;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {      // four independent 16-byte loads in flight per thread
+            const float4 v0 = ld4(base, (size_t)p * c + cv * 4);
+            const float4 v1 = ld4(base, (size_t)(p + lanes) * c + cv * 4);
+            const float4 v2 = ld4(base, (size_t)(p + 2 * lanes) * c + cv * 4);
+            const float4 v3 = ld4(base, (size_t)(p + 3 * lanes) * c + cv * 4);
+            // fp32 pre-sum of four values, then one double accumulate (sums of squares of O(1..100) values: safe in fp32x4)
+            s[0] += (double)((v0.x + v1.x) + (v2.x + v3.x)); q[0] += (double)((v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x));
+            s[1] += (double)((v0.y + v1.y) + (v2.y + v3.y)); q[1] += (double)((v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y));
+            s[2] += (double)((v0.z + v1.z) + (v2.z + v3.z)); q[2] += (double)((v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z));
+            s[3] += (double)((v0.w + v1.w) + (v2.w + v3.w)); q[3] += (double)((v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w));
+        }
+        for (; p < p1; p += lanes) {
+            const float4 v = ld4(base, (size_t)p * c + cv * 4);
+            s[0] += v.x; q[0] += (double)v.x * v.x;
+            s[1] += v.y; q[1] += (double)v.y * v.y;
+            s[2] += v.z; q[2] += (double)v.z * v.z;
+            s[3] += v.w; q[3] += (double)v.w * v.w;
+        }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        sm[((size_t)lane * c + cv * 4 + j) * 2 + 0] = s[j];
-        sm[((size_t)lane * c + cv * 4 + j) * 2 + 1] = q[j];
+        for (int j = 0; j < 4; ++j) {
+            sm[((size_t)lane * c + cv * 4 + j) * 2 + 0] = s[j];
+            sm[((size_t)lane * c + cv * 4 + j) * 2 + 1] = q[j];
+        }
     }
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -55,17 +70,17 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, int hw, int c, int nc
     }
 }
 
-// one warp per (n, group)
-__global__ void gn_finalize_kernel(const double* __restrict__ partial, int n, int hw, int c, int cpg, int nchunks, float eps,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ scale, float* __restrict__ shift, int c_total, int c_off) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// Stage 2: one 128-thread block per (image, group): fixed-order reduction of the partials -> per-(n, channel) affine
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restrict__ partial, int hw, int c, int cpg, int nchunks,
+                                                          float eps, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ scale,
+                                                          float* __restrict__ shift, int c_total, int c_off) {
+    __shared__ double rs[4], rq[4];
     const int groups = c / cpg;
-    if (warp >= n * groups) return;
-    const int in = warp / groups, g = warp % groups;
+    const int in = blockIdx.x / groups, g = blockIdx.x % groups;
     double s = 0, q = 0;
     const int total = nchunks * cpg;
-    for (int i = lane; i < total; i += 32) {
+    for (int i = threadIdx.x; i < total; i += 128) {
         const int chunk = i / cpg, ch = g * cpg + i % cpg;
         const double* o = partial + (((size_t)in * nchunks + chunk) * c + ch) * 2;
         s += o[0];
@@ -73,12 +88,16 @@ __global__ void gn_finalize_kernel(const double* __restrict__ partial, int n, in
     }
     s = warp_sum(s);
     q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; }
+    __syncthreads();
+    s = (rs[0] + rs[1]) + (rs[2] + rs[3]);
+    q = (rq[0] + rq[1]) + (rq[2] + rq[3]);
     const double cnt = (double)hw * cpg;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
     if (var < 0) var = 0;
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    for (int i = lane; i < cpg; i += 32) {
+    for (int i = threadIdx.x; i < cpg; i += 128) {
         const int ch = g * cpg + i;
         const float ga = gamma ? gamma[c_off + ch] : 1.0f;
         const float be = beta ? beta[c_off + ch] : 0.0f;
@@ -125,23 +144,23 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 }  // namespace
 
-size_t gn_scratch_doubles(int n, int hw, int c) { return (size_t)n * GN_MAX_CHUNKS * c * 2 < (size_t)n * gn_num_chunks(hw, c) * c * 2 ? 0 : (size_t)n * gn_num_chunks(hw, c) * c * 2; }
+size_t gn_scratch_doubles(int n, int hw, int c) { return (size_t)n * gn_num_chunks(hw, c) * c * 2; }
+
+void gn_warmup() {}
 
 void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, float eps, const float* gamma, const float* beta,
                       float* scale, float* shift, int c_total, int c_off, double* scratch, cudaStream_t s) {
-    KEEP_CHECK(c % 4 == 0 && c / 4 <= 256 && c % cpg == 0, "groupnorm: unsupported channels %d (cpg %d)", c, cpg);
+    KEEP_CHECK(c % 4 == 0 && c / 4 <= 256 && c % cpg == 0, "groupnorm: unsupported shape c=%d cpg=%d", c, cpg);
     const int nchunks = gn_num_chunks(hw, c);
     const int c4 = c / 4;
     const int lanes = 256 / c4 > 0 ? 256 / c4 : 1;
-    const int threads = lanes * c4;
+    const int threads = ((lanes * c4 + 31) / 32) * 32;
     const size_t smem = (size_t)lanes * c * 2 * sizeof(double);
     dim3 grid(nchunks, n);
     if (dt == F32) gn_partial_kernel<float><<<grid, threads, smem, s>>>((const float*)x, hw, c, nchunks, scratch);
     else gn_partial_kernel<__half><<<grid, threads, smem, s>>>((const __half*)x, hw, c, nchunks, scratch);
     CUDA_CHECK(cudaGetLastError());
-    const int warps = n * (c / cpg);
-    gn_finalize_kernel<<<cdiv(warps, 8), 256, 0, s>>>(scratch, n, hw, c, cpg, nchunks, eps, gamma, beta, scale, shift, c_total,
-                                                      c_off);
+    gn_finalize_kernel<<<n * (c / cpg), 128, 0, s>>>(scratch, hw, c, cpg, nchunks, eps, gamma, beta, scale, shift, c_total, c_off);
     CUDA_CHECK(cudaGetLastError());
 }
 

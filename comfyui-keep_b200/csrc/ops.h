@@ -58,6 +58,7 @@ void bgemm_simt(const BGemmArgs& a, cudaStream_t s);
 //   writes scale/shift at [n][c_total] + c_off  (c_total >= c, for concatenated inputs)
 //   scratch: gn_scratch_doubles(...) doubles
 size_t gn_scratch_doubles(int n, int hw, int c);
+void gn_warmup();   // allocate the per-device ticket array (must happen outside CUDA-graph capture)
 void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, float eps,
                       const float* gamma, const float* beta, float* scale, float* shift,
                       int c_total, int c_off, double* scratch, cudaStream_t s);

@@ -10,6 +10,7 @@ struct TcConvArgs {
     const float* pre_scale; const float* pre_shift; int pre_act;
     const __half* wt; const float* bias;
     int taps, cout, bn, ho, wo, ncb;
+    int win, s2d, ncbr, pad_t, pad_l;   // window mode (3 / 2 / 1); stride-2 virtual space-to-depth parameters
     int tiles_y, tiles_x, ntile_n;
     int splitk; float* partial;
     int act; const void* res; int res_dt; void* out; int out_dt;
@@ -25,8 +26,11 @@ bool tc_eligible(const ConvArgs& a);
 int tc_pick_bn(int cout, long long m_tiles, int passes);
 int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb);
 size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn, int passes);
+bool tc_is_s2d(const ConvArgs& a);
+int tc_virtual_cin(const ConvArgs& a);   // 4 * ceil(cin/64) * 64 for the stride-2 mode, else cin
 void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out);
-void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, __half* out, cudaStream_t s);
+// s2d_pad < 0: plain repack; else stride-2 mode with pad_t = pad_l = s2d_pad (weights indexed [9*cin][cout])
+void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s);
 // partial: splitk * M * cout floats when splitk > 1
 void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
                cudaStream_t s);

@@ -110,3 +110,39 @@ def test_conv_tcgen05_split_precision_matches_fp32(lib, case):
     with open(os.path.join(ROOT, "gpurun_out", "tc_op_report.txt"), "a") as f:
         f.write("split3 %s err=%.3e max=%.3f\n" % (name, err, float(want.abs().max())))
     assert err <= 2e-5 * max(1.0, float(want.abs().max())), "%s: max abs err %g" % (name, err)
+
+
+S2_CASES = [
+    # name, n, cin, h, w, cout, pads(t,l,b,r), pre, pre_act
+    ("vq_down_64", 2, 64, 64, 48, 64, (0, 0, 1, 1), False, "none"),
+    ("vq_down_256", 1, 256, 64, 64, 256, (0, 0, 1, 1), False, "none"),
+    ("vq_down_128_big", 1, 128, 256, 256, 128, (0, 0, 1, 1), False, "none"),
+    ("gm_s2_64_96", 2, 64, 64, 64, 96, (1, 1, 1, 1), True, "relu"),
+    ("gm_s2_96_128", 2, 96, 32, 32, 128, (1, 1, 1, 1), False, "none"),
+]
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("case", S2_CASES, ids=[c[0] for c in S2_CASES])
+def test_conv_tcgen05_stride2_virtual_s2d(lib, case, mode):
+    """3x3 stride-2 convolutions run as a 2x2 window over the virtual space-to-depth input (4*Cin channels)."""
+    name, n, cin, h, w, cout, pads, pre, pre_act = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) & 0xFFFF)
+    x = torch.randn((n, cin, h, w), generator=g).cuda()
+    wt = (torch.randn((cout, cin, 3, 3), generator=g) / math.sqrt(cin * 9)).cuda()
+    b = torch.randn((cout,), generator=g).cuda()
+    prep = None
+    if pre:
+        prep = (1.0 + 0.2 * torch.randn((n, cin), generator=g)).cuda(), (0.2 * torch.randn((n, cin), generator=g)).cuda()
+    if mode == 1:
+        xa = x if prep is None else x * prep[0][:, :, None, None] + prep[1][:, :, None, None]
+        want = ref_conv(_act(xa, pre_act).half().float(), wt.half().float(), b, 2, pads, 1, None, "none", "none", None)
+        tol = 2e-4
+    else:
+        want = ref_conv(x.double(), wt.double(), b.double(), 2, pads, 1, (prep[0].double(), prep[1].double()) if prep else None,
+                        pre_act, "none", None).float()
+        tol = 2e-5
+    got = run_conv(lib, x, wt, b, 2, pads, 1, prep, pre_act, "none", None, use_tc=mode)
+    torch.cuda.synchronize()
+    err = float((got - want).abs().max())
+    assert got.shape == want.shape and err <= tol * max(1.0, float(want.abs().max())), "%s mode %d: err %g" % (name, mode, err)
