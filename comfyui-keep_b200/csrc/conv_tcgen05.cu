@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         if (!stage_live(cb, tap)) continue;
                         mbar_wait(B_EMPTY(stage), phase ^ 1);
                         mbar_arrive_expect_tx(B_FULL(stage), (uint32_t)b_stage_bytes);
-                        const uint8_t* g = reinterpret_cast<const uint8_t*>(a.wt) +
+                        const uint8_t* g = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)img * a.wt_img_stride * sizeof(__half) +
                                            ((size_t)((size_t)nt * a.ncb + cb) * a.taps + tap) * (size_t)b_stage_bytes;
                         tma_bulk_g2s(smem_u32(sB + stage * b_stage_bytes), g, (uint32_t)b_stage_bytes, B_FULL(stage));
                         if (cb == cb0 && tap == 0) TC_TRACE(8, trace_l);
@@ -643,6 +643,43 @@ __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout,
 }
 }  // namespace
 
+namespace {
+// Activation matrix -> tcgen05 "weight" panels, so that C[z] = A[z] * B[z]^T (attention QK^T, PV) runs on the same kernel:
+// B[z] is (N x K) with element (n, k) at src[z*bstride + n*ld_n + k*ld_k] (ld_k = 1: row-major; ld_n = 1: transposed view).
+__global__ void tc_pack_matrix_kernel(const float* __restrict__ src, long long bstride, int ld_n, int ld_k, int N, int K, int bn,
+                                      int ncb, int nop, float alpha, size_t per_batch, size_t total, __half* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t z = idx / per_batch;
+    size_t r = idx - z * per_batch;
+    const int e = (int)(r % 8); r /= 8;
+    const int chunk = (int)(r % 8); r /= 8;
+    const int row = (int)(r % bn); r /= bn;
+    const int part = (int)(r % nop); r /= nop;
+    const int cb = (int)(r % ncb); r /= ncb;
+    const int nt = (int)r;
+    const int k = cb * CB + ((chunk ^ (row & 7)) << 3) + e;
+    const int n = nt * bn + row;
+    float v = 0.0f;
+    if (n < N && k < K) v = alpha * src[z * bstride + (size_t)n * ld_n + (size_t)k * ld_k];
+    const __half hi = __float2half_rn(v);
+    out[idx] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+}
+}  // namespace
+
+size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, int nbatch, int N, int K, int bn, int passes,
+                      float alpha, __half* out, cudaStream_t s) {
+    const int ncb = (K + CB - 1) / CB, nop = passes == 3 ? 2 : 1;
+    const size_t per_batch = tc_packed_weight_halfs(K, N, 1, bn, passes);
+    if (out) {
+        const size_t total = per_batch * nbatch;
+        tc_pack_matrix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, bstride, ld_n, ld_k, N, K, bn, ncb, nop, alpha,
+                                                                             per_batch, total, out);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    return per_batch;
+}
+
 void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s) {
     // stride-2 mode: `cin` real channels are seen as 4 * ceil(cin/64) * 64 virtual channels with a 2x2 (taps = 4) window
     const int vcin = s2d_pad >= 0 ? 4 * ((cin + CB - 1) / CB) * CB : cin;
@@ -688,6 +725,7 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     t.n = a.n; t.h = a.h; t.w = a.w; t.up = a.up;
     t.pre_scale = a.pre_scale; t.pre_shift = a.pre_shift; t.pre_act = a.pre_act;
     t.wt = packed; t.bias = a.bias;
+    t.wt_img_stride = a.wt_img_stride;
     const bool s2d = tc_is_s2d(a);
     t.s2d = s2d ? 1 : 0;
     t.win = s2d ? 2 : (a.kh == 3 ? 3 : 1);

@@ -191,6 +191,7 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
                    prop.major, prop.minor);
         num_sms_ = prop.multiProcessorCount;
         gn_warmup();
+        { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 56; if (side_sms_ < 8 || side_sms_ > num_sms_) side_sms_ = num_sms_; }
     }
     adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
     tc_passes_ = (flags & KEEP_FLAG_TC_SPLIT3) ? 3 : 1;
@@ -236,6 +237,8 @@ Engine::~Engine() {
     cudaFree(gx_);
     cudaFree(gout_);
     if (gs_) { cudaStreamDestroy(gs_); cudaEventDestroy(ev_in_); cudaEventDestroy(ev_out_); }
+    if (side_) { cudaStreamDestroy(side_); cudaEventDestroy(ev_fork_); }
+    for (auto& e : ev_flow_) cudaEventDestroy(e);
     for (auto& p : prof_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& e : ev_pool_) cudaEventDestroy(e);
 }
@@ -243,23 +246,32 @@ Engine::~Engine() {
 // =============================================================================================
 // building blocks
 // =============================================================================================
+// The workspace is split in two arenas: the main one and a side one for the GMFlow branch, which runs on its own
+// stream concurrently with the serial per-frame chain (stream-ordered reuse is only safe within one stream).
 void Engine::begin(void* ws, size_t ws_bytes, cudaStream_t s, bool dry) {
-    s_ = s;
-    if (dry) arena_.reset((char*)(uintptr_t)4096, (size_t)1 << 46, true);
-    else arena_.reset((char*)ws, ws_bytes, false);
+    s_ = s_main_ = s;
+    ar_ = &arena_;
+    if (dry) {
+        arena_.reset((char*)(uintptr_t)4096, (size_t)1 << 45, true);
+        arena2_.reset((char*)(uintptr_t)4096 + ((size_t)1 << 45), (size_t)1 << 45, true);
+    } else {
+        KEEP_CHECK(side_bytes_ > 0 && side_bytes_ < ws_bytes, "workspace split not planned");
+        arena_.reset((char*)ws, ws_bytes - side_bytes_, false);
+        arena2_.reset((char*)ws + (ws_bytes - side_bytes_), side_bytes_, false);
+    }
 }
 
 Tensor Engine::talloc(int n, int h, int w, int c, int dt) {
     Tensor t;
     t.n = n; t.h = h; t.w = w; t.c = c; t.dt = (DType)dt;
-    t.p = arena_.alloc(t.bytes());
+    t.p = ar_->alloc(t.bytes());
     return t;
 }
-void Engine::tfree(Tensor& t) { arena_.free(t.p); t.p = nullptr; }
-void Engine::afree(Aff& a) { arena_.free(a.scale); a.scale = a.shift = nullptr; }
+void Engine::tfree(Tensor& t) { ar_->free(t.p); t.p = nullptr; }
+void Engine::afree(Aff& a) { ar_->free(a.scale); a.scale = a.shift = nullptr; }
 
 void Engine::capture(const std::string& name, const void* dev, size_t bytes) {
-    if (!capture_ || arena_.dry()) return;
+    if (!capture_ || ar_->dry()) return;
     Cap& c = cap_[name];
     if (c.bytes < bytes) {
         cudaFree(c.p);
@@ -305,10 +317,10 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         a.splitk = use_small ? 1 : conv_pick_splitk(a);
     }
     if (a.splitk > 1) {
-        part = arena_.alloc((size_t)a.splitk * out.numel() * sizeof(float));
+        part = ar_->alloc((size_t)a.splitk * out.numel() * sizeof(float));
         a.partial = (float*)part;
     }
-    if (!arena_.dry()) {
+    if (!ar_->dry()) {
         Prof pr;
         if (profile_) {
             pr.a = get_event(); pr.b = get_event();
@@ -319,7 +331,10 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             pr.m = (int)out.rows(); pr.k = cw.kh * cw.kw * cw.cin; pr.n = cw.cout; pr.kh = cw.kh * 10 + o.stride; pr.splitk = a.splitk; pr.bn = bn;
             CUDA_CHECK(cudaEventRecord(pr.a, s_));
         }
-        if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_, tc_is_s2d(a) ? a.pad_t : -1), bn, tc_passes_, a.splitk, a.partial, num_sms_, s_);
+        // side-branch (GMFlow) kernels are persistent too: cap their grid so the latency-critical serial chain on the main
+        // stream always finds free SMs
+        const int grid_cap = (s_ == side_ && side_) ? side_sms_ : num_sms_;
+        if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_, tc_is_s2d(a) ? a.pad_t : -1), bn, tc_passes_, a.splitk, a.partial, grid_cap, s_);
         else if (use_small) conv2d_small(a, s_);
         else conv2d_simt(a, s_);
         launches_ += a.splitk > 1 ? 2 : 1;
@@ -328,7 +343,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             prof_.push_back(pr);
         }
     }
-    if (part) arena_.free(part);
+    if (part) ar_->free(part);
     return out;
 }
 
@@ -360,13 +375,13 @@ Aff Engine::gn(const Tensor& x, const std::string& prefix, const Tensor* x2) {
     KEEP_CHECK(ct % 32 == 0, "GroupNorm(32): %d channels", ct);
     const int cpg = ct / 32;
     Aff a;
-    a.scale = (float*)arena_.alloc((size_t)2 * x.n * ct * sizeof(float));
+    a.scale = (float*)ar_->alloc((size_t)2 * x.n * ct * sizeof(float));
     a.shift = a.scale + (size_t)x.n * ct;
     const float* g = warr(prefix + ".weight");
     const float* b = warr(prefix + ".bias");
     const int hw = x.h * x.w;
-    double* scratch = (double*)arena_.alloc(gn_scratch_doubles(x.n, hw, std::max(x.c, x2 ? x2->c : 0)) * sizeof(double));
-    if (!arena_.dry()) {
+    double* scratch = (double*)ar_->alloc(gn_scratch_doubles(x.n, hw, std::max(x.c, x2 ? x2->c : 0)) * sizeof(double));
+    if (!ar_->dry()) {
         groupnorm_affine(x.p, x.dt, x.n, hw, x.c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, 0, scratch, s_);
         launches_ += 1;
         if (x2) {
@@ -375,21 +390,21 @@ Aff Engine::gn(const Tensor& x, const std::string& prefix, const Tensor* x2) {
             launches_ += 1;
         }
     }
-    arena_.free(scratch);
+    ar_->free(scratch);
     return a;
 }
 
 Aff Engine::inorm(const Tensor& x) {
     Aff a;
-    a.scale = (float*)arena_.alloc((size_t)2 * x.n * x.c * sizeof(float));
+    a.scale = (float*)ar_->alloc((size_t)2 * x.n * x.c * sizeof(float));
     a.shift = a.scale + (size_t)x.n * x.c;
     const int hw = x.h * x.w;
-    double* scratch = (double*)arena_.alloc(gn_scratch_doubles(x.n, hw, x.c) * sizeof(double));
-    if (!arena_.dry()) {
+    double* scratch = (double*)ar_->alloc(gn_scratch_doubles(x.n, hw, x.c) * sizeof(double));
+    if (!ar_->dry()) {
         groupnorm_affine(x.p, x.dt, x.n, hw, x.c, 1, 1e-5f, nullptr, nullptr, a.scale, a.shift, x.c, 0, scratch, s_);
         launches_ += 2;
     }
-    arena_.free(scratch);
+    ar_->free(scratch);
     return a;
 }
 
@@ -397,7 +412,7 @@ Tensor Engine::ln(const Tensor& x, const std::string& prefix, const Tensor* res,
     KEEP_CHECK(x.dt == F32, "layernorm expects fp32 tokens");
     Tensor out = talloc(x.n, x.h, x.w, x.c, F32);
     if (out2) *out2 = talloc(x.n, x.h, x.w, x.c, F32);
-    if (!arena_.dry()) {
+    if (!ar_->dry()) {
         layernorm(x.f(), (int)x.rows(), x.c, warr(prefix + ".weight"), warr(prefix + ".bias"), 1e-5f, res ? res->f() : nullptr,
                   out.f(), add2, add2_rows, out2 ? out2->f() : nullptr, s_);
         launches_ += 1;
@@ -431,12 +446,46 @@ Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2
     return out;
 }
 
+// C[z] = alpha * A[z] (M x K) * B[z]^T, B[z] = (N x K) strided view, on the tcgen05 kernel: B is packed into per-batch
+// "weight" panel sets (tc_pack_matrix) and the batch rides on the kernel's image index.  fp32 in / out.
+Tensor Engine::gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, long long b_bstride, int ld_n, int ld_k, int N,
+                          float alpha) {
+    const long long m_tiles = (long long)nb * cdiv(M, 128);
+    const int bn = tc_pick_bn(N, m_tiles, tc_passes_);
+    const size_t per = tc_pack_matrix(nullptr, 0, 0, 0, nb, N, K, bn, tc_passes_, 1.0f, nullptr, s_);
+    __half* panels = (__half*)ar_->alloc(per * nb * sizeof(__half));
+    Tensor out = talloc(nb, M, 1, N, F32);
+    if (!ar_->dry()) {
+        tc_pack_matrix(B, b_bstride, ld_n, ld_k, nb, N, K, bn, tc_passes_, alpha, panels, s_);
+        ConvArgs a;
+        a.in0 = A; a.in0_dt = F32; a.c0 = K;
+        a.n = nb; a.h = M; a.w = 1; a.up = 1;
+        a.kh = 1; a.kw = 1; a.stride = 1; a.cout = N; a.ho = M; a.wo = 1;
+        a.out = out.p; a.out_dt = F32;
+        a.wt_img_stride = (long long)per;
+        Prof pr;
+        if (profile_) {
+            pr.a = get_event(); pr.b = get_event();
+            pr.flops = 2.0 * nb * (double)M * N * K;
+            pr.bytes = 4.0 * nb * ((double)M * K + (double)N * K + (double)M * N);
+            pr.tag = 1; pr.m = nb * M; pr.k = K; pr.n = N; pr.kh = 11; pr.splitk = 1; pr.bn = bn;
+            CUDA_CHECK(cudaEventRecord(pr.a, s_));
+        }
+        const int grid_cap = (s_ == side_ && side_) ? side_sms_ : num_sms_;
+        conv2d_tc(a, panels, bn, tc_passes_, 1, nullptr, grid_cap, s_);
+        launches_ += 2;
+        if (profile_) { CUDA_CHECK(cudaEventRecord(pr.b, s_)); prof_.push_back(pr); }
+    }
+    ar_->free(panels);
+    return out;
+}
+
 // generic multi-head attention: scores -> softmax -> PV, all fp32
 Tensor Engine::mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv,
                    long long sv, int nb, int Lq, int Lk, int heads, int dh, float scale) {
     Tensor S = talloc(nb * heads, Lq, 1, Lk, F32);
     Tensor O = talloc(nb, Lq, 1, heads * dh, F32);
-    if (!arena_.dry()) {
+    if (!ar_->dry()) {
         BGemmArgs g;
         g.A = q; g.B = k; g.C = S.f();
         g.M = Lq; g.N = Lk; g.K = dh; g.lda = ldq; g.ldb = ldk; g.ldc = Lk; g.transB = 1; g.alpha = scale;
@@ -552,7 +601,7 @@ void Engine::gm_resblock(Tensor& x, Aff* x_aff, const std::string& p, int stride
     e.B = y2.p; e.b_dt = y2.dt; e.sb = a2.scale; e.bb = a2.shift; e.act_b = ACT_RELU;
     e.act_o = ACT_RELU;
     e.out = out.p; e.o_dt = out.dt; e.n = out.n; e.hw = out.h * out.w; e.c = out.c;
-    if (!arena_.dry()) { elementwise(e, s_); launches_ += 1; }
+    if (!ar_->dry()) { elementwise(e, s_); launches_ += 1; }
     if (ds) { afree(a3); tfree(d); }
     afree(a2);
     tfree(y2);
@@ -566,34 +615,45 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
     Tensor q = linear(src, p + ".q_proj"), kk = linear(tgt, p + ".k_proj"), v = linear(tgt, p + ".v_proj");
     Tensor qw = talloc(nimg * 4, L, 1, C, F32), kw = talloc(nimg * 4, L, 1, C, F32), vw = talloc(nimg * 4, L, 1, C, F32);
     const int sh = shift ? 16 : 0;
-    if (!arena_.dry()) {
+    if (!ar_->dry()) {
         window_partition(q.f(), qw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
         window_partition(kk.f(), kw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
         window_partition(v.f(), vw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
         launches_ += 3;
     }
     tfree(q); tfree(kk); tfree(v);
-    Tensor S = talloc(nimg * 4, L, 1, L, F32);
-    Tensor Ow = talloc(nimg * 4, L, 1, C, F32);
-    if (!arena_.dry()) {
-        BGemmArgs g;
-        g.A = qw.f(); g.B = kw.f(); g.C = S.f();
-        g.M = L; g.N = L; g.K = C; g.lda = C; g.ldb = C; g.ldc = L; g.transB = 1; g.alpha = 1.0f / sqrtf((float)C);
-        g.nz0 = nimg * 4;
-        g.sA[0] = (long long)L * C; g.sB[0] = (long long)L * C; g.sC[0] = (long long)L * L;
-        bgemm_simt(g, s_);
-        softmax_rows(S.f(), (long long)nimg * 4 * L, L, shift ? region_ : nullptr, 4, L, s_);
-        BGemmArgs h;
-        h.A = S.f(); h.B = vw.f(); h.C = Ow.f();
-        h.M = L; h.N = C; h.K = L; h.lda = L; h.ldb = C; h.ldc = C; h.transB = 0;
-        h.nz0 = nimg * 4;
-        h.sA[0] = (long long)L * L; h.sB[0] = (long long)L * C; h.sC[0] = (long long)L * C;
-        bgemm_simt(h, s_);
-        launches_ += 3;
+    Tensor S, Ow;
+    if (flags_ & KEEP_FLAG_TCGEN05) {
+        // window attention on the tensor cores: S = (Q K^T)/sqrt(C), softmax (+ shift mask), O = P V
+        S = gemm_nt_tc(qw.f(), nimg * 4, L, C, kw.f(), (long long)L * C, C, 1, L, 1.0f / sqrtf((float)C));
+        if (!ar_->dry()) {
+            softmax_rows(S.f(), (long long)nimg * 4 * L, L, shift ? region_ : nullptr, 4, L, s_);
+            launches_ += 1;
+        }
+        Ow = gemm_nt_tc(S.f(), nimg * 4, L, L, vw.f(), (long long)L * C, 1, C, C, 1.0f);   // B = V^T as a strided view
+    } else {
+        S = talloc(nimg * 4, L, 1, L, F32);
+        Ow = talloc(nimg * 4, L, 1, C, F32);
+        if (!ar_->dry()) {
+            BGemmArgs g;
+            g.A = qw.f(); g.B = kw.f(); g.C = S.f();
+            g.M = L; g.N = L; g.K = C; g.lda = C; g.ldb = C; g.ldc = L; g.transB = 1; g.alpha = 1.0f / sqrtf((float)C);
+            g.nz0 = nimg * 4;
+            g.sA[0] = (long long)L * C; g.sB[0] = (long long)L * C; g.sC[0] = (long long)L * L;
+            bgemm_simt(g, s_);
+            softmax_rows(S.f(), (long long)nimg * 4 * L, L, shift ? region_ : nullptr, 4, L, s_);
+            BGemmArgs h;
+            h.A = S.f(); h.B = vw.f(); h.C = Ow.f();
+            h.M = L; h.N = C; h.K = L; h.lda = L; h.ldb = C; h.ldc = C; h.transB = 0;
+            h.nz0 = nimg * 4;
+            h.sA[0] = (long long)L * L; h.sB[0] = (long long)L * C; h.sC[0] = (long long)L * C;
+            bgemm_simt(h, s_);
+            launches_ += 3;
+        }
     }
     tfree(S); tfree(qw); tfree(kw); tfree(vw);
     Tensor O = talloc(nimg, H * Wd, 1, C, F32);
-    if (!arena_.dry()) { window_merge(Ow.f(), O.f(), nimg, H, Wd, C, k, sh, sh, s_); launches_ += 1; }
+    if (!ar_->dry()) { window_merge(Ow.f(), O.f(), nimg, H, Wd, C, k, sh, sh, s_); launches_ += 1; }
     tfree(Ow);
     Tensor m = linear(O, p + ".merge");
     tfree(O);
@@ -626,7 +686,7 @@ void Engine::gmflow(const float* x_nchw, int T, float* flows) {
         const int np = std::min(chunk, T - 1 - p0);
         // images: [img0 = frames p0+1 .. p0+np | img1 = frames p0 .. p0+np-1], ImageNet-normalised NHWC
         Tensor img = talloc(2 * np, 512, 512, 3, F32);
-        if (!arena_.dry()) {
+        if (!ar_->dry()) {
             nchw_to_nhwc(x_nchw + (size_t)(p0 + 1) * 3 * HW, img.p, F32, np, 3, 512, 512, 1, s_);
             nchw_to_nhwc(x_nchw + (size_t)p0 * 3 * HW, (float*)img.p + (size_t)np * HW * 3, F32, np, 3, 512, 512, 1, s_);
             launches_ += 2;
@@ -648,14 +708,14 @@ void Engine::gmflow(const float* x_nchw, int T, float* flows) {
         oc.out_dt = F32;
         Tensor feat = conv(x, P + ".backbone.conv2", oc);   // (2np, 64, 64, 128)
         tfree(x);
-        if (!arena_.dry()) { add_window_sine_pos(feat.f(), 2 * np, 64, 64, 128, 2, s_); launches_ += 1; }
+        if (!ar_->dry()) { add_window_sine_pos(feat.f(), 2 * np, 64, 64, 128, 2, s_); launches_ += 1; }
         // transformer (gmflow/transformer.py:273-322): c0 = [f0; f1], c1 = [f1; f0]
         Tensor c0 = feat;
         c0.h = 4096; c0.w = 1;
         Tensor c1 = talloc(2 * np, 4096, 1, 128, F32);
         const size_t half = (size_t)np * 4096 * 128;
         auto swap_into_c1 = [&]() {
-            if (arena_.dry()) return;
+            if (ar_->dry()) return;
             CUDA_CHECK(cudaMemcpyAsync(c1.f(), c0.f() + half, half * sizeof(float), cudaMemcpyDeviceToDevice, s_));
             CUDA_CHECK(cudaMemcpyAsync(c1.f() + half, c0.f(), half * sizeof(float), cudaMemcpyDeviceToDevice, s_));
         };
@@ -672,24 +732,36 @@ void Engine::gmflow(const float* x_nchw, int T, float* flows) {
         f0.n = np;
         const float* f1 = c0.f() + half;
         // global correlation softmax (gmflow/matching.py:7-36)
-        Tensor S = talloc(np, 4096, 1, 4096, F32);
+        const bool tcg = (flags_ & KEEP_FLAG_TCGEN05) != 0;
+        Tensor S;
         Tensor flow = talloc(np, 64, 64, 2, F32);
-        if (!arena_.dry()) {
-            BGemmArgs g;
-            g.A = f0.f(); g.B = f1; g.C = S.f();
-            g.M = 4096; g.N = 4096; g.K = 128; g.lda = 128; g.ldb = 128; g.ldc = 4096; g.transB = 1;
-            g.alpha = 1.0f / sqrtf(128.0f);
-            g.nz0 = np;
-            g.sA[0] = 4096LL * 128; g.sB[0] = 4096LL * 128; g.sC[0] = 4096LL * 4096;
-            bgemm_simt(g, s_);
+        if (tcg) {
+            S = gemm_nt_tc(f0.f(), np, 4096, 128, f1, 4096LL * 128, 128, 1, 4096, 1.0f / sqrtf(128.0f));
+        } else {
+            S = talloc(np, 4096, 1, 4096, F32);
+            if (!ar_->dry()) {
+                BGemmArgs g;
+                g.A = f0.f(); g.B = f1; g.C = S.f();
+                g.M = 4096; g.N = 4096; g.K = 128; g.lda = 128; g.ldb = 128; g.ldc = 4096; g.transB = 1;
+                g.alpha = 1.0f / sqrtf(128.0f);
+                g.nz0 = np;
+                g.sA[0] = 4096LL * 128; g.sB[0] = 4096LL * 128; g.sC[0] = 4096LL * 4096;
+                bgemm_simt(g, s_);
+                launches_ += 1;
+            }
+        }
+        if (!ar_->dry()) {
             softmax_expect2(S.f(), (long long)np * 4096, 4096, 4096, grid64_, 0, grid64_, flow.f(), s_);
-            launches_ += 2;
+            launches_ += 1;
         }
         // flow propagation (gmflow/transformer.py:343-374): q = q_proj(f0), k = k_proj(q)
         Tensor q = linear(f0, P + ".feature_flow_attn.q_proj");
         Tensor kq = linear(q, P + ".feature_flow_attn.k_proj");
         Tensor flow2 = talloc(np, 64, 64, 2, F32);
-        if (!arena_.dry()) {
+        if (tcg) {
+            tfree(S);
+            S = gemm_nt_tc(q.f(), np, 4096, 128, kq.f(), 4096LL * 128, 128, 1, 4096, 1.0f / sqrtf(128.0f));
+        } else if (!ar_->dry()) {
             BGemmArgs g;
             g.A = q.f(); g.B = kq.f(); g.C = S.f();
             g.M = 4096; g.N = 4096; g.K = 128; g.lda = 128; g.ldb = 128; g.ldc = 4096; g.transB = 1;
@@ -697,8 +769,11 @@ void Engine::gmflow(const float* x_nchw, int T, float* flows) {
             g.nz0 = np;
             g.sA[0] = 4096LL * 128; g.sB[0] = 4096LL * 128; g.sC[0] = 4096LL * 4096;
             bgemm_simt(g, s_);
+            launches_ += 1;
+        }
+        if (!ar_->dry()) {
             softmax_expect2(S.f(), (long long)np * 4096, 4096, 4096, flow.f(), 4096LL * 2, nullptr, flow2.f(), s_);
-            launches_ += 2;
+            launches_ += 1;
         }
         tfree(S); tfree(q); tfree(kq); tfree(flow);
         // convex x8 upsampling (gmflow/gmflow.py:74-88): conv3x3 on cat(flow, feature0) -> ReLU -> 1x1 -> 576 logits
@@ -711,11 +786,12 @@ void Engine::gmflow(const float* x_nchw, int T, float* flows) {
         om.out_dt = F32;
         Tensor mask = conv(u, P + ".upsampler.2", om);
         tfree(u);
-        if (!arena_.dry()) {
+        if (!ar_->dry()) {
             convex_upsample8(mask.f(), flow2.f(), flows + (size_t)p0 * HW * 2, np, 64, 64, s_);
             launches_ += 1;
         }
         tfree(mask); tfree(flow2); tfree(c0);
+        if (!ar_->dry() && s_ == side_ && side_) CUDA_CHECK(cudaEventRecord(ev_flow_[p0 / chunk], side_));
     }
 }
 
@@ -726,7 +802,7 @@ Tensor Engine::kalman_gains(const Tensor& z_codes, int T) {
     const int L = 256, C = 256, heads = 8, dh = 48, inner = heads * dh;
     const float scale = 1.0f / sqrtf((float)dh);
     Tensor h = talloc(1, T * L, 1, C, F32);
-    if (!arena_.dry()) CUDA_CHECK(cudaMemcpyAsync(h.p, z_codes.p, h.bytes(), cudaMemcpyDeviceToDevice, s_));
+    if (!ar_->dry()) CUDA_CHECK(cudaMemcpyAsync(h.p, z_codes.p, h.bytes(), cudaMemcpyDeviceToDevice, s_));
     for (int blk = 0; blk < 3; ++blk) {
         const std::string p = "kalman_filter.uncertainty_estimator." + std::to_string(blk);
         // sparse-causal attention: keys/values = [frame 0 || frame i-1]
@@ -734,7 +810,7 @@ Tensor Engine::kalman_gains(const Tensor& z_codes, int T) {
         Tensor q = linear(hn, p + ".attn1.to_q"), k = linear(hn, p + ".attn1.to_k"), v = linear(hn, p + ".attn1.to_v");
         tfree(hn);
         Tensor k2 = talloc(1, T * 2 * L, 1, inner, F32), v2 = talloc(1, T * 2 * L, 1, inner, F32);
-        if (!arena_.dry()) {
+        if (!ar_->dry()) {
             sparse_causal_gather(k.f(), k2.f(), 1, T, L, inner, s_);
             sparse_causal_gather(v.f(), v2.f(), 1, T, L, inner, s_);
             launches_ += 2;
@@ -750,7 +826,7 @@ Tensor Engine::kalman_gains(const Tensor& z_codes, int T) {
         Tensor pr = linear(n3, p + ".ff.net.0.proj");
         tfree(n3);
         Tensor gg = talloc(1, T * L, 1, 4 * C, F32);
-        if (!arena_.dry()) { geglu(pr.f(), gg.f(), T * L, 4 * C, s_); launches_ += 1; }
+        if (!ar_->dry()) { geglu(pr.f(), gg.f(), T * L, 4 * C, s_); launches_ += 1; }
         tfree(pr);
         Tensor h2 = linear(gg, p + ".ff.net.2", ACT_NONE, &h1);
         tfree(gg); tfree(h1);
@@ -760,7 +836,7 @@ Tensor Engine::kalman_gains(const Tensor& z_codes, int T) {
         tfree(nt);
         Tensor St = talloc(L * heads, T, 1, T, F32);
         Tensor ot = talloc(1, T * L, 1, inner, F32);
-        if (!arena_.dry()) {
+        if (!ar_->dry()) {
             BGemmArgs g;
             g.A = qt.f(); g.B = kt.f(); g.C = St.f();
             g.M = T; g.N = T; g.K = dh; g.lda = L * inner; g.ldb = L * inner; g.ldc = T; g.transB = 1; g.alpha = scale;
@@ -831,8 +907,8 @@ Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
     Tensor logits = linear(tn, "idx_pred_layer.1");
     tfree(tn);
     Tensor quant = talloc(1, 16, 16, 256, adt_);
-    int* idx = (int*)arena_.alloc(L * sizeof(int));
-    if (!arena_.dry()) {
+    int* idx = (int*)ar_->alloc(L * sizeof(int));
+    if (!ar_->dry()) {
         const int* forced = nullptr;
         auto it = forced_.find("codes");
         if (it != forced_.end() && it->second.p) forced = (const int*)it->second.p + (size_t)frame * L;
@@ -848,7 +924,7 @@ Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
                 CUDA_CHECK(cudaMemcpyAsync((int*)cc.p + (size_t)frame * L, idx, (size_t)L * 4, cudaMemcpyDeviceToDevice, s_));
         }
     }
-    arena_.free(idx);
+    ar_->free(idx);
     tfree(logits);
     return quant;
 }
@@ -867,7 +943,7 @@ Tensor Engine::cft(const Tensor& enc, const Tensor& dec, const std::string& p) {
     Tensor sh = conv(t1, p + ".shift.2", o2);
     tfree(t1); tfree(f);
     Tensor out = talloc(dec.n, dec.h, dec.w, dec.c, dec.dt);
-    if (!arena_.dry()) { cft_combine(dec.p, dec.dt, sc.p, sh.p, sc.dt, 1.0f, out.p, out.dt, out.numel(), s_); launches_ += 1; }
+    if (!ar_->dry()) { cft_combine(dec.p, dec.dt, sc.p, sh.p, sc.dt, 1.0f, out.p, out.dt, out.numel(), s_); launches_ += 1; }
     tfree(sc); tfree(sh);
     return out;
 }
@@ -888,7 +964,7 @@ Tensor Engine::cfa(const Tensor& cur, const Tensor& prev, const std::string& p) 
     tfree(y);
     Tensor pr = linear(x1, p + ".ff.net.0.proj");
     Tensor gg = talloc(1, L, 1, 4 * C, F32);
-    if (!arena_.dry()) { geglu(pr.f(), gg.f(), L, 4 * C, s_); launches_ += 1; }
+    if (!ar_->dry()) { geglu(pr.f(), gg.f(), L, 4 * C, s_); launches_ += 1; }
     tfree(pr);
     Tensor y2 = linear(gg, p + ".ff.net.2");
     tfree(gg);
@@ -943,7 +1019,7 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[3], Tensor 
                     tfree(x);
                     x = z2;
                 }
-                if (!arena_.dry())
+                if (!ar_->dry())
                     CUDA_CHECK(cudaMemcpyAsync(cfa_prev[ti].p, x.p, x.bytes(), cudaMemcpyDeviceToDevice, s_));
             }
         }
@@ -956,7 +1032,7 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[3], Tensor 
 // =============================================================================================
 void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtype) {
     const int HW = 512 * 512;
-    const bool dry = arena_.dry();
+    const bool dry = ar_->dry();
     // ---- persistent per-clip tensors
     Tensor flows = talloc(T - 1, 512, 512, 2, F32);
     Tensor taps[3] = {talloc(T, 16, 16, 512, adt_), talloc(T, 32, 32, 256, adt_), talloc(T, 64, 64, 256, adt_)};
@@ -965,11 +1041,38 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
 
     // ---- optical flow (batched over pairs)
     auto ff = forced_.find("flows");
+    bool flows_async = false;
     if (!dry && ff != forced_.end() && ff->second.p) {
         KEEP_CHECK(ff->second.bytes == flows.bytes(), "forced flows have the wrong size");
         CUDA_CHECK(cudaMemcpyAsync(flows.p, ff->second.p, flows.bytes(), cudaMemcpyDeviceToDevice, s_));
     } else {
+        // fork: GMFlow for all pairs runs on the side stream / side arena, overlapping the LQ encoder, the gain
+        // estimator and the serial per-frame chain (frame i only needs the flow of pair i-1).
+        if (!dry) {
+            if (!side_) {
+                int lo = 0, hi = 0;
+                CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = least urgent
+                CUDA_CHECK(cudaStreamCreateWithPriority(&side_, cudaStreamNonBlocking, lo));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+            }
+            while ((int)ev_flow_.size() < (T - 1 + 3) / 4) {
+                cudaEvent_t e;
+                CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ev_flow_.push_back(e);
+            }
+            CUDA_CHECK(cudaEventRecord(ev_fork_, s_main_));
+            CUDA_CHECK(cudaStreamWaitEvent(side_, ev_fork_, 0));
+            s_ = side_;
+        }
+        ar_ = &arena2_;
         gmflow(x_dev, T, flows.f());
+        ar_ = &arena_;
+        s_ = s_main_;
+        flows_async = !dry;
+    }
+    if (capture_ && flows_async) {   // debug capture wants the complete flows now
+        CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / 4], 0));
+        flows_async = false;
     }
     capture("flows", flows.p, flows.bytes());
 
@@ -1022,6 +1125,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
                 own_src = true;
                 if (!dry) { nchw_to_nhwc((const float*)fp->second.p + (size_t)(i - 1) * 3 * HW, src.p, F32, 1, 3, 512, 512, 0, s_); launches_ += 1; }
             }
+            if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(i - 1) / 4], 0));   // flow of pair i-1 is ready
             Tensor warped = talloc(1, 512, 512, 3, adt_);
             if (!dry) {
                 flow_warp(src.p, src.dt, flows.f() + (size_t)(i - 1) * HW * 2, warped.p, warped.dt, 1, 512, 512, 3, s_);
@@ -1052,6 +1156,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
         if (prev_out.p) tfree(prev_out);
         prev_out = img;
     }
+    if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / 4], 0));   // join the side branch
     if (prev_out.p) tfree(prev_out);
     tfree(gains);
     tfree(cfa_prev[0]); tfree(cfa_prev[1]);
@@ -1066,8 +1171,10 @@ size_t Engine::workspace_bytes(int b, int T) {
     if (it != ws_cache_.end()) return it->second;
     begin(nullptr, 0, nullptr, true);
     forward_clip(nullptr, T, nullptr, KEEP_OUT_F32);
-    const size_t need = arena_.peak() + 4096;
+    const size_t side = (arena2_.peak() + 4095) & ~(size_t)4095;
+    const size_t need = ((arena_.peak() + 4095) & ~(size_t)4095) + side + 4096;
     ws_cache_[T] = need;
+    side_cache_[T] = side;
     return need;
 }
 
@@ -1078,6 +1185,7 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
     KEEP_CHECK(out_dtype == KEEP_OUT_F32 || out_dtype == KEEP_OUT_F16, "keep_forward: bad out_dtype %d", out_dtype);
     CUDA_CHECK(cudaSetDevice(device_));
     const size_t need = workspace_bytes(1, T);
+    side_bytes_ = side_cache_[T];
     if (!ws) {
         if (own_ws_bytes_ < need) {
             CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1114,7 +1222,9 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
             // the caller's stream may be the legacy default stream, which cannot be captured: the graph lives on an
             // engine-owned non-blocking stream, ordered against the caller's stream with events
             if (!gs_) {
-                CUDA_CHECK(cudaStreamCreateWithFlags(&gs_, cudaStreamNonBlocking));
+                int lo = 0, hi = 0;
+                CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // hi = most urgent
+                CUDA_CHECK(cudaStreamCreateWithPriority(&gs_, cudaStreamNonBlocking, hi));
                 CUDA_CHECK(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
                 CUDA_CHECK(cudaEventCreateWithFlags(&ev_out_, cudaEventDisableTiming));
             }

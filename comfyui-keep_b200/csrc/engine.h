@@ -78,12 +78,13 @@ class Engine {
     // multi-head attention on (rows, ld) matrices; writes (nb*Lq, heads*dh)
     Tensor mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv, long long sv,
                int nb, int Lq, int Lk, int heads, int dh, float scale);
+    Tensor gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, long long b_bstride, int ld_n, int ld_k, int N, float alpha);
     ConvW convw(const std::string& prefix) const;
     const float* warr(const std::string& key) const;
     bool has(const std::string& key) const { return W_.count(key) != 0; }
     void begin(void* ws, size_t ws_bytes, cudaStream_t s, bool dry);
     cudaStream_t stream() const { return s_; }
-    Arena& arena() { return arena_; }
+    Arena& arena() { return *ar_; }
 
    private:
     void forward_clip(const float* x_dev, int T, void* out_dev, int out_dtype);
@@ -106,7 +107,14 @@ class Engine {
     float* wpool_ = nullptr;
     int* region_ = nullptr;      // GMFlow shifted-window region ids [4][1024]
     float* grid64_ = nullptr;    // GMFlow coordinate grid (4096, 2)
-    Arena arena_;
+    Arena arena_, arena2_;          // main / side-branch (GMFlow) workspaces
+    Arena* ar_ = &arena_;           // arena of the branch currently being enqueued
+    cudaStream_t s_main_ = nullptr, side_ = nullptr;
+    cudaEvent_t ev_fork_ = nullptr;
+    std::vector<cudaEvent_t> ev_flow_;   // one per GMFlow chunk of 4 pairs
+    size_t side_bytes_ = 0;
+    int side_sms_ = 56;                  // grid cap of persistent kernels on the side branch
+    std::unordered_map<int, size_t> side_cache_;
     cudaStream_t s_ = nullptr;
     long long launches_ = 0;
     // engine-owned workspace (used when the caller passes none)

@@ -9,6 +9,7 @@ struct TcConvArgs {
     int n, h, w, up;
     const float* pre_scale; const float* pre_shift; int pre_act;
     const __half* wt; const float* bias;
+    long long wt_img_stride;   // halfs between per-image weight panel sets (attention GEMMs); 0 for convolutions
     int taps, cout, bn, ho, wo, ncb;
     int win, s2d, ncbr, pad_t, pad_l;   // window mode (3 / 2 / 1); stride-2 virtual space-to-depth parameters
     int tiles_y, tiles_x, ntile_n;
@@ -31,6 +32,9 @@ int tc_virtual_cin(const ConvArgs& a);   // 4 * ceil(cin/64) * 64 for the stride
 void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out);
 // s2d_pad < 0: plain repack; else stride-2 mode with pad_t = pad_l = s2d_pad (weights indexed [9*cin][cout])
 void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s);
+// pack B[z] (N x K, strided) into per-batch panel sets; returns halfs per batch (out == null: size query only)
+size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, int nbatch, int N, int K, int bn, int passes,
+                      float alpha, __half* out, cudaStream_t s);
 // partial: splitk * M * cout floats when splitk > 1
 void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
                cudaStream_t s);
