@@ -144,6 +144,58 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 }  // namespace
 
+namespace {
+// Small tensors (the 16^2..64^2 maps of the serial per-frame chain): one launch, one block per (image, group) reads the
+// group's hw x cpg slab and writes its channels' affine directly -- no partial buffer, no second kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_small_kernel(const T* __restrict__ x, int hw, int c, int cpg, float eps,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float* __restrict__ scale, float* __restrict__ shift, int c_total, int c_off) {
+    __shared__ double rs[8], rq[8];
+    const int groups = c / cpg;
+    const int in = blockIdx.x / groups, g = blockIdx.x % groups;
+    const T* base = x + (size_t)in * hw * c + (size_t)g * cpg;
+    double s = 0, q = 0;
+    if ((cpg & 3) == 0) {
+        const int v4 = cpg >> 2;
+        const int total = hw * v4;
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int p = i / v4, j = i - p * v4;
+            const float4 v = ld4(base, (size_t)p * c + j * 4);
+            s += (double)((v.x + v.y) + (v.z + v.w));
+            q += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+        }
+    } else {
+        const int total = hw * cpg;
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int p = i / cpg, j = i - p * cpg;
+            const float v = ldf(base, (size_t)p * c + j);
+            s += v;
+            q += (double)v * v;
+        }
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; }
+    __syncthreads();
+    s = ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7]));
+    q = ((rq[0] + rq[1]) + (rq[2] + rq[3])) + ((rq[4] + rq[5]) + (rq[6] + rq[7]));
+    const double cnt = (double)hw * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    for (int i = threadIdx.x; i < cpg; i += 256) {
+        const int ch = g * cpg + i;
+        const float ga = gamma ? gamma[c_off + ch] : 1.0f;
+        const float be = beta ? beta[c_off + ch] : 0.0f;
+        const float sc = ga * rstd;
+        scale[(size_t)in * c_total + c_off + ch] = sc;
+        shift[(size_t)in * c_total + c_off + ch] = be - (float)mean * sc;
+    }
+}
+}  // namespace
+
 size_t gn_scratch_doubles(int n, int hw, int c) { return (size_t)n * gn_num_chunks(hw, c) * c * 2; }
 
 void gn_warmup() {}
@@ -151,6 +203,13 @@ void gn_warmup() {}
 void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, float eps, const float* gamma, const float* beta,
                       float* scale, float* shift, int c_total, int c_off, double* scratch, cudaStream_t s) {
     KEEP_CHECK(c % 4 == 0 && c / 4 <= 256 && c % cpg == 0, "groupnorm: unsupported shape c=%d cpg=%d", c, cpg);
+    if ((long long)hw * cpg <= 8192 && (long long)n * (c / cpg) >= 16) {   // small slab per group and enough groups to fill SMs
+        const int blocks = n * (c / cpg);
+        if (dt == F32) gn_small_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, hw, c, cpg, eps, gamma, beta, scale, shift, c_total, c_off);
+        else gn_small_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)x, hw, c, cpg, eps, gamma, beta, scale, shift, c_total, c_off);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     const int nchunks = gn_num_chunks(hw, c);
     const int c4 = c / 4;
     const int lanes = 256 / c4 > 0 ? 256 / c4 : 1;
