@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
+#include <utility>
 #include <stdexcept>
 
 namespace keep {
@@ -115,5 +117,36 @@ __device__ __forceinline__ float warp_max(float v) {
 #endif
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): ~560 small dependent kernels per frame make launch latency a first-order cost.
+// Every kernel starts with pdl_prologue(): it lets the NEXT kernel's CTAs be scheduled right away (launch_dependents) and
+// then waits until the PREVIOUS kernel has fully completed and flushed (wait), so correctness is that of plain stream
+// order while CTA dispatch / prologue latency of kernel N+1 overlaps the tail of kernel N.  Both instructions are no-ops
+// for a kernel launched without the attribute.
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Measured: triggering at the top parks the next kernel's CTAs (220 KB smem each for the tcgen05 kernel) on SMs the running
+// kernel still needs (-21%).  So kernels only *wait*; the dependent launch is released implicitly as this grid's CTAs retire,
+// which still overlaps the grid-boundary drain with the next kernel's dispatch.
+__device__ __forceinline__ void pdl_prologue() { pdl_wait(); }
+
+bool pdl_enabled();   // engine.cu: KEEP_PDL env (default on)
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+#endif
 
 }  // namespace keep

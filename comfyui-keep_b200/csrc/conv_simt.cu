@@ -42,6 +42,7 @@ __device__ __forceinline__ void store1(void* dst, int dt, size_t off, float v) {
 
 template <bool FAST>
 __global__ void __launch_bounds__(NTHREADS) conv_igemm_simt_kernel(const ConvArgs a) {
+    pdl_prologue();
     __shared__ __align__(16) float As[BK][BM];
     __shared__ __align__(16) float Bs[BK][BN];
     const int tid = threadIdx.x;
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_simt_kernel(const ConvArg
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
                                                             const float* __restrict__ bias, int act, const void* res,
                                                             int res_dt, void* out, int out_dt) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= MN) return;
     float v = 0.0f;
@@ -228,7 +230,7 @@ int conv_pick_splitk(const ConvArgs& a) {
 
 void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
                    int res_dt, void* out, int out_dt, cudaStream_t s) {
-    splitk_reduce_kernel<<<cdiv(MN, 256), 256, 0, s>>>(partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
+    launch_k(splitk_reduce_kernel, dim3(cdiv(MN, 256)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -241,12 +243,12 @@ void conv2d_simt(const ConvArgs& a, cudaStream_t s) {
     const bool fast = (a.c0 % 16 == 0) && (a.c1 % 16 == 0) && (a.cout % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.in0) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.in1) & 15) == 0);
     dim3 grid(cdiv(M, BM), cdiv(a.cout, BN), a.splitk);
-    if (fast) conv_igemm_simt_kernel<true><<<grid, NTHREADS, 0, s>>>(a);
-    else conv_igemm_simt_kernel<false><<<grid, NTHREADS, 0, s>>>(a);
+    if (fast) launch_k(conv_igemm_simt_kernel<true>, dim3(grid), dim3(NTHREADS), 0, s, a);
+    else launch_k(conv_igemm_simt_kernel<false>, dim3(grid), dim3(NTHREADS), 0, s, a);
     CUDA_CHECK(cudaGetLastError());
     if (a.splitk > 1) {
         const long long MN = M * a.cout;
-        splitk_reduce_kernel<<<cdiv(MN, 256), 256, 0, s>>>(a.partial, a.splitk, MN, a.cout, a.bias, a.act, a.res, a.res_dt,
+        launch_k(splitk_reduce_kernel, dim3(cdiv(MN, 256)), dim3(256), 0, s, a.partial, a.splitk, MN, a.cout, a.bias, a.act, a.res, a.res_dt,
                                                             a.out, a.out_dt);
         CUDA_CHECK(cudaGetLastError());
     }

@@ -16,6 +16,7 @@ template <int KS, int STRIDE>
 __global__ void __launch_bounds__(256) conv_cin3_kernel(const void* __restrict__ in, int in_dt, int n, int h, int w, int pad,
                                                         const float* __restrict__ wt, const float* __restrict__ bias, int ho, int wo,
                                                         void* __restrict__ out, int out_dt) {
+    pdl_prologue();
     constexpr int K = KS * KS * 3;
     __shared__ __align__(16) float sw[K * 64];
     for (int i = threadIdx.x; i < K * 64; i += 256) sw[i] = wt[i];
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) conv_cout4_kernel(const void* __restrict_
                                                          const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
                                                          const float* __restrict__ wt /*[9*cin][cout]*/, const float* __restrict__ bias,
                                                          int cout, float* __restrict__ out) {
+    pdl_prologue();
     extern __shared__ __align__(16) float sm[];
     float* sw = sm;                                   // [9][cin][4]
     float* sx = sm + 9 * cin * 4;                     // [(HT_H+2)*(HT_W+2)][HPITCH]
@@ -147,8 +149,8 @@ void conv2d_small(const ConvArgs& a, cudaStream_t s) {
     if (cin == 3) {
         const long long threads = (long long)a.n * a.ho * a.wo * 4;
         const unsigned grid = (unsigned)((threads + 255) / 256);
-        if (a.kh == 3) conv_cin3_kernel<3, 1><<<grid, 256, 0, s>>>(a.in0, a.in0_dt, a.n, a.h, a.w, 1, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);
-        else conv_cin3_kernel<7, 2><<<grid, 256, 0, s>>>(a.in0, a.in0_dt, a.n, a.h, a.w, 3, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);
+        if (a.kh == 3) launch_k(conv_cin3_kernel<3, 1>, dim3(grid), dim3(256), 0, s, a.in0, a.in0_dt, a.n, a.h, a.w, 1, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);
+        else launch_k(conv_cin3_kernel<7, 2>, dim3(grid), dim3(256), 0, s, a.in0, a.in0_dt, a.n, a.h, a.w, 3, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);
     } else {
         const int tiles = ((a.w + HT_W - 1) / HT_W) * ((a.h + HT_H - 1) / HT_H);
         const size_t smem = (size_t)(9 * cin * 4 + (HT_H + 2) * (HT_W + 2) * HPITCH) * sizeof(float);
@@ -157,7 +159,7 @@ void conv2d_small(const ConvArgs& a, cudaStream_t s) {
             CUDA_CHECK(cudaFuncSetAttribute(conv_cout4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             configured = true;
         }
-        conv_cout4_kernel<<<a.n * tiles, 256, smem, s>>>(a.in0, a.in0_dt, a.n, a.h, a.w, cin, a.pre_scale, a.pre_shift, a.wt, a.bias,
+        launch_k(conv_cout4_kernel, dim3(a.n * tiles), dim3(256), smem, s, a.in0, a.in0_dt, a.n, a.h, a.w, cin, a.pre_scale, a.pre_shift, a.wt, a.bias,
                                                          a.cout, (float*)a.out);
     }
     CUDA_CHECK(cudaGetLastError());

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // barrier init + TMEM allocation above overlapped the previous kernel's tail; inputs are read below
 
     const int win = a.win;                 // 3: 3x3 s1 | 2: 3x3 stride-2 as a 2x2 window over the virtual space-to-depth input | 1: 1x1
     const bool conv3 = win > 1;            // halo-tile modes
@@ -617,6 +618,7 @@ namespace {
 // device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 swizzled panels
 __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int nop, int s2d_pad,
                                  size_t total, __half* __restrict__ out) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     size_t r = idx;
@@ -648,6 +650,7 @@ namespace {
 // B[z] is (N x K) with element (n, k) at src[z*bstride + n*ld_n + k*ld_k] (ld_k = 1: row-major; ld_n = 1: transposed view).
 __global__ void tc_pack_matrix_kernel(const float* __restrict__ src, long long bstride, int ld_n, int ld_k, int N, int K, int bn,
                                       int ncb, int nop, float alpha, size_t per_batch, size_t total, __half* __restrict__ out) {
+    pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const size_t z = idx / per_batch;
@@ -673,7 +676,7 @@ size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, i
     const size_t per_batch = tc_packed_weight_halfs(K, N, 1, bn, passes);
     if (out) {
         const size_t total = per_batch * nbatch;
-        tc_pack_matrix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, bstride, ld_n, ld_k, N, K, bn, ncb, nop, alpha,
+        launch_k(tc_pack_matrix_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, bstride, ld_n, ld_k, N, K, bn, ncb, nop, alpha,
                                                                              per_batch, total, out);
         CUDA_CHECK(cudaGetLastError());
     }
@@ -686,7 +689,7 @@ void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, in
     const int vtaps = s2d_pad >= 0 ? 4 : taps;
     const int ncb = (vcin + CB - 1) / CB;
     const size_t total = tc_packed_weight_halfs(vcin, cout, vtaps, bn, passes);
-    tc_repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_kc, cin, cout, vtaps, bn, ncb, passes == 3 ? 2 : 1, s2d_pad, total, out);
+    launch_k(tc_repack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, w_kc, cin, cout, vtaps, bn, ncb, passes == 3 ? 2 : 1, s2d_pad, total, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -769,11 +772,11 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     const int grid = (int)std::min<long long>(total, num_sms);
     const bool f16 = a.in0_dt == F16;
     if (passes == 3) {
-        if (f16) conv_tc_kernel<3, true><<<grid, kThreads, smem, s>>>(t);
-        else conv_tc_kernel<3, false><<<grid, kThreads, smem, s>>>(t);
+        if (f16) launch_k(conv_tc_kernel<3, true>, dim3(grid), dim3(kThreads), smem, s, t);
+        else launch_k(conv_tc_kernel<3, false>, dim3(grid), dim3(kThreads), smem, s, t);
     } else {
-        if (f16) conv_tc_kernel<1, true><<<grid, kThreads, smem, s>>>(t);
-        else conv_tc_kernel<1, false><<<grid, kThreads, smem, s>>>(t);
+        if (f16) launch_k(conv_tc_kernel<1, true>, dim3(grid), dim3(kThreads), smem, s, t);
+        else launch_k(conv_tc_kernel<1, false>, dim3(grid), dim3(kThreads), smem, s, t);
     }
     CUDA_CHECK(cudaGetLastError());
     if (splitk > 1) splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);

@@ -9,6 +9,12 @@
 
 namespace keep {
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KEEP_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 // =============================================================================================
 // Arena
 // =============================================================================================

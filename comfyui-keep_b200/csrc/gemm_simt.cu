@@ -12,6 +12,7 @@ constexpr int TM = 64, TN = 64, TK = 16;
 
 template <bool TRANSB>
 __global__ void __launch_bounds__(256) bgemm_kernel(const BGemmArgs a, int vecA, int vecB) {
+    pdl_prologue();
     __shared__ __align__(16) float As[TK][TM + 4];
     __shared__ __align__(16) float Bs[TK][TN + 4];
     const int tid = threadIdx.x;
@@ -118,8 +119,8 @@ void bgemm_simt(const BGemmArgs& a, cudaStream_t s) {
     };
     const int vecA = al4(a.A, a.lda, a.sA), vecB = al4(a.B, a.ldb, a.sB);
     dim3 grid(cdiv(a.M, TM), cdiv(a.N, TN), (unsigned)nz);
-    if (a.transB) bgemm_kernel<true><<<grid, 256, 0, s>>>(a, vecA, vecB);
-    else bgemm_kernel<false><<<grid, 256, 0, s>>>(a, vecA, vecB);
+    if (a.transB) launch_k(bgemm_kernel<true>, dim3(grid), dim3(256), 0, s, a, vecA, vecB);
+    else launch_k(bgemm_kernel<false>, dim3(grid), dim3(256), 0, s, a, vecA, vecB);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -22,6 +22,7 @@ __device__ __forceinline__ void st1_any(void* p, int dt, size_t i, float v) {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) elementwise_kernel(const EwArgs a, size_t n4) {
+    pdl_prologue();
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= n4) return;
     const size_t i = i4 * 4;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwArgs a, size_t
 
 __global__ void __launch_bounds__(256) cft_combine_kernel(const void* dec, int dec_dt, const void* scale, const void* shift,
                                                           int ss_dt, float cond, void* out, int o_dt, size_t n4) {
+    pdl_prologue();
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= n4) return;
     const size_t i = i4 * 4;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256) cft_combine_kernel(const void* dec, int d
 
 __global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ in, float* __restrict__ out, size_t total4,
                                                     int inner) {
+    pdl_prologue();
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= total4) return;
     const size_t i = i4 * 4;
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ in
 // one warp per row, L <= 1024
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, long long rows, int L,
                                                            const int* __restrict__ region, int n_win, int Lq) {
+    pdl_prologue();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -130,6 +134,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s
 __global__ void __launch_bounds__(256) softmax_expect2_kernel(const float* __restrict__ s, int L, int Lq,
                                                               const float* __restrict__ v, long long v_bstride,
                                                               const float* __restrict__ sub, float* __restrict__ out) {
+    pdl_prologue();
     __shared__ float red[3][8];
     const long long row = blockIdx.x;
     const float* r = s + (size_t)row * L;
@@ -169,6 +174,7 @@ __global__ void __launch_bounds__(256) softmax_expect2_kernel(const float* __res
 __global__ void __launch_bounds__(256) kalman_update_kernel(const float* __restrict__ z, const float* __restrict__ zp,
                                                             const float* __restrict__ gain, float* __restrict__ out,
                                                             size_t total, int c) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float g = gain[i / c];
@@ -180,6 +186,7 @@ __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restr
                                                             const float* __restrict__ codebook, int cdim,
                                                             const int* __restrict__ forced, int* __restrict__ idx_out,
                                                             void* quant, int q_dt) {
+    pdl_prologue();
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (tok >= tokens) return;
     const float* r = logits + (size_t)tok * ncodes;
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restr
 
 __global__ void __launch_bounds__(256) sparse_causal_gather_kernel(const float* __restrict__ kv, float* __restrict__ out,
                                                                    int T, int L, int c4, size_t total4) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int cc = (int)(i % c4);
@@ -217,6 +225,7 @@ __global__ void __launch_bounds__(256) sparse_causal_gather_kernel(const float* 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, void* out, int o_dt, int c, int hw,
                                                            size_t total, int mode) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
     if (i >= total) return;
     const size_t n = i / hw, p = i % hw;
@@ -234,6 +243,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const void* x, int dt, void* out, int o_dt, int c, int hw,
                                                            size_t total) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
     if (i >= total) return;
     const size_t n = i / hw, p = i % hw;
@@ -243,6 +253,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const void* x, int dt
 // arch_util.py:113-144 -> F.grid_sample(bilinear, zeros, align_corners=True)
 __global__ void __launch_bounds__(256) flow_warp_kernel(const void* img, int dt, const float* __restrict__ flow, void* out,
                                                         int o_dt, int h, int w, int c, size_t total) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*h*w
     if (i >= total) return;
     const int x = (int)(i % w);
@@ -276,6 +287,7 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const void* img, int dt,
 // gmflow/position.py:26-46 on (h/splits, w/splits) windows, tiled over the map (gmflow/utils.py:66-86)
 __global__ void __launch_bounds__(256) add_window_sine_pos_kernel(float* __restrict__ x, int h, int w, int c, int splits,
                                                                   size_t total) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int ch = (int)(i % c);
@@ -296,6 +308,7 @@ __global__ void __launch_bounds__(256) add_window_sine_pos_kernel(float* __restr
 __global__ void __launch_bounds__(256) window_partition_kernel(const float* __restrict__ x, float* __restrict__ out, int h, int w,
                                                                int c4, int k, int sh, int sw, int ldx4, size_t total4,
                                                                int merge) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over windowed layout (n*k*k, wh*ww, c4)
     if (i >= total4) return;
     const int wh = h / k, ww = w / k;
@@ -314,6 +327,7 @@ __global__ void __launch_bounds__(256) window_partition_kernel(const float* __re
 
 __global__ void __launch_bounds__(256) convex_upsample8_kernel(const float* __restrict__ mask, const float* __restrict__ flow,
                                                                float* __restrict__ out, int h, int w, size_t total) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n * 8h * 8w
     if (i >= total) return;
     const int W8 = 8 * w, H8 = 8 * h;
@@ -342,6 +356,7 @@ __global__ void __launch_bounds__(256) convex_upsample8_kernel(const float* __re
 
 __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
                                                       float* __restrict__ out, size_t total) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int ct = ca + cb;
@@ -357,46 +372,46 @@ static inline unsigned blocks_for(size_t n, int t = 256) { return (unsigned)((n 
 void elementwise(const EwArgs& a, cudaStream_t s) {
     KEEP_CHECK(a.c % 4 == 0, "elementwise: c %% 4 != 0");
     const size_t n4 = (size_t)a.n * a.hw * a.c / 4;
-    elementwise_kernel<<<blocks_for(n4), 256, 0, s>>>(a, n4);
+    launch_k(elementwise_kernel, dim3(blocks_for(n4)), dim3(256), 0, s, a, n4);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void cft_combine(const void* dec, int dec_dt, const void* scale, const void* shift, int ss_dt, float cond, void* out, int o_dt,
                  size_t numel, cudaStream_t s) {
     KEEP_CHECK(numel % 4 == 0, "cft_combine: numel %% 4 != 0");
-    cft_combine_kernel<<<blocks_for(numel / 4), 256, 0, s>>>(dec, dec_dt, scale, shift, ss_dt, cond, out, o_dt, numel / 4);
+    launch_k(cft_combine_kernel, dim3(blocks_for(numel / 4)), dim3(256), 0, s, dec, dec_dt, scale, shift, ss_dt, cond, out, o_dt, numel / 4);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void geglu(const float* in, float* out, int rows, int inner, cudaStream_t s) {
     KEEP_CHECK(inner % 4 == 0, "geglu: inner %% 4 != 0");
     const size_t t4 = (size_t)rows * inner / 4;
-    geglu_kernel<<<blocks_for(t4), 256, 0, s>>>(in, out, t4, inner);
+    launch_k(geglu_kernel, dim3(blocks_for(t4)), dim3(256), 0, s, in, out, t4, inner);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void softmax_rows(float* sc, long long rows, int L, const int* region, int n_win, int Lq, cudaStream_t s) {
     KEEP_CHECK(L <= 1024, "softmax_rows: L=%d > 1024", L);
     KEEP_CHECK(!region || Lq == L, "softmax_rows: region mask needs square windows");
-    softmax_rows_kernel<<<blocks_for((size_t)rows, 8), 256, 0, s>>>(sc, rows, L, region, n_win > 0 ? n_win : 1, Lq > 0 ? Lq : 1);
+    launch_k(softmax_rows_kernel, dim3(blocks_for((size_t)rows, 8)), dim3(256), 0, s, sc, rows, L, region, n_win > 0 ? n_win : 1, Lq > 0 ? Lq : 1);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void softmax_expect2(const float* sc, long long rows, int L, int Lq, const float* v, long long v_bstride, const float* sub,
                      float* out, cudaStream_t s) {
-    softmax_expect2_kernel<<<(unsigned)rows, 256, 0, s>>>(sc, L, Lq, v, v_bstride, sub, out);
+    launch_k(softmax_expect2_kernel, dim3((unsigned)rows), dim3(256), 0, s, sc, L, Lq, v, v_bstride, sub, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void kalman_update(const float* z, const float* zp, const float* gain, float* out, int pixels, int c, cudaStream_t s) {
     const size_t total = (size_t)pixels * c;
-    kalman_update_kernel<<<blocks_for(total), 256, 0, s>>>(z, zp, gain, out, total, c);
+    launch_k(kalman_update_kernel, dim3(blocks_for(total)), dim3(256), 0, s, z, zp, gain, out, total, c);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void argmax_gather(const float* logits, int tokens, int ncodes, const float* codebook, int cdim, const int* forced_idx,
                    int* idx_out, void* quant, int q_dt, cudaStream_t s) {
-    argmax_gather_kernel<<<blocks_for((size_t)tokens, 8), 256, 0, s>>>(logits, tokens, ncodes, codebook, cdim, forced_idx,
+    launch_k(argmax_gather_kernel, dim3(blocks_for((size_t)tokens, 8)), dim3(256), 0, s, logits, tokens, ncodes, codebook, cdim, forced_idx,
                                                                       idx_out, quant, q_dt);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -404,31 +419,31 @@ void argmax_gather(const float* logits, int tokens, int ncodes, const float* cod
 void sparse_causal_gather(const float* kv, float* out, int b, int T, int L, int c, cudaStream_t s) {
     KEEP_CHECK(c % 4 == 0, "sparse_causal_gather: c %% 4");
     const size_t t4 = (size_t)b * T * 2 * L * (c / 4);
-    sparse_causal_gather_kernel<<<blocks_for(t4), 256, 0, s>>>(kv, out, T, L, c / 4, t4);
+    launch_k(sparse_causal_gather_kernel, dim3(blocks_for(t4)), dim3(256), 0, s, kv, out, T, L, c / 4, t4);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void nchw_to_nhwc(const float* x, void* out, int o_dt, int n, int c, int h, int w, int mode, cudaStream_t s) {
     const size_t total = (size_t)n * h * w;
-    nchw_to_nhwc_kernel<<<blocks_for(total), 256, 0, s>>>(x, out, o_dt, c, h * w, total, mode);
+    launch_k(nchw_to_nhwc_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, out, o_dt, c, h * w, total, mode);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s) {
     const size_t total = (size_t)n * h * w;
-    nhwc_to_nchw_kernel<<<blocks_for(total), 256, 0, s>>>(x, dt, out, out_dt, c, h * w, total);
+    launch_k(nhwc_to_nchw_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, dt, out, out_dt, c, h * w, total);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void flow_warp(const void* img, int dt, const float* flow, void* out, int o_dt, int n, int h, int w, int c, cudaStream_t s) {
     const size_t total = (size_t)n * h * w;
-    flow_warp_kernel<<<blocks_for(total), 256, 0, s>>>(img, dt, flow, out, o_dt, h, w, c, total);
+    launch_k(flow_warp_kernel, dim3(blocks_for(total)), dim3(256), 0, s, img, dt, flow, out, o_dt, h, w, c, total);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void add_window_sine_pos(float* x, int n, int h, int w, int c, int splits, cudaStream_t s) {
     const size_t total = (size_t)n * h * w * c;
-    add_window_sine_pos_kernel<<<blocks_for(total), 256, 0, s>>>(x, h, w, c, splits, total);
+    launch_k(add_window_sine_pos_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, h, w, c, splits, total);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -436,26 +451,26 @@ void window_partition(const float* x, float* out, int n, int h, int w, int c, in
                       cudaStream_t s) {
     KEEP_CHECK(c % 4 == 0 && ldx % 4 == 0 && h % k == 0 && w % k == 0, "window_partition: bad shape");
     const size_t t4 = (size_t)n * h * w * (c / 4);
-    window_partition_kernel<<<blocks_for(t4), 256, 0, s>>>(x, out, h, w, c / 4, k, shift_h, shift_w, ldx / 4, t4, 0);
+    launch_k(window_partition_kernel, dim3(blocks_for(t4)), dim3(256), 0, s, x, out, h, w, c / 4, k, shift_h, shift_w, ldx / 4, t4, 0);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void window_merge(const float* x, float* out, int n, int h, int w, int c, int k, int shift_h, int shift_w, cudaStream_t s) {
     KEEP_CHECK(c % 4 == 0 && h % k == 0 && w % k == 0, "window_merge: bad shape");
     const size_t t4 = (size_t)n * h * w * (c / 4);
-    window_partition_kernel<<<blocks_for(t4), 256, 0, s>>>(x, out, h, w, c / 4, k, shift_h, shift_w, c / 4, t4, 1);
+    launch_k(window_partition_kernel, dim3(blocks_for(t4)), dim3(256), 0, s, x, out, h, w, c / 4, k, shift_h, shift_w, c / 4, t4, 1);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void convex_upsample8(const float* mask, const float* flow, float* out, int n, int h, int w, cudaStream_t s) {
     const size_t total = (size_t)n * 64 * h * w;
-    convex_upsample8_kernel<<<blocks_for(total), 256, 0, s>>>(mask, flow, out, h, w, total);
+    launch_k(convex_upsample8_kernel, dim3(blocks_for(total)), dim3(256), 0, s, mask, flow, out, h, w, total);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void concat2(const float* a, int ca, const float* b, int cb, float* out, long long rows, cudaStream_t s) {
     const size_t total = (size_t)rows * (ca + cb);
-    concat2_kernel<<<blocks_for(total), 256, 0, s>>>(a, ca, b, cb, out, total);
+    launch_k(concat2_kernel, dim3(blocks_for(total)), dim3(256), 0, s, a, ca, b, cb, out, total);
     CUDA_CHECK(cudaGetLastError());
 }
 

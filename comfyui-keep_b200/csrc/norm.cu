@@ -22,6 +22,7 @@ static inline int gn_num_chunks(int hw, int c) {
 template <typename T>
 __global__ void __launch_bounds__(256) gn_partial_kernel(const T* __restrict__ x, int hw, int c, int nchunks,
                                                          double* __restrict__ partial) {
+    pdl_prologue();
     extern __shared__ double sm[];  // [lanes][c][2]
     const int c4 = c >> 2;
     const int lanes = blockDim.x / c4;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restri
                                                           float eps, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ scale,
                                                           float* __restrict__ shift, int c_total, int c_off) {
+    pdl_prologue();
     __shared__ double rs[4], rq[4];
     const int groups = c / cpg;
     const int in = blockIdx.x / groups, g = blockIdx.x % groups;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ b, float eps, const float* __restrict__ res,
                                                         float* __restrict__ out, const float* __restrict__ add2, int add2_rows,
                                                         float* __restrict__ out2) {
+    pdl_prologue();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* xr = x + (size_t)row * c;
@@ -151,6 +154,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gn_small_kernel(const T* __restrict__ x, int hw, int c, int cpg, float eps,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ scale, float* __restrict__ shift, int c_total, int c_off) {
+    pdl_prologue();
     __shared__ double rs[8], rq[8];
     const int groups = c / cpg;
     const int in = blockIdx.x / groups, g = blockIdx.x % groups;
@@ -205,8 +209,8 @@ void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, floa
     KEEP_CHECK(c % 4 == 0 && c / 4 <= 256 && c % cpg == 0, "groupnorm: unsupported shape c=%d cpg=%d", c, cpg);
     if ((long long)hw * cpg <= 8192 && (long long)n * (c / cpg) >= 16) {   // small slab per group and enough groups to fill SMs
         const int blocks = n * (c / cpg);
-        if (dt == F32) gn_small_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, hw, c, cpg, eps, gamma, beta, scale, shift, c_total, c_off);
-        else gn_small_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)x, hw, c, cpg, eps, gamma, beta, scale, shift, c_total, c_off);
+        if (dt == F32) launch_k(gn_small_kernel<float>, dim3(blocks), dim3(256), 0, s, (const float*)x, hw, c, cpg, eps, gamma, beta, scale, shift, c_total, c_off);
+        else launch_k(gn_small_kernel<__half>, dim3(blocks), dim3(256), 0, s, (const __half*)x, hw, c, cpg, eps, gamma, beta, scale, shift, c_total, c_off);
         CUDA_CHECK(cudaGetLastError());
         return;
     }
@@ -216,17 +220,17 @@ void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, floa
     const int threads = ((lanes * c4 + 31) / 32) * 32;
     const size_t smem = (size_t)lanes * c * 2 * sizeof(double);
     dim3 grid(nchunks, n);
-    if (dt == F32) gn_partial_kernel<float><<<grid, threads, smem, s>>>((const float*)x, hw, c, nchunks, scratch);
-    else gn_partial_kernel<__half><<<grid, threads, smem, s>>>((const __half*)x, hw, c, nchunks, scratch);
+    if (dt == F32) launch_k(gn_partial_kernel<float>, dim3(grid), dim3(threads), smem, s, (const float*)x, hw, c, nchunks, scratch);
+    else launch_k(gn_partial_kernel<__half>, dim3(grid), dim3(threads), smem, s, (const __half*)x, hw, c, nchunks, scratch);
     CUDA_CHECK(cudaGetLastError());
-    gn_finalize_kernel<<<n * (c / cpg), 128, 0, s>>>(scratch, hw, c, cpg, nchunks, eps, gamma, beta, scale, shift, c_total, c_off);
+    launch_k(gn_finalize_kernel, dim3(n * (c / cpg)), dim3(128), 0, s, scratch, hw, c, cpg, nchunks, eps, gamma, beta, scale, shift, c_total, c_off);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void layernorm(const float* x, int rows, int c, const float* g, const float* b, float eps, const float* res, float* out,
                const float* add2, int add2_rows, float* out2, cudaStream_t s) {
     KEEP_CHECK(c <= 1024, "layernorm: c=%d > 1024", c);
-    layernorm_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, rows, c, g, b, eps, res, out, add2, add2_rows > 0 ? add2_rows : 1, out2);
+    launch_k(layernorm_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, s, x, rows, c, g, b, eps, res, out, add2, add2_rows > 0 ? add2_rows : 1, out2);
     CUDA_CHECK(cudaGetLastError());
 }
 
