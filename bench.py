@@ -251,13 +251,35 @@ def main():
     net.profile(True)
     step(x)
     prof = net.profile_read()
+    dump = os.path.join(tempfile.gettempdir(), "keep_layers_%d.csv" % os.getpid())
+    net.profile_dump(dump)
     net.profile(False)
+    # the single most expensive layer shape of the family (per-launch numbers, same CUDA-event timing)
+    import collections
+    import csv as _csv
+    shapes = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for r in _csv.DictReader(open(dump)):
+        k = (int(r["tag"]), int(r["M"]), int(r["K"]), int(r["N"]))
+        shapes[k][0] += 1; shapes[k][1] += float(r["ms"]); shapes[k][2] += float(r["gflop"])
+    os.unlink(dump)
+    dom_k, dom_v = max(shapes.items(), key=lambda kv: kv[1][1])
+    ncu_path = os.path.join(ROOT, "profiles", "r1_ncu_conv_tc3_512x512_64_64.json")
+    traffic, traffic_note = None, None
+    if os.path.exists(ncu_path):
+        l0 = json.load(open(ncu_path))["launches"][0]
+        traffic = (float(l0["dram__bytes_read.sum"].split()[0]) + float(l0["dram__bytes_write.sum"].split()[0])) * 1e6
+        traffic_note = ("dram read+write bytes of ONE conv_tc_kernel<3,false> launch at M=524288 K=576 N=64 (two 512x512 frames, 64->64 3x3; "
+                        "algorithmic 268.6 MB) from profiles/r1_ncu_conv_tc3_512x512_64_64.json")
     fam = "tcgen05" if prof["tcgen05"]["gflop"] > prof["cuda_core"]["gflop"] else "cuda_core"
     pf = prof[fam]
     achieved = pf["gflop"] / max(pf["ms"], 1e-9)  # GFLOP / ms == TFLOP/s
     roofline = {
         "bound": "tensor", "kernel": "conv/linear implicit GEMM (%s path)" % fam, "achieved": achieved,
-        "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": None,
+        "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+        "traffic_note": traffic_note,
+        "dominant_shape": {"path": "tcgen05" if dom_k[0] else "cuda_core", "M": dom_k[1], "K": dom_k[2], "N": dom_k[3],
+                           "launches_per_clip": dom_v[0], "avg_us": 1e3 * dom_v[1] / dom_v[0],
+                           "tflops": dom_v[2] / max(dom_v[1], 1e-9), "share_of_family_time": dom_v[1] / max(pf["ms"], 1e-9)},
         "peak_source": pk["source"] + ", bf16 sustained", "launches_per_clip": pf["launches"], "ms_per_clip": pf["ms"],
         "gflop_per_clip": pf["gflop"], "algorithmic_gb_per_clip": pf["gbytes"],
         "hbm_achieved_gbs": pf["gbytes"] / max(pf["ms"], 1e-9) * 1e3, "hbm_peak_gbs": pk["hbm_gbs"],

@@ -122,7 +122,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Producer prologue activations are only ever swish (VQGAN) or ReLU (GMFlow); everything else is out of line.
 template <bool EXACT>
 __device__ __forceinline__ float swish_f(float v) {
-    if (EXACT) return v / (1.0f + __expf(-v));
+    if (EXACT) return __fdividef(v, 1.0f + __expf(-v));   // ex2 + rcp (<= 3 ulp); an IEEE divide costs ~20 instructions per element
     float t;   // x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU op
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
     return 0.5f * v * (1.0f + t);
