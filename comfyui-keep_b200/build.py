@@ -13,6 +13,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+# extra -D switches for A/B experiments on the GPU box, e.g. KEEP_NVCC_EXTRA="-DKEEP_PDL_TRIGGER_MAX=0" (run build.py --force with it)
+EXTRA = os.environ.get("KEEP_NVCC_EXTRA", "").split()
+
+
 def _nvcc():
     for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if c and os.path.exists(c):
@@ -46,7 +50,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -131,7 +131,16 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // Measured: triggering at the top parks the next kernel's CTAs (220 KB smem each for the tcgen05 kernel) on SMs the running
 // kernel still needs (-21%).  So kernels only *wait*; the dependent launch is released implicitly as this grid's CTAs retire,
 // which still overlaps the grid-boundary drain with the next kernel's dispatch.
-__device__ __forceinline__ void pdl_prologue() { pdl_wait(); }
+// Experiment knob (KEEP_PDL_TRIGGER_MAX, default 0 = off): let grids of at most that many CTAs trigger at the top so the next
+// kernel's prologue overlaps them.  Measured on B200 (profiles/r1_ab_pdl_side.md): 72 or 148 -> 87 frames/s vs 109 with
+// wait-only -- the cascade of parked CTAs (each holding ~200 KB of shared memory) starves the low-priority GMFlow branch.
+#ifndef KEEP_PDL_TRIGGER_MAX
+#define KEEP_PDL_TRIGGER_MAX 0
+#endif
+__device__ __forceinline__ void pdl_early_trigger() {
+    if (KEEP_PDL_TRIGGER_MAX > 0 && gridDim.x * gridDim.y * gridDim.z <= (unsigned)KEEP_PDL_TRIGGER_MAX) pdl_trigger();
+}
+__device__ __forceinline__ void pdl_prologue() { pdl_early_trigger(); pdl_wait(); }
 
 bool pdl_enabled();   // engine.cu: KEEP_PDL env (default on)
 

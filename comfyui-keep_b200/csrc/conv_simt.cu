@@ -201,9 +201,43 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_simt_kernel(const ConvArg
     }
 }
 
+// four consecutive outputs per thread (MN and cout are multiples of 4), all K-split loads of a thread in flight at once;
+// partials are summed in split order -> deterministic
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
                                                             const float* __restrict__ bias, int act, const void* res,
                                                             int res_dt, void* out, int out_dt) {
+    pdl_prologue();
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= MN) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 4 <= splitk; z += 4) {
+        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)z * MN + i));
+        const float4 p1 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)(z + 1) * MN + i));
+        const float4 p2 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)(z + 2) * MN + i));
+        const float4 p3 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)(z + 3) * MN + i));
+        v.x = (((v.x + p0.x) + p1.x) + p2.x) + p3.x; v.y = (((v.y + p0.y) + p1.y) + p2.y) + p3.y;
+        v.z = (((v.z + p0.z) + p1.z) + p2.z) + p3.z; v.w = (((v.w + p0.w) + p1.w) + p2.w) + p3.w;
+    }
+    for (; z < splitk; ++z) {
+        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)z * MN + i));
+        v.x += p0.x; v.y += p0.y; v.z += p0.z; v.w += p0.w;
+    }
+    if (bias) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + (i % cout));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (act != ACT_NONE) { v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act); }
+    if (res) {
+        const float4 r = res_dt == F32 ? ld4(reinterpret_cast<const float*>(res), (size_t)i) : ld4(reinterpret_cast<const __half*>(res), (size_t)i);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (out_dt == F32) st4(reinterpret_cast<float*>(out), (size_t)i, v);
+    else st4(reinterpret_cast<__half*>(out), (size_t)i, v);
+}
+__global__ void __launch_bounds__(256) splitk_reduce1_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
+                                                             const float* __restrict__ bias, int act, const void* res,
+                                                             int res_dt, void* out, int out_dt) {
     pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= MN) return;
@@ -230,7 +264,10 @@ int conv_pick_splitk(const ConvArgs& a) {
 
 void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
                    int res_dt, void* out, int out_dt, cudaStream_t s) {
-    launch_k(splitk_reduce_kernel, dim3(cdiv(MN, 256)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
+    if (MN % 4 != 0 || cout % 4 != 0)
+        launch_k(splitk_reduce1_kernel, dim3(cdiv(MN, 256)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
+    else
+        launch_k(splitk_reduce_kernel, dim3(cdiv(MN, 1024)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -248,9 +285,7 @@ void conv2d_simt(const ConvArgs& a, cudaStream_t s) {
     CUDA_CHECK(cudaGetLastError());
     if (a.splitk > 1) {
         const long long MN = M * a.cout;
-        launch_k(splitk_reduce_kernel, dim3(cdiv(MN, 256)), dim3(256), 0, s, a.partial, a.splitk, MN, a.cout, a.bias, a.act, a.res, a.res_dt,
-                                                            a.out, a.out_dt);
-        CUDA_CHECK(cudaGetLastError());
+        splitk_reduce(a.partial, a.splitk, MN, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);
     }
 }
 

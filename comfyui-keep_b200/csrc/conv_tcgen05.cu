@@ -6,10 +6,11 @@
 //
 //   warps 0-3   epilogue      tcgen05.ld TMEM -> registers -> {bias, activation, +residual, cast} -> HBM
 //   warp  4     MMA issuer    one thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and tcgen05.commit
-//   warp  5     weight loader one thread streams pre-packed fp16 weight panels with 1-D TMA (cp.async.bulk)
-//   warps 6-21  A producers   coalesced NHWC loads of the (16+2)x(8+2) input halo, GroupNorm/InstanceNorm
-//                             apply + swish/ReLU in registers, fp16 pack, st.shared into the UMMA
-//                             "interleaved" (no-swizzle, K-major) core-matrix layout
+//   warp  8     weight loader one thread streams pre-packed fp16 weight panels with 1-D TMA (cp.async.bulk), or
+//                             parks the layer's whole panel set in shared memory once when it fits
+//   15 warps    A producers   (warps >= 5 off scheduler 0) coalesced NHWC loads of the (16+2)x(8+2) input halo,
+//                             GroupNorm/InstanceNorm apply + swish/ReLU in registers, fp16 (hi, lo) split,
+//                             st.shared into the UMMA SWIZZLE_128B K-major layout
 //
 // Implicit GEMM without im2col traffic: the halo tile of 64 input channels is staged ONCE in shared
 // memory; the nine filter taps are nine *shifted views* of it, expressed purely through the UMMA
@@ -32,10 +33,17 @@
 namespace keep {
 namespace {
 
-constexpr int kThreads = 704;
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 5, kProdWarp0 = 6, kProdThreads = 512;   // 16 producer warps
-constexpr int MAX_SA = 4, MAX_SB = 6;  // barrier slots (actual pipeline depths come from the launch arguments)
-constexpr int CB = 64;                 // channels per A stage (4 MMA K-steps of 16)
+// Warp roles are laid out by SM sub-partition (warp % 4 picks the scheduler).  The MMA issuer needs ~90 instructions per
+// filter tap; sharing a scheduler with four busy producer warps stretched that to 350-550 cycles per tap, more than the
+// MMAs themselves take (measured: 88-105 clk per N=64 MMA in the kernel vs 55-64 in isolation, tools/ubench/umma_rate.cu).
+// So sub-partition 0 holds only the MMA issuer, the weight loader and one epilogue warp; the 15 producer warps live on
+// sub-partitions 1-3 next to the other three epilogue warps (tcgen05.ld ties epilogue warp w to TMEM lanes 32*(w%4)...).
+constexpr int kThreads = 768;                          // 24 warps; warps 12, 16, 20 have no role
+constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 8, kProdThreads = 480;   // producers: warps >= 5 with warp % 4 != 0
+constexpr int MAX_SA = 6, MAX_SB = 8;  // barrier slots (actual pipeline depths come from the launch arguments)
+// channels per A stage: 64 with fp16 operands (4 MMA K-steps of 16); 32 in the split-precision mode, whose 128-byte rows
+// hold [hi 32 ch | lo 32 ch] side by side (2 K-steps each), so a stage and a weight panel have the same geometry in both
+__host__ __device__ constexpr int cb_of(int passes) { return passes == 3 ? 32 : 64; }
 // A stage = halo tile in the UMMA SWIZZLE_128B K-major layout: one 128-byte row (64 channels, fp16) per halo pixel,
 // 16-byte chunks XOR-swizzled by (row & 7).  The halo is 18 rows x 10 columns but rows are PITCHED at 16 pixels, so
 // that (a) every 8-pixel group of an MMA operand view starts SBO = 16*128 = 2048 B after the previous one (a multiple
@@ -43,8 +51,7 @@ constexpr int CB = 64;                 // channels per A stage (4 MMA K-steps of
 // address base + (dy*16 + dx)*128 with descriptor base_offset = dx.  (The first version used the no-swizzle
 // "interleaved" core-matrix layout: correct, but the tensor core fetched it 16 bytes per cycle, ~300 cycles per MMA.)
 constexpr int HPITCH_PX = KEEP_TC_HPITCH;
-constexpr int A_SUB_BYTES = (18 * HPITCH_PX * 128 + 1023) / 1024 * 1024;   // one operand tile (hi); split precision appends a lo tile
-constexpr int MAXIT = 3;               // ceil(180 * 8 / 512) halo units per producer thread
+constexpr int A_SUB_BYTES = (18 * HPITCH_PX * 128 + 1023) / 1024 * 1024;   // one A stage
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -122,7 +129,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Producer prologue activations are only ever swish (VQGAN) or ReLU (GMFlow); everything else is out of line.
 template <bool EXACT>
 __device__ __forceinline__ float swish_f(float v) {
-    if (EXACT) return __fdividef(v, 1.0f + __expf(-v));   // ex2 + rcp (<= 3 ulp); an IEEE divide costs ~20 instructions per element
+    if (EXACT) {   // v * rcp(1 + ex2(-v log2 e)): 5 instructions, <= 3 ulp (__expf/__fdividef add range fix-ups: 8+; an IEEE divide ~20)
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        return v * r;
+    }
     float t;   // x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU op
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
     return 0.5f * v * (1.0f + t);
@@ -142,19 +154,23 @@ __device__ __noinline__ float act_slow(float v, int act) { return apply_act(v, a
         if (a.trace && blockIdx.x == 0 && (idx) < 16) a.trace[(slot) * 16 + (idx)] = clock64();    \
     } while (0)
 
-template <int PASSES, bool IN_F16>
+template <int PASSES, bool IN_F16, int WIN>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms are 1024-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NOP = PASSES == 3 ? 2 : 1;             // operand tiles per stage (hi [, lo])
-    constexpr int A_STAGE_BYTES = NOP * A_SUB_BYTES;
+    constexpr int CBK = cb_of(PASSES);                   // channels per A stage / weight panel
+    constexpr int UPP = CBK / 8;                         // 8-channel producer units per pixel
+    constexpr int PPI = kProdThreads / UPP;              // pixels per producer iteration
+    constexpr int MAXIT = (180 + PPI - 1) / PPI;         // halo units per producer thread and stage
+    constexpr int KSTEPS = CBK / 16;                     // MMA K-steps per operand tile
+    constexpr int A_STAGE_BYTES = A_SUB_BYTES;
     const int SA = a.sa_stages, SB = a.sb_stages;
-    const int b_panel_bytes = a.bn * 128;
-    const int b_stage_bytes = NOP * b_panel_bytes;
+    const int b_stage_bytes = a.bn * 128;                // one weight panel: bn rows x 128 bytes
     uint8_t* sA = smem;
     uint8_t* sB = smem + SA * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SB * b_stage_bytes);
+    // weight region: SB streaming stages, or (a.w_resident) every panel of the layer, loaded once per CTA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (a.w_resident ? a.ncb * WIN * WIN : SB) * b_stage_bytes);
     // barrier map: a_full[MAX_SA] a_empty[MAX_SA] b_full[MAX_SB] b_empty[MAX_SB] acc_full[2] acc_empty[2]
     const uint32_t bar0 = smem_u32(bars);
     auto A_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -166,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SA + 2 * MAX_SB + 4);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [256] bias of the current N tile
 
+    pdl_early_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_SA; ++s) { mbar_init(A_FULL(s), kProdThreads); mbar_init(A_EMPTY(s), 1); }
         for (int s = 0; s < MAX_SB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
@@ -179,9 +196,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();      // barrier init + TMEM allocation above overlapped the previous kernel's tail; inputs are read below
 
-    const int win = a.win;                 // 3: 3x3 s1 | 2: 3x3 stride-2 as a 2x2 window over the virtual space-to-depth input | 1: 1x1
-    const bool conv3 = win > 1;            // halo-tile modes
-    const int hcols = 8 + win - 1;         // halo columns (rows are pitched at HPITCH_PX pixels)
+    // WIN = 3: 3x3 s1 | 2: 3x3 stride-2 as a 2x2 window over the virtual space-to-depth input | 1: 1x1
+    constexpr int win = WIN, TAPS = WIN * WIN;
+    constexpr bool conv3 = WIN > 1;        // halo-tile modes
+    constexpr int hcols = 8 + WIN - 1;     // halo columns (rows are pitched at HPITCH_PX pixels)
     // stride-2 mode: virtual channel block cb = parity p * ncbr + real block; tap (a,b) x parity (py,px) maps to filter
     // position ky = 2a + py - pad_t, kx = 2b + px - pad_l; combinations outside the 3x3 filter are skipped entirely
     auto stage_live = [&](int cb, int tap) -> bool {
@@ -207,22 +225,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         tx = t2 - ty * a.tiles_x;
     };
 
-    if (warp >= kProdWarp0) {
+    if (warp > 4 && (warp & 3) != 0) {
         // =========================== A producers ===========================
-        const int pt = threadIdx.x - kProdWarp0 * 32;       // 0..511
-        const int pl = pt & 7;                              // 8-channel plane handled by this thread
+        const int pt = (((warp >> 2) - 1) * 3 + (warp & 3) - 1) * 32 + lane;       // 0..479
+        const int pl = pt % UPP;                            // 8-channel plane of the stage handled by this thread
         const int Hl = a.h * a.up, Wl = a.w * a.up;
-        const int npix = conv3 ? (16 + win - 1) * hcols : 128;
+        constexpr int npix = conv3 ? (16 + win - 1) * hcols : 128;
         const int cin = a.c0 + a.c1;
         const int ushift = a.up - 1;
-        // halo units of this thread: pixel p = p_first + it*64 -> (row, col) within the 18x10 halo; tile independent
-        const int p_first = pt >> 3;
-        int hy[MAXIT], hx[MAXIT];
+        // halo units of this thread: pixel p = p_first + it*PPI -> (row, col) within the halo; tile independent, and so
+        // are the shared-memory offsets of its 16-byte chunks (row-XOR swizzle; the lo half sits 4 chunks after the hi half)
+        const int p_first = pt / UPP;
+        int hy[MAXIT], hx[MAXIT], soff[MAXIT];
 #pragma unroll
         for (int it = 0; it < MAXIT; ++it) {
-            const int p = p_first + it * (kProdThreads / 8);
+            const int p = p_first + it * PPI;
             hy[it] = p / hcols;
             hx[it] = p - hy[it] * hcols;
+            const int row = conv3 ? hy[it] * HPITCH_PX + hx[it] : p;
+            soff[it] = p < npix ? row * 128 + ((pl ^ (row & 7)) << 4) : -1;
         }
         int stage = 0, phase = 0, trace_i = 0;
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
@@ -230,11 +251,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             decode(w, nt, img, ty, tx, ks);
             const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
             const int oy0 = ty * 16 - (a.s2d ? a.pad_t : 1), ox0 = tx * 8 - (a.s2d ? a.pad_l : 1);
+            // pixel index of every halo unit (-1: outside the image / the tile): once per tile, except in the stride-2 mode
+            // where it depends on the parity of the virtual channel block
+            int pixv[MAXIT];                // (host checks n*h*w < 2^31)
+            auto locate = [&](int py, int px) {
+#pragma unroll
+                for (int it = 0; it < MAXIT; ++it) {
+                    bool ok = soff[it] >= 0;
+                    int pix;
+                    if (conv3) {
+                        int iy = oy0 + hy[it], ix = ox0 + hx[it];
+                        if (a.s2d) { iy = 2 * iy + py; ix = 2 * ix + px; }
+                        ok = ok && iy >= 0 && iy < Hl && ix >= 0 && ix < Wl;
+                        pix = (img * a.h + (iy >> ushift)) * a.w + (ix >> ushift);
+                    } else {
+                        const long long q = (long long)ty * 128 + p_first + it * PPI;     // pixel index within the image
+                        ok = ok && q < (long long)a.h * a.w;
+                        pix = (int)((long long)img * a.h * a.w + q);
+                    }
+                    pixv[it] = ok ? pix : -1;
+                }
+            };
+            if (!a.s2d) locate(0, 0);
             for (int cb = cb0; cb < cb1; ++cb) {
                 const int par = a.s2d ? cb / a.ncbr : 0;    // stride-2 mode: input parity (py, px) of this virtual block
-                const int py = par >> 1, px = par & 1;
-                const int ch = (a.s2d ? (cb - par * a.ncbr) : cb) * CB + pl * 8;   // first of this thread's 8 real channels
+                if (a.s2d) locate(par >> 1, par & 1);
+                const int ch = (a.s2d ? (cb - par * a.ncbr) : cb) * CBK + pl * 8;   // first of this thread's 8 real channels
                 const bool ch_ok = ch < cin;
+                const uint8_t* src; int sc_ch, cc;
+                if (ch < a.c0) { src = reinterpret_cast<const uint8_t*>(a.in0); sc_ch = a.c0; cc = ch; }
+                else { src = reinterpret_cast<const uint8_t*>(a.in1); sc_ch = a.c1; cc = ch - a.c0; }
+                constexpr int ESZ = IN_F16 ? 2 : 4;
+                // ---- issue every global load of this stage first (memory-level parallelism), then transform
+                uint4 raw[MAXIT][IN_F16 ? 1 : 2];
+#pragma unroll
+                for (int it = 0; it < MAXIT; ++it) {
+                    if (ch_ok && pixv[it] >= 0) {
+                        const uint4* g = reinterpret_cast<const uint4*>(src + ((size_t)pixv[it] * sc_ch + cc) * ESZ);
+                        raw[it][0] = g[0];
+                        if (!IN_F16) raw[it][1] = g[1];
+                    }
+                }
                 float sc[8], sh[8];
                 if (a.pre_scale && ch_ok) {
                     const float4* ps = reinterpret_cast<const float4*>(a.pre_scale + (size_t)img * cin + ch);
@@ -243,45 +300,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
                     sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
                 }
-                const uint8_t* src; int sc_ch, cc;
-                if (ch < a.c0) { src = reinterpret_cast<const uint8_t*>(a.in0); sc_ch = a.c0; cc = ch; }
-                else { src = reinterpret_cast<const uint8_t*>(a.in1); sc_ch = a.c1; cc = ch - a.c0; }
-                constexpr int ESZ = IN_F16 ? 2 : 4;
-                // ---- issue every global load of this stage first (memory-level parallelism), then transform
-                uint4 raw[MAXIT][IN_F16 ? 1 : 2];
-                bool okv[MAXIT];
-#pragma unroll
-                for (int it = 0; it < MAXIT; ++it) {
-                    const int p = p_first + it * (kProdThreads / 8);
-                    bool ok = ch_ok && p < npix;
-                    size_t pix;
-                    if (conv3) {
-                        int iy = oy0 + hy[it], ix = ox0 + hx[it];
-                        if (a.s2d) { iy = 2 * iy + py; ix = 2 * ix + px; }
-                        ok = ok && iy >= 0 && iy < Hl && ix >= 0 && ix < Wl;
-                        pix = ((size_t)img * a.h + (iy >> ushift)) * a.w + (ix >> ushift);
-                    } else {
-                        const long long q = (long long)ty * 128 + p;     // pixel index within the image
-                        ok = ok && q < (long long)a.h * a.w;
-                        pix = (size_t)img * a.h * a.w + (size_t)q;
-                    }
-                    okv[it] = ok;
-                    if (ok) {
-                        const uint4* g = reinterpret_cast<const uint4*>(src + (pix * sc_ch + cc) * ESZ);
-                        raw[it][0] = g[0];
-                        if (!IN_F16) raw[it][1] = g[1];
-                    }
-                }
                 if (pt == 0) TC_TRACE(0, trace_i);
                 mbar_wait(A_EMPTY(stage), phase ^ 1);
                 if (pt == 0) TC_TRACE(1, trace_i);
                 uint8_t* dst = sA + stage * A_STAGE_BYTES;
 #pragma unroll
                 for (int it = 0; it < MAXIT; ++it) {
-                    const int p = p_first + it * (kProdThreads / 8);
-                    if (p >= npix) continue;
+                    if (soff[it] < 0) continue;
                     uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = make_uint4(0u, 0u, 0u, 0u);
-                    if (okv[it]) {
+                    if (ch_ok && pixv[it] >= 0) {
                         float v[8];
                         if (!IN_F16) {
                             const float* f0 = reinterpret_cast<const float*>(&raw[it][0]);
@@ -310,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                             for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
                             __half2 lq[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {   // residual (lo) tile: v - float(fp16(v))
+                            for (int j = 0; j < 4; ++j) {   // residual (lo) operand: v - float(fp16(v))
                                 const float2 r = __half22float2(hq[j]);
                                 lq[j] = __floats2half2_rn(v[2 * j] - r.x, v[2 * j + 1] - r.y);
                             }
@@ -335,11 +362,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         o.x = *reinterpret_cast<uint32_t*>(&hq[0]); o.y = *reinterpret_cast<uint32_t*>(&hq[1]);
                         o.z = *reinterpret_cast<uint32_t*>(&hq[2]); o.w = *reinterpret_cast<uint32_t*>(&hq[3]);
                     }
-                    // row = halo pixel (pitch 16) or tile pixel; 16-byte chunk `pl` lands at chunk (pl ^ (row & 7))
-                    const int row = conv3 ? hy[it] * HPITCH_PX + hx[it] : p;
-                    const int soff = row * 128 + ((pl ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(dst + soff) = o;
-                    if (PASSES == 3) *reinterpret_cast<uint4*>(dst + A_SUB_BYTES + soff) = ol;
+                    // 16-byte chunk `pl` of the row lands at chunk (pl ^ (row & 7)); the lo half 4 chunks (64 bytes) further
+                    *reinterpret_cast<uint4*>(dst + soff[it]) = o;
+                    if (PASSES == 3) *reinterpret_cast<uint4*>(dst + (soff[it] ^ 64)) = ol;
                 }
                 fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
                 mbar_arrive(A_FULL(stage));
@@ -349,19 +374,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         }
     } else if (warp == kLoadWarp) {
         // =========================== weight loader (1-D TMA) ===========================
-        if (lane == 0) {
+        if (lane == 0 && a.w_resident) {
+            // the layer's whole panel set (one N tile, no K split) fits next to the activation stages: fetch it once
+            // per CTA instead of once per 128-pixel tile (which costs 64 B/clk/SM of L2 bandwidth at the MMA floor)
+            if ((long long)blockIdx.x < total) {
+                const int npanels = a.ncb * TAPS;
+                mbar_arrive_expect_tx(B_FULL(0), (uint32_t)(npanels * b_stage_bytes));
+                const uint8_t* g = reinterpret_cast<const uint8_t*>(a.wt);
+                for (int i = 0; i < npanels; ++i)
+                    tma_bulk_g2s(smem_u32(sB + i * b_stage_bytes), g + (size_t)i * b_stage_bytes, (uint32_t)b_stage_bytes, B_FULL(0));
+            }
+        } else if (lane == 0) {
             int stage = 0, phase = 0, trace_l = 0;
             for (long long w = blockIdx.x; w < total; w += gridDim.x) {
                 int nt, img, ty, tx, ks;
                 decode(w, nt, img, ty, tx, ks);
                 const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
                 for (int cb = cb0; cb < cb1; ++cb) {
-                    for (int tap = 0; tap < a.taps; ++tap) {
+                    for (int tap = 0; tap < TAPS; ++tap) {
                         if (!stage_live(cb, tap)) continue;
                         mbar_wait(B_EMPTY(stage), phase ^ 1);
                         mbar_arrive_expect_tx(B_FULL(stage), (uint32_t)b_stage_bytes);
                         const uint8_t* g = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)img * a.wt_img_stride * sizeof(__half) +
-                                           ((size_t)((size_t)nt * a.ncb + cb) * a.taps + tap) * (size_t)b_stage_bytes;
+                                           ((size_t)((size_t)nt * a.ncb + cb) * TAPS + tap) * (size_t)b_stage_bytes;
                         tma_bulk_g2s(smem_u32(sB + stage * b_stage_bytes), g, (uint32_t)b_stage_bytes, B_FULL(stage));
                         if (cb == cb0 && tap == 0) TC_TRACE(8, trace_l);
                         if (++stage == SB) { stage = 0; phase ^= 1; }
@@ -377,72 +412,109 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         // filter tap on one thread made *instruction issue of this warp* the bottleneck of the whole kernel.
         const uint32_t idesc = (1u << 4) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, K-major A/B
         // descriptor = {lo: start>>4 | LBO(1)<<16, hi: SBO>>4 | version 1<<14 | base_offset<<17 | SWIZZLE_128B(2)<<29}
-        const uint32_t a_sbo = conv3 ? (uint32_t)(HPITCH_PX * 128) : 1024u;
-        const uint32_t a_hi0 = ((a_sbo >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
-        const uint32_t b_hi = ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
-        const uint32_t a_lo0 = 1u << 16, b_lo0 = 1u << 16;
-        const uint32_t a_kstep = 32u >> 4, b_kstep = 32u >> 4;                 // K=16 halfs = 32 bytes inside the 128-byte row
-        const uint32_t a_lo_off = (uint32_t)A_SUB_BYTES >> 4, b_lo_off = (uint32_t)b_panel_bytes >> 4;
+        constexpr uint32_t a_sbo = conv3 ? (uint32_t)(HPITCH_PX * 128) : 1024u;
+        constexpr uint32_t a_hi = ((a_sbo >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+        constexpr uint32_t b_hi = ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+        constexpr uint32_t lo0 = 1u << 16;                                      // LBO field (unused for swizzled K-major)
+        constexpr uint32_t kstep = 32u >> 4;                                    // K=16 halfs = 32 bytes inside the 128-byte row
+        constexpr uint32_t lo_off = 64u >> 4;                                   // split precision: the lo half of a row
         // Measured on B200: with a 128-byte-row-shifted start address the swizzle XOR is applied on the absolute shared
         // memory address bits, so base_offset stays 0 (setting it to dx double-counts the phase and corrupts the tile).
-        const uint32_t use_bo = a.swap_lbo_sbo ? 1u : 0u;                       // debug knob: KEEP_TC_BASE_OFFSET=1
+        // The tap loop is unrolled at compile time: every descriptor is "stage base + constant".  (With run-time window
+        // sizes the issuing warp executed ~90 mostly dependent instructions per tap -- 500+ cycles of single-warp latency
+        // against 200-400 cycles of MMA work -- and the tensor pipe idled: profiles/r1_trace_conv64_*.txt.)
         const bool leader = elect_one();
-        int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0, trace_m = 0;
-        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-            int nt, img, ty, tx, ks;
-            decode(w, nt, img, ty, tx, ks);
-            const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
-            mbar_wait(ACC_EMPTY(as), pacc ^ 1);
+        const uint32_t b_step = (uint32_t)b_stage_bytes >> 4;
+        const uint32_t b_base = lo0 | (smem_u32(sB) >> 4);
+        // the MMAs of one (channel block, tap): K-steps x {lo*hi, hi*lo, hi*hi}
+        auto issue_tap = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+                const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + k * kstep);
+                const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + k * kstep);
+                if (PASSES == 3) {   // small cross terms first, then the leading term
+                    umma_f16(d_tmem, ad + lo_off, bd, idesc, k == 0 ? acc : 1u);
+                    umma_f16(d_tmem, ad, bd + lo_off, idesc, 1u);
+                    umma_f16(d_tmem, ad, bd, idesc, 1u);
+                } else {
+                    umma_f16(d_tmem, ad, bd, idesc, k == 0 ? acc : 1u);
+                }
+            }
+        };
+        int sa = 0, pa = 0, as = 0, pacc = 0, trace_m = 0;
+        if (a.w_resident && WIN != 2) {
+            // ---- weights resident: one wait per activation stage, then TAPS x KSTEPS x PASSES back-to-back MMAs
+            mbar_wait(B_FULL(0), 0);
             tc_fence_after();
-            if (lane == 0) TC_TRACE(3, trace_m);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
-            uint32_t acc = 0;
-            for (int cb = cb0; cb < cb1; ++cb) {
-                mbar_wait(A_FULL(sa), pa);
+            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+                mbar_wait(ACC_EMPTY(as), pacc ^ 1);
                 tc_fence_after();
-                if (lane == 0 && cb == cb0) TC_TRACE(4, trace_m);
-                uint32_t a_lo = a_lo0 | (smem_u32(sA + sa * A_STAGE_BYTES) >> 4);
-                int dx = 0;
-                for (int tap = 0; tap < a.taps; ++tap) {
-                    if (!stage_live(cb, tap)) {   // keep the shifted-view cursor in step, issue nothing
-                        if (++dx == win) { dx = 0; a_lo += (uint32_t)((HPITCH_PX - (win - 1)) * 128) >> 4; } else { a_lo += 128u >> 4; }
-                        continue;
-                    }
-                    mbar_wait(B_FULL(sb), pb);
+                if (lane == 0) TC_TRACE(3, trace_m);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
+                uint32_t b_cur = b_base;                                       // panels [cb][tap]; one N tile, no K split
+                for (int cb = 0; cb < a.ncb; ++cb) {
+                    mbar_wait(A_FULL(sa), pa);
                     tc_fence_after();
-                    const uint32_t b_lo = b_lo0 | (smem_u32(sB + sb * b_stage_bytes) >> 4);
-                    const uint32_t a_hi = a_hi0 | ((use_bo * (uint32_t)dx) << 17);   // tap dx shifts the start by dx rows of 128 B
+                    if (lane == 0 && cb == 0) TC_TRACE(4, trace_m);
+                    const uint32_t a_base = lo0 | (smem_u32(sA + sa * A_STAGE_BYTES) >> 4);
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + k * a_kstep);
-                            const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + k * b_kstep);
-                            if (PASSES == 3) {   // small cross terms first, then the leading term
-                                umma_f16(d_tmem, ad + a_lo_off, bd, idesc, acc);
-                                umma_f16(d_tmem, ad, bd + b_lo_off, idesc, 1u);
-                                umma_f16(d_tmem, ad, bd, idesc, 1u);
-                            } else {
-                                umma_f16(d_tmem, ad, bd, idesc, acc);
-                            }
-                            acc = 1;
-                        }
-                        umma_commit(B_EMPTY(sb));            // frees the weight stage when these MMAs retire
+                        for (int tap = 0; tap < TAPS; ++tap)
+                            issue_tap(d_tmem, a_base + (uint32_t)((((tap / WIN) * HPITCH_PX + (tap % WIN)) * 128) >> 4),
+                                      b_cur + (uint32_t)tap * b_step, (cb | tap) ? 1u : 0u);
+                        umma_commit(A_EMPTY(sa));
                     }
                     __syncwarp();
-                    // next tap = shifted view of the same halo tile: +1 pixel (128 B), or to the next halo row
-                    if (++dx == win) { dx = 0; a_lo += (uint32_t)((HPITCH_PX - (win - 1)) * 128) >> 4; } else { a_lo += 128u >> 4; }
-                    if (++sb == SB) { sb = 0; pb ^= 1; }
+                    b_cur += (uint32_t)TAPS * b_step;
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
-                if (leader) umma_commit(A_EMPTY(sa));
+                if (leader) umma_commit(ACC_FULL(as));
                 __syncwarp();
-                if (++sa == SA) { sa = 0; pa ^= 1; }
+                if (lane == 0) { TC_TRACE(5, trace_m); ++trace_m; }
+                if (++as == 2) { as = 0; pacc ^= 1; }
             }
-            if (leader) umma_commit(ACC_FULL(as));
-            __syncwarp();
-            if (lane == 0) { TC_TRACE(5, trace_m); ++trace_m; }
-            if (++as == 2) { as = 0; pacc ^= 1; }
+        } else {
+            // ---- weights streamed: one panel per (channel block, tap) through the SB-deep ring
+            int sb = 0, pb = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+                int nt, img, ty, tx, ks;
+                decode(w, nt, img, ty, tx, ks);
+                const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
+                mbar_wait(ACC_EMPTY(as), pacc ^ 1);
+                tc_fence_after();
+                if (lane == 0) TC_TRACE(3, trace_m);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
+                uint32_t acc = 0;
+                for (int cb = cb0; cb < cb1; ++cb) {
+                    mbar_wait(A_FULL(sa), pa);
+                    tc_fence_after();
+                    if (lane == 0 && cb == cb0) TC_TRACE(4, trace_m);
+                    const uint32_t a_base = lo0 | (smem_u32(sA + sa * A_STAGE_BYTES) >> 4);
+#pragma unroll
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        if (WIN == 2 && !stage_live(cb, tap)) continue;
+                        mbar_wait(B_FULL(sb), pb);
+                        tc_fence_after();
+                        if (leader) {
+                            issue_tap(d_tmem, a_base + (uint32_t)((((tap / WIN) * HPITCH_PX + (tap % WIN)) * 128) >> 4),
+                                      b_base + (uint32_t)sb * b_step, acc);
+                            umma_commit(B_EMPTY(sb));            // frees the weight stage when these MMAs retire
+                        }
+                        __syncwarp();
+                        acc = 1;
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                    if (leader) umma_commit(A_EMPTY(sa));
+                    __syncwarp();
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+                if (leader) umma_commit(ACC_FULL(as));
+                __syncwarp();
+                if (lane == 0) { TC_TRACE(5, trace_m); ++trace_m; }
+                if (++as == 2) { as = 0; pacc ^= 1; }
+            }
         }
-    } else {
+    } else if (warp < kEpiWarps) {
         // =========================== epilogue (warps 0-3 <-> TMEM lane quarters) ===========================
         // Each thread owns one accumulator row (= one output pixel) and walks its BN columns 16 at a time:
         // tcgen05.ld -> (+bias from shared memory) -> activation -> (+residual, loaded while the TMEM load is in
@@ -555,9 +627,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+int tc_cb(int passes) { return cb_of(passes); }
+
 int tc_pick_bn(int cout, long long m_tiles, int passes) {
     // N tile: a multiple of 16 up to 256.  Wider tiles amortise the A-operand transform; narrower ones give
-    // more CTAs when the layer is small.  The split-precision mode doubles the smem per stage -> BN <= 128.
+    // more CTAs when the layer is small.  The split-precision mode triples the MMAs per tile -> BN <= 128 keeps
+    // both TMEM accumulators and a deep weight pipeline.
     if (cout <= 64) return (cout + 15) / 16 * 16;
     if (cout == 96) return 96;
     if (cout == 192 && passes == 1) return 192;
@@ -571,9 +646,9 @@ bool tc_is_s2d(const ConvArgs& a) {
            a.h % 2 == 0 && a.w % 2 == 0 && a.ho == a.h / 2 && a.wo == a.w / 2;
 }
 
-int tc_virtual_cin(const ConvArgs& a) {
-    const int cin = a.c0 + a.c1;
-    return tc_is_s2d(a) ? 4 * ((cin + CB - 1) / CB) * CB : cin;
+int tc_virtual_cin(const ConvArgs& a, int passes) {
+    const int cin = a.c0 + a.c1, cb = cb_of(passes);
+    return tc_is_s2d(a) ? 4 * ((cin + cb - 1) / cb) * cb : cin;
 }
 
 bool tc_eligible(const ConvArgs& a) {
@@ -589,94 +664,93 @@ bool tc_eligible(const ConvArgs& a) {
     return true;
 }
 
+// a panel = bn rows x 128 bytes (64 halfs): 64 input channels, or [hi | lo] of 32 input channels (split precision)
 size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn, int passes) {
-    const int ncb = (cin + CB - 1) / CB, ntile = (cout + bn - 1) / bn;
-    return (size_t)ntile * ncb * taps * bn * 64 * (passes == 3 ? 2 : 1);
+    const int cb = cb_of(passes), ncb = (cin + cb - 1) / cb, ntile = (cout + bn - 1) / bn;
+    return (size_t)ntile * ncb * taps * bn * 64;
 }
 
-// OIHW fp32 (host) -> [ntile][cb][tap][hi|lo] panels; a panel is the SWIZZLE_128B K-major image of the (bn x 64) tile:
-// row n = 128 bytes (64 input channels), 16-byte chunk j stored at chunk position j ^ (n & 7)
+// position `idx` (halfs) inside a packed panel set -> (n tile, channel block, tap, row, logical channel k within the block,
+// hi/lo part); the 16-byte chunk j of a row is stored at chunk position j ^ (row & 7)   (SWIZZLE_128B, K-major)
+struct PanelPos { int nt, cb, tap, row, k, part; };
+__host__ __device__ inline PanelPos panel_pos(size_t idx, int bn, int taps, int ncb, int passes) {
+    PanelPos q;
+    size_t r = idx;
+    const int e = (int)(r % 8); r /= 8;
+    const int chunk = (int)(r % 8); r /= 8;
+    q.row = (int)(r % bn); r /= bn;
+    q.tap = (int)(r % taps); r /= taps;
+    q.cb = (int)(r % ncb); r /= ncb;
+    q.nt = (int)r;
+    const int cl = chunk ^ (q.row & 7);                  // logical chunk
+    if (passes == 3) { q.part = cl >> 2; q.k = ((cl & 3) << 3) + e; }
+    else { q.part = 0; q.k = (cl << 3) + e; }
+    return q;
+}
+__host__ __device__ inline __half split_part(float v, int part) {
+    const __half hi = __float2half_rn(v);
+    return part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+}
+
+// OIHW fp32 (host) -> [ntile][cb][tap] panels
 void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out) {
-    const int taps = kh * kw, ncb = (cin + CB - 1) / CB, ntile = (cout + bn - 1) / bn, nop = passes == 3 ? 2 : 1;
-    size_t base = 0;
-    for (int nt = 0; nt < ntile; ++nt)
-        for (int cb = 0; cb < ncb; ++cb)
-            for (int tap = 0; tap < taps; ++tap)
-                for (int part = 0; part < nop; ++part, base += (size_t)bn * 64)
-                    for (int r = 0; r < bn; ++r)
-                        for (int k = 0; k < 64; ++k) {
-                            const int o = nt * bn + r, i = cb * CB + k;
-                            float v = 0.0f;
-                            if (o < cout && i < cin) v = w_oihw[(((size_t)o * cin + i) * kh + tap / kw) * kw + tap % kw];
-                            const __half hi = __float2half_rn(v);
-                            const int chunk = (k >> 3) ^ (r & 7);
-                            out[base + (size_t)r * 64 + chunk * 8 + (k & 7)] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
-                        }
+    const int taps = kh * kw, cb = cb_of(passes), ncb = (cin + cb - 1) / cb;
+    const size_t total = tc_packed_weight_halfs(cin, cout, taps, bn, passes);
+    for (size_t idx = 0; idx < total; ++idx) {
+        const PanelPos q = panel_pos(idx, bn, taps, ncb, passes);
+        const int o = q.nt * bn + q.row, i = q.cb * cb + q.k;
+        float v = 0.0f;
+        if (o < cout && i < cin) v = w_oihw[(((size_t)o * cin + i) * kh + q.tap / kw) * kw + q.tap % kw];
+        out[idx] = split_part(v, q.part);
+    }
 }
 
 namespace {
 // device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 swizzled panels
-__global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int nop, int s2d_pad,
+__global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int passes, int s2d_pad,
                                  size_t total, __half* __restrict__ out) {
     pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    size_t r = idx;
-    const int e = (int)(r % 8); r /= 8;
-    const int chunk = (int)(r % 8); r /= 8;
-    const int row = (int)(r % bn); r /= bn;
-    const int part = (int)(r % nop); r /= nop;
-    const int tap = (int)(r % taps); r /= taps;
-    const int cb = (int)(r % ncb); r /= ncb;
-    const int nt = (int)r;
-    const int k = ((chunk ^ (row & 7)) << 3) + e;      // logical input channel within the 64-channel block
-    const int o = nt * bn + row;
+    const PanelPos q = panel_pos(idx, bn, taps, ncb, passes);
+    const int cb = cb_of(passes);
+    const int o = q.nt * bn + q.row;
     float v = 0.0f;
     if (s2d_pad < 0) {
-        const int i = cb * CB + k;
-        if (o < cout && i < cin) v = w[((size_t)tap * cin + i) * cout + o];
+        const int i = q.cb * cb + q.k;
+        if (o < cout && i < cin) v = w[((size_t)q.tap * cin + i) * cout + o];
     } else {   // virtual space-to-depth: block cb = parity * ncbr + real block; tap = (a, b) of the 2x2 cell window
-        const int ncbr = ncb / 4, par = cb / ncbr, i = (cb - par * ncbr) * CB + k;
-        const int ky = 2 * (tap >> 1) + (par >> 1) - s2d_pad, kx = 2 * (tap & 1) + (par & 1) - s2d_pad;
+        const int ncbr = ncb / 4, par = q.cb / ncbr, i = (q.cb - par * ncbr) * cb + q.k;
+        const int ky = 2 * (q.tap >> 1) + (par >> 1) - s2d_pad, kx = 2 * (q.tap & 1) + (par & 1) - s2d_pad;
         if (o < cout && i < cin && ky >= 0 && ky <= 2 && kx >= 0 && kx <= 2) v = w[((size_t)(ky * 3 + kx) * cin + i) * cout + o];
     }
-    const __half hi = __float2half_rn(v);
-    out[idx] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+    out[idx] = split_part(v, q.part);
 }
-}  // namespace
 
-namespace {
 // Activation matrix -> tcgen05 "weight" panels, so that C[z] = A[z] * B[z]^T (attention QK^T, PV) runs on the same kernel:
 // B[z] is (N x K) with element (n, k) at src[z*bstride + n*ld_n + k*ld_k] (ld_k = 1: row-major; ld_n = 1: transposed view).
 __global__ void tc_pack_matrix_kernel(const float* __restrict__ src, long long bstride, int ld_n, int ld_k, int N, int K, int bn,
-                                      int ncb, int nop, float alpha, size_t per_batch, size_t total, __half* __restrict__ out) {
+                                      int ncb, int passes, float alpha, size_t per_batch, size_t total, __half* __restrict__ out) {
     pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const size_t z = idx / per_batch;
-    size_t r = idx - z * per_batch;
-    const int e = (int)(r % 8); r /= 8;
-    const int chunk = (int)(r % 8); r /= 8;
-    const int row = (int)(r % bn); r /= bn;
-    const int part = (int)(r % nop); r /= nop;
-    const int cb = (int)(r % ncb); r /= ncb;
-    const int nt = (int)r;
-    const int k = cb * CB + ((chunk ^ (row & 7)) << 3) + e;
-    const int n = nt * bn + row;
+    const PanelPos q = panel_pos(idx - z * per_batch, bn, 1, ncb, passes);
+    const int k = q.cb * cb_of(passes) + q.k;
+    const int n = q.nt * bn + q.row;
     float v = 0.0f;
     if (n < N && k < K) v = alpha * src[z * bstride + (size_t)n * ld_n + (size_t)k * ld_k];
-    const __half hi = __float2half_rn(v);
-    out[idx] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+    out[idx] = split_part(v, q.part);
 }
 }  // namespace
 
 size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, int nbatch, int N, int K, int bn, int passes,
                       float alpha, __half* out, cudaStream_t s) {
-    const int ncb = (K + CB - 1) / CB, nop = passes == 3 ? 2 : 1;
+    const int cb = cb_of(passes), ncb = (K + cb - 1) / cb;
     const size_t per_batch = tc_packed_weight_halfs(K, N, 1, bn, passes);
     if (out) {
         const size_t total = per_batch * nbatch;
-        launch_k(tc_pack_matrix_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, bstride, ld_n, ld_k, N, K, bn, ncb, nop, alpha,
+        launch_k(tc_pack_matrix_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, bstride, ld_n, ld_k, N, K, bn, ncb, passes, alpha,
                                                                              per_batch, total, out);
         CUDA_CHECK(cudaGetLastError());
     }
@@ -684,12 +758,13 @@ size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, i
 }
 
 void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s) {
-    // stride-2 mode: `cin` real channels are seen as 4 * ceil(cin/64) * 64 virtual channels with a 2x2 (taps = 4) window
-    const int vcin = s2d_pad >= 0 ? 4 * ((cin + CB - 1) / CB) * CB : cin;
+    // stride-2 mode: `cin` real channels are seen as 4 * ceil(cin/cb) * cb virtual channels with a 2x2 (taps = 4) window
+    const int cb = cb_of(passes);
+    const int vcin = s2d_pad >= 0 ? 4 * ((cin + cb - 1) / cb) * cb : cin;
     const int vtaps = s2d_pad >= 0 ? 4 : taps;
-    const int ncb = (vcin + CB - 1) / CB;
+    const int ncb = (vcin + cb - 1) / cb;
     const size_t total = tc_packed_weight_halfs(vcin, cout, vtaps, bn, passes);
-    launch_k(tc_repack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, w_kc, cin, cout, vtaps, bn, ncb, passes == 3 ? 2 : 1, s2d_pad, total, out);
+    launch_k(tc_repack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, w_kc, cin, cout, vtaps, bn, ncb, passes, s2d_pad, total, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -701,28 +776,51 @@ int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb) {
     return (int)(s < 1 ? 1 : s);
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 static int env_swap() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("KEEP_TC_BASE_OFFSET"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) v = env_int("KEEP_TC_BASE_OFFSET", 0) == 1 ? 1 : 0;
     return v;
 }
 
 long long* g_tc_trace = nullptr;   // debug: device buffer of 10*16 clock64 stamps (keepop_tc_trace)
 
-static void pick_stages(int passes, int bn, int& sa, int& sb) {
-    const int a_stage = (passes == 3 ? 2 : 1) * A_SUB_BYTES, b_stage = (passes == 3 ? 2 : 1) * bn * 128;
-    const int budget = 224 * 1024;
+constexpr int SMEM_FIXED = 1024 + 8 * (2 * MAX_SA + 2 * MAX_SB + 4) + 16 + 256 * (int)sizeof(float);   // alignment slack, barriers, TMEM slot, bias
+constexpr int SMEM_BUDGET = 227 * 1024 - SMEM_FIXED;
+
+// weights resident in shared memory for the CTA's lifetime: one N tile, no K split, per-layer (not per-image) panels, and
+// the whole panel set fits next to at least two activation stages (KEEP_TC_RESIDENT=0 disables)
+static bool pick_resident(const TcConvArgs& t, int splitk) {
+    static int en = -1;
+    if (en < 0) en = env_int("KEEP_TC_RESIDENT", 1);
+    if (!en || t.ntile_n != 1 || splitk != 1 || t.wt_img_stride != 0 || t.s2d) return false;
+    return (size_t)t.ncb * t.taps * t.bn * 128 + 2 * (size_t)A_SUB_BYTES <= (size_t)SMEM_BUDGET;
+}
+
+static void pick_stages(int bn, size_t resident_bytes, int& sa, int& sb) {
+    const int a_stage = A_SUB_BYTES, b_stage = bn * 128;
     sa = 2;
+    if (resident_bytes) {
+        sb = 0;
+        while (sa < MAX_SA && resident_bytes + (size_t)(sa + 1) * a_stage <= (size_t)SMEM_BUDGET) ++sa;
+        return;
+    }
     sb = 2;
-    // grow the weight pipeline first (9 weight stages are consumed per activation stage), then the activation one
-    while (sb < MAX_SB && sa * a_stage + (sb + 1) * b_stage <= budget) ++sb;
-    while (sa < MAX_SA && (sa + 1) * a_stage + sb * b_stage <= budget) ++sa;
+    // grow the weight pipeline first (up to 9 weight stages are consumed per activation stage), then the activation one
+    while (sb < 6 && sa * a_stage + (sb + 1) * b_stage <= SMEM_BUDGET) ++sb;
+    while (sa < 4 && (sa + 1) * a_stage + sb * b_stage <= SMEM_BUDGET) ++sa;
+    while (sb < MAX_SB && sa * a_stage + (sb + 1) * b_stage <= SMEM_BUDGET) ++sb;
+    while (sa < MAX_SA && (sa + 1) * a_stage + sb * b_stage <= SMEM_BUDGET) ++sa;
 }
 
 void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
                cudaStream_t s) {
     KEEP_CHECK(tc_eligible(a), "conv2d_tc: layer not eligible for the tcgen05 kernel");
     KEEP_CHECK(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3");
+    const int cb = cb_of(passes);
     TcConvArgs t;
     t.in0 = a.in0; t.in1 = a.in1; t.in0_dt = a.in0_dt; t.in1_dt = a.in1_dt; t.c0 = a.c0; t.c1 = a.c1;
     t.n = a.n; t.h = a.h; t.w = a.w; t.up = a.up;
@@ -734,7 +832,7 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     t.win = s2d ? 2 : (a.kh == 3 ? 3 : 1);
     t.taps = t.win * t.win; t.cout = a.cout; t.bn = bn;
     t.ho = a.ho; t.wo = a.wo;
-    t.ncbr = (a.c0 + a.c1 + CB - 1) / CB;
+    t.ncbr = (a.c0 + a.c1 + cb - 1) / cb;
     t.ncb = s2d ? 4 * t.ncbr : t.ncbr;
     t.pad_t = a.pad_t; t.pad_l = a.pad_l;
     if (t.win > 1) { t.tiles_y = cdiv(a.ho, 16); t.tiles_x = cdiv(a.wo, 8); }
@@ -747,37 +845,40 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     t.splitk = splitk; t.partial = partial;
     t.act = a.act; t.res = a.res; t.res_dt = a.res_dt; t.out = a.out; t.out_dt = a.out_dt;
     t.M = (long long)a.n * a.ho * a.wo;
+    KEEP_CHECK((long long)a.n * a.h * a.w < (1ll << 31) && t.M < (1ll << 31), "conv2d_tc: more than 2^31 pixels");
     int cols = 32;
     while (cols < 2 * bn) cols *= 2;
     KEEP_CHECK(cols <= 512, "conv2d_tc: BN %d needs more than 512 TMEM columns", bn);
     t.tmem_cols = cols;
     t.swap_lbo_sbo = env_swap();
-    pick_stages(passes, bn, t.sa_stages, t.sb_stages);
+    t.w_resident = pick_resident(t, splitk) ? 1 : 0;
+    const size_t resident_bytes = t.w_resident ? (size_t)t.ncb * t.taps * bn * 128 : 0;
+    pick_stages(bn, resident_bytes, t.sa_stages, t.sb_stages);
     t.trace = g_tc_trace;
     KEEP_CHECK(splitk == 1 || partial, "conv2d_tc: split-K needs a partial buffer");
-    const int nop = passes == 3 ? 2 : 1;
-    const size_t smem = 1024 + (size_t)t.sa_stages * nop * A_SUB_BYTES + (size_t)t.sb_stages * nop * bn * 128 +
-                        8 * (2 * MAX_SA + 2 * MAX_SB + 4) + 16 + 256 * sizeof(float);
+    const size_t smem = SMEM_FIXED + (size_t)t.sa_stages * A_SUB_BYTES + (t.w_resident ? resident_bytes : (size_t)t.sb_stages * bn * 128);
     KEEP_CHECK(smem <= 227 * 1024, "conv2d_tc: %zu bytes of shared memory", smem);
     KEEP_CHECK(a.c1 == 0 || a.in0_dt == a.in1_dt, "conv2d_tc: concatenated sources must share a dtype");
+    const long long total = (long long)t.n * t.tiles_y * t.tiles_x * t.ntile_n * splitk;
+    // num_sms > 0: persistent grid capped at that many CTAs.  num_sms < 0 (low-priority side branch): short-lived CTAs
+    // of about -num_sms work items each and as many of them as that takes -- they soak up whatever SMs the
+    // latency-critical main stream leaves idle and hand an SM back within a few microseconds when it wants one.
+    const int grid = num_sms > 0 ? (int)std::min<long long>(total, num_sms)
+                                 : (int)std::min<long long>(total, std::max<long long>(1, (total + (-num_sms) - 1) / (-num_sms)));
+    const bool f16 = a.in0_dt == F16;
+    using Kern = void (*)(const TcConvArgs);
+    static const Kern kerns[2][2][3] = {
+        {{conv_tc_kernel<1, false, 1>, conv_tc_kernel<1, false, 2>, conv_tc_kernel<1, false, 3>},
+         {conv_tc_kernel<1, true, 1>, conv_tc_kernel<1, true, 2>, conv_tc_kernel<1, true, 3>}},
+        {{conv_tc_kernel<3, false, 1>, conv_tc_kernel<3, false, 2>, conv_tc_kernel<3, false, 3>},
+         {conv_tc_kernel<3, true, 1>, conv_tc_kernel<3, true, 2>, conv_tc_kernel<3, true, 3>}}};
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        for (int i = 0; i < 12; ++i)
+            CUDA_CHECK(cudaFuncSetAttribute(kerns[i / 6][(i / 3) % 2][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    const long long total = (long long)t.n * t.tiles_y * t.tiles_x * t.ntile_n * splitk;
-    const int grid = (int)std::min<long long>(total, num_sms);
-    const bool f16 = a.in0_dt == F16;
-    if (passes == 3) {
-        if (f16) launch_k(conv_tc_kernel<3, true>, dim3(grid), dim3(kThreads), smem, s, t);
-        else launch_k(conv_tc_kernel<3, false>, dim3(grid), dim3(kThreads), smem, s, t);
-    } else {
-        if (f16) launch_k(conv_tc_kernel<1, true>, dim3(grid), dim3(kThreads), smem, s, t);
-        else launch_k(conv_tc_kernel<1, false>, dim3(grid), dim3(kThreads), smem, s, t);
-    }
+    launch_k(kerns[passes == 3 ? 1 : 0][f16 ? 1 : 0][t.win - 1], dim3(grid), dim3(kThreads), smem, s, t);
     CUDA_CHECK(cudaGetLastError());
     if (splitk > 1) splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);
 }
@@ -792,7 +893,7 @@ int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, int pass
     const long long m_tiles = a.kh == 3 ? (long long)a.n * cdiv(a.ho, 16) * cdiv(a.wo, 8) : (long long)a.n * cdiv((long long)a.h * a.w, 128);
     const int bn = tc_pick_bn(a.cout, m_tiles, passes);
     const bool s2d = tc_is_s2d(a);
-    const int vcin = tc_virtual_cin(a);
+    const int vcin = tc_virtual_cin(a, passes);
     __half* dw = nullptr;
     float* part = nullptr;
     if (!s2d) {
@@ -804,7 +905,7 @@ int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, int pass
         CUDA_CHECK(cudaMalloc((void**)&dw, tc_packed_weight_halfs(vcin, a.cout, 4, bn, passes) * sizeof(__half)));
         tc_repack_device(a.wt, cin, a.cout, 9, bn, passes, a.pad_t, dw, s);
     }
-    const int splitk = tc_pick_splitk(m_tiles, cdiv(a.cout, bn), (vcin + 63) / 64);
+    const int splitk = tc_pick_splitk(m_tiles, cdiv(a.cout, bn), cdiv(vcin, tc_cb(passes)));
     if (splitk > 1) CUDA_CHECK(cudaMalloc((void**)&part, (size_t)splitk * a.n * a.ho * a.wo * a.cout * sizeof(float)));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -197,7 +197,8 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
                    prop.major, prop.minor);
         num_sms_ = prop.multiProcessorCount;
         gn_warmup();
-        { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 56; if (side_sms_ < 8 || side_sms_ > num_sms_) side_sms_ = num_sms_; }
+        // KEEP_SIDE_SMS = n > 0: side-branch persistent kernels capped at n CTAs; n < 0: short CTAs of -n work items each
+        { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 56; if (side_sms_ > num_sms_ || (side_sms_ >= 0 && side_sms_ < 8)) side_sms_ = num_sms_; }
     }
     adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
     tc_passes_ = (flags & KEEP_FLAG_TC_SPLIT3) ? 3 : 1;
@@ -318,7 +319,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         const long long m_tiles = cw.kh == 3 ? (long long)x.n * cdiv(a.ho, 16) * cdiv(a.wo, 8)
                                              : (long long)x.n * cdiv((long long)x.h * x.w, 128);
         bn = tc_pick_bn(cw.cout, m_tiles, tc_passes_);
-        a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), (tc_virtual_cin(a) + 63) / 64);
+        a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), cdiv(tc_virtual_cin(a, tc_passes_), tc_cb(tc_passes_)));
     } else {
         a.splitk = use_small ? 1 : conv_pick_splitk(a);
     }
@@ -358,7 +359,8 @@ const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pa
     if (it != tcw_.end() && it->second.bn == bn && it->second.passes == passes) return it->second.p;
     TcW t;
     t.bn = bn; t.passes = passes;
-    const int vcin = s2d_pad >= 0 ? 4 * ((cw.cin + 63) / 64) * 64 : cw.cin;
+    const int cb = tc_cb(passes);
+    const int vcin = s2d_pad >= 0 ? 4 * ((cw.cin + cb - 1) / cb) * cb : cw.cin;
     const int vtaps = s2d_pad >= 0 ? 4 : cw.kh * cw.kw;
     CUDA_CHECK(cudaMalloc((void**)&t.p, tc_packed_weight_halfs(vcin, cw.cout, vtaps, bn, passes) * sizeof(__half)));
     tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, passes, s2d_pad, t.p, s_);
@@ -1048,9 +1050,12 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     // ---- optical flow (batched over pairs)
     auto ff = forced_.find("flows");
     bool flows_async = false;
+    static const bool skip_flow = getenv("KEEP_DEBUG_SKIP_FLOW") != nullptr;   // timing experiments only: zero flows, no GMFlow
     if (!dry && ff != forced_.end() && ff->second.p) {
         KEEP_CHECK(ff->second.bytes == flows.bytes(), "forced flows have the wrong size");
         CUDA_CHECK(cudaMemcpyAsync(flows.p, ff->second.p, flows.bytes(), cudaMemcpyDeviceToDevice, s_));
+    } else if (!dry && skip_flow) {
+        CUDA_CHECK(cudaMemsetAsync(flows.p, 0, flows.bytes(), s_));
     } else {
         // fork: GMFlow for all pairs runs on the side stream / side arena, overlapping the LQ encoder, the gain
         // estimator and the serial per-frame chain (frame i only needs the flow of pair i-1).

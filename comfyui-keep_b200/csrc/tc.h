@@ -18,6 +18,7 @@ struct TcConvArgs {
     long long M;
     int tmem_cols;
     int sa_stages, sb_stages;
+    int w_resident;     // 1: the whole panel set of the layer stays in shared memory (loaded once per CTA)
     long long* trace;   // debug timeline (null = off)
     int swap_lbo_sbo;   // debug: KEEP_TC_SWAP_LBO_SBO=1
 };
@@ -28,7 +29,8 @@ int tc_pick_bn(int cout, long long m_tiles, int passes);
 int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb);
 size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn, int passes);
 bool tc_is_s2d(const ConvArgs& a);
-int tc_virtual_cin(const ConvArgs& a);   // 4 * ceil(cin/64) * 64 for the stride-2 mode, else cin
+int tc_cb(int passes);                        // input channels per A stage / weight panel: 64, or 32 in the split-precision mode
+int tc_virtual_cin(const ConvArgs& a, int passes);   // 4 * ceil(cin/cb) * cb for the stride-2 mode, else cin
 void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out);
 // s2d_pad < 0: plain repack; else stride-2 mode with pad_t = pad_l = s2d_pad (weights indexed [9*cin][cout])
 void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s);
