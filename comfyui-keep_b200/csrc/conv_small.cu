@@ -65,6 +65,79 @@ __global__ void __launch_bounds__(256) conv_cin3_kernel(const void* __restrict__
     }
 }
 
+// ---- stem, register-tiled: thread = (4 consecutive output pixels of a row, group of 16 output channels).  Every weight
+// float4 fetched from shared memory feeds 4 pixels (16 FMA per LDS.128: FMA-bound instead of LDS-bound), and the input row
+// segment the 4 pixels share ((4-1)*STRIDE + KS columns x 3 channels, contiguous in NHWC) is loaded once per filter row.
+template <int KS, int STRIDE>
+__global__ void __launch_bounds__(256) conv_cin3_px4_kernel(const void* __restrict__ in, int in_dt, int n, int h, int w, int pad,
+                                                            const float* __restrict__ wt, const float* __restrict__ bias, int ho, int wo,
+                                                            void* __restrict__ out, int out_dt) {
+    pdl_prologue();
+    constexpr int K = KS * KS * 3, PX = 4, SPAN = (PX - 1) * STRIDE + KS;
+    __shared__ __align__(16) float sw[K * 64];
+    for (int i = threadIdx.x; i < K * 64; i += 256) sw[i] = wt[i];
+    __syncthreads();
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long pg = gid >> 2;                      // group of 4 output pixels
+    const int grp = (int)(gid & 3);
+    const int wg = wo / PX;
+    if (pg >= (long long)n * ho * wg) return;
+    const int ox0 = (int)(pg % wg) * PX, oy = (int)((pg / wg) % ho), img = (int)(pg / ((long long)wg * ho));
+    float acc[PX][16];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[p][j] = bias ? bias[grp * 16 + j] : 0.0f;
+    const int ix0 = ox0 * STRIDE - pad;
+#pragma unroll 1
+    for (int ky = 0; ky < KS; ++ky) {
+        const int iy = oy * STRIDE - pad + ky;
+        if (iy < 0 || iy >= h) continue;
+        float xin[SPAN * 3];
+        const size_t rowbase = ((size_t)img * h + iy) * w;
+#pragma unroll
+        for (int j = 0; j < SPAN; ++j) {
+            const int ix = ix0 + j;
+            const bool ok = ix >= 0 && ix < w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xin[j * 3 + c] = ok ? ld1(in, in_dt, (rowbase + ix) * 3 + c) : 0.0f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + c) * 64 + grp * 16);
+                const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    const float x = xin[(p * STRIDE + kx) * 3 + c];
+                    acc[p][0] = fmaf(x, w0.x, acc[p][0]); acc[p][1] = fmaf(x, w0.y, acc[p][1]);
+                    acc[p][2] = fmaf(x, w0.z, acc[p][2]); acc[p][3] = fmaf(x, w0.w, acc[p][3]);
+                    acc[p][4] = fmaf(x, w1.x, acc[p][4]); acc[p][5] = fmaf(x, w1.y, acc[p][5]);
+                    acc[p][6] = fmaf(x, w1.z, acc[p][6]); acc[p][7] = fmaf(x, w1.w, acc[p][7]);
+                    acc[p][8] = fmaf(x, w2.x, acc[p][8]); acc[p][9] = fmaf(x, w2.y, acc[p][9]);
+                    acc[p][10] = fmaf(x, w2.z, acc[p][10]); acc[p][11] = fmaf(x, w2.w, acc[p][11]);
+                    acc[p][12] = fmaf(x, w3.x, acc[p][12]); acc[p][13] = fmaf(x, w3.y, acc[p][13]);
+                    acc[p][14] = fmaf(x, w3.z, acc[p][14]); acc[p][15] = fmaf(x, w3.w, acc[p][15]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        const size_t o = ((((size_t)img * ho + oy) * wo) + ox0 + p) * 64 + grp * 16;
+        if (out_dt == F32) {
+            float4* po = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) po[q] = make_float4(acc[p][4 * q], acc[p][4 * q + 1], acc[p][4 * q + 2], acc[p][4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                st4(reinterpret_cast<__half*>(out), o + 4 * q, make_float4(acc[p][4 * q], acc[p][4 * q + 1], acc[p][4 * q + 2], acc[p][4 * q + 3]));
+        }
+    }
+}
+
 // ---- head: 3x3 s1 p1, Cin % 16 == 0, Cout <= 4.  Block = 32x8 output pixels, one thread per pixel; the input halo is
 // staged through shared memory 16 channels at a time with the GroupNorm affine applied; weights [9][cin][4] in smem.
 constexpr int HT_W = 32, HT_H = 8, HC = 16, HPITCH = 20;   // channel pitch 20 floats: conflict-free float4 reads
@@ -147,6 +220,14 @@ void conv2d_small(const ConvArgs& a, cudaStream_t s) {
     KEEP_CHECK(conv_small_eligible(a), "conv2d_small: not eligible");
     const int cin = a.c0 + a.c1;
     if (cin == 3) {
+        if (a.wo % 4 == 0) {   // register-tiled variant: 4 output pixels per thread
+            const long long threads4 = (long long)a.n * a.ho * (a.wo / 4) * 4;
+            const unsigned grid4 = (unsigned)((threads4 + 255) / 256);
+            if (a.kh == 3) launch_k(conv_cin3_px4_kernel<3, 1>, dim3(grid4), dim3(256), 0, s, a.in0, a.in0_dt, a.n, a.h, a.w, 1, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);
+            else launch_k(conv_cin3_px4_kernel<7, 2>, dim3(grid4), dim3(256), 0, s, a.in0, a.in0_dt, a.n, a.h, a.w, 3, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);
+            CUDA_CHECK(cudaGetLastError());
+            return;
+        }
         const long long threads = (long long)a.n * a.ho * a.wo * 4;
         const unsigned grid = (unsigned)((threads + 255) / 256);
         if (a.kh == 3) launch_k(conv_cin3_kernel<3, 1>, dim3(grid), dim3(256), 0, s, a.in0, a.in0_dt, a.n, a.h, a.w, 1, a.wt, a.bias, a.ho, a.wo, a.out, a.out_dt);

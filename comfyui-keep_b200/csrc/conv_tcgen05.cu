@@ -40,7 +40,7 @@ namespace {
 // sub-partitions 1-3 next to the other three epilogue warps (tcgen05.ld ties epilogue warp w to TMEM lanes 32*(w%4)...).
 constexpr int kThreads = 768;                          // 24 warps; warps 12, 16, 20 have no role
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 8, kProdThreads = 480;   // producers: warps >= 5 with warp % 4 != 0
-constexpr int MAX_SA = 6, MAX_SB = 8;  // barrier slots (actual pipeline depths come from the launch arguments)
+constexpr int MAX_SA = 8, MAX_SB = 8;  // barrier slots (actual pipeline depths come from the launch arguments)
 // channels per A stage: 64 with fp16 operands (4 MMA K-steps of 16); 32 in the split-precision mode, whose 128-byte rows
 // hold [hi 32 ch | lo 32 ch] side by side (2 K-steps each), so a stage and a weight panel have the same geometry in both
 __host__ __device__ constexpr int cb_of(int passes) { return passes == 3 ? 32 : 64; }
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     constexpr int PPI = kProdThreads / UPP;              // pixels per producer iteration
     constexpr int MAXIT = (180 + PPI - 1) / PPI;         // halo units per producer thread and stage
     constexpr int KSTEPS = CBK / 16;                     // MMA K-steps per operand tile
-    constexpr int A_STAGE_BYTES = A_SUB_BYTES;
+    constexpr int A_STAGE_BYTES = WIN == 1 ? 128 * 128 : A_SUB_BYTES;   // 1x1: 128 pixels, no halo
     const int SA = a.sa_stages, SB = a.sb_stages;
     const int b_stage_bytes = a.bn * 128;                // one weight panel: bn rows x 128 bytes
     uint8_t* sA = smem;
@@ -210,13 +210,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     };
     const int mt_per_img = a.tiles_y * a.tiles_x;
     const int m_tiles = a.n * mt_per_img;
-    const long long total = (long long)m_tiles * a.ntile_n * a.splitk;
+    // Work items.  Default: item = (n tile, m tile, k split), n tile fastest, items strided over the CTAs.
+    // A-stationary (a.a_stat; 1x1 layers with several N tiles and many M tiles): item = (m tile, k split); the CTA walks
+    // all N tiles of the item back to back against ONE production of the activation stages, which stay in shared memory
+    // until the last N tile has consumed them (an N = 1024 linear otherwise converts the same activations eight times).
+    const int nt_inner = a.a_stat ? a.ntile_n : 1;
+    const long long total = (long long)m_tiles * a.splitk * (a.a_stat ? 1 : a.ntile_n);
     const int cb_per = (a.ncb + a.splitk - 1) / a.splitk;
 
-    // work item w -> (n-tile fastest, then m-tile, then k-split)
-    auto decode = [&](long long w, int& nt, int& img, int& ty, int& tx, int& ks) {
-        nt = (int)(w % a.ntile_n);
-        long long r = w / a.ntile_n;
+    auto decode = [&](long long w, int nti, int& nt, int& img, int& ty, int& tx, int& ks) {
+        long long r = w;
+        if (a.a_stat) nt = nti;
+        else { nt = (int)(w % a.ntile_n); r = w / a.ntile_n; }
         const int mt = (int)(r % m_tiles);
         ks = (int)(r / m_tiles);
         img = mt / mt_per_img;
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         int stage = 0, phase = 0, trace_i = 0;
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
             int nt, img, ty, tx, ks;
-            decode(w, nt, img, ty, tx, ks);
+            decode(w, 0, nt, img, ty, tx, ks);
             const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
             const int oy0 = ty * 16 - (a.s2d ? a.pad_t : 1), ox0 = tx * 8 - (a.s2d ? a.pad_l : 1);
             // pixel index of every halo unit (-1: outside the image / the tile): once per tile, except in the stride-2 mode
@@ -386,9 +391,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             }
         } else if (lane == 0) {
             int stage = 0, phase = 0, trace_l = 0;
-            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            for (long long w = blockIdx.x; w < total; w += gridDim.x)
+            for (int nti = 0; nti < nt_inner; ++nti) {
                 int nt, img, ty, tx, ks;
-                decode(w, nt, img, ty, tx, ks);
+                decode(w, nti, nt, img, ty, tx, ks);
                 const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
                 for (int cb = cb0; cb < cb1; ++cb) {
                     for (int tap = 0; tap < TAPS; ++tap) {
@@ -477,41 +483,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             // ---- weights streamed: one panel per (channel block, tap) through the SB-deep ring
             int sb = 0, pb = 0;
             for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-                int nt, img, ty, tx, ks;
-                decode(w, nt, img, ty, tx, ks);
-                const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
-                mbar_wait(ACC_EMPTY(as), pacc ^ 1);
-                tc_fence_after();
-                if (lane == 0) TC_TRACE(3, trace_m);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
-                uint32_t acc = 0;
-                for (int cb = cb0; cb < cb1; ++cb) {
-                    mbar_wait(A_FULL(sa), pa);
+                const int sa0 = sa, pa0 = pa;      // A-stationary: every N tile of the item re-reads the same activation stages
+                for (int nti = 0; nti < nt_inner; ++nti) {
+                    int nt, img, ty, tx, ks;
+                    decode(w, nti, nt, img, ty, tx, ks);
+                    const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
+                    const bool last_nt = nti == nt_inner - 1;
+                    sa = sa0; pa = pa0;
+                    mbar_wait(ACC_EMPTY(as), pacc ^ 1);
                     tc_fence_after();
-                    if (lane == 0 && cb == cb0) TC_TRACE(4, trace_m);
-                    const uint32_t a_base = lo0 | (smem_u32(sA + sa * A_STAGE_BYTES) >> 4);
-#pragma unroll
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        if (WIN == 2 && !stage_live(cb, tap)) continue;
-                        mbar_wait(B_FULL(sb), pb);
+                    if (lane == 0) TC_TRACE(3, trace_m);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
+                    uint32_t acc = 0;
+                    for (int cb = cb0; cb < cb1; ++cb) {
+                        mbar_wait(A_FULL(sa), pa);     // (returns at once when an earlier N tile already saw this phase)
                         tc_fence_after();
-                        if (leader) {
-                            issue_tap(d_tmem, a_base + (uint32_t)((((tap / WIN) * HPITCH_PX + (tap % WIN)) * 128) >> 4),
-                                      b_base + (uint32_t)sb * b_step, acc);
-                            umma_commit(B_EMPTY(sb));            // frees the weight stage when these MMAs retire
+                        if (lane == 0 && cb == cb0) TC_TRACE(4, trace_m);
+                        const uint32_t a_base = lo0 | (smem_u32(sA + sa * A_STAGE_BYTES) >> 4);
+#pragma unroll
+                        for (int tap = 0; tap < TAPS; ++tap) {
+                            if (WIN == 2 && !stage_live(cb, tap)) continue;
+                            mbar_wait(B_FULL(sb), pb);
+                            tc_fence_after();
+                            if (leader) {
+                                issue_tap(d_tmem, a_base + (uint32_t)((((tap / WIN) * HPITCH_PX + (tap % WIN)) * 128) >> 4),
+                                          b_base + (uint32_t)sb * b_step, acc);
+                                umma_commit(B_EMPTY(sb));            // frees the weight stage when these MMAs retire
+                            }
+                            __syncwarp();
+                            acc = 1;
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
+                        if (leader && last_nt) umma_commit(A_EMPTY(sa));
                         __syncwarp();
-                        acc = 1;
-                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
                     }
-                    if (leader) umma_commit(A_EMPTY(sa));
+                    if (leader) umma_commit(ACC_FULL(as));
                     __syncwarp();
-                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    if (lane == 0) { TC_TRACE(5, trace_m); ++trace_m; }
+                    if (++as == 2) { as = 0; pacc ^= 1; }
                 }
-                if (leader) umma_commit(ACC_FULL(as));
-                __syncwarp();
-                if (lane == 0) { TC_TRACE(5, trace_m); ++trace_m; }
-                if (++as == 2) { as = 0; pacc ^= 1; }
             }
         }
     } else if (warp < kEpiWarps) {
@@ -523,9 +534,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         int as = 0, pacc = 0, trace_e = 0, bias_nt = -1;
         const int row = warp * 32 + lane;          // accumulator row = output pixel within the tile
         const int r = row >> 3, c = row & 7;
-        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        for (long long w = blockIdx.x; w < total; w += gridDim.x)
+        for (int nti = 0; nti < nt_inner; ++nti) {
             int nt, img, ty, tx, ks;
-            decode(w, nt, img, ty, tx, ks);
+            decode(w, nti, nt, img, ty, tx, ks);
             if (nt != bias_nt) {   // stage this N tile's bias (zeros when absent / beyond cout) in shared memory
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int i = threadIdx.x; i < a.bn; i += kEpiWarps * 32) {
@@ -589,6 +601,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 if (a.act == ACT_RELU) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
+                } else if (a.act == ACT_GELU) {   // GMFlow / transformer FFNs: N = 1024 outputs per row -- inline, 16 independent erff chains
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0.5f * v[e] * (1.0f + erff(v[e] * 0.70710678118654752440f));
                 } else if (a.act != ACT_NONE) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = act_slow(v[e], a.act);
@@ -729,29 +744,59 @@ __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout,
 
 // Activation matrix -> tcgen05 "weight" panels, so that C[z] = A[z] * B[z]^T (attention QK^T, PV) runs on the same kernel:
 // B[z] is (N x K) with element (n, k) at src[z*bstride + n*ld_n + k*ld_k] (ld_k = 1: row-major; ld_n = 1: transposed view).
-__global__ void tc_pack_matrix_kernel(const float* __restrict__ src, long long bstride, int ld_n, int ld_k, int N, int K, int bn,
-                                      int ncb, int passes, float alpha, size_t per_batch, size_t total, __half* __restrict__ out) {
+// One thread per 8 consecutive k of one row: 8 fp32 in (two 16-byte loads when the source is row-major; eight loads that
+// coalesce across the warp's rows when it is a transposed view), one 16-byte hi chunk (+ one lo chunk) out.
+__global__ void __launch_bounds__(256) tc_pack_matrix_kernel(const float* __restrict__ src, long long bstride, int ld_n, int ld_k,
+                                                             int N, int K, int bn, int ncb, int ntile, int passes, float alpha,
+                                                             size_t per_batch, size_t total_units, __half* __restrict__ out) {
     pdl_prologue();
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const size_t z = idx / per_batch;
-    const PanelPos q = panel_pos(idx - z * per_batch, bn, 1, ncb, passes);
-    const int k = q.cb * cb_of(passes) + q.k;
-    const int n = q.nt * bn + q.row;
-    float v = 0.0f;
-    if (n < N && k < K) v = alpha * src[z * bstride + (size_t)n * ld_n + (size_t)k * ld_k];
-    out[idx] = split_part(v, q.part);
+    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total_units) return;
+    const int cb = cb_of(passes), upr = cb / 8;
+    size_t r = u;
+    int row, j;
+    if (ld_n == 1) { row = (int)(r % bn); r /= bn; j = (int)(r % upr); r /= upr; }
+    else { j = (int)(r % upr); r /= upr; row = (int)(r % bn); r /= bn; }
+    const int cbi = (int)(r % ncb); r /= ncb;
+    const int nt = (int)(r % ntile);
+    const size_t z = r / ntile;
+    const int n = nt * bn + row, k0 = cbi * cb + j * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+    if (n < N) {
+        const float* p = src + z * bstride + (size_t)n * ld_n + (size_t)k0 * ld_k;
+        if (ld_k == 1 && k0 + 8 <= K && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (k0 + i < K) v[i] = p[(size_t)i * ld_k];
+        }
+    }
+    __half2 hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float x = alpha * v[2 * i], y = alpha * v[2 * i + 1];
+        hi[i] = __floats2half2_rn(x, y);
+        const float2 f = __half22float2(hi[i]);
+        lo[i] = __floats2half2_rn(x - f.x, y - f.y);
+    }
+    __half* base = out + z * per_batch + ((size_t)(nt * ncb + cbi) * bn + row) * 64;
+    *reinterpret_cast<uint4*>(base + ((j ^ (row & 7)) << 3)) = *reinterpret_cast<const uint4*>(hi);
+    if (passes == 3) *reinterpret_cast<uint4*>(base + (((j + 4) ^ (row & 7)) << 3)) = *reinterpret_cast<const uint4*>(lo);
 }
 }  // namespace
 
 size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, int nbatch, int N, int K, int bn, int passes,
                       float alpha, __half* out, cudaStream_t s) {
-    const int cb = cb_of(passes), ncb = (K + cb - 1) / cb;
+    const int cb = cb_of(passes), ncb = (K + cb - 1) / cb, ntile = (N + bn - 1) / bn;
     const size_t per_batch = tc_packed_weight_halfs(K, N, 1, bn, passes);
     if (out) {
-        const size_t total = per_batch * nbatch;
-        launch_k(tc_pack_matrix_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, bstride, ld_n, ld_k, N, K, bn, ncb, passes, alpha,
-                                                                             per_batch, total, out);
+        const size_t units = (size_t)nbatch * ntile * ncb * bn * (cb / 8);
+        launch_k(tc_pack_matrix_kernel, dim3((unsigned)((units + 255) / 256)), dim3(256), 0, s, src, bstride, ld_n, ld_k, N, K, bn, ncb, ntile, passes,
+                                                                             alpha, per_batch, units, out);
         CUDA_CHECK(cudaGetLastError());
     }
     return per_batch;
@@ -793,16 +838,31 @@ constexpr int SMEM_BUDGET = 227 * 1024 - SMEM_FIXED;
 
 // weights resident in shared memory for the CTA's lifetime: one N tile, no K split, per-layer (not per-image) panels, and
 // the whole panel set fits next to at least two activation stages (KEEP_TC_RESIDENT=0 disables)
+static int a_stage_bytes(int win) { return win == 1 ? 128 * 128 : A_SUB_BYTES; }
+
 static bool pick_resident(const TcConvArgs& t, int splitk) {
     static int en = -1;
     if (en < 0) en = env_int("KEEP_TC_RESIDENT", 1);
     if (!en || t.ntile_n != 1 || splitk != 1 || t.wt_img_stride != 0 || t.s2d) return false;
-    return (size_t)t.ncb * t.taps * t.bn * 128 + 2 * (size_t)A_SUB_BYTES <= (size_t)SMEM_BUDGET;
+    return (size_t)t.ncb * t.taps * t.bn * 128 + 2 * (size_t)a_stage_bytes(t.win) <= (size_t)SMEM_BUDGET;
 }
 
-static void pick_stages(int bn, size_t resident_bytes, int& sa, int& sb) {
-    const int a_stage = A_SUB_BYTES, b_stage = bn * 128;
-    sa = 2;
+// A-stationary walk over the N tiles (see the kernel): 1x1 layers with several N tiles, every activation stage of an item
+// resident at once (<= MAX_SA stages next to >= 3 weight stages), and enough (m tile, k split) items to fill the grid
+static bool pick_a_stationary(const TcConvArgs& t, int splitk, int grid_cap) {
+    static int en = -1;
+    if (en < 0) en = env_int("KEEP_TC_ASTAT", 1);
+    if (!en || t.win != 1 || t.ntile_n < 2) return false;
+    const int cb_per = cdiv(t.ncb, splitk);
+    if (cb_per > MAX_SA) return false;
+    if ((size_t)cb_per * a_stage_bytes(1) + 3 * (size_t)t.bn * 128 > (size_t)SMEM_BUDGET) return false;
+    const long long items = (long long)t.n * t.tiles_y * t.tiles_x * splitk;
+    return items >= grid_cap;
+}
+
+static void pick_stages(int win, int bn, size_t resident_bytes, int min_sa, int& sa, int& sb) {
+    const int a_stage = a_stage_bytes(win), b_stage = bn * 128;
+    sa = min_sa > 2 ? min_sa : 2;
     if (resident_bytes) {
         sb = 0;
         while (sa < MAX_SA && resident_bytes + (size_t)(sa + 1) * a_stage <= (size_t)SMEM_BUDGET) ++sa;
@@ -811,7 +871,7 @@ static void pick_stages(int bn, size_t resident_bytes, int& sa, int& sb) {
     sb = 2;
     // grow the weight pipeline first (up to 9 weight stages are consumed per activation stage), then the activation one
     while (sb < 6 && sa * a_stage + (sb + 1) * b_stage <= SMEM_BUDGET) ++sb;
-    while (sa < 4 && (sa + 1) * a_stage + sb * b_stage <= SMEM_BUDGET) ++sa;
+    while (sa < (min_sa > 4 ? min_sa : 4) && (sa + 1) * a_stage + sb * b_stage <= SMEM_BUDGET) ++sa;
     while (sb < MAX_SB && sa * a_stage + (sb + 1) * b_stage <= SMEM_BUDGET) ++sb;
     while (sa < MAX_SA && (sa + 1) * a_stage + sb * b_stage <= SMEM_BUDGET) ++sa;
 }
@@ -852,14 +912,24 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     t.tmem_cols = cols;
     t.swap_lbo_sbo = env_swap();
     t.w_resident = pick_resident(t, splitk) ? 1 : 0;
+    t.a_stat = (!t.w_resident && pick_a_stationary(t, splitk, num_sms > 0 ? num_sms : 148)) ? 1 : 0;
     const size_t resident_bytes = t.w_resident ? (size_t)t.ncb * t.taps * bn * 128 : 0;
-    pick_stages(bn, resident_bytes, t.sa_stages, t.sb_stages);
+    // A-stationary: room for the stages of two items when that fits, so the next item is produced while this one is consumed
+    const int cb_per_item = cdiv(t.ncb, splitk);
+    pick_stages(t.win, bn, resident_bytes, t.a_stat ? cb_per_item : 0, t.sa_stages, t.sb_stages);
+    if (t.a_stat) {
+        const int a_stage = a_stage_bytes(1), b_stage = bn * 128;
+        while (t.sa_stages < std::min(MAX_SA, 2 * cb_per_item) && (t.sa_stages + 1) * a_stage + 3 * b_stage <= SMEM_BUDGET) {
+            ++t.sa_stages;
+            while (t.sb_stages > 3 && t.sa_stages * a_stage + t.sb_stages * b_stage > SMEM_BUDGET) --t.sb_stages;
+        }
+    }
     t.trace = g_tc_trace;
     KEEP_CHECK(splitk == 1 || partial, "conv2d_tc: split-K needs a partial buffer");
-    const size_t smem = SMEM_FIXED + (size_t)t.sa_stages * A_SUB_BYTES + (t.w_resident ? resident_bytes : (size_t)t.sb_stages * bn * 128);
+    const size_t smem = SMEM_FIXED + (size_t)t.sa_stages * a_stage_bytes(t.win) + (t.w_resident ? resident_bytes : (size_t)t.sb_stages * bn * 128);
     KEEP_CHECK(smem <= 227 * 1024, "conv2d_tc: %zu bytes of shared memory", smem);
     KEEP_CHECK(a.c1 == 0 || a.in0_dt == a.in1_dt, "conv2d_tc: concatenated sources must share a dtype");
-    const long long total = (long long)t.n * t.tiles_y * t.tiles_x * t.ntile_n * splitk;
+    const long long total = (long long)t.n * t.tiles_y * t.tiles_x * splitk * (t.a_stat ? 1 : t.ntile_n);
     // num_sms > 0: persistent grid capped at that many CTAs.  num_sms < 0 (low-priority side branch): short-lived CTAs
     // of about -num_sms work items each and as many of them as that takes -- they soak up whatever SMs the
     // latency-critical main stream leaves idle and hand an SM back within a few microseconds when it wants one.

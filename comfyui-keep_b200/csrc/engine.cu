@@ -121,6 +121,18 @@ void Engine::pack_weights(const keep_weight_desc* w, int n_w) {
         } else if (d->ndim == 4) {
             add_arr(key, pack_oihw(d->data, (int)d->shape[0], (int)d->shape[1], (int)d->shape[2], (int)d->shape[3]),
                     (int)d->shape[1], (int)d->shape[0], (int)d->shape[2], (int)d->shape[3]);
+            // GMFlow upsampler conv on cat(flow[2], feature[128]) (gmflow/gmflow.py:46-48,76): a tensor-core copy with the
+            // input channels reordered to [feature 128 | flow 2 | 6 zeros] = 136, so both sources start on 8-channel units
+            if (ends_with(key, ".upsampler.0.weight") && d->shape[1] == 130 && d->shape[2] == 3) {
+                const int O = (int)d->shape[0];
+                std::vector<float> perm((size_t)O * 136 * 9, 0.0f);
+                for (int o = 0; o < O; ++o)
+                    for (int i = 0; i < 130; ++i) {
+                        const int ni = i < 2 ? 128 + i : i - 2;
+                        for (int t = 0; t < 9; ++t) perm[((size_t)o * 136 + ni) * 9 + t] = d->data[((size_t)o * 130 + i) * 9 + t];
+                    }
+                add_arr(key.substr(0, key.size() - strlen("weight")) + "perm136.weight", pack_oihw(perm.data(), O, 136, 3, 3), 136, O, 3, 3);
+            }
             // AttnBlock q|k|v 1x1 convs fused into one N = 3C GEMM (vqgan_arch.py:222-224)
             if (ends_with(key, ".q.weight")) {
                 const std::string base = key.substr(0, key.size() - strlen("q.weight"));
@@ -196,6 +208,7 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         KEEP_CHECK(prop.major == 10, "keep_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device,
                    prop.major, prop.minor);
         num_sms_ = prop.multiProcessorCount;
+        main_cap_ = num_sms_;
         gn_warmup();
         // KEEP_SIDE_SMS = n > 0: side-branch persistent kernels capped at n CTAs; n < 0: short CTAs of -n work items each
         { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 56; if (side_sms_ > num_sms_ || (side_sms_ >= 0 && side_sms_ < 8)) side_sms_ = num_sms_; }
@@ -340,7 +353,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         }
         // side-branch (GMFlow) kernels are persistent too: cap their grid so the latency-critical serial chain on the main
         // stream always finds free SMs
-        const int grid_cap = (s_ == side_ && side_) ? side_sms_ : num_sms_;
+        const int grid_cap = (s_ == side_ && side_) ? side_sms_ : main_cap_;
         if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_, tc_is_s2d(a) ? a.pad_t : -1), bn, tc_passes_, a.splitk, a.partial, grid_cap, s_);
         else if (use_small) conv2d_small(a, s_);
         else conv2d_simt(a, s_);
@@ -479,7 +492,7 @@ Tensor Engine::gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, 
             pr.tag = 1; pr.m = nb * M; pr.k = K; pr.n = N; pr.kh = 11; pr.splitk = 1; pr.bn = bn;
             CUDA_CHECK(cudaEventRecord(pr.a, s_));
         }
-        const int grid_cap = (s_ == side_ && side_) ? side_sms_ : num_sms_;
+        const int grid_cap = (s_ == side_ && side_) ? side_sms_ : main_cap_;
         conv2d_tc(a, panels, bn, tc_passes_, 1, nullptr, grid_cap, s_);
         launches_ += 2;
         if (profile_) { CUDA_CHECK(cudaEventRecord(pr.b, s_)); prof_.push_back(pr); }
@@ -788,8 +801,20 @@ void Engine::gmflow(const float* x_nchw, int T, float* flows) {
         Tensor f0m = f0;
         f0m.h = 64; f0m.w = 64;
         ConvOpt ou;
-        ou.pad(1); ou.in1 = &f0m; ou.act = ACT_RELU; ou.out_dt = F32;
-        Tensor u = conv(flow2, convw(P + ".upsampler.0"), ou);
+        ou.pad(1); ou.act = ACT_RELU; ou.out_dt = F32;
+        Tensor u;
+        if (tcg && has(P + ".upsampler.0.perm136.weight")) {   // tensor-core path: [feature | flow padded to 8 channels]
+            Tensor flow8 = talloc(np, 64, 64, 8, F32);
+            if (!ar_->dry()) { concat2(flow2.f(), 2, nullptr, 6, flow8.f(), (long long)np * 4096, s_); launches_ += 1; }
+            ConvW cw = convw(P + ".upsampler.0.perm136");
+            cw.b = convw(P + ".upsampler.0").b;
+            ou.in1 = &flow8;
+            u = conv(f0m, cw, ou);
+            tfree(flow8);
+        } else {
+            ou.in1 = &f0m;
+            u = conv(flow2, convw(P + ".upsampler.0"), ou);
+        }
         ConvOpt om;
         om.out_dt = F32;
         Tensor mask = conv(u, P + ".upsampler.2", om);
@@ -1087,6 +1112,12 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     }
     capture("flows", flows.p, flows.bytes());
 
+    // While the GMFlow branch holds side_sms_ SMs with long-lived persistent CTAs, a full-width main-stream grid would have
+    // its last CTAs queue behind them; KEEP_MAIN_SMS caps main-stream persistent grids for the LQ encoder and the first
+    // KEEP_MAIN_CAP_FRAMES frames of the recurrence (the stretch GMFlow overlaps).
+    static const int env_main_sms = getenv("KEEP_MAIN_SMS") ? atoi(getenv("KEEP_MAIN_SMS")) : 0;
+    static const int env_cap_frames = getenv("KEEP_MAIN_CAP_FRAMES") ? atoi(getenv("KEEP_MAIN_CAP_FRAMES")) : 8;
+    main_cap_ = (flows_async && env_main_sms > 0) ? std::min(env_main_sms, num_sms_) : num_sms_;
     // ---- LQ encoder, batched over frames in chunks (keep_arch.py:1034-1037)
     const int chunk = 4;
     for (int f0 = 0; f0 < T; f0 += chunk) {
@@ -1123,6 +1154,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     auto fp = forced_.find("prev");
     const bool force_prev = dry || (fp != forced_.end() && fp->second.p);
     for (int i = 0; i < T; ++i) {
+        if (i >= env_cap_frames) main_cap_ = num_sms_;
         Tensor z_hat;
         bool own_z = false;
         if (i == 0) {
@@ -1167,6 +1199,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
         if (prev_out.p) tfree(prev_out);
         prev_out = img;
     }
+    main_cap_ = num_sms_;
     if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / 4], 0));   // join the side branch
     if (prev_out.p) tfree(prev_out);
     tfree(gains);

@@ -113,6 +113,7 @@ class Engine {
     cudaEvent_t ev_fork_ = nullptr;
     std::vector<cudaEvent_t> ev_flow_;   // one per GMFlow chunk of 4 pairs
     size_t side_bytes_ = 0;
+    int main_cap_ = 148;                 // grid cap of main-stream persistent kernels (lowered while GMFlow overlaps)
     int side_sms_ = 56;                  // grid cap of persistent kernels on the side branch
     std::unordered_map<int, size_t> side_cache_;
     cudaStream_t s_ = nullptr;

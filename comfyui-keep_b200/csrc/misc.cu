@@ -130,6 +130,60 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s
     }
 }
 
+// vectorised variant: L % 4 == 0, NV4 float4 per lane (L <= 128 * NV4), one warp per row
+template <int NV4>
+__global__ void __launch_bounds__(256) softmax_rows_v4_kernel(float* __restrict__ s, long long rows, int L,
+                                                              const int* __restrict__ region, int n_win, int Lq) {
+    pdl_prologue();
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float4* r = reinterpret_cast<float4*>(s + (size_t)row * L);
+    const int L4 = L >> 2;
+    const int4* reg = nullptr;
+    int myreg = 0;
+    if (region) {
+        const long long batch = row / Lq;
+        const int* rg = region + (size_t)(batch % n_win) * L;   // self-attention windows: Lq == L
+        myreg = rg[row % Lq];
+        reg = reinterpret_cast<const int4*>(rg);
+    }
+    float4 v[NV4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int q = lane + i * 32;
+        float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (q < L4) {
+            x = r[q];
+            if (reg) {
+                const int4 g = reg[q];
+                if (g.x != myreg) x.x += -100.0f;
+                if (g.y != myreg) x.y += -100.0f;
+                if (g.z != myreg) x.z += -100.0f;
+                if (g.w != myreg) x.w += -100.0f;
+            }
+        }
+        v[i] = x;
+        mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        if (lane + i * 32 < L4) {
+            v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx); v[i].z = expf(v[i].z - mx); v[i].w = expf(v[i].w - mx);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int q = lane + i * 32;
+        if (q < L4) r[q] = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+    }
+}
+
 // one block (256 threads) per row; V has two columns
 __global__ void __launch_bounds__(256) softmax_expect2_kernel(const float* __restrict__ s, int L, int Lq,
                                                               const float* __restrict__ v, long long v_bstride,
@@ -362,7 +416,7 @@ __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ 
     const int ct = ca + cb;
     const size_t row = i / ct;
     const int col = (int)(i % ct);
-    out[i] = col < ca ? a[row * ca + col] : b[row * cb + (col - ca)];
+    out[i] = col < ca ? a[row * ca + col] : (b ? b[row * cb + (col - ca)] : 0.0f);   // b == null: zero padding
 }
 
 static inline unsigned blocks_for(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
@@ -393,7 +447,17 @@ void geglu(const float* in, float* out, int rows, int inner, cudaStream_t s) {
 void softmax_rows(float* sc, long long rows, int L, const int* region, int n_win, int Lq, cudaStream_t s) {
     KEEP_CHECK(L <= 1024, "softmax_rows: L=%d > 1024", L);
     KEEP_CHECK(!region || Lq == L, "softmax_rows: region mask needs square windows");
-    launch_k(softmax_rows_kernel, dim3(blocks_for((size_t)rows, 8)), dim3(256), 0, s, sc, rows, L, region, n_win > 0 ? n_win : 1, Lq > 0 ? Lq : 1);
+    const int nw = n_win > 0 ? n_win : 1, lq = Lq > 0 ? Lq : 1;
+    const bool v4 = L % 4 == 0 && ((reinterpret_cast<uintptr_t>(sc) | reinterpret_cast<uintptr_t>(region)) & 15) == 0;
+    // few rows (the per-frame chain's 256-token attentions): 2 rows per block spreads them over the SMs
+    const int wpb = rows <= 4096 ? 2 : 8;
+    const dim3 grid(blocks_for((size_t)rows, wpb)), block(wpb * 32);
+    if (v4 && L <= 128) launch_k(softmax_rows_v4_kernel<1>, grid, block, 0, s, sc, rows, L, region, nw, lq);
+    else if (v4 && L <= 256) launch_k(softmax_rows_v4_kernel<2>, grid, block, 0, s, sc, rows, L, region, nw, lq);
+    else if (v4 && L <= 512) launch_k(softmax_rows_v4_kernel<4>, grid, block, 0, s, sc, rows, L, region, nw, lq);
+    else if (v4 && L <= 1024) launch_k(softmax_rows_v4_kernel<8>, grid, block, 0, s, sc, rows, L, region, nw, lq);
+    else
+    launch_k(softmax_rows_kernel, dim3(blocks_for((size_t)rows, 8)), dim3(256), 0, s, sc, rows, L, region, nw, lq);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -145,6 +145,55 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         }
     }
 }
+// vectorised variant: c % 4 == 0, NV4 float4 per lane (c <= 128 * NV4); one warp per row, two-pass statistics in registers
+template <int NV4>
+__global__ void __launch_bounds__(256) layernorm_v4_kernel(const float* __restrict__ x, int rows, int c, const float* __restrict__ g,
+                                                           const float* __restrict__ b, float eps, const float* __restrict__ res,
+                                                           float* __restrict__ out, const float* __restrict__ add2, int add2_rows,
+                                                           float* __restrict__ out2) {
+    pdl_prologue();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * c);
+    const int c4 = c >> 2;
+    float4 v[NV4];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int q = lane + i * 32;
+        v[i] = q < c4 ? xr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)c;
+    float qq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        if (lane + i * 32 < c4) {
+            const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+            qq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(qq) / (float)c + eps);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int q = lane + i * 32;
+        if (q < c4) {
+            const float4 gg = reinterpret_cast<const float4*>(g)[q], bb = reinterpret_cast<const float4*>(b)[q];
+            float4 y;
+            y.x = (v[i].x - mean) * rstd * gg.x + bb.x; y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+            y.z = (v[i].z - mean) * rstd * gg.z + bb.z; y.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+            if (res) {
+                const float4 r = reinterpret_cast<const float4*>(res + (size_t)row * c)[q];
+                y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+            }
+            reinterpret_cast<float4*>(out + (size_t)row * c)[q] = y;
+            if (out2) {
+                const float4 a2 = reinterpret_cast<const float4*>(add2 + (size_t)(row % add2_rows) * c)[q];
+                reinterpret_cast<float4*>(out2 + (size_t)row * c)[q] = make_float4(y.x + a2.x, y.y + a2.y, y.z + a2.z, y.w + a2.w);
+            }
+        }
+    }
+}
 }  // namespace
 
 namespace {
@@ -230,7 +279,18 @@ void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, floa
 void layernorm(const float* x, int rows, int c, const float* g, const float* b, float eps, const float* res, float* out,
                const float* add2, int add2_rows, float* out2, cudaStream_t s) {
     KEEP_CHECK(c <= 1024, "layernorm: c=%d > 1024", c);
-    launch_k(layernorm_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, s, x, rows, c, g, b, eps, res, out, add2, add2_rows > 0 ? add2_rows : 1, out2);
+    const int ar = add2_rows > 0 ? add2_rows : 1;
+    const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b) |
+                      reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(add2) | reinterpret_cast<uintptr_t>(out2)) & 15) == 0;
+    // few rows (the 256-token matrices of the per-frame chain): 2 rows per block spreads them over the SMs
+    const int wpb = rows <= 2048 ? 2 : 8;
+    const dim3 grid(cdiv(rows, wpb)), block(wpb * 32);
+    if (c % 4 == 0 && al && c <= 128) launch_k(layernorm_v4_kernel<1>, grid, block, 0, s, x, rows, c, g, b, eps, res, out, add2, ar, out2);
+    else if (c % 4 == 0 && al && c <= 256) launch_k(layernorm_v4_kernel<2>, grid, block, 0, s, x, rows, c, g, b, eps, res, out, add2, ar, out2);
+    else if (c % 4 == 0 && al && c <= 512) launch_k(layernorm_v4_kernel<4>, grid, block, 0, s, x, rows, c, g, b, eps, res, out, add2, ar, out2);
+    else if (c % 4 == 0 && al) launch_k(layernorm_v4_kernel<8>, grid, block, 0, s, x, rows, c, g, b, eps, res, out, add2, ar, out2);
+    else
+    launch_k(layernorm_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, s, x, rows, c, g, b, eps, res, out, add2, ar, out2);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -18,6 +18,7 @@ struct TcConvArgs {
     long long M;
     int tmem_cols;
     int sa_stages, sb_stages;
+    int a_stat;         // 1: A-stationary walk over the N tiles of each (m tile, k split) item (1x1 layers)
     int w_resident;     // 1: the whole panel set of the layer stays in shared memory (loaded once per CTA)
     long long* trace;   // debug timeline (null = off)
     int swap_lbo_sbo;   // debug: KEEP_TC_SWAP_LBO_SBO=1

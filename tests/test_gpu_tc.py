@@ -39,6 +39,9 @@ TC_CASES = [
     ("persistent_64_64_256sq", 1, 64, 256, 256, 64, 3, 1, True, "swish", "none", True, True),
     ("persistent_128_128_n3", 3, 128, 128, 64, 128, 3, 1, False, "none", "none", False, True),
     ("wide_256_256_128sq", 1, 256, 128, 128, 256, 3, 1, False, "none", "none", False, True),
+    # 1x1 layers with several N tiles and >= 148 M tiles: the A-stationary walk (activation stages produced once per M tile)
+    ("astat_ffn_256_1024", 1, 256, 160, 128, 1024, 1, 1, False, "none", "gelu", False, True),
+    ("astat_128_384_res_ragged", 2, 128, 100, 96, 384, 1, 1, True, "relu", "none", True, True),
 ]
 
 
@@ -85,7 +88,8 @@ def test_conv_tcgen05_vs_fp32_kernel_is_fp16_close(lib):
 
 
 SPLIT_CASES = [c for c in TC_CASES if c[0] in ("3x3_64_64", "3x3_gn_swish_res_ragged", "up2_128", "linear_splitk", "c16_512_splitk_res",
-                                                "gm_96_96_relu", "qkv_1x1_pre_n2", "persistent_64_64_256sq", "wide_256_256_128sq")]
+                                                "gm_96_96_relu", "qkv_1x1_pre_n2", "persistent_64_64_256sq", "wide_256_256_128sq",
+                                                "astat_ffn_256_1024", "astat_128_384_res_ragged")]
 
 
 @pytest.mark.parametrize("case", SPLIT_CASES, ids=[c[0] for c in SPLIT_CASES])
