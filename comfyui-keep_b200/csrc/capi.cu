@@ -28,6 +28,13 @@ static thread_local std::string g_err;
 
 int keepop_conv2d_tc(const ConvArgs& a, const float* w_oihw_host, int passes, cudaStream_t s);   // conv_tcgen05.cu
 
+namespace keep {
+void stamp_set_conv_simt(unsigned long long*); void stamp_set_conv_small(unsigned long long*); void stamp_set_conv_tc(unsigned long long*);
+void stamp_set_gemm(unsigned long long*); void stamp_set_misc(unsigned long long*); void stamp_set_norm(unsigned long long*);
+void launch_log_enable(bool on);
+int launch_log_dump(const char* path);
+}
+
 extern "C" {
 
 const char* keep_last_error(void) { return g_err.c_str(); }
@@ -183,6 +190,15 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
     return 0;
     KEEP_API_END
 }
+
+// debug: kernel-start timeline.  stamps = device buffer of 1 + 65536 uint64 (null = off); launch log = host-side names
+int keepop_kernel_stamps(unsigned long long* dev_buf) {
+    keep::stamp_set_conv_simt(dev_buf); keep::stamp_set_conv_small(dev_buf); keep::stamp_set_conv_tc(dev_buf);
+    keep::stamp_set_gemm(dev_buf); keep::stamp_set_misc(dev_buf); keep::stamp_set_norm(dev_buf);
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
+}
+int keepop_launch_log(int enable) { keep::launch_log_enable(enable != 0); return 0; }
+int keepop_launch_log_dump(const char* path) { return keep::launch_log_dump(path); }
 
 // debug: point the tcgen05 kernel's role timeline at a device buffer of 160 int64 (null = off)
 int keepop_tc_trace(long long* dev_buf) {

@@ -140,12 +140,33 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_early_trigger() {
     if (KEEP_PDL_TRIGGER_MAX > 0 && gridDim.x * gridDim.y * gridDim.z <= (unsigned)KEEP_PDL_TRIGGER_MAX) pdl_trigger();
 }
-__device__ __forceinline__ void pdl_prologue() { pdl_early_trigger(); pdl_wait(); }
+// Debug timeline (tools/timeline.py): when a stamp buffer is set, the first thread of every kernel appends %globaltimer at the
+// moment its grid may start (right after griddepcontrol.wait).  b[0] = running count, b[1..] = stamps.  One copy of the
+// pointer per translation unit (no relocatable device code); KEEP_STAMP_SETTER defines the TU's setter.
+constexpr unsigned long long KEEP_STAMP_CAP = 1ull << 16;
+static __device__ unsigned long long* g_stamp_buf = nullptr;
+__device__ __forceinline__ void keep_stamp() {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long* b = g_stamp_buf;
+        if (b) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            const unsigned long long i = atomicAdd(b, 1ull);
+            if (i < KEEP_STAMP_CAP) b[1 + i] = t;
+        }
+    }
+}
+#define KEEP_STAMP_SETTER(fn) \
+    void fn(unsigned long long* p) { cudaMemcpyToSymbol(g_stamp_buf, &p, sizeof(p)); }
+__device__ __forceinline__ void pdl_prologue() { pdl_early_trigger(); pdl_wait(); keep_stamp(); }
 
 bool pdl_enabled();   // engine.cu: KEEP_PDL env (default on)
 
+void launch_log_add(const void* func, dim3 grid, dim3 block);   // engine.cu: no-op unless the debug launch log is on
+
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    launch_log_add(reinterpret_cast<const void*>(kernel), grid, block);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -154,6 +175,22 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+// same, as a thread-block cluster of `cluster_x` consecutive CTAs (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline void launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, Args&&... args) {
+    launch_log_add(reinterpret_cast<const void*>(kernel), grid, block);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 #endif

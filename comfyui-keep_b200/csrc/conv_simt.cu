@@ -289,4 +289,6 @@ void conv2d_simt(const ConvArgs& a, cudaStream_t s) {
     }
 }
 
+KEEP_STAMP_SETTER(stamp_set_conv_simt)
+
 }  // namespace keep

@@ -246,4 +246,6 @@ void conv2d_small(const ConvArgs& a, cudaStream_t s) {
     CUDA_CHECK(cudaGetLastError());
 }
 
+KEEP_STAMP_SETTER(stamp_set_conv_small)
+
 }  // namespace keep

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();      // barrier init + TMEM allocation above overlapped the previous kernel's tail; inputs are read below
+    keep_stamp();
 
     // WIN = 3: 3x3 s1 | 2: 3x3 stride-2 as a 2x2 window over the virtual space-to-depth input | 1: 1x1
     constexpr int win = WIN, TAPS = WIN * WIN;
@@ -220,10 +221,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 
     auto decode = [&](long long w, int nti, int& nt, int& img, int& ty, int& tx, int& ks) {
         long long r = w;
-        if (a.a_stat) nt = nti;
-        else { nt = (int)(w % a.ntile_n); r = w / a.ntile_n; }
-        const int mt = (int)(r % m_tiles);
-        ks = (int)(r / m_tiles);
+        int mt;
+        if (a.cluster_k) {   // cluster split-K: the K splits of one output tile are the CTAs of one cluster (k split fastest)
+            ks = (int)(w % a.splitk); r = w / a.splitk;
+            nt = (int)(r % a.ntile_n);
+            mt = (int)(r / a.ntile_n);
+        } else {
+            if (a.a_stat) nt = nti;
+            else { nt = (int)(w % a.ntile_n); r = w / a.ntile_n; }
+            mt = (int)(r % m_tiles);
+            ks = (int)(r / m_tiles);
+        }
         img = mt / mt_per_img;
         const int t2 = mt - img * mt_per_img;
         ty = t2 / a.tiles_x;
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int i = threadIdx.x; i < a.bn; i += kEpiWarps * 32) {
                     const int nn = nt * a.bn + i;
-                    s_bias[i] = (a.bias && a.splitk == 1 && nn < a.cout) ? a.bias[nn] : 0.0f;
+                    s_bias[i] = (a.bias && (a.splitk == 1 || a.cluster_k) && nn < a.cout) ? a.bias[nn] : 0.0f;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 bias_nt = nt;
@@ -564,6 +572,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             if (threadIdx.x == 0) TC_TRACE(6, trace_e);
             const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * a.bn);
             const bool partial_out = a.splitk > 1;
+            if (a.cluster_k) {
+                // cluster split-K: park this CTA's fp32 partial tile in its (now idle) activation stages, row = pixel,
+                // 16-byte pieces XOR-swizzled by the row so that both this row-per-thread write and the piece-per-thread
+                // reads of the reduction below are bank-conflict free; the cluster reduces it after the roles join
+                const int row = warp * 32 + lane;
+                uint8_t* dstrow = sA + (size_t)row * a.bn * 4;
+                for (int j = 0; j < a.bn; j += 16) {
+                    uint32_t rr[16];
+                    __syncwarp();
+                    tmem_ld16(t0 + (uint32_t)j, rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        *reinterpret_cast<uint4*>(dstrow + ((((j >> 2) + e) ^ (row & 7)) << 4)) = make_uint4(rr[4 * e], rr[4 * e + 1], rr[4 * e + 2], rr[4 * e + 3]);
+                }
+                tc_fence_before();
+                mbar_arrive(ACC_EMPTY(as));
+                if (threadIdx.x == 0) { TC_TRACE(7, trace_e); ++trace_e; }
+                if (++as == 2) { as = 0; pacc ^= 1; }
+                continue;
+            }
             for (int j = 0; j < a.bn; j += 16) {
                 uint32_t rr[16];
                 __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge after divergent stores
@@ -583,6 +612,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     }
                 }
                 tmem_ld_wait();
+#ifdef KEEP_TC_EPI_TRACE
+                if (threadIdx.x == 0 && trace_e == 0) TC_TRACE(8, j >> 4);
+#endif
                 if (!live) continue;
                 float v[16];
 #pragma unroll
@@ -591,6 +623,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     float4* o = reinterpret_cast<float4*>(a.partial + (size_t)ks * a.M * a.cout + off);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+#ifdef KEEP_TC_EPI_TRACE
+                    if (threadIdx.x == 0 && trace_e == 0) TC_TRACE(9, j >> 4);
+#endif
                     continue;
                 }
 #pragma unroll
@@ -621,6 +656,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     for (int e = 0; e < 4; ++e)
                         st4(reinterpret_cast<__half*>(a.out), off + 4 * e, make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]));
                 }
+#ifdef KEEP_TC_EPI_TRACE
+                if (threadIdx.x == 0 && trace_e == 0) TC_TRACE(9, j >> 4);
+#endif
             }
             tc_fence_before();
             mbar_arrive(ACC_EMPTY(as));
@@ -629,6 +667,59 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         }
     }
 
+    if (a.cluster_k) {
+        // ---- cluster split-K reduction over distributed shared memory (replaces the partial round trip through L2 and the
+        // separate reduce kernel): after the first cluster barrier every CTA holds its partial tile in shared memory; the
+        // CTA of rank r then sums rows [r*R, (r+1)*R) over all ranks IN RANK ORDER (deterministic), applies bias /
+        // activation / residual and writes the final rows with coalesced 16-byte stores.
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (warp < kEpiWarps) {
+            const int S = a.splitk, rank = (int)(blockIdx.x % (unsigned)S);
+            int nt, img, ty, tx, ks;
+            decode(blockIdx.x, 0, nt, img, ty, tx, ks);
+            const int R = (128 + S - 1) / S, r0 = rank * R, r1 = min(128, r0 + R);
+            const int q4 = a.bn >> 2;                       // 16-byte pieces per row
+            const int n0 = nt * a.bn;
+            const uint32_t sbase = smem_u32(sA);
+            for (int idx = threadIdx.x; idx < (r1 - r0) * q4; idx += kEpiWarps * 32) {
+                const int row = r0 + idx / q4, c4 = idx - (idx / q4) * q4;
+                const int col = n0 + c4 * 4;
+                long long pixel;
+                bool ok;
+                if (conv3) {
+                    const int oy = ty * 16 + (row >> 3), ox = tx * 8 + (row & 7);
+                    ok = oy < a.ho && ox < a.wo;
+                    pixel = ((long long)img * a.ho + oy) * a.wo + ox;
+                } else {
+                    const long long q = (long long)ty * 128 + row;
+                    ok = q < (long long)a.h * a.w;
+                    pixel = (long long)img * a.h * a.w + q;
+                }
+                if (!ok || col >= a.cout) continue;
+                const uint32_t laddr = sbase + (uint32_t)(row * a.bn * 4 + ((c4 ^ (row & 7)) << 4));
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < S; ++k) {
+                    uint32_t raddr;
+                    float4 p;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(k));
+                    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w) : "r"(raddr) : "memory");
+                    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+                }
+                const float4 b = *reinterpret_cast<const float4*>(s_bias + c4 * 4);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                if (a.act != ACT_NONE) { v.x = act_slow(v.x, a.act); v.y = act_slow(v.y, a.act); v.z = act_slow(v.z, a.act); v.w = act_slow(v.w, a.act); }
+                const size_t off = (size_t)pixel * a.cout + col;
+                if (a.res) {
+                    const float4 r4 = a.res_dt == F32 ? ld4(reinterpret_cast<const float*>(a.res), off) : ld4(reinterpret_cast<const __half*>(a.res), off);
+                    v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+                }
+                if (a.out_dt == F32) st4(reinterpret_cast<float*>(a.out), off, v);
+                else st4(reinterpret_cast<__half*>(a.out), off, v);
+            }
+        }
+        // no CTA may exit (and release its shared memory) while a peer is still reading it
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) {
@@ -876,8 +967,8 @@ static void pick_stages(int win, int bn, size_t resident_bytes, int min_sa, int&
     while (sa < MAX_SA && (sa + 1) * a_stage + sb * b_stage <= SMEM_BUDGET) ++sa;
 }
 
-void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
-               cudaStream_t s) {
+int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
+              cudaStream_t s) {
     KEEP_CHECK(tc_eligible(a), "conv2d_tc: layer not eligible for the tcgen05 kernel");
     KEEP_CHECK(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3");
     const int cb = cb_of(passes);
@@ -898,10 +989,17 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     if (t.win > 1) { t.tiles_y = cdiv(a.ho, 16); t.tiles_x = cdiv(a.wo, 8); }
     else { t.tiles_y = cdiv((long long)a.h * a.w, 128); t.tiles_x = 1; }
     t.ntile_n = cdiv(a.cout, bn);
+    // split-K inside a thread-block cluster (<= 8 CTAs, portable size) whenever the layer splits at all: the partial
+    // tiles meet in distributed shared memory instead of L2 and no second kernel is needed (opt-in: KEEP_TC_CLUSTER=8; measured slower than the two-kernel path, profiles/r1_experiments.md;
+    // the value caps the cluster size)
+    static const int cluster_max = std::min(8, std::max(0, env_int("KEEP_TC_CLUSTER", 0)));
+    const bool want_cluster = splitk > 1 && cluster_max >= 2 && bn % 32 == 0;
+    if (want_cluster && splitk > cluster_max) splitk = cluster_max;
     {   // every K-split must own at least one channel block
         const int cb_per = cdiv(t.ncb, splitk < 1 ? 1 : splitk);
         splitk = cdiv(t.ncb, cb_per);
     }
+    t.cluster_k = (want_cluster && splitk > 1) ? 1 : 0;
     t.splitk = splitk; t.partial = partial;
     t.act = a.act; t.res = a.res; t.res_dt = a.res_dt; t.out = a.out; t.out_dt = a.out_dt;
     t.M = (long long)a.n * a.ho * a.wo;
@@ -912,7 +1010,7 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
     t.tmem_cols = cols;
     t.swap_lbo_sbo = env_swap();
     t.w_resident = pick_resident(t, splitk) ? 1 : 0;
-    t.a_stat = (!t.w_resident && pick_a_stationary(t, splitk, num_sms > 0 ? num_sms : 148)) ? 1 : 0;
+    t.a_stat = (!t.w_resident && !t.cluster_k && pick_a_stationary(t, splitk, num_sms > 0 ? num_sms : 148)) ? 1 : 0;
     const size_t resident_bytes = t.w_resident ? (size_t)t.ncb * t.taps * bn * 128 : 0;
     // A-stationary: room for the stages of two items when that fits, so the next item is produced while this one is consumed
     const int cb_per_item = cdiv(t.ncb, splitk);
@@ -925,11 +1023,13 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
         }
     }
     t.trace = g_tc_trace;
-    KEEP_CHECK(splitk == 1 || partial, "conv2d_tc: split-K needs a partial buffer");
+    if (t.cluster_k && (size_t)t.sa_stages * a_stage_bytes(t.win) < (size_t)128 * bn * 4) t.cluster_k = 0;   // partial tile must fit the A stages
+    KEEP_CHECK(splitk == 1 || t.cluster_k || partial, "conv2d_tc: split-K needs a partial buffer");
     const size_t smem = SMEM_FIXED + (size_t)t.sa_stages * a_stage_bytes(t.win) + (t.w_resident ? resident_bytes : (size_t)t.sb_stages * bn * 128);
     KEEP_CHECK(smem <= 227 * 1024, "conv2d_tc: %zu bytes of shared memory", smem);
     KEEP_CHECK(a.c1 == 0 || a.in0_dt == a.in1_dt, "conv2d_tc: concatenated sources must share a dtype");
     const long long total = (long long)t.n * t.tiles_y * t.tiles_x * splitk * (t.a_stat ? 1 : t.ntile_n);
+    KEEP_CHECK(!t.cluster_k || total < (1ll << 30), "conv2d_tc: cluster grid too large");
     // num_sms > 0: persistent grid capped at that many CTAs.  num_sms < 0 (low-priority side branch): short-lived CTAs
     // of about -num_sms work items each and as many of them as that takes -- they soak up whatever SMs the
     // latency-critical main stream leaves idle and hand an SM back within a few microseconds when it wants one.
@@ -948,10 +1048,19 @@ void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int 
             CUDA_CHECK(cudaFuncSetAttribute(kerns[i / 6][(i / 3) % 2][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    launch_k(kerns[passes == 3 ? 1 : 0][f16 ? 1 : 0][t.win - 1], dim3(grid), dim3(kThreads), smem, s, t);
+    const Kern kern = kerns[passes == 3 ? 1 : 0][f16 ? 1 : 0][t.win - 1];
+    if (t.cluster_k) {   // one work item per CTA, the splitk CTAs of a tile form one cluster
+        launch_k_cluster(kern, dim3((unsigned)total), dim3(kThreads), smem, s, splitk, t);
+        CUDA_CHECK(cudaGetLastError());
+        return 1;
+    }
+    launch_k(kern, dim3(grid), dim3(kThreads), smem, s, t);
     CUDA_CHECK(cudaGetLastError());
     if (splitk > 1) splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);
+    return splitk > 1 ? 2 : 1;
 }
+
+KEEP_STAMP_SETTER(stamp_set_conv_tc)
 
 }  // namespace keep
 

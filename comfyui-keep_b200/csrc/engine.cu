@@ -9,6 +9,29 @@
 
 namespace keep {
 
+// debug launch log (tools/timeline.py): kernel name + grid of every launch, in enqueue order
+static std::vector<std::string>* g_launch_log = nullptr;
+void launch_log_enable(bool on) {
+    delete g_launch_log;
+    g_launch_log = on ? new std::vector<std::string>() : nullptr;
+}
+void launch_log_add(const void* func, dim3 grid, dim3 block) {
+    if (!g_launch_log) return;
+    const char* nm = nullptr;
+    if (cudaFuncGetName(&nm, func) != cudaSuccess || !nm) nm = "?";
+    char b[512];
+    snprintf(b, sizeof(b), "%s\t%u,%u,%u\t%u", nm, grid.x, grid.y, grid.z, block.x);
+    g_launch_log->push_back(b);
+}
+int launch_log_dump(const char* path) {
+    if (!g_launch_log) return -1;
+    FILE* f = fopen(path, "w");
+    if (!f) return -1;
+    for (auto& l : *g_launch_log) fprintf(f, "%s\n", l.c_str());
+    fclose(f);
+    return (int)g_launch_log->size();
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("KEEP_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -354,10 +377,11 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         // side-branch (GMFlow) kernels are persistent too: cap their grid so the latency-critical serial chain on the main
         // stream always finds free SMs
         const int grid_cap = (s_ == side_ && side_) ? side_sms_ : main_cap_;
-        if (use_tc) conv2d_tc(a, tc_weights(cw, bn, tc_passes_, tc_is_s2d(a) ? a.pad_t : -1), bn, tc_passes_, a.splitk, a.partial, grid_cap, s_);
+        int nl = a.splitk > 1 ? 2 : 1;
+        if (use_tc) nl = conv2d_tc(a, tc_weights(cw, bn, tc_passes_, tc_is_s2d(a) ? a.pad_t : -1), bn, tc_passes_, a.splitk, a.partial, grid_cap, s_);
         else if (use_small) conv2d_small(a, s_);
         else conv2d_simt(a, s_);
-        launches_ += a.splitk > 1 ? 2 : 1;
+        launches_ += nl;
         if (profile_) {
             CUDA_CHECK(cudaEventRecord(pr.b, s_));
             prof_.push_back(pr);
@@ -1084,7 +1108,8 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     } else {
         // fork: GMFlow for all pairs runs on the side stream / side arena, overlapping the LQ encoder, the gain
         // estimator and the serial per-frame chain (frame i only needs the flow of pair i-1).
-        if (!dry) {
+        static const bool no_side = getenv("KEEP_NO_SIDE") != nullptr;   // debug / timeline: GMFlow inline on the main stream
+        if (!dry && !no_side) {
             if (!side_) {
                 int lo = 0, hi = 0;
                 CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = least urgent
@@ -1104,7 +1129,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
         gmflow(x_dev, T, flows.f());
         ar_ = &arena_;
         s_ = s_main_;
-        flows_async = !dry;
+        flows_async = !dry && !no_side;
     }
     if (capture_ && flows_async) {   // debug capture wants the complete flows now
         CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / 4], 0));

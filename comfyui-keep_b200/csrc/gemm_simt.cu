@@ -107,6 +107,76 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BGemmArgs a, int vecA,
         }
     }
 }
+// 32 x 32 output tile, K step 32, 2 x 2 outputs per thread: for the 256-token attentions of the serial per-frame chain,
+// whose 64-wide tiling fills only 16-32 SMs (26 us for a 256 x 256 x 512 product).  Same summation order over k.
+template <bool TRANSB>
+__global__ void __launch_bounds__(256) bgemm32_kernel(const BGemmArgs a, int vecA, int vecB) {
+    pdl_prologue();
+    constexpr int T = 32, KT = 32;
+    __shared__ __align__(16) float As[KT][T + 4];
+    __shared__ __align__(16) float Bs[KT][T + 4];
+    const int tid = threadIdx.x;
+    int z = blockIdx.z;
+    const int z2 = z % a.nz2; z /= a.nz2;
+    const int z1 = z % a.nz1; z /= a.nz1;
+    const int z0 = z;
+    const float* A = a.A + z0 * a.sA[0] + z1 * a.sA[1] + z2 * a.sA[2];
+    const float* B = a.B + z0 * a.sB[0] + z1 * a.sB[1] + z2 * a.sB[2];
+    float* C = a.C + z0 * a.sC[0] + z1 * a.sC[1] + z2 * a.sC[2];
+    const int m0 = blockIdx.x * T, n0 = blockIdx.y * T;
+    const int lr = tid >> 3, lq = (tid & 7) * 4;    // [row][k] loader: 32 rows x 32 k, one float4 per thread
+    float ra[4], rb[4];
+    auto load4 = [&](const float* P, int ld, int row, int rmax, int col, int cmax, int vec, float (&r)[4]) {
+        if (row < rmax && vec && col + 3 < cmax) {
+            const float4 t = *reinterpret_cast<const float4*>(P + (size_t)row * ld + col);
+            r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = (row < rmax && col + j < cmax) ? P[(size_t)row * ld + col + j] : 0.0f;
+        }
+    };
+    auto load = [&](int k0) {
+        load4(A, a.lda, m0 + lr, a.M, k0 + lq, a.K, vecA, ra);                       // A[m][k]
+        if (TRANSB) load4(B, a.ldb, n0 + lr, a.N, k0 + lq, a.K, vecB, rb);            // B[n][k]
+        else load4(B, a.ldb, k0 + lr, a.K, n0 + lq, a.N, vecB, rb);                   // B[k][n]: 32 k x 32 n
+    };
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    const int ty = tid >> 4, tx = tid & 15;
+    load(0);
+    for (int k0 = 0; k0 < a.K; k0 += KT) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) As[lq + j][lr] = ra[j];
+        if (TRANSB) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Bs[lq + j][lr] = rb[j];
+        } else {
+            *reinterpret_cast<float4*>(&Bs[lr][lq]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+        }
+        __syncthreads();
+        if (k0 + KT < a.K) load(k0 + KT);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const float2 av = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
+            const float2 bv = *reinterpret_cast<const float2*>(&Bs[k][tx * 2]);
+            acc[0][0] = fmaf(av.x, bv.x, acc[0][0]); acc[0][1] = fmaf(av.x, bv.y, acc[0][1]);
+            acc[1][0] = fmaf(av.y, bv.x, acc[1][0]); acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty * 2 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = n0 + tx * 2 + j;
+            if (n >= a.N) continue;
+            float* c = C + (size_t)m * a.ldc + n;
+            const float v = a.alpha * acc[i][j];
+            *c = a.accumulate ? (*c + v) : v;
+        }
+    }
+}
 }  // namespace
 
 void bgemm_simt(const BGemmArgs& a, cudaStream_t s) {
@@ -118,10 +188,20 @@ void bgemm_simt(const BGemmArgs& a, cudaStream_t s) {
                (st[2] % 4 == 0);
     };
     const int vecA = al4(a.A, a.lda, a.sA), vecB = al4(a.B, a.ldb, a.sB);
+    const long long tiles64 = (long long)cdiv(a.M, TM) * cdiv(a.N, TN) * nz;
+    if (tiles64 < 148) {   // too few 64 x 64 tiles to fill the SMs: quarter-size tiles
+        dim3 grid(cdiv(a.M, 32), cdiv(a.N, 32), (unsigned)nz);
+        if (a.transB) launch_k(bgemm32_kernel<true>, dim3(grid), dim3(256), 0, s, a, vecA, vecB);
+        else launch_k(bgemm32_kernel<false>, dim3(grid), dim3(256), 0, s, a, vecA, vecB);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     dim3 grid(cdiv(a.M, TM), cdiv(a.N, TN), (unsigned)nz);
     if (a.transB) launch_k(bgemm_kernel<true>, dim3(grid), dim3(256), 0, s, a, vecA, vecB);
     else launch_k(bgemm_kernel<false>, dim3(grid), dim3(256), 0, s, a, vecA, vecB);
     CUDA_CHECK(cudaGetLastError());
 }
+
+KEEP_STAMP_SETTER(stamp_set_gemm)
 
 }  // namespace keep

@@ -538,4 +538,6 @@ void concat2(const float* a, int ca, const float* b, int cb, float* out, long lo
     CUDA_CHECK(cudaGetLastError());
 }
 
+KEEP_STAMP_SETTER(stamp_set_misc)
+
 }  // namespace keep

@@ -294,4 +294,6 @@ void layernorm(const float* x, int rows, int c, const float* g, const float* b, 
     CUDA_CHECK(cudaGetLastError());
 }
 
+KEEP_STAMP_SETTER(stamp_set_norm)
+
 }  // namespace keep

@@ -18,6 +18,7 @@ struct TcConvArgs {
     long long M;
     int tmem_cols;
     int sa_stages, sb_stages;
+    int cluster_k;      // 1: split-K across the CTAs of a thread-block cluster, reduced over distributed shared memory
     int a_stat;         // 1: A-stationary walk over the N tiles of each (m tile, k split) item (1x1 layers)
     int w_resident;     // 1: the whole panel set of the layer stays in shared memory (loaded once per CTA)
     long long* trace;   // debug timeline (null = off)
@@ -39,8 +40,9 @@ void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, in
 size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, int nbatch, int N, int K, int bn, int passes,
                       float alpha, __half* out, cudaStream_t s);
 // partial: splitk * M * cout floats when splitk > 1
-void conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
-               cudaStream_t s);
+// returns the number of kernel launches made (1, or 2 with the separate split-K reduce)
+int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
+              cudaStream_t s);
 // fixed-order split-K reduce + epilogue (conv_simt.cu)
 void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
                    int res_dt, void* out, int out_dt, cudaStream_t s);

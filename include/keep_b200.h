@@ -92,6 +92,11 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
                   int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
                   const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
                   float* out_dev, void* stream);
+/* debug timeline (tools/timeline.py): every kernel appends %globaltimer at its start to dev_buf (uint64[1 + 65536], [0] = count;
+ * NULL = off); the launch log records kernel names and grids on the host in enqueue order */
+int keepop_kernel_stamps(unsigned long long* dev_buf);
+int keepop_launch_log(int enable);
+int keepop_launch_log_dump(const char* path);
 int keepop_tc_trace(long long* dev_buf_160_i64); /* debug: per-role clock64 timeline of CTA 0 of the tcgen05 kernel */
 int keepop_groupnorm_affine(const float* x_dev, int n, int hw, int c, int groups, float eps, const float* gamma_dev,
                             const float* beta_dev, float* scale_dev, float* shift_dev, void* stream);
