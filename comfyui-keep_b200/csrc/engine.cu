@@ -32,6 +32,15 @@ int launch_log_dump(const char* path) {
     return (int)g_launch_log->size();
 }
 
+// batching of the throughput-bound front half: GMFlow pairs per pass and LQ-encoder frames per pass
+static int env_or(const char* name, int dflt, int lo, int hi) {
+    const char* e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+static int flow_chunk() { static const int v = env_or("KEEP_FLOW_CHUNK", 4, 1, 32); return v; }
+static int lq_chunk() { static const int v = env_or("KEEP_LQ_CHUNK", 10, 1, 32); return v; }
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("KEEP_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -233,8 +242,10 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         num_sms_ = prop.multiProcessorCount;
         main_cap_ = num_sms_;
         gn_warmup();
+        CUDA_CHECK(cudaMalloc((void**)&gn_tickets_, 2 * gn_ticket_count() * sizeof(int)));   // main / side stream
+        CUDA_CHECK(cudaMemset(gn_tickets_, 0, 2 * gn_ticket_count() * sizeof(int)));
         // KEEP_SIDE_SMS = n > 0: side-branch persistent kernels capped at n CTAs; n < 0: short CTAs of -n work items each
-        { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 56; if (side_sms_ > num_sms_ || (side_sms_ >= 0 && side_sms_ < 8)) side_sms_ = num_sms_; }
+        { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 100; if (side_sms_ > num_sms_ || (side_sms_ >= 0 && side_sms_ < 8)) side_sms_ = num_sms_; }
     }
     adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
     tc_passes_ = (flags & KEEP_FLAG_TC_SPLIT3) ? 3 : 1;
@@ -271,6 +282,7 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     cudaFree(wpool_);
     cudaFree(region_);
+    cudaFree(gn_tickets_);
     cudaFree(grid64_);
     cudaFree(own_ws_);
     for (auto& kv : cap_) cudaFree(kv.second.p);
@@ -427,11 +439,11 @@ Aff Engine::gn(const Tensor& x, const std::string& prefix, const Tensor* x2) {
     const int hw = x.h * x.w;
     double* scratch = (double*)ar_->alloc(gn_scratch_doubles(x.n, hw, std::max(x.c, x2 ? x2->c : 0)) * sizeof(double));
     if (!ar_->dry()) {
-        groupnorm_affine(x.p, x.dt, x.n, hw, x.c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, 0, scratch, s_);
+        groupnorm_affine(x.p, x.dt, x.n, hw, x.c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, 0, scratch, s_, gn_tickets_ ? gn_tickets_ + ((s_ == side_ && side_) ? gn_ticket_count() : 0) : nullptr);
         launches_ += 1;
         if (x2) {
             KEEP_CHECK(x.c % cpg == 0, "GroupNorm over concat: group straddles the sources");
-            groupnorm_affine(x2->p, x2->dt, x2->n, hw, x2->c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, x.c, scratch, s_);
+            groupnorm_affine(x2->p, x2->dt, x2->n, hw, x2->c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, x.c, scratch, s_, gn_tickets_ ? gn_tickets_ + ((s_ == side_ && side_) ? gn_ticket_count() : 0) : nullptr);
             launches_ += 1;
         }
     }
@@ -446,7 +458,7 @@ Aff Engine::inorm(const Tensor& x) {
     const int hw = x.h * x.w;
     double* scratch = (double*)ar_->alloc(gn_scratch_doubles(x.n, hw, x.c) * sizeof(double));
     if (!ar_->dry()) {
-        groupnorm_affine(x.p, x.dt, x.n, hw, x.c, 1, 1e-5f, nullptr, nullptr, a.scale, a.shift, x.c, 0, scratch, s_);
+        groupnorm_affine(x.p, x.dt, x.n, hw, x.c, 1, 1e-5f, nullptr, nullptr, a.scale, a.shift, x.c, 0, scratch, s_, gn_tickets_ ? gn_tickets_ + ((s_ == side_ && side_) ? gn_ticket_count() : 0) : nullptr);
         launches_ += 2;
     }
     ar_->free(scratch);
@@ -726,7 +738,7 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
 void Engine::gmflow(const float* x_nchw, int T, float* flows) {
     const std::string P = "flownet.model";
     const int HW = 512 * 512;
-    const int chunk = 4;
+    const int chunk = flow_chunk();
     for (int p0 = 0; p0 < T - 1; p0 += chunk) {
         const int np = std::min(chunk, T - 1 - p0);
         // images: [img0 = frames p0+1 .. p0+np | img1 = frames p0 .. p0+np-1], ImageNet-normalised NHWC
@@ -1116,7 +1128,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
                 CUDA_CHECK(cudaStreamCreateWithPriority(&side_, cudaStreamNonBlocking, lo));
                 CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
             }
-            while ((int)ev_flow_.size() < (T - 1 + 3) / 4) {
+            while ((int)ev_flow_.size() < (T - 1 + flow_chunk() - 1) / flow_chunk()) {
                 cudaEvent_t e;
                 CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 ev_flow_.push_back(e);
@@ -1132,7 +1144,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
         flows_async = !dry && !no_side;
     }
     if (capture_ && flows_async) {   // debug capture wants the complete flows now
-        CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / 4], 0));
+        CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / flow_chunk()], 0));
         flows_async = false;
     }
     capture("flows", flows.p, flows.bytes());
@@ -1144,7 +1156,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     static const int env_cap_frames = getenv("KEEP_MAIN_CAP_FRAMES") ? atoi(getenv("KEEP_MAIN_CAP_FRAMES")) : 8;
     main_cap_ = (flows_async && env_main_sms > 0) ? std::min(env_main_sms, num_sms_) : num_sms_;
     // ---- LQ encoder, batched over frames in chunks (keep_arch.py:1034-1037)
-    const int chunk = 4;
+    const int chunk = lq_chunk();
     for (int f0 = 0; f0 < T; f0 += chunk) {
         const int nf = std::min(chunk, T - f0);
         Tensor img = talloc(nf, 512, 512, 3, adt_);
@@ -1193,7 +1205,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
                 own_src = true;
                 if (!dry) { nchw_to_nhwc((const float*)fp->second.p + (size_t)(i - 1) * 3 * HW, src.p, F32, 1, 3, 512, 512, 0, s_); launches_ += 1; }
             }
-            if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(i - 1) / 4], 0));   // flow of pair i-1 is ready
+            if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(i - 1) / flow_chunk()], 0));   // flow of pair i-1 is ready
             Tensor warped = talloc(1, 512, 512, 3, adt_);
             if (!dry) {
                 flow_warp(src.p, src.dt, flows.f() + (size_t)(i - 1) * HW * 2, warped.p, warped.dt, 1, 512, 512, 3, s_);
@@ -1225,7 +1237,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
         prev_out = img;
     }
     main_cap_ = num_sms_;
-    if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / 4], 0));   // join the side branch
+    if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / flow_chunk()], 0));   // join the side branch
     if (prev_out.p) tfree(prev_out);
     tfree(gains);
     tfree(cfa_prev[0]); tfree(cfa_prev[1]);

@@ -105,6 +105,7 @@ class Engine {
     std::unordered_map<std::string, DevArr> W_;
     std::vector<std::pair<std::string, std::vector<float>>> staging_;
     float* wpool_ = nullptr;
+    int* gn_tickets_ = nullptr;  // GroupNorm fused-finalize arrival counters [2 streams][gn_ticket_count()]
     int* region_ = nullptr;      // GMFlow shifted-window region ids [4][1024]
     float* grid64_ = nullptr;    // GMFlow coordinate grid (4096, 2)
     Arena arena_, arena2_;          // main / side-branch (GMFlow) workspaces
@@ -114,7 +115,7 @@ class Engine {
     std::vector<cudaEvent_t> ev_flow_;   // one per GMFlow chunk of 4 pairs
     size_t side_bytes_ = 0;
     int main_cap_ = 148;                 // grid cap of main-stream persistent kernels (lowered while GMFlow overlaps)
-    int side_sms_ = 56;                  // grid cap of persistent kernels on the side branch
+    int side_sms_ = 100;                  // grid cap of persistent kernels on the side branch
     std::unordered_map<int, size_t> side_cache_;
     cudaStream_t s_ = nullptr;
     long long launches_ = 0;

@@ -10,7 +10,8 @@
 namespace keep {
 namespace {
 
-constexpr int GN_MAX_CHUNKS = 2048;
+constexpr int GN_MAX_CHUNKS = 296;   // two waves of 148 SMs per image; also bounds the fused finalize (one block reads them all)
+constexpr int GN_TICKETS = 256;       // arrival counters of the fused finalize: one per image, self-resetting
 
 // ~16K elements per block (16 float4 per thread): 512^2 x 64 -> 1024 blocks per image = ~7 resident blocks per SM
 static inline int gn_num_chunks(int hw, int c) {
@@ -19,11 +20,17 @@ static inline int gn_num_chunks(int hw, int c) {
 }
 
 // Stage 1: per-(image, chunk, channel) partial sums -> partial[n][chunk][c][2] (double).  Pure streaming read.
+// Fused finalize (tickets != null): the block that arrives LAST for its image reduces all of that image's partials in
+// chunk order (deterministic) and writes the per-channel affine -- the second kernel of the pair disappears (~4 us of a
+// ~12 us pair on the serial per-frame chain).
 template <typename T>
 __global__ void __launch_bounds__(256) gn_partial_kernel(const T* __restrict__ x, int hw, int c, int nchunks,
-                                                         double* __restrict__ partial) {
+                                                         double* __restrict__ partial, int* __restrict__ tickets, int cpg, float eps,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float* __restrict__ scale, float* __restrict__ shift, int c_total, int c_off) {
     pdl_prologue();
     extern __shared__ double sm[];  // [lanes][c][2]
+    __shared__ int s_last;
     const int c4 = c >> 2;
     const int lanes = blockDim.x / c4;
     const int cv = threadIdx.x % c4, lane = threadIdx.x / c4;
@@ -68,6 +75,47 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const T* __restrict__ x
         double* o = partial + (((size_t)n * nchunks + chunk) * c + ch) * 2;
         o[0] = ss;
         o[1] = qq;
+    }
+    if (!tickets) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(&tickets[n], 1);
+        s_last = (t == nchunks - 1) ? 1 : 0;
+        if (s_last) tickets[n] = 0;          // ready for the next launch on this stream
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // per-channel totals over the chunks (fixed order), into shared memory
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        double ss = 0, qq = 0;
+        const double* o = partial + ((size_t)n * nchunks * c + ch) * 2;
+        for (int k = 0; k < nchunks; ++k) {
+            ss += __ldcg(o + (size_t)k * c * 2);
+            qq += __ldcg(o + (size_t)k * c * 2 + 1);
+        }
+        sm[ch * 2] = ss;
+        sm[ch * 2 + 1] = qq;
+    }
+    __syncthreads();
+    const int groups = c / cpg;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double ss = 0, qq = 0;
+        for (int i = 0; i < cpg; ++i) { ss += sm[(g * cpg + i) * 2]; qq += sm[(g * cpg + i) * 2 + 1]; }
+        const double cnt = (double)hw * cpg;
+        const double mean = ss / cnt;
+        double var = qq / cnt - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        for (int i = 0; i < cpg; ++i) {
+            const int ch = g * cpg + i;
+            const float ga = gamma ? gamma[c_off + ch] : 1.0f;
+            const float be = beta ? beta[c_off + ch] : 0.0f;
+            const float sc = ga * rstd;
+            scale[(size_t)n * c_total + c_off + ch] = sc;
+            shift[(size_t)n * c_total + c_off + ch] = be - (float)mean * sc;
+        }
     }
 }
 
@@ -252,9 +300,10 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const T* __restrict__ x, 
 size_t gn_scratch_doubles(int n, int hw, int c) { return (size_t)n * gn_num_chunks(hw, c) * c * 2; }
 
 void gn_warmup() {}
+int gn_ticket_count() { return GN_TICKETS; }
 
 void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, float eps, const float* gamma, const float* beta,
-                      float* scale, float* shift, int c_total, int c_off, double* scratch, cudaStream_t s) {
+                      float* scale, float* shift, int c_total, int c_off, double* scratch, cudaStream_t s, int* ticket_buf) {
     KEEP_CHECK(c % 4 == 0 && c / 4 <= 256 && c % cpg == 0, "groupnorm: unsupported shape c=%d cpg=%d", c, cpg);
     if ((long long)hw * cpg <= 8192 && (long long)n * (c / cpg) >= 16) {   // small slab per group and enough groups to fill SMs
         const int blocks = n * (c / cpg);
@@ -269,9 +318,14 @@ void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, floa
     const int threads = ((lanes * c4 + 31) / 32) * 32;
     const size_t smem = (size_t)lanes * c * 2 * sizeof(double);
     dim3 grid(nchunks, n);
-    if (dt == F32) launch_k(gn_partial_kernel<float>, dim3(grid), dim3(threads), smem, s, (const float*)x, hw, c, nchunks, scratch);
-    else launch_k(gn_partial_kernel<__half>, dim3(grid), dim3(threads), smem, s, (const __half*)x, hw, c, nchunks, scratch);
+    // opt-in (KEEP_GN_FUSED=1): measured 135.2 -> 129.0 frames/s -- one block reducing nchunks x c doubles serially costs more
+    // than the ~4 us slot of a second, 32-block kernel (profiles/r1_experiments.md)
+    static const bool fuse_en = getenv("KEEP_GN_FUSED") && getenv("KEEP_GN_FUSED")[0] == '1';
+    int* tickets = (fuse_en && ticket_buf && n <= GN_TICKETS) ? ticket_buf : nullptr;
+    if (dt == F32) launch_k(gn_partial_kernel<float>, dim3(grid), dim3(threads), smem, s, (const float*)x, hw, c, nchunks, scratch, tickets, cpg, eps, gamma, beta, scale, shift, c_total, c_off);
+    else launch_k(gn_partial_kernel<__half>, dim3(grid), dim3(threads), smem, s, (const __half*)x, hw, c, nchunks, scratch, tickets, cpg, eps, gamma, beta, scale, shift, c_total, c_off);
     CUDA_CHECK(cudaGetLastError());
+    if (tickets) return;
     launch_k(gn_finalize_kernel, dim3(n * (c / cpg)), dim3(128), 0, s, scratch, hw, c, cpg, nchunks, eps, gamma, beta, scale, shift, c_total, c_off);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -58,11 +58,14 @@ void bgemm_simt(const BGemmArgs& a, cudaStream_t s);
 //   groups of `cpg` consecutive channels; gamma/beta may be null (InstanceNorm, affine-free)
 //   writes scale/shift at [n][c_total] + c_off  (c_total >= c, for concatenated inputs)
 //   scratch: gn_scratch_doubles(...) doubles
+//   ticket_buf: gn_ticket_count() zero-initialised ints owned by the caller, one buffer per concurrently used stream --
+//   large maps then fuse the finalize stage into the partial kernel; null: two kernels
 size_t gn_scratch_doubles(int n, int hw, int c);
+int gn_ticket_count();
 void gn_warmup();   // allocate the per-device ticket array (must happen outside CUDA-graph capture)
 void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, float eps,
                       const float* gamma, const float* beta, float* scale, float* shift,
-                      int c_total, int c_off, double* scratch, cudaStream_t s);
+                      int c_total, int c_off, double* scratch, cudaStream_t s, int* ticket_buf = nullptr);
 // LayerNorm over the last dim of (rows, c) fp32; out = LN(x)*g+b (+ res) ; out2 = out + add2[row % add2_rows]
 void layernorm(const float* x, int rows, int c, const float* g, const float* b, float eps,
                const float* res, float* out, const float* add2, int add2_rows, float* out2, cudaStream_t s);
