@@ -356,6 +356,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                             }
                             ol.x = *reinterpret_cast<uint32_t*>(&lq[0]); ol.y = *reinterpret_cast<uint32_t*>(&lq[1]);
                             ol.z = *reinterpret_cast<uint32_t*>(&lq[2]); ol.w = *reinterpret_cast<uint32_t*>(&lq[3]);
+                        } else if (a.pre_exact) {       // fp16 operands, but the activation still in fp32 (hybrid precision)
+                            if (a.pre_act == ACT_SWISH) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = swish_f<true>(v[j]);
+                            } else if (a.pre_act == ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
@@ -975,7 +985,7 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     TcConvArgs t;
     t.in0 = a.in0; t.in1 = a.in1; t.in0_dt = a.in0_dt; t.in1_dt = a.in1_dt; t.c0 = a.c0; t.c1 = a.c1;
     t.n = a.n; t.h = a.h; t.w = a.w; t.up = a.up;
-    t.pre_scale = a.pre_scale; t.pre_shift = a.pre_shift; t.pre_act = a.pre_act;
+    t.pre_scale = a.pre_scale; t.pre_shift = a.pre_shift; t.pre_act = a.pre_act; t.pre_exact = a.pre_exact;
     t.wt = packed; t.bias = a.bias;
     t.wt_img_stride = a.wt_img_stride;
     const bool s2d = tc_is_s2d(a);

@@ -363,11 +363,15 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     const bool use_tc = !use_small && (flags_ & KEEP_FLAG_TCGEN05) && !o.exact && tc_eligible(a);
     int bn = 0;
     void* part = nullptr;
+    // precision of this layer's tensor-core operands: the engine mode, or 1 pass where the caller marked the layer as
+    // downstream of every decision (pass_override_, see generator())
+    const int passes = (pass_override_ && tc_passes_ == 3) ? pass_override_ : tc_passes_;
+    a.pre_exact = (passes == 1 && tc_passes_ == 3) ? 1 : 0;   // keep the exact fp32 swish in front of the fp16 rounding
     if (use_tc) {
         const long long m_tiles = cw.kh == 3 ? (long long)x.n * cdiv(a.ho, 16) * cdiv(a.wo, 8)
                                              : (long long)x.n * cdiv((long long)x.h * x.w, 128);
-        bn = tc_pick_bn(cw.cout, m_tiles, tc_passes_);
-        a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), cdiv(tc_virtual_cin(a, tc_passes_), tc_cb(tc_passes_)));
+        bn = tc_pick_bn(cw.cout, m_tiles, passes);
+        a.splitk = tc_pick_splitk(m_tiles, cdiv(cw.cout, bn), cdiv(tc_virtual_cin(a, passes), tc_cb(passes)));
     } else {
         a.splitk = use_small ? 1 : conv_pick_splitk(a);
     }
@@ -381,7 +385,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             pr.a = get_event(); pr.b = get_event();
             pr.flops = 2.0 * (double)out.rows() * cw.cout * cw.kh * cw.kw * cw.cin;
             pr.bytes = (double)x.bytes() + (o.in1 ? (double)o.in1->bytes() : 0.0) + (double)out.bytes() +
-                       (o.res ? (double)o.res->bytes() : 0.0) + (use_tc ? 2.0 * (tc_passes_ == 3 ? 2 : 1) : 4.0) * cw.cout * cw.kh * cw.kw * cw.cin;
+                       (o.res ? (double)o.res->bytes() : 0.0) + (use_tc ? 2.0 * (passes == 3 ? 2 : 1) : 4.0) * cw.cout * cw.kh * cw.kw * cw.cin;
             pr.tag = use_tc ? 1 : 0;
             pr.m = (int)out.rows(); pr.k = cw.kh * cw.kw * cw.cin; pr.n = cw.cout; pr.kh = cw.kh * 10 + o.stride; pr.splitk = a.splitk; pr.bn = bn;
             CUDA_CHECK(cudaEventRecord(pr.a, s_));
@@ -390,7 +394,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         // stream always finds free SMs
         const int grid_cap = (s_ == side_ && side_) ? side_sms_ : main_cap_;
         int nl = a.splitk > 1 ? 2 : 1;
-        if (use_tc) nl = conv2d_tc(a, tc_weights(cw, bn, tc_passes_, tc_is_s2d(a) ? a.pad_t : -1), bn, tc_passes_, a.splitk, a.partial, grid_cap, s_);
+        if (use_tc) nl = conv2d_tc(a, tc_weights(cw, bn, passes, tc_is_s2d(a) ? a.pad_t : -1), bn, passes, a.splitk, a.partial, grid_cap, s_);
         else if (use_small) conv2d_small(a, s_);
         else conv2d_simt(a, s_);
         launches_ += nl;
@@ -1048,7 +1052,12 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[3], Tensor 
     Tensor x = quant;
     bool own = false;
     Aff pend;
+    // KEEP_GEN_FAST_FROM=j (experiment, default off): generator blocks >= j run with plain fp16 operands (1 MMA pass instead
+    // of 3) in the split-precision mode -- they are the last layers before the pixels, so their rounding error is not
+    // amplified by later normalisations; 20 = the 512^2 level, 17 = + the 256^2 level
+    static const int fast_from = getenv("KEEP_GEN_FAST_FROM") ? atoi(getenv("KEEP_GEN_FAST_FROM")) : 99;
     for (int j = 0; j < 25; ++j) {
+        pass_override_ = j >= fast_from ? 1 : 0;
         const std::string bp = "generator.blocks." + std::to_string(j);
         const std::string kind = kGenProg[j];
         Tensor y;
@@ -1093,6 +1102,7 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[3], Tensor 
             }
         }
     }
+    pass_override_ = 0;
     return x;   // (1,512,512,3) fp32
 }
 

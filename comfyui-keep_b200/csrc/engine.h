@@ -126,6 +126,7 @@ class Engine {
     struct TcW { __half* p = nullptr; int bn = 0, passes = 0; };
     std::unordered_map<const float*, TcW> tcw_;
     const __half* tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad);
+    int pass_override_ = 0;   // != 0: operand passes for the layers being enqueued (generator tail experiment)
     int tc_passes_ = 1;   // 1: fp16 operands; 3: split-precision (fp32-grade) tensor-core mode
     int num_sms_ = 148;
     // CUDA graph of one clip forward (KEEP_FLAG_CUDA_GRAPH): ~1800 launches per frame collapse into one graph launch

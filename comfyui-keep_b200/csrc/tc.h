@@ -7,7 +7,7 @@ namespace keep {
 struct TcConvArgs {
     const void* in0; const void* in1; int in0_dt, in1_dt; int c0, c1;
     int n, h, w, up;
-    const float* pre_scale; const float* pre_shift; int pre_act;
+    const float* pre_scale; const float* pre_shift; int pre_act; int pre_exact;
     const __half* wt; const float* bias;
     long long wt_img_stride;   // halfs between per-image weight panel sets (attention GEMMs); 0 for convolutions
     int taps, cout, bn, ho, wo, ncb;
