@@ -76,6 +76,16 @@ int keep_forward(keep_handle h, const float* x_dev, int b, int T, void* out_dev,
     KEEP_API_END
 }
 
+int keep_forward_u8(keep_handle h, const unsigned char* x_u8_dev, int b, int T, unsigned char* out_u8_dev, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h, "keep_forward_u8: null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->e->forward_u8(x_u8_dev, b, T, out_u8_dev, workspace, workspace_bytes, (cudaStream_t)stream);
+    return 0;
+    KEEP_API_END
+}
+
 int keep_destroy(keep_handle h) {
     KEEP_API_BEGIN
     if (h) {

@@ -915,9 +915,11 @@ void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, in
 }
 
 int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb) {
+    static const int target = getenv("KEEP_TC_SPLIT_TARGET") ? atoi(getenv("KEEP_TC_SPLIT_TARGET")) : 80;   // CTAs to aim for
+    static const int nosplit = getenv("KEEP_TC_SPLIT_MIN") ? atoi(getenv("KEEP_TC_SPLIT_MIN")) : 96;          // enough tiles: no split
     const long long ctas = m_tiles * ntile_n;
-    if (ctas >= 96 || ncb < 2) return 1;
-    long long s = (148 + ctas - 1) / ctas;
+    if (ctas >= nosplit || ncb < 2) return 1;
+    long long s = (target + ctas - 1) / ctas;
     if (s > ncb) s = ncb;
     return (int)(s < 1 ? 1 : s);
 }

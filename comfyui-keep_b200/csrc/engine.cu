@@ -283,6 +283,7 @@ Engine::~Engine() {
     cudaFree(wpool_);
     cudaFree(region_);
     cudaFree(gn_tickets_);
+    cudaFree(u8_stage_);
     cudaFree(grid64_);
     cudaFree(own_ws_);
     for (auto& kv : cap_) cudaFree(kv.second.p);
@@ -1239,8 +1240,11 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
         Tensor img = generator(quant, i, taps, cfa_prev);
         tfree(quant);
         if (!dry) {
-            nhwc_to_nchw(img.p, img.dt, (char*)out_dev + (size_t)i * 3 * HW * (out_dtype == KEEP_OUT_F16 ? 2 : 4),
-                         out_dtype == KEEP_OUT_F16 ? F16 : F32, 1, 3, 512, 512, s_);
+            if (out_dtype == KEEP_OUT_U8_BGR)
+                nhwc_to_u8bgr(img.p, img.dt, (unsigned char*)out_dev + (size_t)i * 3 * HW, 1, 512, 512, s_);
+            else
+                nhwc_to_nchw(img.p, img.dt, (char*)out_dev + (size_t)i * 3 * HW * (out_dtype == KEEP_OUT_F16 ? 2 : 4),
+                             out_dtype == KEEP_OUT_F16 ? F16 : F32, 1, 3, 512, 512, s_);
             launches_ += 1;
         }
         if (prev_out.p) tfree(prev_out);
@@ -1273,7 +1277,7 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
     KEEP_CHECK(!dry_only_, "keep_forward: engine was created with KEEP_FLAG_PLAN_ONLY (no device)");
     KEEP_CHECK(x_dev && out_dev, "keep_forward: null tensor");
     KEEP_CHECK(b >= 1 && T >= 2 && T <= 100, "keep_forward: need b >= 1 and 2 <= T <= 100 (got b=%d T=%d)", b, T);
-    KEEP_CHECK(out_dtype == KEEP_OUT_F32 || out_dtype == KEEP_OUT_F16, "keep_forward: bad out_dtype %d", out_dtype);
+    KEEP_CHECK(out_dtype == KEEP_OUT_F32 || out_dtype == KEEP_OUT_F16 || out_dtype == KEEP_OUT_U8_BGR, "keep_forward: bad out_dtype %d", out_dtype);
     CUDA_CHECK(cudaSetDevice(device_));
     const size_t need = workspace_bytes(1, T);
     side_bytes_ = side_cache_[T];
@@ -1292,7 +1296,7 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
     KEEP_CHECK(ws_bytes >= need, "keep_forward: workspace too small (%zu < %zu)", ws_bytes, need);
     KEEP_CHECK(((uintptr_t)ws & 255) == 0, "keep_forward: workspace must be 256-byte aligned");
     const size_t per_clip = (size_t)T * 3 * 512 * 512;
-    const size_t osz = out_dtype == KEEP_OUT_F16 ? 2 : 4;
+    const size_t osz = out_dtype == KEEP_OUT_F16 ? 2 : (out_dtype == KEEP_OUT_U8_BGR ? 1 : 4);
     bool forcing = false;
     for (auto& kv : forced_) forcing = forcing || kv.second.p != nullptr;
     const bool want_graph = (flags_ & KEEP_FLAG_CUDA_GRAPH) && !capture_ && !profile_ && !forcing && ws == own_ws_;
@@ -1354,6 +1358,26 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
             eager_runs_[T] += 1;
         }
     }
+}
+
+// uint8 BGR HWC in / out: the host-side img2tensor / normalize / tensor2img of keep_processor.py:258-260,
+// 272-273 folded into the device path -- one conversion kernel in front, the output layout kernel writes the bytes
+void Engine::forward_u8(const unsigned char* x_u8_dev, int b, int T, unsigned char* out_u8_dev, void* ws, size_t ws_bytes, cudaStream_t s) {
+    KEEP_CHECK(!dry_only_, "keep_forward_u8: engine was created with KEEP_FLAG_PLAN_ONLY (no device)");
+    KEEP_CHECK(x_u8_dev && out_u8_dev, "keep_forward_u8: null tensor");
+    KEEP_CHECK(b >= 1 && T >= 2 && T <= 100, "keep_forward_u8: need b >= 1 and 2 <= T <= 100 (got b=%d T=%d)", b, T);
+    CUDA_CHECK(cudaSetDevice(device_));
+    const size_t need = (size_t)b * T * 3 * 512 * 512 * sizeof(float);
+    if (u8_stage_bytes_ < need) {
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        cudaFree(u8_stage_);
+        u8_stage_ = nullptr; u8_stage_bytes_ = 0;
+        CUDA_CHECK(cudaMalloc((void**)&u8_stage_, need));
+        u8_stage_bytes_ = need;
+    }
+    u8bgr_to_nchw_norm(x_u8_dev, u8_stage_, b * T, 512, 512, s);
+    launches_ += 1;
+    forward(u8_stage_, b, T, out_u8_dev, KEEP_OUT_U8_BGR, ws, ws_bytes, s);
 }
 
 // =============================================================================================

@@ -50,6 +50,7 @@ class Engine {
     ~Engine();
     size_t workspace_bytes(int b, int T);
     void forward(const float* x_dev, int b, int T, void* out_dev, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t s);
+    void forward_u8(const unsigned char* x_u8_dev, int b, int T, unsigned char* out_u8_dev, void* ws, size_t ws_bytes, cudaStream_t s);
     // test hooks (stage-wise teacher forcing / intermediate capture)
     void force(const std::string& what, const void* host, size_t bytes);
     size_t read(const std::string& what, void* host, size_t bytes);
@@ -105,6 +106,7 @@ class Engine {
     std::unordered_map<std::string, DevArr> W_;
     std::vector<std::pair<std::string, std::vector<float>>> staging_;
     float* wpool_ = nullptr;
+    float* u8_stage_ = nullptr; size_t u8_stage_bytes_ = 0;   // fp32 copy of a uint8 input clip (forward_u8)
     int* gn_tickets_ = nullptr;  // GroupNorm fused-finalize arrival counters [2 streams][gn_ticket_count()]
     int* region_ = nullptr;      // GMFlow shifted-window region ids [4][1024]
     float* grid64_ = nullptr;    // GMFlow coordinate grid (4096, 2)

@@ -304,6 +304,36 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const void* x, int dt
     for (int ch = 0; ch < c; ++ch) st1_any(out, o_dt, (n * c + ch) * hw + p, ld1_any(x, dt, i * c + ch));
 }
 
+// keep_processor.py:258-260: float32(crop_u8 / 255.) (the division is done in float64), BGR -> RGB, (v - 0.5) / 0.5
+__global__ void __launch_bounds__(256) u8bgr_to_nchw_norm_kernel(const unsigned char* __restrict__ x, float* __restrict__ out, int hw,
+                                                                 size_t total) {
+    pdl_prologue();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
+    if (i >= total) return;
+    const size_t n = i / hw, p = i % hw;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {   // output channel ch (R, G, B) <- input byte 2 - ch
+        float v = (float)((double)x[i * 3 + (2 - ch)] / 255.0);
+        v = (v - 0.5f) / 0.5f;
+        out[(n * 3 + ch) * hw + p] = v;
+    }
+}
+
+// B/utils/img_util.py:38-94 (tensor2img, rgb2bgr=True, min_max=(-1, 1), uint8): clamp, (x - min) / (max - min), * 255, round half even
+__global__ void __launch_bounds__(256) nhwc_to_u8bgr_kernel(const void* x, int dt, unsigned char* __restrict__ out, size_t total) {
+    pdl_prologue();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
+    if (i >= total) return;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float v = ld1_any(x, dt, i * 3 + ch);
+        v = fminf(fmaxf(v, -1.0f), 1.0f);
+        v = (v - (-1.0f)) / (1.0f - (-1.0f));
+        v = v * 255.0f;
+        out[i * 3 + (2 - ch)] = (unsigned char)__float2int_rn(v);
+    }
+}
+
 // arch_util.py:113-144 -> F.grid_sample(bilinear, zeros, align_corners=True)
 __global__ void __launch_bounds__(256) flow_warp_kernel(const void* img, int dt, const float* __restrict__ flow, void* out,
                                                         int o_dt, int h, int w, int c, size_t total) {
@@ -496,6 +526,18 @@ void nchw_to_nhwc(const float* x, void* out, int o_dt, int n, int c, int h, int 
 void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s) {
     const size_t total = (size_t)n * h * w;
     launch_k(nhwc_to_nchw_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, dt, out, out_dt, c, h * w, total);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void u8bgr_to_nchw_norm(const unsigned char* x, float* out, int n, int h, int w, cudaStream_t s) {
+    const size_t total = (size_t)n * h * w;
+    launch_k(u8bgr_to_nchw_norm_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, out, h * w, total);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void nhwc_to_u8bgr(const void* x, int dt, unsigned char* out, int n, int h, int w, cudaStream_t s) {
+    const size_t total = (size_t)n * h * w;
+    launch_k(nhwc_to_u8bgr_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, dt, out, total);
     CUDA_CHECK(cudaGetLastError());
 }
 

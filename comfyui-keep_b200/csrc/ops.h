@@ -108,6 +108,10 @@ void sparse_causal_gather(const float* kv, float* out, int b, int T, int L, int 
 // x NCHW fp32 [-1,1] -> NHWC (dt): mode 0 copy ; mode 1 GMFlow normalisation ((x+1)/2 - mean)/std
 void nchw_to_nhwc(const float* x, void* out, int o_dt, int n, int c, int h, int w, int mode, cudaStream_t s);
 void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s);
+// caller-side conversions of keep_processor.py folded in: uint8 BGR HWC crops -> fp32 RGB NCHW in [-1, 1]
+// (img2tensor(crop / 255., bgr2rgb=True) + normalize(0.5, 0.5)), and fp32 RGB NHWC -> uint8 BGR HWC (tensor2img, min_max (-1, 1))
+void u8bgr_to_nchw_norm(const unsigned char* x, float* out, int n, int h, int w, cudaStream_t s);
+void nhwc_to_u8bgr(const void* x, int dt, unsigned char* out, int n, int h, int w, cudaStream_t s);
 // bilinear warp (grid_sample bilinear / zeros / align_corners=True), img NHWC c channels, flow (n,h,w,2) px
 void flow_warp(const void* img, int dt, const float* flow, void* out, int o_dt, int n, int h, int w, int c, cudaStream_t s);
 // GMFlow: add windowed sine position embedding in place on (n, h, w, c) fp32  (utils.py:66-86)

@@ -62,6 +62,7 @@ def load_library():
     lib.keep_workspace_bytes.argtypes = [vp, ci, ci]
     lib.keep_workspace_bytes.restype = cs
     lib.keep_forward.argtypes = [vp, vp, ci, ci, vp, ci, vp, cs, vp]
+    lib.keep_forward_u8.argtypes = [vp, vp, ci, ci, vp, vp, cs, vp]
     lib.keep_destroy.argtypes = [vp]
     lib.keep_launch_count.argtypes = [vp]
     lib.keep_launch_count.restype = ctypes.c_longlong
@@ -238,6 +239,32 @@ class KeepNetB200(nn.Module):
             rc = lib.keep_forward(self._engine, x.data_ptr(), int(x.shape[0]), int(x.shape[1]), out.data_ptr(),
                                   1 if out_dtype == torch.float16 else 0, None, 0, ctypes.c_void_p(stream))
         _check(lib, rc, "keep_forward")
+        return out
+
+    @torch.no_grad()
+    def forward_u8(self, crops_u8):
+        """crops_u8: (b, T>=2, 512, 512, 3) uint8 BGR (the aligned crops as OpenCV holds them) on the engine's device ->
+        restored crops, same layout and dtype.  Equals, bit for bit, what keep_processor.py:258-260,272-273 computes on the
+        host around the fp32 call: tensor2img(net(normalize(img2tensor(crop / 255., bgr2rgb=True), .5, .5)), rgb2bgr=True,
+        min_max=(-1, 1)) -- with a quarter of the host<->device bytes."""
+        if self._engine is None:
+            raise RuntimeError("KeepNetB200: no device engine — call .load_state_dict(...) and .to('cuda') first "
+                               "(there is no CPU fallback)")
+        x = crops_u8
+        if x.dtype != torch.uint8 or x.dim() != 5 or tuple(x.shape[2:]) != (512, 512, 3):
+            raise RuntimeError("KeepNetB200.forward_u8: expected uint8 (b, T, 512, 512, 3), got %s %s" % (x.dtype, tuple(x.shape)))
+        if x.shape[1] < 2:
+            raise RuntimeError("KeepNetB200: T must be >= 2 (the reference duplicates single frames, keep_processor.py:173-175)")
+        if not x.is_cuda or x.device != self._device:
+            raise RuntimeError("KeepNetB200: input on %s but the engine lives on %s" % (x.device, self._device))
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        lib = load_library()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            rc = lib.keep_forward_u8(self._engine, x.data_ptr(), int(x.shape[0]), int(x.shape[1]), out.data_ptr(), None, 0,
+                                     ctypes.c_void_p(stream))
+        _check(lib, rc, "keep_forward_u8")
         return out
 
     # ---- test hooks ----------------------------------------------------------------------------

@@ -34,7 +34,9 @@ typedef struct {
     int64_t shape[4];
 } keep_weight_desc;
 
-enum { KEEP_OUT_F32 = 0, KEEP_OUT_F16 = 1 };
+/* KEEP_OUT_U8_BGR: (b, T, 512, 512, 3) uint8, BGR, HWC -- the image tensor2img(rgb2bgr=True, min_max=(-1, 1)) would make of
+ * the fp32 output (clamp, (x+1)/2*255, round-half-even; B/utils/img_util.py:38-94) */
+enum { KEEP_OUT_F32 = 0, KEEP_OUT_F16 = 1, KEEP_OUT_U8_BGR = 2 };
 enum {
     KEEP_FLAG_DEFAULT = 0,
     KEEP_FLAG_FP16_FEATURES = 1, /* store conv feature maps as fp16 in HBM */
@@ -61,6 +63,13 @@ size_t keep_workspace_bytes(keep_handle h, int b, int T);
  * synchronisation inside. */
 int keep_forward(keep_handle h, const float* x_dev, int b, int T, void* out_dev, int out_dtype, void* workspace,
                  size_t workspace_bytes, void* stream);
+
+/* Same path with the caller-side conversions folded in: x_u8_dev is (b, T, 512, 512, 3) uint8 BGR HWC --
+ * the aligned crops as OpenCV holds them -- converted on the device exactly as keep_processor.py:258-260 does on the host
+ * (img2tensor(crop / 255., bgr2rgb=True) then normalize(0.5, 0.5)); out_u8_dev is KEEP_OUT_U8_BGR.  A 20-frame clip moves
+ * 15.7 MB each way instead of 62.9 MB. */
+int keep_forward_u8(keep_handle h, const unsigned char* x_u8_dev, int b, int T, unsigned char* out_u8_dev, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* Free packed weights and any engine-owned workspace (KEEPModelPack.offload, keep_model_loader.py:45-61). */
 int keep_destroy(keep_handle h);

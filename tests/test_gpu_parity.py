@@ -216,3 +216,42 @@ def test_cuda_graph_replay_is_bitwise_identical_to_eager(keep_mod, state_dict):
     st.synchronize()
     assert torch.equal(y, rb)
     eager.to("cpu"); graph.to("cpu")
+
+
+def _host_pre(crops_u8):
+    """keep_processor.py:258-260 restated: img2tensor(crop / 255., bgr2rgb=True, float32=True) then normalize(.5, .5)
+    (B/utils/img_util.py:9-35: the float64 quotient is cast to float32 before the BGR->RGB swap)."""
+    import numpy as np
+    a = crops_u8.cpu().numpy()                                   # (b, T, 512, 512, 3) BGR
+    f = (a / 255.).astype("float32")[..., ::-1]                  # RGB
+    t = torch.from_numpy(np.ascontiguousarray(f.transpose(0, 1, 4, 2, 3)))
+    return (t - 0.5) / 0.5
+
+
+def _host_post(out_f32):
+    """keep_processor.py:272-273 restated: tensor2img(t, rgb2bgr=True, min_max=(-1, 1)) -> uint8 BGR HWC
+    (B/utils/img_util.py:38-94: clamp, (x - min) / (max - min), * 255, numpy round half even)."""
+    import numpy as np
+    t = out_f32.float().cpu().clamp(-1, 1)
+    t = (t - (-1.0)) / (1.0 - (-1.0))
+    a = t.numpy().transpose(0, 1, 3, 4, 2)[..., ::-1]            # HWC, BGR
+    return torch.from_numpy(np.ascontiguousarray((a * 255.0).round().astype("uint8")))
+
+
+def test_forward_u8_equals_host_conversions_around_fp32_call(net):
+    """uint8 BGR crops in, uint8 BGR crops out must be bit-identical to the reference's host-side
+    img2tensor / normalize / tensor2img wrapped around the fp32 call of the same engine."""
+    g = torch.Generator().manual_seed(2024)
+    base = torch.randint(0, 256, (1, 1, 64, 64, 3), generator=g, dtype=torch.uint8)
+    crops = torch.nn.functional.interpolate(base[0].permute(0, 3, 1, 2).float(), size=(512, 512), mode="bilinear")
+    crops = crops.permute(0, 2, 3, 1).round().clamp(0, 255).to(torch.uint8)[None]       # smooth face-like content
+    crops = torch.cat([crops, crops.roll(3, dims=3)], 1).contiguous()                   # T = 2, shifted copy
+    x = _host_pre(crops)
+    want = _host_post(net(x.cuda(), need_upscale=False))
+    got = net.forward_u8(crops.cuda()).cpu()
+    assert got.dtype == torch.uint8 and got.shape == crops.shape
+    assert torch.equal(got, want), "uint8 path differs from the host conversions in %d bytes" % int((got != want).sum())
+    with pytest.raises(RuntimeError):
+        net.forward_u8(crops.cuda().float())                                            # wrong dtype
+    with pytest.raises(RuntimeError):
+        net.forward_u8(crops)                                                           # CPU tensor: no fallback
