@@ -246,6 +246,30 @@ def main():
     e2e_value = world * T * k2 / (float(t2.item()) * 1e-3)
     nbytes = x_host.numel() * 4
 
+    # ---- the same call with uint8 BGR crops in / out (keep_forward_u8): the host-side img2tensor /
+    # normalize / tensor2img of keep_processor.py folded into the device path, a quarter of the host<->device bytes
+    u8_host = ((x_host.permute(0, 1, 3, 4, 2).flip(-1) * 0.5 + 0.5) * 255.0).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+    u8_out_host = torch.empty_like(u8_host).pin_memory()
+
+    def e2e_u8_step():
+        out = net.forward_u8(u8_host.to(dev, non_blocking=True))
+        u8_out_host.copy_(out, non_blocking=True)
+
+    e2e_u8_step(); e2e_u8_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(k2):
+        e2e_u8_step()
+    b.record()
+    torch.cuda.synchronize()
+    t3 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * T * k2 / (float(t3.item()) * 1e-3)
+
     # ---- roofline leg: per-launch CUDA events around every conv/GEMM launch (one extra clip, rank 0's view)
     pk = peaks()
     net.profile(True)
@@ -311,6 +335,8 @@ def main():
                        "collective": "NCCL gather of fp16 decoded frames to rank 0" if world > 1 else "none"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+            "e2e_u8": {"value": e2e_u8_value, "unit": "frames/s", "h2d_bytes_per_step": u8_host.numel(), "d2h_bytes_per_step": u8_host.numel(),
+                       "note": "keep_forward_u8: uint8 BGR crops in/out, host-side img2tensor/normalize/tensor2img folded in (no gather leg)"},
             "roofline": roofline,
         }
         if cpu is not None:
