@@ -143,6 +143,9 @@ def main():
     ap.add_argument("--frames", type=int, default=T_CLIP)
     ap.add_argument("--mode", default=os.environ.get("KEEP_BENCH_MODE", "auto"), choices=["auto", "fp32", "tc", "tc3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clips-per-step", type=int, default=1,
+                    help="clips per GPU per step (default 1 = BASELINE configs[1]); > 1 is the stream-of-clips workload (configs[4]): "
+                         "independent clips, two in flight per GPU on engine replicas (KeepNetB200(concurrent_clips=2))")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying the per-clip CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -175,15 +178,16 @@ def main():
         flags |= keep_b200.keep_net.FLAG_TCGEN05 | keep_b200.keep_net.FLAG_TC_SPLIT3
     if not args.no_graph:
         flags |= keep_b200.keep_net.FLAG_CUDA_GRAPH
-    net = keep_b200.KeepNetB200(flags=flags)
+    B = max(1, args.clips_per_step)
+    net = keep_b200.KeepNetB200(flags=flags, concurrent_clips=min(B, int(os.environ.get("KEEP_BENCH_REPLICAS", "2"))) if B > 1 else 1)
     net.load_state_dict(keep_b200.synth.make_state_dict(seed=0), strict=True)
     net.eval().to(dev)
-    x_host = keep_b200.synth.make_clip(T, seed=1234 + rank, coherent=True).pin_memory()
+    x_host = torch.cat([keep_b200.synth.make_clip(T, seed=1234 + rank + 100 * i, coherent=True) for i in range(B)], 0).pin_memory()
     out_host = torch.empty_like(x_host).pin_memory()
     x = x_host.to(dev)
     gather_buf = None
     if world > 1 and rank == 0:
-        gather_buf = [torch.empty((1, T, 3, 512, 512), dtype=torch.float16, device=dev) for _ in range(world)]
+        gather_buf = [torch.empty((B, T, 3, 512, 512), dtype=torch.float16, device=dev) for _ in range(world)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(inp):
@@ -221,7 +225,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = world * T * args.steps / (ms * 1e-3)
+    value = world * B * T * args.steps / (ms * 1e-3)
 
     # ---- e2e through the plugin call with host buffers (H2D + D2H inside the timed span)
     def e2e_step():
@@ -243,7 +247,7 @@ def main():
     t2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * T * k2 / (float(t2.item()) * 1e-3)
+    e2e_value = world * B * T * k2 / (float(t2.item()) * 1e-3)
     nbytes = x_host.numel() * 4
 
     # ---- the same call with uint8 BGR crops in / out (keep_forward_u8): the host-side img2tensor /
@@ -268,7 +272,7 @@ def main():
     t3 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-    e2e_u8_value = world * T * k2 / (float(t3.item()) * 1e-3)
+    e2e_u8_value = world * B * T * k2 / (float(t3.item()) * 1e-3)
 
     # ---- roofline leg: per-launch CUDA events around every conv/GEMM launch (one extra clip, rank 0's view)
     pk = peaks()
@@ -308,8 +312,8 @@ def main():
         "gflop_per_clip": pf["gflop"], "algorithmic_gb_per_clip": pf["gbytes"],
         "hbm_achieved_gbs": pf["gbytes"] / max(pf["ms"], 1e-9) * 1e3, "hbm_peak_gbs": pk["hbm_gbs"],
         "other_family": prof["cuda_core" if fam == "tcgen05" else "tcgen05"],
-        "whole_path_tflops": clip_flops(T) * world * args.steps / (ms * 1e-3) / 1e12 / world,
-        "whole_path_frac_of_tensor_peak": clip_flops(T) * args.steps / (ms * 1e-3) / 1e12 / pk["tflops_sustained"],
+        "whole_path_tflops": clip_flops(T) * B * world * args.steps / (ms * 1e-3) / 1e12 / world,
+        "whole_path_frac_of_tensor_peak": clip_flops(T) * B * args.steps / (ms * 1e-3) / 1e12 / pk["tflops_sustained"],
     }
 
     if world > 1:
@@ -328,7 +332,8 @@ def main():
             "metric": "512x512 aligned-face frames/sec through keep_net (20-frame clips)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[mode], "data": "synthetic",
-            "config": {"workload": "KEEP general model, %d-frame aligned 512x512 synthetic clip, one clip per GPU per step" % T,
+            "config": {"workload": "KEEP general model, %d-frame aligned 512x512 synthetic clip, %s per GPU per step" % (
+                           T, "one clip" if B == 1 else "%d independent clips (two in flight on engine replicas)" % B),
                        "weights": "seeded synthetic (no checkpoint offline)", "engine_mode": mode,
                        "cuda_graph": not args.no_graph,
                        "l2": "256 MiB buffer zeroed between timed steps; per-step working set >> 126 MB L2",

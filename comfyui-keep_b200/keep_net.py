@@ -99,8 +99,15 @@ def expected_shapes():
 class KeepNetB200(nn.Module):
     """Drop-in replacement for the reference `KEEP` module on the inference path."""
 
-    def __init__(self, flags=0, **cfg):
+    def __init__(self, flags=0, concurrent_clips=1, **cfg):
+        """concurrent_clips > 1: a batch of b > 1 clips is spread over that many engine replicas, each on its
+        own CUDA stream.  Clips are independent (keep_processor.py:263-270) and one clip's serial per-frame chain leaves most
+        SMs idle most of the time, so two clips in flight raise the throughput of a stream of clips; results are bitwise those
+        of the clip-by-clip loop."""
         super().__init__()
+        self._nrep = max(1, int(concurrent_clips))
+        self._replicas = []           # extra engines (keep_handle) beyond the primary one, created on first use
+        self._rep_streams = []
         for k, v in cfg.items():
             if k in KEEP_GENERAL_CFG and KEEP_GENERAL_CFG[k] != v:
                 raise ValueError("KeepNetB200 implements the 'KEEP' (general) config only: %s=%r != %r"
@@ -135,13 +142,16 @@ class KeepNetB200(nn.Module):
         self._weights = w
         self._drop_engine()
         if self._device.type == "cuda":
-            self._make_engine()
+            self._engine = self._make_engine()
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     # ---- residency -----------------------------------------------------------------------------
     def _drop_engine(self):
+        lib = load_library() if (self._engine is not None or self._replicas) else None
+        for h in self._replicas:
+            lib.keep_destroy(h)
+        self._replicas, self._rep_streams = [], []
         if self._engine is not None:
-            lib = load_library()
             lib.keep_destroy(self._engine)
             self._engine = None
 
@@ -166,7 +176,6 @@ class KeepNetB200(nn.Module):
         dev = self._device.index if self._device.type == "cuda" and self._device.index is not None else (
             torch.cuda.current_device() if self._device.type == "cuda" else 0)
         _check(lib, lib.keep_create(ctypes.byref(h), int(dev), descs, len(names), int(flags)), "keep_create")
-        self._engine = h
         return h
 
     def to(self, *args, **kwargs):
@@ -188,7 +197,7 @@ class KeepNetB200(nn.Module):
                 self._drop_engine()
                 self._device = device
                 if self._weights is not None:
-                    self._make_engine()
+                    self._engine = self._make_engine()
         else:  # offload: free packed device weights + workspace (keep_model_loader.py:45-61)
             self._drop_engine()
             self._device = device
@@ -234,12 +243,39 @@ class KeepNetB200(nn.Module):
         x = x.to(torch.float32).contiguous()
         out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
         lib = load_library()
+        odt = 1 if out_dtype == torch.float16 else 0
+        b, T = int(x.shape[0]), int(x.shape[1])
+        if b > 1 and self._nrep > 1:
+            self._forward_concurrent(lib, x, out, odt)
+            return out
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
-            rc = lib.keep_forward(self._engine, x.data_ptr(), int(x.shape[0]), int(x.shape[1]), out.data_ptr(),
-                                  1 if out_dtype == torch.float16 else 0, None, 0, ctypes.c_void_p(stream))
+            rc = lib.keep_forward(self._engine, x.data_ptr(), b, T, out.data_ptr(), odt, None, 0, ctypes.c_void_p(stream))
         _check(lib, rc, "keep_forward")
         return out
+
+    def _forward_concurrent(self, lib, x, out, odt):
+        """clip i -> engine replica i % R on stream i % R; the caller's stream waits for all of them."""
+        R = min(self._nrep, int(x.shape[0]))
+        with torch.cuda.device(x.device):
+            while len(self._replicas) < R - 1:
+                self._replicas.append(self._make_engine())
+            while len(self._rep_streams) < R:
+                self._rep_streams.append(torch.cuda.Stream(device=x.device))
+            engines = [self._engine] + self._replicas
+            cur = torch.cuda.current_stream(x.device)
+            per_in, per_out = x[0].numel() * x.element_size(), out[0].numel() * out.element_size()
+            for r in range(R):
+                self._rep_streams[r].wait_stream(cur)
+            for i in range(int(x.shape[0])):
+                st = self._rep_streams[i % R]
+                rc = lib.keep_forward(engines[i % R], x.data_ptr() + i * per_in, 1, int(x.shape[1]), out.data_ptr() + i * per_out,
+                                      odt, None, 0, ctypes.c_void_p(st.cuda_stream))
+                _check(lib, rc, "keep_forward")
+            for r in range(R):
+                x.record_stream(self._rep_streams[r])
+                out.record_stream(self._rep_streams[r])
+                cur.wait_stream(self._rep_streams[r])
 
     @torch.no_grad()
     def forward_u8(self, crops_u8):

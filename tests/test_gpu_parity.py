@@ -255,3 +255,25 @@ def test_forward_u8_equals_host_conversions_around_fp32_call(net):
         net.forward_u8(crops.cuda().float())                                            # wrong dtype
     with pytest.raises(RuntimeError):
         net.forward_u8(crops)                                                           # CPU tensor: no fallback
+
+
+def test_concurrent_clip_replicas_equal_clip_by_clip(keep_mod, state_dict):
+    """a batch of clips spread over two engine replicas on two streams returns the bits of the
+    clip-by-clip loop (clips are independent, keep_processor.py:263-270)."""
+    from oracle import weights
+    kn = keep_mod.keep_net
+    flags = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3 | kn.FLAG_CUDA_GRAPH
+    one = keep_mod.KeepNetB200(flags=flags)
+    one.load_state_dict(state_dict, strict=True)
+    one.eval().to("cuda")
+    two = keep_mod.KeepNetB200(flags=flags, concurrent_clips=2)
+    two.load_state_dict(state_dict, strict=True)
+    two.eval().to("cuda")
+    x = torch.cat([weights.make_clip(2, seed=31 + i, coherent=True) for i in range(3)], 0).cuda()
+    want = torch.cat([one(x[i:i + 1].contiguous(), need_upscale=False) for i in range(3)], 0)
+    for _ in range(3):   # eager call, capture call, replay
+        got = two(x, need_upscale=False)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+    two.to("cpu")        # offload frees every replica
+    assert two._engine is None and not two._replicas
