@@ -8,7 +8,7 @@
 //   warp  4     MMA issuer    one thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and tcgen05.commit
 //   warp  8     weight loader one thread streams pre-packed fp16 weight panels with 1-D TMA (cp.async.bulk), or
 //                             parks the layer's whole panel set in shared memory once when it fits
-//   15 warps    A producers   (warps >= 5 off scheduler 0) coalesced NHWC loads of the (16+2)x(8+2) input halo,
+//   16 warps    A producers   (two groups of 8 on alternate stages) coalesced NHWC loads of the (16+2)x(8+2) input halo,
 //                             GroupNorm/InstanceNorm apply + swish/ReLU in registers, fp16 (hi, lo) split,
 //                             st.shared into the UMMA SWIZZLE_128B K-major layout
 //
@@ -38,8 +38,9 @@ namespace {
 // MMAs themselves take (measured: 88-105 clk per N=64 MMA in the kernel vs 55-64 in isolation, tools/ubench/umma_rate.cu).
 // So sub-partition 0 holds only the MMA issuer, the weight loader and one epilogue warp; the 15 producer warps live on
 // sub-partitions 1-3 next to the other three epilogue warps (tcgen05.ld ties epilogue warp w to TMEM lanes 32*(w%4)...).
-constexpr int kThreads = 768;                          // 24 warps; warps 12, 16, 20 have no role
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 8, kProdThreads = 480;   // producers: warps >= 5 with warp % 4 != 0
+constexpr int kThreads = 704;                          // 22 warps
+constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 8;
+constexpr int kProdThreads = 512;                      // producers: the 16 warps >= 5 other than the loader (8)
 constexpr int MAX_SA = 8, MAX_SB = 8;  // barrier slots (actual pipeline depths come from the launch arguments)
 // channels per A stage: 64 with fp16 operands (4 MMA K-steps of 16); 32 in the split-precision mode, whose 128-byte rows
 // hold [hi 32 ch | lo 32 ch] side by side (2 K-steps each), so a stage and a weight panel have the same geometry in both
@@ -161,8 +162,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int CBK = cb_of(PASSES);                   // channels per A stage / weight panel
     constexpr int UPP = CBK / 8;                         // 8-channel producer units per pixel
-    constexpr int PPI = kProdThreads / UPP;              // pixels per producer iteration
-    constexpr int MAXIT = (180 + PPI - 1) / PPI;         // halo units per producer thread and stage
+    // Producer groups: in the split-precision mode the 16 producer warps work as TWO groups of 8 that take alternate stages.
+    // A stage's critical path is load latency + convert + proxy fence (the fence -- MEMBAR.ALL.CTA -- also waits for any
+    // prefetched global load of the same thread, which is why register double-buffering inside one thread bought nothing);
+    // with two groups one stage's latency hides behind the other's conversion.
+    constexpr int NGROUPS = (PASSES == 3 && WIN == 1) ? 2 : 1;   // (3x3 layers: one group -- MAXIT 3 at 83 % fill and spills cost more than the overlap gives)
+    constexpr int GT = kProdThreads / NGROUPS;           // threads per group = arrivals per stage
+    constexpr int PPI = GT / UPP;                        // pixels per producer iteration
+    constexpr int NPIX = WIN == 3 ? 18 * 10 : (WIN == 2 ? 17 * 9 : 128);   // pixels per stage (halo tile, or the 128 of a 1x1)
+    constexpr int MAXIT = (NPIX + PPI - 1) / PPI;        // units per producer thread and stage
     constexpr int KSTEPS = CBK / 16;                     // MMA K-steps per operand tile
     constexpr int A_STAGE_BYTES = WIN == 1 ? 128 * 128 : A_SUB_BYTES;   // 1x1: 128 pixels, no halo
     const int SA = a.sa_stages, SB = a.sb_stages;
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 
     pdl_early_trigger();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < MAX_SA; ++s) { mbar_init(A_FULL(s), kProdThreads); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < MAX_SA; ++s) { mbar_init(A_FULL(s), GT); mbar_init(A_EMPTY(s), 1); }
         for (int s = 0; s < MAX_SB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(ACC_FULL(s), 1); mbar_init(ACC_EMPTY(s), kEpiWarps * 32); }
         fence_barrier_init();
@@ -238,12 +246,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         tx = t2 - ty * a.tiles_x;
     };
 
-    if (warp > 4 && (warp & 3) != 0) {
+    if (warp > 4 && warp != kLoadWarp) {
         // =========================== A producers ===========================
-        const int pt = (((warp >> 2) - 1) * 3 + (warp & 3) - 1) * 32 + lane;       // 0..479
+        const int pw = warp - (warp > kLoadWarp ? 6 : 5);                           // 0..15
+        const int grp = NGROUPS == 2 ? (pw & 1) : 0;                                // this warp's group
+        const int pt = (NGROUPS == 2 ? (pw >> 1) : pw) * 32 + lane;                 // thread index within the group
         const int pl = pt % UPP;                            // 8-channel plane of the stage handled by this thread
         const int Hl = a.h * a.up, Wl = a.w * a.up;
-        constexpr int npix = conv3 ? (16 + win - 1) * hcols : 128;
+        constexpr int npix = NPIX;
         const int cin = a.c0 + a.c1;
         const int ushift = a.up - 1;
         // halo units of this thread: pixel p = p_first + it*PPI -> (row, col) within the halo; tile independent, and so
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             const int row = conv3 ? hy[it] * HPITCH_PX + hx[it] : p;
             soff[it] = p < npix ? row * 128 + ((pl ^ (row & 7)) << 4) : -1;
         }
-        int stage = 0, phase = 0, trace_i = 0;
+        int stage = 0, phase = 0, trace_i = 0, seq = 0;
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
             int nt, img, ty, tx, ks;
             decode(w, 0, nt, img, ty, tx, ks);
@@ -287,6 +297,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             };
             if (!a.s2d) locate(0, 0);
             for (int cb = cb0; cb < cb1; ++cb) {
+                if (NGROUPS == 2 && ((seq++ & 1) != grp)) {   // the other group's stage: only keep the ring position in step
+                    if (++stage == SA) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 const int par = a.s2d ? cb / a.ncbr : 0;    // stride-2 mode: input parity (py, px) of this virtual block
                 if (a.s2d) locate(par >> 1, par & 1);
                 const int ch = (a.s2d ? (cb - par * a.ncbr) : cb) * CBK + pl * 8;   // first of this thread's 8 real channels
@@ -313,9 +327,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
                     sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
                 }
-                if (pt == 0) TC_TRACE(0, trace_i);
+                if (pt == 0 && grp == 0) TC_TRACE(0, trace_i);
                 mbar_wait(A_EMPTY(stage), phase ^ 1);
-                if (pt == 0) TC_TRACE(1, trace_i);
+                if (pt == 0 && grp == 0) TC_TRACE(1, trace_i);
                 uint8_t* dst = sA + stage * A_STAGE_BYTES;
 #pragma unroll
                 for (int it = 0; it < MAXIT; ++it) {
@@ -391,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 }
                 fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
                 mbar_arrive(A_FULL(stage));
-                if (pt == 0) { TC_TRACE(2, trace_i); ++trace_i; }
+                if (pt == 0 && grp == 0) { TC_TRACE(2, trace_i); ++trace_i; }
                 if (++stage == SA) { stage = 0; phase ^= 1; }
             }
         }

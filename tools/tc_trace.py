@@ -7,12 +7,15 @@ from test_gpu_ops import run_conv
 lib = keep_b200.keep_net.load_library()
 n, cin, h, w, cout = [int(v) for v in (sys.argv[1:6] if len(sys.argv) > 5 else (1, 64, 512, 512, 64))]
 mode = int(sys.argv[6]) if len(sys.argv) > 6 else 1
-x = torch.randn((n, cin, h, w), device="cuda"); wt = torch.randn((cout, cin, 3, 3), device="cuda") / math.sqrt(cin * 9); b = torch.randn(cout, device="cuda")
+ksz = int(sys.argv[7]) if len(sys.argv) > 7 else 3          # 3: 3x3 conv, 1: 1x1 / linear
+act = sys.argv[8] if len(sys.argv) > 8 else "swish"
+pads = (1, 1, 1, 1) if ksz == 3 else (0, 0, 0, 0)
+x = torch.randn((n, cin, h, w), device="cuda"); wt = torch.randn((cout, cin, ksz, ksz), device="cuda") / math.sqrt(cin * ksz * ksz); b = torch.randn(cout, device="cuda")
 pre = (torch.ones((n, cin), device="cuda"), torch.zeros((n, cin), device="cuda"))
-run_conv(lib, x, wt, b, 1, (1, 1, 1, 1), 1, pre, "swish", "none", None, use_tc=mode)
+run_conv(lib, x, wt, b, 1, pads, 1, pre if act != "none" else None, act, "none", None, use_tc=mode)
 buf = torch.zeros(160, dtype=torch.int64, device="cuda")
 lib.keepop_tc_trace(ctypes.c_void_p(buf.data_ptr()))
-run_conv(lib, x, wt, b, 1, (1, 1, 1, 1), 1, pre, "swish", "none", None, use_tc=mode)
+run_conv(lib, x, wt, b, 1, pads, 1, pre if act != "none" else None, act, "none", None, use_tc=mode)
 lib.keepop_tc_trace(None)
 t = buf.cpu().reshape(10, 16); t0 = int(t[t > 0].min())
 names = ["prod:loads_issued", "prod:got_A_EMPTY", "prod:A_FULL_arrive", "mma:got_ACC_EMPTY", "mma:got_A_FULL", "mma:issued_all", "epi:got_ACC_FULL", "epi:done", "load:first_tap", "load:last_tap"]
