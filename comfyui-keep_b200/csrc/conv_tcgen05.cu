@@ -119,6 +119,18 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction.  The epilogue's
+// row-per-thread stores and the producers' 8-channel fp32 units are exactly 32 bytes wide and 32-byte aligned.
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, SWIZZLE_128B, K-major (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30)
@@ -314,9 +326,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 #pragma unroll
                 for (int it = 0; it < MAXIT; ++it) {
                     if (ch_ok && pixv[it] >= 0) {
-                        const uint4* g = reinterpret_cast<const uint4*>(src + ((size_t)pixv[it] * sc_ch + cc) * ESZ);
-                        raw[it][0] = g[0];
-                        if (!IN_F16) raw[it][1] = g[1];
+                        const uint8_t* g = src + ((size_t)pixv[it] * sc_ch + cc) * ESZ;
+                        if (IN_F16) raw[it][0] = *reinterpret_cast<const uint4*>(g);
+                        else ldg256(reinterpret_cast<const float*>(g), reinterpret_cast<float*>(&raw[it][0]));
                     }
                 }
                 float sc[8], sh[8];
@@ -628,8 +640,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 const bool has_res = live && !partial_out && a.res != nullptr;
                 if (has_res) {
                     if (a.res_dt == F32) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) rs[e] = ld4(reinterpret_cast<const float*>(a.res), off + 4 * e);
+                        ldg256(reinterpret_cast<const float*>(a.res) + off, reinterpret_cast<float*>(&rs[0]));
+                        ldg256(reinterpret_cast<const float*>(a.res) + off + 8, reinterpret_cast<float*>(&rs[2]));
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) rs[e] = ld4(reinterpret_cast<const __half*>(a.res), off + 4 * e);
@@ -644,9 +656,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
                 if (partial_out) {
-                    float4* o = reinterpret_cast<float4*>(a.partial + (size_t)ks * a.M * a.cout + off);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                    float* o = a.partial + (size_t)ks * a.M * a.cout + off;
+                    stg256(o, v);
+                    stg256(o + 8, v + 8);
 #ifdef KEEP_TC_EPI_TRACE
                     if (threadIdx.x == 0 && trace_e == 0) TC_TRACE(9, j >> 4);
 #endif
@@ -672,9 +684,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     for (int e = 0; e < 4; ++e) { v[4 * e] += rs[e].x; v[4 * e + 1] += rs[e].y; v[4 * e + 2] += rs[e].z; v[4 * e + 3] += rs[e].w; }
                 }
                 if (a.out_dt == F32) {
-                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                    float* o = reinterpret_cast<float*>(a.out) + off;
+                    stg256(o, v);
+                    stg256(o + 8, v + 8);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
