@@ -88,6 +88,18 @@ __device__ __forceinline__ void st4(__half* p, size_t i, float4 v) {
     *reinterpret_cast<uint2*>(p + i) = u;
 }
 
+// 256-bit global accesses (sm_100: LDG / STG.E.ENL2.256): one full 32-byte sector per lane and instruction; p 32-byte aligned
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
         case ACT_SWISH: return v / (1.0f + expf(-v));                       // x * sigmoid(x)

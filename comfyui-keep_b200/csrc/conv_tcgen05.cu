@@ -119,18 +119,6 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction.  The epilogue's
-// row-per-thread stores and the producers' 8-channel fp32 units are exactly 32 bytes wide and 32-byte aligned.
-__device__ __forceinline__ void stg256(float* p, const float* v) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void ldg256(const float* p, float* v) {
-    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, SWIZZLE_128B, K-major (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30)
