@@ -291,13 +291,13 @@ def main():
         shapes[k][0] += 1; shapes[k][1] += float(r["ms"]); shapes[k][2] += float(r["gflop"])
     os.unlink(dump)
     dom_k, dom_v = max(shapes.items(), key=lambda kv: kv[1][1])
-    ncu_path = os.path.join(ROOT, "profiles", "r1_ncu_conv_tc3_v10_512x512_64_64.json")
+    ncu_path = os.path.join(ROOT, "profiles", "r1_ncu_conv_tc3_v19_512x512_64_64.json")
     traffic, traffic_note = None, None
     if os.path.exists(ncu_path):
         l0 = json.load(open(ncu_path))["launches"][0]
         traffic = (float(l0["dram__bytes_read.sum"].split()[0]) + float(l0["dram__bytes_write.sum"].split()[0])) * 1e6
         traffic_note = ("dram read+write bytes of ONE conv_tc_kernel<3,false> launch at M=524288 K=576 N=64 (two 512x512 frames, 64->64 3x3; "
-                        "algorithmic 268.6 MB) from profiles/r1_ncu_conv_tc3_v10_512x512_64_64.json")
+                        "algorithmic 268.6 MB) from profiles/r1_ncu_conv_tc3_v19_512x512_64_64.json")
     fam = "tcgen05" if prof["tcgen05"]["gflop"] > prof["cuda_core"]["gflop"] else "cuda_core"
     pf = prof[fam]
     achieved = pf["gflop"] / max(pf["ms"], 1e-9)  # GFLOP / ms == TFLOP/s
