@@ -224,6 +224,13 @@ ConvW Engine::convw(const std::string& prefix) const {
     return c;
 }
 
+// fusion points: feature size -> channels (keep_arch.py:940-947), encoder block whose output is tapped (:950-951) and
+// generator block after which CFT / CFA run (:953-954)
+static const int kFuseSize[6] = {16, 32, 64, 128, 256, 512};
+static const int kFuseCh[6] = {512, 256, 256, 128, 128, 64};
+static const int kFuseEnc[6] = {18, 14, 11, 8, 5, 2};
+static const int kFuseGen[6] = {6, 9, 12, 15, 18, 21};
+
 // =============================================================================================
 // construction
 // =============================================================================================
@@ -254,8 +261,28 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
     const char* must[] = {"position_emb", "quantize.embedding.weight", "feat_emb.weight", "idx_pred_layer.1.weight",
                           "encoder.blocks.0.weight", "hq_encoder.blocks.24.weight", "generator.blocks.24.weight",
                           "flownet.model.backbone.conv1.weight", "kalman_filter.kalman_gain_calculator.3.weight",
-                          "cft.16.scale.0.weight", "cfa.32.attn.to_q.weight", "ft_layers.8.linear2.weight"};
+                          "cfa.16.attn.to_q.weight", "cfa.32.attn.to_q.weight", "ft_layers.8.linear2.weight"};
     for (const char* k : must) KEEP_CHECK(has(k), "state dict is missing '%s'", k);
+    // fusion points are read off the tensor names, like the reference builds cft / cfa from cft_list / cfa_list
+    // (keep_arch.py:957-967): a size is fused iff its block is in the state dict, and then the block must be complete
+    int n_cft = 0;
+    for (int i = 0; i < 6; ++i) {
+        const std::string sz = std::to_string(kFuseSize[i]);
+        cft_on_[i] = has("cft." + sz + ".scale.0.weight") || has("cft." + sz + ".encode_enc.conv1.weight");
+        cfa_on_[i] = has("cfa." + sz + ".attn.to_q.weight");
+        if (cft_on_[i]) {
+            ++n_cft;
+            for (const char* k : {".encode_enc.norm1.weight", ".encode_enc.conv1.weight", ".encode_enc.norm2.weight",
+                                  ".encode_enc.conv2.weight", ".encode_enc.conv_out.weight", ".scale.0.weight", ".scale.2.weight",
+                                  ".shift.0.weight", ".shift.2.weight"})
+                KEEP_CHECK(has("cft." + sz + k), "state dict is missing 'cft.%s%s'", sz.c_str(), k);
+            const DevArr& w = W_.at("cft." + sz + ".scale.0.weight");
+            KEEP_CHECK(w.d[0] == kFuseCh[i] && w.d[1] == kFuseCh[i], "cft.%s.scale.0.weight: expected %d channels, got (%d, %d)",
+                       sz.c_str(), kFuseCh[i], w.d[0], w.d[1]);
+        }
+    }
+    KEEP_CHECK(n_cft > 0, "state dict has no 'cft.<size>.*' block (KEEP fuses at 16/32/64, Asian at 32/64/128/256)");
+    KEEP_CHECK(!cfa_on_[2] && !cfa_on_[3] && !cfa_on_[4] && !cfa_on_[5], "cfa blocks beyond 16/32 are not part of either reference config");
 
     // GMFlow shifted-window region ids (gmflow/transformer.py:19-43) for a 64x64 map, 2x2 windows, shift 16
     if (!dry_only_) {
@@ -1049,7 +1076,7 @@ Tensor Engine::cfa(const Tensor& cur, const Tensor& prev, const std::string& p) 
 }
 
 // Generator programme with CFT / CFA hooks (keep_arch.py:1101-1125)
-Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[3], Tensor cfa_prev[2]) {
+Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[6], Tensor cfa_prev[6]) {
     Tensor x = quant;
     bool own = false;
     Aff pend;
@@ -1083,24 +1110,26 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[3], Tensor 
         if (own) tfree(x);
         x = y;
         own = true;
-        const int ti = j == 6 ? 0 : (j == 9 ? 1 : (j == 12 ? 2 : -1));   // sizes 16 / 32 / 64
-        if (ti >= 0) {
-            static const char* sz[3] = {"16", "32", "64"};
+        int ti = -1;
+        for (int k = 0; k < 6; ++k) if (kFuseGen[k] == j) ti = k;
+        if (ti < 0) continue;
+        const std::string sz = std::to_string(kFuseSize[ti]);
+        if (cft_on_[ti]) {   // keep_arch.py:1104-1108
             Tensor enc = taps[ti];   // (T, s, s, C): slice frame
             enc.n = 1;
             enc.p = (char*)enc.p + (size_t)frame * enc.h * enc.w * enc.c * dtype_size(enc.dt);
-            Tensor z = cft(enc, x, std::string("cft.") + sz[ti]);
+            Tensor z = cft(enc, x, "cft." + sz);
             tfree(x);
             x = z;
-            if (ti < 2) {  // CFA at 16 and 32
-                if (frame > 0) {
-                    Tensor z2 = cfa(x, cfa_prev[ti], std::string("cfa.") + sz[ti]);
-                    tfree(x);
-                    x = z2;
-                }
-                if (!ar_->dry())
-                    CUDA_CHECK(cudaMemcpyAsync(cfa_prev[ti].p, x.p, x.bytes(), cudaMemcpyDeviceToDevice, s_));
+        }
+        if (cfa_on_[ti]) {   // keep_arch.py:1110-1121: the previous frame's *fused* feature is the key / value source
+            if (frame > 0) {
+                Tensor z2 = cfa(x, cfa_prev[ti], "cfa." + sz);
+                tfree(x);
+                x = z2;
             }
+            if (!ar_->dry())
+                CUDA_CHECK(cudaMemcpyAsync(cfa_prev[ti].p, x.p, x.bytes(), cudaMemcpyDeviceToDevice, s_));
         }
     }
     pass_override_ = 0;
@@ -1115,9 +1144,12 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     const bool dry = ar_->dry();
     // ---- persistent per-clip tensors
     Tensor flows = talloc(T - 1, 512, 512, 2, F32);
-    Tensor taps[3] = {talloc(T, 16, 16, 512, adt_), talloc(T, 32, 32, 256, adt_), talloc(T, 64, 64, 256, adt_)};
+    Tensor taps[6], cfa_prev[6];
+    for (int k = 0; k < 6; ++k)
+        if (cft_on_[k]) taps[k] = talloc(T, kFuseSize[k], kFuseSize[k], kFuseCh[k], adt_);
     Tensor z_codes = talloc(T, 16, 16, 256, F32);
-    Tensor cfa_prev[2] = {talloc(1, 16, 16, 512, F32), talloc(1, 32, 32, 256, F32)};
+    for (int k = 0; k < 6; ++k)
+        if (cfa_on_[k]) cfa_prev[k] = talloc(1, kFuseSize[k], kFuseSize[k], kFuseCh[k], F32);
 
     // ---- optical flow (batched over pairs)
     auto ff = forced_.find("flows");
@@ -1173,7 +1205,8 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
         Tensor img = talloc(nf, 512, 512, 3, adt_);
         if (!dry) { nchw_to_nhwc(x_dev + (size_t)f0 * 3 * HW, img.p, img.dt, nf, 3, 512, 512, 0, s_); launches_ += 1; }
         auto tap = [&](int i, const Tensor& t) {
-            const int ti = i == 18 ? 0 : (i == 14 ? 1 : (i == 11 ? 2 : -1));
+            int ti = -1;
+            for (int k = 0; k < 6; ++k) if (kFuseEnc[k] == i && cft_on_[k]) ti = k;
             if (ti < 0 || dry) return;
             const size_t per = (size_t)t.h * t.w * t.c * dtype_size(t.dt);
             CUDA_CHECK(cudaMemcpyAsync((char*)taps[ti].p + (size_t)f0 * per, t.p, per * nf, cudaMemcpyDeviceToDevice, s_));
@@ -1254,9 +1287,9 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(T - 2) / flow_chunk()], 0));   // join the side branch
     if (prev_out.p) tfree(prev_out);
     tfree(gains);
-    tfree(cfa_prev[0]); tfree(cfa_prev[1]);
+    for (int k = 5; k >= 0; --k) if (cfa_on_[k]) tfree(cfa_prev[k]);
     tfree(z_codes);
-    for (int i = 0; i < 3; ++i) tfree(taps[i]);
+    for (int k = 0; k < 6; ++k) if (cft_on_[k]) tfree(taps[k]);
     tfree(flows);
 }
 

@@ -96,11 +96,15 @@ class Engine {
     Tensor code_transformer(const Tensor& z_hat, int frame);
     Tensor cft(const Tensor& enc, const Tensor& dec, const std::string& p);
     Tensor cfa(const Tensor& cur, const Tensor& prev, const std::string& p);
-    Tensor generator(const Tensor& quant, int frame, Tensor taps[3], Tensor cfa_prev[2]);
+    Tensor generator(const Tensor& quant, int frame, Tensor taps[6], Tensor cfa_prev[6]);
     void pack_weights(const keep_weight_desc* w, int n_w);
     void add_arr(const std::string& key, const std::vector<float>& host, int d0, int d1 = 0, int d2 = 0, int d3 = 0);
 
     int device_ = 0, flags_ = 0;
+    // feature sizes (16, 32, 64, 128, 256, 512) that own cft.<s>.* / cfa.<s>.* tensors: 'KEEP' fuses CFT at 16/32/64,
+    // 'Asian' at 32/64/128/256 (modules/utils.py:46,62); CFA at 16/32 in both
+    bool cft_on_[6] = {false, false, false, false, false, false};
+    bool cfa_on_[6] = {false, false, false, false, false, false};
     bool dry_only_ = false;  // KEEP_FLAG_PLAN_ONLY: host-side planning only (workspace sizing, key checks), no device
     int adt_ = F32;  // feature-map storage dtype
     std::unordered_map<std::string, DevArr> W_;

@@ -20,11 +20,15 @@ import torch.nn as nn
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-KEEP_GENERAL_CFG = dict(  # modules/utils.py:42-57 (+ defaults :76-90): the config this engine implements
+KEEP_GENERAL_CFG = dict(  # modules/utils.py:42-57 (+ defaults :76-90): the 'KEEP' config
     img_size=512, emb_dim=256, dim_embd=512, n_head=8, n_layers=9, codebook_size=1024,
     cft_list=['16', '32', '64'], kalman_attn_head_dim=48, num_uncertainty_layers=3,
     cfa_list=['16', '32'], cfa_nhead=4, cfa_dim=256, cond=1, nf=64, ch_mult=[1, 2, 2, 4, 4, 8],
     attn_resolutions=[16], res_blocks=2, quantizer_type='nearest', latent_size=256, cross_residual=True)
+# modules/utils.py:58-73: the 'Asian' config differs only in where the encoder features are fused into the generator
+# (CFT after the 32^2 .. 256^2 levels instead of 16^2 .. 64^2) and in `temp_reg_list` (training-only bookkeeping).
+KEEP_ASIAN_CFG = dict(KEEP_GENERAL_CFG, cft_list=['32', '64', '128', '256'])
+_SHAPE_TABLES = {"KEEP": "keep_state_shapes.json", "Asian": "keep_state_shapes_asian.json"}
 
 FLAG_FP16_FEATURES = 1
 FLAG_TCGEN05 = 2
@@ -91,9 +95,22 @@ def _check(lib, rc, what):
         raise RuntimeError("keep_b200: %s failed: %s" % (what, lib.keep_last_error().decode("utf-8", "replace")))
 
 
-def expected_shapes():
-    with open(os.path.join(_HERE, "keep_state_shapes.json")) as f:
+def expected_shapes(config="KEEP"):
+    with open(os.path.join(_HERE, _SHAPE_TABLES[config])) as f:
         return json.load(f)
+
+
+def config_name(cfg):
+    """'KEEP' or 'Asian' for a reference architecture dict (KEEP_MODEL_CONFIGS[...]['architecture'] merged with the
+    defaults, modules/utils.py:42-90); anything else is rejected -- the engine implements these two programmes only."""
+    cft = [str(s) for s in cfg.get("cft_list", KEEP_GENERAL_CFG["cft_list"])]
+    name = "Asian" if cft == KEEP_ASIAN_CFG["cft_list"] else "KEEP"
+    want = KEEP_ASIAN_CFG if name == "Asian" else KEEP_GENERAL_CFG
+    for k, v in cfg.items():
+        if k in want and want[k] != (cft if k == "cft_list" else v):
+            raise ValueError("KeepNetB200 implements the reference's 'KEEP' and 'Asian' configs only: %s=%r != %r"
+                             % (k, v, want[k]))
+    return name
 
 
 class KeepNetB200(nn.Module):
@@ -108,12 +125,9 @@ class KeepNetB200(nn.Module):
         self._nrep = max(1, int(concurrent_clips))
         self._replicas = []           # extra engines (keep_handle) beyond the primary one, created on first use
         self._rep_streams = []
-        for k, v in cfg.items():
-            if k in KEEP_GENERAL_CFG and KEEP_GENERAL_CFG[k] != v:
-                raise ValueError("KeepNetB200 implements the 'KEEP' (general) config only: %s=%r != %r"
-                                 % (k, v, KEEP_GENERAL_CFG[k]))
+        self.config = config_name(cfg)   # 'KEEP' | 'Asian'; the engine reads the fusion points off the tensor names
         self._flags = int(flags)
-        self._shapes = expected_shapes()
+        self._shapes = expected_shapes(self.config)
         self._weights = None          # CPU fp32 tensors, reference key names
         self._engine = None           # keep_handle (c_void_p)
         self._device = torch.device("cpu")
@@ -350,7 +364,7 @@ def install_into_model_pack(model_pack, flags=0):
     `model_pack` is the reference's KEEPModelPack (modules/keep_model_loader.py:12-61); everything else in
     the pack (face helper, detector, parser) is left untouched."""
     ref = model_pack.keep_net
-    net = KeepNetB200(flags=flags)
+    net = KeepNetB200(flags=flags, cft_list=list(getattr(ref, "cft_list", KEEP_GENERAL_CFG["cft_list"])))
     net.load_state_dict(ref.state_dict(), strict=True)
     net.eval()
     model_pack.keep_net = net

@@ -1,9 +1,10 @@
-"""Seeded synthetic weights and clips for the KEEP (general) network (benchmarks and tests; not the oracle).
+"""Seeded synthetic weights and clips for the KEEP network, 'KEEP' general or 'Asian' config (benchmarks and tests; not the oracle).
 
 No checkpoint is available offline (the reference downloads `KEEP-b76feb75.pth` at run time,
 modules/utils.py:55), so parity and benchmarks use a seeded synthetic state dict with the
 reference's exact key set and shapes (`keep_state_shapes.json`, dumped from the reference's own
-`KEEP(**cfg).state_dict()` — 896 tensors, 158.49 M parameters).
+`KEEP(**cfg).state_dict()` by oracle/dump_shapes.py — general: 896 tensors, 158.49 M parameters; `keep_state_shapes_asian.json`:
+914 tensors, 143.57 M: no `cft.16`, `cft.128` and `cft.256` added, modules/utils.py:58-73).
 
 The reference's default init makes several paths no-ops (CFT convs, CFA linears,
 `position_emb`, a ±1/1024 codebook), so this generator draws *every* tensor from a live
@@ -25,13 +26,16 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def load_shapes():
-    with open(os.path.join(_HERE, "keep_state_shapes.json")) as f:
+SHAPE_TABLES = {"KEEP": "keep_state_shapes.json", "Asian": "keep_state_shapes_asian.json"}
+
+
+def load_shapes(config="KEEP"):
+    with open(os.path.join(_HERE, SHAPE_TABLES[config])) as f:
         return json.load(f)  # insertion-ordered: reference state_dict order
 
 
-def make_state_dict(seed=0, dtype=torch.float32):
-    shapes = load_shapes()
+def make_state_dict(seed=0, dtype=torch.float32, config="KEEP"):
+    shapes = load_shapes(config)
     sd = {}
     for idx, (key, shape) in enumerate(shapes.items()):
         g = torch.Generator(device="cpu")

@@ -422,9 +422,16 @@ def gmflow_forward(img0, img1, w):
 # full forward
 # ----------------------------------------------------------------------------------------------
 
-ENC_TAPS = {18: "16", 14: "32", 11: "64"}          # keep_arch.py:950-951 for cft_list 16/32/64
-GEN_CFT = {6: "16", 9: "32", 12: "64"}             # keep_arch.py:953-954
-GEN_CFA = {6: "16", 9: "32"}
+FUSE_ENCODER_BLOCK = {"512": 2, "256": 5, "128": 8, "64": 11, "32": 14, "16": 18}    # keep_arch.py:950-951
+FUSE_GENERATOR_BLOCK = {"16": 6, "32": 9, "64": 12, "128": 15, "256": 18, "512": 21}  # keep_arch.py:953-954
+
+
+def fusion_lists(sd):
+    """(cft_list, cfa_list) of the checkpoint: the feature sizes that own `cft.<s>.*` / `cfa.<s>.*` tensors.
+    'KEEP' general: cft 16/32/64 (modules/utils.py:46); 'Asian': cft 32/64/128/256 (:62); cfa 16/32 in both."""
+    cft = [s for s in FUSE_GENERATOR_BLOCK if "cft.%s.scale.0.weight" % s in sd]
+    cfa = [s for s in FUSE_GENERATOR_BLOCK if "cfa.%s.attn.to_q.weight" % s in sd]
+    return cft, cfa
 
 
 @torch.no_grad()
@@ -440,6 +447,10 @@ def keep_forward(sd, x, force_codes=None, force_flows=None, force_prev=None, cap
     W = _W(sd)
     b, T, c, H, Wd = x.shape
     cap = {}
+    cft_list, cfa_list = fusion_lists(sd)
+    ENC_TAPS = {FUSE_ENCODER_BLOCK[s]: s for s in cft_list}       # keep_arch.py:1030-1037
+    GEN_CFT = {FUSE_GENERATOR_BLOCK[s]: s for s in cft_list}      # keep_arch.py:1053-1054
+    GEN_CFA = {FUSE_GENERATOR_BLOCK[s]: s for s in cfa_list}      # keep_arch.py:1056-1057
     if force_flows is None:
         flows = gmflow_forward(x[:, 1:].reshape(-1, c, H, Wd), x[:, :-1].reshape(-1, c, H, Wd),
                                W.sub("flownet.model")).reshape(b, T - 1, 2, H, Wd)

@@ -56,13 +56,30 @@ def psnr(a, b):
     return 999.0 if mse == 0 else 10 * np.log10(1.0 / mse)
 
 
+CASES = (  # fixture name, model config, T, coherent clip, clip seed
+    ("T3_coherent", "KEEP", 3, True, 1234),
+    ("T2_noise", "KEEP", 2, False, 1234),
+    ("asian_T2_coherent", "Asian", 2, True, 1234),   # CFT at 32/64/128/256, none at 16
+)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
-    sd = weights.make_state_dict(seed=0)
-    net = ref_loader.load_reference_keep(sd)
+    only = set(sys.argv[1:])
     report = {"torch": torch.__version__, "weights_seed": 0, "cases": {}}
-    for name, T, coherent, seed in (("T3_coherent", 3, True, 1234), ("T2_noise", 2, False, 1234)):
+    rp = os.path.join(GOLD, "pin_report.json")
+    if only and os.path.exists(rp):
+        with open(rp) as f:
+            report = json.load(f)
+    nets = {}
+    for name, config, T, coherent, seed in CASES:
+        if only and name not in only:
+            continue
+        if config not in nets:
+            sd_c = weights.make_state_dict(seed=0, config=config)
+            nets[config] = (sd_c, ref_loader.load_reference_keep(sd_c, config=config))
+        sd, net = nets[config]
         x = weights.make_clip(T, seed=seed, coherent=coherent)
         t0 = time.time()
         ref_out, ref_cap = run_reference(net, x)
@@ -71,13 +88,14 @@ def main():
         ora_out, ora_cap = keep_oracle.keep_forward(sd, x, capture=True)
         t_ora = time.time() - t0
         case = {
-            "T": T, "coherent": coherent, "clip_seed": seed, "ref_seconds": t_ref, "oracle_seconds": t_ora,
+            "config": config, "T": T, "coherent": coherent, "clip_seed": seed, "ref_seconds": t_ref, "oracle_seconds": t_ora,
             "oracle_vs_ref_maxabs": {
                 "flows": maxabs(ora_cap["flows"].reshape(-1), ref_cap["flows"].reshape(-1)),
                 "z_codes": maxabs(ora_cap["z_codes"].reshape(-1), ref_cap["z_codes"].reshape(-1)),
                 "gains": maxabs(ora_cap["gains"].reshape(-1), ref_cap["gains"].reshape(-1)),
                 "logits": maxabs(ora_cap["logits"], ref_cap["logits"]),
                 "out": maxabs(ora_out, ref_out),
+                "out_clamped": maxabs(ora_out.clamp(-1, 1), ref_out.clamp(-1, 1)),   # what tensor2img sees (img_util.py:56)
             },
             "oracle_vs_ref_code_agreement": float((ora_cap["codes"] == ref_cap["codes"]).float().mean()),
             "oracle_vs_ref_psnr_db": psnr(ora_out, ref_out),
@@ -118,7 +136,7 @@ def main():
             codes=ref_cap["codes"].numpy().astype(np.int16),
             logit_top2=top2.numpy().astype(np.float32),
         )
-    with open(os.path.join(GOLD, "pin_report.json"), "w") as f:
+    with open(rp, "w") as f:
         json.dump(report, f, indent=1)
 
 

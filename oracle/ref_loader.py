@@ -33,6 +33,11 @@ KEEP_GENERAL_CFG = dict(  # modules/utils.py:42-57 merged with defaults :76-90
     mask_ratio=0.)
 
 
+KEEP_ASIAN_CFG = dict(KEEP_GENERAL_CFG, cft_list=['32', '64', '128', '256'], temp_reg_list=[])  # modules/utils.py:58-73
+
+CONFIGS = {"KEEP": KEEP_GENERAL_CFG, "Asian": KEEP_ASIAN_CFG}
+
+
 def available():
     return os.path.isdir(os.path.join(REF_DEPS, "wm_basicsr"))
 
@@ -76,13 +81,13 @@ def _install_shims():
         sys.path.insert(0, REF_DEPS)
 
 
-def load_reference_keep(state_dict=None):
-    """Build reference KEEP (general config), optionally load a state dict (strict)."""
+def load_reference_keep(state_dict=None, config="KEEP"):
+    """Build reference KEEP ('KEEP' general or 'Asian' config), optionally load a state dict (strict)."""
     if not available():
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
     _install_shims()
     from wm_basicsr.archs.keep_arch import KEEP  # noqa
-    net = KEEP(**KEEP_GENERAL_CFG).eval()
+    net = KEEP(**CONFIGS[config]).eval()
     if state_dict is not None:
         net.load_state_dict(state_dict, strict=True)
     return net

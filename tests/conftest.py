@@ -28,3 +28,10 @@ def lib(keep_mod):
 def state_dict():
     from oracle import weights
     return weights.make_state_dict(seed=0)
+
+
+@pytest.fixture(scope="session")
+def state_dict_asian():
+    """Seeded synthetic weights with the 'Asian' config's key set (CFT at 32/64/128/256, modules/utils.py:58-73)."""
+    from oracle import weights
+    return weights.make_state_dict(seed=0, config="Asian")

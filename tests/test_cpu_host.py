@@ -16,7 +16,9 @@ def test_pin_report_says_oracle_matches_reference():
     rep = json.load(open(os.path.join(GOLD, "pin_report.json")))
     for name, case in rep["cases"].items():
         assert case["oracle_vs_ref_code_agreement"] == 1.0, name
-        assert case["oracle_vs_ref_maxabs"]["out"] < 1e-3, name
+        # unclamped outputs of the synthetic-weight nets reach |70| (Asian: CFT at 256^2); the pixel bar is on the clamped range
+        assert case["oracle_vs_ref_maxabs"]["out"] < 1e-3 * max(1.0, case["ref_out_absmax"] / 16), name
+        assert case["oracle_vs_ref_maxabs"].get("out_clamped", case["oracle_vs_ref_maxabs"]["out"]) < 1e-3, name
         assert case["oracle_vs_ref_maxabs"]["flows"] < 1e-3, name
         assert case["oracle_vs_ref_psnr_db"] > 90.0, name
 
@@ -101,3 +103,50 @@ def test_missing_key_is_rejected_by_the_c_side(keep_mod, lib, state_dict):
     del net._weights["quantize.embedding.weight"]
     with pytest.raises(RuntimeError, match="quantize.embedding.weight"):
         net._make_engine(flags=256)
+
+
+# ---- 'Asian' model config (modules/utils.py:58-73) ----------------------------------------------------
+
+def test_oracle_reproduces_reference_golden_asian_T2(state_dict_asian):
+    """Fixture produced by the REAL reference built with the 'Asian' config (CFT after the 32^2..256^2 generator levels)."""
+    from oracle import keep_oracle, weights
+    g = np.load(os.path.join(GOLD, "ref_asian_T2_coherent.npz"))
+    assert keep_oracle.fusion_lists(state_dict_asian) == (["32", "64", "128", "256"], ["16", "32"])
+    x = weights.make_clip(2, seed=1234, coherent=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    out, cap = keep_oracle.keep_forward(state_dict_asian, x, capture=True)
+    assert sorted(cap["enc_feat"]) == ["128", "256", "32", "64"]
+    assert np.array_equal(cap["codes"].numpy().astype(np.int16), g["codes"])
+    np.testing.assert_allclose(cap["z_codes"].reshape(g["z_codes"].shape).numpy(), g["z_codes"], atol=2e-4)
+    np.testing.assert_allclose(cap["gains"].reshape(g["gains"].shape).numpy(), g["gains"], atol=2e-5)
+    np.testing.assert_allclose(out[:, :, :, ::4, ::4].clamp(-1, 1).numpy(), np.clip(g["out_sub4"], -1, 1), atol=2e-3)
+
+
+def test_asian_config_host_mirror_and_plan_only_engine(keep_mod, lib, state_dict, state_dict_asian):
+    kn = keep_mod.keep_net
+    assert kn.config_name(dict(kn.KEEP_GENERAL_CFG)) == "KEEP"
+    assert kn.config_name(dict(kn.KEEP_ASIAN_CFG, temp_reg_list=[])) == "Asian"
+    with pytest.raises(ValueError):
+        kn.config_name(dict(cft_list=["16", "64"]))
+    assert len(state_dict_asian) == 914 and "cft.16.scale.0.weight" not in state_dict_asian
+    net = keep_mod.KeepNetB200(cft_list=["32", "64", "128", "256"])
+    assert net.config == "Asian"
+    with pytest.raises(RuntimeError, match="Missing key|Unexpected key"):
+        net.load_state_dict(state_dict, strict=True)          # general weights into the Asian programme
+    net.load_state_dict(state_dict_asian, strict=True)
+    h = net._make_engine(flags=256)  # KEEP_FLAG_PLAN_ONLY: dry run of the Asian programme (taps at 32..256, CFA without CFT at 16)
+    gen = keep_mod.KeepNetB200()
+    gen.load_state_dict(state_dict, strict=True)
+    hg = gen._make_engine(flags=256)
+    wa, wg = lib.keep_workspace_bytes(h, 1, 20), lib.keep_workspace_bytes(hg, 1, 20)
+    # the Asian programme keeps (T,128,128,128) and (T,256,256,128) encoder taps resident: 0.84 GB more fp32 at T = 20
+    assert wa > wg and wa - wg > 20 * (128 * 128 * 128 + 256 * 256 * 128 - 16 * 16 * 512) * 4 * 0.9
+    assert wa < 12 << 30
+    net._drop_engine()
+    gen._drop_engine()
+    # an incomplete CFT block is rejected by the C side by name
+    bad = keep_mod.KeepNetB200(cft_list=["32", "64", "128", "256"])
+    bad.load_state_dict(state_dict_asian, strict=True)
+    del bad._weights["cft.256.shift.2.weight"]
+    with pytest.raises(RuntimeError, match="cft.256.shift.2.weight"):
+        bad._make_engine(flags=256)
