@@ -295,4 +295,13 @@ int keepop_argmax_gather(const float* logits, int tokens, int ncodes, const floa
     KEEP_API_END
 }
 
+int keepop_vq_nearest(const float* z, int tokens, int cdim, const float* codebook, int ncodes, int straight_through, int* idx,
+                      float* zq, float* dmin, void* stream) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(z && codebook && idx, "keepop_vq_nearest: null tensor");
+    vq_nearest(z, tokens, cdim, codebook, ncodes, straight_through, idx, zq, dmin, (cudaStream_t)stream);
+    return 0;
+    KEEP_API_END
+}
+
 }  // extern "C"

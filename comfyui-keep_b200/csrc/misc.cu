@@ -261,6 +261,102 @@ __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restr
     for (int ch = lane; ch < cdim; ch += 32) st1_any(quant, q_dt, (size_t)tok * cdim + ch, codebook[(size_t)use * cdim + ch]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// VectorQuantizer.forward (vqgan_arch.py:37-76): nearest codebook entry per token,
+//   d[t][j] = (||z_t||^2 + ||e_j||^2) - 2 z_t . e_j ,  idx[t] = argmin_j d[t][j]  (ties -> lowest j),  z_q[t] = e[idx[t]]
+// One CTA = 16 tokens (8 warps x 2), staged once in shared memory.  The codebook streams through a 32-code x 128-dim
+// shared tile (row pitch 132 floats: conflict-free 128-bit reads, one code per lane); a lane keeps the running dot
+// products of its code with the warp's two tokens plus ||e||^2 in registers, so no shuffle is needed until the final
+// warp-wide argmin (5 xor-shuffles of (distance, index) per token).  z is read once, the 1 MB codebook stays in L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int VQ_TOK = 16, VQ_DC = 128, VQ_LD = VQ_DC + 4;
+__global__ void __launch_bounds__(256) vq_nearest_kernel(const float* __restrict__ z, int tokens, int cdim,
+                                                         const float* __restrict__ codebook, int ncodes, int straight_through,
+                                                         int* __restrict__ idx_out, float* __restrict__ zq,
+                                                         float* __restrict__ dmin_out) {
+    pdl_prologue();
+    __shared__ __align__(16) float tile[32 * VQ_LD];
+    extern __shared__ __align__(16) float vq_zs[];   // [VQ_TOK][cdim]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tok0 = blockIdx.x * VQ_TOK, c4n = cdim >> 2;
+    for (int i = tid; i < VQ_TOK * c4n; i += 256) {
+        const int t = i / c4n, tok = tok0 + t;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tok < tokens) v = __ldg(reinterpret_cast<const float4*>(z) + (size_t)tok * c4n + (i - t * c4n));
+        reinterpret_cast<float4*>(vq_zs)[i] = v;
+    }
+    __syncthreads();
+    const float* za = vq_zs + (size_t)(warp * 2) * cdim;
+    const float* zb = za + cdim;
+    float zz0 = 0.f, zz1 = 0.f;
+    for (int k = lane; k < cdim; k += 32) { zz0 = fmaf(za[k], za[k], zz0); zz1 = fmaf(zb[k], zb[k], zz1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        zz0 += __shfl_xor_sync(0xffffffffu, zz0, o);
+        zz1 += __shfl_xor_sync(0xffffffffu, zz1, o);
+    }
+    float best0 = INFINITY, best1 = INFINITY;
+    int bi0 = 0x7fffffff, bi1 = 0x7fffffff;
+    for (int c0 = 0; c0 < ncodes; c0 += 32) {
+        float dot0 = 0.f, dot1 = 0.f, ee = 0.f;
+        for (int d0 = 0; d0 < cdim; d0 += VQ_DC) {
+            __syncthreads();   // the previous tile has been consumed by every warp
+            for (int i = tid; i < 32 * (VQ_DC / 4); i += 256) {
+                const int r = i / (VQ_DC / 4), q = i - r * (VQ_DC / 4), code = c0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (code < ncodes) v = __ldg(reinterpret_cast<const float4*>(codebook + (size_t)code * cdim + d0) + q);
+                *reinterpret_cast<float4*>(tile + r * VQ_LD + q * 4) = v;
+            }
+            __syncthreads();
+            const float* row = tile + lane * VQ_LD;
+#pragma unroll 8
+            for (int k = 0; k < VQ_DC; k += 4) {
+                const float4 e = *reinterpret_cast<const float4*>(row + k);
+                const float4 a = *reinterpret_cast<const float4*>(za + d0 + k);
+                const float4 b = *reinterpret_cast<const float4*>(zb + d0 + k);
+                dot0 = fmaf(e.x, a.x, dot0); dot0 = fmaf(e.y, a.y, dot0); dot0 = fmaf(e.z, a.z, dot0); dot0 = fmaf(e.w, a.w, dot0);
+                dot1 = fmaf(e.x, b.x, dot1); dot1 = fmaf(e.y, b.y, dot1); dot1 = fmaf(e.z, b.z, dot1); dot1 = fmaf(e.w, b.w, dot1);
+                ee = fmaf(e.x, e.x, ee); ee = fmaf(e.y, e.y, ee); ee = fmaf(e.z, e.z, ee); ee = fmaf(e.w, e.w, ee);
+            }
+        }
+        const int code = c0 + lane;
+        if (code < ncodes) {   // codes arrive in increasing order: strict < keeps the lowest index on ties
+            const float d0v = __fsub_rn(__fadd_rn(zz0, ee), __fmul_rn(2.f, dot0));
+            const float d1v = __fsub_rn(__fadd_rn(zz1, ee), __fmul_rn(2.f, dot1));
+            if (d0v < best0) { best0 = d0v; bi0 = code; }
+            if (d1v < best1) { best1 = d1v; bi1 = code; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob0 = __shfl_xor_sync(0xffffffffu, best0, o), ob1 = __shfl_xor_sync(0xffffffffu, best1, o);
+        const int oi0 = __shfl_xor_sync(0xffffffffu, bi0, o), oi1 = __shfl_xor_sync(0xffffffffu, bi1, o);
+        if (ob0 < best0 || (ob0 == best0 && oi0 < bi0)) { best0 = ob0; bi0 = oi0; }
+        if (ob1 < best1 || (ob1 == best1 && oi1 < bi1)) { best1 = ob1; bi1 = oi1; }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int tok = tok0 + warp * 2 + u;
+        if (tok >= tokens) continue;
+        const int bi = u ? bi1 : bi0;
+        if (lane == 0) {
+            idx_out[tok] = bi;
+            if (dmin_out) dmin_out[tok] = u ? best1 : best0;
+        }
+        if (!zq || bi < 0 || bi >= ncodes) continue;   // all-NaN rows leave no valid index: nothing to gather
+        const float* zt = u ? zb : za;
+        for (int q = lane; q < c4n; q += 32) {
+            float4 e = __ldg(reinterpret_cast<const float4*>(codebook + (size_t)bi * cdim) + q);
+            if (straight_through) {   // forward value of z + (z_q - z).detach()   (vqgan_arch.py:61), same two roundings
+                const float4 a = *reinterpret_cast<const float4*>(zt + q * 4);
+                e.x = __fadd_rn(a.x, __fsub_rn(e.x, a.x)); e.y = __fadd_rn(a.y, __fsub_rn(e.y, a.y));
+                e.z = __fadd_rn(a.z, __fsub_rn(e.z, a.z)); e.w = __fadd_rn(a.w, __fsub_rn(e.w, a.w));
+            }
+            reinterpret_cast<float4*>(zq + (size_t)tok * cdim)[q] = e;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) sparse_causal_gather_kernel(const float* __restrict__ kv, float* __restrict__ out,
                                                                    int T, int L, int c4, size_t total4) {
     pdl_prologue();
@@ -507,6 +603,15 @@ void argmax_gather(const float* logits, int tokens, int ncodes, const float* cod
                    int* idx_out, void* quant, int q_dt, cudaStream_t s) {
     launch_k(argmax_gather_kernel, dim3(blocks_for((size_t)tokens, 8)), dim3(256), 0, s, logits, tokens, ncodes, codebook, cdim, forced_idx,
                                                                       idx_out, quant, q_dt);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void vq_nearest(const float* z, int tokens, int cdim, const float* codebook, int ncodes, int straight_through, int* idx_out,
+                float* zq, float* dmin_out, cudaStream_t s) {
+    KEEP_CHECK(tokens > 0 && ncodes > 0, "vq_nearest: empty input (tokens %d, codes %d)", tokens, ncodes);
+    KEEP_CHECK(cdim % VQ_DC == 0 && cdim <= 384, "vq_nearest: embedding dim %d (need a multiple of %d, <= 384)", cdim, VQ_DC);
+    launch_k(vq_nearest_kernel, dim3((unsigned)((tokens + VQ_TOK - 1) / VQ_TOK)), dim3(256), (size_t)VQ_TOK * cdim * sizeof(float), s,
+             z, tokens, cdim, codebook, ncodes, straight_through, idx_out, zq, dmin_out);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -99,6 +99,11 @@ void kalman_update(const float* z, const float* zp, const float* gain, float* ou
 // logits (tokens, ncodes) -> idx (tokens) int32, quant (tokens, cdim) = codebook[idx]; forced idx optional
 void argmax_gather(const float* logits, int tokens, int ncodes, const float* codebook, int cdim,
                    const int* forced_idx, int* idx_out, void* quant, int q_dt, cudaStream_t s);
+// VectorQuantizer.forward (vqgan_arch.py:37-76): z (tokens, cdim) -> idx = argmin_j ||z - e_j||^2 (int32, ties -> lowest j),
+// zq (tokens, cdim) = e[idx] (straight_through: the forward value z + (e[idx] - z)), dmin (tokens) the winning distance;
+// zq / dmin optional
+void vq_nearest(const float* z, int tokens, int cdim, const float* codebook, int ncodes, int straight_through, int* idx_out,
+                float* zq, float* dmin_out, cudaStream_t s);
 // sparse-causal K/V gather: out[(b,f)][0:L] = kv[(b,0)], out[(b,f)][L:2L] = kv[(b,max(f-1,0))]  keep_arch.py:704-716
 void sparse_causal_gather(const float* kv, float* out, int b, int T, int L, int c, cudaStream_t s);
 

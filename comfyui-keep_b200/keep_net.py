@@ -86,6 +86,7 @@ def load_library():
     lib.keepop_convex_upsample8.argtypes = [vp, vp, vp, ci, ci, ci, vp]
     lib.keepop_window_sine_pos.argtypes = [vp, ci, ci, ci, ci, ci, vp]
     lib.keepop_argmax_gather.argtypes = [vp, ci, ci, vp, ci, vp, vp, vp]
+    lib.keepop_vq_nearest.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp, vp, vp]
     _LIB = lib
     return lib
 
@@ -356,6 +357,39 @@ class KeepNetB200(nn.Module):
         if n < 0:
             raise RuntimeError("keep_b200: debug_read(%s): %s" % (what, lib.keep_last_error().decode()))
         return t
+
+
+@torch.no_grad()
+def vector_quantize(z, codebook, straight_through=True):
+    """Nearest-neighbour codebook lookup on the GPU = the inference values of `VectorQuantizer.forward`
+    (modules/deps/wm_basicsr/archs/vqgan_arch.py:37-76).
+
+    z (n, C, h, w) fp32 CUDA, codebook (K, C) = `quantize.embedding.weight` on the same device ->
+      z_q (n, C, h, w): codebook[idx] laid back out as NCHW -- with straight_through the forward value z + (z_q - z)
+                        the reference returns (:61), bit for bit;
+      min_encoding_indices (n*h*w, 1) int64, as in the reference's info dict (:47);
+      d_min (n*h*w,): the winning squared distance (its mean over tokens, divided by C, is the reference's MSE term).
+    One hand-written kernel (`vq_nearest_kernel`, csrc/misc.cu) through the C-ABI `keepop_vq_nearest`; no CPU fallback."""
+    if not (z.is_cuda and codebook.is_cuda and z.device == codebook.device):
+        raise RuntimeError("vector_quantize: z and codebook must live on the same CUDA device (no CPU fallback)")
+    if z.dim() != 4 or codebook.dim() != 2 or z.shape[1] != codebook.shape[1]:
+        raise RuntimeError("vector_quantize: expected z (n, C, h, w) and codebook (K, C), got %s and %s"
+                           % (tuple(z.shape), tuple(codebook.shape)))
+    lib = load_library()
+    n, C, h, w = (int(v) for v in z.shape)
+    zt = z.to(torch.float32).permute(0, 2, 3, 1).contiguous()           # token-major, as the reference flattens it (:39-40)
+    cb = codebook.to(torch.float32).contiguous()
+    tokens = n * h * w
+    idx = torch.empty((tokens,), dtype=torch.int32, device=z.device)
+    zq = torch.empty_like(zt)
+    dmin = torch.empty((tokens,), dtype=torch.float32, device=z.device)
+    if tokens:
+        stream = torch.cuda.current_stream(z.device).cuda_stream
+        with torch.cuda.device(z.device):
+            rc = lib.keepop_vq_nearest(zt.data_ptr(), tokens, C, cb.data_ptr(), int(cb.shape[0]), 1 if straight_through else 0,
+                                       idx.data_ptr(), zq.data_ptr(), dmin.data_ptr(), ctypes.c_void_p(stream))
+        _check(lib, rc, "keepop_vq_nearest")
+    return zq.permute(0, 3, 1, 2).contiguous(), idx.long().unsqueeze(1), dmin
 
 
 def install_into_model_pack(model_pack, flags=0):

@@ -84,3 +84,38 @@ def make_clip(T, seed=1234, coherent=True, b=1):
         f = f + 0.02 * torch.randn(f.shape, generator=g)
         frames.append(f.clamp(-1.0, 1.0))
     return torch.stack(frames, dim=1).contiguous()
+
+
+def make_latents(codebook, n=2, seed=99, hw=16):
+    """Synthetic encoder latents (n, C, hw, hw) for the nearest-neighbour quantiser: half of the tokens sit near a
+    codebook entry (entry + small noise, as a trained encoder's outputs do), a quarter are far from everything (pure noise,
+    near-tied distances), an eighth equal an entry exactly (distance ~ 0) and an eighth are midpoints of two entries
+    (a constructed near-tie).  Deterministic in (codebook, n, seed)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    K, C = codebook.shape
+    L = n * hw * hw
+    pick = torch.randint(0, K, (L,), generator=g)
+    pick2 = torch.randint(0, K, (L,), generator=g)
+    kind = torch.randint(0, 8, (L,), generator=g)
+    noise = torch.randn((L, C), generator=g)
+    z = codebook[pick] + 0.1 * codebook.std() * noise                      # kinds 0-3: near an entry
+    z = torch.where((kind >= 4)[:, None] & (kind < 6)[:, None], codebook.std() * noise, z)
+    z = torch.where((kind == 6)[:, None], codebook[pick], z)
+    z = torch.where((kind == 7)[:, None], 0.5 * (codebook[pick] + codebook[pick2]) + 1e-3 * noise, z)
+    return z.view(n, hw, hw, C).permute(0, 3, 1, 2).contiguous()
+
+
+def make_vq_case(codebook, n=2, seed=99):
+    """(codebook', z) for the quantiser tests: entry 700 is made an exact duplicate of entry 3 and the first eight tokens
+    sit on / next to that pair, so exact ties occur and must resolve to the lowest index (torch.argmin, vqgan_arch.py:47)."""
+    cb = codebook.clone()
+    cb[700] = cb[3]
+    z = make_latents(cb, n=n, seed=seed)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed + 1)
+    zt = z.permute(0, 2, 3, 1).contiguous()
+    flat = zt.view(-1, cb.shape[1])
+    flat[0:4] = cb[700]
+    flat[4:8] = cb[700] + 0.05 * cb.std() * torch.randn((4, cb.shape[1]), generator=g)
+    return cb, zt.permute(0, 3, 1, 2).contiguous()

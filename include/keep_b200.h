@@ -119,6 +119,15 @@ int keepop_convex_upsample8(const float* mask_dev, const float* flow_dev, float*
 int keepop_window_sine_pos(float* x_dev, int n, int h, int w, int c, int splits, void* stream);
 int keepop_argmax_gather(const float* logits_dev, int tokens, int ncodes, const float* codebook_dev, int cdim, int* idx_dev,
                          float* quant_dev, void* stream);
+/* Nearest-neighbour codebook lookup = VectorQuantizer.forward of the VQGAN (modules/deps/wm_basicsr/archs/vqgan_arch.py:37-76;
+ * SURVEY.md §8f N4): z_dev (tokens, cdim) fp32 token-major (the reference's z.permute(0, 2, 3, 1).view(-1, emb_dim)),
+ * codebook_dev (ncodes, cdim) = quantize.embedding.weight.  Writes idx_dev[t] = argmin_j (|z_t|^2 + |e_j|^2 - 2 z_t.e_j)
+ * (int32, ties -> lowest j, as torch.argmin), zq_dev (tokens, cdim) = e[idx] -- with straight_through != 0 the forward
+ * value z + (e[idx] - z) the reference returns (:61) -- and dmin_dev[t] = the winning distance.  zq_dev / dmin_dev may be
+ * NULL.  Asynchronous on `stream`.  Returns 0, or a negative code with keep_last_error() set (cdim must be a multiple
+ * of 128, <= 384). */
+int keepop_vq_nearest(const float* z_dev, int tokens, int cdim, const float* codebook_dev, int ncodes, int straight_through,
+                      int* idx_dev, float* zq_dev, float* dmin_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,8 @@ else:
 
 KeepNetB200 = pkg.KeepNetB200
 KEEP_GENERAL_CFG = pkg.KEEP_GENERAL_CFG
+KEEP_ASIAN_CFG = pkg.KEEP_ASIAN_CFG
+vector_quantize = pkg.vector_quantize
 install_into_model_pack = pkg.install_into_model_pack
 build = pkg.build
 lib_path = pkg.lib_path

@@ -419,6 +419,24 @@ def gmflow_forward(img0, img1, w):
 
 
 # ----------------------------------------------------------------------------------------------
+# nearest-neighbour quantiser (the VQGAN's own `quantize` module; KEEP inference uses get_codebook_feat instead)
+# ----------------------------------------------------------------------------------------------
+
+@torch.no_grad()
+def vq_nearest(z, codebook):
+    """VectorQuantizer.forward, inference values only (vqgan_arch.py:37-76).
+    z (n, C, h, w), codebook (K, C) -> z_q (n, C, h, w) [the forward value of z + (z_q - z).detach(), :61],
+    indices (n*h*w,) int64 [torch.argmin, :47], d (n*h*w, K) the distance matrix [:43-44]."""
+    zp = z.permute(0, 2, 3, 1).contiguous()
+    zf = zp.view(-1, codebook.shape[1])
+    d = (zf ** 2).sum(dim=1, keepdim=True) + (codebook ** 2).sum(1) - 2 * torch.matmul(zf, codebook.t())
+    idx = torch.argmin(d, dim=1)
+    z_q = codebook[idx].view(zp.shape)          # one_hot @ codebook (:50-55) is an exact row gather
+    z_q = zp + (z_q - zp)
+    return z_q.permute(0, 3, 1, 2).contiguous(), idx, d
+
+
+# ----------------------------------------------------------------------------------------------
 # full forward
 # ----------------------------------------------------------------------------------------------
 

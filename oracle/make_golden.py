@@ -63,6 +63,31 @@ CASES = (  # fixture name, model config, T, coherent clip, clip seed
 )
 
 
+def pin_vq(report):
+    """Pin oracle vq_nearest against the real VectorQuantizer.forward (vqgan_arch.py:37-76) -> ref_vq.npz."""
+    ref_loader._install_shims()
+    from wm_basicsr.archs.vqgan_arch import VectorQuantizer
+    sd = weights.make_state_dict(seed=0)
+    cb, z = weights.make_vq_case(sd["quantize.embedding.weight"], n=2, seed=99)   # entry 700 duplicates entry 3: exact ties
+    vq = VectorQuantizer(1024, 256, 0.25).eval()
+    vq.embedding.weight.data.copy_(cb)
+    with torch.no_grad():
+        zq_ref, _, info = vq(z)
+    idx_ref = info["min_encoding_indices"].view(-1)
+    zq, idx, d = keep_oracle.vq_nearest(z, cb)
+    top2 = d.topk(2, dim=1, largest=False).values
+    case = {"tokens": int(idx.numel()), "index_agreement": float((idx == idx_ref).float().mean()),
+            "zq_bit_equal": bool(torch.equal(zq, zq_ref)), "mean_distance_ref": float(info["mean_distance"]),
+            "mean_distance_oracle": float(d.mean()), "unique_codes": int(idx_ref.unique().numel()),
+            "margin_min": float((top2[:, 1] - top2[:, 0]).min()), "hits_duplicate_low": int((idx_ref == 3).sum()),
+            "hits_duplicate_high": int((idx_ref == 700).sum())}
+    report["cases"]["vq_nearest"] = case
+    print("vq_nearest", json.dumps(case, indent=1))
+    np.savez_compressed(os.path.join(GOLD, "ref_vq.npz"), idx=idx_ref.numpy().astype(np.int16),
+                        top2=top2.numpy().astype(np.float32), zq_sum=zq_ref.double().sum(dim=(2, 3)).numpy(),
+                        zq_crop=zq_ref[:, :8, :4, :4].numpy())
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
@@ -136,6 +161,8 @@ def main():
             codes=ref_cap["codes"].numpy().astype(np.int16),
             logit_top2=top2.numpy().astype(np.float32),
         )
+    if not only or "vq_nearest" in only:
+        pin_vq(report)
     with open(rp, "w") as f:
         json.dump(report, f, indent=1)
 

@@ -14,7 +14,11 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def test_pin_report_says_oracle_matches_reference():
     rep = json.load(open(os.path.join(GOLD, "pin_report.json")))
+    vq = rep["cases"]["vq_nearest"]
+    assert vq["index_agreement"] == 1.0 and vq["zq_bit_equal"] and vq["hits_duplicate_low"] == 8 and vq["hits_duplicate_high"] == 0
     for name, case in rep["cases"].items():
+        if name == "vq_nearest":
+            continue
         assert case["oracle_vs_ref_code_agreement"] == 1.0, name
         # unclamped outputs of the synthetic-weight nets reach |70| (Asian: CFT at 256^2); the pixel bar is on the clamped range
         assert case["oracle_vs_ref_maxabs"]["out"] < 1e-3 * max(1.0, case["ref_out_absmax"] / 16), name
@@ -150,3 +154,24 @@ def test_asian_config_host_mirror_and_plan_only_engine(keep_mod, lib, state_dict
     del bad._weights["cft.256.shift.2.weight"]
     with pytest.raises(RuntimeError, match="cft.256.shift.2.weight"):
         bad._make_engine(flags=256)
+
+
+# ---- nearest-neighbour quantiser (vqgan_arch.py:37-76) -------------------------------------------------
+
+def test_oracle_vq_nearest_reproduces_reference_fixture(state_dict):
+    """ref_vq.npz holds what the REAL VectorQuantizer.forward returned (oracle/make_golden.py::pin_vq)."""
+    from oracle import keep_oracle, weights
+    g = np.load(os.path.join(GOLD, "ref_vq.npz"))
+    cb, z = weights.make_vq_case(state_dict["quantize.embedding.weight"], n=2, seed=99)
+    zq, idx, d = keep_oracle.vq_nearest(z, cb)
+    assert np.array_equal(idx.numpy().astype(np.int16), g["idx"])
+    assert int((idx[:8] == 3).sum()) == 8 and int((idx == 700).sum()) == 0      # exact ties -> lowest index
+    np.testing.assert_allclose(d.topk(2, dim=1, largest=False).values.numpy(), g["top2"], rtol=0, atol=1e-4)
+    assert np.array_equal(zq[:, :8, :4, :4].numpy(), g["zq_crop"])
+    np.testing.assert_allclose(zq.double().sum(dim=(2, 3)).numpy(), g["zq_sum"], atol=1e-9)
+
+
+def test_vector_quantize_has_no_cpu_fallback(keep_mod, state_dict):
+    cb = state_dict["quantize.embedding.weight"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        keep_mod.vector_quantize(torch.zeros(1, 256, 16, 16), cb)
