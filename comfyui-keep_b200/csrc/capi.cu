@@ -187,8 +187,9 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
         CUDA_CHECK(cudaStreamSynchronize(s));
         return 0;
     }
-    if (use_tc) {
-        int rc = keepop_conv2d_tc(a, weight_host, use_tc == 3 ? 3 : 1, s);
+    if (use_tc) {   // 1: fp16 operands; 3: split precision; 19 (= 3 | 16): split precision with bf16 activation pairs (KEEP_FLAG_TC_WIDE)
+        a.a_wide = (use_tc & 16) ? 1 : 0;
+        int rc = keepop_conv2d_tc(a, weight_host, (use_tc & 3) == 3 ? 3 : 1, s);
         CUDA_CHECK(cudaStreamSynchronize(s));
         return rc;
     }

@@ -1,6 +1,7 @@
 // keep_b200 — shared host/device helpers for the sm_100a KEEP engine.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>

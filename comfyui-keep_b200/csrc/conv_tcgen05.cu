@@ -155,7 +155,10 @@ __device__ __noinline__ float act_slow(float v, int act) { return apply_act(v, a
         if (a.trace && blockIdx.x == 0 && (idx) < 16) a.trace[(slot) * 16 + (idx)] = clock64();    \
     } while (0)
 
-template <int PASSES, bool IN_F16, int WIN>
+// A_BF16 (split-precision mode only): both operand pairs (Ah, Al), (Wh, Wl) are bf16 instead of fp16 -- fp32's exponent
+// range, 16 mantissa bits per pair instead of 22.  For layers whose input is a raw (un-normalised) feature map of
+// unbounded magnitude: fp16 overflows to inf beyond 65504 (KEEP_FLAG_TC_WIDE).
+template <int PASSES, bool IN_F16, int WIN, bool A_BF16 = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms are 1024-byte aligned
@@ -360,13 +363,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
                             }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
                             __half2 lq[4];
+                            if (A_BF16) {   // same split with bf16 parts (bit patterns carried in the __half2 registers)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {   // residual (lo) operand: v - float(fp16(v))
-                                const float2 r = __half22float2(hq[j]);
-                                lq[j] = __floats2half2_rn(v[2 * j] - r.x, v[2 * j + 1] - r.y);
+                                for (int j = 0; j < 4; ++j) {
+                                    const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                                    const float2 r = __bfloat1622float2(hb);
+                                    const __nv_bfloat162 lb = __floats2bfloat162_rn(v[2 * j] - r.x, v[2 * j + 1] - r.y);
+                                    hq[j] = *reinterpret_cast<const __half2*>(&hb);
+                                    lq[j] = *reinterpret_cast<const __half2*>(&lb);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {   // residual (lo) operand: v - float(fp16(v))
+                                    const float2 r = __half22float2(hq[j]);
+                                    lq[j] = __floats2half2_rn(v[2 * j] - r.x, v[2 * j + 1] - r.y);
+                                }
                             }
                             ol.x = *reinterpret_cast<uint32_t*>(&lq[0]); ol.y = *reinterpret_cast<uint32_t*>(&lq[1]);
                             ol.z = *reinterpret_cast<uint32_t*>(&lq[2]); ol.w = *reinterpret_cast<uint32_t*>(&lq[3]);
@@ -448,7 +462,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         // descriptors live in the uniform datapath; one elected lane issues the tcgen05 instructions.  A first version
         // ran this loop on a single divergent lane with per-MMA 64-bit descriptor construction: ~150 instructions per
         // filter tap on one thread made *instruction issue of this warp* the bottleneck of the whole kernel.
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, K-major A/B
+        // f16 x f16 -> f32, K-major A/B; A_BF16: a_format (bits [7,10)) = b_format (bits [10,13)) = 1 = bf16 (kind::f16 traps
+        // on mixed f16 / bf16 operands, so the wide variant's weight panels hold bf16 pairs too)
+        const uint32_t idesc = (1u << 4) | (A_BF16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
         // descriptor = {lo: start>>4 | LBO(1)<<16, hi: SBO>>4 | version 1<<14 | base_offset<<17 | SWIZZLE_128B(2)<<29}
         constexpr uint32_t a_sbo = conv3 ? (uint32_t)(HPITCH_PX * 128) : 1024u;
         constexpr uint32_t a_hi = ((a_sbo >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
@@ -817,13 +833,18 @@ __host__ __device__ inline PanelPos panel_pos(size_t idx, int bn, int taps, int 
     else { q.part = 0; q.k = (cl << 3) + e; }
     return q;
 }
-__host__ __device__ inline __half split_part(float v, int part) {
+__host__ __device__ inline __half split_part(float v, int part, int wide = 0) {
+    if (wide) {   // bf16 (hi, lo) pair, bit patterns stored in the fp16 panel (KEEP_FLAG_TC_WIDE: both MMA operands are bf16)
+        const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+        const __nv_bfloat16 r = part == 0 ? hb : __float2bfloat16_rn(v - __bfloat162float(hb));
+        return *reinterpret_cast<const __half*>(&r);
+    }
     const __half hi = __float2half_rn(v);
     return part == 0 ? hi : __float2half_rn(v - __half2float(hi));
 }
 
 // OIHW fp32 (host) -> [ntile][cb][tap] panels
-void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out) {
+void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out, int wide) {
     const int taps = kh * kw, cb = cb_of(passes), ncb = (cin + cb - 1) / cb;
     const size_t total = tc_packed_weight_halfs(cin, cout, taps, bn, passes);
     for (size_t idx = 0; idx < total; ++idx) {
@@ -831,14 +852,14 @@ void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int
         const int o = q.nt * bn + q.row, i = q.cb * cb + q.k;
         float v = 0.0f;
         if (o < cout && i < cin) v = w_oihw[(((size_t)o * cin + i) * kh + q.tap / kw) * kw + q.tap % kw];
-        out[idx] = split_part(v, q.part);
+        out[idx] = split_part(v, q.part, wide);
     }
 }
 
 namespace {
 // device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 swizzled panels
 __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int passes, int s2d_pad,
-                                 size_t total, __half* __restrict__ out) {
+                                 size_t total, __half* __restrict__ out, int wide) {
     pdl_prologue();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -854,7 +875,7 @@ __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout,
         const int ky = 2 * (q.tap >> 1) + (par >> 1) - s2d_pad, kx = 2 * (q.tap & 1) + (par & 1) - s2d_pad;
         if (o < cout && i < cin && ky >= 0 && ky <= 2 && kx >= 0 && kx <= 2) v = w[((size_t)(ky * 3 + kx) * cin + i) * cout + o];
     }
-    out[idx] = split_part(v, q.part);
+    out[idx] = split_part(v, q.part, wide);
 }
 
 // Activation matrix -> tcgen05 "weight" panels, so that C[z] = A[z] * B[z]^T (attention QK^T, PV) runs on the same kernel:
@@ -917,14 +938,14 @@ size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, i
     return per_batch;
 }
 
-void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s) {
+void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s, int wide) {
     // stride-2 mode: `cin` real channels are seen as 4 * ceil(cin/cb) * cb virtual channels with a 2x2 (taps = 4) window
     const int cb = cb_of(passes);
     const int vcin = s2d_pad >= 0 ? 4 * ((cin + cb - 1) / cb) * cb : cin;
     const int vtaps = s2d_pad >= 0 ? 4 : taps;
     const int ncb = (vcin + cb - 1) / cb;
     const size_t total = tc_packed_weight_halfs(vcin, cout, vtaps, bn, passes);
-    launch_k(tc_repack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, w_kc, cin, cout, vtaps, bn, ncb, passes, s2d_pad, total, out);
+    launch_k(tc_repack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, w_kc, cin, cout, vtaps, bn, ncb, passes, s2d_pad, total, out, wide);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1074,7 +1095,16 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
             CUDA_CHECK(cudaFuncSetAttribute(kerns[i / 6][(i / 3) % 2][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    const Kern kern = kerns[passes == 3 ? 1 : 0][f16 ? 1 : 0][t.win - 1];
+    // wide-range variant (bf16 activation pairs): split-precision mode, fp32 feature maps only
+    static const Kern kerns_wide[3] = {conv_tc_kernel<3, false, 1, true>, conv_tc_kernel<3, false, 2, true>, conv_tc_kernel<3, false, 3, true>};
+    static bool configured_wide = false;
+    const bool wide = a.a_wide && passes == 3 && !f16;
+    if (wide && !configured_wide) {
+        for (int i = 0; i < 3; ++i)
+            CUDA_CHECK(cudaFuncSetAttribute(kerns_wide[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured_wide = true;
+    }
+    const Kern kern = wide ? kerns_wide[t.win - 1] : kerns[passes == 3 ? 1 : 0][f16 ? 1 : 0][t.win - 1];
     if (t.cluster_k) {   // one work item per CTA, the splitk CTAs of a tile form one cluster
         launch_k_cluster(kern, dim3((unsigned)total), dim3(kThreads), smem, s, splitk, t);
         CUDA_CHECK(cudaGetLastError());
@@ -1103,12 +1133,12 @@ int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, int pass
     float* part = nullptr;
     if (!s2d) {
         std::vector<__half> packed(tc_packed_weight_halfs(cin, a.cout, a.kh * a.kw, bn, passes));
-        tc_pack_weights(w_oihw_host, a.cout, cin, a.kh, a.kw, bn, passes, packed.data());
+        tc_pack_weights(w_oihw_host, a.cout, cin, a.kh, a.kw, bn, passes, packed.data(), (a.a_wide && passes == 3) ? 1 : 0);
         CUDA_CHECK(cudaMalloc((void**)&dw, packed.size() * sizeof(__half)));
         CUDA_CHECK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
     } else {   // a.wt already holds the [9*cin][cout] fp32 layout on the device
         CUDA_CHECK(cudaMalloc((void**)&dw, tc_packed_weight_halfs(vcin, a.cout, 4, bn, passes) * sizeof(__half)));
-        tc_repack_device(a.wt, cin, a.cout, 9, bn, passes, a.pad_t, dw, s);
+        tc_repack_device(a.wt, cin, a.cout, 9, bn, passes, a.pad_t, dw, s, (a.a_wide && passes == 3) ? 1 : 0);
     }
     const int splitk = tc_pick_splitk(m_tiles, cdiv(a.cout, bn), cdiv(vcin, tc_cb(passes)));
     if (splitk > 1) CUDA_CHECK(cudaMalloc((void**)&part, (size_t)splitk * a.n * a.ho * a.wo * a.cout * sizeof(float)));

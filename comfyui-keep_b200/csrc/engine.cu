@@ -1,6 +1,7 @@
 // keep_b200 — KEEP forward orchestration: reference call graph (keep_arch.py:1008-1145) re-expressed
 // as a stream of hand-written sm_100a kernels over NHWC activations.
 #include "engine.h"
+#include <cmath>
 
 #include <math.h>
 #include <string.h>
@@ -395,6 +396,9 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     // downstream of every decision (pass_override_, see generator())
     const int passes = (pass_override_ && tc_passes_ == 3) ? pass_override_ : tc_passes_;
     a.pre_exact = (passes == 1 && tc_passes_ == 3) ? 1 : 0;   // keep the exact fp32 swish in front of the fp16 rounding
+    // un-normalised feature maps in the generator (upsample convs, 1x1 shortcuts, CFT scale / shift convs) have no bound on
+    // their magnitude: four stacked CFT modulations of the 'Asian' programme reach 6e4 with synthetic weights, past fp16
+    a.a_wide = (wide_scope_ && !o.pre && x.w > 1) ? 1 : 0;
     if (use_tc) {
         const long long m_tiles = cw.kh == 3 ? (long long)x.n * cdiv(a.ho, 16) * cdiv(a.wo, 8)
                                              : (long long)x.n * cdiv((long long)x.h * x.w, 128);
@@ -422,7 +426,10 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         // stream always finds free SMs
         const int grid_cap = (s_ == side_ && side_) ? side_sms_ : main_cap_;
         int nl = a.splitk > 1 ? 2 : 1;
-        if (use_tc) nl = conv2d_tc(a, tc_weights(cw, bn, passes, tc_is_s2d(a) ? a.pad_t : -1), bn, passes, a.splitk, a.partial, grid_cap, s_);
+        if (use_tc) {
+            a.a_wide = (a.a_wide && passes == 3 && a.in0_dt == F32) ? 1 : 0;
+            nl = conv2d_tc(a, tc_weights(cw, bn, passes, tc_is_s2d(a) ? a.pad_t : -1, a.a_wide), bn, passes, a.splitk, a.partial, grid_cap, s_);
+        }
         else if (use_small) conv2d_small(a, s_);
         else conv2d_simt(a, s_);
         launches_ += nl;
@@ -430,21 +437,53 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             CUDA_CHECK(cudaEventRecord(pr.b, s_));
             prof_.push_back(pr);
         }
+        // KEEP_DEBUG_VERIFY_TC=1 (debug, eager mode only): re-run every tcgen05 layer on the exact-fp32 CUDA-core kernel and
+        // report the layers whose results differ -- pinpoints a bad (shape, tile, split) configuration in one forward
+        static const bool verify = getenv("KEEP_DEBUG_VERIFY_TC") != nullptr;
+        if (verify && use_tc && out.dt == F32) {
+            CUDA_CHECK(cudaStreamSynchronize(s_));
+            ConvArgs b = a;
+            float* ref = nullptr;
+            CUDA_CHECK(cudaMalloc((void**)&ref, out.bytes()));
+            b.out = ref; b.splitk = 1; b.partial = nullptr;
+            conv2d_simt(b, s_);
+            CUDA_CHECK(cudaStreamSynchronize(s_));
+            std::vector<float> h_tc(out.numel()), h_ref(out.numel());
+            CUDA_CHECK(cudaMemcpy(h_tc.data(), out.p, out.bytes(), cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(h_ref.data(), ref, out.bytes(), cudaMemcpyDeviceToHost));
+            cudaFree(ref);
+            double emax = 0.0, rmax = 0.0;
+            long long bad = 0, first_bad = -1;
+            for (size_t i = 0; i < h_tc.size(); ++i) {
+                if (!std::isfinite(h_tc[i])) { if (bad++ == 0) first_bad = (long long)i; continue; }
+                emax = std::max(emax, (double)std::fabs(h_tc[i] - h_ref[i]));
+                rmax = std::max(rmax, (double)std::fabs(h_ref[i]));
+            }
+            static long long checked = 0, flagged = 0;
+            ++checked;
+            const bool flag = bad > 0 || emax > 2e-3 * std::max(1.0, rmax);
+            if (flag) ++flagged;
+            if (flag || checked % 200 == 0)
+                fprintf(stderr, "[verify_tc] %s layer %lld: n=%d h=%d w=%d c0=%d c1=%d cout=%d k=%d stride=%d up=%d pre=%d/%d act=%d res=%d "
+                        "splitk=%d bn=%d passes=%d | max|err|=%.3g max|ref|=%.3g nonfinite=%lld (first at %lld) [flagged %lld of %lld]\n",
+                        flag ? "MISMATCH" : "ok", checked, a.n, a.h, a.w, a.c0, a.c1, a.cout, a.kh, a.stride, a.up, a.pre_scale ? 1 : 0,
+                        a.pre_act, a.act, a.res ? 1 : 0, a.splitk, bn, passes, emax, rmax, bad, first_bad, flagged, checked);
+        }
     }
     if (part) ar_->free(part);
     return out;
 }
 
-const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad) {
+const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide) {
     auto it = tcw_.find(cw.w);
-    if (it != tcw_.end() && it->second.bn == bn && it->second.passes == passes) return it->second.p;
+    if (it != tcw_.end() && it->second.bn == bn && it->second.passes == passes && it->second.wide == wide) return it->second.p;
     TcW t;
-    t.bn = bn; t.passes = passes;
+    t.bn = bn; t.passes = passes; t.wide = wide;
     const int cb = tc_cb(passes);
     const int vcin = s2d_pad >= 0 ? 4 * ((cw.cin + cb - 1) / cb) * cb : cw.cin;
     const int vtaps = s2d_pad >= 0 ? 4 : cw.kh * cw.kw;
     CUDA_CHECK(cudaMalloc((void**)&t.p, tc_packed_weight_halfs(vcin, cw.cout, vtaps, bn, passes) * sizeof(__half)));
-    tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, passes, s2d_pad, t.p, s_);
+    tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, passes, s2d_pad, t.p, s_, wide);
     if (it != tcw_.end()) {
         CUDA_CHECK(cudaStreamSynchronize(s_));
         cudaFree(it->second.p);
@@ -1084,6 +1123,7 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[6], Tensor 
     // of 3) in the split-precision mode -- they are the last layers before the pixels, so their rounding error is not
     // amplified by later normalisations; 20 = the 512^2 level, 17 = + the 256^2 level
     static const int fast_from = getenv("KEEP_GEN_FAST_FROM") ? atoi(getenv("KEEP_GEN_FAST_FROM")) : 99;
+    wide_scope_ = (flags_ & KEEP_FLAG_TC_WIDE) != 0;
     for (int j = 0; j < 25; ++j) {
         pass_override_ = j >= fast_from ? 1 : 0;
         const std::string bp = "generator.blocks." + std::to_string(j);
@@ -1133,6 +1173,7 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[6], Tensor 
         }
     }
     pass_override_ = 0;
+    wide_scope_ = false;
     return x;   // (1,512,512,3) fp32
 }
 

@@ -129,9 +129,10 @@ class Engine {
     void* own_ws_ = nullptr; size_t own_ws_bytes_ = 0;
     std::unordered_map<int, size_t> ws_cache_;
     // tcgen05 path: fp16 weight panels, packed on first use, keyed by (fp32 weight pointer, N tile)
-    struct TcW { __half* p = nullptr; int bn = 0, passes = 0; };
+    struct TcW { __half* p = nullptr; int bn = 0, passes = 0, wide = 0; };
     std::unordered_map<const float*, TcW> tcw_;
-    const __half* tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad);
+    const __half* tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide = 0);
+    bool wide_scope_ = false; // KEEP_FLAG_TC_WIDE and inside generator(): raw-input feature-map layers use bf16 activation pairs
     int pass_override_ = 0;   // != 0: operand passes for the layers being enqueued (generator tail experiment)
     int tc_passes_ = 1;   // 1: fp16 operands; 3: split-precision (fp32-grade) tensor-core mode
     int num_sms_ = 148;

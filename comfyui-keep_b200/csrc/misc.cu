@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restr
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
+    if (bi == 0x7fffffff) bi = 0;   // a row of NaNs compares false everywhere: stay inside the codebook (torch returns a NaN's index)
     if (lane == 0) idx_out[tok] = bi;
     const int use = forced ? forced[tok] : bi;
     for (int ch = lane; ch < cdim; ch += 32) st1_any(quant, q_dt, (size_t)tok * cdim + ch, codebook[(size_t)use * cdim + ch]);

@@ -26,6 +26,7 @@ struct ConvArgs {
     void* out = nullptr; int out_dt = F32;
     // split-K (deterministic: partials to workspace, fixed-order reduce)
     int splitk = 1; float* partial = nullptr;
+    int a_wide = 0;                // tcgen05 split-precision path: bf16 activation pairs (fp32 range) instead of fp16 pairs
     int pre_exact = 0;             // tcgen05 fp16-operand path: exact fp32 swish before the fp16 rounding (default: packed tanh.approx)
     long long wt_img_stride = 0;   // tcgen05 path only: per-image packed weight sets (batched A*B^T for attention)
 };

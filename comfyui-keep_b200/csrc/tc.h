@@ -33,9 +33,9 @@ size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn, int passes);
 bool tc_is_s2d(const ConvArgs& a);
 int tc_cb(int passes);                        // input channels per A stage / weight panel: 64, or 32 in the split-precision mode
 int tc_virtual_cin(const ConvArgs& a, int passes);   // 4 * ceil(cin/cb) * cb for the stride-2 mode, else cin
-void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out);
+void tc_pack_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int bn, int passes, __half* out, int wide = 0);
 // s2d_pad < 0: plain repack; else stride-2 mode with pad_t = pad_l = s2d_pad (weights indexed [9*cin][cout])
-void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s);
+void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, int passes, int s2d_pad, __half* out, cudaStream_t s, int wide = 0);
 // pack B[z] (N x K, strided) into per-batch panel sets; returns halfs per batch (out == null: size query only)
 size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, int nbatch, int N, int K, int bn, int passes,
                       float alpha, __half* out, cudaStream_t s);

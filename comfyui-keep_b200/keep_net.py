@@ -34,6 +34,7 @@ FLAG_FP16_FEATURES = 1
 FLAG_TCGEN05 = 2
 FLAG_TC_SPLIT3 = 4
 FLAG_CUDA_GRAPH = 8
+FLAG_TC_WIDE = 16
 FLAG_PLAN_ONLY = 256
 
 
@@ -128,6 +129,10 @@ class KeepNetB200(nn.Module):
         self._rep_streams = []
         self.config = config_name(cfg)   # 'KEEP' | 'Asian'; the engine reads the fusion points off the tensor names
         self._flags = int(flags)
+        if self.config == "Asian" and (self._flags & FLAG_TC_SPLIT3):
+            # four stacked CFT modulations (32^2 .. 256^2) leave raw generator features with no magnitude bound (6e4 with
+            # the synthetic weights, past fp16's 65504): bf16 activation pairs on those layers (include/keep_b200.h)
+            self._flags |= FLAG_TC_WIDE
         self._shapes = expected_shapes(self.config)
         self._weights = None          # CPU fp32 tensors, reference key names
         self._engine = None           # keep_handle (c_void_p)

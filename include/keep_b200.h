@@ -43,6 +43,9 @@ enum {
     KEEP_FLAG_TCGEN05 = 2,       /* run eligible convolutions / GEMMs on the tcgen05 tensor-core kernel */
     KEEP_FLAG_TC_SPLIT3 = 4,     /* with TCGEN05: split-precision operands (A=Ah+Al, W=Wh+Wl, 3 MMAs) -> fp32-grade results */
     KEEP_FLAG_CUDA_GRAPH = 8,    /* capture one clip forward per T into a CUDA graph after the first (eager) call and replay it */
+    KEEP_FLAG_TC_WIDE = 16,      /* with TC_SPLIT3: generator / CFT layers that read a raw (un-normalised) feature map take their
+                                    activation operand as a bf16 pair (fp32 exponent range, 16 mantissa bits) instead of an fp16
+                                    pair (22 bits, overflows beyond 65504) */
     KEEP_FLAG_PLAN_ONLY = 256    /* host-side planning only (strict key check + workspace sizing); keep_forward fails */
 };
 
@@ -96,7 +99,9 @@ long long keep_debug_read(keep_handle h, const char* what, void* host_data, size
 
 /* ---- op-level entry points (tests/ only): each runs ONE kernel family on device pointers --------
  * conv: x (n,h,w,cin) NHWC fp32, weight OIHW host fp32, bias host or NULL; pads (t,l,b,r); `up` nearest
- * factor; pre_scale/pre_shift (n,cin) device or NULL; res (n,ho,wo,cout) device or NULL; out device fp32. */
+ * factor; pre_scale/pre_shift (n,cin) device or NULL; res (n,ho,wo,cout) device or NULL; out device fp32.
+ * use_tc: 0 exact-fp32 CUDA cores | 1 tcgen05, fp16 operands | 3 tcgen05, split precision | 19 (3|16) split precision with
+ * bf16 activation pairs (KEEP_FLAG_TC_WIDE) | 4 the Cin=3 / Cout<=4 stem and head kernels. */
 int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, const float* weight_host, const float* bias_host,
                   int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
                   const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,

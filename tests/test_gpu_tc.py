@@ -116,6 +116,40 @@ def test_conv_tcgen05_split_precision_matches_fp32(lib, case):
     assert err <= 2e-5 * max(1.0, float(want.abs().max())), "%s: max abs err %g" % (name, err)
 
 
+WIDE_CASES = [  # name, n, cin, h, w, cout, k, up, act, res, input scale
+    ("wide_up2_128_big", 1, 128, 32, 32, 128, 3, 2, "none", False, 3.0e5),       # generator Upsample conv on blown-up features
+    ("wide_3x3_lrelu_128", 1, 128, 48, 40, 128, 3, 1, "lrelu", False, 1.0e5),    # CFT scale.0 / shift.0
+    ("wide_1x1_256_128_res", 1, 256, 64, 64, 128, 1, 1, "none", True, 2.0e5),    # CFT encode_enc.conv_out over the concat
+    ("wide_3x3_unit_scale", 1, 64, 32, 32, 64, 3, 1, "none", False, 1.0),        # ordinary magnitudes: 16-bit-mantissa pair
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES, ids=[c[0] for c in WIDE_CASES])
+def test_conv_tcgen05_wide_range_bf16_pairs(lib, case):
+    """use_tc=19 (KEEP_FLAG_TC_WIDE): activations as bf16 (hi, lo) pairs -> finite and accurate where fp16 pairs overflow
+    (|x| > 65504); relative accuracy 2^-17 per operand instead of 2^-23."""
+    name, n, cin, h, w, cout, k, up, act, res, scale = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) & 0xFFFF)
+    x = (scale * torch.randn((n, cin, h, w), generator=g)).cuda()
+    wt = (torch.randn((cout, cin, k, k), generator=g) / math.sqrt(cin * k * k)).cuda()
+    b = torch.randn((cout,), generator=g).cuda()
+    pads = (1, 1, 1, 1) if k == 3 else (0, 0, 0, 0)
+    want0 = ref_conv(x.double(), wt.double(), b.double(), 1, pads, up, None, "none", act, None).float()
+    r = (scale * torch.randn(want0.shape, generator=g)).cuda() if res else None
+    want = want0 + r if res else want0
+    got = run_conv(lib, x, wt, b, 1, pads, up, None, "none", act, r, use_tc=19)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(got).all())
+    err = float((got - want).abs().max())
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "tc_op_report.txt"), "a") as f:
+        f.write("wide %s err=%.3e max=%.3f\n" % (name, err, float(want.abs().max())))
+    assert err <= 1e-4 * max(1.0, float(want.abs().max())), "%s: max abs err %g" % (name, err)
+    if scale > 7e4:   # the fp16-pair mode cannot represent these inputs at all
+        plain = run_conv(lib, x, wt, b, 1, pads, up, None, "none", act, r, use_tc=3)
+        assert not bool(torch.isfinite(plain).all())
+
+
 S2_CASES = [
     # name, n, cin, h, w, cout, pads(t,l,b,r), pre, pre_act
     ("vq_down_64", 2, 64, 64, 48, 64, (0, 0, 1, 1), False, "none"),
