@@ -146,6 +146,9 @@ def main():
     ap.add_argument("--clips-per-step", type=int, default=1,
                     help="clips per GPU per step (default 1 = BASELINE configs[1]); > 1 is the stream-of-clips workload (configs[4]): "
                          "independent clips, two in flight per GPU on engine replicas (KeepNetB200(concurrent_clips=2))")
+    ap.add_argument("--batch-clips", type=int, default=int(os.environ.get("KEEP_BENCH_BATCH", "1")),
+                    help="with --clips-per-step > 1: clips per lockstep group inside one engine (KeepNetB200(batch_clips=N)) instead of "
+                         "engine replicas on separate streams")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying the per-clip CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +182,9 @@ def main():
     if not args.no_graph:
         flags |= keep_b200.keep_net.FLAG_CUDA_GRAPH
     B = max(1, args.clips_per_step)
-    net = keep_b200.KeepNetB200(flags=flags, concurrent_clips=min(B, int(os.environ.get("KEEP_BENCH_REPLICAS", "2"))) if B > 1 else 1)
+    batch = min(B, max(1, args.batch_clips))
+    net = keep_b200.KeepNetB200(flags=flags, batch_clips=batch,
+                                concurrent_clips=min(B, int(os.environ.get("KEEP_BENCH_REPLICAS", "2"))) if (B > 1 and batch <= 1) else 1)
     net.load_state_dict(keep_b200.synth.make_state_dict(seed=0), strict=True)
     net.eval().to(dev)
     x_host = torch.cat([keep_b200.synth.make_clip(T, seed=1234 + rank + 100 * i, coherent=True) for i in range(B)], 0).pin_memory()
@@ -333,7 +338,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[mode], "data": "synthetic",
             "config": {"workload": "KEEP general model, %d-frame aligned 512x512 synthetic clip, %s per GPU per step" % (
-                           T, "one clip" if B == 1 else "%d independent clips (two in flight on engine replicas)" % B),
+                           T, "one clip" if B == 1 else ("%d independent clips (lockstep groups of %d inside one engine)" % (B, batch) if batch > 1
+                                                     else "%d independent clips (two in flight on engine replicas)" % B)),
                        "weights": "seeded synthetic (no checkpoint offline)", "engine_mode": mode,
                        "cuda_graph": not args.no_graph,
                        "l2": "256 MiB buffer zeroed between timed steps; per-step working set >> 126 MB L2",

@@ -76,6 +76,16 @@ int keep_forward(keep_handle h, const float* x_dev, int b, int T, void* out_dev,
     KEEP_API_END
 }
 
+int keep_set_batch_clips(keep_handle h, int max_clips) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h, "keep_set_batch_clips: null handle");
+    KEEP_CHECK(max_clips >= 1 && max_clips <= 8, "keep_set_batch_clips: 1 <= max_clips <= 8 (got %d)", max_clips);
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->e->set_batch_clips(max_clips);
+    return 0;
+    KEEP_API_END
+}
+
 int keep_forward_u8(keep_handle h, const unsigned char* x_u8_dev, int b, int T, unsigned char* out_u8_dev, void* workspace,
                     size_t workspace_bytes, void* stream) {
     KEEP_API_BEGIN

@@ -255,6 +255,7 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         // KEEP_SIDE_SMS = n > 0: side-branch persistent kernels capped at n CTAs; n < 0: short CTAs of -n work items each
         { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 100; if (side_sms_ > num_sms_ || (side_sms_ >= 0 && side_sms_ < 8)) side_sms_ = num_sms_; }
     }
+    { const char* e = getenv("KEEP_BATCH_MAX"); batch_max_ = e ? std::max(1, std::min(8, atoi(e))) : 2; }
     adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
     tc_passes_ = (flags & KEEP_FLAG_TC_SPLIT3) ? 3 : 1;
     pack_weights(w, n_w);
@@ -931,7 +932,7 @@ void Engine::gmflow(const float* x_nchw, int T, float* flows) {
             launches_ += 1;
         }
         tfree(mask); tfree(flow2); tfree(c0);
-        if (!ar_->dry() && s_ == side_ && side_) CUDA_CHECK(cudaEventRecord(ev_flow_[p0 / chunk], side_));
+        if (!ar_->dry() && s_ == side_ && side_) CUDA_CHECK(cudaEventRecord(ev_flow_[ev_flow_base_ + p0 / chunk], side_));
     }
 }
 
@@ -1021,8 +1022,9 @@ Tensor Engine::kalman_gains(const Tensor& z_codes, int T) {
 // =============================================================================================
 Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
     const int L = 256, E = 512, heads = 8, dh = 64;
+    const int nbt = z_hat.n;   // clips in lockstep (1 on the per-clip path): tokens of clip c are rows [c*L, (c+1)*L)
     Tensor zt = z_hat;
-    zt.n = 1; zt.h = L; zt.w = 1;
+    zt.n = 1; zt.h = nbt * L; zt.w = 1;
     Tensor t = linear(zt, "feat_emb");
     const float* pos = warr("position_emb");
     for (int l = 0; l < 9; ++l) {
@@ -1032,7 +1034,8 @@ Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
         Tensor qk = linear(qk_in, p + ".self_attn.in_proj_qk");
         Tensor v = linear(tn, p + ".self_attn.in_proj_v");
         tfree(qk_in); tfree(tn);
-        Tensor o = mha(qk.f(), 2 * E, 0, qk.f() + E, 2 * E, 0, v.f(), E, 0, 1, L, L, heads, dh, 1.0f / sqrtf((float)dh));
+        Tensor o = mha(qk.f(), 2 * E, (long long)L * 2 * E, qk.f() + E, 2 * E, (long long)L * 2 * E, v.f(), E, (long long)L * E, nbt, L, L,
+                       heads, dh, 1.0f / sqrtf((float)dh));
         tfree(qk); tfree(v);
         Tensor t1 = linear(o, p + ".self_attn.out_proj", ACT_NONE, &t);
         tfree(o); tfree(t);
@@ -1046,13 +1049,13 @@ Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
     tfree(t);
     Tensor logits = linear(tn, "idx_pred_layer.1");
     tfree(tn);
-    Tensor quant = talloc(1, 16, 16, 256, adt_);
-    int* idx = (int*)ar_->alloc(L * sizeof(int));
+    Tensor quant = talloc(nbt, 16, 16, 256, adt_);
+    int* idx = (int*)ar_->alloc((size_t)nbt * L * sizeof(int));
     if (!ar_->dry()) {
         const int* forced = nullptr;
         auto it = forced_.find("codes");
-        if (it != forced_.end() && it->second.p) forced = (const int*)it->second.p + (size_t)frame * L;
-        argmax_gather(logits.f(), L, 1024, warr("quantize.embedding.weight"), 256, forced, idx, quant.p, quant.dt, s_);
+        if (it != forced_.end() && it->second.p) forced = (const int*)it->second.p + (size_t)frame * L;   // per-clip path only
+        argmax_gather(logits.f(), nbt * L, 1024, warr("quantize.embedding.weight"), 256, forced, idx, quant.p, quant.dt, s_);
         launches_ += 1;
         if (capture_) {
             Cap& cl = cap_["logits"];
@@ -1092,19 +1095,22 @@ Tensor Engine::cft(const Tensor& enc, const Tensor& dec, const std::string& p) {
 Tensor Engine::cfa(const Tensor& cur, const Tensor& prev, const std::string& p) {
     KEEP_CHECK(cur.dt == F32 && prev.dt == F32, "cfa expects fp32 feature maps");
     const int L = cur.h * cur.w, C = cur.c, heads = 4, dh = 256, inner = heads * dh;
+    const int nbt = cur.n;   // clips in lockstep (1 on the per-clip path)
+    KEEP_CHECK(prev.n == nbt, "cfa: current / previous feature batch mismatch");
     Tensor x = cur, pv = prev;
-    x.n = 1; x.h = L; x.w = 1;
-    pv.n = 1; pv.h = L; pv.w = 1;
+    x.n = 1; x.h = nbt * L; x.w = 1;
+    pv.n = 1; pv.h = nbt * L; pv.w = 1;
     Tensor q = linear(x, p + ".attn.to_q"), k = linear(pv, p + ".attn.to_k"), v = linear(pv, p + ".attn.to_v");
-    Tensor o = mha(q.f(), inner, 0, k.f(), inner, 0, v.f(), inner, 0, 1, L, L, heads, dh, 1.0f / sqrtf((float)dh));
+    const long long bs = (long long)L * inner;
+    Tensor o = mha(q.f(), inner, bs, k.f(), inner, bs, v.f(), inner, bs, nbt, L, L, heads, dh, 1.0f / sqrtf((float)dh));
     tfree(q); tfree(k); tfree(v);
     Tensor y = linear(o, p + ".attn.to_out.0");
     tfree(o);
     Tensor x1 = ln(y, p + ".norm1", &x);
     tfree(y);
     Tensor pr = linear(x1, p + ".ff.net.0.proj");
-    Tensor gg = talloc(1, L, 1, 4 * C, F32);
-    if (!ar_->dry()) { geglu(pr.f(), gg.f(), L, 4 * C, s_); launches_ += 1; }
+    Tensor gg = talloc(1, nbt * L, 1, 4 * C, F32);
+    if (!ar_->dry()) { geglu(pr.f(), gg.f(), nbt * L, 4 * C, s_); launches_ += 1; }
     tfree(pr);
     Tensor y2 = linear(gg, p + ".ff.net.2");
     tfree(gg);
@@ -1155,9 +1161,9 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[6], Tensor 
         if (ti < 0) continue;
         const std::string sz = std::to_string(kFuseSize[ti]);
         if (cft_on_[ti]) {   // keep_arch.py:1104-1108
-            Tensor enc = taps[ti];   // (T, s, s, C): slice frame
-            enc.n = 1;
-            enc.p = (char*)enc.p + (size_t)frame * enc.h * enc.w * enc.c * dtype_size(enc.dt);
+            Tensor enc = taps[ti];   // (T * nb, s, s, C), frame-major: the nb maps of this frame (nb = 1 on the per-clip path)
+            enc.n = x.n;
+            enc.p = (char*)enc.p + (size_t)frame * x.n * enc.h * enc.w * enc.c * dtype_size(enc.dt);
             Tensor z = cft(enc, x, "cft." + sz);
             tfree(x);
             x = z;
@@ -1334,8 +1340,255 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     tfree(flows);
 }
 
+// =============================================================================================
+// lockstep forward for a group of nb clips (KEEP_FLAG_BATCH_CLIPS)
+// =============================================================================================
+// Clips are independent (keep_processor.py:263-270) but each one is a serial chain of ~500 small kernels per frame that
+// cannot fill 148 SMs (16^2 .. 64^2 maps: 2-32 M tiles per layer).  Here nb clips walk the recurrence together: frame i of
+// every clip goes through ONE hq_encoder / code-transformer / generator pass with batch nb, so each launch carries nb times
+// the work (fewer K-splits per layer, the fixed per-kernel cost paid once per nb frames).  Per-clip tensors that the
+// recurrence slices by frame (encoder taps, z_codes, gains) are stored frame-major -- slot i*nb + c -- so the nb maps
+// of one frame index are one contiguous batch.  GMFlow, the LQ encoder and the gain estimator are already batched over
+// frames and run clip by clip, as on the per-clip path.  No debug forcing / capture on this path.
+void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int out_dtype) {
+    const int HW = 512 * 512;
+    const bool dry = ar_->dry();
+    const size_t per_clip_in = (size_t)T * 3 * HW;
+    const size_t osz = out_dtype == KEEP_OUT_F16 ? 2 : (out_dtype == KEEP_OUT_U8_BGR ? 1 : 4);
+    std::vector<Tensor> flows(nb);
+    for (int c = 0; c < nb; ++c) flows[c] = talloc(T - 1, 512, 512, 2, F32);
+    Tensor taps[6], cfa_prev[6];
+    for (int k = 0; k < 6; ++k)
+        if (cft_on_[k]) taps[k] = talloc(T * nb, kFuseSize[k], kFuseSize[k], kFuseCh[k], adt_);
+    Tensor z_all = talloc(T * nb, 16, 16, 256, F32);
+    Tensor gains_all = talloc(T * nb, 16, 16, 1, F32);
+    for (int k = 0; k < 6; ++k)
+        if (cfa_on_[k]) cfa_prev[k] = talloc(nb, kFuseSize[k], kFuseSize[k], kFuseCh[k], F32);
+    // rows of `per` bytes, one per frame of clip c: contiguous (T, per) <-> frame-major slots (i*nb + c)
+    auto scatter_frames = [&](void* dst_all, const void* src, size_t per, int f0, int nf, int c) {
+        CUDA_CHECK(cudaMemcpy2DAsync((char*)dst_all + ((size_t)f0 * nb + c) * per, (size_t)nb * per, src, per, per, nf,
+                                     cudaMemcpyDeviceToDevice, s_));
+    };
+
+    // ---- optical flow of every clip on the side stream (low priority), overlapping everything below
+    static const bool no_side = getenv("KEEP_NO_SIDE") != nullptr;
+    const int nchunk = (T - 1 + flow_chunk() - 1) / flow_chunk();
+    const bool flows_async = !dry && !no_side;
+    if (flows_async) {
+        if (!side_) {
+            int lo = 0, hi = 0;
+            CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_CHECK(cudaStreamCreateWithPriority(&side_, cudaStreamNonBlocking, lo));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+        }
+        while ((int)ev_flow_.size() < nb * nchunk) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev_flow_.push_back(e);
+        }
+        CUDA_CHECK(cudaEventRecord(ev_fork_, s_main_));
+        CUDA_CHECK(cudaStreamWaitEvent(side_, ev_fork_, 0));
+        s_ = side_;
+    }
+    ar_ = &arena2_;
+    for (int c = 0; c < nb; ++c) {
+        ev_flow_base_ = c * nchunk;
+        gmflow(x_dev + (size_t)c * per_clip_in, T, flows[c].f());
+    }
+    ev_flow_base_ = 0;
+    ar_ = &arena_;
+    s_ = s_main_;
+    main_cap_ = num_sms_;
+
+    // ---- LQ encoder (frames of one clip per pass, keep_arch.py:1034-1037) and Kalman gains, clip by clip
+    const int chunk = lq_chunk();
+    for (int c = 0; c < nb; ++c) {
+        const float* xc = x_dev + (size_t)c * per_clip_in;
+        Tensor zc = talloc(T, 16, 16, 256, F32);
+        for (int f0 = 0; f0 < T; f0 += chunk) {
+            const int nf = std::min(chunk, T - f0);
+            Tensor img = talloc(nf, 512, 512, 3, adt_);
+            if (!dry) { nchw_to_nhwc(xc + (size_t)f0 * 3 * HW, img.p, img.dt, nf, 3, 512, 512, 0, s_); launches_ += 1; }
+            auto tap = [&](int i, const Tensor& t) {
+                int ti = -1;
+                for (int k = 0; k < 6; ++k) if (kFuseEnc[k] == i && cft_on_[k]) ti = k;
+                if (ti < 0 || dry) return;
+                scatter_frames(taps[ti].p, t.p, (size_t)t.h * t.w * t.c * dtype_size(t.dt), f0, nf, c);
+            };
+            Tensor z = encoder(img, "encoder", tap);
+            if (!dry) {
+                CUDA_CHECK(cudaMemcpyAsync(zc.f() + (size_t)f0 * 256 * 256, z.p, z.bytes(), cudaMemcpyDeviceToDevice, s_));
+                scatter_frames(z_all.p, z.p, (size_t)256 * 256 * sizeof(float), f0, nf, c);
+            }
+            tfree(z);
+            tfree(img);
+        }
+        Tensor g = kalman_gains(zc, T);   // (T, 16, 16, 1)
+        if (!dry) scatter_frames(gains_all.p, g.p, (size_t)256 * sizeof(float), 0, T, c);
+        tfree(g);
+        tfree(zc);
+    }
+
+    // ---- the recurrence, all clips in lockstep (keep_arch.py:1062-1128)
+    Tensor prev_out;   // (nb, 512, 512, 3) fp32 NHWC
+    for (int i = 0; i < T; ++i) {
+        Tensor z_hat;
+        bool own_z = false;
+        if (i == 0) {
+            z_hat = z_all;   // slots 0 .. nb-1 = frame 0 of every clip
+            z_hat.n = nb;
+        } else {
+            Tensor warped = talloc(nb, 512, 512, 3, adt_);
+            for (int c = 0; c < nb; ++c) {
+                if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[c * nchunk + (i - 1) / flow_chunk()], 0));
+                if (!dry) {
+                    flow_warp((const char*)prev_out.p + (size_t)c * HW * 3 * dtype_size(prev_out.dt), prev_out.dt,
+                              flows[c].f() + (size_t)(i - 1) * HW * 2, (char*)warped.p + (size_t)c * HW * 3 * dtype_size(warped.dt),
+                              warped.dt, 1, 512, 512, 3, s_);
+                    launches_ += 1;
+                }
+            }
+            Tensor zp = encoder(warped, "hq_encoder", nullptr);   // (nb, 16, 16, 256)
+            tfree(warped);
+            z_hat = talloc(nb, 16, 16, 256, F32);
+            own_z = true;
+            if (!dry) {
+                kalman_update(z_all.f() + (size_t)i * nb * 256 * 256, zp.f(), gains_all.f() + (size_t)i * nb * 256, z_hat.f(), nb * 256,
+                              256, s_);
+                launches_ += 1;
+            }
+            tfree(zp);
+        }
+        Tensor quant = code_transformer(z_hat, i);
+        if (own_z) tfree(z_hat);
+        Tensor img = generator(quant, i, taps, cfa_prev);   // (nb, 512, 512, 3)
+        tfree(quant);
+        if (!dry) {
+            for (int c = 0; c < nb; ++c) {
+                const char* src = (const char*)img.p + (size_t)c * HW * 3 * dtype_size(img.dt);
+                char* dst = (char*)out_dev + ((size_t)c * T + i) * 3 * HW * osz;
+                if (out_dtype == KEEP_OUT_U8_BGR) nhwc_to_u8bgr(src, img.dt, (unsigned char*)dst, 1, 512, 512, s_);
+                else nhwc_to_nchw(src, img.dt, dst, out_dtype == KEEP_OUT_F16 ? F16 : F32, 1, 3, 512, 512, s_);
+                launches_ += 1;
+            }
+        }
+        if (prev_out.p) tfree(prev_out);
+        prev_out = img;
+    }
+    if (flows_async)
+        for (int c = 0; c < nb; ++c) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[c * nchunk + nchunk - 1], 0));   // join the side branch
+    if (prev_out.p) tfree(prev_out);
+    for (int k = 5; k >= 0; --k) if (cfa_on_[k]) tfree(cfa_prev[k]);
+    tfree(gains_all);
+    tfree(z_all);
+    for (int k = 0; k < 6; ++k) if (cft_on_[k]) tfree(taps[k]);
+    for (int c = 0; c < nb; ++c) tfree(flows[c]);
+}
+
+// workspace plan of a lockstep group (dry run), cached per (nb, T)
+size_t Engine::plan_clips(int nb, int T) {
+    const int key = nb * 1000 + T;
+    auto it = ws_cache_.find(key);
+    if (it != ws_cache_.end()) return it->second;
+    begin(nullptr, 0, nullptr, true);
+    forward_clips(nullptr, nb, T, nullptr, KEEP_OUT_F32);
+    const size_t side = (arena2_.peak() + 4095) & ~(size_t)4095;
+    const size_t need = ((arena_.peak() + 4095) & ~(size_t)4095) + side + 4096;
+    ws_cache_[key] = need;
+    side_cache_[key] = side;
+    return need;
+}
+
+// keep_forward with KEEP_FLAG_BATCH_CLIPS and b > 1: groups of up to batch_max_ clips in lockstep, a trailing single clip on
+// the per-clip path.  Engine-owned workspace; CUDA-graph replay per (group size, T) like the per-clip path.
+void Engine::forward_batched(const float* x_dev, int b, int T, void* out_dev, int out_dtype, cudaStream_t s) {
+    const size_t per_clip = (size_t)T * 3 * 512 * 512;
+    const size_t osz = out_dtype == KEEP_OUT_F16 ? 2 : (out_dtype == KEEP_OUT_U8_BGR ? 1 : 4);
+    for (int b0 = 0; b0 < b;) {
+        const int g = std::min(batch_max_, b - b0);
+        const float* xin = x_dev + (size_t)b0 * per_clip;
+        char* xout = (char*)out_dev + (size_t)b0 * per_clip * osz;
+        if (g == 1) {   // odd clip out: the ordinary per-clip call
+            forward(xin, 1, T, xout, out_dtype, nullptr, 0, s);
+            b0 += 1;
+            continue;
+        }
+        const int key = g * 1000 + T;
+        const size_t need = plan_clips(g, T);
+        if (own_ws_bytes_ < need) {
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            cudaFree(own_ws_);
+            own_ws_ = nullptr; own_ws_bytes_ = 0;
+            for (auto& gr : graphs_) cudaGraphExecDestroy(gr.second.exec);
+            graphs_.clear();
+            CUDA_CHECK(cudaMalloc(&own_ws_, need));
+            own_ws_bytes_ = need;
+        }
+        side_bytes_ = side_cache_[key];
+        void* ws = own_ws_;
+        const size_t ws_bytes = own_ws_bytes_;
+        const bool want_graph = (flags_ & KEEP_FLAG_CUDA_GRAPH) != 0;
+        if (want_graph && eager_runs_[key] >= 1) {
+            const size_t in_bytes = (size_t)g * per_clip * 4;
+            if (gx_bytes_ < in_bytes || gout_bytes_ < in_bytes) {
+                CUDA_CHECK(cudaStreamSynchronize(s));
+                cudaFree(gx_); cudaFree(gout_);
+                gx_ = nullptr; gout_ = nullptr;
+                for (auto& gr : graphs_) cudaGraphExecDestroy(gr.second.exec);
+                graphs_.clear();
+                CUDA_CHECK(cudaMalloc((void**)&gx_, in_bytes));
+                CUDA_CHECK(cudaMalloc(&gout_, in_bytes));
+                gx_bytes_ = gout_bytes_ = in_bytes;
+            }
+            if (!gs_) {
+                int lo = 0, hi = 0;
+                CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CUDA_CHECK(cudaStreamCreateWithPriority(&gs_, cudaStreamNonBlocking, hi));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ev_out_, cudaEventDisableTiming));
+            }
+            ClipGraph& gr = graphs_[key];
+            if (gr.exec && (gr.ws != ws || gr.out_dtype != out_dtype)) { cudaGraphExecDestroy(gr.exec); gr.exec = nullptr; }
+            CUDA_CHECK(cudaEventRecord(ev_in_, s));
+            CUDA_CHECK(cudaStreamWaitEvent(gs_, ev_in_, 0));
+            if (!gr.exec) {
+                cudaGraph_t graph = nullptr;
+                CUDA_CHECK(cudaStreamBeginCapture(gs_, cudaStreamCaptureModeThreadLocal));
+                try {
+                    begin(ws, ws_bytes, gs_, false);
+                    forward_clips(gx_, g, T, gout_, out_dtype);
+                } catch (...) {
+                    cudaStreamEndCapture(gs_, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                CUDA_CHECK(cudaStreamEndCapture(gs_, &graph));
+                cudaError_t e = cudaGraphInstantiate(&gr.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                CUDA_CHECK(e);
+                gr.ws = ws; gr.out_dtype = out_dtype;
+            }
+            CUDA_CHECK(cudaMemcpyAsync(gx_, xin, (size_t)g * per_clip * 4, cudaMemcpyDeviceToDevice, gs_));
+            CUDA_CHECK(cudaGraphLaunch(gr.exec, gs_));
+            CUDA_CHECK(cudaMemcpyAsync(xout, gout_, (size_t)g * per_clip * osz, cudaMemcpyDeviceToDevice, gs_));
+            CUDA_CHECK(cudaEventRecord(ev_out_, gs_));
+            CUDA_CHECK(cudaStreamWaitEvent(s, ev_out_, 0));
+            launches_ += launches_per_clip_[key];
+        } else {
+            const long long l0 = launches_;
+            begin(ws, ws_bytes, s, false);
+            forward_clips(xin, g, T, xout, out_dtype);
+            launches_per_clip_[key] = launches_ - l0;
+            eager_runs_[key] += 1;
+        }
+        b0 += g;
+    }
+}
+
 size_t Engine::workspace_bytes(int b, int T) {
     KEEP_CHECK(b >= 1 && T >= 2 && T <= 100, "keep_workspace_bytes: need b >= 1 and 2 <= T <= 100 (got b=%d T=%d)", b, T);
+    if ((flags_ & KEEP_FLAG_BATCH_CLIPS) && b > 1 && batch_max_ > 1)   // engine-owned workspace of a lockstep group (informational)
+        return std::max(plan_clips(std::min(b, batch_max_), T), workspace_bytes(1, T));
     auto it = ws_cache_.find(T);
     if (it != ws_cache_.end()) return it->second;
     begin(nullptr, 0, nullptr, true);
@@ -1353,6 +1606,11 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
     KEEP_CHECK(b >= 1 && T >= 2 && T <= 100, "keep_forward: need b >= 1 and 2 <= T <= 100 (got b=%d T=%d)", b, T);
     KEEP_CHECK(out_dtype == KEEP_OUT_F32 || out_dtype == KEEP_OUT_F16 || out_dtype == KEEP_OUT_U8_BGR, "keep_forward: bad out_dtype %d", out_dtype);
     CUDA_CHECK(cudaSetDevice(device_));
+    if ((flags_ & KEEP_FLAG_BATCH_CLIPS) && b > 1 && batch_max_ > 1 && !ws && !capture_ && !profile_) {
+        bool forcing_b = false;
+        for (auto& kv : forced_) forcing_b = forcing_b || kv.second.p != nullptr;
+        if (!forcing_b) { forward_batched(x_dev, b, T, out_dev, out_dtype, s); return; }
+    }
     const size_t need = workspace_bytes(1, T);
     side_bytes_ = side_cache_[T];
     if (!ws) {

@@ -55,6 +55,7 @@ class Engine {
     void force(const std::string& what, const void* host, size_t bytes);
     size_t read(const std::string& what, void* host, size_t bytes);
     void set_capture(bool on) { capture_ = on; }
+    void set_batch_clips(int n) { batch_max_ = n < 1 ? 1 : (n > 8 ? 8 : n); }
     // per-launch CUDA-event timing of the conv/GEMM kernel family (bench.py roofline)
     void set_profile(bool on);
     void profile_read(double* out8);
@@ -89,6 +90,11 @@ class Engine {
 
    private:
     void forward_clip(const float* x_dev, int T, void* out_dev, int out_dtype);
+    // KEEP_FLAG_BATCH_CLIPS: nb clips advance through the per-frame recurrence in lockstep (one hq_encoder / code transformer /
+    // generator pass over a batch of nb per frame index)
+    void forward_clips(const float* x_dev, int nb, int T, void* out_dev, int out_dtype);
+    void forward_batched(const float* x_dev, int b, int T, void* out_dev, int out_dtype, cudaStream_t s);
+    size_t plan_clips(int nb, int T);
     void gmflow(const float* x_nchw, int T, float* flows);
     void gm_resblock(Tensor& x, Aff* x_aff, const std::string& p, int stride);
     void gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int nimg, bool shift, bool ffn);
@@ -118,7 +124,9 @@ class Engine {
     Arena* ar_ = &arena_;           // arena of the branch currently being enqueued
     cudaStream_t s_main_ = nullptr, side_ = nullptr;
     cudaEvent_t ev_fork_ = nullptr;
-    std::vector<cudaEvent_t> ev_flow_;   // one per GMFlow chunk of 4 pairs
+    std::vector<cudaEvent_t> ev_flow_;   // one per GMFlow chunk of 4 pairs (per clip in the lockstep mode)
+    int ev_flow_base_ = 0;               // first event of the clip whose GMFlow is being enqueued
+    int batch_max_ = 2;                  // KEEP_FLAG_BATCH_CLIPS: clips per lockstep group (KEEP_BATCH_MAX)
     size_t side_bytes_ = 0;
     int main_cap_ = 148;                 // grid cap of main-stream persistent kernels (lowered while GMFlow overlaps)
     int side_sms_ = 100;                  // grid cap of persistent kernels on the side branch

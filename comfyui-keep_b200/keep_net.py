@@ -35,6 +35,7 @@ FLAG_TCGEN05 = 2
 FLAG_TC_SPLIT3 = 4
 FLAG_CUDA_GRAPH = 8
 FLAG_TC_WIDE = 16
+FLAG_BATCH_CLIPS = 32
 FLAG_PLAN_ONLY = 256
 
 
@@ -68,6 +69,7 @@ def load_library():
     lib.keep_workspace_bytes.restype = cs
     lib.keep_forward.argtypes = [vp, vp, ci, ci, vp, ci, vp, cs, vp]
     lib.keep_forward_u8.argtypes = [vp, vp, ci, ci, vp, vp, cs, vp]
+    lib.keep_set_batch_clips.argtypes = [vp, ci]
     lib.keep_destroy.argtypes = [vp]
     lib.keep_launch_count.argtypes = [vp]
     lib.keep_launch_count.restype = ctypes.c_longlong
@@ -118,17 +120,21 @@ def config_name(cfg):
 class KeepNetB200(nn.Module):
     """Drop-in replacement for the reference `KEEP` module on the inference path."""
 
-    def __init__(self, flags=0, concurrent_clips=1, **cfg):
+    def __init__(self, flags=0, concurrent_clips=1, batch_clips=1, **cfg):
         """concurrent_clips > 1: a batch of b > 1 clips is spread over that many engine replicas, each on its
         own CUDA stream.  Clips are independent (keep_processor.py:263-270) and one clip's serial per-frame chain leaves most
         SMs idle most of the time, so two clips in flight raise the throughput of a stream of clips; results are bitwise those
         of the clip-by-clip loop."""
         super().__init__()
+        # batch_clips > 1 (the other half of N2): a batch of b > 1 clips goes to ONE engine, which walks groups of that many clips
+        # through the per-frame recurrence in lockstep (KEEP_FLAG_BATCH_CLIPS: one batched hq_encoder / transformer / generator
+        # pass per frame index).  Results equal the clip-by-clip loop up to fp32 summation order (different K-splits).
+        self._batch = max(1, min(8, int(batch_clips)))
         self._nrep = max(1, int(concurrent_clips))
         self._replicas = []           # extra engines (keep_handle) beyond the primary one, created on first use
         self._rep_streams = []
         self.config = config_name(cfg)   # 'KEEP' | 'Asian'; the engine reads the fusion points off the tensor names
-        self._flags = int(flags)
+        self._flags = int(flags) | (FLAG_BATCH_CLIPS if self._batch > 1 else 0)
         if self.config == "Asian" and (self._flags & FLAG_TC_SPLIT3):
             # four stacked CFT modulations (32^2 .. 256^2) leave raw generator features with no magnitude bound (6e4 with
             # the synthetic weights, past fp16's 65504): bf16 activation pairs on those layers (include/keep_b200.h)
@@ -196,6 +202,8 @@ class KeepNetB200(nn.Module):
         dev = self._device.index if self._device.type == "cuda" and self._device.index is not None else (
             torch.cuda.current_device() if self._device.type == "cuda" else 0)
         _check(lib, lib.keep_create(ctypes.byref(h), int(dev), descs, len(names), int(flags)), "keep_create")
+        if self._batch > 1:
+            _check(lib, lib.keep_set_batch_clips(h, self._batch), "keep_set_batch_clips")
         return h
 
     def to(self, *args, **kwargs):
@@ -265,7 +273,7 @@ class KeepNetB200(nn.Module):
         lib = load_library()
         odt = 1 if out_dtype == torch.float16 else 0
         b, T = int(x.shape[0]), int(x.shape[1])
-        if b > 1 and self._nrep > 1:
+        if b > 1 and self._nrep > 1 and self._batch <= 1:
             self._forward_concurrent(lib, x, out, odt)
             return out
         stream = torch.cuda.current_stream(x.device).cuda_stream

@@ -46,6 +46,9 @@ enum {
     KEEP_FLAG_TC_WIDE = 16,      /* with TC_SPLIT3: generator / CFT layers that read a raw (un-normalised) feature map take their
                                     activation operand as a bf16 pair (fp32 exponent range, 16 mantissa bits) instead of an fp16
                                     pair (22 bits, overflows beyond 65504) */
+    KEEP_FLAG_BATCH_CLIPS = 32,  /* keep_forward with b > 1: groups of clips (2 by default, KEEP_BATCH_MAX) advance through the
+                                    per-frame recurrence in lockstep -- one batched hq_encoder / code-transformer / generator pass
+                                    per frame index instead of one per clip; engine-owned workspace only */
     KEEP_FLAG_PLAN_ONLY = 256    /* host-side planning only (strict key check + workspace sizing); keep_forward fails */
 };
 
@@ -66,6 +69,10 @@ size_t keep_workspace_bytes(keep_handle h, int b, int T);
  * synchronisation inside. */
 int keep_forward(keep_handle h, const float* x_dev, int b, int T, void* out_dev, int out_dtype, void* workspace,
                  size_t workspace_bytes, void* stream);
+
+/* Clips per lockstep group for engines created with KEEP_FLAG_BATCH_CLIPS (default 2, or KEEP_BATCH_MAX; 1 = clip by clip).
+ * Replaces nothing in the reference: its caller loops over clips one at a time (keep_processor.py:263-270). */
+int keep_set_batch_clips(keep_handle h, int max_clips);
 
 /* Same path with the caller-side conversions folded in: x_u8_dev is (b, T, 512, 512, 3) uint8 BGR HWC --
  * the aligned crops as OpenCV holds them -- converted on the device exactly as keep_processor.py:258-260 does on the host
