@@ -236,6 +236,8 @@ static const int kFuseGen[6] = {6, 9, 12, 15, 18, 21};
 // construction
 // =============================================================================================
 Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : device_(device), flags_(flags) {
+    // KEEP_FORCE_FLAGS=<int>: OR extra engine flags in (A/B runs on the GPU box, e.g. 16 = KEEP_FLAG_TC_WIDE on the general config)
+    if (const char* e = getenv("KEEP_FORCE_FLAGS")) { flags |= atoi(e) & ~KEEP_FLAG_PLAN_ONLY; flags_ = flags; }
     dry_only_ = (flags & KEEP_FLAG_PLAN_ONLY) != 0;
     if (!dry_only_) {
         int ndev = 0;

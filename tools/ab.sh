@@ -1,11 +1,11 @@
 #!/bin/bash
 # A/B harness for the GPU box: each line = label + env assignments; prints frames/s of a short bench per setting.
-# usage: tools/ab.sh "label1|ENV=..;ENV2=.." "label2|..."
+# usage: tools/ab.sh "label1|ENV=..;ENV2=.." "label2|..."     (AB_BENCH_ARGS=<extra bench.py arguments> in a spec applies to that line)
 mkdir -p gpurun_out
 for spec in "$@"; do
   label="${spec%%|*}"; envs="${spec#*|}"
-  ( IFS=';'; for kv in $envs; do [ -n "$kv" ] && export "$kv"; done
-    timeout 240 python bench.py --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/ab_$label.json 2> gpurun_out/ab_$label.err
+  ( IFS=';'; for kv in $envs; do [ -n "$kv" ] && export "$kv"; done; unset IFS
+    timeout 240 python bench.py --no-cpu-baseline --steps 4 --warmup 3 $AB_BENCH_ARGS > gpurun_out/ab_$label.json 2> gpurun_out/ab_$label.err
     python - "$label" <<'P'
 import json,sys
 lab=sys.argv[1]

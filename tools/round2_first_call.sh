@@ -1,0 +1,19 @@
+#!/bin/bash
+# First gpurun call of a round: the whole GPU test tier (timed), the headline bench line, and the A/Bs left unmeasured
+# at the end of round 1 (lockstep clip batching, bf16 "wide" operands on the general config).  Everything lands in gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -q -m gpu -x ) > gpurun_out/r2_gpu_tests.log 2>&1
+tail -3 gpurun_out/r2_gpu_tests.log
+timeout 400 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
+tail -c 600 gpurun_out/r2_bench_n1.json
+bash tools/ab.sh \
+  "one_clip|" \
+  "replicas2_b4|AB_BENCH_ARGS=--clips-per-step 4" \
+  "lockstep2_b4|AB_BENCH_ARGS=--clips-per-step 4 --batch-clips 2" \
+  "lockstep4_b4|AB_BENCH_ARGS=--clips-per-step 4 --batch-clips 4" \
+  "lockstep2_b2|AB_BENCH_ARGS=--clips-per-step 2 --batch-clips 2" \
+  "wide_general|KEEP_FORCE_FLAGS=16" | tee gpurun_out/r2_ab.txt
+# parity of the wide flag on the general config (teacher-forced + free-running, tc3)
+KEEP_FORCE_FLAGS=16 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k tc3 > gpurun_out/r2_parity_wide_general.log 2>&1
+tail -3 gpurun_out/r2_parity_wide_general.log
