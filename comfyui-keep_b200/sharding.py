@@ -38,6 +38,29 @@ def run_clips(net, frames, max_clip_length):
     return torch.cat(outs, dim=1)
 
 
+def run_clips_batched(net, frames, max_clip_length, clips_per_call=4):
+    """Same result as `run_clips`, but the full-length clips go to the engine `clips_per_call` at a time as one
+    (b, T, 3, 512, 512) call, so a `KeepNetB200(concurrent_clips=...)` / `KeepNetB200(batch_clips=...)` engine can overlap
+    them; the shorter tail clip is its own call, a 1-frame tail is duplicated as in the reference."""
+    clips = split_clips(frames.shape[1], max_clip_length)
+    full = [c for c in clips if c[2] == max_clip_length and max_clip_length >= 2]
+    outs = {}
+    for g0 in range(0, len(full), max(1, clips_per_call)):
+        group = full[g0:g0 + max(1, clips_per_call)]
+        x = torch.cat([frames[:, s:e] for s, e, _ in group], dim=0)          # (b, T, 3, 512, 512)
+        y = net(x, need_upscale=False)
+        for j, (s, e, keep) in enumerate(group):
+            outs[s] = y[j:j + 1, :keep]
+    for s, e, keep in clips:
+        if s in outs:
+            continue
+        clip = frames[:, s:e]
+        if clip.shape[1] == 1:
+            clip = torch.cat([clip, clip], dim=1)
+        outs[s] = net(clip, need_upscale=False)[:, :keep]
+    return torch.cat([outs[s] for s, _, _ in clips], dim=1) if clips else frames[:, :0]
+
+
 def run_clips_sharded(net, frames, max_clip_length, group=None, gather_dtype=torch.float16):
     """Every rank holds `frames`; rank r runs clips k with k % world == r; rank 0 returns the reassembled sequence
     (other ranks return None).  One gather per round of `world` clips."""

@@ -175,3 +175,20 @@ def test_vector_quantize_has_no_cpu_fallback(keep_mod, state_dict):
     cb = state_dict["quantize.embedding.weight"]
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         keep_mod.vector_quantize(torch.zeros(1, 256, 16, 16), cb)
+
+
+# ---- lockstep clip batching: host-side plan ------------------------------------------------------------
+
+def test_lockstep_plan_only_engine(keep_mod, lib, state_dict):
+    kn = keep_mod.keep_net
+    net = keep_mod.KeepNetB200(batch_clips=2)
+    assert net._flags & kn.FLAG_BATCH_CLIPS
+    net.load_state_dict(state_dict, strict=True)
+    h = net._make_engine(flags=256 | kn.FLAG_BATCH_CLIPS | kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3)
+    w1, w2, w3 = (lib.keep_workspace_bytes(h, b, 20) for b in (1, 2, 3))
+    assert 0 < w1 < w2 == w3 < 2 * w1          # groups of 2: resident taps / latents double, the encoder passes do not
+    assert lib.keep_set_batch_clips(h, 4) == 0
+    assert lib.keep_workspace_bytes(h, 4, 20) > w2
+    assert lib.keep_set_batch_clips(h, 0) != 0 and b"max_clips" in lib.keep_last_error()
+    assert lib.keep_set_batch_clips(None, 2) != 0
+    net._drop_engine()

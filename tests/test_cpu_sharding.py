@@ -30,6 +30,26 @@ class _FakeNet:
         return x * 2.0 + t * 1e-3
 
 
+@pytest.mark.parametrize("n_frames,clip_len,per_call", [(7, 3, 2), (9, 2, 4), (4, 4, 4), (5, 1, 3), (41, 20, 2)])
+def test_batched_clip_runner_equals_the_reference_loop(keep_mod, n_frames, clip_len, per_call):
+    sh = keep_mod.sharding
+    g = torch.Generator().manual_seed(1)
+    frames = torch.rand((1, n_frames, 3, 8, 8), generator=g)
+    calls = []
+
+    class Net(_FakeNet):
+        def __call__(self, x, need_upscale=False):
+            calls.append(tuple(x.shape[:2]))
+            return super().__call__(x, need_upscale)
+
+    out = sh.run_clips_batched(Net(), frames, clip_len, clips_per_call=per_call)
+    ref = sh.run_clips(_FakeNet(), frames, clip_len)
+    assert torch.equal(out, ref)
+    assert max(b for b, _ in calls) <= per_call
+    if clip_len >= 2 and n_frames >= 2 * clip_len and per_call >= 2:
+        assert any(b > 1 for b, _ in calls)        # full-length clips really went in together
+
+
 def _worker(rank, world, port, n_frames, clip_len, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
