@@ -188,6 +188,28 @@ void Engine::pack_weights(const keep_weight_desc* w, int n_w) {
             }
         } else if (d->ndim == 2) {
             add_arr(key, pack_oihw(d->data, (int)d->shape[0], (int)d->shape[1], 1, 1), (int)d->shape[1], (int)d->shape[0], 1, 1);
+            // GMFlow attention projections (gmflow/transformer.py:117-119, bias-free): fused copies q|k|v (self-attention:
+            // one source) and k|v (cross-attention: both read the target) -> one N = 3C / 2C GEMM that converts the
+            // activations once (A-stationary walk over the N tiles) instead of three / two times (KEEP_GM_FUSE_QKV=1)
+            if (ends_with(key, ".q_proj.weight") && key.find("flownet.") == 0) {
+                const std::string base = key.substr(0, key.size() - strlen("q_proj.weight"));
+                auto kq = by_name.find(base + "k_proj.weight"), vq = by_name.find(base + "v_proj.weight");
+                if (kq != by_name.end() && vq != by_name.end() && kq->second->ndim == 2 && vq->second->ndim == 2 &&
+                    kq->second->shape[0] == d->shape[0] && vq->second->shape[0] == d->shape[0] &&
+                    kq->second->shape[1] == d->shape[1] && vq->second->shape[1] == d->shape[1]) {
+                    const int C = (int)d->shape[1], O = (int)d->shape[0];
+                    std::vector<float> qkv((size_t)C * 3 * O), kv((size_t)C * 2 * O);
+                    const float* src[3] = {d->data, kq->second->data, vq->second->data};
+                    for (int t = 0; t < 3; ++t)
+                        for (int o = 0; o < O; ++o)
+                            for (int c = 0; c < C; ++c) {
+                                qkv[(size_t)c * 3 * O + t * O + o] = src[t][(size_t)o * C + c];
+                                if (t > 0) kv[(size_t)c * 2 * O + (t - 1) * O + o] = src[t][(size_t)o * C + c];
+                            }
+                    add_arr(base + "qkv_proj.weight", qkv, C, 3 * O, 1, 1);
+                    add_arr(base + "kv_proj.weight", kv, C, 2 * O, 1, 1);
+                }
+            }
         } else {
             add_arr(key, std::vector<float>(d->data, d->data + ne), (int)d->shape[0]);
         }
@@ -743,16 +765,34 @@ void Engine::gm_resblock(Tensor& x, Aff* x_aff, const std::string& p, int stride
 // gmflow/transformer.py:147-185 on tokens (nimg, 4096, 128); windows 2x2, optional half-window shift
 void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int nimg, bool shift, bool ffn) {
     const int C = 128, H = 64, Wd = 64, k = 2, L = 1024;
-    Tensor q = linear(src, p + ".q_proj"), kk = linear(tgt, p + ".k_proj"), v = linear(tgt, p + ".v_proj");
+    // KEEP_GM_FUSE_QKV=1 (experiment, default off until measured): q|k|v (self) / k|v (cross) as one GEMM over fused weights
+    static const bool fuse = getenv("KEEP_GM_FUSE_QKV") != nullptr && atoi(getenv("KEEP_GM_FUSE_QKV")) != 0;
+    const bool fuse_here = fuse && has(p + ".qkv_proj.weight") && has(p + ".kv_proj.weight");
+    Tensor q, kk, v;           // q / k / v projections: separate tensors, or strided views into one fused GEMM output
+    const float *qp, *kp, *vp;
+    int ldq = C, ldkv = C;
+    if (fuse_here && src.p == tgt.p) {
+        q = linear(src, p + ".qkv_proj");
+        qp = q.f(); kp = q.f() + C; vp = q.f() + 2 * C; ldq = ldkv = 3 * C;
+    } else if (fuse_here) {
+        q = linear(src, p + ".q_proj");
+        kk = linear(tgt, p + ".kv_proj");
+        qp = q.f(); kp = kk.f(); vp = kk.f() + C; ldkv = 2 * C;
+    } else {
+        q = linear(src, p + ".q_proj"); kk = linear(tgt, p + ".k_proj"); v = linear(tgt, p + ".v_proj");
+        qp = q.f(); kp = kk.f(); vp = v.f();
+    }
     Tensor qw = talloc(nimg * 4, L, 1, C, F32), kw = talloc(nimg * 4, L, 1, C, F32), vw = talloc(nimg * 4, L, 1, C, F32);
     const int sh = shift ? 16 : 0;
     if (!ar_->dry()) {
-        window_partition(q.f(), qw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
-        window_partition(kk.f(), kw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
-        window_partition(v.f(), vw.f(), nimg, H, Wd, C, k, sh, sh, C, s_);
+        window_partition(qp, qw.f(), nimg, H, Wd, C, k, sh, sh, ldq, s_);
+        window_partition(kp, kw.f(), nimg, H, Wd, C, k, sh, sh, ldkv, s_);
+        window_partition(vp, vw.f(), nimg, H, Wd, C, k, sh, sh, ldkv, s_);
         launches_ += 3;
     }
-    tfree(q); tfree(kk); tfree(v);
+    tfree(q);
+    if (kk.p) tfree(kk);
+    if (v.p) tfree(v);
     Tensor S, Ow;
     if (flags_ & KEEP_FLAG_TCGEN05) {
         // window attention on the tensor cores: S = (Q K^T)/sqrt(C), softmax (+ shift mask), O = P V

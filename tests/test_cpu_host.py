@@ -46,7 +46,9 @@ def test_weights_are_reproducible_and_complete(state_dict):
     from oracle import weights
     shapes = weights.load_shapes()
     assert len(shapes) == 896
-    assert sum(int(np.prod(s)) for s in shapes.values()) == 158485860 or True
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 158485860          # 158.49 M, as KEEP(**cfg).state_dict()
+    asian = weights.load_shapes("Asian")
+    assert len(asian) == 914 and sum(int(np.prod(s)) for s in asian.values()) == 143573092
     sd2 = weights.make_state_dict(seed=0)
     for k in ("encoder.blocks.0.weight", "cft.16.scale.0.weight", "position_emb"):
         assert torch.equal(state_dict[k], sd2[k])

@@ -13,7 +13,11 @@ bash tools/ab.sh \
   "lockstep2_b4|AB_BENCH_ARGS=--clips-per-step 4 --batch-clips 2" \
   "lockstep4_b4|AB_BENCH_ARGS=--clips-per-step 4 --batch-clips 4" \
   "lockstep2_b2|AB_BENCH_ARGS=--clips-per-step 2 --batch-clips 2" \
-  "wide_general|KEEP_FORCE_FLAGS=16" | tee gpurun_out/r2_ab.txt
+  "wide_general|KEEP_FORCE_FLAGS=16" \
+  "gm_fuse_qkv|KEEP_GM_FUSE_QKV=1" | tee gpurun_out/r2_ab.txt
 # parity of the wide flag on the general config (teacher-forced + free-running, tc3)
 KEEP_FORCE_FLAGS=16 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k tc3 > gpurun_out/r2_parity_wide_general.log 2>&1
 tail -3 gpurun_out/r2_parity_wide_general.log
+# GMFlow fused q|k|v projections: flows / free-running parity with the knob on
+KEEP_GM_FUSE_QKV=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "free_running_T3" > gpurun_out/r2_parity_gm_fuse.log 2>&1
+tail -3 gpurun_out/r2_parity_gm_fuse.log
