@@ -60,6 +60,7 @@ CASES = (  # fixture name, model config, T, coherent clip, clip seed
     ("T3_coherent", "KEEP", 3, True, 1234),
     ("T2_noise", "KEEP", 2, False, 1234),
     ("asian_T2_coherent", "Asian", 2, True, 1234),   # CFT at 32/64/128/256, none at 16
+    ("T20_coherent", "KEEP", 20, True, 1234),        # BASELINE.json configs[1] at full size (compact fixture, see below)
 )
 
 
@@ -148,6 +149,24 @@ def main():
             }
         report["cases"][name] = case
         print(name, json.dumps(case, indent=1))
+        if T > 8:
+            # full-size clip: compact fixture -- stride-8 pixels of every frame, a full-resolution crop of three frames, the
+            # discrete decisions with their margins, the gains (temporal attention over all T frames) and per-frame
+            # latent statistics plus the first / last latents in full
+            zc = ref_cap["z_codes"].reshape(T, 256, 16, 16)
+            np.savez_compressed(
+                os.path.join(GOLD, "ref_%s.npz" % name),
+                out_sub8=ref_out[:, :, :, ::8, ::8].numpy().astype(np.float32),
+                out_crop=ref_out[:, [0, T // 2, T - 1], :, 192:320, 192:320].numpy().astype(np.float32),
+                out_mean=ref_out.double().mean(dim=(2, 3, 4)).numpy(),
+                gains=ref_cap["gains"].numpy().astype(np.float32),
+                codes=ref_cap["codes"].numpy().astype(np.int16),
+                logit_top2=top2.numpy().astype(np.float32),
+                z_mean=zc.double().mean(dim=(1, 2, 3)).numpy(), z_sqmean=(zc.double() ** 2).mean(dim=(1, 2, 3)).numpy(),
+                z_first=zc[0].numpy().astype(np.float32), z_last=zc[T - 1].numpy().astype(np.float32),
+                flows_sub16=ref_cap["flows"].reshape(1, T - 1, 2, 512, 512)[:, :, :, ::16, ::16].numpy().astype(np.float32),
+            )
+            continue
         # fixtures: full-res output is 3 MB/frame fp32 -> keep a stride-4 subsample + fp16 copy of frame 0 crop
         np.savez_compressed(
             os.path.join(GOLD, "ref_%s.npz" % name),
