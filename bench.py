@@ -184,7 +184,7 @@ def main():
     B = max(1, args.clips_per_step)
     batch = min(B, max(1, args.batch_clips))
     net = keep_b200.KeepNetB200(flags=flags, batch_clips=batch,
-                                concurrent_clips=min(B, int(os.environ.get("KEEP_BENCH_REPLICAS", "2"))) if (B > 1 and batch <= 1) else 1)
+                                concurrent_clips=min(B, int(os.environ.get("KEEP_BENCH_REPLICAS", "2"))) if (B > 1 and B > batch) else 1)
     net.load_state_dict(keep_b200.synth.make_state_dict(seed=0), strict=True)
     net.eval().to(dev)
     x_host = torch.cat([keep_b200.synth.make_clip(T, seed=1234 + rank + 100 * i, coherent=True) for i in range(B)], 0).pin_memory()
@@ -338,7 +338,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[mode], "data": "synthetic",
             "config": {"workload": "KEEP general model, %d-frame aligned 512x512 synthetic clip, %s per GPU per step" % (
-                           T, "one clip" if B == 1 else ("%d independent clips (lockstep groups of %d inside one engine)" % (B, batch) if batch > 1
+                           T, "one clip" if B == 1 else ("%d independent clips (lockstep groups of %d%s)" % (B, batch, ", groups on engine replicas" if B > batch else " inside one engine") if batch > 1
                                                      else "%d independent clips (two in flight on engine replicas)" % B)),
                        "weights": "seeded synthetic (no checkpoint offline)", "engine_mode": mode,
                        "cuda_graph": not args.no_graph,

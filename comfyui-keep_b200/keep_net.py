@@ -273,7 +273,7 @@ class KeepNetB200(nn.Module):
         lib = load_library()
         odt = 1 if out_dtype == torch.float16 else 0
         b, T = int(x.shape[0]), int(x.shape[1])
-        if b > 1 and self._nrep > 1 and self._batch <= 1:
+        if b > 1 and self._nrep > 1 and b > self._batch:
             self._forward_concurrent(lib, x, out, odt)
             return out
         stream = torch.cuda.current_stream(x.device).cuda_stream
@@ -283,8 +283,11 @@ class KeepNetB200(nn.Module):
         return out
 
     def _forward_concurrent(self, lib, x, out, odt):
-        """clip i -> engine replica i % R on stream i % R; the caller's stream waits for all of them."""
-        R = min(self._nrep, int(x.shape[0]))
+        """clip group j (one clip, or `batch_clips` clips that the engine walks in lockstep) -> engine replica j % R on stream
+        j % R; the caller's stream waits for all of them."""
+        G = self._batch
+        ngroups = (int(x.shape[0]) + G - 1) // G
+        R = min(self._nrep, ngroups)
         with torch.cuda.device(x.device):
             while len(self._replicas) < R - 1:
                 self._replicas.append(self._make_engine())
@@ -295,9 +298,10 @@ class KeepNetB200(nn.Module):
             per_in, per_out = x[0].numel() * x.element_size(), out[0].numel() * out.element_size()
             for r in range(R):
                 self._rep_streams[r].wait_stream(cur)
-            for i in range(int(x.shape[0])):
-                st = self._rep_streams[i % R]
-                rc = lib.keep_forward(engines[i % R], x.data_ptr() + i * per_in, 1, int(x.shape[1]), out.data_ptr() + i * per_out,
+            for j in range(ngroups):
+                i, n = j * G, min(G, int(x.shape[0]) - j * G)
+                st = self._rep_streams[j % R]
+                rc = lib.keep_forward(engines[j % R], x.data_ptr() + i * per_in, n, int(x.shape[1]), out.data_ptr() + i * per_out,
                                       odt, None, 0, ctypes.c_void_p(st.cuda_stream))
                 _check(lib, rc, "keep_forward")
             for r in range(R):

@@ -10,7 +10,8 @@ tail -c 600 gpurun_out/r2_bench_n1.json
 bash tools/ab.sh \
   "one_clip|" \
   "replicas2_b4|AB_BENCH_ARGS=--clips-per-step 4" \
-  "lockstep2_b4|AB_BENCH_ARGS=--clips-per-step 4 --batch-clips 2" \
+  "lockstep2_b4_seq|KEEP_BENCH_REPLICAS=1;AB_BENCH_ARGS=--clips-per-step 4 --batch-clips 2" \
+  "lockstep2_b4_rep2|AB_BENCH_ARGS=--clips-per-step 4 --batch-clips 2" \
   "lockstep4_b4|AB_BENCH_ARGS=--clips-per-step 4 --batch-clips 4" \
   "lockstep2_b2|AB_BENCH_ARGS=--clips-per-step 2 --batch-clips 2" \
   "wide_general|KEEP_FORCE_FLAGS=16" \
