@@ -849,11 +849,12 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
 }
 
 // x_nchw: (T,3,512,512) fp32 in [-1,1]; flows: (T-1,512,512,2), pair i = flow(frame i+1 -> frame i)  (keep_arch.py:976-986)
-void Engine::gmflow(const float* x_nchw, int T, float* flows) {
+void Engine::gmflow(const float* x_nchw, int T, float* flows, int p_lo, int p_hi) {
     const std::string P = "flownet.model";
     const int HW = 512 * 512;
     const int chunk = flow_chunk();
-    for (int p0 = 0; p0 < T - 1; p0 += chunk) {
+    const int p_end = p_hi < 0 ? T - 1 : std::min(T - 1, p_hi);   // pairs [p_lo, p_end), p_lo a multiple of the chunk size
+    for (int p0 = p_lo; p0 < p_end; p0 += chunk) {
         const int np = std::min(chunk, T - 1 - p0);
         // images: [img0 = frames p0+1 .. p0+np | img1 = frames p0 .. p0+np-1], ImageNet-normalised NHWC
         Tensor img = talloc(2 * np, 512, 512, 3, F32);
@@ -1433,10 +1434,13 @@ void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int
         s_ = side_;
     }
     ar_ = &arena2_;
-    for (int c = 0; c < nb; ++c) {
-        ev_flow_base_ = c * nchunk;
-        gmflow(x_dev + (size_t)c * per_clip_in, T, flows[c].f());
-    }
+    // chunk-major order: frame i of the lockstep group needs pair i-1 of EVERY clip, so chunk k of all clips goes before
+    // chunk k+1 of any (clip-major order would hold frame 1 back until nearly all of the group's GMFlow work is done)
+    for (int p0 = 0; p0 < T - 1; p0 += flow_chunk())
+        for (int c = 0; c < nb; ++c) {
+            ev_flow_base_ = c * nchunk;
+            gmflow(x_dev + (size_t)c * per_clip_in, T, flows[c].f(), p0, p0 + flow_chunk());
+        }
     ev_flow_base_ = 0;
     ar_ = &arena_;
     s_ = s_main_;

@@ -95,7 +95,7 @@ class Engine {
     void forward_clips(const float* x_dev, int nb, int T, void* out_dev, int out_dtype);
     void forward_batched(const float* x_dev, int b, int T, void* out_dev, int out_dtype, cudaStream_t s);
     size_t plan_clips(int nb, int T);
-    void gmflow(const float* x_nchw, int T, float* flows);
+    void gmflow(const float* x_nchw, int T, float* flows, int p_lo = 0, int p_hi = -1);
     void gm_resblock(Tensor& x, Aff* x_aff, const std::string& p, int stride);
     void gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int nimg, bool shift, bool ffn);
     Tensor kalman_gains(const Tensor& z_codes, int T);
