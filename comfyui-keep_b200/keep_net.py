@@ -120,7 +120,7 @@ def config_name(cfg):
 class KeepNetB200(nn.Module):
     """Drop-in replacement for the reference `KEEP` module on the inference path."""
 
-    def __init__(self, flags=0, concurrent_clips=1, batch_clips=1, **cfg):
+    def __init__(self, flags=0, concurrent_clips=1, batch_clips=1, check_finite=False, **cfg):
         """concurrent_clips > 1: a batch of b > 1 clips is spread over that many engine replicas, each on its
         own CUDA stream.  Clips are independent (keep_processor.py:263-270) and one clip's serial per-frame chain leaves most
         SMs idle most of the time, so two clips in flight raise the throughput of a stream of clips; results are bitwise those
@@ -129,6 +129,10 @@ class KeepNetB200(nn.Module):
         # batch_clips > 1 (the other half of N2): a batch of b > 1 clips goes to ONE engine, which walks groups of that many clips
         # through the per-frame recurrence in lockstep (KEEP_FLAG_BATCH_CLIPS: one batched hq_encoder / transformer / generator
         # pass per frame index).  Results equal the clip-by-clip loop up to fp32 summation order (different K-splits).
+        # check_finite: after every call, one reduction over the output + a host sync; raises instead of handing inf / NaN frames
+        # to the caller (the fp16-pair tensor-core mode overflows on raw features beyond 65504 -- see KEEP_FLAG_TC_WIDE).  Off by
+        # default: the call contract is "no host synchronisation inside forward" (SURVEY.md §8b).
+        self._check_finite = bool(check_finite)
         self._batch = max(1, min(8, int(batch_clips)))
         self._nrep = max(1, int(concurrent_clips))
         self._replicas = []           # extra engines (keep_handle) beyond the primary one, created on first use
@@ -275,11 +279,14 @@ class KeepNetB200(nn.Module):
         b, T = int(x.shape[0]), int(x.shape[1])
         if b > 1 and self._nrep > 1 and b > self._batch:
             self._forward_concurrent(lib, x, out, odt)
-            return out
-        stream = torch.cuda.current_stream(x.device).cuda_stream
-        with torch.cuda.device(x.device):
-            rc = lib.keep_forward(self._engine, x.data_ptr(), b, T, out.data_ptr(), odt, None, 0, ctypes.c_void_p(stream))
-        _check(lib, rc, "keep_forward")
+        else:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            with torch.cuda.device(x.device):
+                rc = lib.keep_forward(self._engine, x.data_ptr(), b, T, out.data_ptr(), odt, None, 0, ctypes.c_void_p(stream))
+            _check(lib, rc, "keep_forward")
+        if self._check_finite and not bool(torch.isfinite(out).all()):
+            raise RuntimeError("KeepNetB200: non-finite values in the restored frames (engine flags %d); if the network's raw "
+                               "features exceed fp16 range, create the engine with FLAG_TC_WIDE" % self._flags)
         return out
 
     def _forward_concurrent(self, lib, x, out, odt):
