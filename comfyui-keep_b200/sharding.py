@@ -90,3 +90,42 @@ def run_clips_sharded(net, frames, max_clip_length, group=None, gather_dtype=tor
     if rank == 0:
         return torch.cat(result, dim=1)
     return None
+
+
+def run_clips_sharded_batched(net, frames, max_clip_length, group=None, gather_dtype=torch.float16):
+    """Config 5 of BASELINE.json (a long stream, clips round-robin over the ranks) with each rank's clips handed to its
+    engine in ONE call, so `KeepNetB200(batch_clips=...)` / `(concurrent_clips=...)` overlap them, and ONE
+    gather of all decoded frames at the end instead of one per round.  Every rank holds `frames`; rank 0 returns the
+    reassembled (1, N, 3, 512, 512) sequence, other ranks None.  Same result as `run_clips`."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    clips = split_clips(frames.shape[1], max_clip_length)
+    owner = assign_round_robin(len(clips), world)
+    slots = [[k for k in range(len(clips)) if owner[k] == r] for r in range(world)]   # rank r's clips, in order
+    mine = slots[rank]
+    outs = {}
+    full = [k for k in mine if clips[k][2] == max_clip_length and max_clip_length >= 2]
+    if full:
+        y = net(torch.cat([frames[:, clips[k][0]:clips[k][1]] for k in full], dim=0), need_upscale=False)
+        for j, k in enumerate(full):
+            outs[k] = y[j:j + 1]
+    for k in mine:
+        if k in outs:
+            continue
+        s, e, keep = clips[k]
+        clip = frames[:, s:e]
+        if clip.shape[1] == 1:
+            clip = torch.cat([clip, clip], dim=1)
+        outs[k] = net(clip, need_upscale=False)[:, :keep]
+    per_rank = max(1, max(len(sl) for sl in slots))
+    T = max(2, max_clip_length)
+    buf = torch.zeros((per_rank, T) + tuple(frames.shape[2:]), dtype=gather_dtype, device=frames.device)
+    for j, k in enumerate(mine):
+        buf[j, :clips[k][2]] = outs[k][0].to(gather_dtype)
+    gathered = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    if not clips:
+        return frames[:, :0].to(gather_dtype)
+    return torch.cat([gathered[owner[k]][slots[owner[k]].index(k), :clips[k][2]].unsqueeze(0) for k in range(len(clips))], dim=1)

@@ -58,14 +58,25 @@ def _worker(rank, world, port, n_frames, clip_len, q):
     g = torch.Generator().manual_seed(0)
     frames = torch.rand((1, n_frames, 3, 512, 512), generator=g)[:, :, :, :8, :8].repeat(1, 1, 1, 64, 64)
     out = keep_b200.sharding.run_clips_sharded(_FakeNet(), frames, clip_len, gather_dtype=torch.float32)
+    calls = []
+
+    class Net(_FakeNet):
+        def __call__(self, x, need_upscale=False):
+            calls.append(int(x.shape[0]))
+            return super().__call__(x, need_upscale)
+
+    out2 = keep_b200.sharding.run_clips_sharded_batched(Net(), frames, clip_len, gather_dtype=torch.float32)
     if rank == 0:
         ref = keep_b200.sharding.run_clips(_FakeNet(), frames, clip_len)
-        q.put((tuple(out.shape), bool(torch.equal(out, ref))))
+        n_full_mine = len([k for k, c in enumerate(keep_b200.sharding.split_clips(n_frames, clip_len))
+                           if k % world == 0 and c[2] == clip_len and clip_len >= 2])
+        batched_ok = (max(calls) if calls else 0) == max(1, n_full_mine)       # rank 0's full clips went in as one call
+        q.put((tuple(out.shape), bool(torch.equal(out, ref)) and bool(torch.equal(out2, ref)) and batched_ok))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames,clip_len", [(7, 3), (5, 2), (4, 4)])
+@pytest.mark.parametrize("n_frames,clip_len", [(7, 3), (5, 2), (4, 4), (13, 2)])
 def test_sharded_equals_single_process_gloo_world2(n_frames, clip_len):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
