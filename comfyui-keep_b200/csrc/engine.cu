@@ -341,7 +341,8 @@ Engine::~Engine() {
     cudaFree(own_ws_);
     for (auto& kv : cap_) cudaFree(kv.second.p);
     for (auto& kv : forced_) cudaFree(kv.second.p);
-    for (auto& kv : tcw_) cudaFree(kv.second.p);
+    for (auto& kv : tcw_)
+        for (auto& v : kv.second) cudaFree(v.p);
     for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
     cudaFree(gx_);
     cudaFree(gout_);
@@ -500,8 +501,9 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
 }
 
 const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide) {
-    auto it = tcw_.find(cw.w);
-    if (it != tcw_.end() && it->second.bn == bn && it->second.passes == passes && it->second.wide == wide) return it->second.p;
+    std::vector<TcW>& variants = tcw_[cw.w];
+    for (const TcW& v : variants)
+        if (v.bn == bn && v.passes == passes && v.wide == wide) return v.p;
     TcW t;
     t.bn = bn; t.passes = passes; t.wide = wide;
     const int cb = tc_cb(passes);
@@ -509,11 +511,7 @@ const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pa
     const int vtaps = s2d_pad >= 0 ? 4 : cw.kh * cw.kw;
     CUDA_CHECK(cudaMalloc((void**)&t.p, tc_packed_weight_halfs(vcin, cw.cout, vtaps, bn, passes) * sizeof(__half)));
     tc_repack_device(cw.w, cw.cin, cw.cout, cw.kh * cw.kw, bn, passes, s2d_pad, t.p, s_, wide);
-    if (it != tcw_.end()) {
-        CUDA_CHECK(cudaStreamSynchronize(s_));
-        cudaFree(it->second.p);
-    }
-    tcw_[cw.w] = t;
+    variants.push_back(t);
     return t.p;
 }
 

@@ -136,9 +136,10 @@ class Engine {
     // engine-owned workspace (used when the caller passes none)
     void* own_ws_ = nullptr; size_t own_ws_bytes_ = 0;
     std::unordered_map<int, size_t> ws_cache_;
-    // tcgen05 path: fp16 weight panels, packed on first use, keyed by (fp32 weight pointer, N tile)
+    // tcgen05 path: fp16 weight panels, packed on first use, keyed by the fp32 weight pointer; variants are kept (a layer can be
+    // asked for a second N tile when the per-clip and the lockstep path alternate), nothing is freed before the engine dies
     struct TcW { __half* p = nullptr; int bn = 0, passes = 0, wide = 0; };
-    std::unordered_map<const float*, TcW> tcw_;
+    std::unordered_map<const float*, std::vector<TcW>> tcw_;   // every (N tile, passes, wide) variant a layer has been run with
     const __half* tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide = 0);
     bool wide_scope_ = false; // KEEP_FLAG_TC_WIDE and inside generator(): raw-input feature-map layers use bf16 activation pairs
     int pass_override_ = 0;   // != 0: operand passes for the layers being enqueued (generator tail experiment)
