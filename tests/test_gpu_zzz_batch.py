@@ -4,13 +4,22 @@ A batch of b > 1 clips handed to ONE engine walks the per-frame recurrence in lo
 transformer / generator pass per frame index).  Clips are independent in the reference (keep_processor.py:263-270), so the
 result must equal the clip-by-clip loop -- up to fp32 summation order (a batch of two picks different K-splits), i.e. to
 the pixel bar (max-abs <= 1e-2 on clamped pixels) until a code index flips at a near-tie of the per-clip run's own logits."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NEAR_TIE = 2e-2
+
+
+def _report(tag, **kw):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.txt"), "a") as f:
+        f.write(tag + " " + " ".join("%s=%s" % (k, v) for k, v in kw.items()) + "\n")
 
 
 def _make(keep_mod, state_dict, mode, **kw):
@@ -56,6 +65,10 @@ def test_lockstep_pair_matches_clip_by_clip(keep_mod, state_dict, mode):
     net = _make(keep_mod, state_dict, mode, batch_clips=2)
     out = net(x, need_upscale=False).cpu()
     assert out.shape == ref.shape and bool(torch.isfinite(out).all())
+    _report("lockstep_pair[%s]" % mode,
+            maxabs_per_clip_frame=[["%.2e" % float((out[c, i].clamp(-1, 1) - ref[c, i].clamp(-1, 1)).abs().max()) for i in range(T)]
+                                   for c in range(b)],
+            min_margin=[["%.2e" % float(margins[c][i].min()) for i in range(T)] for c in range(b)])
     _compare(out, ref, margins, "lockstep[%s]" % mode)
     # frame 0 has no recurrence behind it and the LQ encoder runs clip by clip on both paths: tight agreement
     assert float((out[:, 0] - ref[:, 0]).abs().max()) < 5e-3
@@ -81,6 +94,7 @@ def test_lockstep_odd_clip_graph_replay_and_u8(keep_mod, state_dict):
     want = torch.cat([single.forward_u8(u8[c:c + 1]) for c in range(b)], 0)
     assert got.shape == want.shape and got.dtype == torch.uint8
     close = ((got.int() - want.int()).abs() <= 1).float().mean()
+    _report("lockstep_u8", within_1_lsb=float(close), exact=float((got == want).float().mean()))
     assert float(close) > 0.98, "uint8 lockstep output differs from the clip-by-clip loop on %.3f of the bytes" % (1 - float(close))
     net.to("cpu")
     single.to("cpu")
