@@ -22,3 +22,8 @@ tail -3 gpurun_out/r2_parity_wide_general.log
 # GMFlow fused q|k|v projections: flows / free-running parity with the knob on
 KEEP_GM_FUSE_QKV=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "free_running_T3" > gpurun_out/r2_parity_gm_fuse.log 2>&1
 tail -3 gpurun_out/r2_parity_gm_fuse.log
+# where a lockstep frame's time goes (single stream: no GMFlow), next to the per-clip timeline
+KEEP_DEBUG_SKIP_FLOW=1 timeout 300 python tools/timeline.py --frames 4 --out gpurun_out/r2_tl_single > gpurun_out/r2_timeline_single.txt 2>&1
+KEEP_DEBUG_SKIP_FLOW=1 timeout 300 python tools/timeline.py --frames 4 --clips 2 --batch-clips 2 --out gpurun_out/r2_tl_lock2 > gpurun_out/r2_timeline_lockstep2.txt 2>&1
+KEEP_DEBUG_SKIP_FLOW=1 timeout 300 python tools/timeline.py --frames 4 --clips 4 --batch-clips 4 --out gpurun_out/r2_tl_lock4 > gpurun_out/r2_timeline_lockstep4.txt 2>&1
+tail -n +1 gpurun_out/r2_timeline_lockstep2.txt | head -40

@@ -8,16 +8,19 @@ import torch, keep_b200
 
 ap = argparse.ArgumentParser(); ap.add_argument("--frames", type=int, default=4); ap.add_argument("--mode", default="tc3")
 ap.add_argument("--out", default="gpurun_out/timeline")
+ap.add_argument("--clips", type=int, default=1, help="clips per call; with --batch-clips N they walk the recurrence in lockstep groups of N")
+ap.add_argument("--batch-clips", type=int, default=1)
 a = ap.parse_args()
 assert os.environ.get("KEEP_DEBUG_SKIP_FLOW") or os.environ.get("KEEP_NO_SIDE"), "set KEEP_DEBUG_SKIP_FLOW=1 or KEEP_NO_SIDE=1 (the timeline needs a single stream)"
 kn = keep_b200.keep_net
 lib = kn.load_library()
 flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3}[a.mode]
 sd = keep_b200.synth.make_state_dict(0)
-x = keep_b200.synth.make_clip(a.frames, seed=1234).cuda()
+x = torch.cat([keep_b200.synth.make_clip(a.frames, seed=1234 + 100 * i) for i in range(a.clips)], 0).cuda()
+bk = dict(batch_clips=min(a.clips, a.batch_clips)) if a.batch_clips > 1 else {}
 
 # 1. names: eager engine, launch log on for the third clip (weights packed, arenas warm)
-eager = keep_b200.KeepNetB200(flags=flags); eager.load_state_dict(sd); eager.eval().to("cuda")
+eager = keep_b200.KeepNetB200(flags=flags, **bk); eager.load_state_dict(sd); eager.eval().to("cuda")
 eager(x, need_upscale=False); eager(x, need_upscale=False); torch.cuda.synchronize()
 lib.keepop_launch_log(1)
 eager(x, need_upscale=False); torch.cuda.synchronize()
@@ -27,7 +30,7 @@ names = [l.rstrip("\n").split("\t") for l in open(a.out + "_names.txt")]
 del eager
 
 # 2. stamps: graph engine, replay once with the stamp buffer set
-net = keep_b200.KeepNetB200(flags=flags | kn.FLAG_CUDA_GRAPH); net.load_state_dict(sd); net.eval().to("cuda")
+net = keep_b200.KeepNetB200(flags=flags | kn.FLAG_CUDA_GRAPH, **bk); net.load_state_dict(sd); net.eval().to("cuda")
 for _ in range(4): net(x, need_upscale=False)
 torch.cuda.synchronize()
 buf = torch.zeros(1 + 65536, dtype=torch.int64, device="cuda")
@@ -46,13 +49,14 @@ with open(a.out + "_slots.csv", "w") as f:
     f.write("idx,kernel,grid,block,start_us,slot_us\n")
     for i in range(n): f.write("%d,%s,%s,%s,%.3f,%.3f\n" % (i, names[i][0].replace(",", ";"), names[i][1].replace(",", "x"), names[i][2], (st[i] - st[0]) / 1e3, dt[i]))
 total = (st[n - 1] - st[0]) / 1e3
-print("clip: %.1f us from first to last kernel start (T=%d)" % (total, a.frames))
+print("call: %.1f us from first to last kernel start (T=%d, %d clip(s), lockstep groups of %d)" % (total, a.frames, a.clips, max(1, a.batch_clips)))
 def short(nm):
     nm = nm.split("(")[0]
     return nm[nm.rfind("::") + 2:] if "::" in nm else nm
-# last frame = after the second-to-last nhwc_to_nchw
+# last frame = after the second-to-last nhwc_to_nchw (a lockstep group writes one per clip back to back: step over the group)
 ends = [i for i in range(n) if "nhwc_to_nchw" in names[i][0]]
-lo = ends[-2] + 1 if len(ends) >= 2 else 0
+g = max(1, min(a.clips, a.batch_clips))
+lo = ends[-1 - g] + 1 if len(ends) >= 1 + g else 0
 hi = ends[-1] + 1 if ends else n
 for title, (p, q) in (("whole clip", (0, n)), ("last frame", (lo, hi))):
     agg = collections.defaultdict(lambda: [0, 0.0])
