@@ -1413,8 +1413,9 @@ void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int
 
     // ---- optical flow of every clip on the side stream (low priority), overlapping everything below
     static const bool no_side = getenv("KEEP_NO_SIDE") != nullptr;
+    static const bool skip_flow = getenv("KEEP_DEBUG_SKIP_FLOW") != nullptr;   // timing experiments only: zero flows, no GMFlow
     const int nchunk = (T - 1 + flow_chunk() - 1) / flow_chunk();
-    const bool flows_async = !dry && !no_side;
+    const bool flows_async = !dry && !no_side && !skip_flow;
     if (flows_async) {
         if (!side_) {
             int lo = 0, hi = 0;
@@ -1434,11 +1435,15 @@ void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int
     ar_ = &arena2_;
     // chunk-major order: frame i of the lockstep group needs pair i-1 of EVERY clip, so chunk k of all clips goes before
     // chunk k+1 of any (clip-major order would hold frame 1 back until nearly all of the group's GMFlow work is done)
-    for (int p0 = 0; p0 < T - 1; p0 += flow_chunk())
-        for (int c = 0; c < nb; ++c) {
-            ev_flow_base_ = c * nchunk;
-            gmflow(x_dev + (size_t)c * per_clip_in, T, flows[c].f(), p0, p0 + flow_chunk());
-        }
+    if (!dry && skip_flow) {
+        for (int c = 0; c < nb; ++c) CUDA_CHECK(cudaMemsetAsync(flows[c].p, 0, flows[c].bytes(), s_));
+    } else {
+        for (int p0 = 0; p0 < T - 1; p0 += flow_chunk())
+            for (int c = 0; c < nb; ++c) {
+                ev_flow_base_ = c * nchunk;
+                gmflow(x_dev + (size_t)c * per_clip_in, T, flows[c].f(), p0, p0 + flow_chunk());
+            }
+    }
     ev_flow_base_ = 0;
     ar_ = &arena_;
     s_ = s_main_;
