@@ -136,6 +136,16 @@ def main():
                                     "p01": float(margin.flatten().kthvalue(max(1, margin.numel() // 100)).values)}
         case["ref_unique_codes"] = int(ref_cap["codes"].unique().numel())
         # reference's own fp32 noise floor: same net in float64
+        if name == "T20_coherent":
+            # the same floor at full size: where do the fp32 reference and the fp64 restatement part ways, and at what margin
+            sd64 = {k: v.double() for k, v in sd.items()}
+            _, cap64 = keep_oracle.keep_forward(sd64, x.double(), capture=True)
+            c64, rc = cap64["codes"][0], ref_cap["codes"][0]
+            case["ref_fp32_vs_fp64"] = {
+                "code_agreement_per_frame": [float((c64[i] == rc[i]).float().mean()) for i in range(T)],
+                "worst_flipped_margin_per_frame": [float(margin[0, i][c64[i] != rc[i]].max()) if bool((c64[i] != rc[i]).any()) else 0.0
+                                                   for i in range(T)],
+            }
         if name == "T3_coherent":
             # (the reference itself cannot run in float64: matching.py:31 mixes a float32 grid in;
             #  the restatement, pinned above, is run in float64 instead)
