@@ -132,6 +132,15 @@ int keep_profile_dump(keep_handle h, const char* path) {
     KEEP_API_END
 }
 
+int keep_plan_dump(keep_handle h, int clips, int T, const char* path) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h && path, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->e->plan_dump(clips, T, path);
+    return 0;
+    KEEP_API_END
+}
+
 int keep_debug_capture(keep_handle h, int enable) {
     KEEP_API_BEGIN
     KEEP_CHECK(h, "null handle");

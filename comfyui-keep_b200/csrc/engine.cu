@@ -437,6 +437,13 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         part = ar_->alloc((size_t)a.splitk * out.numel() * sizeof(float));
         a.partial = (float*)part;
     }
+    if (plan_) {
+        char line[256];
+        snprintf(line, sizeof(line), "conv n=%d h=%d w=%d c0=%d c1=%d cout=%d k=%d stride=%d up=%d pre=%d act=%d res=%d kernel=%s splitk=%d bn=%d wide=%d",
+                 a.n, a.h, a.w, a.c0, a.c1, a.cout, a.kh, a.stride, a.up, a.pre_scale ? a.pre_act + 1 : 0, a.act, a.res ? 1 : 0,
+                 use_tc ? "tcgen05" : (use_small ? "small" : "simt"), a.splitk, bn, (a.a_wide && use_tc && passes == 3) ? 1 : 0);
+        plan_->push_back(line);
+    }
     if (!ar_->dry()) {
         Prof pr;
         if (profile_) {
@@ -531,6 +538,7 @@ Aff Engine::gn(const Tensor& x, const std::string& prefix, const Tensor* x2) {
     const float* g = warr(prefix + ".weight");
     const float* b = warr(prefix + ".bias");
     const int hw = x.h * x.w;
+    if (plan_) plan_->push_back("groupnorm n=" + std::to_string(x.n) + " hw=" + std::to_string(hw) + " c=" + std::to_string(ct));
     double* scratch = (double*)ar_->alloc(gn_scratch_doubles(x.n, hw, std::max(x.c, x2 ? x2->c : 0)) * sizeof(double));
     if (!ar_->dry()) {
         groupnorm_affine(x.p, x.dt, x.n, hw, x.c, cpg, 1e-6f, g, b, a.scale, a.shift, ct, 0, scratch, s_, gn_tickets_ ? gn_tickets_ + ((s_ == side_ && side_) ? gn_ticket_count() : 0) : nullptr);
@@ -561,6 +569,7 @@ Aff Engine::inorm(const Tensor& x) {
 
 Tensor Engine::ln(const Tensor& x, const std::string& prefix, const Tensor* res, const float* add2, int add2_rows, Tensor* out2) {
     KEEP_CHECK(x.dt == F32, "layernorm expects fp32 tokens");
+    if (plan_) plan_->push_back("layernorm rows=" + std::to_string(x.rows()) + " c=" + std::to_string(x.c));
     Tensor out = talloc(x.n, x.h, x.w, x.c, F32);
     if (out2) *out2 = talloc(x.n, x.h, x.w, x.c, F32);
     if (!ar_->dry()) {
@@ -634,6 +643,8 @@ Tensor Engine::gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, 
 // generic multi-head attention: scores -> softmax -> PV, all fp32
 Tensor Engine::mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv,
                    long long sv, int nb, int Lq, int Lk, int heads, int dh, float scale) {
+    if (plan_) plan_->push_back("attention nb=" + std::to_string(nb) + " Lq=" + std::to_string(Lq) + " Lk=" + std::to_string(Lk) +
+                                " heads=" + std::to_string(heads) + " dh=" + std::to_string(dh));
     Tensor S = talloc(nb * heads, Lq, 1, Lk, F32);
     Tensor O = talloc(nb, Lq, 1, heads * dh, F32);
     if (!ar_->dry()) {
@@ -1532,6 +1543,25 @@ void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int
     tfree(z_all);
     for (int k = 0; k < 6; ++k) if (cft_on_[k]) tfree(taps[k]);
     for (int c = 0; c < nb; ++c) tfree(flows[c]);
+}
+
+void Engine::plan_dump(int nb, int T, const char* path) {
+    KEEP_CHECK(nb >= 1 && nb <= 8 && T >= 2 && T <= 100, "keep_plan_dump: need 1 <= clips <= 8 and 2 <= T <= 100");
+    std::vector<std::string> lines;
+    plan_ = &lines;
+    try {
+        begin(nullptr, 0, nullptr, true);
+        if (nb == 1) forward_clip(nullptr, T, nullptr, KEEP_OUT_F32);
+        else forward_clips(nullptr, nb, T, nullptr, KEEP_OUT_F32);
+    } catch (...) {
+        plan_ = nullptr;
+        throw;
+    }
+    plan_ = nullptr;
+    FILE* f = fopen(path, "w");
+    KEEP_CHECK(f, "cannot open %s", path);
+    for (auto& l : lines) fprintf(f, "%s\n", l.c_str());
+    fclose(f);
 }
 
 // workspace plan of a lockstep group (dry run), cached per (nb, T)

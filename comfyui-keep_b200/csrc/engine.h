@@ -56,6 +56,9 @@ class Engine {
     size_t read(const std::string& what, void* host, size_t bytes);
     void set_capture(bool on) { capture_ = on; }
     void set_batch_clips(int n) { batch_max_ = n < 1 ? 1 : (n > 8 ? 8 : n); }
+    // host-side plan of one call (dry run, no device): one line per conv / linear / GroupNorm / LayerNorm / attention op with
+    // its shape and the kernel choice (CPU test tier: control flow of both configs and of the lockstep path)
+    void plan_dump(int nb, int T, const char* path);
     // per-launch CUDA-event timing of the conv/GEMM kernel family (bench.py roofline)
     void set_profile(bool on);
     void profile_read(double* out8);
@@ -157,6 +160,7 @@ class Engine {
     std::unordered_map<std::string, Cap> cap_;      // device buffers holding last forward's intermediates
     std::unordered_map<std::string, Cap> forced_;   // device buffers with forced values
     bool capture_ = false;
+    std::vector<std::string>* plan_ = nullptr;   // plan_dump(): op trace of the dry run in progress
     bool profile_ = false;
     struct Prof { cudaEvent_t a, b; double flops, bytes; int tag; int m, k, n, kh, splitk, bn; };
     std::vector<Prof> prof_;

@@ -70,6 +70,7 @@ def load_library():
     lib.keep_forward.argtypes = [vp, vp, ci, ci, vp, ci, vp, cs, vp]
     lib.keep_forward_u8.argtypes = [vp, vp, ci, ci, vp, vp, cs, vp]
     lib.keep_set_batch_clips.argtypes = [vp, ci]
+    lib.keep_plan_dump.argtypes = [vp, ci, ci, ctypes.c_char_p]
     lib.keep_destroy.argtypes = [vp]
     lib.keep_launch_count.argtypes = [vp]
     lib.keep_launch_count.restype = ctypes.c_longlong

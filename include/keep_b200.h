@@ -96,6 +96,11 @@ int keep_profile_enable(keep_handle h, int enable);
 int keep_profile_read(keep_handle h, double* out8);
 int keep_profile_dump(keep_handle h, const char* csv_path); /* one row per conv/GEMM launch: shape, ms */
 
+/* Host-side plan of one call, no device needed (works on a KEEP_FLAG_PLAN_ONLY engine): one text line per conv / linear /
+ * GroupNorm / LayerNorm / attention op of a forward over `clips` clips of T frames (clips > 1: the lockstep path) with its
+ * shape and kernel choice.  CPU test tier; replaces nothing in the reference. */
+int keep_plan_dump(keep_handle h, int clips, int T, const char* path);
+
 /* ---- test hooks (stage-wise teacher forcing and intermediate capture; tests/ only) -------------
  * what ∈ {"flows" (T-1,512,512,2) f32, "z_codes" (T,16,16,256) f32 NHWC, "gains" (T,256) f32,
  *         "logits" (T,256,1024) f32, "codes" (T,256) i32, "prev" (T,3,512,512) f32 NCHW (force only)}.

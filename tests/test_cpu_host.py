@@ -194,3 +194,61 @@ def test_lockstep_plan_only_engine(keep_mod, lib, state_dict):
     assert lib.keep_set_batch_clips(h, 0) != 0 and b"max_clips" in lib.keep_last_error()
     assert lib.keep_set_batch_clips(None, 2) != 0
     net._drop_engine()
+
+
+# ---- host-side plan (keep_plan_dump): control flow of both configs and of the lockstep path, no device --------------------
+
+def _plan(keep_mod, lib, sd, clips, T, flags, tmp_path, **cfg):
+    import collections
+    net = keep_mod.KeepNetB200(flags=flags, **cfg)
+    net.load_state_dict(sd, strict=True)
+    h = net._make_engine(flags=256 | net._flags)
+    path = os.path.join(str(tmp_path), "plan_%d_%d_%d.txt" % (clips, T, flags))
+    assert lib.keep_plan_dump(h, clips, T, path.encode()) == 0, lib.keep_last_error()
+    net._drop_engine()
+    lines = open(path).read().splitlines()
+    kinds = collections.Counter(l.split()[0] for l in lines)
+    return lines, kinds
+
+
+def test_plan_per_frame_chain_and_kernel_choice(keep_mod, lib, state_dict, tmp_path):
+    kn = keep_mod.keep_net
+    tc3 = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3
+    l2, k2 = _plan(keep_mod, lib, state_dict, 1, 2, tc3, tmp_path)
+    l3, k3 = _plan(keep_mod, lib, state_dict, 1, 3, tc3, tmp_path)
+    l4, k4 = _plan(keep_mod, lib, state_dict, 1, 4, tc3, tmp_path)
+    # one more frame = one more pass of the serial chain (hq_encoder + code transformer + generator with CFT / CFA)
+    per_frame = {k: k3[k] - k2[k] for k in k3}
+    assert per_frame == {k: k4[k] - k3[k] for k in k4}
+    assert per_frame["conv"] == 168 and per_frame["attention"] == 17 and per_frame["layernorm"] == 23
+    # every GEMM-shaped layer runs on the tcgen05 kernel in the tensor-core modes; the stems / heads on their own kernels
+    for l in l2:
+        if l.startswith("conv"):
+            f = dict(kv.split("=") for kv in l.split()[1:])
+            strided_1x1 = f["k"] == "1" and f["stride"] != "1"      # GMFlow's three downsample shortcuts stay on CUDA cores
+            if int(f["c0"]) + int(f["c1"]) >= 32 and int(f["cout"]) % 16 == 0 and not strided_1x1:
+                assert f["kernel"] == "tcgen05", l
+            assert f["wide"] == "0", l                              # general config: fp16 pairs everywhere
+    lf, kf = _plan(keep_mod, lib, state_dict, 1, 2, 0, tmp_path)
+    assert kf == k2 and not any("tcgen05" in l for l in lf)        # fp32 engine mode: same programme, CUDA-core kernels
+
+
+def test_plan_lockstep_shares_the_chain_and_asian_adds_a_cft(keep_mod, lib, state_dict, state_dict_asian, tmp_path):
+    kn = keep_mod.keep_net
+    tc3 = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3
+    _, s2 = _plan(keep_mod, lib, state_dict, 1, 2, tc3, tmp_path)
+    _, s3 = _plan(keep_mod, lib, state_dict, 1, 3, tc3, tmp_path)
+    lk2, b2 = _plan(keep_mod, lib, state_dict, 2, 2, tc3, tmp_path, batch_clips=2)
+    _, b3 = _plan(keep_mod, lib, state_dict, 2, 3, tc3, tmp_path, batch_clips=2)
+    # two clips in lockstep: the per-frame chain runs once per frame index (at batch 2), not once per clip
+    assert {k: b3[k] - b2[k] for k in b3} == {k: s3[k] - s2[k] for k in s3}
+    assert b2["conv"] < 2 * s2["conv"]
+    assert any(l.startswith("conv n=2 h=512 w=512 c0=3 ") for l in lk2)                 # hq_encoder stem at batch 2
+    assert any(l.startswith("attention nb=2 Lq=256 Lk=256 heads=8 dh=64") for l in lk2)   # code transformer at batch 2
+    # 'Asian': four CFT blocks instead of three (7 convs + 2 GroupNorms each per frame), wide operands on raw-input layers
+    la, a2 = _plan(keep_mod, lib, state_dict_asian, 1, 2, tc3, tmp_path, **kn.KEEP_ASIAN_CFG)
+    assert a2["conv"] - s2["conv"] == 2 * 7 and a2["groupnorm"] - s2["groupnorm"] == 2 * 2
+    assert any("c0=128 c1=128 cout=128 k=3" in l and "h=256" in l for l in la)        # cat[enc, dec] at 256^2
+    wide = [l for l in la if "wide=1" in l]
+    assert wide and all(" pre=0 " in l and "kernel=tcgen05" in l for l in wide)
+    assert any("up=2" in l for l in wide) and not any(" w=1 " in l for l in wide)
