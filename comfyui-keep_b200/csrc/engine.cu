@@ -612,6 +612,8 @@ Tensor Engine::gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, 
                           float alpha) {
     const long long m_tiles = (long long)nb * cdiv(M, 128);
     const int bn = tc_pick_bn(N, m_tiles, tc_passes_);
+    if (plan_) plan_->push_back("gemm nb=" + std::to_string(nb) + " M=" + std::to_string(M) + " K=" + std::to_string(K) + " N=" +
+                                std::to_string(N) + " kernel=tcgen05");
     const size_t per = tc_pack_matrix(nullptr, 0, 0, 0, nb, N, K, bn, tc_passes_, 1.0f, nullptr, s_);
     __half* panels = (__half*)ar_->alloc(per * nb * sizeof(__half));
     Tensor out = talloc(nb, M, 1, N, F32);

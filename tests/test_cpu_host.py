@@ -252,3 +252,33 @@ def test_plan_lockstep_shares_the_chain_and_asian_adds_a_cft(keep_mod, lib, stat
     wide = [l for l in la if "wide=1" in l]
     assert wide and all(" pre=0 " in l and "kernel=tcgen05" in l for l in wide)
     assert any("up=2" in l for l in wide) and not any(" w=1 " in l for l in wide)
+
+
+def _plan_gflop(lines):
+    """Algorithmic GFLOP (2 x MAC) of the conv / linear / GEMM / attention ops of a plan."""
+    tot = 0.0
+    for l in lines:
+        kind = l.split()[0]
+        f = dict(kv.split("=") for kv in l.split()[1:])
+        if kind == "conv":
+            n, h, w, c0, c1, co, k, st, up = (int(f[x]) for x in ("n", "h", "w", "c0", "c1", "cout", "k", "stride", "up"))
+            tot += 2.0 * n * (h * up // st) * (w * up // st) * co * k * k * (c0 + c1)
+        elif kind == "gemm":
+            tot += 2.0 * int(f["nb"]) * int(f["M"]) * int(f["K"]) * int(f["N"])
+        elif kind == "attention":
+            tot += 4.0 * int(f["nb"]) * int(f["heads"]) * int(f["Lq"]) * int(f["Lk"]) * int(f["dh"])
+    return tot / 1e9
+
+
+def test_engine_executes_the_reference_flop_count(keep_mod, lib, state_dict, tmp_path):
+    """No work skipped: the engine's planned conv / GEMM / attention FLOPs equal what torch's FlopCounterMode counts for the
+    reference forward -- FLOPs(T) = 1058.97 T - 410.13 GFLOP -- to 0.1 %.  The remainder is the one-hot @
+    codebook matmul the engine replaces by a row gather (0.13 GFLOP / frame), the two V-in-R^2 softmax expectations of GMFlow
+    and the gain estimator's T x T temporal attention, which run outside the traced GEMM family."""
+    kn = keep_mod.keep_net
+    for T in (2, 5, 20):
+        lines, _ = _plan(keep_mod, lib, state_dict, 1, T, kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3, tmp_path)
+        want = 1058.97 * T - 410.13
+        got = _plan_gflop(lines)
+        assert abs(got / want - 1.0) < 1e-3, (T, got, want)
+        assert got <= want                       # never more than the reference either (nothing recomputed)
