@@ -282,3 +282,34 @@ def test_engine_executes_the_reference_flop_count(keep_mod, lib, state_dict, tmp
         got = _plan_gflop(lines)
         assert abs(got / want - 1.0) < 1e-3, (T, got, want)
         assert got <= want                       # never more than the reference either (nothing recomputed)
+
+
+def test_gmflow_fused_projection_plan_keeps_the_flops(tmp_path):
+    """KEEP_GM_FUSE_QKV=1 (opt-in): q|k|v (self-attention) and k|v (cross-attention) projections of GMFlow as one GEMM over fused
+    weights -- fewer, wider GEMMs, the same FLOPs.  The knob is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, os, collections; sys.path.insert(0, %r)\n"
+        "import keep_b200\n"
+        "sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+        "lib = keep_b200.keep_net.load_library()\n"
+        "net = keep_b200.KeepNetB200(flags=6); net.load_state_dict(keep_b200.synth.make_state_dict(seed=0), strict=True)\n"
+        "h = net._make_engine(flags=256 | 6)\n"
+        "p = os.path.join(%r, 'plan_fuse.txt')\n"
+        "assert lib.keep_plan_dump(h, 1, 3, p.encode()) == 0\n"
+        "L = open(p).read().splitlines()\n"
+        "import test_cpu_host as t\n"
+        "print(len([l for l in L if l.startswith('conv')]), sum(' c0=128 c1=0 cout=384 k=1 ' in l and ' h=4096 ' in l for l in L), sum(' c0=128 c1=0 cout=256 k=1 ' in l and ' h=4096 ' in l for l in L), '%%.3f' %% t._plan_gflop(L))\n"
+    ) % (ROOT, ROOT, str(tmp_path))
+    out = {}
+    for knob in ("0", "1"):
+        env = dict(os.environ, KEEP_GM_FUSE_QKV=knob)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[knob] = r.stdout.strip().splitlines()[-1].split()
+    n0, q0, kv0, g0 = int(out["0"][0]), int(out["0"][1]), int(out["0"][2]), float(out["0"][3])
+    n1, q1, kv1, g1 = int(out["1"][0]), int(out["1"][1]), int(out["1"][2]), float(out["1"][3])
+    assert q0 == 0 and kv0 == 0 and q1 == 6 and kv1 == 6   # T = 3: one GMFlow pass, 6 self-attention + 6 cross-attention layers
+    assert n1 == n0 - 6 * 2 - 6 * 1                    # three projections -> one (self), two -> one (cross)
+    assert abs(g1 - g0) < 1e-6 * g0
