@@ -230,7 +230,8 @@ def test_plan_per_frame_chain_and_kernel_choice(keep_mod, lib, state_dict, tmp_p
                 assert f["kernel"] == "tcgen05", l
             assert f["wide"] == "0", l                              # general config: fp16 pairs everywhere
     lf, kf = _plan(keep_mod, lib, state_dict, 1, 2, 0, tmp_path)
-    assert kf == k2 and not any("tcgen05" in l for l in lf)        # fp32 engine mode: same programme, CUDA-core kernels
+    # fp32 engine mode: same programme on CUDA-core kernels (its batched attention GEMMs are not traced as "gemm" lines)
+    assert {k: v for k, v in k2.items() if k != "gemm"} == dict(kf) and not any("tcgen05" in l for l in lf)
 
 
 def test_plan_lockstep_shares_the_chain_and_asian_adds_a_cft(keep_mod, lib, state_dict, state_dict_asian, tmp_path):
