@@ -314,3 +314,18 @@ def test_gmflow_fused_projection_plan_keeps_the_flops(tmp_path):
     assert q0 == 0 and kv0 == 0 and q1 == 6 and kv1 == 6   # T = 3: one GMFlow pass, 6 self-attention + 6 cross-attention layers
     assert n1 == n0 - 6 * 2 - 6 * 1                    # three projections -> one (self), two -> one (cross)
     assert abs(g1 - g0) < 1e-6 * g0
+
+
+def test_maximum_clip_length_fits_the_gpu(keep_mod, lib, state_dict, state_dict_asian):
+    """T = 100 is the node's upper bound for max_clip_length (nodes.py): the workspace plan must fit a 180 GB B200 many times
+    over, in both configs and for the largest lockstep group; T = 101 and T = 1 are rejected by name."""
+    kn = keep_mod.keep_net
+    for sd, cfg in ((state_dict, {}), (state_dict_asian, kn.KEEP_ASIAN_CFG)):
+        net = keep_mod.KeepNetB200(flags=kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3, batch_clips=4, **cfg)
+        net.load_state_dict(sd, strict=True)
+        h = net._make_engine(flags=256 | net._flags)
+        w1, w4 = lib.keep_workspace_bytes(h, 1, 100), lib.keep_workspace_bytes(h, 4, 100)
+        assert 0 < w1 < w4 < 32 << 30
+        assert lib.keep_workspace_bytes(h, 1, 101) == 0 and b"T <= 100" in lib.keep_last_error()
+        assert lib.keep_workspace_bytes(h, 1, 1) == 0
+        net._drop_engine()
