@@ -108,6 +108,15 @@ int keep_destroy(keep_handle h) {
 
 long long keep_launch_count(keep_handle h) { return h ? h->e->launches() : 0; }
 
+int keep_status(keep_handle h, int clear, int* status_out) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(h && status_out, "keep_status: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *status_out = h->e->status(clear != 0);
+    return 0;
+    KEEP_API_END
+}
+
 int keep_profile_enable(keep_handle h, int enable) {
     KEEP_API_BEGIN
     KEEP_CHECK(h, "null handle");

@@ -131,6 +131,10 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: true exactly once per (call site's mask, current device),
+// so a second engine on another GPU of the same process configures its own context (thread-safe)
+bool first_use_on_current_device(unsigned long long* mask);   // engine.cu
+
 // ------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL): ~560 small dependent kernels per frame make launch latency a first-order cost.
 // Every kernel starts with pdl_prologue(): it lets the NEXT kernel's CTAs be scheduled right away (launch_dependents) and

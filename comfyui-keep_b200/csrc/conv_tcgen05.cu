@@ -1089,20 +1089,18 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
          {conv_tc_kernel<1, true, 1>, conv_tc_kernel<1, true, 2>, conv_tc_kernel<1, true, 3>}},
         {{conv_tc_kernel<3, false, 1>, conv_tc_kernel<3, false, 2>, conv_tc_kernel<3, false, 3>},
          {conv_tc_kernel<3, true, 1>, conv_tc_kernel<3, true, 2>, conv_tc_kernel<3, true, 3>}}};
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_current_device(&configured)) {
         for (int i = 0; i < 12; ++i)
             CUDA_CHECK(cudaFuncSetAttribute(kerns[i / 6][(i / 3) % 2][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
     }
     // wide-range variant (bf16 activation pairs): split-precision mode, fp32 feature maps only
     static const Kern kerns_wide[3] = {conv_tc_kernel<3, false, 1, true>, conv_tc_kernel<3, false, 2, true>, conv_tc_kernel<3, false, 3, true>};
-    static bool configured_wide = false;
+    static unsigned long long configured_wide = 0;
     const bool wide = a.a_wide && passes == 3 && !f16;
-    if (wide && !configured_wide) {
+    if (wide && first_use_on_current_device(&configured_wide)) {
         for (int i = 0; i < 3; ++i)
             CUDA_CHECK(cudaFuncSetAttribute(kerns_wide[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured_wide = true;
     }
     const Kern kern = wide ? kerns_wide[t.win - 1] : kerns[passes == 3 ? 1 : 0][f16 ? 1 : 0][t.win - 1];
     if (t.cluster_k) {   // one work item per CTA, the splitk CTAs of a tile form one cluster

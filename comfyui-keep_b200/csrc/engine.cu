@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 namespace keep {
 
@@ -41,6 +42,17 @@ static int env_or(const char* name, int dflt, int lo, int hi) {
 }
 static int flow_chunk() { static const int v = env_or("KEEP_FLOW_CHUNK", 4, 1, 32); return v; }
 static int lq_chunk() { static const int v = env_or("KEEP_LQ_CHUNK", 10, 1, 32); return v; }
+
+bool first_use_on_current_device(unsigned long long* mask) {
+    static std::mutex mu;
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
+}
 
 bool pdl_enabled() {
     static int v = -1;
@@ -261,6 +273,9 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
     // KEEP_FORCE_FLAGS=<int>: OR extra engine flags in (A/B runs on the GPU box, e.g. 16 = KEEP_FLAG_TC_WIDE on the general config)
     if (const char* e = getenv("KEEP_FORCE_FLAGS")) { flags |= atoi(e) & ~KEEP_FLAG_PLAN_ONLY; flags_ = flags; }
     dry_only_ = (flags & KEEP_FLAG_PLAN_ONLY) != 0;
+    // fp16 feature-map storage is wired through the kernels but not through the whole programme (CFA and the cross-frame
+    // state are fp32-only) and it cannot meet the parity bar with fp32-grade operands anyway: refuse it loudly
+    KEEP_CHECK(!(flags & KEEP_FLAG_FP16_FEATURES), "KEEP_FLAG_FP16_FEATURES is not supported by this engine (feature maps are fp32)");
     if (!dry_only_) {
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -276,6 +291,9 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         gn_warmup();
         CUDA_CHECK(cudaMalloc((void**)&gn_tickets_, 2 * gn_ticket_count() * sizeof(int)));   // main / side stream
         CUDA_CHECK(cudaMemset(gn_tickets_, 0, 2 * gn_ticket_count() * sizeof(int)));
+        CUDA_CHECK(cudaMalloc((void**)&status_, sizeof(int)));
+        CUDA_CHECK(cudaMemset(status_, 0, sizeof(int)));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_last_, cudaEventDisableTiming));
         // KEEP_SIDE_SMS = n > 0: side-branch persistent kernels capped at n CTAs; n < 0: short CTAs of -n work items each
         { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 100; if (side_sms_ > num_sms_ || (side_sms_ >= 0 && side_sms_ < 8)) side_sms_ = num_sms_; }
     }
@@ -336,6 +354,8 @@ Engine::~Engine() {
     cudaFree(wpool_);
     cudaFree(region_);
     cudaFree(gn_tickets_);
+    cudaFree(status_);
+    if (ev_last_) cudaEventDestroy(ev_last_);
     cudaFree(u8_stage_);
     cudaFree(grid64_);
     cudaFree(own_ws_);
@@ -1109,7 +1129,7 @@ Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
         const int* forced = nullptr;
         auto it = forced_.find("codes");
         if (it != forced_.end() && it->second.p) forced = (const int*)it->second.p + (size_t)frame * L;   // per-clip path only
-        argmax_gather(logits.f(), nbt * L, 1024, warr("quantize.embedding.weight"), 256, forced, idx, quant.p, quant.dt, s_);
+        argmax_gather(logits.f(), nbt * L, 1024, warr("quantize.embedding.weight"), 256, forced, idx, quant.p, quant.dt, s_, status_);
         launches_ += 1;
         if (capture_) {
             Cap& cl = cap_["logits"];
@@ -1335,6 +1355,13 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     Tensor prev_out;  // (1,512,512,3) fp32 NHWC
     auto fp = forced_.find("prev");
     const bool force_prev = dry || (fp != forced_.end() && fp->second.p);
+    if (!dry) {   // forced buffers are indexed by frame below: refuse short ones instead of reading out of bounds
+        if (fp != forced_.end() && fp->second.p)
+            KEEP_CHECK(fp->second.bytes >= (size_t)(T - 1) * 3 * HW * sizeof(float), "forced 'prev' holds fewer than T-1 = %d frames", T - 1);
+        auto fc = forced_.find("codes");
+        if (fc != forced_.end() && fc->second.p)
+            KEEP_CHECK(fc->second.bytes >= (size_t)T * 256 * sizeof(int), "forced 'codes' holds fewer than T = %d frames of 256 indices", T);
+    }
     for (int i = 0; i < T; ++i) {
         if (i >= env_cap_frames) main_cap_ = num_sms_;
         Tensor z_hat;
@@ -1353,7 +1380,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
             if (flows_async) CUDA_CHECK(cudaStreamWaitEvent(s_main_, ev_flow_[(i - 1) / flow_chunk()], 0));   // flow of pair i-1 is ready
             Tensor warped = talloc(1, 512, 512, 3, adt_);
             if (!dry) {
-                flow_warp(src.p, src.dt, flows.f() + (size_t)(i - 1) * HW * 2, warped.p, warped.dt, 1, 512, 512, 3, s_);
+                flow_warp(src.p, src.dt, flows.f() + (size_t)(i - 1) * HW * 2, warped.p, warped.dt, 1, 512, 512, 3, s_, status_);
                 launches_ += 1;
             }
             if (own_src) tfree(src);
@@ -1362,7 +1389,7 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
             z_hat = talloc(1, 16, 16, 256, F32);
             own_z = true;
             if (!dry) {
-                kalman_update(z_codes.f() + (size_t)i * 256 * 256, zp.f(), gains.f() + (size_t)i * 256, z_hat.f(), 256, 256, s_);
+                kalman_update(z_codes.f() + (size_t)i * 256 * 256, zp.f(), gains.f() + (size_t)i * 256, z_hat.f(), 256, 256, s_, status_);
                 launches_ += 1;
             }
             tfree(zp);
@@ -1375,10 +1402,10 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
         tfree(quant);
         if (!dry) {
             if (out_dtype == KEEP_OUT_U8_BGR)
-                nhwc_to_u8bgr(img.p, img.dt, (unsigned char*)out_dev + (size_t)i * 3 * HW, 1, 512, 512, s_);
+                nhwc_to_u8bgr(img.p, img.dt, (unsigned char*)out_dev + (size_t)i * 3 * HW, 1, 512, 512, s_, status_);
             else
                 nhwc_to_nchw(img.p, img.dt, (char*)out_dev + (size_t)i * 3 * HW * (out_dtype == KEEP_OUT_F16 ? 2 : 4),
-                             out_dtype == KEEP_OUT_F16 ? F16 : F32, 1, 3, 512, 512, s_);
+                             out_dtype == KEEP_OUT_F16 ? F16 : F32, 1, 3, 512, 512, s_, status_);
             launches_ += 1;
         }
         if (prev_out.p) tfree(prev_out);
@@ -1506,7 +1533,7 @@ void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int
                 if (!dry) {
                     flow_warp((const char*)prev_out.p + (size_t)c * HW * 3 * dtype_size(prev_out.dt), prev_out.dt,
                               flows[c].f() + (size_t)(i - 1) * HW * 2, (char*)warped.p + (size_t)c * HW * 3 * dtype_size(warped.dt),
-                              warped.dt, 1, 512, 512, 3, s_);
+                              warped.dt, 1, 512, 512, 3, s_, status_);
                     launches_ += 1;
                 }
             }
@@ -1516,7 +1543,7 @@ void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int
             own_z = true;
             if (!dry) {
                 kalman_update(z_all.f() + (size_t)i * nb * 256 * 256, zp.f(), gains_all.f() + (size_t)i * nb * 256, z_hat.f(), nb * 256,
-                              256, s_);
+                              256, s_, status_);
                 launches_ += 1;
             }
             tfree(zp);
@@ -1529,8 +1556,8 @@ void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int
             for (int c = 0; c < nb; ++c) {
                 const char* src = (const char*)img.p + (size_t)c * HW * 3 * dtype_size(img.dt);
                 char* dst = (char*)out_dev + ((size_t)c * T + i) * 3 * HW * osz;
-                if (out_dtype == KEEP_OUT_U8_BGR) nhwc_to_u8bgr(src, img.dt, (unsigned char*)dst, 1, 512, 512, s_);
-                else nhwc_to_nchw(src, img.dt, dst, out_dtype == KEEP_OUT_F16 ? F16 : F32, 1, 3, 512, 512, s_);
+                if (out_dtype == KEEP_OUT_U8_BGR) nhwc_to_u8bgr(src, img.dt, (unsigned char*)dst, 1, 512, 512, s_, status_);
+                else nhwc_to_nchw(src, img.dt, dst, out_dtype == KEEP_OUT_F16 ? F16 : F32, 1, 3, 512, 512, s_, status_);
                 launches_ += 1;
             }
         }
@@ -1687,6 +1714,10 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
     KEEP_CHECK(b >= 1 && T >= 2 && T <= 100, "keep_forward: need b >= 1 and 2 <= T <= 100 (got b=%d T=%d)", b, T);
     KEEP_CHECK(out_dtype == KEEP_OUT_F32 || out_dtype == KEEP_OUT_F16 || out_dtype == KEEP_OUT_U8_BGR, "keep_forward: bad out_dtype %d", out_dtype);
     CUDA_CHECK(cudaSetDevice(device_));
+    // Engine-owned buffers (workspace, staging, lazily packed weight panels) are ordered by the stream of the call that
+    // touches them; a caller that switches streams between calls gets the dependency from this event instead of a race.
+    CUDA_CHECK(cudaStreamWaitEvent(s, ev_last_, 0));
+    struct Tail { cudaEvent_t e; cudaStream_t s; ~Tail() { cudaEventRecord(e, s); } } tail{ev_last_, s};
     if ((flags_ & KEEP_FLAG_BATCH_CLIPS) && b > 1 && batch_max_ > 1 && !ws && !capture_ && !profile_) {
         bool forcing_b = false;
         for (auto& kv : forced_) forcing_b = forcing_b || kv.second.p != nullptr;
@@ -1780,6 +1811,7 @@ void Engine::forward_u8(const unsigned char* x_u8_dev, int b, int T, unsigned ch
     KEEP_CHECK(x_u8_dev && out_u8_dev, "keep_forward_u8: null tensor");
     KEEP_CHECK(b >= 1 && T >= 2 && T <= 100, "keep_forward_u8: need b >= 1 and 2 <= T <= 100 (got b=%d T=%d)", b, T);
     CUDA_CHECK(cudaSetDevice(device_));
+    CUDA_CHECK(cudaStreamWaitEvent(s, ev_last_, 0));   // u8_stage_ may still be read by the previous call on another stream
     const size_t need = (size_t)b * T * 3 * 512 * 512 * sizeof(float);
     if (u8_stage_bytes_ < need) {
         CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1847,9 +1879,25 @@ void Engine::force(const std::string& what, const void* host, size_t bytes) {
     cudaFree(c.p);
     c.p = nullptr; c.bytes = 0;
     if (!host || bytes == 0) return;
+    if (what == "codes") {   // indices gather rows of the 1024-entry codebook
+        const int* idx = (const int*)host;
+        for (size_t i = 0; i < bytes / sizeof(int); ++i)
+            KEEP_CHECK(idx[i] >= 0 && idx[i] < 1024, "forced code index %d at position %zu is outside the codebook", idx[i], i);
+    }
     CUDA_CHECK(cudaMalloc(&c.p, bytes));
     CUDA_CHECK(cudaMemcpy(c.p, host, bytes, cudaMemcpyHostToDevice));
     c.bytes = bytes;
+}
+
+// sticky non-finite status word: synchronises the device, returns the bits seen since the last clearing read
+int Engine::status(bool clear) {
+    if (dry_only_ || !status_) return 0;
+    CUDA_CHECK(cudaSetDevice(device_));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    int v = 0;
+    CUDA_CHECK(cudaMemcpy(&v, status_, sizeof(int), cudaMemcpyDeviceToHost));
+    if (clear && v) CUDA_CHECK(cudaMemset(status_, 0, sizeof(int)));
+    return v;
 }
 
 size_t Engine::read(const std::string& what, void* host, size_t bytes) {

@@ -55,6 +55,7 @@ class Engine {
     void force(const std::string& what, const void* host, size_t bytes);
     size_t read(const std::string& what, void* host, size_t bytes);
     void set_capture(bool on) { capture_ = on; }
+    int status(bool clear);   // sticky non-finite bits (KEEP_STATUS_*), synchronises
     void set_batch_clips(int n) { batch_max_ = n < 1 ? 1 : (n > 8 ? 8 : n); }
     // host-side plan of one call (dry run, no device): one line per conv / linear / GroupNorm / LayerNorm / attention op with
     // its shape and the kernel choice (CPU test tier: control flow of both configs and of the lockstep path)
@@ -120,6 +121,8 @@ class Engine {
     std::vector<std::pair<std::string, std::vector<float>>> staging_;
     float* wpool_ = nullptr;
     float* u8_stage_ = nullptr; size_t u8_stage_bytes_ = 0;   // fp32 copy of a uint8 input clip (forward_u8)
+    int* status_ = nullptr;      // sticky non-finite status word (device)
+    cudaEvent_t ev_last_ = nullptr;   // tail of the previous forward call (cross-stream ordering of engine-owned buffers)
     int* gn_tickets_ = nullptr;  // GroupNorm fused-finalize arrival counters [2 streams][gn_ticket_count()]
     int* region_ = nullptr;      // GMFlow shifted-window region ids [4][1024]
     float* grid64_ = nullptr;    // GMFlow coordinate grid (4096, 2)

@@ -227,29 +227,34 @@ __global__ void __launch_bounds__(256) softmax_expect2_kernel(const float* __res
 
 __global__ void __launch_bounds__(256) kalman_update_kernel(const float* __restrict__ z, const float* __restrict__ zp,
                                                             const float* __restrict__ gain, float* __restrict__ out,
-                                                            size_t total, int c) {
+                                                            size_t total, int c, int* status) {
     pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float g = gain[i / c];
-    out[i] = (1.0f - g) * z[i] + g * zp[i];   // keep_arch.py:798
+    const float v = (1.0f - g) * z[i] + g * zp[i];   // keep_arch.py:798
+    out[i] = v;
+    if (status && !isfinite(v)) atomicOr(status, KEEP_STATUS_BAD_LATENT);
 }
 
 // one warp per token; ties resolve to the lowest index
 __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restrict__ logits, int tokens, int ncodes,
                                                             const float* __restrict__ codebook, int cdim,
                                                             const int* __restrict__ forced, int* __restrict__ idx_out,
-                                                            void* quant, int q_dt) {
+                                                            void* quant, int q_dt, int* status) {
     pdl_prologue();
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (tok >= tokens) return;
     const float* r = logits + (size_t)tok * ncodes;
     float best = -INFINITY;
     int bi = 0x7fffffff;
+    bool bad = false;
     for (int k = lane; k < ncodes; k += 32) {
         const float x = r[k];
+        bad = bad || !isfinite(x);
         if (x > best) { best = x; bi = k; }
     }
+    if (status && bad) atomicOr(status, KEEP_STATUS_BAD_LOGITS);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -393,12 +398,18 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 }
 
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const void* x, int dt, void* out, int o_dt, int c, int hw,
-                                                           size_t total) {
+                                                           size_t total, int* status) {
     pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
     if (i >= total) return;
     const size_t n = i / hw, p = i % hw;
-    for (int ch = 0; ch < c; ++ch) st1_any(out, o_dt, (n * c + ch) * hw + p, ld1_any(x, dt, i * c + ch));
+    bool bad = false;
+    for (int ch = 0; ch < c; ++ch) {
+        const float v = ld1_any(x, dt, i * c + ch);
+        bad = bad || !isfinite(v);
+        st1_any(out, o_dt, (n * c + ch) * hw + p, v);
+    }
+    if (status && bad) atomicOr(status, KEEP_STATUS_BAD_PIXELS);
 }
 
 // keep_processor.py:258-260: float32(crop_u8 / 255.) (the division is done in float64), BGR -> RGB, (v - 0.5) / 0.5
@@ -417,13 +428,15 @@ __global__ void __launch_bounds__(256) u8bgr_to_nchw_norm_kernel(const unsigned 
 }
 
 // B/utils/img_util.py:38-94 (tensor2img, rgb2bgr=True, min_max=(-1, 1), uint8): clamp, (x - min) / (max - min), * 255, round half even
-__global__ void __launch_bounds__(256) nhwc_to_u8bgr_kernel(const void* x, int dt, unsigned char* __restrict__ out, size_t total) {
+__global__ void __launch_bounds__(256) nhwc_to_u8bgr_kernel(const void* x, int dt, unsigned char* __restrict__ out, size_t total,
+                                                            int* status) {
     pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
     if (i >= total) return;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         float v = ld1_any(x, dt, i * 3 + ch);
+        if (status && !isfinite(v)) atomicOr(status, KEEP_STATUS_BAD_PIXELS);
         v = fminf(fmaxf(v, -1.0f), 1.0f);
         v = (v - (-1.0f)) / (1.0f - (-1.0f));
         v = v * 255.0f;
@@ -433,7 +446,7 @@ __global__ void __launch_bounds__(256) nhwc_to_u8bgr_kernel(const void* x, int d
 
 // arch_util.py:113-144 -> F.grid_sample(bilinear, zeros, align_corners=True)
 __global__ void __launch_bounds__(256) flow_warp_kernel(const void* img, int dt, const float* __restrict__ flow, void* out,
-                                                        int o_dt, int h, int w, int c, size_t total) {
+                                                        int o_dt, int h, int w, int c, size_t total, int* status) {
     pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*h*w
     if (i >= total) return;
@@ -441,6 +454,7 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const void* img, int dt,
     const int y = (int)((i / w) % h);
     const size_t n = i / ((size_t)w * h);
     const float vx = (float)x + flow[2 * i], vy = (float)y + flow[2 * i + 1];
+    if (status && !(isfinite(vx) && isfinite(vy))) atomicOr(status, KEEP_STATUS_BAD_FLOW);
     const float wm = (float)max(w - 1, 1), hm = (float)max(h - 1, 1);
     const float gx = 2.0f * vx / wm - 1.0f, gy = 2.0f * vy / hm - 1.0f;
     const float ix = ((gx + 1.0f) / 2.0f) * (float)(w - 1), iy = ((gy + 1.0f) / 2.0f) * (float)(h - 1);
@@ -594,16 +608,16 @@ void softmax_expect2(const float* sc, long long rows, int L, int Lq, const float
     CUDA_CHECK(cudaGetLastError());
 }
 
-void kalman_update(const float* z, const float* zp, const float* gain, float* out, int pixels, int c, cudaStream_t s) {
+void kalman_update(const float* z, const float* zp, const float* gain, float* out, int pixels, int c, cudaStream_t s, int* status) {
     const size_t total = (size_t)pixels * c;
-    launch_k(kalman_update_kernel, dim3(blocks_for(total)), dim3(256), 0, s, z, zp, gain, out, total, c);
+    launch_k(kalman_update_kernel, dim3(blocks_for(total)), dim3(256), 0, s, z, zp, gain, out, total, c, status);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void argmax_gather(const float* logits, int tokens, int ncodes, const float* codebook, int cdim, const int* forced_idx,
-                   int* idx_out, void* quant, int q_dt, cudaStream_t s) {
+                   int* idx_out, void* quant, int q_dt, cudaStream_t s, int* status) {
     launch_k(argmax_gather_kernel, dim3(blocks_for((size_t)tokens, 8)), dim3(256), 0, s, logits, tokens, ncodes, codebook, cdim, forced_idx,
-                                                                      idx_out, quant, q_dt);
+                                                                      idx_out, quant, q_dt, status);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -629,9 +643,9 @@ void nchw_to_nhwc(const float* x, void* out, int o_dt, int n, int c, int h, int 
     CUDA_CHECK(cudaGetLastError());
 }
 
-void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s) {
+void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s, int* status) {
     const size_t total = (size_t)n * h * w;
-    launch_k(nhwc_to_nchw_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, dt, out, out_dt, c, h * w, total);
+    launch_k(nhwc_to_nchw_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, dt, out, out_dt, c, h * w, total, status);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -641,15 +655,15 @@ void u8bgr_to_nchw_norm(const unsigned char* x, float* out, int n, int h, int w,
     CUDA_CHECK(cudaGetLastError());
 }
 
-void nhwc_to_u8bgr(const void* x, int dt, unsigned char* out, int n, int h, int w, cudaStream_t s) {
+void nhwc_to_u8bgr(const void* x, int dt, unsigned char* out, int n, int h, int w, cudaStream_t s, int* status) {
     const size_t total = (size_t)n * h * w;
-    launch_k(nhwc_to_u8bgr_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, dt, out, total);
+    launch_k(nhwc_to_u8bgr_kernel, dim3(blocks_for(total)), dim3(256), 0, s, x, dt, out, total, status);
     CUDA_CHECK(cudaGetLastError());
 }
 
-void flow_warp(const void* img, int dt, const float* flow, void* out, int o_dt, int n, int h, int w, int c, cudaStream_t s) {
+void flow_warp(const void* img, int dt, const float* flow, void* out, int o_dt, int n, int h, int w, int c, cudaStream_t s, int* status) {
     const size_t total = (size_t)n * h * w;
-    launch_k(flow_warp_kernel, dim3(blocks_for(total)), dim3(256), 0, s, img, dt, flow, out, o_dt, h, w, c, total);
+    launch_k(flow_warp_kernel, dim3(blocks_for(total)), dim3(256), 0, s, img, dt, flow, out, o_dt, h, w, c, total, status);
     CUDA_CHECK(cudaGetLastError());
 }
 

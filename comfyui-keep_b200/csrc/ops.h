@@ -1,5 +1,6 @@
 // keep_b200 — host-side launchers for the hand-written kernels (all on one stream).
 #pragma once
+#include "../../include/keep_b200.h"
 #include "common.h"
 
 namespace keep {
@@ -73,6 +74,12 @@ void layernorm(const float* x, int rows, int c, const float* g, const float* b, 
                const float* res, float* out, const float* add2, int add2_rows, float* out2, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------
+// sticky non-finite status word (keep_status, include/keep_b200.h): kernels at the joints of the path OR a bit into an
+// engine-owned device int when they see inf / NaN -- no host synchronisation, the caller reads it after its own sync
+// ------------------------------------------------------------------------------------------
+// (bits: KEEP_STATUS_* in the public header)
+
+// ------------------------------------------------------------------------------------------
 // elementwise
 // ------------------------------------------------------------------------------------------
 // out = act_o( act_a(A*sa+ba) + act_b(B*sb+bb) ), per-(n,c) affines optional, B optional
@@ -96,10 +103,10 @@ void softmax_rows(float* s, long long rows, int L, const int* region, int n_win,
 //   v is indexed [(row / Lq) * v_bstride + 2*k]  (v_bstride = 0 shares one value table across batches)
 void softmax_expect2(const float* s, long long rows, int L, int Lq, const float* v, long long v_bstride, const float* sub,
                      float* out, cudaStream_t s_);
-void kalman_update(const float* z, const float* zp, const float* gain, float* out, int pixels, int c, cudaStream_t s);
+void kalman_update(const float* z, const float* zp, const float* gain, float* out, int pixels, int c, cudaStream_t s, int* status = nullptr);
 // logits (tokens, ncodes) -> idx (tokens) int32, quant (tokens, cdim) = codebook[idx]; forced idx optional
 void argmax_gather(const float* logits, int tokens, int ncodes, const float* codebook, int cdim,
-                   const int* forced_idx, int* idx_out, void* quant, int q_dt, cudaStream_t s);
+                   const int* forced_idx, int* idx_out, void* quant, int q_dt, cudaStream_t s, int* status = nullptr);
 // VectorQuantizer.forward (vqgan_arch.py:37-76): z (tokens, cdim) -> idx = argmin_j ||z - e_j||^2 (int32, ties -> lowest j),
 // zq (tokens, cdim) = e[idx] (straight_through: the forward value z + (e[idx] - z)), dmin (tokens) the winning distance;
 // zq / dmin optional
@@ -113,13 +120,13 @@ void sparse_causal_gather(const float* kv, float* out, int b, int T, int L, int 
 // ------------------------------------------------------------------------------------------
 // x NCHW fp32 [-1,1] -> NHWC (dt): mode 0 copy ; mode 1 GMFlow normalisation ((x+1)/2 - mean)/std
 void nchw_to_nhwc(const float* x, void* out, int o_dt, int n, int c, int h, int w, int mode, cudaStream_t s);
-void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s);
+void nhwc_to_nchw(const void* x, int dt, void* out, int out_dt, int n, int c, int h, int w, cudaStream_t s, int* status = nullptr);
 // caller-side conversions of keep_processor.py folded in: uint8 BGR HWC crops -> fp32 RGB NCHW in [-1, 1]
 // (img2tensor(crop / 255., bgr2rgb=True) + normalize(0.5, 0.5)), and fp32 RGB NHWC -> uint8 BGR HWC (tensor2img, min_max (-1, 1))
 void u8bgr_to_nchw_norm(const unsigned char* x, float* out, int n, int h, int w, cudaStream_t s);
-void nhwc_to_u8bgr(const void* x, int dt, unsigned char* out, int n, int h, int w, cudaStream_t s);
+void nhwc_to_u8bgr(const void* x, int dt, unsigned char* out, int n, int h, int w, cudaStream_t s, int* status = nullptr);
 // bilinear warp (grid_sample bilinear / zeros / align_corners=True), img NHWC c channels, flow (n,h,w,2) px
-void flow_warp(const void* img, int dt, const float* flow, void* out, int o_dt, int n, int h, int w, int c, cudaStream_t s);
+void flow_warp(const void* img, int dt, const float* flow, void* out, int o_dt, int n, int h, int w, int c, cudaStream_t s, int* status = nullptr);
 // GMFlow: add windowed sine position embedding in place on (n, h, w, c) fp32  (utils.py:66-86)
 void add_window_sine_pos(float* x, int n, int h, int w, int c, int splits, cudaStream_t s);
 // GMFlow window partition with optional cyclic shift: (n, h, w, c) -> (n*k*k, h/k*w/k, c) and back

@@ -37,6 +37,9 @@ FLAG_CUDA_GRAPH = 8
 FLAG_TC_WIDE = 16
 FLAG_BATCH_CLIPS = 32
 FLAG_PLAN_ONLY = 256
+# The product default = the mode bench.py measures and the parity tests hold to the pixel bar: tcgen05 tensor cores with
+# split-precision (fp32-grade) operands, one CUDA graph per clip length.  flags=0 is still the exact-fp32 CUDA-core engine.
+DEFAULT_FLAGS = FLAG_TCGEN05 | FLAG_TC_SPLIT3 | FLAG_CUDA_GRAPH
 
 
 def lib_path():
@@ -72,6 +75,7 @@ def load_library():
     lib.keep_set_batch_clips.argtypes = [vp, ci]
     lib.keep_plan_dump.argtypes = [vp, ci, ci, ctypes.c_char_p]
     lib.keep_destroy.argtypes = [vp]
+    lib.keep_status.argtypes = [vp, ci, ctypes.POINTER(ci)]
     lib.keep_launch_count.argtypes = [vp]
     lib.keep_launch_count.restype = ctypes.c_longlong
     lib.keep_profile_enable.argtypes = [vp, ci]
@@ -121,7 +125,7 @@ def config_name(cfg):
 class KeepNetB200(nn.Module):
     """Drop-in replacement for the reference `KEEP` module on the inference path."""
 
-    def __init__(self, flags=0, concurrent_clips=1, batch_clips=1, check_finite=False, **cfg):
+    def __init__(self, flags=None, concurrent_clips=1, batch_clips=1, check_finite=False, plan_only=False, **cfg):
         """concurrent_clips > 1: a batch of b > 1 clips is spread over that many engine replicas, each on its
         own CUDA stream.  Clips are independent (keep_processor.py:263-270) and one clip's serial per-frame chain leaves most
         SMs idle most of the time, so two clips in flight raise the throughput of a stream of clips; results are bitwise those
@@ -130,16 +134,22 @@ class KeepNetB200(nn.Module):
         # batch_clips > 1 (the other half of N2): a batch of b > 1 clips goes to ONE engine, which walks groups of that many clips
         # through the per-frame recurrence in lockstep (KEEP_FLAG_BATCH_CLIPS: one batched hq_encoder / transformer / generator
         # pass per frame index).  Results equal the clip-by-clip loop up to fp32 summation order (different K-splits).
-        # check_finite: after every call, one reduction over the output + a host sync; raises instead of handing inf / NaN frames
-        # to the caller (the fp16-pair tensor-core mode overflows on raw features beyond 65504 -- see KEEP_FLAG_TC_WIDE).  Off by
-        # default: the call contract is "no host synchronisation inside forward" (SURVEY.md §8b).
+        # check_finite: after every call, read the engine's sticky non-finite status word (one host sync, no extra pass over the
+        # frames) and raise instead of handing wrong / NaN frames to the caller (the fp16-pair tensor-core mode overflows on raw
+        # features beyond 65504 -- see KEEP_FLAG_TC_WIDE).  Off by default: the call contract is "no host synchronisation inside
+        # forward" (SURVEY.md §8b); callers that keep it off can poll `net.status()` after their own sync.
         self._check_finite = bool(check_finite)
         self._batch = max(1, min(8, int(batch_clips)))
         self._nrep = max(1, int(concurrent_clips))
         self._replicas = []           # extra engines (keep_handle) beyond the primary one, created on first use
         self._rep_streams = []
         self.config = config_name(cfg)   # 'KEEP' | 'Asian'; the engine reads the fusion points off the tensor names
-        self._flags = int(flags) | (FLAG_BATCH_CLIPS if self._batch > 1 else 0)
+        # flags=None: DEFAULT_FLAGS (tcgen05 split precision + CUDA graph).  plan_only (tests): `.to('cuda')` builds a host-side
+        # KEEP_FLAG_PLAN_ONLY engine (strict key check + workspace plan) and needs no device; the call itself still raises.
+        self._plan_only = bool(plan_only)
+        self._flags = (DEFAULT_FLAGS if flags is None else int(flags)) | (FLAG_BATCH_CLIPS if self._batch > 1 else 0)
+        if self._plan_only:
+            self._flags |= FLAG_PLAN_ONLY
         if self.config == "Asian" and (self._flags & FLAG_TC_SPLIT3):
             # four stacked CFT modulations (32^2 .. 256^2) leave raw generator features with no magnitude bound (6e4 with
             # the synthetic weights, past fp16's 65504): bf16 activation pairs on those layers (include/keep_b200.h)
@@ -205,7 +215,7 @@ class KeepNetB200(nn.Module):
                 descs[i].shape[j] = t.shape[j] if j < t.dim() else 1
         h = ctypes.c_void_p()
         dev = self._device.index if self._device.type == "cuda" and self._device.index is not None else (
-            torch.cuda.current_device() if self._device.type == "cuda" else 0)
+            torch.cuda.current_device() if (self._device.type == "cuda" and not self._plan_only) else 0)
         _check(lib, lib.keep_create(ctypes.byref(h), int(dev), descs, len(names), int(flags)), "keep_create")
         if self._batch > 1:
             _check(lib, lib.keep_set_batch_clips(h, self._batch), "keep_set_batch_clips")
@@ -222,9 +232,11 @@ class KeepNetB200(nn.Module):
             return self
         device = torch.device(device)
         if device.type == "cuda":
-            if not torch.cuda.is_available():
+            if self._plan_only:
+                device = torch.device("cuda", device.index or 0)
+            elif not torch.cuda.is_available():
                 raise RuntimeError("KeepNetB200.to(cuda): no CUDA device (no CPU fallback for the KEEP hot path)")
-            if device.index is None:
+            elif device.index is None:
                 device = torch.device("cuda", torch.cuda.current_device())
             if self._engine is None or device != self._device:
                 self._drop_engine()
@@ -285,9 +297,12 @@ class KeepNetB200(nn.Module):
             with torch.cuda.device(x.device):
                 rc = lib.keep_forward(self._engine, x.data_ptr(), b, T, out.data_ptr(), odt, None, 0, ctypes.c_void_p(stream))
             _check(lib, rc, "keep_forward")
-        if self._check_finite and not bool(torch.isfinite(out).all()):
-            raise RuntimeError("KeepNetB200: non-finite values in the restored frames (engine flags %d); if the network's raw "
-                               "features exceed fp16 range, create the engine with FLAG_TC_WIDE" % self._flags)
+        if self._check_finite:
+            st = self.status(clear=True)
+            if st:
+                raise RuntimeError("KeepNetB200: non-finite values on the path (status bits %d: 1 latent, 2 logits, 4 pixels, 8 flow; "
+                                   "engine flags %d); if the network's raw features exceed fp16 range, create the engine with "
+                                   "FLAG_TC_WIDE" % (st, self._flags))
         return out
 
     def _forward_concurrent(self, lib, x, out, odt):
@@ -342,6 +357,20 @@ class KeepNetB200(nn.Module):
                                      ctypes.c_void_p(stream))
         _check(lib, rc, "keep_forward_u8")
         return out
+
+    def status(self, clear=True):
+        """Sticky non-finite status bits of the engine(s) since the last clearing read (include/keep_b200.h `keep_status`):
+        1 latent, 2 logits, 4 output pixels, 8 flow.  Synchronises the device -- call it after your own sync (e.g. after the
+        `.cpu()` of tensor2img); 0 means every joint of the path saw finite values only."""
+        if self._engine is None:
+            return 0
+        lib = load_library()
+        bits = 0
+        for h in [self._engine] + list(self._replicas):
+            v = ctypes.c_int(0)
+            _check(lib, lib.keep_status(h, 1 if clear else 0, ctypes.byref(v)), "keep_status")
+            bits |= int(v.value)
+        return bits
 
     # ---- test hooks ----------------------------------------------------------------------------
     def launch_count(self):
@@ -417,14 +446,53 @@ def vector_quantize(z, codebook, straight_through=True):
     return zq.permute(0, 3, 1, 2).contiguous(), idx.long().unsqueeze(1), dmin
 
 
-def install_into_model_pack(model_pack, flags=0):
+def from_reference(ref_net, flags=None, **kwargs):
+    """The B200 engine carrying the weights of a reference `KEEP` module (anything with `.state_dict()` in the reference's
+    key set, after the loader's `cross_fuse -> cfa` / `fuse_convs_dict -> cft` renames, keep_model_loader.py:110-118).
+
+    This is the swap point INTEGRATION.md documents: between `net.eval()` (keep_model_loader.py:121) and the construction of
+    the pack (:140), `net = keep_b200.from_reference(net)` -- so BOTH the returned pack and the loader's cache (:142-143)
+    hold the engine, and the cache-hit path (:76-86) hands the same engine back on the second `Load KEEP Models` execution."""
+    if isinstance(ref_net, KeepNetB200):
+        return ref_net
+    net = KeepNetB200(flags=flags, cft_list=list(getattr(ref_net, "cft_list", KEEP_GENERAL_CFG["cft_list"])), **kwargs)
+    net.load_state_dict(ref_net.state_dict(), strict=True)
+    net.eval()
+    return net
+
+
+def install_into_model_pack(model_pack, flags=None, **kwargs):
     """Swap `model_pack.keep_net` (reference KEEP module) for the B200 engine, keeping its weights.
 
-    `model_pack` is the reference's KEEPModelPack (modules/keep_model_loader.py:12-61); everything else in
-    the pack (face helper, detector, parser) is left untouched."""
-    ref = model_pack.keep_net
-    net = KeepNetB200(flags=flags, cft_list=list(getattr(ref, "cft_list", KEEP_GENERAL_CFG["cft_list"])))
-    net.load_state_dict(ref.state_dict(), strict=True)
-    net.eval()
+    `model_pack` is the reference's KEEPModelPack (modules/keep_model_loader.py:12-61); everything else in the pack (face
+    helper, detector, parser) is left untouched.  NOTE: this swaps ONE pack.  The loader caches a second pack object holding
+    the same reference module (:142-143) and builds a fresh pack from it on every cache hit (:76-86) -- use
+    `install_into_loader(loader)` (or `from_reference` inside the loader) so that later loads get the engine too."""
+    net = from_reference(model_pack.keep_net, flags=flags, **kwargs)
     model_pack.keep_net = net
     return net
+
+
+def install_into_loader(loader, flags=None, **kwargs):
+    """Patch a reference `KEEPModelLoader` instance (modules/keep_model_loader.py:63-145) in place, without editing the
+    reference: `load_keep_model_pack` is wrapped so that the pack it returns AND the pack it caches (`loader.loaded_models`,
+    :142-143) both hold the B200 engine -- first load and every cache hit (:76-86) hand out the same `KeepNetB200`.
+    Idempotent; returns the loader."""
+    if getattr(loader, "_keep_b200_installed", False):
+        return loader
+    inner = loader.load_keep_model_pack
+
+    def load_keep_model_pack(*a, **kw):
+        pack = inner(*a, **kw)
+        if not isinstance(pack.keep_net, KeepNetB200):
+            ref = pack.keep_net
+            net = from_reference(ref, flags=flags, **kwargs)
+            pack.keep_net = net
+            for cached in getattr(loader, "loaded_models", {}).values():
+                if cached.keep_net is ref:
+                    cached.keep_net = net
+        return pack
+
+    loader.load_keep_model_pack = load_keep_model_pack
+    loader._keep_b200_installed = True
+    return loader

@@ -39,7 +39,7 @@ typedef struct {
 enum { KEEP_OUT_F32 = 0, KEEP_OUT_F16 = 1, KEEP_OUT_U8_BGR = 2 };
 enum {
     KEEP_FLAG_DEFAULT = 0,
-    KEEP_FLAG_FP16_FEATURES = 1, /* store conv feature maps as fp16 in HBM */
+    KEEP_FLAG_FP16_FEATURES = 1, /* RESERVED: fp16 feature-map storage; keep_create rejects it (feature maps are fp32) */
     KEEP_FLAG_TCGEN05 = 2,       /* run eligible convolutions / GEMMs on the tcgen05 tensor-core kernel */
     KEEP_FLAG_TC_SPLIT3 = 4,     /* with TCGEN05: split-precision operands (A=Ah+Al, W=Wh+Wl, 3 MMAs) -> fp32-grade results */
     KEEP_FLAG_CUDA_GRAPH = 8,    /* capture one clip forward per T into a CUDA graph after the first (eager) call and replay it */
@@ -85,6 +85,15 @@ int keep_forward_u8(keep_handle h, const unsigned char* x_u8_dev, int b, int T, 
 int keep_destroy(keep_handle h);
 
 const char* keep_last_error(void);
+
+/* Sticky non-finite status of the engine since the last clearing read.  keep_forward never synchronises, so it cannot look
+ * at its own result; instead the kernels at the joints of the path (flow warp, Kalman update, logits -> argmax, final frame
+ * conversion) OR a bit into a device word when they meet inf / NaN -- e.g. an fp16-pair operand overflow on raw features
+ * beyond 65504 (see KEEP_FLAG_TC_WIDE), which would otherwise reach the caller as a silently wrong code index or a NaN frame.
+ * This call synchronises the device, so make it after your own sync (the caller's .cpu() in tensor2img, keep_processor.py:273).
+ * Replaces nothing in the reference (PyTorch fp32 does not overflow here). */
+enum { KEEP_STATUS_BAD_LATENT = 1, KEEP_STATUS_BAD_LOGITS = 2, KEEP_STATUS_BAD_PIXELS = 4, KEEP_STATUS_BAD_FLOW = 8 };
+int keep_status(keep_handle h, int clear, int* status_out);
 
 /* Number of kernels the engine launched since creation (bench.py `gpu_launches`). */
 long long keep_launch_count(keep_handle h);

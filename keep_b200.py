@@ -21,6 +21,9 @@ KEEP_GENERAL_CFG = pkg.KEEP_GENERAL_CFG
 KEEP_ASIAN_CFG = pkg.KEEP_ASIAN_CFG
 vector_quantize = pkg.vector_quantize
 install_into_model_pack = pkg.install_into_model_pack
+install_into_loader = pkg.install_into_loader
+from_reference = pkg.from_reference
+DEFAULT_FLAGS = pkg.DEFAULT_FLAGS
 build = pkg.build
 lib_path = pkg.lib_path
 keep_net = sys.modules[_NAME + ".keep_net"]

@@ -61,6 +61,7 @@ CASES = (  # fixture name, model config, T, coherent clip, clip seed
     ("T2_noise", "KEEP", 2, False, 1234),
     ("asian_T2_coherent", "Asian", 2, True, 1234),   # CFT at 32/64/128/256, none at 16
     ("T20_coherent", "KEEP", 20, True, 1234),        # BASELINE.json configs[1] at full size (compact fixture, see below)
+    ("T12_coherent", "KEEP", 12, True, 1236),        # the 12-frame tail clip of BASELINE.json configs[4] (512 frames = 25 x 20 + 12)
 )
 
 

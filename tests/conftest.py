@@ -12,6 +12,27 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# Parity numbers measured by the GPU tier: every test appends lines through `parity_report(...)`; they go to
+# gpurun_out/parity_report.txt AND are printed in the terminal summary, so the run's log carries them (the driver keeps the
+# log, not gpurun_out/).
+_PARITY_LINES = []
+
+
+def parity_report(tag, **kw):
+    line = tag + " " + " ".join("%s=%s" % (k, v) for k, v in kw.items())
+    _PARITY_LINES.append(line)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.txt"), "a") as f:
+        f.write(line + "\n")
+
+
+def pytest_terminal_summary(terminalreporter):
+    if _PARITY_LINES:
+        terminalreporter.section("parity report (engine vs oracle / reference fixtures)")
+        for line in _PARITY_LINES:
+            terminalreporter.write_line(line)
+
+
 @pytest.fixture(scope="session")
 def keep_mod():
     import keep_b200

@@ -82,6 +82,32 @@ def test_plan_only_engine_checks_keys_and_sizes_workspace(keep_mod, lib, state_d
     net._drop_engine()
 
 
+def test_default_flags_and_rejected_flags(keep_mod, lib, state_dict):
+    """The default-constructed module is the measured engine (tcgen05 split precision + CUDA graph), 'Asian' adds the wide
+    operand range; the reserved fp16-feature flag is refused by the C side instead of failing inside the first forward."""
+    kn = keep_mod.keep_net
+    assert kn.DEFAULT_FLAGS == kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3 | kn.FLAG_CUDA_GRAPH
+    assert keep_mod.KeepNetB200()._flags == kn.DEFAULT_FLAGS
+    assert keep_mod.KeepNetB200(flags=0)._flags == 0                                  # exact-fp32 CUDA-core engine, on request
+    assert keep_mod.KeepNetB200(**kn.KEEP_ASIAN_CFG)._flags == kn.DEFAULT_FLAGS | kn.FLAG_TC_WIDE
+    net = keep_mod.KeepNetB200()
+    net.load_state_dict(state_dict, strict=True)
+    for bad in (kn.FLAG_FP16_FEATURES, kn.FLAG_FP16_FEATURES | kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3):
+        with pytest.raises(RuntimeError, match="FP16_FEATURES"):
+            net._make_engine(flags=bad | kn.FLAG_PLAN_ONLY)
+    # a plan-only module walks the residency calls without a device (what the reference-host lifecycle test relies on)
+    po = keep_mod.KeepNetB200(plan_only=True)
+    po.load_state_dict(state_dict, strict=True)
+    po.to("cuda")
+    assert po._engine is not None and lib.keep_workspace_bytes(po._engine, 1, 2) > 0
+    st = ctypes.c_int(-1)
+    assert lib.keep_status(po._engine, 1, ctypes.byref(st)) == 0 and st.value == 0
+    with pytest.raises(RuntimeError):
+        po(torch.zeros(1, 2, 3, 512, 512), need_upscale=False)
+    po.to("cpu")
+    assert po._engine is None
+
+
 def test_strict_state_dict_and_no_cpu_fallback(keep_mod, state_dict):
     net = keep_mod.KeepNetB200()
     bad = dict(state_dict)

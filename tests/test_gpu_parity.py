@@ -48,9 +48,8 @@ def oracle_T2(state_dict):
 
 
 def _report(tag, **kw):
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_report.txt"), "a") as f:
-        f.write(tag + " " + " ".join("%s=%s" % (k, v) for k, v in kw.items()) + "\n")
+    from conftest import parity_report
+    parity_report(tag, **kw)
 
 
 NEAR_TIE = 2e-2   # ~3x the reference's own fp32-vs-fp64 logit spread (5.8e-3, tests/golden/pin_report.json)

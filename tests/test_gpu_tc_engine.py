@@ -39,9 +39,8 @@ def oracle_T2(state_dict):
 
 
 def _report(tag, **kw):
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_report_tc.txt"), "a") as f:
-        f.write(tag + " " + " ".join("%s=%s" % (k, v) for k, v in kw.items()) + "\n")
+    from conftest import parity_report
+    parity_report(tag, **kw)
 
 
 def test_tc_teacher_forced_T2(net_tc, oracle_T2):

@@ -23,9 +23,8 @@ def psnr(a, b):
 
 
 def _report(tag, **kw):
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_report.txt"), "a") as f:
-        f.write(tag + " " + " ".join("%s=%s" % (k, v) for k, v in kw.items()) + "\n")
+    from conftest import parity_report
+    parity_report(tag, **kw)
 
 
 @pytest.fixture(scope="module", params=["fp32", "tc3"])

@@ -17,9 +17,8 @@ NEAR_TIE = 2e-2
 
 
 def _report(tag, **kw):
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_report.txt"), "a") as f:
-        f.write(tag + " " + " ".join("%s=%s" % (k, v) for k, v in kw.items()) + "\n")
+    from conftest import parity_report
+    parity_report(tag, **kw)
 
 
 def _make(keep_mod, state_dict, mode, **kw):
