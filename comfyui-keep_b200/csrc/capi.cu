@@ -26,7 +26,8 @@ static thread_local std::string g_err;
         return -2;                                     \
     }
 
-int keepop_conv2d_tc(const ConvArgs& a, const float* w_oihw_host, int passes, cudaStream_t s);   // conv_tcgen05.cu
+int keepop_conv2d_tc(const ConvArgs& a, const float* w_oihw_host, int passes, cudaStream_t s, const float* gn_gamma = nullptr,
+                     const float* gn_beta = nullptr, float* gn_scale = nullptr, float* gn_shift = nullptr);   // conv_tcgen05.cu
 
 namespace keep {
 void stamp_set_conv_simt(unsigned long long*); void stamp_set_conv_small(unsigned long long*); void stamp_set_conv_tc(unsigned long long*);
@@ -187,10 +188,10 @@ struct DevBuf {
 };
 }  // namespace
 
-int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, const float* weight_host, const float* bias_host,
-                  int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
-                  const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
-                  float* out_dev, void* stream) {
+static int conv2d_op(int use_tc, const float* x_dev, int n, int h, int w, int cin, const float* weight_host, const float* bias_host,
+                     int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
+                     const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
+                     float* out_dev, void* stream, const float* gn_gamma, const float* gn_beta, float* gn_scale, float* gn_shift) {
     KEEP_API_BEGIN
     cudaStream_t s = (cudaStream_t)stream;
     std::vector<float> packed((size_t)cout * cin * kh * kw);
@@ -217,10 +218,11 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
     }
     if (use_tc) {   // 1: fp16 operands; 3: split precision; 19 (= 3 | 16): split precision with bf16 activation pairs (KEEP_FLAG_TC_WIDE)
         a.a_wide = (use_tc & 16) ? 1 : 0;
-        int rc = keepop_conv2d_tc(a, weight_host, (use_tc & 3) == 3 ? 3 : 1, s);
+        int rc = keepop_conv2d_tc(a, weight_host, (use_tc & 3) == 3 ? 3 : 1, s, gn_gamma, gn_beta, gn_scale, gn_shift);
         CUDA_CHECK(cudaStreamSynchronize(s));
         return rc;
     }
+    KEEP_CHECK(!gn_scale, "keepop_conv2d_gn: statistics are emitted by the tcgen05 path only (use_tc = 1 or 3)");
     a.splitk = conv_pick_splitk(a);
     DevBuf part(a.splitk > 1 ? (size_t)a.splitk * n * a.ho * a.wo * cout * 4 : 0);
     a.partial = (float*)part.p;
@@ -228,6 +230,26 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
     CUDA_CHECK(cudaStreamSynchronize(s));
     return 0;
     KEEP_API_END
+}
+
+int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, const float* weight_host, const float* bias_host,
+                  int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
+                  const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
+                  float* out_dev, void* stream) {
+    return conv2d_op(use_tc, x_dev, n, h, w, cin, weight_host, bias_host, cout, kh, kw, stride, pad_t, pad_l, pad_b, pad_r, up, pre_scale_dev,
+                     pre_shift_dev, pre_act, act, res_dev, out_dev, stream, nullptr, nullptr, nullptr, nullptr);
+}
+
+int keepop_conv2d_gn(int use_tc, const float* x_dev, int n, int h, int w, int cin, const float* weight_host, const float* bias_host,
+                     int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
+                     const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
+                     float* out_dev, const float* gn_gamma_dev, const float* gn_beta_dev, float* gn_scale_dev, float* gn_shift_dev,
+                     void* stream) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(gn_gamma_dev && gn_beta_dev && gn_scale_dev && gn_shift_dev, "keepop_conv2d_gn: null GroupNorm argument");
+    KEEP_API_END
+    return conv2d_op(use_tc, x_dev, n, h, w, cin, weight_host, bias_host, cout, kh, kw, stride, pad_t, pad_l, pad_b, pad_r, up, pre_scale_dev,
+                     pre_shift_dev, pre_act, act, res_dev, out_dev, stream, gn_gamma_dev, gn_beta_dev, gn_scale_dev, gn_shift_dev);
 }
 
 // debug: kernel-start timeline.  stamps = device buffer of 1 + 65536 uint64 (null = off); launch log = host-side names

@@ -53,6 +53,9 @@ struct Tensor {
     void* p = nullptr;
     int n = 0, h = 0, w = 0, c = 0;
     DType dt = F32;
+    // GroupNorm(32) partial statistics of this tensor written by the kernel that produced it ([n][gn_P][32][2] fp32; see
+    // ConvArgs::gn_part): consumed (and released) by the one Engine::gn() that normalises the tensor, else by tfree()
+    float* gn_part = nullptr; int gn_P = 0;
     size_t numel() const { return (size_t)n * h * w * c; }
     size_t bytes() const { return numel() * dtype_size(dt); }
     size_t rows() const { return (size_t)n * h * w; }

@@ -202,13 +202,19 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_simt_kernel(const ConvArg
 }
 
 // four consecutive outputs per thread (MN and cout are multiples of 4), all K-split loads of a thread in flight at once;
-// partials are summed in split order -> deterministic
+// partials are summed in split order -> deterministic.
+// GN (gn_part != null; MN % 1024 == 0, cout in {128, 256, 512}): the block also emits GroupNorm(32) partial statistics of
+// the final values it writes -- its 1024 consecutive elements are 1024 / cout whole pixels of one image, every group has
+// exactly 8 of the block's threads; 32 threads add them up in a fixed order -> one slot gn_part[img][slot][32][2]
+template <bool GN>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
                                                             const float* __restrict__ bias, int act, const void* res,
-                                                            int res_dt, void* out, int out_dt) {
+                                                            int res_dt, void* out, int out_dt, float* __restrict__ gn_part, int gn_P,
+                                                            long long img_elems) {
     pdl_prologue();
+    __shared__ float2 s_gn[GN ? 256 : 1];
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= MN) return;
+    if (!GN && i >= MN) return;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     int z = 0;
     for (; z + 4 <= splitk; z += 4) {
@@ -234,6 +240,23 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     }
     if (out_dt == F32) st4(reinterpret_cast<float*>(out), (size_t)i, v);
     else st4(reinterpret_cast<__half*>(out), (size_t)i, v);
+    if (GN) {
+        s_gn[threadIdx.x] = make_float2((v.x + v.y) + (v.z + v.w), fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w));
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int g = threadIdx.x, tpp = cout >> 2, tpg = cout >> 7;   // threads per pixel / per group (cpg / 4)
+            float ss = 0.0f, qq = 0.0f;
+            for (int p = 0; p < 256 / tpp; ++p)
+                for (int k = 0; k < tpg; ++k) {
+                    const float2 e = s_gn[p * tpp + g * tpg + k];
+                    ss += e.x; qq += e.y;
+                }
+            const long long e0 = (long long)blockIdx.x * 1024;
+            const long long img = e0 / img_elems;
+            const long long slot = (e0 - img * img_elems) >> 10;
+            *reinterpret_cast<float2*>(gn_part + ((size_t)(img * gn_P + slot) * 32 + g) * 2) = make_float2(ss, qq);
+        }
+    }
 }
 __global__ void __launch_bounds__(256) splitk_reduce1_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
                                                              const float* __restrict__ bias, int act, const void* res,
@@ -263,11 +286,18 @@ int conv_pick_splitk(const ConvArgs& a) {
 }
 
 void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
-                   int res_dt, void* out, int out_dt, cudaStream_t s) {
-    if (MN % 4 != 0 || cout % 4 != 0)
+                   int res_dt, void* out, int out_dt, cudaStream_t s, float* gn_part, int gn_P, long long hw) {
+    if (gn_part) {
+        const long long img_elems = hw * cout;
+        KEEP_CHECK(MN % 1024 == 0 && img_elems % 1024 == 0 && (cout == 128 || cout == 256 || cout == 512) && gn_P == img_elems / 1024,
+                   "splitk_reduce: layer cannot emit GroupNorm statistics (MN %lld, cout %d)", MN, cout);
+        launch_k(splitk_reduce_kernel<true>, dim3((unsigned)(MN / 1024)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out,
+                 out_dt, gn_part, gn_P, img_elems);
+    } else if (MN % 4 != 0 || cout % 4 != 0)
         launch_k(splitk_reduce1_kernel, dim3(cdiv(MN, 256)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
     else
-        launch_k(splitk_reduce_kernel, dim3(cdiv(MN, 1024)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
+        launch_k(splitk_reduce_kernel<false>, dim3(cdiv(MN, 1024)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt,
+                 (float*)nullptr, 0, 0LL);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -285,7 +315,7 @@ void conv2d_simt(const ConvArgs& a, cudaStream_t s) {
     CUDA_CHECK(cudaGetLastError());
     if (a.splitk > 1) {
         const long long MN = M * a.cout;
-        splitk_reduce(a.partial, a.splitk, MN, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);
+        splitk_reduce(a.partial, a.splitk, MN, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);   // (no statistics on this path)
     }
 }
 

@@ -638,7 +638,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge after divergent stores
                 tmem_ld16(t0 + (uint32_t)j, rr);
                 const int nn = n0 + j;
-                const bool live = ok && nn < a.cout;       // cout % 16 == 0
+                const bool col_ok = nn < a.cout;           // cout % 16 == 0 (warp-uniform)
+                const bool live = ok && col_ok;
                 const size_t off = (size_t)pixel * a.cout + nn;
                 float4 rs[4];
                 const bool has_res = live && !partial_out && a.res != nullptr;
@@ -655,14 +656,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
 #ifdef KEEP_TC_EPI_TRACE
                 if (threadIdx.x == 0 && trace_e == 0) TC_TRACE(8, j >> 4);
 #endif
-                if (!live) continue;
+                if (!col_ok || (!live && !a.gn_part)) continue;
                 float v[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
                 if (partial_out) {
-                    float* o = a.partial + (size_t)ks * a.M * a.cout + off;
-                    stg256(o, v);
-                    stg256(o + 8, v + 8);
+                    if (live) {
+                        float* o = a.partial + (size_t)ks * a.M * a.cout + off;
+                        stg256(o, v);
+                        stg256(o + 8, v + 8);
+                    }
 #ifdef KEEP_TC_EPI_TRACE
                     if (threadIdx.x == 0 && trace_e == 0) TC_TRACE(9, j >> 4);
 #endif
@@ -686,6 +689,49 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 if (has_res) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { v[4 * e] += rs[e].x; v[4 * e + 1] += rs[e].y; v[4 * e + 2] += rs[e].z; v[4 * e + 3] += rs[e].w; }
+                }
+                if (a.gn_part) {
+                    // GroupNorm(32) statistics of the final values, for the consumer's normalisation (vqgan_arch.py:16-17): this
+                    // chunk's 16 channels are 16 / cpg groups; per lane (= pixel) group sums, then a warp reduce-scatter over the
+                    // 32 pixels in a fixed tree (deterministic): 16 values -> 16 shuffles; lane 2i ends up with value i
+                    float w16[16];
+                    const int cpg = a.gn_cpg;               // 2, 4, 8 or 16 (warp-uniform)
+                    {
+                        float gs[8], gq[8];                 // channel pairs first, then pairs of pairs up to the group width
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            gs[g] = ok ? v[2 * g] + v[2 * g + 1] : 0.0f;
+                            gq[g] = ok ? fmaf(v[2 * g], v[2 * g], v[2 * g + 1] * v[2 * g + 1]) : 0.0f;
+                        }
+                        if (cpg >= 4) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) { gs[g] = gs[2 * g] + gs[2 * g + 1]; gq[g] = gq[2 * g] + gq[2 * g + 1]; }
+                        }
+                        if (cpg >= 8) {
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) { gs[g] = gs[2 * g] + gs[2 * g + 1]; gq[g] = gq[2 * g] + gq[2 * g + 1]; }
+                        }
+                        if (cpg >= 16) { gs[0] += gs[1]; gq[0] += gq[1]; }
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) { w16[2 * g] = gs[g]; w16[2 * g + 1] = gq[g]; }   // slots >= 16 / cpg: unused
+                    }
+#pragma unroll
+                    for (int half = 8; half >= 1; half >>= 1) {
+                        const bool up = (lane & (half * 2)) != 0;
+#pragma unroll
+                        for (int e = 0; e < half; ++e) {
+                            const float keep = up ? w16[e + half] : w16[e];
+                            const float send = up ? w16[e] : w16[e + half];
+                            w16[e] = keep + __shfl_xor_sync(0xffffffffu, send, half * 2);
+                        }
+                    }
+                    w16[0] += __shfl_xor_sync(0xffffffffu, w16[0], 1);
+                    const int vi = lane >> 1, gslot = vi >> 1;
+                    if ((lane & 1) == 0 && gslot < (16 >> (cpg == 2 ? 1 : (cpg == 4 ? 2 : (cpg == 8 ? 3 : 4))))) {
+                        const int mt_in_img = ty * a.tiles_x + tx;
+                        a.gn_part[(((size_t)img * a.gn_P + (size_t)mt_in_img * 4 + warp) * 32 + (nn / cpg + gslot)) * 2 + (vi & 1)] = w16[0];
+                    }
+                    if (!ok) continue;
                 }
                 if (a.out_dt == F32) {
                     float* o = reinterpret_cast<float*>(a.out) + off;
@@ -949,6 +995,22 @@ void tc_repack_device(const float* w_kc, int cin, int cout, int taps, int bn, in
     CUDA_CHECK(cudaGetLastError());
 }
 
+// GroupNorm(32) statistics slots per image that the producing kernel writes (ConvArgs::gn_part): 4 per m tile (one per
+// epilogue warp) without split-K, one per 1024-element block of the reduce kernel with it; 0 = the layer cannot emit them
+int conv_gn_slots(const ConvArgs& a, int splitk) {
+    if (!tc_eligible(a) || a.cout % 32 != 0 || a.out_dt != F32) return 0;
+    const int cpg = a.cout / 32;
+    if (cpg != 2 && cpg != 4 && cpg != 8 && cpg != 16) return 0;
+    const long long hw = (long long)a.ho * a.wo;
+    if (splitk > 1) {
+        if (cpg < 4 || (hw * a.cout) % 1024 != 0 || 1024 % a.cout != 0) return 0;
+        return (int)(hw * a.cout / 1024);
+    }
+    const bool s2d = tc_is_s2d(a);
+    if (s2d || a.kh == 3) return cdiv(a.ho, 16) * cdiv(a.wo, 8) * 4;
+    return cdiv((long long)a.h * a.w, 128) * 4;
+}
+
 int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb) {
     static const int target = getenv("KEEP_TC_SPLIT_TARGET") ? atoi(getenv("KEEP_TC_SPLIT_TARGET")) : 80;   // CTAs to aim for
     static const int nosplit = getenv("KEEP_TC_SPLIT_MIN") ? atoi(getenv("KEEP_TC_SPLIT_MIN")) : 96;          // enough tiles: no split
@@ -1049,6 +1111,12 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     t.cluster_k = (want_cluster && splitk > 1) ? 1 : 0;
     t.splitk = splitk; t.partial = partial;
     t.act = a.act; t.res = a.res; t.res_dt = a.res_dt; t.out = a.out; t.out_dt = a.out_dt;
+    t.gn_part = nullptr; t.gn_cpg = 0; t.gn_P = 0;
+    if (a.gn_part && splitk == 1) {   // (split layers: the reduce kernel emits the statistics)
+        KEEP_CHECK(!t.cluster_k && a.cout % 32 == 0 && a.gn_P == t.tiles_y * t.tiles_x * 4, "conv2d_tc: bad GroupNorm statistics request");
+        t.gn_part = a.gn_part; t.gn_cpg = a.cout / 32; t.gn_P = a.gn_P;
+        KEEP_CHECK(t.gn_cpg == 2 || t.gn_cpg == 4 || t.gn_cpg == 8 || t.gn_cpg == 16, "conv2d_tc: GroupNorm statistics need 64..512 channels");
+    }
     t.M = (long long)a.n * a.ho * a.wo;
     KEEP_CHECK((long long)a.n * a.h * a.w < (1ll << 31) && t.M < (1ll << 31), "conv2d_tc: more than 2^31 pixels");
     int cols = 32;
@@ -1110,7 +1178,9 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     }
     launch_k(kern, dim3(grid), dim3(kThreads), smem, s, t);
     CUDA_CHECK(cudaGetLastError());
-    if (splitk > 1) splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s);
+    if (splitk > 1)
+        splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s, a.gn_part, a.gn_P,
+                      (long long)a.ho * a.wo);
     return splitk > 1 ? 2 : 1;
 }
 
@@ -1119,8 +1189,10 @@ KEEP_STAMP_SETTER(stamp_set_conv_tc)
 }  // namespace keep
 
 // op-level test hook (capi.cu): pack on the fly, run, free.  use_tc: 1 = fp16 operands, 3 = split precision
-int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, int passes, cudaStream_t s) {
+int keepop_conv2d_tc(const keep::ConvArgs& a_in, const float* w_oihw_host, int passes, cudaStream_t s, const float* gn_gamma,
+                     const float* gn_beta, float* gn_scale, float* gn_shift) {
     using namespace keep;
+    ConvArgs a = a_in;
     const int cin = a.c0 + a.c1;
     KEEP_CHECK(tc_eligible(a), "keepop_conv2d(use_tc): layer not eligible for the tcgen05 kernel");
     const long long m_tiles = a.kh == 3 ? (long long)a.n * cdiv(a.ho, 16) * cdiv(a.wo, 8) : (long long)a.n * cdiv((long long)a.h * a.w, 128);
@@ -1140,18 +1212,30 @@ int keepop_conv2d_tc(const keep::ConvArgs& a, const float* w_oihw_host, int pass
     }
     const int splitk = tc_pick_splitk(m_tiles, cdiv(a.cout, bn), cdiv(vcin, tc_cb(passes)));
     if (splitk > 1) CUDA_CHECK(cudaMalloc((void**)&part, (size_t)splitk * a.n * a.ho * a.wo * a.cout * sizeof(float)));
+    float* gn_part = nullptr;
+    if (gn_scale) {   // GroupNorm(32) statistics of the output from the producing kernel + the finalize launch
+        a.out_dt = F32;
+        const int P = conv_gn_slots(a, splitk);
+        KEEP_CHECK(P > 0, "keepop_conv2d_gn: this layer cannot emit GroupNorm statistics");
+        CUDA_CHECK(cudaMalloc((void**)&gn_part, (size_t)a.n * P * 64 * sizeof(float)));
+        CUDA_CHECK(cudaMemsetAsync(gn_part, 0xff, (size_t)a.n * P * 64 * sizeof(float), s));   // NaN pattern: every slot must be written
+        a.gn_part = gn_part; a.gn_P = P;
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     try {
         conv2d_tc(a, dw, bn, passes, splitk, part, sms, s);
+        if (gn_part) gn_finalize_parts(gn_part, a.n, a.gn_P, a.ho * a.wo, a.cout, 1e-6f, gn_gamma, gn_beta, gn_scale, gn_shift, s);
         CUDA_CHECK(cudaStreamSynchronize(s));
     } catch (...) {
         cudaFree(dw);
         cudaFree(part);
+        cudaFree(gn_part);
         throw;
     }
     cudaFree(dw);
     cudaFree(part);
+    cudaFree(gn_part);
     return 0;
 }

@@ -397,7 +397,11 @@ Tensor Engine::talloc(int n, int h, int w, int c, int dt) {
     t.p = ar_->alloc(t.bytes());
     return t;
 }
-void Engine::tfree(Tensor& t) { ar_->free(t.p); t.p = nullptr; }
+void Engine::tfree(Tensor& t) {
+    if (t.gn_part) { ar_->free(t.gn_part); t.gn_part = nullptr; }
+    ar_->free(t.p);
+    t.p = nullptr;
+}
 void Engine::afree(Aff& a) { ar_->free(a.scale); a.scale = a.shift = nullptr; }
 
 void Engine::capture(const std::string& name, const void* dev, size_t bytes) {
@@ -457,12 +461,24 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         part = ar_->alloc((size_t)a.splitk * out.numel() * sizeof(float));
         a.partial = (float*)part;
     }
+    // GroupNorm statistics of the output from the producing kernel (conv epilogue, or the split-K reduce): the consumer's
+    // gn() then needs one tiny finalize launch instead of a read pass over the tensor plus a second kernel
+    static const bool gn_fuse = !(getenv("KEEP_GN_EPILOGUE") && getenv("KEEP_GN_EPILOGUE")[0] == '0') &&
+                                !(getenv("KEEP_TC_CLUSTER") && atoi(getenv("KEEP_TC_CLUSTER")) >= 2);
+    if (o.want_stats && use_tc && gn_fuse) {
+        const int P = conv_gn_slots(a, a.splitk);
+        if (P > 0) {
+            out.gn_P = P;
+            out.gn_part = (float*)ar_->alloc((size_t)x.n * P * 64 * sizeof(float));
+            a.gn_part = out.gn_part; a.gn_P = P;
+        }
+    }
     if (plan_) {
         char line[256];
         snprintf(line, sizeof(line), "conv n=%d h=%d w=%d c0=%d c1=%d cout=%d k=%d stride=%d up=%d pre=%d act=%d res=%d kernel=%s splitk=%d bn=%d wide=%d",
                  a.n, a.h, a.w, a.c0, a.c1, a.cout, a.kh, a.stride, a.up, a.pre_scale ? a.pre_act + 1 : 0, a.act, a.res ? 1 : 0,
                  use_tc ? "tcgen05" : (use_small ? "small" : "simt"), a.splitk, bn, (a.a_wide && use_tc && passes == 3) ? 1 : 0);
-        plan_->push_back(line);
+        plan_->push_back(std::string(line) + (a.gn_part ? " gnstats=1" : ""));
     }
     if (!ar_->dry()) {
         Prof pr;
@@ -558,6 +574,17 @@ Aff Engine::gn(const Tensor& x, const std::string& prefix, const Tensor* x2) {
     const float* g = warr(prefix + ".weight");
     const float* b = warr(prefix + ".bias");
     const int hw = x.h * x.w;
+    if (x.gn_part && !x2) {   // the producing kernel left the statistics: finalize only
+        if (plan_) plan_->push_back("groupnorm n=" + std::to_string(x.n) + " hw=" + std::to_string(hw) + " c=" + std::to_string(ct) + " fused=1");
+        if (!ar_->dry()) {
+            gn_finalize_parts(x.gn_part, x.n, x.gn_P, hw, ct, 1e-6f, g, b, a.scale, a.shift, s_);
+            launches_ += 1;
+        }
+        Tensor& xm = const_cast<Tensor&>(x);   // single consumer: release the slots (stream-ordered reuse is safe)
+        ar_->free(xm.gn_part);
+        xm.gn_part = nullptr;
+        return a;
+    }
     if (plan_) plan_->push_back("groupnorm n=" + std::to_string(x.n) + " hw=" + std::to_string(hw) + " c=" + std::to_string(ct));
     double* scratch = (double*)ar_->alloc(gn_scratch_doubles(x.n, hw, std::max(x.c, x2 ? x2->c : 0)) * sizeof(double));
     if (!ar_->dry()) {
@@ -601,10 +628,10 @@ Tensor Engine::ln(const Tensor& x, const std::string& prefix, const Tensor* res,
 }
 
 // vqgan_arch.py:170-181
-Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2) {
+Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2, bool out_stats) {
     Aff a1 = gn(x, p + ".norm1", x2);
     ConvOpt o1;
-    o1.pad(1); o1.pre = &a1; o1.pre_act = ACT_SWISH; o1.in1 = x2;
+    o1.pad(1); o1.pre = &a1; o1.pre_act = ACT_SWISH; o1.in1 = x2; o1.want_stats = true;   // h feeds norm2
     Tensor h = conv(x, p + ".conv1", o1);
     afree(a1);
     Aff a2 = gn(h, p + ".norm2");
@@ -618,7 +645,7 @@ Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2
         KEEP_CHECK(!x2, "res_block: concat input needs conv_out");
     }
     ConvOpt o2;
-    o2.pad(1); o2.pre = &a2; o2.pre_act = ACT_SWISH; o2.res = &skip;
+    o2.pad(1); o2.pre = &a2; o2.pre_act = ACT_SWISH; o2.res = &skip; o2.want_stats = out_stats;
     Tensor out = conv(h, p + ".conv2", o2);
     afree(a2);
     tfree(h);
@@ -693,7 +720,7 @@ Tensor Engine::mha(const float* q, int ldq, long long sq, const float* k, int ld
 }
 
 // vqgan_arch.py:219-243
-Tensor Engine::attn_block(const Tensor& x, const std::string& p) {
+Tensor Engine::attn_block(const Tensor& x, const std::string& p, bool out_stats) {
     Aff a = gn(x, p + ".norm");
     ConvOpt o;
     o.pre = &a; o.out_dt = F32;
@@ -705,7 +732,7 @@ Tensor Engine::attn_block(const Tensor& x, const std::string& p) {
     tfree(qkv);
     O.h = x.h; O.w = x.w;
     ConvOpt po;
-    po.res = &x;
+    po.res = &x; po.want_stats = out_stats;
     Tensor out = conv(O, p + ".proj_out", po);
     tfree(O);
     return out;
@@ -724,20 +751,23 @@ Tensor Engine::encoder(const Tensor& img, const std::string& p, const std::funct
     for (int i = 0; i < 25; ++i) {
         const std::string bp = p + ".blocks." + std::to_string(i);
         const std::string kind = kEncProg[i];
+        // the next block starts with a GroupNorm of this block's output (res: norm1, attn: norm, norm_out)
+        const std::string next = i + 1 < 25 ? kEncProg[i + 1] : "";
+        const bool next_gn = next == "res" || next == "attn" || next == "norm";
         Tensor y;
         if (kind == "conv") {
             ConvOpt o;
-            o.pad(1);
+            o.pad(1); o.want_stats = next_gn;
             if (i == 24) { o.pre = &pend; o.out_dt = F32; }
             y = conv(x, bp, o);
             if (i == 24) afree(pend);
         } else if (kind == "res") {
-            y = res_block(x, bp);
+            y = res_block(x, bp, nullptr, next_gn);
         } else if (kind == "attn") {
-            y = attn_block(x, bp);
+            y = attn_block(x, bp, next_gn);
         } else if (kind == "down") {  // vqgan_arch.py:135-139
             ConvOpt o;
-            o.stride = 2; o.pad_b = 1; o.pad_r = 1;
+            o.stride = 2; o.pad_b = 1; o.pad_r = 1; o.want_stats = next_gn;
             y = conv(x, bp + ".conv", o);
         } else {  // norm_out: statistics only; apply is fused into the next conv
             pend = gn(x, bp);
@@ -1079,7 +1109,7 @@ Tensor Engine::kalman_gains(const Tensor& z_codes, int T) {
     const int save = adt_;
     adt_ = F32;
     for (int i = 0; i < 3; ++i) {
-        Tensor y = res_block(x, "kalman_filter.kalman_gain_calculator." + std::to_string(i));
+        Tensor y = res_block(x, "kalman_filter.kalman_gain_calculator." + std::to_string(i), nullptr, i < 2);
         tfree(x);
         x = y;
     }
@@ -1208,20 +1238,26 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[6], Tensor 
         pass_override_ = j >= fast_from ? 1 : 0;
         const std::string bp = "generator.blocks." + std::to_string(j);
         const std::string kind = kGenProg[j];
+        // the next block normalises this block's output -- unless a CFT / CFA hook replaces it first (then the hook's output
+        // is what gets normalised, by the stand-alone statistics kernel)
+        const std::string next = j + 1 < 25 ? kGenProg[j + 1] : "";
+        bool next_gn = next == "res" || next == "attn" || next == "norm";
+        for (int k = 0; k < 6; ++k)
+            if (kFuseGen[k] == j && (cft_on_[k] || (cfa_on_[k] && frame > 0))) next_gn = false;
         Tensor y;
         if (kind == "conv") {
             ConvOpt o;
-            o.pad(1);
+            o.pad(1); o.want_stats = next_gn;
             if (j == 24) { o.pre = &pend; o.out_dt = F32; }
             y = conv(x, bp, o);
             if (j == 24) afree(pend);
         } else if (kind == "res") {
-            y = res_block(x, bp);
+            y = res_block(x, bp, nullptr, next_gn);
         } else if (kind == "attn") {
-            y = attn_block(x, bp);
+            y = attn_block(x, bp, next_gn);
         } else if (kind == "up") {  // vqgan_arch.py:148-152: nearest x2 fused into the conv's gather
             ConvOpt o;
-            o.pad(1); o.up = 2;
+            o.pad(1); o.up = 2; o.want_stats = next_gn;
             y = conv(x, bp + ".conv", o);
         } else {
             pend = gn(x, bp);

@@ -41,6 +41,7 @@ struct ConvOpt {
     const Tensor* in1 = nullptr;
     int out_dt = -1;  // -1: engine feature-map dtype
     bool exact = false;  // force the exact-fp32 CUDA-core kernel even when the tcgen05 path is enabled
+    bool want_stats = false;   // the output's next consumer is a GroupNorm(32): let the producing kernel emit its statistics
     ConvOpt& pad(int p) { pad_t = pad_l = pad_b = pad_r = p; return *this; }
 };
 
@@ -78,8 +79,9 @@ class Engine {
     Aff inorm(const Tensor& x);
     Tensor ln(const Tensor& x, const std::string& prefix, const Tensor* res = nullptr, const float* add2 = nullptr,
               int add2_rows = 0, Tensor* out2 = nullptr);
-    Tensor res_block(const Tensor& x, const std::string& p, const Tensor* x2 = nullptr);
-    Tensor attn_block(const Tensor& x, const std::string& p);
+    // out_stats: the block's output is normalised next (GroupNorm) -> its last conv emits the statistics
+    Tensor res_block(const Tensor& x, const std::string& p, const Tensor* x2 = nullptr, bool out_stats = false);
+    Tensor attn_block(const Tensor& x, const std::string& p, bool out_stats = false);
     Tensor encoder(const Tensor& img, const std::string& p, const std::function<void(int, const Tensor&)>& tap);
     // multi-head attention on (rows, ld) matrices; writes (nb*Lq, heads*dh)
     Tensor mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv, long long sv,

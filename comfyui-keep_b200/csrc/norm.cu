@@ -297,6 +297,59 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const T* __restrict__ x, 
 }
 }  // namespace
 
+namespace {
+// Statistics emitted by the producing kernel (conv epilogue / split-K reduce): part[img][P][32][2] fp32 (sum, sum of squares per
+// slot and group).  One block per (image, 4 consecutive groups): a thread reads the 32-byte sector of a slot that holds those
+// four groups, accumulates in double, and the block reduces in a fixed order -> the consumer's per-(n, channel) affine.
+// Replaces the read pass over the whole tensor (gn_partial / gn_small) and its second kernel.
+__global__ void __launch_bounds__(256) gn_finalize_parts_kernel(const float* __restrict__ part, int P, int c, int cpg, double cnt, float eps,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_prologue();
+    __shared__ double red[8][8];
+    __shared__ float s_mean[4], s_rstd[4];
+    const int img = blockIdx.x >> 3, gq = blockIdx.x & 7;          // groups 4 gq .. 4 gq + 3
+    const float* base = part + ((size_t)img * P * 32 + (size_t)gq * 4) * 2;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = threadIdx.x; k < P; k += 256) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(base + (size_t)k * 64));
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(base + (size_t)k * 64 + 4));
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x >> 5][j] = acc[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double ss = 0, qq = 0;
+        for (int w = 0; w < 8; ++w) { ss += red[w][2 * threadIdx.x]; qq += red[w][2 * threadIdx.x + 1]; }
+        const double mean = ss / cnt;
+        double var = qq / cnt - mean * mean;
+        if (var < 0) var = 0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * cpg; i += 256) {
+        const int ch = gq * 4 * cpg + i, gl = i / cpg;
+        const float sc = gamma[ch] * s_rstd[gl];
+        scale[(size_t)img * c + ch] = sc;
+        shift[(size_t)img * c + ch] = beta[ch] - s_mean[gl] * sc;
+    }
+}
+}  // namespace
+
+void gn_finalize_parts(const float* part, int n, int P, int hw, int c, float eps, const float* gamma, const float* beta, float* scale,
+                       float* shift, cudaStream_t s) {
+    KEEP_CHECK(c % 32 == 0 && P > 0 && gamma && beta, "gn_finalize_parts: bad arguments (c=%d, P=%d)", c, P);
+    const int cpg = c / 32;
+    launch_k(gn_finalize_parts_kernel, dim3(n * 8), dim3(256), 0, s, part, P, c, cpg, (double)hw * cpg, eps, gamma, beta, scale, shift);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 size_t gn_scratch_doubles(int n, int hw, int c) { return (size_t)n * gn_num_chunks(hw, c) * c * 2; }
 
 void gn_warmup() {}

@@ -30,7 +30,12 @@ struct ConvArgs {
     int a_wide = 0;                // tcgen05 split-precision path: bf16 activation pairs (fp32 range) instead of fp16 pairs
     int pre_exact = 0;             // tcgen05 fp16-operand path: exact fp32 swish before the fp16 rounding (default: packed tanh.approx)
     long long wt_img_stride = 0;   // tcgen05 path only: per-image packed weight sets (batched A*B^T for attention)
+    // tcgen05 path only: GroupNorm(32) partial statistics of the output, written by the producing kernel (the conv epilogue,
+    // or the split-K reduce) as gn_part[n][gn_P][32][2] fp32 (sum, sum of squares) -- see conv_gn_slots()
+    float* gn_part = nullptr; int gn_P = 0;
 };
+// slots per image the producing kernel writes for a layer run with `splitk` K-splits (0: this layer cannot emit statistics)
+int conv_gn_slots(const ConvArgs& a, int splitk);
 void conv2d_simt(const ConvArgs& a, cudaStream_t s);
 // picks split-K for small-M layers; `scratch` must hold conv_splitk_scratch_floats(a) floats when splitk>1
 int conv_pick_splitk(const ConvArgs& a);
@@ -70,6 +75,9 @@ void groupnorm_affine(const void* x, int dt, int n, int hw, int c, int cpg, floa
                       const float* gamma, const float* beta, float* scale, float* shift,
                       int c_total, int c_off, double* scratch, cudaStream_t s, int* ticket_buf = nullptr);
 // LayerNorm over the last dim of (rows, c) fp32; out = LN(x)*g+b (+ res) ; out2 = out + add2[row % add2_rows]
+// statistics emitted by a producing kernel (ConvArgs::gn_part) -> per-(n, channel) affine; one small launch, fixed order
+void gn_finalize_parts(const float* part, int n, int P, int hw, int c, float eps, const float* gamma, const float* beta,
+                       float* scale, float* shift, cudaStream_t s);
 void layernorm(const float* x, int rows, int c, const float* g, const float* b, float eps,
                const float* res, float* out, const float* add2, int add2_rows, float* out2, cudaStream_t s);
 

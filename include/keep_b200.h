@@ -127,6 +127,14 @@ int keepop_conv2d(int use_tc, const float* x_dev, int n, int h, int w, int cin, 
                   int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
                   const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
                   float* out_dev, void* stream);
+/* same convolution on the tcgen05 path (use_tc 1 | 3) with the GroupNorm(32, eps 1e-6) statistics of its OUTPUT emitted by the
+ * producing kernel (conv epilogue, or the split-K reduce) and finalized into the per-(n, channel) affine the next layer's
+ * operand producers apply: scale_dev / shift_dev (n, cout), y = x * scale + shift  (normalize(), vqgan_arch.py:16-17) */
+int keepop_conv2d_gn(int use_tc, const float* x_dev, int n, int h, int w, int cin, const float* weight_host, const float* bias_host,
+                     int cout, int kh, int kw, int stride, int pad_t, int pad_l, int pad_b, int pad_r, int up,
+                     const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
+                     float* out_dev, const float* gn_gamma_dev, const float* gn_beta_dev, float* gn_scale_dev, float* gn_shift_dev,
+                     void* stream);
 /* debug timeline (tools/timeline.py): every kernel appends %globaltimer at its start to dev_buf (uint64[1 + 65536], [0] = count;
  * NULL = off); the launch log records kernel names and grids on the host in enqueue order */
 int keepop_kernel_stamps(unsigned long long* dev_buf);

@@ -184,3 +184,53 @@ def test_conv_tcgen05_stride2_virtual_s2d(lib, case, mode):
     torch.cuda.synchronize()
     err = float((got - want).abs().max())
     assert got.shape == want.shape and err <= tol * max(1.0, float(want.abs().max())), "%s mode %d: err %g" % (name, mode, err)
+
+
+# ---- GroupNorm statistics emitted by the producing kernel (conv epilogue / split-K reduce) + finalize --------------------
+GN_CASES = [
+    # name, n, cin, h, w, cout, k, stride, pads, up, res        (cout / 32 = channels per group: 2, 4, 8, 16)
+    ("epi_64_64_cpg2_n2", 2, 64, 64, 64, 64, 3, 1, (1, 1, 1, 1), 1, True),
+    ("epi_ragged_128_cpg4", 1, 64, 40, 24, 128, 3, 1, (1, 1, 1, 1), 1, False),
+    ("epi_up2_256_cpg8", 3, 128, 32, 32, 256, 3, 1, (1, 1, 1, 1), 2, False),
+    ("epi_1x1_512_cpg16", 4, 256, 64, 64, 512, 1, 1, (0, 0, 0, 0), 1, True),
+    ("epi_down_s2_128", 2, 128, 128, 128, 128, 3, 2, (0, 0, 1, 1), 1, False),
+    ("split_16sq_512", 1, 512, 16, 16, 512, 3, 1, (1, 1, 1, 1), 1, True),
+    ("split_32sq_256_n2", 2, 256, 32, 32, 256, 3, 1, (1, 1, 1, 1), 1, True),
+    ("split_64sq_128_1x1", 1, 256, 64, 64, 128, 1, 1, (0, 0, 0, 0), 1, False),
+]
+
+
+@pytest.mark.parametrize("case", GN_CASES, ids=[c[0] for c in GN_CASES])
+def test_conv_epilogue_groupnorm_statistics(lib, case):
+    """conv (split precision) + statistics of its output from the producing kernel + finalize  vs  torch GroupNorm(32, eps 1e-6)
+    statistics of the very tensor the kernel wrote (vqgan_arch.py:16-17): scale = gamma * rstd, shift = beta - mean * scale."""
+    from test_gpu_ops import ACT, _p, _rc
+    name, n, cin, h, w, cout, k, stride, pads, up, res = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) & 0xFFFF)
+    x = (torch.randn((n, cin, h, w), generator=g) * 3 + 0.7).cuda()
+    wt = (torch.randn((cout, cin, k, k), generator=g) / math.sqrt(cin * k * k)).cuda()
+    b = torch.randn((cout,), generator=g).cuda()
+    ho = (h * up + pads[0] + pads[2] - k) // stride + 1
+    wo = (w * up + pads[1] + pads[3] - k) // stride + 1
+    r = torch.randn((n, ho, wo, cout), generator=g).cuda() if res else None
+    gamma, beta = (1 + 0.3 * torch.randn((cout,), generator=g)).cuda(), (0.3 * torch.randn((cout,), generator=g)).cuda()
+    xin = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty((n, ho, wo, cout), device="cuda")
+    scale, shift = torch.full((n, cout), float("nan"), device="cuda"), torch.full((n, cout), float("nan"), device="cuda")
+    _rc(lib, lib.keepop_conv2d_gn(3, _p(xin), n, h, w, cin, _p(wt.cpu().contiguous()), _p(b.cpu()), cout, k, k, stride, pads[0], pads[1],
+                                  pads[2], pads[3], up, None, None, ACT["none"], ACT["none"], _p(r), _p(out), _p(gamma), _p(beta),
+                                  _p(scale), _p(shift), None))
+    torch.cuda.synchronize()
+    y = out.double().reshape(n, ho * wo, 32, cout // 32)
+    mean = y.mean(dim=(1, 3))
+    var = y.var(dim=(1, 3), unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + 1e-6)
+    want_scale = gamma.double().reshape(1, 32, -1) * rstd[:, :, None]
+    want_shift = beta.double().reshape(1, 32, -1) - mean[:, :, None] * want_scale
+    e_sc = float((scale.double().reshape(n, 32, -1) - want_scale).abs().max() / want_scale.abs().max())
+    e_sh = float((shift.double().reshape(n, 32, -1) - want_shift).abs().max() / max(1.0, float(want_shift.abs().max())))
+    assert bool(torch.isfinite(scale).all()) and bool(torch.isfinite(shift).all()), "a statistics slot was never written"
+    assert e_sc < 2e-6 and e_sh < 2e-6, "%s: scale err %g, shift err %g" % (name, e_sc, e_sh)
+    # and the convolution itself is untouched by the extra epilogue work
+    want = ref_conv(x, wt, b, stride, pads, up, None, "none", "none", r.permute(0, 3, 1, 2) if res else None)
+    assert float((out.permute(0, 3, 1, 2) - want).abs().max()) < 2e-4 * max(1.0, float(want.abs().max()))
