@@ -216,6 +216,12 @@ bool conv_small_eligible(const ConvArgs& a) {
     return false;
 }
 
+void conv_small_configure_device() {
+    static unsigned long long configured = 0;
+    if (first_use_on_current_device(&configured))
+        CUDA_CHECK(cudaFuncSetAttribute(conv_cout4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+}
+
 void conv2d_small(const ConvArgs& a, cudaStream_t s) {
     KEEP_CHECK(conv_small_eligible(a), "conv2d_small: not eligible");
     const int cin = a.c0 + a.c1;
@@ -235,9 +241,7 @@ void conv2d_small(const ConvArgs& a, cudaStream_t s) {
     } else {
         const int tiles = ((a.w + HT_W - 1) / HT_W) * ((a.h + HT_H - 1) / HT_H);
         const size_t smem = (size_t)(9 * cin * 4 + (HT_H + 2) * (HT_W + 2) * HPITCH) * sizeof(float);
-        static unsigned long long configured = 0;
-        if (first_use_on_current_device(&configured))
-            CUDA_CHECK(cudaFuncSetAttribute(conv_cout4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        conv_small_configure_device();
         launch_k(conv_cout4_kernel, dim3(a.n * tiles), dim3(256), smem, s, a.in0, a.in0_dt, a.n, a.h, a.w, cin, a.pre_scale, a.pre_shift, a.wt, a.bias,
                                                          a.cout, (float*)a.out);
     }

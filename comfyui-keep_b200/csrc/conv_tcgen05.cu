@@ -1076,6 +1076,26 @@ static void pick_stages(int win, int bn, size_t resident_bytes, int min_sa, int&
     while (sa < MAX_SA && (sa + 1) * a_stage + sb * b_stage <= SMEM_BUDGET) ++sa;
 }
 
+using Kern = void (*)(const TcConvArgs);
+static const Kern kerns[2][2][3] = {
+    {{conv_tc_kernel<1, false, 1>, conv_tc_kernel<1, false, 2>, conv_tc_kernel<1, false, 3>},
+     {conv_tc_kernel<1, true, 1>, conv_tc_kernel<1, true, 2>, conv_tc_kernel<1, true, 3>}},
+    {{conv_tc_kernel<3, false, 1>, conv_tc_kernel<3, false, 2>, conv_tc_kernel<3, false, 3>},
+     {conv_tc_kernel<3, true, 1>, conv_tc_kernel<3, true, 2>, conv_tc_kernel<3, true, 3>}}};
+// wide-range variant (bf16 activation pairs): split-precision mode, fp32 feature maps only
+static const Kern kerns_wide[3] = {conv_tc_kernel<3, false, 1, true>, conv_tc_kernel<3, false, 2, true>, conv_tc_kernel<3, false, 3, true>};
+
+// opt every variant into 227 KB of dynamic shared memory, once per device (also called at engine creation, so that no
+// attribute call happens while a CUDA graph is being captured)
+void tc_configure_device() {
+    static unsigned long long configured = 0;
+    if (!first_use_on_current_device(&configured)) return;
+    for (int i = 0; i < 12; ++i)
+        CUDA_CHECK(cudaFuncSetAttribute(kerns[i / 6][(i / 3) % 2][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 3; ++i)
+        CUDA_CHECK(cudaFuncSetAttribute(kerns_wide[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
 int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int splitk, float* partial, int num_sms,
               cudaStream_t s) {
     KEEP_CHECK(tc_eligible(a), "conv2d_tc: layer not eligible for the tcgen05 kernel");
@@ -1151,25 +1171,8 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     const int grid = num_sms > 0 ? (int)std::min<long long>(total, num_sms)
                                  : (int)std::min<long long>(total, std::max<long long>(1, (total + (-num_sms) - 1) / (-num_sms)));
     const bool f16 = a.in0_dt == F16;
-    using Kern = void (*)(const TcConvArgs);
-    static const Kern kerns[2][2][3] = {
-        {{conv_tc_kernel<1, false, 1>, conv_tc_kernel<1, false, 2>, conv_tc_kernel<1, false, 3>},
-         {conv_tc_kernel<1, true, 1>, conv_tc_kernel<1, true, 2>, conv_tc_kernel<1, true, 3>}},
-        {{conv_tc_kernel<3, false, 1>, conv_tc_kernel<3, false, 2>, conv_tc_kernel<3, false, 3>},
-         {conv_tc_kernel<3, true, 1>, conv_tc_kernel<3, true, 2>, conv_tc_kernel<3, true, 3>}}};
-    static unsigned long long configured = 0;
-    if (first_use_on_current_device(&configured)) {
-        for (int i = 0; i < 12; ++i)
-            CUDA_CHECK(cudaFuncSetAttribute(kerns[i / 6][(i / 3) % 2][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    }
-    // wide-range variant (bf16 activation pairs): split-precision mode, fp32 feature maps only
-    static const Kern kerns_wide[3] = {conv_tc_kernel<3, false, 1, true>, conv_tc_kernel<3, false, 2, true>, conv_tc_kernel<3, false, 3, true>};
-    static unsigned long long configured_wide = 0;
+    tc_configure_device();
     const bool wide = a.a_wide && passes == 3 && !f16;
-    if (wide && first_use_on_current_device(&configured_wide)) {
-        for (int i = 0; i < 3; ++i)
-            CUDA_CHECK(cudaFuncSetAttribute(kerns_wide[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    }
     const Kern kern = wide ? kerns_wide[t.win - 1] : kerns[passes == 3 ? 1 : 0][f16 ? 1 : 0][t.win - 1];
     if (t.cluster_k) {   // one work item per CTA, the splitk CTAs of a tile form one cluster
         launch_k_cluster(kern, dim3((unsigned)total), dim3(kThreads), smem, s, splitk, t);

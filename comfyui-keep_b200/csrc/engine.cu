@@ -128,7 +128,16 @@ void Engine::add_arr(const std::string& key, const std::vector<float>& host, int
     W_[key] = a;
 }
 
-// conv OIHW -> [(ky*kw + kx)*I + i][o]; linear (O, I) is the 1x1 case
+// plain conv / linear weights: registered now, uploaded raw and transposed on the device (oihw_to_kc) at the end of pack_weights
+void Engine::add_job(const std::string& key, const float* src, int O, int I, int kh, int kw) {
+    jobs_.push_back({key, src, O, I, kh * kw});
+    DevArr a;
+    a.numel = (long long)O * I * kh * kw;
+    a.d[0] = I; a.d[1] = O; a.d[2] = kh; a.d[3] = kw;
+    W_[key] = a;
+}
+
+// conv OIHW -> [(ky*kw + kx)*I + i][o]; linear (O, I) is the 1x1 case  (host version: the few fused / permuted copies)
 static std::vector<float> pack_oihw(const float* w, int O, int I, int kh, int kw) {
     std::vector<float> out((size_t)O * I * kh * kw);
     for (int o = 0; o < O; ++o)
@@ -164,8 +173,7 @@ void Engine::pack_weights(const keep_weight_desc* w, int n_w) {
             add_arr(base + "in_proj_qk.bias", std::vector<float>(d->data, d->data + 2 * E), 2 * E);
             add_arr(base + "in_proj_v.bias", std::vector<float>(d->data + 2 * E, d->data + 3 * E), E);
         } else if (d->ndim == 4) {
-            add_arr(key, pack_oihw(d->data, (int)d->shape[0], (int)d->shape[1], (int)d->shape[2], (int)d->shape[3]),
-                    (int)d->shape[1], (int)d->shape[0], (int)d->shape[2], (int)d->shape[3]);
+            add_job(key, d->data, (int)d->shape[0], (int)d->shape[1], (int)d->shape[2], (int)d->shape[3]);
             // GMFlow upsampler conv on cat(flow[2], feature[128]) (gmflow/gmflow.py:46-48,76): a tensor-core copy with the
             // input channels reordered to [feature 128 | flow 2 | 6 zeros] = 136, so both sources start on 8-channel units
             if (ends_with(key, ".upsampler.0.weight") && d->shape[1] == 130 && d->shape[2] == 3) {
@@ -199,7 +207,7 @@ void Engine::pack_weights(const keep_weight_desc* w, int n_w) {
                 }
             }
         } else if (d->ndim == 2) {
-            add_arr(key, pack_oihw(d->data, (int)d->shape[0], (int)d->shape[1], 1, 1), (int)d->shape[1], (int)d->shape[0], 1, 1);
+            add_job(key, d->data, (int)d->shape[0], (int)d->shape[1], 1, 1);
             // GMFlow attention projections (gmflow/transformer.py:117-119, bias-free): fused copies q|k|v (self-attention:
             // one source) and k|v (cross-attention: both read the target) -> one N = 3C / 2C GEMM that converts the
             // activations once (A-stationary walk over the N tiles) instead of three / two times (KEEP_GM_FUSE_QKV=1)
@@ -226,19 +234,42 @@ void Engine::pack_weights(const keep_weight_desc* w, int n_w) {
             add_arr(key, std::vector<float>(d->data, d->data + ne), (int)d->shape[0]);
         }
     }
-    // one pool, one upload
-    size_t total = 0;
+    // one pool.  Small host-packed arrays are copied as they are; the bulk (jobs_) goes up raw into a temporary buffer and is
+    // transposed by a device kernel -- the host never touches the 158 M parameters element by element
+    size_t total = 0, raw_total = 0;
     for (auto& kv : staging_) total += (kv.second.size() + 63) & ~(size_t)63;
-    if (!dry_only_) CUDA_CHECK(cudaMalloc((void**)&wpool_, total * sizeof(float)));
-    size_t off = 0;
+    for (auto& j : jobs_) { const size_t ne = (size_t)j.O * j.I * j.taps; total += (ne + 63) & ~(size_t)63; raw_total += (ne + 63) & ~(size_t)63; }
+    float* raw = nullptr;
+    if (!dry_only_) {
+        CUDA_CHECK(cudaMalloc((void**)&wpool_, total * sizeof(float)));
+        CUDA_CHECK(cudaMalloc((void**)&raw, std::max<size_t>(raw_total, 64) * sizeof(float)));
+    }
+    size_t off = 0, roff = 0;
     for (auto& kv : staging_) {
         if (!dry_only_)
-            CUDA_CHECK(cudaMemcpy(wpool_ + off, kv.second.data(), kv.second.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpyAsync(wpool_ + off, kv.second.data(), kv.second.size() * sizeof(float), cudaMemcpyHostToDevice, 0));
         W_[kv.first].p = (dry_only_ ? (float*)(uintptr_t)4096 : wpool_) + off;
         off += (kv.second.size() + 63) & ~(size_t)63;
     }
+    for (auto& j : jobs_) {
+        const size_t ne = (size_t)j.O * j.I * j.taps;
+        if (!dry_only_) {
+            CUDA_CHECK(cudaMemcpyAsync(raw + roff, j.src, ne * sizeof(float), cudaMemcpyHostToDevice, 0));
+            if (j.taps == 1 && (j.O == 1 || j.I == 1)) CUDA_CHECK(cudaMemcpyAsync(wpool_ + off, raw + roff, ne * sizeof(float), cudaMemcpyDeviceToDevice, 0));
+            else oihw_to_kc(raw + roff, wpool_ + off, j.O, j.I, j.taps, 0);
+        }
+        W_[j.key].p = (dry_only_ ? (float*)(uintptr_t)4096 : wpool_) + off;
+        off += (ne + 63) & ~(size_t)63;
+        roff += (ne + 63) & ~(size_t)63;
+    }
+    if (!dry_only_) {
+        CUDA_CHECK(cudaStreamSynchronize(0));   // host staging vectors and the caller's tensors are read until here
+        CUDA_CHECK(cudaGetLastError());
+        cudaFree(raw);
+    }
     staging_.clear();
     staging_.shrink_to_fit();
+    jobs_.clear();
 }
 
 const float* Engine::warr(const std::string& key) const {
@@ -345,7 +376,65 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         for (int t = 0; t < 4096; ++t) { grid[2 * t] = (float)(t % 64); grid[2 * t + 1] = (float)(t / 64); }
         CUDA_CHECK(cudaMalloc((void**)&grid64_, grid.size() * sizeof(float)));
         CUDA_CHECK(cudaMemcpy(grid64_, grid.data(), grid.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // streams / events a forward needs: created here so that nothing is created while a graph is being captured
+        int lo = 0, hi = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = least urgent
+        CUDA_CHECK(cudaStreamCreateWithPriority(&side_, cudaStreamNonBlocking, lo));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&gs_, cudaStreamNonBlocking, hi));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_out_, cudaEventDisableTiming));
+        for (int i = 0; i < 64; ++i) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev_flow_.push_back(e);
+        }
+        tc_configure_device();
+        conv_small_configure_device();
+        if ((flags_ & KEEP_FLAG_TCGEN05) && tc_passes_ == 3) prepack_tc_weights();
     }
+}
+
+// tcgen05 weight panels for every layer of a forward, packed once at creation: a dry run (no device work) of a 2-frame clip
+// lists the (layer, N tile, passes, stride-2 pad, wide) variants -- in the split-precision mode the N tile depends on the
+// layer only, not on the batch, so the list holds for every T and for lockstep groups
+void Engine::prepack_tc_weights() {
+    std::vector<TcReq> reqs;
+    tc_collect_ = &reqs;
+    try {
+        begin(nullptr, 0, nullptr, true);
+        forward_clip(nullptr, 2, nullptr, KEEP_OUT_F32);
+    } catch (...) {
+        tc_collect_ = nullptr;
+        throw;
+    }
+    tc_collect_ = nullptr;
+    std::vector<TcReq> uniq;
+    std::vector<size_t> offs;
+    size_t total = 0;
+    for (const TcReq& r : reqs) {
+        bool seen = false;
+        for (const TcReq& u : uniq) seen = seen || (u.cw.w == r.cw.w && u.bn == r.bn && u.passes == r.passes && u.wide == r.wide);
+        if (seen) continue;
+        const int cb = tc_cb(r.passes);
+        const int vcin = r.s2d_pad >= 0 ? 4 * ((r.cw.cin + cb - 1) / cb) * cb : r.cw.cin;
+        const int vtaps = r.s2d_pad >= 0 ? 4 : r.cw.kh * r.cw.kw;
+        uniq.push_back(r);
+        offs.push_back(total);
+        total += (tc_packed_weight_halfs(vcin, r.cw.cout, vtaps, r.bn, r.passes) + 127) & ~(size_t)127;
+    }
+    if (uniq.empty()) return;
+    CUDA_CHECK(cudaMalloc((void**)&tcw_pool_, total * sizeof(__half)));
+    for (size_t i = 0; i < uniq.size(); ++i) {
+        const TcReq& r = uniq[i];
+        TcW t;
+        t.bn = r.bn; t.passes = r.passes; t.wide = r.wide; t.pooled = true;
+        t.p = tcw_pool_ + offs[i];
+        tc_repack_device(r.cw.w, r.cw.cin, r.cw.cout, r.cw.kh * r.cw.kw, r.bn, r.passes, r.s2d_pad, t.p, 0, r.wide);
+        tcw_[r.cw.w].push_back(t);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(0));
+    prepacked_ = true;
 }
 
 Engine::~Engine() {
@@ -362,7 +451,9 @@ Engine::~Engine() {
     for (auto& kv : cap_) cudaFree(kv.second.p);
     for (auto& kv : forced_) cudaFree(kv.second.p);
     for (auto& kv : tcw_)
-        for (auto& v : kv.second) cudaFree(v.p);
+        for (auto& v : kv.second)
+            if (!v.pooled) cudaFree(v.p);
+    cudaFree(tcw_pool_);
     for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
     cudaFree(gx_);
     cudaFree(gout_);
@@ -473,6 +564,8 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             a.gn_part = out.gn_part; a.gn_P = P;
         }
     }
+    if (tc_collect_ && use_tc)
+        tc_collect_->push_back({cw, bn, passes, tc_is_s2d(a) ? a.pad_t : -1, (wide_scope_ && !o.pre && x.w > 1 && passes == 3 && a.in0_dt == F32) ? 1 : 0});
     if (plan_) {
         char line[256];
         snprintf(line, sizeof(line), "conv n=%d h=%d w=%d c0=%d c1=%d cout=%d k=%d stride=%d up=%d pre=%d act=%d res=%d kernel=%s splitk=%d bn=%d wide=%d",
@@ -1672,7 +1765,7 @@ void Engine::forward_batched(const float* x_dev, int b, int T, void* out_dev, in
         void* ws = own_ws_;
         const size_t ws_bytes = own_ws_bytes_;
         const bool want_graph = (flags_ & KEEP_FLAG_CUDA_GRAPH) != 0;
-        if (want_graph && eager_runs_[key] >= 1) {
+        if (want_graph && (eager_runs_[key] >= 1 || prepacked_)) {
             const size_t in_bytes = (size_t)g * per_clip * 4;
             if (gx_bytes_ < in_bytes || gout_bytes_ < in_bytes) {
                 CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1697,6 +1790,7 @@ void Engine::forward_batched(const float* x_dev, int b, int T, void* out_dev, in
             CUDA_CHECK(cudaStreamWaitEvent(gs_, ev_in_, 0));
             if (!gr.exec) {
                 cudaGraph_t graph = nullptr;
+                const long long l0 = launches_;
                 CUDA_CHECK(cudaStreamBeginCapture(gs_, cudaStreamCaptureModeThreadLocal));
                 try {
                     begin(ws, ws_bytes, gs_, false);
@@ -1706,6 +1800,8 @@ void Engine::forward_batched(const float* x_dev, int b, int T, void* out_dev, in
                     if (graph) cudaGraphDestroy(graph);
                     throw;
                 }
+                launches_per_clip_[key] = launches_ - l0;
+                launches_ = l0;
                 CUDA_CHECK(cudaStreamEndCapture(gs_, &graph));
                 cudaError_t e = cudaGraphInstantiate(&gr.exec, graph, 0);
                 cudaGraphDestroy(graph);
@@ -1783,7 +1879,7 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
     for (int bi = 0; bi < b; ++bi) {   // clips are independent (keep_processor.py:263-270)
         const float* xin = x_dev + bi * per_clip;
         char* xout = (char*)out_dev + bi * per_clip * osz;
-        if (want_graph && eager_runs_[T] >= 1) {
+        if (want_graph && (eager_runs_[T] >= 1 || prepacked_)) {   // (prepacked weights: nothing is allocated inside a forward, capture at once)
             // static staging buffers so the captured graph's pointers stay valid across calls
             if (gx_bytes_ < per_clip * 4 || gout_bytes_ < per_clip * 4) {
                 CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1809,6 +1905,7 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
             CUDA_CHECK(cudaStreamWaitEvent(gs_, ev_in_, 0));
             if (!g.exec) {
                 cudaGraph_t graph = nullptr;
+                const long long l0 = launches_;
                 CUDA_CHECK(cudaStreamBeginCapture(gs_, cudaStreamCaptureModeThreadLocal));
                 try {
                     begin(ws, ws_bytes, gs_, false);
@@ -1818,6 +1915,8 @@ void Engine::forward(const float* x_dev, int b, int T, void* out_dev, int out_dt
                     if (graph) cudaGraphDestroy(graph);
                     throw;
                 }
+                launches_per_clip_[T] = launches_ - l0;   // (counted while enqueueing; the replay below adds them)
+                launches_ = l0;
                 CUDA_CHECK(cudaStreamEndCapture(gs_, &graph));
                 cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
                 cudaGraphDestroy(graph);

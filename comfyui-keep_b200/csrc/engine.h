@@ -121,6 +121,10 @@ class Engine {
     int adt_ = F32;  // feature-map storage dtype
     std::unordered_map<std::string, DevArr> W_;
     std::vector<std::pair<std::string, std::vector<float>>> staging_;
+    // bulk of the state dict (every plain conv / linear weight): uploaded raw and transposed on the device at creation
+    struct PackJob { std::string key; const float* src; int O, I, taps; };
+    std::vector<PackJob> jobs_;
+    void add_job(const std::string& key, const float* src, int O, int I, int kh, int kw);
     float* wpool_ = nullptr;
     float* u8_stage_ = nullptr; size_t u8_stage_bytes_ = 0;   // fp32 copy of a uint8 input clip (forward_u8)
     int* status_ = nullptr;      // sticky non-finite status word (device)
@@ -146,7 +150,14 @@ class Engine {
     std::unordered_map<int, size_t> ws_cache_;
     // tcgen05 path: fp16 weight panels, packed on first use, keyed by the fp32 weight pointer; variants are kept (a layer can be
     // asked for a second N tile when the per-clip and the lockstep path alternate), nothing is freed before the engine dies
-    struct TcW { __half* p = nullptr; int bn = 0, passes = 0, wide = 0; };
+    struct TcW { __half* p = nullptr; int bn = 0, passes = 0, wide = 0; bool pooled = false; };
+    // panels of every layer a forward will run, packed at creation into one pool (no cudaMalloc / repack inside the first call,
+    // so the first call can already capture the CUDA graph); the dry run of a 2-frame clip lists the variants
+    struct TcReq { ConvW cw; int bn, passes, s2d_pad, wide; };
+    std::vector<TcReq>* tc_collect_ = nullptr;
+    __half* tcw_pool_ = nullptr;
+    bool prepacked_ = false;
+    void prepack_tc_weights();
     std::unordered_map<const float*, std::vector<TcW>> tcw_;   // every (N tile, passes, wide) variant a layer has been run with
     const __half* tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide = 0);
     bool wide_scope_ = false; // KEEP_FLAG_TC_WIDE and inside generator(): raw-input feature-map layers use bf16 activation pairs

@@ -549,6 +549,17 @@ __global__ void __launch_bounds__(256) convex_upsample8_kernel(const float* __re
     out[2 * i + 1] = ay / se;
 }
 
+// conv OIHW (or linear (O, I): taps = 1) -> [(tap * I + i)][o]: the layout of every kernel's weight operand; one-time, at keep_create
+__global__ void __launch_bounds__(256) oihw_to_kc_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int I, int taps,
+                                                         size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int o = (int)(idx % O);
+    const size_t r = idx / O;
+    const int i = (int)(r % I), t = (int)(r / I);
+    out[idx] = w[((size_t)o * I + i) * taps + t];
+}
+
 __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
                                                       float* __restrict__ out, size_t total) {
     pdl_prologue();
@@ -692,6 +703,14 @@ void convex_upsample8(const float* mask, const float* flow, float* out, int n, i
     const size_t total = (size_t)n * 64 * h * w;
     launch_k(convex_upsample8_kernel, dim3(blocks_for(total)), dim3(256), 0, s, mask, flow, out, h, w, total);
     CUDA_CHECK(cudaGetLastError());
+}
+
+void oihw_to_kc(const float* w_dev, float* out_dev, int O, int I, int taps, cudaStream_t s) {
+    const size_t total = (size_t)O * I * taps;
+    cudaLaunchConfig_t cfg;   // plain launch (no PDL attribute): runs once at engine creation
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks_for(total)); cfg.blockDim = dim3(256); cfg.stream = s;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, oihw_to_kc_kernel, w_dev, out_dev, O, I, taps, total));
 }
 
 void concat2(const float* a, int ca, const float* b, int cb, float* out, long long rows, cudaStream_t s) {

@@ -42,6 +42,7 @@ int conv_pick_splitk(const ConvArgs& a);
 // bandwidth-bound ends of the conv stacks: Cin = 3 stems (3x3 s1, 7x7 s2) and Cout <= 4 heads (3x3 s1)
 bool conv_small_eligible(const ConvArgs& a);
 void conv2d_small(const ConvArgs& a, cudaStream_t s);
+void conv_small_configure_device();   // per-device kernel attributes (idempotent)
 
 // ------------------------------------------------------------------------------------------
 // batched strided GEMM (fp32), used for attention scores / PV
@@ -143,6 +144,8 @@ void window_partition(const float* x, float* out, int n, int h, int w, int c, in
 void window_merge(const float* x, float* out, int n, int h, int w, int c, int k, int shift_h, int shift_w, cudaStream_t s);
 // convex x8 upsampling (gmflow.py:74-88): mask (n,h,w,576), flow (n,h,w,2) -> (n,8h,8w,2)
 void convex_upsample8(const float* mask, const float* flow, float* out, int n, int h, int w, cudaStream_t s);
+// weight layout transform at engine creation: OIHW / (O, I) on the device -> [(tap * I + i)][o]
+void oihw_to_kc(const float* w_dev, float* out_dev, int O, int I, int taps, cudaStream_t s);
 // concat along channels of two (rows, c) fp32 matrices / generic strided copy
 void concat2(const float* a, int ca, const float* b, int cb, float* out, long long rows, cudaStream_t s);
 

@@ -30,6 +30,7 @@ struct TcConvArgs {
 };
 
 extern long long* g_tc_trace;
+void tc_configure_device();      // per-device kernel attributes (idempotent)
 bool tc_eligible(const ConvArgs& a);
 int tc_pick_bn(int cout, long long m_tiles, int passes);
 int tc_pick_splitk(long long m_tiles, int ntile_n, int ncb);
