@@ -251,7 +251,7 @@ def main():
     mode = args.mode
     if mode == "auto":
         mode = os.environ.get("KEEP_DEFAULT_MODE", DEFAULT_MODE)
-    flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3}[mode]
+    flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.TC3_FLAGS}[mode]
     if not args.no_graph:
         flags |= kn.FLAG_CUDA_GRAPH
     cfg = args.config

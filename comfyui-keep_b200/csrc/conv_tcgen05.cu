@@ -783,14 +783,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 }
                 if (!ok || col >= a.cout) continue;
                 const uint32_t laddr = sbase + (uint32_t)(row * a.bn * 4 + ((c4 ^ (row & 7)) << 4));
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int k = 0; k < S; ++k) {
-                    uint32_t raddr;
-                    float4 p;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(k));
-                    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w) : "r"(raddr) : "memory");
-                    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+                // all S remote loads in flight at once (one after the other they cost S x the DSMEM latency: the round-1
+                // version of this loop made the cluster path slower than the separate reduce kernel), summed in rank order
+                float4 pk[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    pk[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (k < S) {
+                        uint32_t raddr;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(k));
+                        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pk[k].x), "=f"(pk[k].y), "=f"(pk[k].z), "=f"(pk[k].w) : "r"(raddr));
+                    }
                 }
+                float4 v = pk[0];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) { v.x += pk[k].x; v.y += pk[k].y; v.z += pk[k].z; v.w += pk[k].w; }
                 const float4 b = *reinterpret_cast<const float4*>(s_bias + c4 * 4);
                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                 if (a.act != ACT_NONE) { v.x = act_slow(v.x, a.act); v.y = act_slow(v.y, a.act); v.z = act_slow(v.z, a.act); v.w = act_slow(v.w, a.act); }

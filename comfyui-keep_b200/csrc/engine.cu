@@ -554,9 +554,9 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     }
     // GroupNorm statistics of the output from the producing kernel (conv epilogue, or the split-K reduce): the consumer's
     // gn() then needs one tiny finalize launch instead of a read pass over the tensor plus a second kernel
-    static const bool gn_fuse = !(getenv("KEEP_GN_EPILOGUE") && getenv("KEEP_GN_EPILOGUE")[0] == '0') &&
-                                !(getenv("KEEP_TC_CLUSTER") && atoi(getenv("KEEP_TC_CLUSTER")) >= 2);
-    if (o.want_stats && use_tc && gn_fuse) {
+    static const bool gn_fuse = !(getenv("KEEP_GN_EPILOGUE") && getenv("KEEP_GN_EPILOGUE")[0] == '0');
+    static const bool cluster_mode = getenv("KEEP_TC_CLUSTER") && atoi(getenv("KEEP_TC_CLUSTER")) >= 2;   // (no reduce kernel to emit them)
+    if (o.want_stats && use_tc && gn_fuse && !(cluster_mode && a.splitk > 1)) {
         const int P = conv_gn_slots(a, a.splitk);
         if (P > 0) {
             out.gn_P = P;

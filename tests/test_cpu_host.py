@@ -86,10 +86,10 @@ def test_default_flags_and_rejected_flags(keep_mod, lib, state_dict):
     """The default-constructed module is the measured engine (tcgen05 split precision + CUDA graph), 'Asian' adds the wide
     operand range; the reserved fp16-feature flag is refused by the C side instead of failing inside the first forward."""
     kn = keep_mod.keep_net
-    assert kn.DEFAULT_FLAGS == kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3 | kn.FLAG_CUDA_GRAPH
+    assert kn.DEFAULT_FLAGS == kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3 | kn.FLAG_TC_WIDE | kn.FLAG_CUDA_GRAPH
     assert keep_mod.KeepNetB200()._flags == kn.DEFAULT_FLAGS
     assert keep_mod.KeepNetB200(flags=0)._flags == 0                                  # exact-fp32 CUDA-core engine, on request
-    assert keep_mod.KeepNetB200(**kn.KEEP_ASIAN_CFG)._flags == kn.DEFAULT_FLAGS | kn.FLAG_TC_WIDE
+    assert keep_mod.KeepNetB200(**kn.KEEP_ASIAN_CFG)._flags == kn.DEFAULT_FLAGS
     net = keep_mod.KeepNetB200()
     net.load_state_dict(state_dict, strict=True)
     for bad in (kn.FLAG_FP16_FEATURES, kn.FLAG_FP16_FEATURES | kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3):

@@ -48,7 +48,7 @@ def test_default_engine_through_load_device_offload_twice(keep_mod, state_dict):
     from oracle import weights
     net = keep_mod.KeepNetB200()                      # flags=None -> DEFAULT_FLAGS
     kn = keep_mod.keep_net
-    assert net._flags & (kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3 | kn.FLAG_CUDA_GRAPH) == kn.DEFAULT_FLAGS
+    assert net._flags == kn.DEFAULT_FLAGS == kn.TC3_FLAGS | kn.FLAG_CUDA_GRAPH
     net.load_state_dict(state_dict, strict=True)
     net.eval()
     pack = _Pack(net)
@@ -107,7 +107,7 @@ def test_status_word_flags_non_finite_inputs(keep_mod, state_dict):
 @pytest.fixture(scope="module")
 def net_dbg(keep_mod, state_dict):
     kn = keep_mod.keep_net
-    n = keep_mod.KeepNetB200(flags=kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3)
+    n = keep_mod.KeepNetB200(flags=kn.TC3_FLAGS)
     n.load_state_dict(state_dict, strict=True)
     n.eval().to("cuda")
     n.debug_capture(True)

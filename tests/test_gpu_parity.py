@@ -28,7 +28,7 @@ def psnr(a, b):
 @pytest.fixture(scope="module", params=["fp32", "tc3"])
 def net(request, keep_mod, state_dict):
     kn = keep_mod.keep_net
-    flags = 0 if request.param == "fp32" else (kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3)
+    flags = 0 if request.param == "fp32" else kn.TC3_FLAGS
     n = keep_mod.KeepNetB200(flags=flags)
     n.mode_name = request.param
     n.load_state_dict(state_dict, strict=True)
@@ -195,7 +195,7 @@ def test_cuda_graph_replay_is_bitwise_identical_to_eager(keep_mod, state_dict):
     engine's bits, including on a different clip after capture (static staging buffers, no stale pointers)."""
     from oracle import weights
     kn = keep_mod.keep_net
-    base = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3
+    base = kn.TC3_FLAGS
     eager = keep_mod.KeepNetB200(flags=base)
     eager.load_state_dict(state_dict, strict=True)
     eager.eval().to("cuda")
@@ -261,7 +261,7 @@ def test_concurrent_clip_replicas_equal_clip_by_clip(keep_mod, state_dict):
     clip-by-clip loop (clips are independent, keep_processor.py:263-270)."""
     from oracle import weights
     kn = keep_mod.keep_net
-    flags = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3 | kn.FLAG_CUDA_GRAPH
+    flags = kn.DEFAULT_FLAGS
     one = keep_mod.KeepNetB200(flags=flags)
     one.load_state_dict(state_dict, strict=True)
     one.eval().to("cuda")

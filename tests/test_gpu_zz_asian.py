@@ -30,7 +30,7 @@ def _report(tag, **kw):
 @pytest.fixture(scope="module", params=["fp32", "tc3"])
 def net(request, keep_mod, state_dict_asian):
     kn = keep_mod.keep_net
-    flags = 0 if request.param == "fp32" else (kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3)
+    flags = 0 if request.param == "fp32" else kn.TC3_FLAGS
     n = keep_mod.KeepNetB200(flags=flags, **kn.KEEP_ASIAN_CFG)
     n.mode_name = request.param
     n.load_state_dict(state_dict_asian, strict=True)

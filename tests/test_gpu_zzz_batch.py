@@ -23,7 +23,7 @@ def _report(tag, **kw):
 
 def _make(keep_mod, state_dict, mode, **kw):
     kn = keep_mod.keep_net
-    flags = (0 if mode == "fp32" else (kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3)) | kw.pop("extra_flags", 0)
+    flags = (0 if mode == "fp32" else kn.TC3_FLAGS) | kw.pop("extra_flags", 0)
     n = keep_mod.KeepNetB200(flags=flags, **kw)
     n.load_state_dict(state_dict, strict=True)
     return n.eval().to("cuda")

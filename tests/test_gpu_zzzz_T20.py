@@ -33,7 +33,7 @@ def _report(tag, **kw):
 @pytest.fixture(scope="module")
 def net(keep_mod, state_dict):
     kn = keep_mod.keep_net
-    n = keep_mod.KeepNetB200(flags=kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3)
+    n = keep_mod.KeepNetB200(flags=kn.TC3_FLAGS)
     n.load_state_dict(state_dict, strict=True)
     n.eval().to("cuda")
     n.debug_capture(True)

@@ -13,7 +13,7 @@ config = sys.argv[1] if len(sys.argv) > 1 else "KEEP"
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 kn = keep_b200.keep_net
 sd = keep_b200.synth.make_state_dict(seed=0, config=config)
-net = keep_b200.KeepNetB200(flags=kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3, **(kn.KEEP_ASIAN_CFG if config == "Asian" else kn.KEEP_GENERAL_CFG))
+net = keep_b200.KeepNetB200(flags=kn.TC3_FLAGS, **(kn.KEEP_ASIAN_CFG if config == "Asian" else kn.KEEP_GENERAL_CFG))
 net.load_state_dict(sd, strict=True)
 net.eval().to("cuda")
 x = keep_b200.synth.make_clip(T, seed=1234, coherent=True).cuda()

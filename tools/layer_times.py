@@ -5,7 +5,7 @@ import torch, keep_b200
 ap = argparse.ArgumentParser(); ap.add_argument("--frames", type=int, default=3); ap.add_argument("--mode", default="tc"); ap.add_argument("--out", default="gpurun_out/layers.csv")
 a = ap.parse_args()
 kn = keep_b200.keep_net
-flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3}[a.mode]
+flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.TC3_FLAGS}[a.mode]
 net = keep_b200.KeepNetB200(flags=flags); net.load_state_dict(keep_b200.synth.make_state_dict(0)); net.eval().to("cuda")
 x = keep_b200.synth.make_clip(a.frames, seed=1234).cuda()
 net(x, need_upscale=False); net(x, need_upscale=False); torch.cuda.synchronize()

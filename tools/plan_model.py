@@ -34,7 +34,7 @@ ceil3 = pk["tflops"] / 3.0          # split-precision mode: three MMAs per MAC
 lib = keep_b200.keep_net.load_library()
 kn = keep_b200.keep_net
 cfg = kn.KEEP_ASIAN_CFG if a.config == "Asian" else {}
-net = keep_b200.KeepNetB200(flags=kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3, **(dict(cfg, batch_clips=a.clips) if a.clips > 1 else cfg))
+net = keep_b200.KeepNetB200(flags=kn.TC3_FLAGS, **(dict(cfg, batch_clips=a.clips) if a.clips > 1 else cfg))
 net.load_state_dict(keep_b200.synth.make_state_dict(seed=0, config=a.config), strict=True)
 h = net._make_engine(flags=256 | net._flags)
 path = os.path.join(tempfile.gettempdir(), "plan_model_%d.txt" % os.getpid())

@@ -14,7 +14,7 @@ ap.add_argument("--mode", default="fp32")
 ap.add_argument("--graph", action="store_true")
 a = ap.parse_args()
 kn = keep_b200.keep_net
-flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3}[a.mode]
+flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.TC3_FLAGS}[a.mode]
 if a.graph:
     flags |= kn.FLAG_CUDA_GRAPH
 net = keep_b200.KeepNetB200(flags=flags)

@@ -14,7 +14,7 @@ a = ap.parse_args()
 assert os.environ.get("KEEP_DEBUG_SKIP_FLOW") or os.environ.get("KEEP_NO_SIDE"), "set KEEP_DEBUG_SKIP_FLOW=1 or KEEP_NO_SIDE=1 (the timeline needs a single stream)"
 kn = keep_b200.keep_net
 lib = kn.load_library()
-flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3}[a.mode]
+flags = {"fp32": 0, "tc": kn.FLAG_TCGEN05, "tc3": kn.TC3_FLAGS}[a.mode]
 sd = keep_b200.synth.make_state_dict(0)
 x = torch.cat([keep_b200.synth.make_clip(a.frames, seed=1234 + 100 * i) for i in range(a.clips)], 0).cuda()
 bk = dict(batch_clips=min(a.clips, a.batch_clips)) if a.batch_clips > 1 else {}
