@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_simt_kernel(const ConvArg
 // partials are summed in split order -> deterministic.
 // GN (gn_part != null; MN % 1024 == 0, cout in {128, 256, 512}): the block also emits GroupNorm(32) partial statistics of
 // the final values it writes -- its 1024 consecutive elements are 1024 / cout whole pixels of one image, every group has
-// exactly 8 of the block's threads; 32 threads add them up in a fixed order -> one slot gn_part[img][slot][32][2]
+// exactly 8 of the block's threads; 32 threads add them up in a fixed order -> one slot per group, gn_part[img][32][slot][2]
 template <bool GN>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
                                                             const float* __restrict__ bias, int act, const void* res,
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
             const long long e0 = (long long)blockIdx.x * 1024;
             const long long img = e0 / img_elems;
             const long long slot = (e0 - img * img_elems) >> 10;
-            *reinterpret_cast<float2*>(gn_part + ((size_t)(img * gn_P + slot) * 32 + g) * 2) = make_float2(ss, qq);
+            *reinterpret_cast<float2*>(gn_part + ((size_t)(img * 32 + g) * gn_P + slot) * 2) = make_float2(ss, qq);
         }
     }
 }

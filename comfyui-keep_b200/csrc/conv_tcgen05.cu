@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [256] bias of the current N tile
 
     pdl_early_trigger();
+    if (threadIdx.x == 0) TC_TRACE(9, 0);                 // kernel entry
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_SA; ++s) { mbar_init(A_FULL(s), GT); mbar_init(A_EMPTY(s), 1); }
         for (int s = 0; s < MAX_SB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
@@ -205,7 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_TRACE(9, 1);                 // barriers + TMEM ready
     pdl_wait();      // barrier init + TMEM allocation above overlapped the previous kernel's tail; inputs are read below
+    if (threadIdx.x == 0) TC_TRACE(9, 2);                 // previous kernel complete
     keep_stamp();
 
     // WIN = 3: 3x3 s1 | 2: 3x3 stride-2 as a 2x2 window over the virtual space-to-depth input | 1: 1x1
@@ -729,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     const int vi = lane >> 1, gslot = vi >> 1;
                     if ((lane & 1) == 0 && gslot < (16 >> (cpg == 2 ? 1 : (cpg == 4 ? 2 : (cpg == 8 ? 3 : 4))))) {
                         const int mt_in_img = ty * a.tiles_x + tx;
-                        a.gn_part[(((size_t)img * a.gn_P + (size_t)mt_in_img * 4 + warp) * 32 + (nn / cpg + gslot)) * 2 + (vi & 1)] = w16[0];
+                        a.gn_part[(((size_t)img * 32 + (nn / cpg + gslot)) * a.gn_P + (size_t)mt_in_img * 4 + warp) * 2 + (vi & 1)] = w16[0];
                     }
                     if (!ok) continue;
                 }
@@ -815,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(9, 3);                 // all roles done
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, a.tmem_cols);

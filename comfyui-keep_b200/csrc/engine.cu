@@ -554,9 +554,14 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     }
     // GroupNorm statistics of the output from the producing kernel (conv epilogue, or the split-K reduce): the consumer's
     // gn() then needs one tiny finalize launch instead of a read pass over the tensor plus a second kernel
-    static const bool gn_fuse = !(getenv("KEEP_GN_EPILOGUE") && getenv("KEEP_GN_EPILOGUE")[0] == '0');
+    // KEEP_GN_EPILOGUE: 0 = stand-alone statistics kernels everywhere; 1 = every eligible layer; 2 = split-K layers only (the
+    // reduce kernel emits them almost for free); 3 (default) = split-K layers + conv epilogues with >= 128 output channels
+    // (measured: on the N = 64 layers the epilogue is on the critical path and the extra ~100 instructions per 16-column chunk
+    // cost more than the stand-alone read pass they save)
+    static const int gn_mode = getenv("KEEP_GN_EPILOGUE") ? atoi(getenv("KEEP_GN_EPILOGUE")) : 3;
     static const bool cluster_mode = getenv("KEEP_TC_CLUSTER") && atoi(getenv("KEEP_TC_CLUSTER")) >= 2;   // (no reduce kernel to emit them)
-    if (o.want_stats && use_tc && gn_fuse && !(cluster_mode && a.splitk > 1)) {
+    const bool gn_here = gn_mode == 1 || (gn_mode >= 2 && a.splitk > 1) || (gn_mode == 3 && cw.cout >= 128);
+    if (o.want_stats && use_tc && gn_here && !(cluster_mode && a.splitk > 1)) {
         const int P = conv_gn_slots(a, a.splitk);
         if (P > 0) {
             out.gn_P = P;

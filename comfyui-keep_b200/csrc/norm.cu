@@ -298,55 +298,54 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const T* __restrict__ x, 
 }  // namespace
 
 namespace {
-// Statistics emitted by the producing kernel (conv epilogue / split-K reduce): part[img][P][32][2] fp32 (sum, sum of squares per
-// slot and group).  One block per (image, 4 consecutive groups): a thread reads the 32-byte sector of a slot that holds those
-// four groups, accumulates in double, and the block reduces in a fixed order -> the consumer's per-(n, channel) affine.
+// Statistics emitted by the producing kernel (conv epilogue / split-K reduce): part[img][32 groups][P][2] fp32 (sum, sum of
+// squares per slot).  One block per (image, group) streams the group's P contiguous slots (float4 = two slots per load, four
+// loads in flight per thread), accumulates in double and reduces in a fixed order -> the consumer's per-(n, channel) affine.
 // Replaces the read pass over the whole tensor (gn_partial / gn_small) and its second kernel.
-__global__ void __launch_bounds__(256) gn_finalize_parts_kernel(const float* __restrict__ part, int P, int c, int cpg, double cnt, float eps,
+__global__ void __launch_bounds__(128) gn_finalize_parts_kernel(const float* __restrict__ part, int P, int c, int cpg, double cnt, float eps,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 float* __restrict__ scale, float* __restrict__ shift) {
     pdl_prologue();
-    __shared__ double red[8][8];
-    __shared__ float s_mean[4], s_rstd[4];
-    const int img = blockIdx.x >> 3, gq = blockIdx.x & 7;          // groups 4 gq .. 4 gq + 3
-    const float* base = part + ((size_t)img * P * 32 + (size_t)gq * 4) * 2;
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = threadIdx.x; k < P; k += 256) {
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(base + (size_t)k * 64));
-        const float4 b = __ldcg(reinterpret_cast<const float4*>(base + (size_t)k * 64 + 4));
-        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    __shared__ double rs[4], rq[4];
+    const int img = blockIdx.x >> 5, g = blockIdx.x & 31;
+    const float4* base = reinterpret_cast<const float4*>(part + ((size_t)img * 32 + g) * P * 2);   // P is even: P / 2 float4
+    const int n4 = P >> 1;
+    double s = 0, q = 0;
+    int k = threadIdx.x;
+    for (; k + 3 * 128 < n4; k += 4 * 128) {
+        const float4 a = __ldcg(base + k), b = __ldcg(base + k + 128), c4 = __ldcg(base + k + 256), d = __ldcg(base + k + 384);
+        s += (double)((a.x + a.z) + (b.x + b.z)) + (double)((c4.x + c4.z) + (d.x + d.z));
+        q += (double)((a.y + a.w) + (b.y + b.w)) + (double)((c4.y + c4.w) + (d.y + d.w));
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[threadIdx.x >> 5][j] = acc[j];
+    for (; k < n4; k += 128) {
+        const float4 a = __ldcg(base + k);
+        s += (double)(a.x + a.z);
+        q += (double)(a.y + a.w);
     }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; }
     __syncthreads();
-    if (threadIdx.x < 4) {
-        double ss = 0, qq = 0;
-        for (int w = 0; w < 8; ++w) { ss += red[w][2 * threadIdx.x]; qq += red[w][2 * threadIdx.x + 1]; }
-        const double mean = ss / cnt;
-        double var = qq / cnt - mean * mean;
-        if (var < 0) var = 0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * cpg; i += 256) {
-        const int ch = gq * 4 * cpg + i, gl = i / cpg;
-        const float sc = gamma[ch] * s_rstd[gl];
+    s = (rs[0] + rs[1]) + (rs[2] + rs[3]);
+    q = (rq[0] + rq[1]) + (rq[2] + rq[3]);
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    for (int i = threadIdx.x; i < cpg; i += 128) {
+        const int ch = g * cpg + i;
+        const float sc = gamma[ch] * rstd;
         scale[(size_t)img * c + ch] = sc;
-        shift[(size_t)img * c + ch] = beta[ch] - s_mean[gl] * sc;
+        shift[(size_t)img * c + ch] = beta[ch] - (float)mean * sc;
     }
 }
 }  // namespace
 
 void gn_finalize_parts(const float* part, int n, int P, int hw, int c, float eps, const float* gamma, const float* beta, float* scale,
                        float* shift, cudaStream_t s) {
-    KEEP_CHECK(c % 32 == 0 && P > 0 && gamma && beta, "gn_finalize_parts: bad arguments (c=%d, P=%d)", c, P);
+    KEEP_CHECK(c % 32 == 0 && P > 0 && P % 2 == 0 && gamma && beta, "gn_finalize_parts: bad arguments (c=%d, P=%d)", c, P);
     const int cpg = c / 32;
-    launch_k(gn_finalize_parts_kernel, dim3(n * 8), dim3(256), 0, s, part, P, c, cpg, (double)hw * cpg, eps, gamma, beta, scale, shift);
+    launch_k(gn_finalize_parts_kernel, dim3(n * 32), dim3(128), 0, s, part, P, c, cpg, (double)hw * cpg, eps, gamma, beta, scale, shift);
     CUDA_CHECK(cudaGetLastError());
 }
 

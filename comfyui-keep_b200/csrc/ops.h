@@ -31,7 +31,7 @@ struct ConvArgs {
     int pre_exact = 0;             // tcgen05 fp16-operand path: exact fp32 swish before the fp16 rounding (default: packed tanh.approx)
     long long wt_img_stride = 0;   // tcgen05 path only: per-image packed weight sets (batched A*B^T for attention)
     // tcgen05 path only: GroupNorm(32) partial statistics of the output, written by the producing kernel (the conv epilogue,
-    // or the split-K reduce) as gn_part[n][gn_P][32][2] fp32 (sum, sum of squares) -- see conv_gn_slots()
+    // or the split-K reduce) as gn_part[n][32][gn_P][2] fp32 (sum, sum of squares) -- see conv_gn_slots()
     float* gn_part = nullptr; int gn_P = 0;
 };
 // slots per image the producing kernel writes for a layer run with `splitk` K-splits (0: this layer cannot emit statistics)

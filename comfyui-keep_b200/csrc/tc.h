@@ -16,7 +16,7 @@ struct TcConvArgs {
     int splitk; float* partial;
     int act; const void* res; int res_dt; void* out; int out_dt;
     // GroupNorm(32) statistics of the OUTPUT, emitted by the epilogue (no split-K): per (image, m tile, epilogue warp) one slot of
-    // 32 x (sum, sum of squares) fp32 partials over the warp's 32 pixels -> gn_part[img][gn_P][32][2]; a fixed-order finalize
+    // 32 x (sum, sum of squares) fp32 partials over the warp's 32 pixels -> gn_part[img][32][gn_P][2]; a fixed-order finalize
     // kernel turns them into the consumer's per-channel affine (norm.cu: gn_finalize_parts)
     float* gn_part; int gn_cpg; int gn_P;
     long long M;
@@ -50,7 +50,7 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
               cudaStream_t s);
 // fixed-order split-K reduce + epilogue (conv_simt.cu)
 // gn_part != null: also emit GroupNorm(32) partial statistics of the final values, one slot of 32 x (sum, sumsq) per
-// 1024-element block -> gn_part[img][gn_P][32][2] (hw = output pixels per image; needs conv_gn_slots(...) > 0)
+// 1024-element block -> gn_part[img][32][gn_P][2] (hw = output pixels per image; needs conv_gn_slots(...) > 0)
 void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
                    int res_dt, void* out, int out_dt, cudaStream_t s, float* gn_part = nullptr, int gn_P = 0, long long hw = 0);
 

@@ -18,6 +18,6 @@ lib.keepop_tc_trace(ctypes.c_void_p(buf.data_ptr()))
 run_conv(lib, x, wt, b, 1, pads, 1, pre if act != "none" else None, act, "none", None, use_tc=mode)
 lib.keepop_tc_trace(None)
 t = buf.cpu().reshape(10, 16); t0 = int(t[t > 0].min())
-names = ["prod:loads_issued", "prod:got_A_EMPTY", "prod:A_FULL_arrive", "mma:got_ACC_EMPTY", "mma:got_A_FULL", "mma:issued_all", "epi:got_ACC_FULL", "epi:done", "load:first_tap", "load:last_tap"]
+names = ["prod:loads_issued", "prod:got_A_EMPTY", "prod:A_FULL_arrive", "mma:got_ACC_EMPTY", "mma:got_A_FULL", "mma:issued_all", "epi:got_ACC_FULL", "epi:done", "load:first_tap", "cta:entry/setup/pdl/done"]
 for i, nm in enumerate(names):
     print("%-20s" % nm, " ".join("%7d" % (int(v) - t0 if v > 0 else -1) for v in t[i][:10]))
