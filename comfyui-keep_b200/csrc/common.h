@@ -134,6 +134,25 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Division of a 31-bit dividend by a run-time constant, magic numbers from the host: q = umulhi(n, mul) >> shr.
+// (p = 31 + ceil(log2 d), mul = ceil(2^p / d) < 2^32, exact for n < 2^31.)  The kernels' work-item decoding used 64-bit
+// divisions -- ~400 cycles of dependent subroutine each, several per role before the first load or MMA of every CTA.
+struct FastDiv { uint32_t mul = 0, shr = 0, d = 1; };
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d < 1 ? 1 : d;
+    if (f.d == 1) return f;
+    uint32_t l = 0;
+    while ((1ull << l) < f.d) ++l;
+    const uint32_t pbits = 31 + l;
+    f.mul = (uint32_t)(((1ull << pbits) + f.d - 1) / f.d);
+    f.shr = pbits - 32;
+    return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
+#endif
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: true exactly once per (call site's mask, current device),
 // so a second engine on another GPU of the same process configures its own context (thread-safe)
 bool first_use_on_current_device(unsigned long long* mask);   // engine.cu
@@ -179,6 +198,33 @@ __device__ __forceinline__ void keep_stamp() {
 #define KEEP_STAMP_SETTER(fn) \
     void fn(unsigned long long* p) { cudaMemcpyToSymbol(g_stamp_buf, &p, sizeof(p)); }
 __device__ __forceinline__ void pdl_prologue() { pdl_early_trigger(); pdl_wait(); keep_stamp(); }
+// Short kernels between two tcgen05 convolutions (split-K reduce, GroupNorm finalize, LayerNorm, softmax, ...): let the NEXT
+// kernel's CTAs be scheduled right away.  The next convolution then runs its prologue (barrier init, TMEM allocation, cold
+// instruction fetch, index setup, and the weight loader's first TMA transfers -- none of which depend on this kernel's
+// output) while this kernel executes, and only its activation loads wait for this grid (griddepcontrol.wait in the roles
+// that touch global memory).  Unlike triggering from the convolutions themselves (round 1: a cascade of parked 200 KB
+// CTAs), the parked kernel is at most one convolution deep: convolutions do not trigger early.  KEEP_PDL_LIGHT_TRIGGER=0 at
+// compile time switches it off.
+#ifndef KEEP_PDL_LIGHT_TRIGGER
+#define KEEP_PDL_LIGHT_TRIGGER 1
+#endif
+__device__ __forceinline__ void pdl_prologue_light() {
+    if (KEEP_PDL_LIGHT_TRIGGER) pdl_trigger(); else pdl_early_trigger();
+    pdl_wait();
+    keep_stamp();
+}
+// stamp from one designated thread of block 0 (kernels whose thread 0 does not pass griddepcontrol.wait first)
+__device__ __forceinline__ void keep_stamp_here() {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long* b = g_stamp_buf;
+        if (b) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            const unsigned long long i = atomicAdd(b, 1ull);
+            if (i < KEEP_STAMP_CAP) b[1 + i] = t;
+        }
+    }
+}
 
 bool pdl_enabled();   // engine.cu: KEEP_PDL env (default on)
 

@@ -207,9 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TC_TRACE(9, 1);                 // barriers + TMEM ready
-    pdl_wait();      // barrier init + TMEM allocation above overlapped the previous kernel's tail; inputs are read below
-    if (threadIdx.x == 0) TC_TRACE(9, 2);                 // previous kernel complete
-    keep_stamp();
+    // griddepcontrol.wait is executed per role, right before its first access to memory the previous kernel may still be
+    // writing (activations, residual, outputs): everything above and the roles' index setup -- and the weight loader's first
+    // TMA transfers, weights being constants -- overlap the previous kernel when it triggered early (pdl_prologue_light).
 
     // WIN = 3: 3x3 s1 | 2: 3x3 stride-2 as a 2x2 window over the virtual space-to-depth input | 1: 1x1
     constexpr int win = WIN, TAPS = WIN * WIN;
@@ -230,25 +230,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     // all N tiles of the item back to back against ONE production of the activation stages, which stay in shared memory
     // until the last N tile has consumed them (an N = 1024 linear otherwise converts the same activations eight times).
     const int nt_inner = a.a_stat ? a.ntile_n : 1;
-    const long long total = (long long)m_tiles * a.splitk * (a.a_stat ? 1 : a.ntile_n);
-    const int cb_per = (a.ncb + a.splitk - 1) / a.splitk;
+    const int total = m_tiles * a.splitk * (a.a_stat ? 1 : a.ntile_n);       // (host checks < 2^31)
+    const int cb_per = a.cb_per;
 
-    auto decode = [&](long long w, int nti, int& nt, int& img, int& ty, int& tx, int& ks) {
-        long long r = w;
+    auto decode = [&](int w, int nti, int& nt, int& img, int& ty, int& tx, int& ks) {
+        uint32_t r = (uint32_t)w;
         int mt;
         if (a.cluster_k) {   // cluster split-K: the K splits of one output tile are the CTAs of one cluster (k split fastest)
-            ks = (int)(w % a.splitk); r = w / a.splitk;
-            nt = (int)(r % a.ntile_n);
-            mt = (int)(r / a.ntile_n);
+            const uint32_t q = fdiv(r, a.fd_splitk);
+            ks = (int)(r - q * a.fd_splitk.d); r = q;
+            const uint32_t q2 = fdiv(r, a.fd_ntile);
+            nt = (int)(r - q2 * a.fd_ntile.d);
+            mt = (int)q2;
         } else {
             if (a.a_stat) nt = nti;
-            else { nt = (int)(w % a.ntile_n); r = w / a.ntile_n; }
-            mt = (int)(r % m_tiles);
-            ks = (int)(r / m_tiles);
+            else { const uint32_t q = fdiv(r, a.fd_ntile); nt = (int)(r - q * a.fd_ntile.d); r = q; }
+            const uint32_t q2 = fdiv(r, a.fd_mtiles);
+            mt = (int)(r - q2 * a.fd_mtiles.d);
+            ks = (int)q2;
         }
-        img = mt / mt_per_img;
+        img = (int)fdiv((uint32_t)mt, a.fd_mtimg);
         const int t2 = mt - img * mt_per_img;
-        ty = t2 / a.tiles_x;
+        ty = (int)fdiv((uint32_t)t2, a.fd_tilesx);
         tx = t2 - ty * a.tiles_x;
     };
 
@@ -275,7 +278,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             soff[it] = p < npix ? row * 128 + ((pl ^ (row & 7)) << 4) : -1;
         }
         int stage = 0, phase = 0, trace_i = 0, seq = 0;
-        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        bool waited = false;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
             int nt, img, ty, tx, ks;
             decode(w, 0, nt, img, ty, tx, ks);
             const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
@@ -294,9 +298,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         ok = ok && iy >= 0 && iy < Hl && ix >= 0 && ix < Wl;
                         pix = (img * a.h + (iy >> ushift)) * a.w + (ix >> ushift);
                     } else {
-                        const long long q = (long long)ty * 128 + p_first + it * PPI;     // pixel index within the image
-                        ok = ok && q < (long long)a.h * a.w;
-                        pix = (int)((long long)img * a.h * a.w + q);
+                        const int q = ty * 128 + p_first + it * PPI;     // pixel index within the image (host checks n*h*w < 2^31)
+                        ok = ok && q < a.h * a.w;
+                        pix = img * a.h * a.w + q;
                     }
                     pixv[it] = ok ? pix : -1;
                 }
@@ -315,6 +319,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 if (ch < a.c0) { src = reinterpret_cast<const uint8_t*>(a.in0); sc_ch = a.c0; cc = ch; }
                 else { src = reinterpret_cast<const uint8_t*>(a.in1); sc_ch = a.c1; cc = ch - a.c0; }
                 constexpr int ESZ = IN_F16 ? 2 : 4;
+                if (!waited) {   // first activation load of this thread: the previous kernel must have completed (PDL)
+                    pdl_wait();
+                    waited = true;
+                    if (pt == 0 && grp == 0) { TC_TRACE(9, 2); keep_stamp_here(); }
+                }
                 // ---- issue every global load of this stage first (memory-level parallelism), then transform
                 uint4 raw[MAXIT][IN_F16 ? 1 : 2];
 #pragma unroll
@@ -428,10 +437,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         }
     } else if (warp == kLoadWarp) {
         // =========================== weight loader (1-D TMA) ===========================
+        // real weights were packed at engine creation: their first panels are fetched while the previous kernel still runs
+        if (!a.wt_static) pdl_wait();
         if (lane == 0 && a.w_resident) {
             // the layer's whole panel set (one N tile, no K split) fits next to the activation stages: fetch it once
             // per CTA instead of once per 128-pixel tile (which costs 64 B/clk/SM of L2 bandwidth at the MMA floor)
-            if ((long long)blockIdx.x < total) {
+            if ((int)blockIdx.x < total) {
                 const int npanels = a.ncb * TAPS;
                 mbar_arrive_expect_tx(B_FULL(0), (uint32_t)(npanels * b_stage_bytes));
                 const uint8_t* g = reinterpret_cast<const uint8_t*>(a.wt);
@@ -440,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             }
         } else if (lane == 0) {
             int stage = 0, phase = 0, trace_l = 0;
-            for (long long w = blockIdx.x; w < total; w += gridDim.x)
+            for (int w = blockIdx.x; w < total; w += gridDim.x)
             for (int nti = 0; nti < nt_inner; ++nti) {
                 int nt, img, ty, tx, ks;
                 decode(w, nti, nt, img, ty, tx, ks);
@@ -503,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             // ---- weights resident: one wait per activation stage, then TAPS x KSTEPS x PASSES back-to-back MMAs
             mbar_wait(B_FULL(0), 0);
             tc_fence_after();
-            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
                 mbar_wait(ACC_EMPTY(as), pacc ^ 1);
                 tc_fence_after();
                 if (lane == 0) TC_TRACE(3, trace_m);
@@ -533,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         } else {
             // ---- weights streamed: one panel per (channel block, tap) through the SB-deep ring
             int sb = 0, pb = 0;
-            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
                 const int sa0 = sa, pa0 = pa;      // A-stationary: every N tile of the item re-reads the same activation stages
                 for (int nti = 0; nti < nt_inner; ++nti) {
                     int nt, img, ty, tx, ks;
@@ -583,9 +594,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         // flight) -> 64 contiguous bytes to HBM.  Everything stays in registers (a first version spilled the row to
         // local memory and re-fetched the bias from L2 every 16 columns: 8K cycles per tile, the kernel's bottleneck).
         int as = 0, pacc = 0, trace_e = 0, bias_nt = -1;
+        bool waited = false;
         const int row = warp * 32 + lane;          // accumulator row = output pixel within the tile
         const int r = row >> 3, c = row & 7;
-        for (long long w = blockIdx.x; w < total; w += gridDim.x)
+        for (int w = blockIdx.x; w < total; w += gridDim.x)
         for (int nti = 0; nti < nt_inner; ++nti) {
             int nt, img, ty, tx, ks;
             decode(w, nti, nt, img, ty, tx, ks);
@@ -605,13 +617,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 ok = oy < a.ho && ox < a.wo;
                 pixel = ((long long)img * a.ho + oy) * a.wo + ox;
             } else {
-                const long long q = (long long)ty * 128 + row;
-                ok = q < (long long)a.h * a.w;
-                pixel = (long long)img * a.h * a.w + q;
+                const int q = ty * 128 + row;
+                ok = q < a.h * a.w;
+                pixel = (long long)(img * a.h * a.w + q);
             }
             const int n0 = nt * a.bn;
             mbar_wait(ACC_FULL(as), pacc);
             tc_fence_after();
+            if (!waited) { pdl_wait(); waited = true; }   // residual reads / output writes below (returns at once: the producers passed it)
             if (threadIdx.x == 0) TC_TRACE(6, trace_e);
             const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * a.bn);
             const bool partial_out = a.splitk > 1;
@@ -732,7 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     const int vi = lane >> 1, gslot = vi >> 1;
                     if ((lane & 1) == 0 && gslot < (16 >> (cpg == 2 ? 1 : (cpg == 4 ? 2 : (cpg == 8 ? 3 : 4))))) {
                         const int mt_in_img = ty * a.tiles_x + tx;
-                        a.gn_part[(((size_t)img * 32 + (nn / cpg + gslot)) * a.gn_P + (size_t)mt_in_img * 4 + warp) * 2 + (vi & 1)] = w16[0];
+                        a.gn_part[(((size_t)img * 32 + ((nn >> a.gn_cpg_shift) + gslot)) * a.gn_P + (size_t)mt_in_img * 4 + warp) * 2 + (vi & 1)] = w16[0];
                     }
                     if (!ok) continue;
                 }
@@ -917,7 +930,7 @@ namespace {
 // device-side repack: fp32 [(tap*cin + ci)][cout] (the CUDA-core path's layout) -> tcgen05 fp16 swizzled panels
 __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout, int taps, int bn, int ncb, int passes, int s2d_pad,
                                  size_t total, __half* __restrict__ out, int wide) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const PanelPos q = panel_pos(idx, bn, taps, ncb, passes);
@@ -942,7 +955,7 @@ __global__ void tc_repack_kernel(const float* __restrict__ w, int cin, int cout,
 __global__ void __launch_bounds__(256) tc_pack_matrix_kernel(const float* __restrict__ src, long long bstride, int ld_n, int ld_k,
                                                              int N, int K, int bn, int ncb, int ntile, int passes, float alpha,
                                                              size_t per_batch, size_t total_units, __half* __restrict__ out) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= total_units) return;
     const int cb = cb_of(passes), upr = cb / 8;
@@ -1129,6 +1142,7 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     if (t.win > 1) { t.tiles_y = cdiv(a.ho, 16); t.tiles_x = cdiv(a.wo, 8); }
     else { t.tiles_y = cdiv((long long)a.h * a.w, 128); t.tiles_x = 1; }
     t.ntile_n = cdiv(a.cout, bn);
+    t.wt_static = (a.wt_static && a.wt_img_stride == 0) ? 1 : 0;
     // split-K inside a thread-block cluster (<= 8 CTAs, portable size) whenever the layer splits at all: the partial
     // tiles meet in distributed shared memory instead of L2 and no second kernel is needed (opt-in: KEEP_TC_CLUSTER=8; measured slower than the two-kernel path, profiles/r1_experiments.md;
     // the value caps the cluster size)
@@ -1142,10 +1156,11 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     t.cluster_k = (want_cluster && splitk > 1) ? 1 : 0;
     t.splitk = splitk; t.partial = partial;
     t.act = a.act; t.res = a.res; t.res_dt = a.res_dt; t.out = a.out; t.out_dt = a.out_dt;
-    t.gn_part = nullptr; t.gn_cpg = 0; t.gn_P = 0;
+    t.gn_part = nullptr; t.gn_cpg = 0; t.gn_P = 0; t.gn_cpg_shift = 0;
     if (a.gn_part && splitk == 1) {   // (split layers: the reduce kernel emits the statistics)
         KEEP_CHECK(!t.cluster_k && a.cout % 32 == 0 && a.gn_P == t.tiles_y * t.tiles_x * 4, "conv2d_tc: bad GroupNorm statistics request");
         t.gn_part = a.gn_part; t.gn_cpg = a.cout / 32; t.gn_P = a.gn_P;
+        while ((1 << t.gn_cpg_shift) < t.gn_cpg) ++t.gn_cpg_shift;
         KEEP_CHECK(t.gn_cpg == 2 || t.gn_cpg == 4 || t.gn_cpg == 8 || t.gn_cpg == 16, "conv2d_tc: GroupNorm statistics need 64..512 channels");
     }
     t.M = (long long)a.n * a.ho * a.wo;
@@ -1175,7 +1190,13 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     KEEP_CHECK(smem <= 227 * 1024, "conv2d_tc: %zu bytes of shared memory", smem);
     KEEP_CHECK(a.c1 == 0 || a.in0_dt == a.in1_dt, "conv2d_tc: concatenated sources must share a dtype");
     const long long total = (long long)t.n * t.tiles_y * t.tiles_x * splitk * (t.a_stat ? 1 : t.ntile_n);
-    KEEP_CHECK(!t.cluster_k || total < (1ll << 30), "conv2d_tc: cluster grid too large");
+    KEEP_CHECK(total < (1ll << 30), "conv2d_tc: too many work items");
+    t.cb_per = cdiv(t.ncb, splitk);
+    t.fd_ntile = make_fastdiv((uint32_t)t.ntile_n);
+    t.fd_mtiles = make_fastdiv((uint32_t)(t.n * t.tiles_y * t.tiles_x));
+    t.fd_mtimg = make_fastdiv((uint32_t)(t.tiles_y * t.tiles_x));
+    t.fd_tilesx = make_fastdiv((uint32_t)t.tiles_x);
+    t.fd_splitk = make_fastdiv((uint32_t)splitk);
     // num_sms > 0: persistent grid capped at that many CTAs.  num_sms < 0 (low-priority side branch): short-lived CTAs
     // of about -num_sms work items each and as many of them as that takes -- they soak up whatever SMs the
     // latency-critical main stream leaves idle and hand an SM back within a few microseconds when it wants one.
@@ -1239,6 +1260,8 @@ int keepop_conv2d_tc(const keep::ConvArgs& a_in, const float* w_oihw_host, int p
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     try {
+        CUDA_CHECK(cudaStreamSynchronize(s));   // panels are complete: the loader may run ahead of griddepcontrol.wait
+        a.wt_static = 1;
         conv2d_tc(a, dw, bn, passes, splitk, part, sms, s);
         if (gn_part) gn_finalize_parts(gn_part, a.n, a.gn_P, a.ho * a.wo, a.cout, 1e-6f, gn_gamma, gn_beta, gn_scale, gn_shift, s);
         CUDA_CHECK(cudaStreamSynchronize(s));

@@ -554,11 +554,12 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     }
     // GroupNorm statistics of the output from the producing kernel (conv epilogue, or the split-K reduce): the consumer's
     // gn() then needs one tiny finalize launch instead of a read pass over the tensor plus a second kernel
-    // KEEP_GN_EPILOGUE: 0 = stand-alone statistics kernels everywhere; 1 = every eligible layer; 2 = split-K layers only (the
-    // reduce kernel emits them almost for free); 3 (default) = split-K layers + conv epilogues with >= 128 output channels
-    // (measured: on the N = 64 layers the epilogue is on the critical path and the extra ~100 instructions per 16-column chunk
-    // cost more than the stand-alone read pass they save)
-    static const int gn_mode = getenv("KEEP_GN_EPILOGUE") ? atoi(getenv("KEEP_GN_EPILOGUE")) : 3;
+    // KEEP_GN_EPILOGUE: 0 = stand-alone statistics kernels everywhere; 1 (default) = every eligible layer; 2 = split-K layers
+    // only (the reduce kernel emits them almost for free); 3 = split-K layers + conv epilogues with >= 128 output channels.
+    // Measured on B200 (same box, frames/s at T = 20): 146.2 / 151.0 / 149.1 / 149.3 -- the N = 64 layers pay ~18 us per launch
+    // for the extra ~100 epilogue instructions per 16-column chunk (their epilogue is on the critical path), the read pass
+    // and second kernel they replace cost more.
+    static const int gn_mode = getenv("KEEP_GN_EPILOGUE") ? atoi(getenv("KEEP_GN_EPILOGUE")) : 1;
     static const bool cluster_mode = getenv("KEEP_TC_CLUSTER") && atoi(getenv("KEEP_TC_CLUSTER")) >= 2;   // (no reduce kernel to emit them)
     const bool gn_here = gn_mode == 1 || (gn_mode >= 2 && a.splitk > 1) || (gn_mode == 3 && cw.cout >= 128);
     if (o.want_stats && use_tc && gn_here && !(cluster_mode && a.splitk > 1)) {
@@ -595,7 +596,10 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         int nl = a.splitk > 1 ? 2 : 1;
         if (use_tc) {
             a.a_wide = (a.a_wide && passes == 3 && a.in0_dt == F32) ? 1 : 0;
-            nl = conv2d_tc(a, tc_weights(cw, bn, passes, tc_is_s2d(a) ? a.pad_t : -1, a.a_wide), bn, passes, a.splitk, a.partial, grid_cap, s_);
+            bool pooled = false;
+            const __half* panels = tc_weights(cw, bn, passes, tc_is_s2d(a) ? a.pad_t : -1, a.a_wide, &pooled);
+            a.wt_static = pooled ? 1 : 0;   // packed at engine creation: the loader may prefetch ahead of griddepcontrol.wait
+            nl = conv2d_tc(a, panels, bn, passes, a.splitk, a.partial, grid_cap, s_);
         }
         else if (use_small) conv2d_small(a, s_);
         else conv2d_simt(a, s_);
@@ -641,10 +645,14 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
     return out;
 }
 
-const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide) {
+const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide, bool* pooled) {
     std::vector<TcW>& variants = tcw_[cw.w];
+    if (pooled) *pooled = false;
     for (const TcW& v : variants)
-        if (v.bn == bn && v.passes == passes && v.wide == wide) return v.p;
+        if (v.bn == bn && v.passes == passes && v.wide == wide) {
+            if (pooled) *pooled = v.pooled;
+            return v.p;
+        }
     TcW t;
     t.bn = bn; t.passes = passes; t.wide = wide;
     const int cb = tc_cb(passes);

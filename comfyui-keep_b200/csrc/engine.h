@@ -159,7 +159,7 @@ class Engine {
     bool prepacked_ = false;
     void prepack_tc_weights();
     std::unordered_map<const float*, std::vector<TcW>> tcw_;   // every (N tile, passes, wide) variant a layer has been run with
-    const __half* tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide = 0);
+    const __half* tc_weights(const ConvW& cw, int bn, int passes, int s2d_pad, int wide = 0, bool* pooled = nullptr);
     bool wide_scope_ = false; // KEEP_FLAG_TC_WIDE and inside generator(): raw-input feature-map layers use bf16 activation pairs
     int pass_override_ = 0;   // != 0: operand passes for the layers being enqueued (generator tail experiment)
     int tc_passes_ = 1;   // 1: fp16 operands; 3: split-precision (fp32-grade) tensor-core mode

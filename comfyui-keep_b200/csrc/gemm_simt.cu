@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BGemmArgs a, int vecA,
 // whose 64-wide tiling fills only 16-32 SMs (26 us for a 256 x 256 x 512 product).  Same summation order over k.
 template <bool TRANSB>
 __global__ void __launch_bounds__(256) bgemm32_kernel(const BGemmArgs a, int vecA, int vecB) {
-    pdl_prologue();
+    pdl_prologue_light();
     constexpr int T = 32, KT = 32;
     __shared__ __align__(16) float As[KT][T + 4];
     __shared__ __align__(16) float Bs[KT][T + 4];

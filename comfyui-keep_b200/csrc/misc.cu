@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwArgs a, size_t
 
 __global__ void __launch_bounds__(256) cft_combine_kernel(const void* dec, int dec_dt, const void* scale, const void* shift,
                                                           int ss_dt, float cond, void* out, int o_dt, size_t n4) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= n4) return;
     const size_t i = i4 * 4;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) cft_combine_kernel(const void* dec, int d
 
 __global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ in, float* __restrict__ out, size_t total4,
                                                     int inner) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= total4) return;
     const size_t i = i4 * 4;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ in
 // one warp per row, L <= 1024
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, long long rows, int L,
                                                            const int* __restrict__ region, int n_win, int Lq) {
-    pdl_prologue();
+    pdl_prologue_light();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s
 template <int NV4>
 __global__ void __launch_bounds__(256) softmax_rows_v4_kernel(float* __restrict__ s, long long rows, int L,
                                                               const int* __restrict__ region, int n_win, int Lq) {
-    pdl_prologue();
+    pdl_prologue_light();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) softmax_expect2_kernel(const float* __res
 __global__ void __launch_bounds__(256) kalman_update_kernel(const float* __restrict__ z, const float* __restrict__ zp,
                                                             const float* __restrict__ gain, float* __restrict__ out,
                                                             size_t total, int c, int* status) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float g = gain[i / c];
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restr
                                                             const float* __restrict__ codebook, int cdim,
                                                             const int* __restrict__ forced, int* __restrict__ idx_out,
                                                             void* quant, int q_dt, int* status) {
-    pdl_prologue();
+    pdl_prologue_light();
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (tok >= tokens) return;
     const float* r = logits + (size_t)tok * ncodes;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(256) vq_nearest_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) sparse_causal_gather_kernel(const float* __restrict__ kv, float* __restrict__ out,
                                                                    int T, int L, int c4, size_t total4) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int cc = (int)(i % c4);
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256) sparse_causal_gather_kernel(const float* 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, void* out, int o_dt, int c, int hw,
                                                            size_t total, int mode) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
     if (i >= total) return;
     const size_t n = i / hw, p = i % hw;
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const void* x, int dt, void* out, int o_dt, int c, int hw,
                                                            size_t total, int* status) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
     if (i >= total) return;
     const size_t n = i / hw, p = i % hw;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const void* x, int dt
 // keep_processor.py:258-260: float32(crop_u8 / 255.) (the division is done in float64), BGR -> RGB, (v - 0.5) / 0.5
 __global__ void __launch_bounds__(256) u8bgr_to_nchw_norm_kernel(const unsigned char* __restrict__ x, float* __restrict__ out, int hw,
                                                                  size_t total) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
     if (i >= total) return;
     const size_t n = i / hw, p = i % hw;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(256) u8bgr_to_nchw_norm_kernel(const unsigned 
 // B/utils/img_util.py:38-94 (tensor2img, rgb2bgr=True, min_max=(-1, 1), uint8): clamp, (x - min) / (max - min), * 255, round half even
 __global__ void __launch_bounds__(256) nhwc_to_u8bgr_kernel(const void* x, int dt, unsigned char* __restrict__ out, size_t total,
                                                             int* status) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw
     if (i >= total) return;
 #pragma unroll
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256) nhwc_to_u8bgr_kernel(const void* x, int d
 // arch_util.py:113-144 -> F.grid_sample(bilinear, zeros, align_corners=True)
 __global__ void __launch_bounds__(256) flow_warp_kernel(const void* img, int dt, const float* __restrict__ flow, void* out,
                                                         int o_dt, int h, int w, int c, size_t total, int* status) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*h*w
     if (i >= total) return;
     const int x = (int)(i % w);
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const void* img, int dt,
 // gmflow/position.py:26-46 on (h/splits, w/splits) windows, tiled over the map (gmflow/utils.py:66-86)
 __global__ void __launch_bounds__(256) add_window_sine_pos_kernel(float* __restrict__ x, int h, int w, int c, int splits,
                                                                   size_t total) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int ch = (int)(i % c);
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(256) add_window_sine_pos_kernel(float* __restr
 __global__ void __launch_bounds__(256) window_partition_kernel(const float* __restrict__ x, float* __restrict__ out, int h, int w,
                                                                int c4, int k, int sh, int sw, int ldx4, size_t total4,
                                                                int merge) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over windowed layout (n*k*k, wh*ww, c4)
     if (i >= total4) return;
     const int wh = h / k, ww = w / k;
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(256) oihw_to_kc_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
                                                       float* __restrict__ out, size_t total) {
-    pdl_prologue();
+    pdl_prologue_light();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int ct = ca + cb;

@@ -33,6 +33,7 @@ struct ConvArgs {
     // tcgen05 path only: GroupNorm(32) partial statistics of the output, written by the producing kernel (the conv epilogue,
     // or the split-K reduce) as gn_part[n][32][gn_P][2] fp32 (sum, sum of squares) -- see conv_gn_slots()
     float* gn_part = nullptr; int gn_P = 0;
+    int wt_static = 0;             // tcgen05 path only: packed weights are older than the stream's previous kernel (see TcConvArgs)
 };
 // slots per image the producing kernel writes for a layer run with `splitk` K-splits (0: this layer cannot emit statistics)
 int conv_gn_slots(const ConvArgs& a, int splitk);

@@ -13,6 +13,11 @@ struct TcConvArgs {
     int taps, cout, bn, ho, wo, ncb;
     int win, s2d, ncbr, pad_t, pad_l;   // window mode (3 / 2 / 1); stride-2 virtual space-to-depth parameters
     int tiles_y, tiles_x, ntile_n;
+    FastDiv fd_ntile, fd_mtiles, fd_mtimg, fd_tilesx, fd_splitk;   // work-item decoding without hardware-less 64-bit divisions
+    int cb_per;         // channel blocks per K split
+    int gn_cpg_shift;   // log2(gn_cpg)
+    int wt_static;      // 1: the weight panels were packed before this launch was enqueued behind its predecessor (engine
+                        // creation): the loader may fetch them before griddepcontrol.wait
     int splitk; float* partial;
     int act; const void* res; int res_dt; void* out; int out_dt;
     // GroupNorm(32) statistics of the OUTPUT, emitted by the epilogue (no split-K): per (image, m tile, epilogue warp) one slot of

@@ -177,14 +177,29 @@ class KeepNetB200(nn.Module):
         if strict and (missing or unexpected):
             raise RuntimeError("Error(s) in loading state_dict for KeepNetB200:\n\tMissing key(s): %s\n\tUnexpected key(s): %s"
                                % (missing[:8], unexpected[:8]))
-        w = {}
         for k, shp in self._shapes.items():
-            if k not in state_dict:
-                continue
+            if k in state_dict and list(state_dict[k].shape) != list(shp):
+                raise RuntimeError("size mismatch for %s: got %s, expected %s" % (k, list(state_dict[k].shape), list(shp)))
+        # one flat host image of the fp32 weights, page-locked when a CUDA device is present: `.to(device)` after an `offload()`
+        # (nodes.py:135-136 does that after EVERY node execution) is then ~900 asynchronous DMA copies (~25 GB/s) instead of
+        # pageable staging; the tensors handed to keep_create are views into it
+        keys = [k for k in self._shapes if k in state_dict]
+        offs, total = {}, 0
+        for k in keys:
+            offs[k] = total
+            total += (state_dict[k].numel() + 63) // 64 * 64
+        flat = torch.empty(max(total, 1), dtype=torch.float32)
+        if torch.cuda.is_available() and not self._plan_only:
+            try:
+                flat = flat.pin_memory()
+            except RuntimeError:
+                pass
+        w = {}
+        for k in keys:
             t = state_dict[k]
-            if list(t.shape) != list(shp):
-                raise RuntimeError("size mismatch for %s: got %s, expected %s" % (k, list(t.shape), list(shp)))
-            w[k] = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            v = flat[offs[k]:offs[k] + t.numel()].view(t.shape)
+            v.copy_(t.detach())
+            w[k] = v
         self._weights = w
         self._drop_engine()
         if self._device.type == "cuda":
