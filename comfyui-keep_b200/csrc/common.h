@@ -198,16 +198,26 @@ __device__ __forceinline__ void keep_stamp() {
 #define KEEP_STAMP_SETTER(fn) \
     void fn(unsigned long long* p) { cudaMemcpyToSymbol(g_stamp_buf, &p, sizeof(p)); }
 __device__ __forceinline__ void pdl_prologue() { pdl_early_trigger(); pdl_wait(); keep_stamp(); }
-// Short kernels between two tcgen05 convolutions (split-K reduce, GroupNorm finalize, LayerNorm, softmax, ...): let the NEXT
-// kernel's CTAs be scheduled right away.  The next convolution then runs its prologue (barrier init, TMEM allocation, cold
-// instruction fetch, index setup, and the weight loader's first TMA transfers -- none of which depend on this kernel's
-// output) while this kernel executes, and only its activation loads wait for this grid (griddepcontrol.wait in the roles
-// that touch global memory).  Unlike triggering from the convolutions themselves (round 1: a cascade of parked 200 KB
-// CTAs), the parked kernel is at most one convolution deep: convolutions do not trigger early.  KEEP_PDL_LIGHT_TRIGGER=0 at
-// compile time switches it off.
-#ifndef KEEP_PDL_LIGHT_TRIGGER
-#define KEEP_PDL_LIGHT_TRIGGER 1
+// Short kernels between two tcgen05 convolutions (split-K reduce, GroupNorm finalize, LayerNorm, ...): let the NEXT kernel's
+// CTAs be scheduled right away (pdl_prologue_tiny).  The next convolution then runs its prologue (barrier init, TMEM
+// allocation, cold instruction fetch, index setup, and the weight loader's first TMA transfers -- none of which depend on
+// this kernel's output) while this kernel executes, and only its activation loads wait for this grid (griddepcontrol.wait
+// in the roles that touch global memory).  Dependents are launched once ALL CTAs of this grid have started, so this grid
+// itself never competes with the parked CTAs.  Measured on B200 (profiles/r2_experiments.md): triggering from every
+// non-convolution kernel (pdl_prologue_light, incl. the 10-30 us SIMT attention GEMMs) lets a convolution's 704-thread /
+// 56K-register CTAs park three kernels ahead and starve the kernels in between (bgemm32 8.7 -> 27.9 us, 158 -> 150
+// frames/s); so only kernels of a few microseconds trigger, and the longer ones keep the plain prologue.
+#ifndef KEEP_PDL_TINY_TRIGGER
+#define KEEP_PDL_TINY_TRIGGER 1
 #endif
+#ifndef KEEP_PDL_LIGHT_TRIGGER
+#define KEEP_PDL_LIGHT_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_prologue_tiny() {
+    if (KEEP_PDL_TINY_TRIGGER) pdl_trigger(); else pdl_early_trigger();
+    pdl_wait();
+    keep_stamp();
+}
 __device__ __forceinline__ void pdl_prologue_light() {
     if (KEEP_PDL_LIGHT_TRIGGER) pdl_trigger(); else pdl_early_trigger();
     pdl_wait();

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             const float* __restrict__ bias, int act, const void* res,
                                                             int res_dt, void* out, int out_dt, float* __restrict__ gn_part, int gn_P,
                                                             long long img_elems) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     __shared__ float2 s_gn[GN ? 256 : 1];
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (!GN && i >= MN) return;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 __global__ void __launch_bounds__(256) splitk_reduce1_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
                                                              const float* __restrict__ bias, int act, const void* res,
                                                              int res_dt, void* out, int out_dt) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= MN) return;
     float v = 0.0f;

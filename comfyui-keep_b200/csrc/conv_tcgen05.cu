@@ -26,6 +26,9 @@
 #ifndef KEEP_TC_HPITCH
 #define KEEP_TC_HPITCH 10
 #endif
+#ifndef KEEP_PDL_CONV_TRIGGER
+#define KEEP_PDL_CONV_TRIGGER 0
+#endif
 
 #include "ops.h"
 #include "tc.h"
@@ -587,6 +590,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 }
             }
         }
+        // every MMA of this CTA is issued: let the next kernel's CTAs be scheduled (KEEP_PDL_CONV_TRIGGER=1).  The next kernel
+        // is almost always a short one (split-K reduce / GroupNorm finalize): its blocks then sit at griddepcontrol.wait while
+        // this grid's last epilogues drain, and start the moment it completes
+#if KEEP_PDL_CONV_TRIGGER
+        if (leader) pdl_trigger();
+#endif
     } else if (warp < kEpiWarps) {
         // =========================== epilogue (warps 0-3 <-> TMEM lane quarters) ===========================
         // Each thread owns one accumulator row (= one output pixel) and walks its BN columns 16 at a time:
@@ -1213,6 +1222,10 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     }
     launch_k(kern, dim3(grid), dim3(kThreads), smem, s, t);
     CUDA_CHECK(cudaGetLastError());
+    if (a.no_reduce) {
+        KEEP_CHECK(splitk == a.splitk && !a.bias && !a.res && a.act == ACT_NONE, "conv2d_tc: no_reduce needs the K split as requested and a plain epilogue");
+        return 1;
+    }
     if (splitk > 1)
         splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s, a.gn_part, a.gn_P,
                       (long long)a.ho * a.wo);

@@ -825,6 +825,44 @@ Tensor Engine::mha(const float* q, int ldq, long long sq, const float* k, int ld
     return O;
 }
 
+// Multi-head attention with every contraction on the tensor cores (single batch; q / k / v token-major with the heads side by
+// side).  Scores: ONE GEMM over K = heads * dh channels run in split-K = heads mode WITHOUT the reduce -- the K split of head h
+// covers exactly that head's channel blocks, so partial tile h is Q_h K_h^T (the key matrix is packed as the B operand with
+// the softmax scale folded in).  P V: the heads ride on the kernel's image index with per-image B panels (V_h^T as a strided
+// view), then one permute back to token-major.  Used where the SIMT GEMMs were the cost: CFA at 32^2 (1024 x 1024 x 4 x 256,
+// keep_arch.py:200-241,519-541: 72 + 68 us per frame on the CUDA cores).
+Tensor Engine::mha_tc(const float* q, const float* k, const float* v, int Lq, int Lk, int heads, int dh, float scale) {
+    const int inner = heads * dh;
+    KEEP_CHECK(dh % tc_cb(tc_passes_) == 0 && Lk % 16 == 0 && Lq % 8 == 0, "mha_tc: unsupported shape (Lq %d, Lk %d, dh %d)", Lq, Lk, dh);
+    if (plan_) plan_->push_back("attention nb=1 Lq=" + std::to_string(Lq) + " Lk=" + std::to_string(Lk) + " heads=" + std::to_string(heads) +
+                                " dh=" + std::to_string(dh) + " kernel=tcgen05");
+    const int grid_cap = (s_ == side_ && side_) ? side_sms_ : main_cap_;
+    const int bn = tc_pick_bn(Lk, cdiv(Lq, 128), tc_passes_);
+    const size_t per = tc_pack_matrix(nullptr, 0, 0, 0, 1, Lk, inner, bn, tc_passes_, 1.0f, nullptr, s_);
+    __half* panels = (__half*)ar_->alloc(per * sizeof(__half));
+    Tensor S = talloc(heads, Lq, 1, Lk, F32);
+    if (!ar_->dry()) {
+        tc_pack_matrix(k, 0, inner, 1, 1, Lk, inner, bn, tc_passes_, scale, panels, s_);
+        ConvArgs a;
+        a.in0 = q; a.in0_dt = F32; a.c0 = inner;
+        a.n = 1; a.h = Lq; a.w = 1; a.up = 1;
+        a.kh = 1; a.kw = 1; a.stride = 1; a.cout = Lk; a.ho = Lq; a.wo = 1;
+        a.out = S.p; a.out_dt = F32;
+        a.wt_img_stride = (long long)per;
+        a.splitk = heads; a.partial = S.f(); a.no_reduce = 1;
+        conv2d_tc(a, panels, bn, tc_passes_, heads, S.f(), grid_cap, s_);
+        softmax_rows(S.f(), (long long)heads * Lq, Lk, nullptr, 1, Lq, s_);
+        launches_ += 3;
+    }
+    ar_->free(panels);
+    Tensor Oh = gemm_nt_tc(S.f(), heads, Lq, Lk, v, dh, 1, inner, dh, 1.0f);   // (heads, Lq, dh); B[h] = V_h^T, a strided view
+    tfree(S);
+    Tensor O = talloc(1, Lq, 1, inner, F32);
+    if (!ar_->dry()) { heads_to_tokens(Oh.f(), O.f(), heads, Lq, dh, s_); launches_ += 1; }
+    tfree(Oh);
+    return O;
+}
+
 // vqgan_arch.py:219-243
 Tensor Engine::attn_block(const Tensor& x, const std::string& p, bool out_stats) {
     Aff a = gn(x, p + ".norm");
@@ -1312,7 +1350,10 @@ Tensor Engine::cfa(const Tensor& cur, const Tensor& prev, const std::string& p) 
     pv.n = 1; pv.h = nbt * L; pv.w = 1;
     Tensor q = linear(x, p + ".attn.to_q"), k = linear(pv, p + ".attn.to_k"), v = linear(pv, p + ".attn.to_v");
     const long long bs = (long long)L * inner;
-    Tensor o = mha(q.f(), inner, bs, k.f(), inner, bs, v.f(), inner, bs, nbt, L, L, heads, dh, 1.0f / sqrtf((float)dh));
+    static const int tc_min_L = getenv("KEEP_MHA_TC_MIN_L") ? atoi(getenv("KEEP_MHA_TC_MIN_L")) : 1024;
+    Tensor o = ((flags_ & KEEP_FLAG_TCGEN05) && nbt == 1 && L >= tc_min_L)
+                   ? mha_tc(q.f(), k.f(), v.f(), L, L, heads, dh, 1.0f / sqrtf((float)dh))
+                   : mha(q.f(), inner, bs, k.f(), inner, bs, v.f(), inner, bs, nbt, L, L, heads, dh, 1.0f / sqrtf((float)dh));
     tfree(q); tfree(k); tfree(v);
     Tensor y = linear(o, p + ".attn.to_out.0");
     tfree(o);

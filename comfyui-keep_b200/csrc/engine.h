@@ -87,6 +87,8 @@ class Engine {
     Tensor mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv, long long sv,
                int nb, int Lq, int Lk, int heads, int dh, float scale);
     Tensor gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, long long b_bstride, int ld_n, int ld_k, int N, float alpha);
+    // multi-head attention on token-major (L, heads * dh) fp32 matrices, all three contractions on the tcgen05 kernel
+    Tensor mha_tc(const float* q, const float* k, const float* v, int Lq, int Lk, int heads, int dh, float scale);
     ConvW convw(const std::string& prefix) const;
     const float* warr(const std::string& key) const;
     bool has(const std::string& key) const { return W_.count(key) != 0; }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwArgs a, size_t
 
 __global__ void __launch_bounds__(256) cft_combine_kernel(const void* dec, int dec_dt, const void* scale, const void* shift,
                                                           int ss_dt, float cond, void* out, int o_dt, size_t n4) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= n4) return;
     const size_t i = i4 * 4;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) cft_combine_kernel(const void* dec, int d
 
 __global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ in, float* __restrict__ out, size_t total4,
                                                     int inner) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= total4) return;
     const size_t i = i4 * 4;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ in
 // one warp per row, L <= 1024
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, long long rows, int L,
                                                            const int* __restrict__ region, int n_win, int Lq) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s
 template <int NV4>
 __global__ void __launch_bounds__(256) softmax_rows_v4_kernel(float* __restrict__ s, long long rows, int L,
                                                               const int* __restrict__ region, int n_win, int Lq) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) softmax_expect2_kernel(const float* __res
 __global__ void __launch_bounds__(256) kalman_update_kernel(const float* __restrict__ z, const float* __restrict__ zp,
                                                             const float* __restrict__ gain, float* __restrict__ out,
                                                             size_t total, int c, int* status) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float g = gain[i / c];
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restr
                                                             const float* __restrict__ codebook, int cdim,
                                                             const int* __restrict__ forced, int* __restrict__ idx_out,
                                                             void* quant, int q_dt, int* status) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (tok >= tokens) return;
     const float* r = logits + (size_t)tok * ncodes;
@@ -560,6 +560,18 @@ __global__ void __launch_bounds__(256) oihw_to_kc_kernel(const float* __restrict
     out[idx] = w[((size_t)o * I + i) * taps + t];
 }
 
+__global__ void __launch_bounds__(256) heads_to_tokens_kernel(const float4* __restrict__ x, float4* __restrict__ out, int heads, int rows,
+                                                              int dh4, size_t total4) {
+    pdl_prologue_tiny();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over the output: (row, head, d4)
+    if (i >= total4) return;
+    const int d = (int)(i % dh4);
+    const size_t r = i / dh4;
+    const int h = (int)(r % heads);
+    const size_t row = r / heads;
+    out[i] = x[((size_t)h * rows + row) * dh4 + d];
+}
+
 __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
                                                       float* __restrict__ out, size_t total) {
     pdl_prologue_light();
@@ -711,6 +723,14 @@ void oihw_to_kc(const float* w_dev, float* out_dev, int O, int I, int taps, cuda
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(blocks_for(total)); cfg.blockDim = dim3(256); cfg.stream = s;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, oihw_to_kc_kernel, w_dev, out_dev, O, I, taps, total));
+}
+
+void heads_to_tokens(const float* x, float* out, int heads, int rows, int dh, cudaStream_t s) {
+    KEEP_CHECK(dh % 4 == 0, "heads_to_tokens: dh %% 4");
+    const size_t total4 = (size_t)heads * rows * (dh / 4);
+    launch_k(heads_to_tokens_kernel, dim3(blocks_for(total4)), dim3(256), 0, s, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out),
+             heads, rows, dh / 4, total4);
+    CUDA_CHECK(cudaGetLastError());
 }
 
 void concat2(const float* a, int ca, const float* b, int cb, float* out, long long rows, cudaStream_t s) {

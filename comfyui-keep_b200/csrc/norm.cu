@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const double* __restri
                                                           float eps, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ scale,
                                                           float* __restrict__ shift, int c_total, int c_off) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     __shared__ double rs[4], rq[4];
     const int groups = c / cpg;
     const int in = blockIdx.x / groups, g = blockIdx.x % groups;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ b, float eps, const float* __restrict__ res,
                                                         float* __restrict__ out, const float* __restrict__ add2, int add2_rows,
                                                         float* __restrict__ out2) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* xr = x + (size_t)row * c;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) layernorm_v4_kernel(const float* __restri
                                                            const float* __restrict__ b, float eps, const float* __restrict__ res,
                                                            float* __restrict__ out, const float* __restrict__ add2, int add2_rows,
                                                            float* __restrict__ out2) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * c);
@@ -251,7 +251,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gn_small_kernel(const T* __restrict__ x, int hw, int c, int cpg, float eps,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ scale, float* __restrict__ shift, int c_total, int c_off) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     __shared__ double rs[8], rq[8];
     const int groups = c / cpg;
     const int in = blockIdx.x / groups, g = blockIdx.x % groups;
@@ -305,7 +305,7 @@ namespace {
 __global__ void __launch_bounds__(128) gn_finalize_parts_kernel(const float* __restrict__ part, int P, int c, int cpg, double cnt, float eps,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 float* __restrict__ scale, float* __restrict__ shift) {
-    pdl_prologue_light();
+    pdl_prologue_tiny();
     __shared__ double rs[4], rq[4];
     const int img = blockIdx.x >> 5, g = blockIdx.x & 31;
     const float4* base = reinterpret_cast<const float4*>(part + ((size_t)img * 32 + g) * P * 2);   // P is even: P / 2 float4

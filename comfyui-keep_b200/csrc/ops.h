@@ -34,6 +34,8 @@ struct ConvArgs {
     // or the split-K reduce) as gn_part[n][32][gn_P][2] fp32 (sum, sum of squares) -- see conv_gn_slots()
     float* gn_part = nullptr; int gn_P = 0;
     int wt_static = 0;             // tcgen05 path only: packed weights are older than the stream's previous kernel (see TcConvArgs)
+    int no_reduce = 0;             // tcgen05 path only: leave the splitk partial tiles as the result -- with K = heads x dh and
+                                   // splitk = heads, partial[h] IS the per-head product Q_h K_h^T (multi-head attention scores)
 };
 // slots per image the producing kernel writes for a layer run with `splitk` K-splits (0: this layer cannot emit statistics)
 int conv_gn_slots(const ConvArgs& a, int splitk);
@@ -147,6 +149,8 @@ void window_merge(const float* x, float* out, int n, int h, int w, int c, int k,
 void convex_upsample8(const float* mask, const float* flow, float* out, int n, int h, int w, cudaStream_t s);
 // weight layout transform at engine creation: OIHW / (O, I) on the device -> [(tap * I + i)][o]
 void oihw_to_kc(const float* w_dev, float* out_dev, int O, int I, int taps, cudaStream_t s);
+// multi-head attention output (heads, rows, dh) -> token-major (rows, heads * dh)
+void heads_to_tokens(const float* x, float* out, int heads, int rows, int dh, cudaStream_t s);
 // concat along channels of two (rows, c) fp32 matrices / generic strided copy
 void concat2(const float* a, int ca, const float* b, int cb, float* out, long long rows, cudaStream_t s);
 
