@@ -198,17 +198,17 @@ __device__ __forceinline__ void keep_stamp() {
 #define KEEP_STAMP_SETTER(fn) \
     void fn(unsigned long long* p) { cudaMemcpyToSymbol(g_stamp_buf, &p, sizeof(p)); }
 __device__ __forceinline__ void pdl_prologue() { pdl_early_trigger(); pdl_wait(); keep_stamp(); }
-// Short kernels between two tcgen05 convolutions (split-K reduce, GroupNorm finalize, LayerNorm, ...): let the NEXT kernel's
-// CTAs be scheduled right away (pdl_prologue_tiny).  The next convolution then runs its prologue (barrier init, TMEM
-// allocation, cold instruction fetch, index setup, and the weight loader's first TMA transfers -- none of which depend on
-// this kernel's output) while this kernel executes, and only its activation loads wait for this grid (griddepcontrol.wait
-// in the roles that touch global memory).  Dependents are launched once ALL CTAs of this grid have started, so this grid
-// itself never competes with the parked CTAs.  Measured on B200 (profiles/r2_experiments.md): triggering from every
-// non-convolution kernel (pdl_prologue_light, incl. the 10-30 us SIMT attention GEMMs) lets a convolution's 704-thread /
-// 56K-register CTAs park three kernels ahead and starve the kernels in between (bgemm32 8.7 -> 27.9 us, 158 -> 150
-// frames/s); so only kernels of a few microseconds trigger, and the longer ones keep the plain prologue.
+// Experiment knobs (both default OFF, measured on B200, profiles/r2_experiments.md): early `launch_dependents` from the short
+// kernels between two tcgen05 convolutions (pdl_prologue_tiny: split-K reduce, GroupNorm finalize, LayerNorm, small softmax,
+// ...) or from every non-convolution kernel (pdl_prologue_light).  The next convolution then runs its prologue (barrier
+// init, TMEM allocation, cold instruction fetch, index setup, the weight loader's first TMA transfers) while the short
+// kernel executes -- the convolution kernel waits per role for exactly that reason -- and the per-frame chain alone does get
+// shorter.  But a parked convolution CTA holds a whole SM (200 KB of shared memory, 56K registers) doing nothing, and the
+// clip as a whole is SM-time bound (GMFlow on the side stream fills every SM the chain leaves idle): 160.3 frames/s without
+// any early trigger, 154.6 with the tiny set, 150.3 with the light set (which also parks convolution CTAs three kernels
+// ahead: bgemm -> softmax -> bgemm -> conv).
 #ifndef KEEP_PDL_TINY_TRIGGER
-#define KEEP_PDL_TINY_TRIGGER 1
+#define KEEP_PDL_TINY_TRIGGER 0
 #endif
 #ifndef KEEP_PDL_LIGHT_TRIGGER
 #define KEEP_PDL_LIGHT_TRIGGER 0
