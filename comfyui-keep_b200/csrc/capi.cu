@@ -32,6 +32,7 @@ int keepop_conv2d_tc(const ConvArgs& a, const float* w_oihw_host, int passes, cu
 namespace keep {
 void stamp_set_conv_simt(unsigned long long*); void stamp_set_conv_small(unsigned long long*); void stamp_set_conv_tc(unsigned long long*);
 void stamp_set_gemm(unsigned long long*); void stamp_set_misc(unsigned long long*); void stamp_set_norm(unsigned long long*);
+void stamp_set_attn(unsigned long long*);
 void launch_log_enable(bool on);
 int launch_log_dump(const char* path);
 }
@@ -255,7 +256,7 @@ int keepop_conv2d_gn(int use_tc, const float* x_dev, int n, int h, int w, int ci
 // debug: kernel-start timeline.  stamps = device buffer of 1 + 65536 uint64 (null = off); launch log = host-side names
 int keepop_kernel_stamps(unsigned long long* dev_buf) {
     keep::stamp_set_conv_simt(dev_buf); keep::stamp_set_conv_small(dev_buf); keep::stamp_set_conv_tc(dev_buf);
-    keep::stamp_set_gemm(dev_buf); keep::stamp_set_misc(dev_buf); keep::stamp_set_norm(dev_buf);
+    keep::stamp_set_gemm(dev_buf); keep::stamp_set_misc(dev_buf); keep::stamp_set_norm(dev_buf); keep::stamp_set_attn(dev_buf);
     return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
 }
 int keepop_launch_log(int enable) { keep::launch_log_enable(enable != 0); return 0; }
@@ -282,6 +283,16 @@ int keepop_layernorm(const float* x_dev, int rows, int c, const float* g_dev, co
                      void* stream) {
     KEEP_API_BEGIN
     layernorm(x_dev, rows, c, g_dev, b_dev, eps, nullptr, out_dev, nullptr, 0, nullptr, (cudaStream_t)stream);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+    KEEP_API_END
+}
+
+int keepop_attention_fused(const float* q, const float* k, const float* v, int nb, int Lq, int Lk, int dh, float scale,
+                           const unsigned char* region_dev, int n_win, float* out_dev, void* stream) {
+    KEEP_API_BEGIN
+    attention_tc(q, dh, (long long)Lq * dh, k, dh, (long long)Lk * dh, v, dh, (long long)Lk * dh, out_dev, dh, (long long)Lq * dh, nb, Lq, Lk, dh,
+                 scale, region_dev, n_win, (cudaStream_t)stream);
     CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
     KEEP_API_END

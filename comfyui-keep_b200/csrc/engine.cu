@@ -372,6 +372,9 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
             }
         CUDA_CHECK(cudaMalloc((void**)&region_, reg.size() * sizeof(int)));
         CUDA_CHECK(cudaMemcpy(region_, reg.data(), reg.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<unsigned char> reg8(reg.begin(), reg.end());
+        CUDA_CHECK(cudaMalloc((void**)&region8_, reg8.size()));
+        CUDA_CHECK(cudaMemcpy(region8_, reg8.data(), reg8.size(), cudaMemcpyHostToDevice));
         std::vector<float> grid(4096 * 2);
         for (int t = 0; t < 4096; ++t) { grid[2 * t] = (float)(t % 64); grid[2 * t + 1] = (float)(t / 64); }
         CUDA_CHECK(cudaMalloc((void**)&grid64_, grid.size() * sizeof(float)));
@@ -391,6 +394,7 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         }
         tc_configure_device();
         conv_small_configure_device();
+        attention_tc_configure_device();
         if ((flags_ & KEEP_FLAG_TCGEN05) && tc_passes_ == 3) prepack_tc_weights();
     }
 }
@@ -442,6 +446,7 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     cudaFree(wpool_);
     cudaFree(region_);
+    cudaFree(region8_);
     cudaFree(gn_tickets_);
     cudaFree(status_);
     if (ev_last_) cudaEventDestroy(ev_last_);
@@ -999,7 +1004,18 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
     if (kk.p) tfree(kk);
     if (v.p) tfree(v);
     Tensor S, Ow;
-    if (flags_ & KEEP_FLAG_TCGEN05) {
+    static const bool fused_attn = !(getenv("KEEP_FUSED_ATTN") && getenv("KEEP_FUSED_ATTN")[0] == '0');
+    if ((flags_ & KEEP_FLAG_TCGEN05) && tc_passes_ == 3 && fused_attn && attention_tc_eligible(L, L, C)) {
+        // fused window attention (attn_tcgen05.cu): scores and probabilities stay in TMEM / shared memory
+        if (plan_) plan_->push_back("attention nb=" + std::to_string(nimg * 4) + " Lq=" + std::to_string(L) + " Lk=" + std::to_string(L) +
+                                    " heads=1 dh=" + std::to_string(C) + " kernel=tcgen05_fused");
+        Ow = talloc(nimg * 4, L, 1, C, F32);
+        if (!ar_->dry()) {
+            attention_tc(qw.f(), C, (long long)L * C, kw.f(), C, (long long)L * C, vw.f(), C, (long long)L * C, Ow.f(), C, (long long)L * C,
+                         nimg * 4, L, L, C, 1.0f / sqrtf((float)C), shift ? region8_ : nullptr, 4, s_);
+            launches_ += 1;
+        }
+    } else if (flags_ & KEEP_FLAG_TCGEN05) {
         // window attention on the tensor cores: S = (Q K^T)/sqrt(C), softmax (+ shift mask), O = P V
         S = gemm_nt_tc(qw.f(), nimg * 4, L, C, kw.f(), (long long)L * C, C, 1, L, 1.0f / sqrtf((float)C));
         if (!ar_->dry()) {
@@ -1027,7 +1043,8 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
             launches_ += 3;
         }
     }
-    tfree(S); tfree(qw); tfree(kw); tfree(vw);
+    if (S.p) tfree(S);
+    tfree(qw); tfree(kw); tfree(vw);
     Tensor O = talloc(nimg, H * Wd, 1, C, F32);
     if (!ar_->dry()) { window_merge(Ow.f(), O.f(), nimg, H, Wd, C, k, sh, sh, s_); launches_ += 1; }
     tfree(Ow);

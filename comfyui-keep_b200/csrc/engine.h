@@ -133,6 +133,7 @@ class Engine {
     cudaEvent_t ev_last_ = nullptr;   // tail of the previous forward call (cross-stream ordering of engine-owned buffers)
     int* gn_tickets_ = nullptr;  // GroupNorm fused-finalize arrival counters [2 streams][gn_ticket_count()]
     int* region_ = nullptr;      // GMFlow shifted-window region ids [4][1024]
+    unsigned char* region8_ = nullptr;   // the same table as bytes (fused attention kernel)
     float* grid64_ = nullptr;    // GMFlow coordinate grid (4096, 2)
     Arena arena_, arena2_;          // main / side-branch (GMFlow) workspaces
     Arena* ar_ = &arena_;           // arena of the branch currently being enqueued

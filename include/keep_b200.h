@@ -148,6 +148,12 @@ int keepop_layernorm(const float* x_dev, int rows, int c, const float* g_dev, co
 /* multi-head attention on packed (nb*L, heads*dh) fp32 matrices */
 int keepop_attention(const float* q_dev, const float* k_dev, const float* v_dev, int nb, int Lq, int Lk, int heads, int dh,
                      float scale, float* out_dev, void* stream);
+/* fused attention on tcgen05 (QK^T -> softmax -> PV in one kernel, scores never in HBM): q (nb, Lq, dh), k / v (nb, Lk, dh),
+ * out (nb, Lq, dh) fp32 contiguous; region_dev: optional (n_win, Lk) uint8 region ids of a shifted swin-window layer (adds -100
+ * where region[q] != region[k]; batch z uses row z % n_win; needs Lq == Lk), gmflow/transformer.py:19-43,88-91.  dh = 128,
+ * Lq % 128 == 0, Lk % 64 == 0, Lk <= 1024.  Replaces softmax(q @ k^T * scale + mask) @ v (gmflow/transformer.py:8-16,78-98). */
+int keepop_attention_fused(const float* q_dev, const float* k_dev, const float* v_dev, int nb, int Lq, int Lk, int dh, float scale,
+                           const unsigned char* region_dev, int n_win, float* out_dev, void* stream);
 int keepop_flow_warp(const float* img_dev, const float* flow_dev, float* out_dev, int n, int h, int w, int c, void* stream);
 int keepop_convex_upsample8(const float* mask_dev, const float* flow_dev, float* out_dev, int n, int h, int w, void* stream);
 int keepop_window_sine_pos(float* x_dev, int n, int h, int w, int c, int splits, void* stream);

@@ -236,3 +236,40 @@ def test_conv_epilogue_groupnorm_statistics(lib, case):
     # and the convolution itself is untouched by the extra epilogue work
     want = ref_conv(x, wt, b, stride, pads, up, None, "none", "none", r.permute(0, 3, 1, 2) if res else None)
     assert float((out.permute(0, 3, 1, 2) - want).abs().max()) < 2e-4 * max(1.0, float(want.abs().max()))
+
+
+# ---- fused attention on tcgen05 (attn_tcgen05.cu): QK^T -> softmax -> PV in one kernel ------------------------------------
+def _swin_regions(L_side=32, shift=16, n_win=4):
+    """region ids of GMFlow's shifted 2x2 windows on a 64x64 map (gmflow/transformer.py:19-43), as the engine builds them"""
+    H = W = 2 * L_side
+    reg = torch.zeros((n_win, L_side * L_side), dtype=torch.uint8)
+    for win in range(n_win):
+        for t in range(L_side * L_side):
+            y, x = (win // 2) * L_side + t // L_side, (win % 2) * L_side + t % L_side
+            ry = 0 if y < H - L_side else (1 if y < H - shift else 2)
+            rx = 0 if x < W - L_side else (1 if x < W - shift else 2)
+            reg[win, t] = ry * 3 + rx
+    return reg
+
+
+@pytest.mark.parametrize("nb,Lq,Lk,masked", [(8, 1024, 1024, False), (8, 1024, 1024, True), (3, 256, 512, False), (2, 128, 64, False)])
+def test_fused_attention_matches_torch(lib, nb, Lq, Lk, masked):
+    """softmax(q k^T / sqrt(d) + mask) v against torch fp32 (TF32 off): the split-precision MMAs are fp32-grade, so the bar is
+    the same 2e-5 as the CUDA-core attention's; the masked case is GMFlow's shifted-window layer (mask values 0 / -100)."""
+    from test_gpu_ops import _p, _rc
+    dh = 128
+    g = torch.Generator(device="cpu").manual_seed(23)
+    q = (torch.randn((nb, Lq, dh), generator=g) * 1.5).cuda()
+    k = (torch.randn((nb, Lk, dh), generator=g) * 1.5).cuda()
+    v = torch.randn((nb, Lk, dh), generator=g).cuda()
+    scale = dh ** -0.5
+    reg = _swin_regions().cuda() if masked else None
+    out = torch.full((nb, Lq, dh), float("nan"), device="cuda")
+    _rc(lib, lib.keepop_attention_fused(_p(q), _p(k), _p(v), nb, Lq, Lk, dh, scale, _p(reg), 4 if masked else 1, _p(out), None))
+    s = q @ k.transpose(-1, -2) * scale
+    if masked:
+        r = reg.long()[torch.arange(nb) % 4]                                   # (nb, L)
+        s = s + torch.where(r[:, :, None] != r[:, None, :], torch.tensor(-100.0, device="cuda"), torch.tensor(0.0, device="cuda"))
+    want = torch.softmax(s, -1) @ v
+    err = float((out - want).abs().max())
+    assert bool(torch.isfinite(out).all()) and err < 2e-5, "max abs err %g" % err
