@@ -326,7 +326,7 @@ Engine::Engine(int device, const keep_weight_desc* w, int n_w, int flags) : devi
         CUDA_CHECK(cudaMemset(status_, 0, sizeof(int)));
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_last_, cudaEventDisableTiming));
         // KEEP_SIDE_SMS = n > 0: side-branch persistent kernels capped at n CTAs; n < 0: short CTAs of -n work items each
-        { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 100; if (side_sms_ > num_sms_ || (side_sms_ >= 0 && side_sms_ < 8)) side_sms_ = num_sms_; }
+        { const char* e = getenv("KEEP_SIDE_SMS"); side_sms_ = e ? atoi(e) : 64; if (side_sms_ > num_sms_ || (side_sms_ >= 0 && side_sms_ < 8)) side_sms_ = num_sms_; }
     }
     { const char* e = getenv("KEEP_BATCH_MAX"); batch_max_ = e ? std::max(1, std::min(8, atoi(e))) : 2; }
     adt_ = (flags & KEEP_FLAG_FP16_FEATURES) ? F16 : F32;
