@@ -91,7 +91,22 @@ struct AttnTcArgs {
     float scale;
     const unsigned char* region;        // [n_win][Lk] region ids of a shifted-window layer (Lq == Lk), or null
     int n_win;
+    // swin window mode (win_side > 0): q / k / v / out are whole token maps (map_w x map_w tokens per image, row stride ld*,
+    // image stride *_bs) and batch z = image * win_side^2 + window; row r of a window is token
+    //   ((wy * wsz + r / wsz + shift) mod map_w) * map_w + (wx * wsz + r mod wsz + shift) mod map_w
+    // i.e. the window partition (with its cyclic shift, gmflow/transformer.py:78-98) and the merge are index math here
+    int win_side, wsz_log2, map_w, shift;
 };
+
+// window row -> token index (plain mode: identity)
+__device__ __forceinline__ int at_token(const AttnTcArgs& a, int win, int r) {
+    if (a.win_side == 0) return r;
+    const int wsz = 1 << a.wsz_log2;
+    const int wy = win / a.win_side, wx = win - wy * a.win_side;
+    const int y = (wy * wsz + (r >> a.wsz_log2) + a.shift) & (a.map_w - 1);
+    const int x = (wx * wsz + (r & (wsz - 1)) + a.shift) & (a.map_w - 1);
+    return y * a.map_w + x;
+}
 
 // 8 fp32 -> (hi, lo) fp16 pairs: hi = fp16(v), lo = fp16(v - hi)
 __device__ __forceinline__ void at_split8(const float* v, uint4& hi, uint4& lo) {
@@ -152,12 +167,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
     const int qtiles = a.Lq >> 7;
     const int z = blockIdx.x / qtiles, qt = blockIdx.x - z * qtiles;
     const int NKB = a.Lk / AT_KB;
+    const int nwin = a.win_side > 0 ? a.win_side * a.win_side : 1;
+    const int img = a.win_side > 0 ? z / nwin : z, win = a.win_side > 0 ? z - img * nwin : 0;   // tensor batch index / window
 
     if (threadIdx.x == 0) {
         at_mbar_init(Q_FULL, AT_PROD);
         for (int s = 0; s < 2; ++s) {
-            at_mbar_init(K_FULL(s), AT_PROD); at_mbar_init(K_EMPTY(s), 1);
-            at_mbar_init(V_FULL(s), AT_PROD); at_mbar_init(V_EMPTY(s), 1);
+            at_mbar_init(K_FULL(s), AT_PROD / 2); at_mbar_init(K_EMPTY(s), 1);     // K / V stages: one producer group each
+            at_mbar_init(V_FULL(s), AT_PROD / 2); at_mbar_init(V_EMPTY(s), 1);
             at_mbar_init(S_FULL(s), 1); at_mbar_init(S_EMPTY(s), 128);
         }
         at_mbar_init(P_FULL, 128); at_mbar_init(P_EMPTY, 1); at_mbar_init(O_FULL, 1);
@@ -172,18 +189,23 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
 
     if (warp >= 5) {
         // =========================== producers ===========================
+        // Two groups of four warps.  A stage's critical path is global-load latency + conversion + the proxy fence (which also
+        // waits for any load the thread has in flight, so a thread cannot prefetch across stages): in pass A the groups take
+        // alternate K stages, in pass B group 0 produces the K blocks and group 1 the (transposed) V blocks, so one
+        // stage's load latency hides behind another's conversion and behind the MMAs / softmax of the block before.
         const int pt = threadIdx.x - 5 * 32;          // 0 .. 255
+        const int grp = pt >> 7, gt = pt & 127;       // producer group, thread within the group
         pdl_wait();                                   // q / k / v come from the previous kernels
         if (pt == 0) keep_stamp_here();
-        // ---- Q tile (scaled): 128 rows x DH channels, unit = 8 channels
+        // ---- Q tile (scaled): 128 rows x DH channels, unit = 8 channels (all 256 threads)
         {
-            const float* qb = a.q + (size_t)z * a.q_bs + (size_t)(qt * 128) * a.ldq;
+            const float* qb = a.q + (size_t)img * a.q_bs;
             constexpr int UPR = NCB * 4;              // units per row
 #pragma unroll 2
             for (int u = pt; u < 128 * UPR; u += AT_PROD) {
                 const int row = u / UPR, cu = u - row * UPR, cb = cu >> 2, pl = cu & 3;
                 float v[8];
-                ldg256(qb + (size_t)row * a.ldq + cb * 32 + pl * 8, v);
+                ldg256(qb + (size_t)at_token(a, win, qt * 128 + row) * a.ldq + cb * 32 + pl * 8, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] *= a.scale;
                 uint4 hi, lo;
@@ -195,67 +217,71 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             at_fence_proxy_async();
             at_mbar_arrive(Q_FULL);
         }
-        const float* kb = a.k + (size_t)z * a.k_bs;
-        const float* vb = a.v + (size_t)z * a.v_bs;
-        for (int t = 0; t < 2 * NKB; ++t) {
-            const int j = t < NKB ? t : t - NKB;
-            // ---- K block j: 64 keys x DH channels (rows = keys)
-            {
-                const int s = t & 1;
-                at_mbar_wait(K_EMPTY(s), (uint32_t)(((t >> 1) & 1) ^ 1));
-                uint8_t* dstK = sK + s * SM::K_STAGE;
-                constexpr int UPR = NCB * 4;
-                float v[(AT_KB * UPR) / AT_PROD][8];
+        const float* kb = a.k + (size_t)img * a.k_bs;
+        const float* vb = a.v + (size_t)img * a.v_bs;
+        // ---- K block j into stage buffer t & 1 (rows = keys), by the 128 threads of one group
+        auto produce_K = [&](int t) {
+            const int j = t < NKB ? t : t - NKB, s = t & 1;
+            constexpr int UPR = NCB * 4;
+            constexpr int NU = (AT_KB * UPR) / (AT_PROD / 2);          // units per thread (8 at DH = 128)
+            float v[NU][8];
 #pragma unroll
-                for (int i = 0; i < (AT_KB * UPR) / AT_PROD; ++i) {
-                    const int u = pt + i * AT_PROD;
-                    const int row = u / UPR, cu = u - row * UPR;
-                    ldg256(kb + (size_t)(j * AT_KB + row) * a.ldk + (cu >> 2) * 32 + (cu & 3) * 8, v[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < (AT_KB * UPR) / AT_PROD; ++i) {
-                    const int u = pt + i * AT_PROD;
-                    const int row = u / UPR, cu = u - row * UPR, cb = cu >> 2, pl = cu & 3;
-                    uint4 hi, lo;
-                    at_split8(v[i], hi, lo);
-                    uint8_t* dst = dstK + cb * (AT_KB * 128) + row * 128 + ((pl ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(dst) = hi;
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>((uintptr_t)dst ^ 64)) = lo;
-                }
-                at_fence_proxy_async();
-                at_mbar_arrive(K_FULL(s));
+            for (int i = 0; i < NU; ++i) {
+                const int u = gt + i * (AT_PROD / 2);
+                const int row = u / UPR, cu = u - row * UPR;
+                ldg256(kb + (size_t)at_token(a, win, j * AT_KB + row) * a.ldk + (cu >> 2) * 32 + (cu & 3) * 8, v[i]);
             }
-            if (t < NKB) continue;
-            // ---- V block j, transposed: B operand rows = head dims, K = the block's 64 keys (2 sub-blocks of 32).
-            // lane = key within the sub-block: the 32 lanes of a warp write 32 consecutive halfs of one row (conflict-free)
-            {
-                const int sv = j & 1;
-                at_mbar_wait(V_EMPTY(sv), (uint32_t)(((j >> 1) & 1) ^ 1));
-                uint8_t* dstV = sV + sv * SM::V_STAGE;
-                const int pw = pt >> 5;                              // 0 .. 7
-                constexpr int NCOMBO = 2 * (DH / 8);                 // (key sub-block, group of 8 head dims)
-                float v[NCOMBO / 8][8];
+            at_mbar_wait(K_EMPTY(s), (uint32_t)(((t >> 1) & 1) ^ 1));
+            uint8_t* dstK = sK + s * SM::K_STAGE;
 #pragma unroll
-                for (int i = 0; i < NCOMBO / 8; ++i) {
-                    const int c = pw + i * 8, kbk = c / (DH / 8), dg = c - kbk * (DH / 8);
-                    ldg256(vb + (size_t)(j * AT_KB + kbk * 32 + lane) * a.ldv + dg * 8, v[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < NCOMBO / 8; ++i) {
-                    const int c = pw + i * 8, kbk = c / (DH / 8), dg = c - kbk * (DH / 8);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int row = dg * 8 + e;
-                        const __half h = __float2half_rn(v[i][e]);
-                        const __half l = __float2half_rn(v[i][e] - __half2float(h));
-                        uint8_t* rowp = dstV + kbk * (DH * 128) + row * 128;
-                        *reinterpret_cast<__half*>(rowp + ((((lane >> 3)) ^ (row & 7)) << 4) + (lane & 7) * 2) = h;
-                        *reinterpret_cast<__half*>(rowp + ((((lane >> 3) + 4) ^ (row & 7)) << 4) + (lane & 7) * 2) = l;
-                    }
-                }
-                at_fence_proxy_async();
-                at_mbar_arrive(V_FULL(sv));
+            for (int i = 0; i < NU; ++i) {
+                const int u = gt + i * (AT_PROD / 2);
+                const int row = u / UPR, cu = u - row * UPR, cb = cu >> 2, pl = cu & 3;
+                uint4 hi, lo;
+                at_split8(v[i], hi, lo);
+                uint8_t* dst = dstK + cb * (AT_KB * 128) + row * 128 + ((pl ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>((uintptr_t)dst ^ 64)) = lo;
             }
+            at_fence_proxy_async();
+            at_mbar_arrive(K_FULL(s));
+        };
+        // ---- V block j, transposed: B operand rows = head dims, K = the block's 64 keys (2 sub-blocks of 32).
+        // lane = key within the sub-block: the 32 lanes of a warp write 32 consecutive halfs of one row (conflict-free)
+        auto produce_V = [&](int j) {
+            const int sv = j & 1;
+            const int pw = gt >> 5;                                  // warp within the group: 0 .. 3
+            constexpr int NCOMBO = 2 * (DH / 8);                     // (key sub-block, group of 8 head dims)
+            constexpr int NC = NCOMBO / 4;                           // combos per warp (8 at DH = 128)
+            float v[NC][8];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int c = pw + i * 4, kbk = c / (DH / 8), dg = c - kbk * (DH / 8);
+                ldg256(vb + (size_t)at_token(a, win, j * AT_KB + kbk * 32 + lane) * a.ldv + dg * 8, v[i]);
+            }
+            at_mbar_wait(V_EMPTY(sv), (uint32_t)(((j >> 1) & 1) ^ 1));
+            uint8_t* dstV = sV + sv * SM::V_STAGE;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int c = pw + i * 4, kbk = c / (DH / 8), dg = c - kbk * (DH / 8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int row = dg * 8 + e;
+                    const __half h = __float2half_rn(v[i][e]);
+                    const __half l = __float2half_rn(v[i][e] - __half2float(h));
+                    uint8_t* rowp = dstV + kbk * (DH * 128) + row * 128;
+                    *reinterpret_cast<__half*>(rowp + ((((lane >> 3)) ^ (row & 7)) << 4) + (lane & 7) * 2) = h;
+                    *reinterpret_cast<__half*>(rowp + ((((lane >> 3) + 4) ^ (row & 7)) << 4) + (lane & 7) * 2) = l;
+                }
+            }
+            at_fence_proxy_async();
+            at_mbar_arrive(V_FULL(sv));
+        };
+        for (int t = grp; t < NKB; t += 2) produce_K(t);              // pass A: alternate stages (NKB is even or the tail is group 0's)
+        if (grp == 0) {
+            for (int t = NKB; t < 2 * NKB; ++t) produce_K(t);         // pass B: every K block
+        } else {
+            for (int j = 0; j < NKB; ++j) produce_V(j);               // pass B: every V block
         }
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
@@ -388,7 +414,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
         at_tc_fence_after();
         pdl_wait();                                                // (returns at once: the producers passed it long ago)
         const float inv = 1.0f / l;
-        float* ob = a.out + (size_t)z * a.o_bs + (size_t)(qt * 128 + row) * a.ldo;
+        float* ob = a.out + (size_t)img * a.o_bs + (size_t)at_token(a, win, qt * 128 + row) * a.ldo;
 #pragma unroll
         for (int c = 0; c < DH / 16; ++c) {
             uint32_t rr[16];
@@ -421,7 +447,7 @@ void attention_tc_configure_device() {
 
 void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int ldk, long long k_bs, const float* v, int ldv, long long v_bs,
                   float* out, int ldo, long long o_bs, int nb, int Lq, int Lk, int dh, float scale, const unsigned char* region, int n_win,
-                  cudaStream_t s) {
+                  cudaStream_t s, int win_side, int wsz, int map_w, int shift) {
     KEEP_CHECK(attention_tc_eligible(Lq, Lk, dh), "attention_tc: unsupported shape (Lq %d, Lk %d, dh %d)", Lq, Lk, dh);
     KEEP_CHECK(!region || (Lq == Lk && n_win > 0), "attention_tc: the region mask needs Lq == Lk");
     KEEP_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 && o_bs % 8 == 0 &&
@@ -434,6 +460,12 @@ void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int l
     a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs; a.o_bs = o_bs;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
     a.nb = nb; a.Lq = Lq; a.Lk = Lk; a.scale = scale; a.region = region; a.n_win = n_win > 0 ? n_win : 1;
+    a.win_side = win_side; a.wsz_log2 = 0; a.map_w = map_w; a.shift = shift;
+    if (win_side > 0) {
+        KEEP_CHECK(wsz > 0 && (wsz & (wsz - 1)) == 0 && (map_w & (map_w - 1)) == 0 && win_side * wsz == map_w && Lq == wsz * wsz && Lk == Lq &&
+                       nb % (win_side * win_side) == 0, "attention_tc: bad window geometry");
+        while ((1 << a.wsz_log2) < wsz) ++a.wsz_log2;
+    }
     launch_k(attn_tc_kernel<128>, dim3((unsigned)(nb * (Lq / 128))), dim3(AT_THREADS), (size_t)AttnSmem<128>::TOTAL, s, a);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -298,6 +298,19 @@ int keepop_attention_fused(const float* q, const float* k, const float* v, int n
     KEEP_API_END
 }
 
+int keepop_attention_window(const float* q, const float* k, const float* v, int nimg, int map_w, int wsz, int shift, int dh, float scale,
+                            const unsigned char* region_dev, float* out_dev, void* stream) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(wsz > 0 && map_w % wsz == 0, "keepop_attention_window: bad geometry");
+    const int side = map_w / wsz, L = wsz * wsz;
+    const long long img = (long long)map_w * map_w * dh;
+    attention_tc(q, dh, img, k, dh, img, v, dh, img, out_dev, dh, img, nimg * side * side, L, L, dh, scale, region_dev, side * side,
+                 (cudaStream_t)stream, side, wsz, map_w, shift);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+    KEEP_API_END
+}
+
 int keepop_attention(const float* q, const float* k, const float* v, int nb, int Lq, int Lk, int heads, int dh, float scale,
                      float* out_dev, void* stream) {
     KEEP_API_BEGIN

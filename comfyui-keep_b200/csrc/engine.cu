@@ -860,7 +860,10 @@ Tensor Engine::mha_tc(const float* q, const float* k, const float* v, int Lq, in
         launches_ += 3;
     }
     ar_->free(panels);
+    std::vector<std::string>* plan_saved = plan_;
+    plan_ = nullptr;                                                            // (the "attention" plan line above covers both contractions)
     Tensor Oh = gemm_nt_tc(S.f(), heads, Lq, Lk, v, dh, 1, inner, dh, 1.0f);   // (heads, Lq, dh); B[h] = V_h^T, a strided view
+    plan_ = plan_saved;
     tfree(S);
     Tensor O = talloc(1, Lq, 1, inner, F32);
     if (!ar_->dry()) { heads_to_tokens(Oh.f(), O.f(), heads, Lq, dh, s_); launches_ += 1; }
@@ -992,8 +995,25 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
         q = linear(src, p + ".q_proj"); kk = linear(tgt, p + ".k_proj"); v = linear(tgt, p + ".v_proj");
         qp = q.f(); kp = kk.f(); vp = v.f();
     }
-    Tensor qw = talloc(nimg * 4, L, 1, C, F32), kw = talloc(nimg * 4, L, 1, C, F32), vw = talloc(nimg * 4, L, 1, C, F32);
     const int sh = shift ? 16 : 0;
+    static const bool fused_attn = !(getenv("KEEP_FUSED_ATTN") && getenv("KEEP_FUSED_ATTN")[0] == '0');
+    Tensor O;
+    if ((flags_ & KEEP_FLAG_TCGEN05) && tc_passes_ == 3 && fused_attn && attention_tc_eligible(L, L, C)) {
+        // fused window attention (attn_tcgen05.cu): scores and probabilities stay in TMEM / shared memory; the window
+        // partition with its cyclic shift and the merge are index math inside the kernel (gmflow/transformer.py:78-103)
+        if (plan_) plan_->push_back("attention nb=" + std::to_string(nimg * 4) + " Lq=" + std::to_string(L) + " Lk=" + std::to_string(L) +
+                                    " heads=1 dh=" + std::to_string(C) + " kernel=tcgen05_fused");
+        O = talloc(nimg, H * Wd, 1, C, F32);
+        if (!ar_->dry()) {
+            attention_tc(qp, ldq, (long long)H * Wd * ldq, kp, ldkv, (long long)H * Wd * ldkv, vp, ldkv, (long long)H * Wd * ldkv, O.f(), C,
+                         (long long)H * Wd * C, nimg * 4, L, L, C, 1.0f / sqrtf((float)C), shift ? region8_ : nullptr, 4, s_, k, 32, Wd, sh);
+            launches_ += 1;
+        }
+        tfree(q);
+        if (kk.p) tfree(kk);
+        if (v.p) tfree(v);
+    } else {
+    Tensor qw = talloc(nimg * 4, L, 1, C, F32), kw = talloc(nimg * 4, L, 1, C, F32), vw = talloc(nimg * 4, L, 1, C, F32);
     if (!ar_->dry()) {
         window_partition(qp, qw.f(), nimg, H, Wd, C, k, sh, sh, ldq, s_);
         window_partition(kp, kw.f(), nimg, H, Wd, C, k, sh, sh, ldkv, s_);
@@ -1004,18 +1024,7 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
     if (kk.p) tfree(kk);
     if (v.p) tfree(v);
     Tensor S, Ow;
-    static const bool fused_attn = !(getenv("KEEP_FUSED_ATTN") && getenv("KEEP_FUSED_ATTN")[0] == '0');
-    if ((flags_ & KEEP_FLAG_TCGEN05) && tc_passes_ == 3 && fused_attn && attention_tc_eligible(L, L, C)) {
-        // fused window attention (attn_tcgen05.cu): scores and probabilities stay in TMEM / shared memory
-        if (plan_) plan_->push_back("attention nb=" + std::to_string(nimg * 4) + " Lq=" + std::to_string(L) + " Lk=" + std::to_string(L) +
-                                    " heads=1 dh=" + std::to_string(C) + " kernel=tcgen05_fused");
-        Ow = talloc(nimg * 4, L, 1, C, F32);
-        if (!ar_->dry()) {
-            attention_tc(qw.f(), C, (long long)L * C, kw.f(), C, (long long)L * C, vw.f(), C, (long long)L * C, Ow.f(), C, (long long)L * C,
-                         nimg * 4, L, L, C, 1.0f / sqrtf((float)C), shift ? region8_ : nullptr, 4, s_);
-            launches_ += 1;
-        }
-    } else if (flags_ & KEEP_FLAG_TCGEN05) {
+    if (flags_ & KEEP_FLAG_TCGEN05) {
         // window attention on the tensor cores: S = (Q K^T)/sqrt(C), softmax (+ shift mask), O = P V
         S = gemm_nt_tc(qw.f(), nimg * 4, L, C, kw.f(), (long long)L * C, C, 1, L, 1.0f / sqrtf((float)C));
         if (!ar_->dry()) {
@@ -1043,11 +1052,11 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
             launches_ += 3;
         }
     }
-    if (S.p) tfree(S);
-    tfree(qw); tfree(kw); tfree(vw);
-    Tensor O = talloc(nimg, H * Wd, 1, C, F32);
+    tfree(S); tfree(qw); tfree(kw); tfree(vw);
+    O = talloc(nimg, H * Wd, 1, C, F32);
     if (!ar_->dry()) { window_merge(Ow.f(), O.f(), nimg, H, Wd, C, k, sh, sh, s_); launches_ += 1; }
     tfree(Ow);
+    }
     Tensor m = linear(O, p + ".merge");
     tfree(O);
     Tensor out;

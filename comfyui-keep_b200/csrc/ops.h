@@ -73,7 +73,9 @@ bool attention_tc_eligible(int Lq, int Lk, int dh);
 void attention_tc_configure_device();
 void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int ldk, long long k_bs, const float* v, int ldv, long long v_bs,
                   float* out, int ldo, long long o_bs, int nb, int Lq, int Lk, int dh, float scale, const unsigned char* region, int n_win,
-                  cudaStream_t s);
+                  cudaStream_t s, int win_side = 0, int wsz = 0, int map_w = 0, int shift = 0);
+// (win_side > 0: swin window mode -- q / k / v / out are whole (map_w x map_w)-token maps, *_bs = image strides, nb = images *
+//  win_side^2, window partition + cyclic shift + merge are index math inside the kernel; wsz = window side, Lq = Lk = wsz^2)
 
 // ------------------------------------------------------------------------------------------
 // normalisation

@@ -154,6 +154,12 @@ int keepop_attention(const float* q_dev, const float* k_dev, const float* v_dev,
  * Lq % 128 == 0, Lk % 64 == 0, Lk <= 1024.  Replaces softmax(q @ k^T * scale + mask) @ v (gmflow/transformer.py:8-16,78-98). */
 int keepop_attention_fused(const float* q_dev, const float* k_dev, const float* v_dev, int nb, int Lq, int Lk, int dh, float scale,
                            const unsigned char* region_dev, int n_win, float* out_dev, void* stream);
+/* the same kernel in swin-window mode: q / k / v / out are whole (nimg, map_w * map_w, dh) token maps; the partition into
+ * (map_w / wsz)^2 windows of wsz x wsz tokens, the cyclic shift (torch.roll by -shift on both axes before, +shift after) and
+ * the merge are index math inside the kernel; region_dev: ((map_w / wsz)^2, wsz^2) uint8 region ids when shift > 0, else
+ * NULL.  Replaces split_feature + roll + attention + merge_splits + roll of gmflow/transformer.py:78-103. */
+int keepop_attention_window(const float* q_dev, const float* k_dev, const float* v_dev, int nimg, int map_w, int wsz, int shift, int dh,
+                            float scale, const unsigned char* region_dev, float* out_dev, void* stream);
 int keepop_flow_warp(const float* img_dev, const float* flow_dev, float* out_dev, int n, int h, int w, int c, void* stream);
 int keepop_convex_upsample8(const float* mask_dev, const float* flow_dev, float* out_dev, int n, int h, int w, void* stream);
 int keepop_window_sine_pos(float* x_dev, int n, int h, int w, int c, int splits, void* stream);

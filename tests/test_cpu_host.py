@@ -257,7 +257,10 @@ def test_plan_per_frame_chain_and_kernel_choice(keep_mod, lib, state_dict, tmp_p
             assert f["wide"] == "0", l                              # general config: fp16 pairs everywhere
     lf, kf = _plan(keep_mod, lib, state_dict, 1, 2, 0, tmp_path)
     # fp32 engine mode: same programme on CUDA-core kernels (its batched attention GEMMs are not traced as "gemm" lines)
-    assert {k: v for k, v in k2.items() if k != "gemm"} == dict(kf) and not any("tcgen05" in l for l in lf)
+    # (tc3 also traces GMFlow's 12 window attentions per chunk of pairs: they run on the fused tcgen05 attention kernel there)
+    fused = [l for l in l2 if l.startswith("attention") and "kernel=tcgen05_fused" in l]
+    assert len(fused) == 12 and all("Lq=1024 Lk=1024 heads=1 dh=128" in l for l in fused)
+    assert {k: v - (12 if k == "attention" else 0) for k, v in k2.items() if k != "gemm"} == dict(kf) and not any("tcgen05" in l for l in lf)
 
 
 def test_plan_lockstep_shares_the_chain_and_asian_adds_a_cft(keep_mod, lib, state_dict, state_dict_asian, tmp_path):

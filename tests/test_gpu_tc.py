@@ -275,3 +275,35 @@ def test_fused_attention_matches_torch(lib, nb, Lq, Lk, masked):
     want = torch.softmax(s, -1) @ v
     err = float((out - want).abs().max())
     assert bool(torch.isfinite(out).all()) and err < 5e-5, "max abs err %g" % err
+
+
+@pytest.mark.parametrize("shift", [0, 16])
+def test_fused_window_attention_matches_torch(lib, shift):
+    """GMFlow's swin attention block (gmflow/transformer.py:78-103) with the partition / cyclic shift / merge done as index
+    math inside the fused kernel: roll(-shift) -> split into 2x2 windows of 32x32 tokens -> masked attention -> merge ->
+    roll(+shift), restated with torch ops."""
+    from test_gpu_ops import _p, _rc
+    nimg, W, wsz, dh = 3, 64, 32, 128
+    g = torch.Generator(device="cpu").manual_seed(29 + shift)
+    q, k, v = ((torch.randn((nimg, W * W, dh), generator=g) * (1.3 if i < 2 else 1.0)).cuda() for i in range(3))
+    scale = dh ** -0.5
+    reg = _swin_regions().cuda() if shift else None
+    out = torch.full((nimg, W * W, dh), float("nan"), device="cuda")
+    _rc(lib, lib.keepop_attention_window(_p(q), _p(k), _p(v), nimg, W, wsz, shift, dh, scale, _p(reg), _p(out), None))
+
+    def part(t):      # (nimg, W*W, dh) -> (nimg*4, wsz*wsz, dh), after the cyclic shift
+        t = t.reshape(nimg, W, W, dh)
+        if shift:
+            t = torch.roll(t, shifts=(-shift, -shift), dims=(1, 2))
+        t = t.reshape(nimg, 2, wsz, 2, wsz, dh).permute(0, 1, 3, 2, 4, 5)
+        return t.reshape(nimg * 4, wsz * wsz, dh)
+    s = part(q) @ part(k).transpose(-1, -2) * scale
+    if shift:
+        r = reg.long()[torch.arange(nimg * 4) % 4]
+        s = s + torch.where(r[:, :, None] != r[:, None, :], torch.tensor(-100.0, device="cuda"), torch.tensor(0.0, device="cuda"))
+    o = torch.softmax(s, -1) @ part(v)
+    o = o.reshape(nimg, 2, 2, wsz, wsz, dh).permute(0, 1, 3, 2, 4, 5).reshape(nimg, W, W, dh)
+    if shift:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    err = float((out - o.reshape(nimg, W * W, dh)).abs().max())
+    assert bool(torch.isfinite(out).all()) and err < 5e-5, "max abs err %g" % err
