@@ -96,6 +96,8 @@ struct AttnTcArgs {
     //   ((wy * wsz + r / wsz + shift) mod map_w) * map_w + (wx * wsz + r mod wsz + shift) mod map_w
     // i.e. the window partition (with its cyclic shift, gmflow/transformer.py:78-98) and the merge are index math here
     int win_side, wsz_log2, map_w, shift;
+    // multi-head mode (heads > 1, plain rows only): batch z = b * heads + h, head h = columns [h * dh, (h + 1) * dh) of the rows
+    int heads;
 };
 
 // window row -> token index (plain mode: identity)
@@ -168,7 +170,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
     const int z = blockIdx.x / qtiles, qt = blockIdx.x - z * qtiles;
     const int NKB = a.Lk / AT_KB;
     const int nwin = a.win_side > 0 ? a.win_side * a.win_side : 1;
-    const int img = a.win_side > 0 ? z / nwin : z, win = a.win_side > 0 ? z - img * nwin : 0;   // tensor batch index / window
+    const int img = a.win_side > 0 ? z / nwin : (a.heads > 1 ? z / a.heads : z);              // tensor batch index
+    const int win = a.win_side > 0 ? z - img * nwin : 0;                                      // window within the image
+    const int hoff = a.heads > 1 ? (z - img * a.heads) * DH : 0;                               // column offset of this head
 
     if (threadIdx.x == 0) {
         at_mbar_init(Q_FULL, AT_PROD);
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
         if (pt == 0) keep_stamp_here();
         // ---- Q tile (scaled): 128 rows x DH channels, unit = 8 channels (all 256 threads)
         {
-            const float* qb = a.q + (size_t)img * a.q_bs;
+            const float* qb = a.q + (size_t)img * a.q_bs + hoff;
             constexpr int UPR = NCB * 4;              // units per row
 #pragma unroll 2
             for (int u = pt; u < 128 * UPR; u += AT_PROD) {
@@ -217,8 +221,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             at_fence_proxy_async();
             at_mbar_arrive(Q_FULL);
         }
-        const float* kb = a.k + (size_t)img * a.k_bs;
-        const float* vb = a.v + (size_t)img * a.v_bs;
+        const float* kb = a.k + (size_t)img * a.k_bs + hoff;
+        const float* vb = a.v + (size_t)img * a.v_bs + hoff;
         // ---- K block j into stage buffer t & 1 (rows = keys), by the 128 threads of one group
         auto produce_K = [&](int t) {
             const int j = t < NKB ? t : t - NKB, s = t & 1;
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
         at_tc_fence_after();
         pdl_wait();                                                // (returns at once: the producers passed it long ago)
         const float inv = 1.0f / l;
-        float* ob = a.out + (size_t)img * a.o_bs + (size_t)at_token(a, win, qt * 128 + row) * a.ldo;
+        float* ob = a.out + (size_t)img * a.o_bs + (size_t)at_token(a, win, qt * 128 + row) * a.ldo + hoff;
 #pragma unroll
         for (int c = 0; c < DH / 16; ++c) {
             uint32_t rr[16];
@@ -437,17 +441,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
 
 }  // namespace
 
-bool attention_tc_eligible(int Lq, int Lk, int dh) { return dh == 128 && Lq % 128 == 0 && Lk % AT_KB == 0 && Lk <= 1024 && Lq > 0 && Lk > 0; }
+bool attention_tc_eligible(int Lq, int Lk, int dh) { return (dh == 128 || dh == 64) && Lq % 128 == 0 && Lk % AT_KB == 0 && Lk <= 1024 && Lq > 0 && Lk > 0; }
 
 void attention_tc_configure_device() {
     static unsigned long long configured = 0;
-    if (first_use_on_current_device(&configured))
+    if (first_use_on_current_device(&configured)) {
         CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<128>::TOTAL));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::TOTAL));
+    }
 }
 
 void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int ldk, long long k_bs, const float* v, int ldv, long long v_bs,
                   float* out, int ldo, long long o_bs, int nb, int Lq, int Lk, int dh, float scale, const unsigned char* region, int n_win,
-                  cudaStream_t s, int win_side, int wsz, int map_w, int shift) {
+                  cudaStream_t s, int win_side, int wsz, int map_w, int shift, int heads) {
     KEEP_CHECK(attention_tc_eligible(Lq, Lk, dh), "attention_tc: unsupported shape (Lq %d, Lk %d, dh %d)", Lq, Lk, dh);
     KEEP_CHECK(!region || (Lq == Lk && n_win > 0), "attention_tc: the region mask needs Lq == Lk");
     KEEP_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 && o_bs % 8 == 0 &&
@@ -460,13 +466,15 @@ void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int l
     a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs; a.o_bs = o_bs;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
     a.nb = nb; a.Lq = Lq; a.Lk = Lk; a.scale = scale; a.region = region; a.n_win = n_win > 0 ? n_win : 1;
-    a.win_side = win_side; a.wsz_log2 = 0; a.map_w = map_w; a.shift = shift;
+    a.win_side = win_side; a.wsz_log2 = 0; a.map_w = map_w; a.shift = shift; a.heads = heads > 1 ? heads : 1;
+    KEEP_CHECK(a.heads == 1 || (win_side == 0 && nb % a.heads == 0), "attention_tc: multi-head mode needs plain rows and nb = batches * heads");
     if (win_side > 0) {
         KEEP_CHECK(wsz > 0 && (wsz & (wsz - 1)) == 0 && (map_w & (map_w - 1)) == 0 && win_side * wsz == map_w && Lq == wsz * wsz && Lk == Lq &&
                        nb % (win_side * win_side) == 0, "attention_tc: bad window geometry");
         while ((1 << a.wsz_log2) < wsz) ++a.wsz_log2;
     }
-    launch_k(attn_tc_kernel<128>, dim3((unsigned)(nb * (Lq / 128))), dim3(AT_THREADS), (size_t)AttnSmem<128>::TOTAL, s, a);
+    if (dh == 128) launch_k(attn_tc_kernel<128>, dim3((unsigned)(nb * (Lq / 128))), dim3(AT_THREADS), (size_t)AttnSmem<128>::TOTAL, s, a);
+    else launch_k(attn_tc_kernel<64>, dim3((unsigned)(nb * (Lq / 128))), dim3(AT_THREADS), (size_t)AttnSmem<64>::TOTAL, s, a);
     CUDA_CHECK(cudaGetLastError());
 }
 

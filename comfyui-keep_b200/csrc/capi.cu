@@ -298,6 +298,17 @@ int keepop_attention_fused(const float* q, const float* k, const float* v, int n
     KEEP_API_END
 }
 
+int keepop_attention_fused_heads(const float* q, const float* k, const float* v, int nb, int Lq, int Lk, int heads, int dh, float scale,
+                                 float* out_dev, void* stream) {
+    KEEP_API_BEGIN
+    const int D = heads * dh;
+    attention_tc(q, D, (long long)Lq * D, k, D, (long long)Lk * D, v, D, (long long)Lk * D, out_dev, D, (long long)Lq * D, nb * heads, Lq, Lk, dh, scale,
+                 nullptr, 1, (cudaStream_t)stream, 0, 0, 0, 0, heads);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+    KEEP_API_END
+}
+
 int keepop_attention_window(const float* q, const float* k, const float* v, int nimg, int map_w, int wsz, int shift, int dh, float scale,
                             const unsigned char* region_dev, float* out_dev, void* stream) {
     KEEP_API_BEGIN

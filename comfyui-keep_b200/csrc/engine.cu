@@ -1308,8 +1308,22 @@ Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
         Tensor qk = linear(qk_in, p + ".self_attn.in_proj_qk");
         Tensor v = linear(tn, p + ".self_attn.in_proj_v");
         tfree(qk_in); tfree(tn);
-        Tensor o = mha(qk.f(), 2 * E, (long long)L * 2 * E, qk.f() + E, 2 * E, (long long)L * 2 * E, v.f(), E, (long long)L * E, nbt, L, L,
-                       heads, dh, 1.0f / sqrtf((float)dh));
+        // nn.MultiheadAttention 8 x 64 over 256 tokens (keep_arch.py:431-432): the fused tcgen05 attention kernel, heads as batch
+        static const bool fused_mha = !(getenv("KEEP_FUSED_MHA") && getenv("KEEP_FUSED_MHA")[0] == '0');
+        Tensor o;
+        if ((flags_ & KEEP_FLAG_TCGEN05) && tc_passes_ == 3 && fused_mha && attention_tc_eligible(L, L, dh)) {
+            if (plan_) plan_->push_back("attention nb=" + std::to_string(nbt) + " Lq=" + std::to_string(L) + " Lk=" + std::to_string(L) +
+                                        " heads=" + std::to_string(heads) + " dh=" + std::to_string(dh) + " kernel=tcgen05_fused");
+            o = talloc(nbt, L, 1, E, F32);
+            if (!ar_->dry()) {
+                attention_tc(qk.f(), 2 * E, (long long)L * 2 * E, qk.f() + E, 2 * E, (long long)L * 2 * E, v.f(), E, (long long)L * E, o.f(), E,
+                             (long long)L * E, nbt * heads, L, L, dh, 1.0f / sqrtf((float)dh), nullptr, 1, s_, 0, 0, 0, 0, heads);
+                launches_ += 1;
+            }
+        } else {
+            o = mha(qk.f(), 2 * E, (long long)L * 2 * E, qk.f() + E, 2 * E, (long long)L * 2 * E, v.f(), E, (long long)L * E, nbt, L, L,
+                    heads, dh, 1.0f / sqrtf((float)dh));
+        }
         tfree(qk); tfree(v);
         Tensor t1 = linear(o, p + ".self_attn.out_proj", ACT_NONE, &t);
         tfree(o); tfree(t);

@@ -67,13 +67,14 @@ void bgemm_simt(const BGemmArgs& a, cudaStream_t s);
 // fused attention on tcgen05 (attn_tcgen05.cu): out[z] = softmax(q[z] k[z]^T * scale (+ region mask)) v[z], scores never in HBM.
 //   q (Lq, dh), k / v (Lk, dh), out (Lq, dh) fp32 row-major with row strides ld* and batch strides *_bs (elements);
 //   region: [n_win][Lk] uint8 region ids (shifted swin windows: -100 where region[q] != region[k]; batch z uses row z % n_win)
-//   or null.  Supported: dh = 128, Lq % 128 == 0, Lk % 64 == 0, Lk <= 1024 (attention_tc_eligible).
+//   or null.  Supported: dh = 128 or 64, Lq % 128 == 0, Lk % 64 == 0, Lk <= 1024 (attention_tc_eligible).
 // ------------------------------------------------------------------------------------------
 bool attention_tc_eligible(int Lq, int Lk, int dh);
 void attention_tc_configure_device();
 void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int ldk, long long k_bs, const float* v, int ldv, long long v_bs,
                   float* out, int ldo, long long o_bs, int nb, int Lq, int Lk, int dh, float scale, const unsigned char* region, int n_win,
-                  cudaStream_t s, int win_side = 0, int wsz = 0, int map_w = 0, int shift = 0);
+                  cudaStream_t s, int win_side = 0, int wsz = 0, int map_w = 0, int shift = 0, int heads = 1);
+// (heads > 1: nb = batches * heads, head h of batch b reads / writes columns [h * dh, (h + 1) * dh) of batch b's rows)
 // (win_side > 0: swin window mode -- q / k / v / out are whole (map_w x map_w)-token maps, *_bs = image strides, nb = images *
 //  win_side^2, window partition + cyclic shift + merge are index math inside the kernel; wsz = window side, Lq = Lk = wsz^2)
 

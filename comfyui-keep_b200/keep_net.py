@@ -96,6 +96,7 @@ def load_library():
     lib.keepop_layernorm.argtypes = [vp, ci, ci, vp, vp, cf, vp, vp]
     lib.keepop_attention.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp]
     lib.keepop_attention_fused.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, vp, ci, vp, vp]
+    lib.keepop_attention_fused_heads.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp]
     lib.keepop_attention_window.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp]
     lib.keepop_flow_warp.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
     lib.keepop_convex_upsample8.argtypes = [vp, vp, vp, ci, ci, ci, vp]

@@ -154,6 +154,9 @@ int keepop_attention(const float* q_dev, const float* k_dev, const float* v_dev,
  * Lq % 128 == 0, Lk % 64 == 0, Lk <= 1024.  Replaces softmax(q @ k^T * scale + mask) @ v (gmflow/transformer.py:8-16,78-98). */
 int keepop_attention_fused(const float* q_dev, const float* k_dev, const float* v_dev, int nb, int Lq, int Lk, int dh, float scale,
                            const unsigned char* region_dev, int n_win, float* out_dev, void* stream);
+/* the same kernel in multi-head mode, operands packed like keepop_attention: (nb * L, heads * dh) fp32, dh = 64 or 128 */
+int keepop_attention_fused_heads(const float* q_dev, const float* k_dev, const float* v_dev, int nb, int Lq, int Lk, int heads, int dh,
+                                 float scale, float* out_dev, void* stream);
 /* the same kernel in swin-window mode: q / k / v / out are whole (nimg, map_w * map_w, dh) token maps; the partition into
  * (map_w / wsz)^2 windows of wsz x wsz tokens, the cyclic shift (torch.roll by -shift on both axes before, +shift after) and
  * the merge are index math inside the kernel; region_dev: ((map_w / wsz)^2, wsz^2) uint8 region ids when shift > 0, else

@@ -259,7 +259,9 @@ def test_plan_per_frame_chain_and_kernel_choice(keep_mod, lib, state_dict, tmp_p
     # fp32 engine mode: same programme on CUDA-core kernels (its batched attention GEMMs are not traced as "gemm" lines)
     # (tc3 also traces GMFlow's 12 window attentions per chunk of pairs: they run on the fused tcgen05 attention kernel there)
     fused = [l for l in l2 if l.startswith("attention") and "kernel=tcgen05_fused" in l]
-    assert len(fused) == 12 and all("Lq=1024 Lk=1024 heads=1 dh=128" in l for l in fused)
+    gm = [l for l in fused if "Lq=1024 Lk=1024 heads=1 dh=128" in l]
+    ft = [l for l in fused if "Lq=256 Lk=256 heads=8 dh=64" in l]          # code transformer: 9 layers per frame, same kernel
+    assert len(gm) == 12 and len(ft) == 2 * 9 and len(fused) == len(gm) + len(ft)
     assert {k: v - (12 if k == "attention" else 0) for k, v in k2.items() if k != "gemm"} == dict(kf) and not any("tcgen05" in l for l in lf)
 
 

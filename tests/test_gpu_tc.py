@@ -307,3 +307,19 @@ def test_fused_window_attention_matches_torch(lib, shift):
         o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
     err = float((out - o.reshape(nimg, W * W, dh)).abs().max())
     assert bool(torch.isfinite(out).all()) and err < 5e-5, "max abs err %g" % err
+
+
+@pytest.mark.parametrize("nb,L,heads,dh", [(1, 256, 8, 64), (3, 256, 8, 64), (2, 128, 2, 128)])
+def test_fused_multihead_attention_matches_torch(lib, nb, L, heads, dh):
+    """nn.MultiheadAttention's core on packed (tokens, heads * dh) operands (keep_arch.py:431-432: 8 x 64 over 256 tokens)."""
+    from test_gpu_ops import _p, _rc
+    g = torch.Generator(device="cpu").manual_seed(31)
+    D = heads * dh
+    q, k, v = (torch.randn((nb, L, D), generator=g).cuda() for _ in range(3))
+    scale = dh ** -0.5
+    out = torch.full((nb, L, D), float("nan"), device="cuda")
+    _rc(lib, lib.keepop_attention_fused_heads(_p(q), _p(k), _p(v), nb, L, L, heads, dh, scale, _p(out), None))
+    qh, kh, vh = (t.reshape(nb, L, heads, dh).transpose(1, 2) for t in (q, k, v))
+    want = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(nb, L, D)
+    err = float((out - want).abs().max())
+    assert bool(torch.isfinite(out).all()) and err < 2e-5, "max abs err %g" % err
