@@ -294,14 +294,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
         constexpr uint32_t lo0 = 1u << 16;
         const uint32_t idesc_s = (1u << 4) | ((uint32_t)(AT_KB >> 3) << 17) | ((128u >> 4) << 24);   // M 128, N 64, f16 x f16 -> f32
         const uint32_t idesc_o = (1u << 4) | ((uint32_t)(DH >> 3) << 17) | ((128u >> 4) << 24);      // M 128, N DH
-        auto issue = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+        auto issue = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc, bool hi_only) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {                       // two K steps of 16 per 32-wide block; lo half 64 B further
                 const uint64_t ad = ((uint64_t)hi_desc << 32) | (a_lo + k * 2u);
                 const uint64_t bd = ((uint64_t)hi_desc << 32) | (b_lo + k * 2u);
-                at_umma(d_tmem, ad + 4u, bd, idesc, k == 0 ? acc : 1u);
-                at_umma(d_tmem, ad, bd + 4u, idesc, 1u);
-                at_umma(d_tmem, ad, bd, idesc, 1u);
+                if (hi_only) {
+                    at_umma(d_tmem, ad, bd, idesc, k == 0 ? acc : 1u);
+                } else {
+                    at_umma(d_tmem, ad + 4u, bd, idesc, k == 0 ? acc : 1u);
+                    at_umma(d_tmem, ad, bd + 4u, idesc, 1u);
+                    at_umma(d_tmem, ad, bd, idesc, 1u);
+                }
             }
         };
         const uint32_t q_base = lo0 | (at_smem_u32(sQ) >> 4);
@@ -313,9 +317,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             if (leader) {
                 const uint32_t k_base = lo0 | (at_smem_u32(sK + s * SM::K_STAGE) >> 4);
 #pragma unroll
+                // pass A only feeds the row maximum -- a stabiliser, any value near the true maximum gives the same softmax --, so
+                // one MMA per K step (hi x hi, ~1e-3 relative) instead of three
                 for (int cb = 0; cb < NCB; ++cb)
                     issue(tmem_base + (uint32_t)(s * AT_KB), q_base + (uint32_t)((cb * 128 * 128) >> 4), k_base + (uint32_t)((cb * AT_KB * 128) >> 4),
-                          idesc_s, cb ? 1u : 0u);
+                          idesc_s, cb ? 1u : 0u, t < NKB);
                 at_commit(K_EMPTY(s));
                 at_commit(S_FULL(s));
             }
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
 #pragma unroll
                 for (int kbk = 0; kbk < 2; ++kbk)
                     issue(tmem_base + 128u, p_base + (uint32_t)((kbk * 128 * 128) >> 4), v_base + (uint32_t)((kbk * DH * 128) >> 4), idesc_o,
-                          (j | kbk) ? 1u : 0u);
+                          (j | kbk) ? 1u : 0u, false);
                 at_commit(P_EMPTY);
                 at_commit(V_EMPTY(sv));
                 if (j == NKB - 1) at_commit(O_FULL);
@@ -382,8 +388,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
         for (int j = 0; j < NKB; ++j) {
             const int t = NKB + j, s = t & 1;
             at_mbar_wait(S_FULL(s), (uint32_t)((t >> 1) & 1));
-            at_mbar_wait(P_EMPTY, (uint32_t)((j & 1) ^ 1));
             at_tc_fence_after();
+            // the whole block's probabilities are formed in registers first: reading S and the exponentials of block j overlap the
+            // P V MMAs of block j-1, which still read the (single) P buffer
+            uint4 ph[AT_KB / 8], pl[AT_KB / 8];
 #pragma unroll
             for (int c = 0; c < AT_KB / 16; ++c) {
                 uint32_t rr[16];
@@ -397,21 +405,24 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
                     p[e] = exp2f(fmaf(sc, 1.4426950408889634f, -m2));
                     l += p[e];
                 }
-                uint4 h0, l0, h1, l1;
-                at_split8(p, h0, l0);
-                at_split8(p + 8, h1, l1);
+                at_split8(p, ph[2 * c], pl[2 * c]);
+                at_split8(p + 8, ph[2 * c + 1], pl[2 * c + 1]);
+            }
+            at_tc_fence_before();
+            at_mbar_arrive(S_EMPTY(s));                            // S buffer free: the MMA warp may issue the scores of block j+2
+            at_mbar_wait(P_EMPTY, (uint32_t)((j & 1) ^ 1));
+#pragma unroll
+            for (int c = 0; c < AT_KB / 16; ++c) {
                 // keys c*16 .. c*16+15 of the block: sub-block c / 2, 16-byte chunks (c & 1) * 2 + {0, 1}; lo halves 4 chunks on
                 uint8_t* rowp = sP + (c >> 1) * (128 * 128) + row * 128;
                 const int ch = (c & 1) * 2;
-                *reinterpret_cast<uint4*>(rowp + (((ch) ^ (row & 7)) << 4)) = h0;
-                *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (row & 7)) << 4)) = h1;
-                *reinterpret_cast<uint4*>(rowp + (((ch + 4) ^ (row & 7)) << 4)) = l0;
-                *reinterpret_cast<uint4*>(rowp + (((ch + 5) ^ (row & 7)) << 4)) = l1;
+                *reinterpret_cast<uint4*>(rowp + (((ch) ^ (row & 7)) << 4)) = ph[2 * c];
+                *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (row & 7)) << 4)) = ph[2 * c + 1];
+                *reinterpret_cast<uint4*>(rowp + (((ch + 4) ^ (row & 7)) << 4)) = pl[2 * c];
+                *reinterpret_cast<uint4*>(rowp + (((ch + 5) ^ (row & 7)) << 4)) = pl[2 * c + 1];
             }
             at_fence_proxy_async();
             at_mbar_arrive(P_FULL);
-            at_tc_fence_before();
-            at_mbar_arrive(S_EMPTY(s));
         }
         // ---- epilogue: O / l -> global (token-major rows of DH floats)
         at_mbar_wait(O_FULL, 0);
