@@ -497,11 +497,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         const bool leader = elect_one();
         const uint32_t b_step = (uint32_t)b_stage_bytes >> 4;
         const uint32_t b_base = lo0 | (smem_u32(sB) >> 4);
+        // stacked panels (split precision, 64-wide N tile): B = [Wh ; Wl] as 128 rows of 64 bytes, SWIZZLE_64B (layout type 4),
+        // 8-row groups 512 bytes apart.  Per K step: D[:, 0:128] += Ah * [Wh ; Wl]^T (N = 128), D[:, 0:64] += Al * Wh^T (N = 64);
+        // the epilogue adds columns j and 64 + j.  Two A fetches instead of three on the operand-fetch-bound N = 64 layers.
+        const bool stacked = KEEP_TC_STACKED && PASSES == 3 && a.bn == 64;
+        constexpr uint32_t b_hi_st = ((512u >> 4) & 0x3FFF) | (1u << 14) | (4u << 29);
+        const uint32_t idesc_n128 = (idesc & ~(0x3Fu << 17)) | ((128u >> 3) << 17);
         // the MMAs of one (channel block, tap): K-steps x {lo*hi, hi*lo, hi*hi}
         auto issue_tap = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k) {
                 const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + k * kstep);
+                if (PASSES == 3 && stacked) {
+                    const uint64_t bd = ((uint64_t)b_hi_st << 32) | (b_lo + k * kstep);
+                    umma_f16(d_tmem, ad, bd, idesc_n128, k == 0 ? acc : 1u);
+                    umma_f16(d_tmem, ad + lo_off, bd, idesc, 1u);
+                    continue;
+                }
                 const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + k * kstep);
                 if (PASSES == 3) {   // small cross terms first, then the leading term
                     umma_f16(d_tmem, ad + lo_off, bd, idesc, k == 0 ? acc : 1u);
@@ -512,6 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 }
             }
         };
+        const int acc_cols = stacked ? 128 : a.bn;        // TMEM columns per accumulator buffer
         int sa = 0, pa = 0, as = 0, pacc = 0, trace_m = 0;
         if (a.w_resident && WIN != 2) {
             // ---- weights resident: one wait per activation stage, then TAPS x KSTEPS x PASSES back-to-back MMAs
@@ -521,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 mbar_wait(ACC_EMPTY(as), pacc ^ 1);
                 tc_fence_after();
                 if (lane == 0) TC_TRACE(3, trace_m);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_cols);
                 uint32_t b_cur = b_base;                                       // panels [cb][tap]; one N tile, no K split
                 for (int cb = 0; cb < a.ncb; ++cb) {
                     mbar_wait(A_FULL(sa), pa);
@@ -558,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     mbar_wait(ACC_EMPTY(as), pacc ^ 1);
                     tc_fence_after();
                     if (lane == 0) TC_TRACE(3, trace_m);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.bn);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_cols);
                     uint32_t acc = 0;
                     for (int cb = cb0; cb < cb1; ++cb) {
                         mbar_wait(A_FULL(sa), pa);     // (returns at once when an earlier N tile already saw this phase)
@@ -635,7 +648,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
             tc_fence_after();
             if (!waited) { pdl_wait(); waited = true; }   // residual reads / output writes below (returns at once: the producers passed it)
             if (threadIdx.x == 0) TC_TRACE(6, trace_e);
-            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * a.bn);
+            const bool stacked = KEEP_TC_STACKED && PASSES == 3 && a.bn == 64;   // accumulator = [Ah*Wh + Al*Wh | Ah*Wl]: add columns j and 64 + j
+            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * (stacked ? 128 : a.bn));
             const bool partial_out = a.splitk > 1;
             if (a.cluster_k) {
                 // cluster split-K: park this CTA's fp32 partial tile in its (now idle) activation stages, row = pixel,
@@ -648,6 +662,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     __syncwarp();
                     tmem_ld16(t0 + (uint32_t)j, rr);
                     tmem_ld_wait();
+                    if (stacked) {
+                        uint32_t r2[16];
+                        tmem_ld16(t0 + 64u + (uint32_t)j, r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) rr[e] = __float_as_uint(__uint_as_float(rr[e]) + __uint_as_float(r2[e]));
+                    }
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         *reinterpret_cast<uint4*>(dstrow + ((((j >> 2) + e) ^ (row & 7)) << 4)) = make_uint4(rr[4 * e], rr[4 * e + 1], rr[4 * e + 2], rr[4 * e + 3]);
@@ -678,6 +699,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     }
                 }
                 tmem_ld_wait();
+                if (stacked) {   // (warp-uniform) second half of the accumulator: the Ah * Wl term
+                    uint32_t r2[16];
+                    tmem_ld16(t0 + 64u + (uint32_t)j, r2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) rr[e] = __float_as_uint(__uint_as_float(rr[e]) + __uint_as_float(r2[e]));
+                }
 #ifdef KEEP_TC_EPI_TRACE
                 if (threadIdx.x == 0 && trace_e == 0) TC_TRACE(8, j >> 4);
 #endif
@@ -898,10 +926,28 @@ size_t tc_packed_weight_halfs(int cin, int cout, int taps, int bn, int passes) {
 // position `idx` (halfs) inside a packed panel set -> (n tile, channel block, tap, row, logical channel k within the block,
 // hi/lo part); the 16-byte chunk j of a row is stored at chunk position j ^ (row & 7)   (SWIZZLE_128B, K-major)
 struct PanelPos { int nt, cb, tap, row, k, part; };
+// Split-precision layers with a 64-wide N tile use the STACKED panel instead: 128 rows of 64 bytes -- rows 0-63 the hi parts
+// (32 channels), rows 64-127 the lo parts -- in the SWIZZLE_64B K-major layout (16-byte chunk j of row r at chunk
+// j ^ ((r >> 1) & 3)).  One N = 128 MMA then forms Ah*Wh and Ah*Wl side by side and one N = 64 MMA adds Al*Wh: two A-operand
+// fetches per K step instead of three (the N = 64 MMAs are bound by shared-memory operand fetch, profiles/r1_ubench_umma_rate.md).
+#ifndef KEEP_TC_STACKED
+#define KEEP_TC_STACKED 1
+#endif
+__host__ __device__ inline bool tc_stacked(int bn, int passes) { return KEEP_TC_STACKED && passes == 3 && bn == 64; }
 __host__ __device__ inline PanelPos panel_pos(size_t idx, int bn, int taps, int ncb, int passes) {
     PanelPos q;
     size_t r = idx;
     const int e = (int)(r % 8); r /= 8;
+    if (tc_stacked(bn, passes)) {
+        const int chunk = (int)(r % 4); r /= 4;
+        const int prow = (int)(r % 128); r /= 128;       // physical row of the 128 x 64-byte panel
+        q.tap = (int)(r % taps); r /= taps;
+        q.cb = (int)(r % ncb); r /= ncb;
+        q.nt = (int)r;
+        const int cl = chunk ^ ((prow >> 1) & 3);
+        q.row = prow & 63; q.part = prow >> 6; q.k = (cl << 3) + e;
+        return q;
+    }
     const int chunk = (int)(r % 8); r /= 8;
     q.row = (int)(r % bn); r /= bn;
     q.tap = (int)(r % taps); r /= taps;
@@ -1007,6 +1053,7 @@ __global__ void __launch_bounds__(256) tc_pack_matrix_kernel(const float* __rest
 size_t tc_pack_matrix(const float* src, long long bstride, int ld_n, int ld_k, int nbatch, int N, int K, int bn, int passes,
                       float alpha, __half* out, cudaStream_t s) {
     const int cb = cb_of(passes), ncb = (K + cb - 1) / cb, ntile = (N + bn - 1) / bn;
+    KEEP_CHECK(!tc_stacked(bn, passes), "tc_pack_matrix: 64-wide N tiles use the stacked panel layout (weights only)");
     const size_t per_batch = tc_packed_weight_halfs(K, N, 1, bn, passes);
     if (out) {
         const size_t units = (size_t)nbatch * ntile * ncb * bn * (cb / 8);
@@ -1175,7 +1222,7 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     t.M = (long long)a.n * a.ho * a.wo;
     KEEP_CHECK((long long)a.n * a.h * a.w < (1ll << 31) && t.M < (1ll << 31), "conv2d_tc: more than 2^31 pixels");
     int cols = 32;
-    while (cols < 2 * bn) cols *= 2;
+    while (cols < 2 * (tc_stacked(bn, passes) ? 128 : bn)) cols *= 2;   // (stacked panels: 128 accumulator columns per 64-wide tile)
     KEEP_CHECK(cols <= 512, "conv2d_tc: BN %d needs more than 512 TMEM columns", bn);
     t.tmem_cols = cols;
     t.swap_lbo_sbo = env_swap();
