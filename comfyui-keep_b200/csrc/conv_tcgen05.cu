@@ -29,6 +29,9 @@
 #ifndef KEEP_PDL_CONV_TRIGGER
 #define KEEP_PDL_CONV_TRIGGER 0
 #endif
+#ifndef KEEP_TC_STACKED
+#define KEEP_TC_STACKED 1   // stacked [Wh ; Wl] weight panels for 64-wide N tiles in the split-precision mode (0: three N = 64 MMAs per K step)
+#endif
 
 #include "ops.h"
 #include "tc.h"
@@ -930,9 +933,6 @@ struct PanelPos { int nt, cb, tap, row, k, part; };
 // (32 channels), rows 64-127 the lo parts -- in the SWIZZLE_64B K-major layout (16-byte chunk j of row r at chunk
 // j ^ ((r >> 1) & 3)).  One N = 128 MMA then forms Ah*Wh and Ah*Wl side by side and one N = 64 MMA adds Al*Wh: two A-operand
 // fetches per K step instead of three (the N = 64 MMAs are bound by shared-memory operand fetch, profiles/r1_ubench_umma_rate.md).
-#ifndef KEEP_TC_STACKED
-#define KEEP_TC_STACKED 1
-#endif
 __host__ __device__ inline bool tc_stacked(int bn, int passes) { return KEEP_TC_STACKED && passes == 3 && bn == 64; }
 __host__ __device__ inline PanelPos panel_pos(size_t idx, int bn, int taps, int ncb, int passes) {
     PanelPos q;
