@@ -9,5 +9,6 @@ cp comfyui-keep_b200/libkeep_b200.so /tmp/lib_default.so
 KEEP_NVCC_EXTRA="-DKEEP_TC_STACKED=0" python comfyui-keep_b200/build.py --force > gpurun_out/r2_rebuild10.log 2>&1
 bash tools/ab.sh "stacked64_off|" | tee -a gpurun_out/r2_ab10.txt
 cp /tmp/lib_default.so comfyui-keep_b200/libkeep_b200.so
-bash tools/ab.sh "stacked64_on_again|" | tee -a gpurun_out/r2_ab10.txt
+bash tools/ab.sh "stacked64_on_again|" "gm_fuse_qkv|KEEP_GM_FUSE_QKV=1" | tee -a gpurun_out/r2_ab10.txt
+KEEP_GM_FUSE_QKV=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "free_running_T3 or free_T2" > gpurun_out/r2_parity_gm_fuse.log 2>&1; tail -3 gpurun_out/r2_parity_gm_fuse.log
 timeout 200 python tools/layer_times.py --mode tc3 --frames 3 > gpurun_out/r2_layer_times_stacked.txt 2>&1; head -12 gpurun_out/r2_layer_times_stacked.txt
