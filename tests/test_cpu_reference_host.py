@@ -156,3 +156,61 @@ def test_real_process_image_sequence_clip_loop_matches_host_mirror(ref_mods, kee
     x = got[0, 0].clamp(-1, 1)
     mine = ((x + 1) / 2 * 255.0).round().permute(1, 2, 0).flip(-1).to(torch.uint8).numpy()
     assert np.array_equal(ref_u8, mine)
+
+
+# ---- the two reference-side edits INTEGRATION.md documents for the caller, applied to the real source ------
+_LOOP_OLD = """            for start_idx in tqdm(range(0, num_total_faces, max_clip_length), desc="Restoring faces with KEEP"):
+                end_idx = min(start_idx + max_clip_length, num_total_faces)
+                current_clip = batched_cropped_faces[:, start_idx:end_idx, ...]
+                if current_clip.shape[1] == 1:
+                    current_clip = torch.cat([current_clip, current_clip], dim=1)
+                    temp_restored_tensors.append(self.keep_net(current_clip, need_upscale=False)[:, 0:1, ...])
+                elif current_clip.shape[1] > 1:
+                    temp_restored_tensors.append(self.keep_net(current_clip, need_upscale=False))
+"""
+_LOOP_NEW = """            import keep_b200   # all clips of equal length in ONE call: the engine overlaps / lock-steps them
+            temp_restored_tensors.append(keep_b200.sharding.run_clips_batched(
+                self.keep_net, batched_cropped_faces, max_clip_length, clips_per_call=4))
+"""
+_DROP_OLD = """            if num_faces_this_frame == 0 or has_aligned_frames:
+                output_frames_cv2.append(bg_img_final) # a little simplified, aligned case could be handled better
+                continue
+"""
+_DROP_NEW = """            if has_aligned_frames and num_faces_this_frame:   # aligned input: the restored crop IS the frame (was: dropped)
+                face = all_restored_faces_cv2[restored_face_idx_counter].astype('uint8')
+                restored_face_idx_counter += num_faces_this_frame
+                output_frames_cv2.append(cv2.resize(face, (target_w, target_h), interpolation=cv2.INTER_LANCZOS4))
+                continue
+            if num_faces_this_frame == 0:
+                output_frames_cv2.append(bg_img_final)
+                continue
+"""
+
+
+def test_documented_processor_patch_batches_clips_and_returns_the_restored_frames(ref_mods, keep_mod):
+    """INTEGRATION.md's caller-side edits (keep_processor.py:263-270 and :289-291), applied literally to the reference's source
+    at test time: the clip loop becomes one batched call per group of equal-length clips (what `batch_clips` / `concurrent_clips`
+    engines overlap), and an aligned sequence returns the restored frames instead of the untouched background."""
+    loader_mod, proc_mod = ref_mods
+    from oracle import ref_host
+    src = open(proc_mod.__file__).read()
+    assert src.count(_LOOP_OLD) == 1 and src.count(_DROP_OLD) == 1, "the reference's clip loop / paste-back changed: update INTEGRATION.md"
+    name = proc_mod.__name__ + "_patched"
+    mod = types.ModuleType(name)
+    mod.__package__ = proc_mod.__package__
+    mod.__file__ = proc_mod.__file__
+    sys.modules[name] = mod
+    exec(compile(src.replace(_LOOP_OLD, _LOOP_NEW).replace(_DROP_OLD, _DROP_NEW), proc_mod.__file__, "exec"), mod.__dict__)
+    net = _RecordingNet.__new__(_RecordingNet)
+    net.calls = []
+    net.__class__ = type("BatchNet", (_RecordingNet,), {"__call__": lambda self, x, need_upscale=True: (self.calls.append(tuple(x.shape)), x.clone())[1]})
+    pack = loader_mod.KEEPModelPack(net, ref_host._FakeFaceHelper(device="cpu"), None, None, "KEEP")
+    pack.device = torch.device("cpu")
+    g = torch.Generator().manual_seed(11)
+    images = torch.rand((9, 64, 64, 3), generator=g)
+    out = mod.KEEPFaceProcessor(pack).process_image_sequence(images, 1.0, True, True, False, max_clip_length=2)
+    # 9 frames, clips of 2: four full clips go in as ONE (4, 2, 3, 512, 512) call, the 1-frame tail duplicated to T = 2
+    assert net.calls == [(4, 2, 3, 512, 512), (1, 2, 3, 512, 512)]
+    assert tuple(out.shape) == (9, 64, 64, 3)
+    # the identity "network" makes the restored frame the input itself (up to the 64 -> 512 -> 64 resampling and uint8 rounding)
+    assert float((out - images).abs().mean()) < 0.05 and not torch.equal(out, images)   # (unpatched: out IS the background = images)
