@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for spec in "$@"; do
   label="${spec%%|*}"; envs="${spec#*|}"
   ( IFS=';'; for kv in $envs; do [ -n "$kv" ] && export "$kv"; done; unset IFS
-    timeout 240 python bench.py --no-cpu-baseline --no-eager-baseline --steps 4 --warmup 3 $AB_BENCH_ARGS > gpurun_out/ab_$label.json 2> gpurun_out/ab_$label.err
+    timeout 240 python bench.py --no-cpu-baseline --no-eager-baseline --steps ${AB_STEPS:-4} --warmup 3 $AB_BENCH_ARGS > gpurun_out/ab_$label.json 2> gpurun_out/ab_$label.err
     python - "$label" <<'P'
 import json,sys
 lab=sys.argv[1]
