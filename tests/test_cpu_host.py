@@ -243,9 +243,12 @@ def test_plan_per_frame_chain_and_kernel_choice(keep_mod, lib, state_dict, tmp_p
     l2, k2 = _plan(keep_mod, lib, state_dict, 1, 2, tc3, tmp_path)
     l3, k3 = _plan(keep_mod, lib, state_dict, 1, 3, tc3, tmp_path)
     l4, k4 = _plan(keep_mod, lib, state_dict, 1, 4, tc3, tmp_path)
-    # one more frame = one more pass of the serial chain (hq_encoder + code transformer + generator with CFT / CFA)
+    _, k5 = _plan(keep_mod, lib, state_dict, 1, 5, tc3, tmp_path)
+    # one more frame = one more pass of the serial chain (hq_encoder + code transformer + generator with CFT / CFA); GMFlow runs
+    # in chunks of 2 pairs (KEEP_FLOW_CHUNK), so T = 2 and 3 share one chunk, T = 4 and 5 need a second one
     per_frame = {k: k3[k] - k2[k] for k in k3}
-    assert per_frame == {k: k4[k] - k3[k] for k in k4}
+    per_chunk = {k: k4[k] - k3[k] - per_frame[k] for k in k4}
+    assert {k: k5[k] - k4[k] for k in k5} == per_frame and per_chunk["attention"] == 12 and per_chunk["conv"] > 0
     assert per_frame["conv"] == 168 and per_frame["attention"] == 17 and per_frame["layernorm"] == 23
     # every GEMM-shaped layer runs on the tcgen05 kernel in the tensor-core modes; the stems / heads on their own kernels
     for l in l2:
