@@ -98,7 +98,12 @@ struct AttnTcArgs {
     int win_side, wsz_log2, map_w, shift;
     // multi-head mode (heads > 1, plain rows only): batch z = b * heads + h, head h = columns [h * dh, (h + 1) * dh) of the rows
     int heads;
+    long long* trace;   // debug (keepop_attn_trace): 8 x 40 clock64 stamps of CTA 0, or null
 };
+#define AT_TRACE(slot, idx)                                                                       \
+    do {                                                                                          \
+        if (a.trace && blockIdx.x == 0 && (idx) < 40) a.trace[(slot) * 40 + (idx)] = clock64();   \
+    } while (0)
 
 // window row -> token index (plain mode: identity)
 __device__ __forceinline__ int at_token(const AttnTcArgs& a, int win, int r) {
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + 8 * 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) AT_TRACE(7, 0);
     const int qtiles = a.Lq >> 7;
     const int z = blockIdx.x / qtiles, qt = blockIdx.x - z * qtiles;
     const int NKB = a.Lk / AT_KB;
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             }
             at_fence_proxy_async();
             at_mbar_arrive(Q_FULL);
+            if (pt == 0) AT_TRACE(7, 1);                                // slot 7: [0] kernel entry, [1] Q produced, [2] done
         }
         const float* kb = a.k + (size_t)img * a.k_bs + hoff;
         const float* vb = a.v + (size_t)img * a.v_bs + hoff;
@@ -249,6 +256,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             }
             at_fence_proxy_async();
             at_mbar_arrive(K_FULL(s));
+            if (gt == 0) AT_TRACE(0, t);                                // slot 0: K stage t produced
         };
         // ---- V block j, transposed: B operand rows = head dims, K = the block's 64 keys (2 sub-blocks of 32).
         // lane = key within the sub-block: the 32 lanes of a warp write 32 consecutive halfs of one row (conflict-free)
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             }
             at_fence_proxy_async();
             at_mbar_arrive(V_FULL(sv));
+            if (gt == 0) AT_TRACE(1, j);                                // slot 1: V stage j produced
         };
         for (int t = grp; t < NKB; t += 2) produce_K(t);              // pass A: alternate stages (NKB is even or the tail is group 0's)
         if (grp == 0) {
@@ -326,6 +335,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
                 at_commit(S_FULL(s));
             }
             __syncwarp();
+            if (lane == 0) AT_TRACE(2, t);                              // slot 2: scores of block t issued
         };
         at_mbar_wait(Q_FULL, 0);
         at_tc_fence_after();
@@ -349,6 +359,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
                 if (j == NKB - 1) at_commit(O_FULL);
             }
             __syncwarp();
+            if (lane == 0) AT_TRACE(3, j);                              // slot 3: P V of block j issued
         }
     } else {
         // =========================== softmax + epilogue (warps 0-3) ===========================
@@ -381,6 +392,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             }
             at_tc_fence_before();
             at_mbar_arrive(S_EMPTY(s));
+            if (threadIdx.x == 0) AT_TRACE(4, t);                       // slot 4: pass A block t consumed
         }
         // ---- pass B: P = exp(s - m) as the (hi, lo) A operand of P V; row sum in fp32
         float l = 0.0f;
@@ -423,6 +435,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             }
             at_fence_proxy_async();
             at_mbar_arrive(P_FULL);
+            if (threadIdx.x == 0) AT_TRACE(5, j);                       // slot 5: P of block j handed over
         }
         // ---- epilogue: O / l -> global (token-major rows of DH floats)
         at_mbar_wait(O_FULL, 0);
@@ -444,6 +457,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
     }
     at_tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) AT_TRACE(7, 2);
     if (warp == 4) {
         at_tc_fence_after();
         at_tmem_dealloc(tmem_base, TMEM_COLS);
@@ -451,6 +465,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
 }
 
 }  // namespace
+
+long long* g_attn_trace = nullptr;   // debug: device buffer of 8 x 40 clock64 stamps (keepop_attn_trace)
 
 bool attention_tc_eligible(int Lq, int Lk, int dh) { return (dh == 128 || dh == 64) && Lq % 128 == 0 && Lk % AT_KB == 0 && Lk <= 1024 && Lq > 0 && Lk > 0; }
 
@@ -477,6 +493,7 @@ void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int l
     a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs; a.o_bs = o_bs;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
     a.nb = nb; a.Lq = Lq; a.Lk = Lk; a.scale = scale; a.region = region; a.n_win = n_win > 0 ? n_win : 1;
+    a.trace = g_attn_trace;
     a.win_side = win_side; a.wsz_log2 = 0; a.map_w = map_w; a.shift = shift; a.heads = heads > 1 ? heads : 1;
     KEEP_CHECK(a.heads == 1 || (win_side == 0 && nb % a.heads == 0), "attention_tc: multi-head mode needs plain rows and nb = batches * heads");
     if (win_side > 0) {

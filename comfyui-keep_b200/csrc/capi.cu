@@ -298,6 +298,9 @@ int keepop_attention_fused(const float* q, const float* k, const float* v, int n
     KEEP_API_END
 }
 
+namespace keep { extern long long* g_attn_trace; }
+int keepop_attn_trace(long long* dev_buf_320_i64) { keep::g_attn_trace = dev_buf_320_i64; return 0; }
+
 int keepop_attention_fused_heads(const float* q, const float* k, const float* v, int nb, int Lq, int Lk, int heads, int dh, float scale,
                                  float* out_dev, void* stream) {
     KEEP_API_BEGIN

@@ -141,6 +141,7 @@ int keepop_kernel_stamps(unsigned long long* dev_buf);
 int keepop_launch_log(int enable);
 int keepop_launch_log_dump(const char* path);
 int keepop_tc_trace(long long* dev_buf_160_i64); /* debug: per-role clock64 timeline of CTA 0 of the tcgen05 kernel */
+int keepop_attn_trace(long long* dev_buf_320_i64); /* debug: the same for the fused attention kernel (8 roles x 40 stamps) */
 int keepop_groupnorm_affine(const float* x_dev, int n, int hw, int c, int groups, float eps, const float* gamma_dev,
                             const float* beta_dev, float* scale_dev, float* shift_dev, void* stream);
 int keepop_layernorm(const float* x_dev, int rows, int c, const float* g_dev, const float* b_dev, float eps, float* out_dev,
