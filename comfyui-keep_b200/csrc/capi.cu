@@ -33,6 +33,7 @@ namespace keep {
 void stamp_set_conv_simt(unsigned long long*); void stamp_set_conv_small(unsigned long long*); void stamp_set_conv_tc(unsigned long long*);
 void stamp_set_gemm(unsigned long long*); void stamp_set_misc(unsigned long long*); void stamp_set_norm(unsigned long long*);
 void stamp_set_attn(unsigned long long*);
+extern long long* g_attn_trace;   // attn_tcgen05.cu
 void launch_log_enable(bool on);
 int launch_log_dump(const char* path);
 }
@@ -298,7 +299,6 @@ int keepop_attention_fused(const float* q, const float* k, const float* v, int n
     KEEP_API_END
 }
 
-namespace keep { extern long long* g_attn_trace; }
 int keepop_attn_trace(long long* dev_buf_320_i64) { keep::g_attn_trace = dev_buf_320_i64; return 0; }
 
 int keepop_attention_fused_heads(const float* q, const float* k, const float* v, int nb, int Lq, int Lk, int heads, int dh, float scale,
