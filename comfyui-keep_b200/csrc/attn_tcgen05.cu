@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
                 at_split8(v[i], hi, lo);
                 uint8_t* dst = dstK + cb * (AT_KB * 128) + row * 128 + ((pl ^ (row & 7)) << 4);
                 *reinterpret_cast<uint4*>(dst) = hi;
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>((uintptr_t)dst ^ 64)) = lo;
+                if (t >= NKB) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>((uintptr_t)dst ^ 64)) = lo;   // (pass A reads hi only)
             }
             at_fence_proxy_async();
             at_mbar_arrive(K_FULL(s));
@@ -378,20 +378,23 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             const int s = t & 1;
             at_mbar_wait(S_FULL(s), (uint32_t)((t >> 1) & 1));
             at_tc_fence_after();
+            // all four TMEM loads of the block in flight, ONE wait (each load waits ~1K cycles while the MMAs own the TMEM ports:
+            // measured 5.8K cycles per block with a wait per 16 columns, profiles/r2_trace_attn_*.txt)
+            uint32_t rr[AT_KB / 16][16];
+#pragma unroll
+            for (int c = 0; c < AT_KB / 16; ++c) at_tmem_ld16(t_lane + (uint32_t)(s * AT_KB + c * 16), rr[c]);
+            at_tmem_ld_wait();
+            at_tc_fence_before();
+            at_mbar_arrive(S_EMPTY(s));                                 // (the scores are in registers now)
 #pragma unroll
             for (int c = 0; c < AT_KB / 16; ++c) {
-                uint32_t rr[16];
-                at_tmem_ld16(t_lane + (uint32_t)(s * AT_KB + c * 16), rr);
-                at_tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    float sc = __uint_as_float(rr[e]);
+                    float sc = __uint_as_float(rr[c][e]);
                     if (a.region && sReg[t * AT_KB + c * 16 + e] != myreg) sc += -100.0f;
                     m = fmaxf(m, sc);
                 }
             }
-            at_tc_fence_before();
-            at_mbar_arrive(S_EMPTY(s));
             if (threadIdx.x == 0) AT_TRACE(4, t);                       // slot 4: pass A block t consumed
         }
         // ---- pass B: P = exp(s - m) as the (hi, lo) A operand of P V; row sum in fp32
@@ -404,24 +407,29 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             // the whole block's probabilities are formed in registers first: reading S and the exponentials of block j overlap the
             // P V MMAs of block j-1, which still read the (single) P buffer
             uint4 ph[AT_KB / 8], pl[AT_KB / 8];
+            {
+                uint32_t rr[AT_KB / 16][16];
 #pragma unroll
-            for (int c = 0; c < AT_KB / 16; ++c) {
-                uint32_t rr[16];
-                at_tmem_ld16(t_lane + (uint32_t)(s * AT_KB + c * 16), rr);
+                for (int c = 0; c < AT_KB / 16; ++c) at_tmem_ld16(t_lane + (uint32_t)(s * AT_KB + c * 16), rr[c]);
                 at_tmem_ld_wait();
-                float p[16];
+                at_tc_fence_before();
+                at_mbar_arrive(S_EMPTY(s));                        // S buffer free: the MMA warp may issue the scores of block j+2
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float sc = __uint_as_float(rr[e]);
-                    if (a.region && sReg[j * AT_KB + c * 16 + e] != myreg) sc += -100.0f;
-                    p[e] = exp2f(fmaf(sc, 1.4426950408889634f, -m2));
-                    l += p[e];
+                for (int c = 0; c < AT_KB / 16; ++c) {
+                    float p[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        float sc = __uint_as_float(rr[c][e]);
+                        if (a.region && sReg[j * AT_KB + c * 16 + e] != myreg) sc += -100.0f;
+                        float ex;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(sc, 1.4426950408889634f, -m2)));
+                        p[e] = ex;
+                        l += ex;
+                    }
+                    at_split8(p, ph[2 * c], pl[2 * c]);
+                    at_split8(p + 8, ph[2 * c + 1], pl[2 * c + 1]);
                 }
-                at_split8(p, ph[2 * c], pl[2 * c]);
-                at_split8(p + 8, ph[2 * c + 1], pl[2 * c + 1]);
             }
-            at_tc_fence_before();
-            at_mbar_arrive(S_EMPTY(s));                            // S buffer free: the MMA warp may issue the scores of block j+2
             at_mbar_wait(P_EMPTY, (uint32_t)((j & 1) ^ 1));
 #pragma unroll
             for (int c = 0; c < AT_KB / 16; ++c) {
