@@ -254,6 +254,31 @@ int keepop_conv2d_gn(int use_tc, const float* x_dev, int n, int h, int w, int ci
                      pre_shift_dev, pre_act, act, res_dev, out_dev, stream, gn_gamma_dev, gn_beta_dev, gn_scale_dev, gn_shift_dev);
 }
 
+int keepop_linear_ln(const float* x_dev, int rows, int cin, const float* weight_host, const float* bias_host, int cout,
+                     const float* res_dev, const float* ln_g_dev, const float* ln_b_dev, float eps, const float* add2_dev, int add2_rows,
+                     float* out_dev, float* ln_out_dev, float* ln_out2_dev, void* stream) {
+    KEEP_API_BEGIN
+    KEEP_CHECK(ln_g_dev && ln_b_dev && ln_out_dev && (!ln_out2_dev || add2_dev), "keepop_linear_ln: null LayerNorm argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<float> packed((size_t)cout * cin);
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i) packed[(size_t)i * cout + o] = weight_host[(size_t)o * cin + i];
+    DevBuf wd(packed.size() * 4), bd((size_t)cout * 4);
+    CUDA_CHECK(cudaMemcpy(wd.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    if (bias_host) CUDA_CHECK(cudaMemcpy(bd.p, bias_host, (size_t)cout * 4, cudaMemcpyHostToDevice));
+    ConvArgs a;
+    a.in0 = x_dev; a.c0 = cin; a.n = 1; a.h = rows; a.w = 1; a.up = 1;
+    a.wt = (const float*)wd.p; a.bias = bias_host ? (const float*)bd.p : nullptr;
+    a.kh = 1; a.kw = 1; a.stride = 1; a.cout = cout; a.ho = rows; a.wo = 1;
+    a.res = res_dev; a.out = out_dev;
+    a.ln_g = ln_g_dev; a.ln_b = ln_b_dev; a.ln_eps = eps; a.ln_out = ln_out_dev;
+    a.ln_add2 = add2_dev; a.ln_add2_rows = add2_rows; a.ln_out2 = ln_out2_dev;
+    int rc = keepop_conv2d_tc(a, weight_host, 3, s, nullptr, nullptr, nullptr, nullptr);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return rc;
+    KEEP_API_END
+}
+
 // debug: kernel-start timeline.  stamps = device buffer of 1 + 65536 uint64 (null = off); launch log = host-side names
 int keepop_kernel_stamps(unsigned long long* dev_buf) {
     keep::stamp_set_conv_simt(dev_buf); keep::stamp_set_conv_small(dev_buf); keep::stamp_set_conv_tc(dev_buf);

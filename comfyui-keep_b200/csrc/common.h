@@ -56,6 +56,9 @@ struct Tensor {
     // GroupNorm(32) partial statistics of this tensor written by the kernel that produced it ([n][gn_P][32][2] fp32; see
     // ConvArgs::gn_part): consumed (and released) by the one Engine::gn() that normalises the tensor, else by tfree()
     float* gn_part = nullptr; int gn_P = 0;
+    // ... or, for split-K layers with few slots, already finalized by the reduce kernel into the consumer's affine
+    // ([2][n][c]: scale, shift; aff_gamma = the consuming norm's weight, checked by Engine::gn())
+    float* aff = nullptr; const float* aff_gamma = nullptr;
     size_t numel() const { return (size_t)n * h * w * c; }
     size_t bytes() const { return numel() * dtype_size(dt); }
     size_t rows() const { return (size_t)n * h * w; }

@@ -210,9 +210,12 @@ template <bool GN>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
                                                             const float* __restrict__ bias, int act, const void* res,
                                                             int res_dt, void* out, int out_dt, float* __restrict__ gn_part, int gn_P,
-                                                            long long img_elems) {
+                                                            long long img_elems, const float* __restrict__ fin_gamma,
+                                                            const float* __restrict__ fin_beta, float* __restrict__ fin_scale,
+                                                            float* __restrict__ fin_shift, int* __restrict__ fin_tickets) {
     pdl_prologue_tiny();
     __shared__ float2 s_gn[GN ? 256 : 1];
+    __shared__ int s_last;
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (!GN && i >= MN) return;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -255,7 +258,109 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
             const long long img = e0 / img_elems;
             const long long slot = (e0 - img * img_elems) >> 10;
             *reinterpret_cast<float2*>(gn_part + ((size_t)(img * 32 + g) * gn_P + slot) * 2) = make_float2(ss, qq);
+            if (fin_scale) __threadfence();
         }
+        if (fin_scale) {
+            // the image's last block to arrive turns the 32 x gn_P slots into the consumer's per-channel affine (the gn_P blocks
+            // of an image are this kernel's only writers of its slots); 8 threads per group, double accumulation, fixed order
+            const long long img = ((long long)blockIdx.x * 1024) / img_elems;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int t = atomicAdd(fin_tickets + img, 1);
+                s_last = (t == gn_P - 1);
+                if (s_last) fin_tickets[img] = 0;
+            }
+            __syncthreads();
+            if (!s_last) return;
+            __threadfence();
+            const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
+            const float2* base = reinterpret_cast<const float2*>(gn_part) + (size_t)(img * 32 + g) * gn_P;
+            double sm = 0.0, sq = 0.0;
+            for (int k = l; k < gn_P; k += 8) {
+                const float2 e = __ldcg(base + k);
+                sm += (double)e.x; sq += (double)e.y;
+            }
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) {
+                sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            }
+            const int cpg = cout >> 5;
+            const double cnt = (double)(img_elems / cout) * cpg;
+            const double mean = sm / cnt;
+            double var = sq / cnt - mean * mean;
+            if (var < 0) var = 0;
+            const float rstd = (float)(1.0 / sqrt(var + 1e-6));
+            for (int i = l; i < cpg; i += 8) {
+                const int ch = g * cpg + i;
+                const float sc = fin_gamma[ch] * rstd;
+                fin_scale[(size_t)img * cout + ch] = sc;
+                fin_shift[(size_t)img * cout + ch] = fin_beta[ch] - (float)mean * sc;
+            }
+        }
+    }
+}
+// Split-K reduce whose rows feed a LayerNorm (transformer linears): the block's 1024 consecutive elements are 1024 / cout whole
+// rows, cout / 128 warps per row; two-pass statistics on the values held in registers (as layernorm_v4_kernel)
+__global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
+                                                               const float* __restrict__ bias, int act, const void* res, int res_dt,
+                                                               float* __restrict__ out, const float* __restrict__ ln_g,
+                                                               const float* __restrict__ ln_b, float eps, float* __restrict__ ln_out,
+                                                               const float* __restrict__ add2, int add2_rows, float* __restrict__ ln_out2) {
+    pdl_prologue_tiny();
+    __shared__ float s_red[2][8];
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 4 <= splitk; z += 4) {
+        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)z * MN + i));
+        const float4 p1 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)(z + 1) * MN + i));
+        const float4 p2 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)(z + 2) * MN + i));
+        const float4 p3 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)(z + 3) * MN + i));
+        v.x = (((v.x + p0.x) + p1.x) + p2.x) + p3.x; v.y = (((v.y + p0.y) + p1.y) + p2.y) + p3.y;
+        v.z = (((v.z + p0.z) + p1.z) + p2.z) + p3.z; v.w = (((v.w + p0.w) + p1.w) + p2.w) + p3.w;
+    }
+    for (; z < splitk; ++z) {
+        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)z * MN + i));
+        v.x += p0.x; v.y += p0.y; v.z += p0.z; v.w += p0.w;
+    }
+    const int col = (int)(i % cout);
+    if (bias) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + col);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (act != ACT_NONE) { v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act); }
+    if (res) {
+        const float4 r = res_dt == F32 ? ld4(reinterpret_cast<const float*>(res), (size_t)i) : ld4(reinterpret_cast<const __half*>(res), (size_t)i);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    st4(out, (size_t)i, v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpr = cout >> 7, w0 = (warp / wpr) * wpr;
+    float sm = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    if (lane == 0) s_red[0][warp] = sm;
+    __syncthreads();
+    float tot = 0.0f;
+    for (int k = 0; k < wpr; ++k) tot += s_red[0][w0 + k];
+    const float mean = tot / (float)cout;
+    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+    float qq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    if (lane == 0) s_red[1][warp] = qq;
+    __syncthreads();
+    tot = 0.0f;
+    for (int k = 0; k < wpr; ++k) tot += s_red[1][w0 + k];
+    const float rstd = rsqrtf(tot / (float)cout + eps);
+    const float4 gg = *reinterpret_cast<const float4*>(ln_g + col), bb = *reinterpret_cast<const float4*>(ln_b + col);
+    float4 y;
+    y.x = dx * rstd * gg.x + bb.x; y.y = dy * rstd * gg.y + bb.y; y.z = dz * rstd * gg.z + bb.z; y.w = dw * rstd * gg.w + bb.w;
+    st4(ln_out, (size_t)i, y);
+    if (ln_out2) {
+        const long long row = i / cout;
+        const float4 a2 = *reinterpret_cast<const float4*>(add2 + (size_t)(row % add2_rows) * cout + col);
+        st4(ln_out2, (size_t)i, make_float4(y.x + a2.x, y.y + a2.y, y.z + a2.z, y.w + a2.w));
     }
 }
 __global__ void __launch_bounds__(256) splitk_reduce1_kernel(const float* __restrict__ part, int splitk, long long MN, int cout,
@@ -286,18 +391,35 @@ int conv_pick_splitk(const ConvArgs& a) {
 }
 
 void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
-                   int res_dt, void* out, int out_dt, cudaStream_t s, float* gn_part, int gn_P, long long hw) {
+                   int res_dt, void* out, int out_dt, cudaStream_t s, float* gn_part, int gn_P, long long hw, const float* fin_gamma,
+                   const float* fin_beta, float* fin_scale, float* fin_shift, int* fin_tickets) {
+    KEEP_CHECK(!fin_scale || (gn_part && fin_shift && fin_gamma && fin_beta && fin_tickets && gn_P <= kGnReduceFinalMaxP),
+               "splitk_reduce: finalize-in-reduce needs statistics slots (<= %d per group), gamma / beta and tickets", kGnReduceFinalMaxP);
     if (gn_part) {
         const long long img_elems = hw * cout;
         KEEP_CHECK(MN % 1024 == 0 && img_elems % 1024 == 0 && (cout == 128 || cout == 256 || cout == 512) && gn_P == img_elems / 1024,
                    "splitk_reduce: layer cannot emit GroupNorm statistics (MN %lld, cout %d)", MN, cout);
         launch_k(splitk_reduce_kernel<true>, dim3((unsigned)(MN / 1024)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out,
-                 out_dt, gn_part, gn_P, img_elems);
+                 out_dt, gn_part, gn_P, img_elems, fin_gamma, fin_beta, fin_scale, fin_shift, fin_tickets);
     } else if (MN % 4 != 0 || cout % 4 != 0)
         launch_k(splitk_reduce1_kernel, dim3(cdiv(MN, 256)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt);
     else
         launch_k(splitk_reduce_kernel<false>, dim3(cdiv(MN, 1024)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, out_dt,
-                 (float*)nullptr, 0, 0LL);
+                 (float*)nullptr, 0, 0LL, (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (float*)nullptr, (int*)nullptr);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+bool splitk_reduce_ln_eligible(long long MN, int cout) {
+    return MN > 0 && MN % 1024 == 0 && (cout == 128 || cout == 256 || cout == 512 || cout == 1024);
+}
+
+void splitk_reduce_ln(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res, int res_dt,
+                      float* out, const float* ln_g, const float* ln_b, float eps, float* ln_out, const float* add2, int add2_rows,
+                      float* ln_out2, cudaStream_t s) {
+    KEEP_CHECK(splitk_reduce_ln_eligible(MN, cout) && ln_g && ln_b && ln_out && (!ln_out2 || (add2 && add2_rows > 0)),
+               "splitk_reduce_ln: unsupported shape (MN %lld, cout %d) or null LayerNorm argument", MN, cout);
+    launch_k(splitk_reduce_ln_kernel, dim3((unsigned)(MN / 1024)), dim3(256), 0, s, partial, splitk, MN, cout, bias, act, res, res_dt, out, ln_g,
+             ln_b, eps, ln_out, add2, add2_rows > 0 ? add2_rows : 1, ln_out2);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -156,6 +156,13 @@ __device__ __noinline__ float act_slow(float v, int act) { return apply_act(v, a
 //             with fp32 accumulation in TMEM -> fp32-grade results on the tensor cores (the "decision path" needs
 //             this: one flipped argmax over the 1024 code logits changes a 32x32-pixel block).
 // optional per-role timeline (debug): a.trace != null -> CTA 0 stamps clock64() at role milestones of its first tiles
+#ifndef KEEP_TC_TRACE_FINE
+#define KEEP_TC_TRACE_FINE 0   // 1 (debug builds): extra producer milestones in rows 10-13 of a 256-entry trace buffer
+#endif
+#define TC_TRACE_FINE(slot, idx)                                                                   \
+    do {                                                                                           \
+        if (KEEP_TC_TRACE_FINE) TC_TRACE(slot, idx);                                               \
+    } while (0)
 #define TC_TRACE(slot, idx)                                                                        \
     do {                                                                                           \
         if (a.trace && blockIdx.x == 0 && (idx) < 16) a.trace[(slot) * 16 + (idx)] = clock64();    \
@@ -286,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
         int stage = 0, phase = 0, trace_i = 0, seq = 0;
         bool waited = false;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            if (pt == 0 && grp == 0) TC_TRACE_FINE(10, trace_i);
             int nt, img, ty, tx, ks;
             decode(w, 0, nt, img, ty, tx, ks);
             const int cb0 = ks * cb_per, cb1 = min(a.ncb, cb0 + cb_per);
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                 }
             };
             if (!a.s2d) locate(0, 0);
+            if (pt == 0 && grp == 0) TC_TRACE_FINE(11, trace_i);
             for (int cb = cb0; cb < cb1; ++cb) {
                 if (NGROUPS == 2 && ((seq++ & 1) != grp)) {   // the other group's stage: only keep the ring position in step
                     if (++stage == SA) { stage = 0; phase ^= 1; }
@@ -340,6 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                         else ldg256(reinterpret_cast<const float*>(g), reinterpret_cast<float*>(&raw[it][0]));
                     }
                 }
+                if (pt == 0 && grp == 0) TC_TRACE_FINE(12, trace_i);
                 float sc[8], sh[8];
                 if (a.pre_scale && ch_ok) {
                     const float4* ps = reinterpret_cast<const float4*>(a.pre_scale + (size_t)img * cin + ch);
@@ -435,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     *reinterpret_cast<uint4*>(dst + soff[it]) = o;
                     if (PASSES == 3) *reinterpret_cast<uint4*>(dst + (soff[it] ^ 64)) = ol;
                 }
+                if (pt == 0 && grp == 0) TC_TRACE_FINE(13, trace_i);
                 fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
                 mbar_arrive(A_FULL(stage));
                 if (pt == 0 && grp == 0) { TC_TRACE(2, trace_i); ++trace_i; }
@@ -1273,9 +1284,15 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
         KEEP_CHECK(splitk == a.splitk && !a.bias && !a.res && a.act == ACT_NONE, "conv2d_tc: no_reduce needs the K split as requested and a plain epilogue");
         return 1;
     }
-    if (splitk > 1)
+    if (splitk > 1 && a.ln_out) {
+        KEEP_CHECK(a.out_dt == F32 && !a.gn_part, "conv2d_tc: the reduce + LayerNorm kernel writes fp32 and no GroupNorm statistics");
+        splitk_reduce_ln(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, (float*)a.out, a.ln_g, a.ln_b, a.ln_eps, a.ln_out,
+                         a.ln_add2, a.ln_add2_rows, a.ln_out2, s);
+    } else if (splitk > 1)
         splitk_reduce(partial, splitk, t.M * a.cout, a.cout, a.bias, a.act, a.res, a.res_dt, a.out, a.out_dt, s, a.gn_part, a.gn_P,
-                      (long long)a.ho * a.wo);
+                      (long long)a.ho * a.wo, a.gn_fin_gamma, a.gn_fin_beta, a.gn_fin_scale, a.gn_fin_shift, a.gn_tickets);
+    else
+        KEEP_CHECK(!a.gn_fin_scale && !a.ln_out, "conv2d_tc: finalize-in-reduce / LayerNorm-in-reduce requested for a layer without a split-K reduce");
     return splitk > 1 ? 2 : 1;
 }
 
@@ -1308,6 +1325,7 @@ int keepop_conv2d_tc(const keep::ConvArgs& a_in, const float* w_oihw_host, int p
     const int splitk = tc_pick_splitk(m_tiles, cdiv(a.cout, bn), cdiv(vcin, tc_cb(passes)));
     if (splitk > 1) CUDA_CHECK(cudaMalloc((void**)&part, (size_t)splitk * a.n * a.ho * a.wo * a.cout * sizeof(float)));
     float* gn_part = nullptr;
+    int* tickets = nullptr;
     if (gn_scale) {   // GroupNorm(32) statistics of the output from the producing kernel + the finalize launch
         a.out_dt = F32;
         const int P = conv_gn_slots(a, splitk);
@@ -1315,6 +1333,12 @@ int keepop_conv2d_tc(const keep::ConvArgs& a_in, const float* w_oihw_host, int p
         CUDA_CHECK(cudaMalloc((void**)&gn_part, (size_t)a.n * P * 64 * sizeof(float)));
         CUDA_CHECK(cudaMemsetAsync(gn_part, 0xff, (size_t)a.n * P * 64 * sizeof(float), s));   // NaN pattern: every slot must be written
         a.gn_part = gn_part; a.gn_P = P;
+        static const bool fin_en = !(getenv("KEEP_GN_REDUCE_FINAL") && getenv("KEEP_GN_REDUCE_FINAL")[0] == '0');
+        if (fin_en && splitk > 1 && P <= kGnReduceFinalMaxP) {   // the engine's choice for such layers: finalize inside the reduce
+            CUDA_CHECK(cudaMalloc((void**)&tickets, a.n * sizeof(int)));
+            CUDA_CHECK(cudaMemsetAsync(tickets, 0, a.n * sizeof(int), s));
+            a.gn_fin_gamma = gn_gamma; a.gn_fin_beta = gn_beta; a.gn_fin_scale = gn_scale; a.gn_fin_shift = gn_shift; a.gn_tickets = tickets;
+        }
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1323,16 +1347,18 @@ int keepop_conv2d_tc(const keep::ConvArgs& a_in, const float* w_oihw_host, int p
         CUDA_CHECK(cudaStreamSynchronize(s));   // panels are complete: the loader may run ahead of griddepcontrol.wait
         a.wt_static = 1;
         conv2d_tc(a, dw, bn, passes, splitk, part, sms, s);
-        if (gn_part) gn_finalize_parts(gn_part, a.n, a.gn_P, a.ho * a.wo, a.cout, 1e-6f, gn_gamma, gn_beta, gn_scale, gn_shift, s);
+        if (gn_part && !a.gn_fin_scale) gn_finalize_parts(gn_part, a.n, a.gn_P, a.ho * a.wo, a.cout, 1e-6f, gn_gamma, gn_beta, gn_scale, gn_shift, s);
         CUDA_CHECK(cudaStreamSynchronize(s));
     } catch (...) {
         cudaFree(dw);
         cudaFree(part);
         cudaFree(gn_part);
+        cudaFree(tickets);
         throw;
     }
     cudaFree(dw);
     cudaFree(part);
     cudaFree(gn_part);
+    cudaFree(tickets);
     return 0;
 }

@@ -495,6 +495,7 @@ Tensor Engine::talloc(int n, int h, int w, int c, int dt) {
 }
 void Engine::tfree(Tensor& t) {
     if (t.gn_part) { ar_->free(t.gn_part); t.gn_part = nullptr; }
+    if (t.aff) { ar_->free(t.aff); t.aff = nullptr; }
     ar_->free(t.p);
     t.p = nullptr;
 }
@@ -573,7 +574,30 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             out.gn_P = P;
             out.gn_part = (float*)ar_->alloc((size_t)x.n * P * 64 * sizeof(float));
             a.gn_part = out.gn_part; a.gn_P = P;
+            // few slots behind a split-K reduce: its last block per image finalizes them (no gn_finalize_parts launch);
+            // KEEP_GN_REDUCE_FINAL=0 keeps the separate launch
+            static const bool fin_en = !(getenv("KEEP_GN_REDUCE_FINAL") && getenv("KEEP_GN_REDUCE_FINAL")[0] == '0');
+            if (fin_en && a.splitk > 1 && P <= kGnReduceFinalMaxP && !o.stats_norm.empty() && x.n <= gn_ticket_count() &&
+                has(o.stats_norm + ".weight")) {
+                out.aff = (float*)ar_->alloc((size_t)2 * x.n * cw.cout * sizeof(float));
+                out.aff_gamma = warr(o.stats_norm + ".weight");
+                a.gn_fin_gamma = out.aff_gamma; a.gn_fin_beta = warr(o.stats_norm + ".bias");
+                a.gn_fin_scale = out.aff; a.gn_fin_shift = out.aff + (size_t)x.n * cw.cout;
+                a.gn_tickets = gn_tickets_ ? gn_tickets_ + ((s_ == side_ && side_) ? gn_ticket_count() : 0) : nullptr;
+            }
         }
+    }
+    // LayerNorm of the output rows inside the split-K reduce (transformer linears; KEEP_LN_REDUCE=0: separate layernorm launch)
+    static const bool ln_en = !(getenv("KEEP_LN_REDUCE") && getenv("KEEP_LN_REDUCE")[0] == '0');
+    if (o.ln && ln_en && use_tc && a.splitk > 1 && !cluster_mode && out.dt == F32 && !a.gn_part &&
+        splitk_reduce_ln_eligible((long long)out.numel(), cw.cout)) {
+        LnFuse& f = *o.ln;
+        f.out = talloc(out.n, out.h, out.w, out.c, F32);
+        if (f.add2) f.out2 = talloc(out.n, out.h, out.w, out.c, F32);
+        a.ln_g = warr(f.prefix + ".weight"); a.ln_b = warr(f.prefix + ".bias"); a.ln_eps = 1e-5f; a.ln_out = f.out.f();
+        a.ln_add2 = f.add2; a.ln_add2_rows = f.add2_rows; a.ln_out2 = f.add2 ? f.out2.f() : nullptr;
+        f.done = true;
+        if (plan_) plan_->push_back("layernorm rows=" + std::to_string(out.rows()) + " c=" + std::to_string(out.c) + " fused=1");
     }
     if (tc_collect_ && use_tc)
         tc_collect_->push_back({cw, bn, passes, tc_is_s2d(a) ? a.pad_t : -1, (wide_scope_ && !o.pre && x.w > 1 && passes == 3 && a.in0_dt == F32) ? 1 : 0});
@@ -582,7 +606,7 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
         snprintf(line, sizeof(line), "conv n=%d h=%d w=%d c0=%d c1=%d cout=%d k=%d stride=%d up=%d pre=%d act=%d res=%d kernel=%s splitk=%d bn=%d wide=%d",
                  a.n, a.h, a.w, a.c0, a.c1, a.cout, a.kh, a.stride, a.up, a.pre_scale ? a.pre_act + 1 : 0, a.act, a.res ? 1 : 0,
                  use_tc ? "tcgen05" : (use_small ? "small" : "simt"), a.splitk, bn, (a.a_wide && use_tc && passes == 3) ? 1 : 0);
-        plan_->push_back(std::string(line) + (a.gn_part ? " gnstats=1" : ""));
+        plan_->push_back(std::string(line) + (a.gn_fin_scale ? " gnstats=2" : (a.gn_part ? " gnstats=1" : "")));
     }
     if (!ar_->dry()) {
         Prof pr;
@@ -669,9 +693,9 @@ const __half* Engine::tc_weights(const ConvW& cw, int bn, int passes, int s2d_pa
     return t.p;
 }
 
-Tensor Engine::linear(const Tensor& x, const std::string& prefix, int act, const Tensor* res) {
+Tensor Engine::linear(const Tensor& x, const std::string& prefix, int act, const Tensor* res, LnFuse* lnf) {
     ConvOpt o;
-    o.act = act; o.res = res; o.out_dt = F32;
+    o.act = act; o.res = res; o.out_dt = F32; o.ln = lnf;
     return conv(x, convw(prefix), o);
 }
 
@@ -680,11 +704,21 @@ Aff Engine::gn(const Tensor& x, const std::string& prefix, const Tensor* x2) {
     KEEP_CHECK(ct % 32 == 0, "GroupNorm(32): %d channels", ct);
     const int cpg = ct / 32;
     Aff a;
-    a.scale = (float*)ar_->alloc((size_t)2 * x.n * ct * sizeof(float));
-    a.shift = a.scale + (size_t)x.n * ct;
     const float* g = warr(prefix + ".weight");
     const float* b = warr(prefix + ".bias");
     const int hw = x.h * x.w;
+    if (x.aff && !x2) {   // the producing layer's split-K reduce already wrote this norm's affine
+        KEEP_CHECK(x.aff_gamma == g, "groupnorm %s: the producer finalized its statistics for another norm", prefix.c_str());
+        if (plan_) plan_->push_back("groupnorm n=" + std::to_string(x.n) + " hw=" + std::to_string(hw) + " c=" + std::to_string(ct) + " fused=2");
+        Tensor& xm = const_cast<Tensor&>(x);
+        a.scale = xm.aff;
+        a.shift = a.scale + (size_t)x.n * ct;
+        xm.aff = nullptr;
+        if (xm.gn_part) { ar_->free(xm.gn_part); xm.gn_part = nullptr; }
+        return a;
+    }
+    a.scale = (float*)ar_->alloc((size_t)2 * x.n * ct * sizeof(float));
+    a.shift = a.scale + (size_t)x.n * ct;
     if (x.gn_part && !x2) {   // the producing kernel left the statistics: finalize only
         if (plan_) plan_->push_back("groupnorm n=" + std::to_string(x.n) + " hw=" + std::to_string(hw) + " c=" + std::to_string(ct) + " fused=1");
         if (!ar_->dry()) {
@@ -739,10 +773,10 @@ Tensor Engine::ln(const Tensor& x, const std::string& prefix, const Tensor* res,
 }
 
 // vqgan_arch.py:170-181
-Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2, bool out_stats) {
+Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2, bool out_stats, const std::string& out_norm) {
     Aff a1 = gn(x, p + ".norm1", x2);
     ConvOpt o1;
-    o1.pad(1); o1.pre = &a1; o1.pre_act = ACT_SWISH; o1.in1 = x2; o1.want_stats = true;   // h feeds norm2
+    o1.pad(1); o1.pre = &a1; o1.pre_act = ACT_SWISH; o1.in1 = x2; o1.want_stats = true; o1.stats_norm = p + ".norm2";   // h feeds norm2
     Tensor h = conv(x, p + ".conv1", o1);
     afree(a1);
     Aff a2 = gn(h, p + ".norm2");
@@ -756,7 +790,7 @@ Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2
         KEEP_CHECK(!x2, "res_block: concat input needs conv_out");
     }
     ConvOpt o2;
-    o2.pad(1); o2.pre = &a2; o2.pre_act = ACT_SWISH; o2.res = &skip; o2.want_stats = out_stats;
+    o2.pad(1); o2.pre = &a2; o2.pre_act = ACT_SWISH; o2.res = &skip; o2.want_stats = out_stats; o2.stats_norm = out_norm;
     Tensor out = conv(h, p + ".conv2", o2);
     afree(a2);
     tfree(h);
@@ -872,7 +906,7 @@ Tensor Engine::mha_tc(const float* q, const float* k, const float* v, int Lq, in
 }
 
 // vqgan_arch.py:219-243
-Tensor Engine::attn_block(const Tensor& x, const std::string& p, bool out_stats) {
+Tensor Engine::attn_block(const Tensor& x, const std::string& p, bool out_stats, const std::string& out_norm) {
     Aff a = gn(x, p + ".norm");
     ConvOpt o;
     o.pre = &a; o.out_dt = F32;
@@ -884,7 +918,7 @@ Tensor Engine::attn_block(const Tensor& x, const std::string& p, bool out_stats)
     tfree(qkv);
     O.h = x.h; O.w = x.w;
     ConvOpt po;
-    po.res = &x; po.want_stats = out_stats;
+    po.res = &x; po.want_stats = out_stats; po.stats_norm = out_norm;
     Tensor out = conv(O, p + ".proj_out", po);
     tfree(O);
     return out;
@@ -906,20 +940,22 @@ Tensor Engine::encoder(const Tensor& img, const std::string& p, const std::funct
         // the next block starts with a GroupNorm of this block's output (res: norm1, attn: norm, norm_out)
         const std::string next = i + 1 < 25 ? kEncProg[i + 1] : "";
         const bool next_gn = next == "res" || next == "attn" || next == "norm";
+        const std::string nbp = p + ".blocks." + std::to_string(i + 1);
+        const std::string next_norm = !next_gn ? "" : (next == "res" ? nbp + ".norm1" : (next == "attn" ? nbp + ".norm" : nbp));
         Tensor y;
         if (kind == "conv") {
             ConvOpt o;
-            o.pad(1); o.want_stats = next_gn;
+            o.pad(1); o.want_stats = next_gn; o.stats_norm = next_norm;
             if (i == 24) { o.pre = &pend; o.out_dt = F32; }
             y = conv(x, bp, o);
             if (i == 24) afree(pend);
         } else if (kind == "res") {
-            y = res_block(x, bp, nullptr, next_gn);
+            y = res_block(x, bp, nullptr, next_gn, next_norm);
         } else if (kind == "attn") {
-            y = attn_block(x, bp, next_gn);
+            y = attn_block(x, bp, next_gn, next_norm);
         } else if (kind == "down") {  // vqgan_arch.py:135-139
             ConvOpt o;
-            o.stride = 2; o.pad_b = 1; o.pad_r = 1; o.want_stats = next_gn;
+            o.stride = 2; o.pad_b = 1; o.pad_r = 1; o.want_stats = next_gn; o.stats_norm = next_norm;
             y = conv(x, bp + ".conv", o);
         } else {  // norm_out: statistics only; apply is fused into the next conv
             pend = gn(x, bp);
@@ -1279,7 +1315,8 @@ Tensor Engine::kalman_gains(const Tensor& z_codes, int T) {
     const int save = adt_;
     adt_ = F32;
     for (int i = 0; i < 3; ++i) {
-        Tensor y = res_block(x, "kalman_filter.kalman_gain_calculator." + std::to_string(i), nullptr, i < 2);
+        Tensor y = res_block(x, "kalman_filter.kalman_gain_calculator." + std::to_string(i), nullptr, i < 2,
+                             i < 2 ? "kalman_filter.kalman_gain_calculator." + std::to_string(i + 1) + ".norm1" : "");
         tfree(x);
         x = y;
     }
@@ -1299,12 +1336,16 @@ Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
     const int nbt = z_hat.n;   // clips in lockstep (1 on the per-clip path): tokens of clip c are rows [c*L, (c+1)*L)
     Tensor zt = z_hat;
     zt.n = 1; zt.h = nbt * L; zt.w = 1;
-    Tensor t = linear(zt, "feat_emb");
     const float* pos = warr("position_emb");
+    // every LayerNorm of the stack follows a split-K linear: its reduce kernel writes the normalised rows too (LnFuse)
+    LnFuse pre;
+    pre.prefix = "ft_layers.0.norm1"; pre.add2 = pos; pre.add2_rows = L;
+    Tensor t = linear(zt, "feat_emb", ACT_NONE, nullptr, &pre);
     for (int l = 0; l < 9; ++l) {
         const std::string p = "ft_layers." + std::to_string(l);
-        Tensor qk_in;
-        Tensor tn = ln(t, p + ".norm1", nullptr, pos, L, &qk_in);
+        Tensor qk_in, tn;
+        if (pre.done) { tn = pre.out; qk_in = pre.out2; }
+        else tn = ln(t, p + ".norm1", nullptr, pos, L, &qk_in);
         Tensor qk = linear(qk_in, p + ".self_attn.in_proj_qk");
         Tensor v = linear(tn, p + ".self_attn.in_proj_v");
         tfree(qk_in); tfree(tn);
@@ -1325,15 +1366,20 @@ Tensor Engine::code_transformer(const Tensor& z_hat, int frame) {
                     heads, dh, 1.0f / sqrtf((float)dh));
         }
         tfree(qk); tfree(v);
-        Tensor t1 = linear(o, p + ".self_attn.out_proj", ACT_NONE, &t);
+        LnFuse f2;
+        f2.prefix = p + ".norm2";
+        Tensor t1 = linear(o, p + ".self_attn.out_proj", ACT_NONE, &t, &f2);
         tfree(o); tfree(t);
-        Tensor n2 = ln(t1, p + ".norm2");
+        Tensor n2 = f2.done ? f2.out : ln(t1, p + ".norm2");
         Tensor hdn = linear(n2, p + ".linear1", ACT_GELU);
         tfree(n2);
-        t = linear(hdn, p + ".linear2", ACT_NONE, &t1);
+        pre = LnFuse();
+        if (l < 8) { pre.prefix = "ft_layers." + std::to_string(l + 1) + ".norm1"; pre.add2 = pos; pre.add2_rows = L; }
+        else pre.prefix = "idx_pred_layer.0";
+        t = linear(hdn, p + ".linear2", ACT_NONE, &t1, &pre);
         tfree(hdn); tfree(t1);
     }
-    Tensor tn = ln(t, "idx_pred_layer.0");
+    Tensor tn = pre.done ? pre.out : ln(t, "idx_pred_layer.0");
     tfree(t);
     Tensor logits = linear(tn, "idx_pred_layer.1");
     tfree(tn);
@@ -1431,20 +1477,22 @@ Tensor Engine::generator(const Tensor& quant, int frame, Tensor taps[6], Tensor 
         bool next_gn = next == "res" || next == "attn" || next == "norm";
         for (int k = 0; k < 6; ++k)
             if (kFuseGen[k] == j && (cft_on_[k] || (cfa_on_[k] && frame > 0))) next_gn = false;
+        const std::string nbp = "generator.blocks." + std::to_string(j + 1);
+        const std::string next_norm = !next_gn ? "" : (next == "res" ? nbp + ".norm1" : (next == "attn" ? nbp + ".norm" : nbp));
         Tensor y;
         if (kind == "conv") {
             ConvOpt o;
-            o.pad(1); o.want_stats = next_gn;
+            o.pad(1); o.want_stats = next_gn; o.stats_norm = next_norm;
             if (j == 24) { o.pre = &pend; o.out_dt = F32; }
             y = conv(x, bp, o);
             if (j == 24) afree(pend);
         } else if (kind == "res") {
-            y = res_block(x, bp, nullptr, next_gn);
+            y = res_block(x, bp, nullptr, next_gn, next_norm);
         } else if (kind == "attn") {
-            y = attn_block(x, bp, next_gn);
+            y = attn_block(x, bp, next_gn, next_norm);
         } else if (kind == "up") {  // vqgan_arch.py:148-152: nearest x2 fused into the conv's gather
             ConvOpt o;
-            o.pad(1); o.up = 2; o.want_stats = next_gn;
+            o.pad(1); o.up = 2; o.want_stats = next_gn; o.stats_norm = next_norm;
             y = conv(x, bp + ".conv", o);
         } else {
             pend = gn(x, bp);

@@ -33,6 +33,15 @@ struct DevArr { float* p = nullptr; long long numel = 0; int d[4] = {0, 0, 0, 0}
 struct ConvW { const float* w = nullptr; const float* b = nullptr; int cin = 0, cout = 0, kh = 1, kw = 1; };
 struct Aff { float* scale = nullptr; float* shift = nullptr; };
 
+// LayerNorm of a split-K layer's output rows folded into its reduce kernel (ConvArgs::ln_out): filled in by Engine::conv() when
+// the layer qualifies (done = true: out / out2 hold LN(y) and LN(y) + add2), else the caller runs Engine::ln() itself
+struct LnFuse {
+    std::string prefix;
+    const float* add2 = nullptr; int add2_rows = 0;
+    Tensor out, out2;
+    bool done = false;
+};
+
 struct ConvOpt {
     int stride = 1, pad_t = 0, pad_l = 0, pad_b = 0, pad_r = 0, up = 1;
     const Aff* pre = nullptr; int pre_act = ACT_NONE;
@@ -42,6 +51,8 @@ struct ConvOpt {
     int out_dt = -1;  // -1: engine feature-map dtype
     bool exact = false;  // force the exact-fp32 CUDA-core kernel even when the tcgen05 path is enabled
     bool want_stats = false;   // the output's next consumer is a GroupNorm(32): let the producing kernel emit its statistics
+    LnFuse* ln = nullptr;      // the output's next consumer is this LayerNorm (fp32 token matrices)
+    std::string stats_norm;    // ... and that norm's parameter prefix, when known: split-K layers finalize inside the reduce kernel
     ConvOpt& pad(int p) { pad_t = pad_l = pad_b = pad_r = p; return *this; }
 };
 
@@ -74,14 +85,14 @@ class Engine {
     void afree(Aff& a);
     Tensor conv(const Tensor& x, const ConvW& cw, const ConvOpt& o);
     Tensor conv(const Tensor& x, const std::string& prefix, const ConvOpt& o) { return conv(x, convw(prefix), o); }
-    Tensor linear(const Tensor& x, const std::string& prefix, int act = ACT_NONE, const Tensor* res = nullptr);
+    Tensor linear(const Tensor& x, const std::string& prefix, int act = ACT_NONE, const Tensor* res = nullptr, LnFuse* lnf = nullptr);
     Aff gn(const Tensor& x, const std::string& prefix, const Tensor* x2 = nullptr);
     Aff inorm(const Tensor& x);
     Tensor ln(const Tensor& x, const std::string& prefix, const Tensor* res = nullptr, const float* add2 = nullptr,
               int add2_rows = 0, Tensor* out2 = nullptr);
     // out_stats: the block's output is normalised next (GroupNorm) -> its last conv emits the statistics
-    Tensor res_block(const Tensor& x, const std::string& p, const Tensor* x2 = nullptr, bool out_stats = false);
-    Tensor attn_block(const Tensor& x, const std::string& p, bool out_stats = false);
+    Tensor res_block(const Tensor& x, const std::string& p, const Tensor* x2 = nullptr, bool out_stats = false, const std::string& out_norm = "");
+    Tensor attn_block(const Tensor& x, const std::string& p, bool out_stats = false, const std::string& out_norm = "");
     Tensor encoder(const Tensor& img, const std::string& p, const std::function<void(int, const Tensor&)>& tap);
     // multi-head attention on (rows, ld) matrices; writes (nb*Lq, heads*dh)
     Tensor mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv, long long sv,

@@ -33,6 +33,15 @@ struct ConvArgs {
     // tcgen05 path only: GroupNorm(32) partial statistics of the output, written by the producing kernel (the conv epilogue,
     // or the split-K reduce) as gn_part[n][32][gn_P][2] fp32 (sum, sum of squares) -- see conv_gn_slots()
     float* gn_part = nullptr; int gn_P = 0;
+    // split-K layers with few slots: the reduce kernel's last block per image (ticket) also finalizes them into the consumer's
+    // affine (gn_fin_scale / shift [n][cout], gamma / beta of the CONSUMING norm) -- no gn_finalize_parts launch.  gn_tickets:
+    // >= n zeroed ints, left zeroed.
+    const float* gn_fin_gamma = nullptr; const float* gn_fin_beta = nullptr; float* gn_fin_scale = nullptr; float* gn_fin_shift = nullptr;
+    int* gn_tickets = nullptr;
+    // split-K layers whose output rows (cout = 128 / 256 / 512 / 1024 channels) feed a LayerNorm: the reduce kernel also writes
+    // ln_out = LN(out) * g + b and, optionally, ln_out2 = ln_out + ln_add2[row % ln_add2_rows] (a positional embedding)
+    const float* ln_g = nullptr; const float* ln_b = nullptr; float ln_eps = 1e-5f; float* ln_out = nullptr;
+    const float* ln_add2 = nullptr; int ln_add2_rows = 1; float* ln_out2 = nullptr;
     int wt_static = 0;             // tcgen05 path only: packed weights are older than the stream's previous kernel (see TcConvArgs)
     int no_reduce = 0;             // tcgen05 path only: leave the splitk partial tiles as the result -- with K = heads x dh and
                                    // splitk = heads, partial[h] IS the per-head product Q_h K_h^T (multi-head attention scores)

@@ -57,6 +57,15 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
 // gn_part != null: also emit GroupNorm(32) partial statistics of the final values, one slot of 32 x (sum, sumsq) per
 // 1024-element block -> gn_part[img][32][gn_P][2] (hw = output pixels per image; needs conv_gn_slots(...) > 0)
 void splitk_reduce(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res,
-                   int res_dt, void* out, int out_dt, cudaStream_t s, float* gn_part = nullptr, int gn_P = 0, long long hw = 0);
+                   int res_dt, void* out, int out_dt, cudaStream_t s, float* gn_part = nullptr, int gn_P = 0, long long hw = 0,
+                   const float* fin_gamma = nullptr, const float* fin_beta = nullptr, float* fin_scale = nullptr, float* fin_shift = nullptr,
+                   int* fin_tickets = nullptr);
+// same reduce + LayerNorm over each output row (see ConvArgs::ln_out); fp32 out, MN % 1024 == 0, cout in {128, 256, 512, 1024}
+void splitk_reduce_ln(const float* partial, int splitk, long long MN, int cout, const float* bias, int act, const void* res, int res_dt,
+                      float* out, const float* ln_g, const float* ln_b, float eps, float* ln_out, const float* add2, int add2_rows,
+                      float* ln_out2, cudaStream_t s);
+bool splitk_reduce_ln_eligible(long long MN, int cout);
+// largest slot count per (image, group) the reduce kernel finalizes itself (one block walks 32 x P slots)
+constexpr int kGnReduceFinalMaxP = 256;
 
 }  // namespace keep

@@ -135,6 +135,13 @@ int keepop_conv2d_gn(int use_tc, const float* x_dev, int n, int h, int w, int ci
                      const float* pre_scale_dev, const float* pre_shift_dev, int pre_act, int act, const float* res_dev,
                      float* out_dev, const float* gn_gamma_dev, const float* gn_beta_dev, float* gn_scale_dev, float* gn_shift_dev,
                      void* stream);
+/* linear layer y = x W^T + b (+ res) over `rows` token rows on the split-precision tcgen05 path whose split-K reduce kernel also
+ * writes the LayerNorm of every output row: ln_out = LN(y) * g + b (eps), and, when add2_dev is given, ln_out2 = ln_out +
+ * add2[row % add2_rows] (the code transformer's norm -> (+ position_emb) pattern, keep_arch.py:423-440).  weight_host (cout, cin);
+ * fails when the shape does not split along K (nothing to fuse into). */
+int keepop_linear_ln(const float* x_dev, int rows, int cin, const float* weight_host, const float* bias_host, int cout,
+                     const float* res_dev, const float* ln_g_dev, const float* ln_b_dev, float eps, const float* add2_dev, int add2_rows,
+                     float* out_dev, float* ln_out_dev, float* ln_out2_dev, void* stream);
 /* debug timeline (tools/timeline.py): every kernel appends %globaltimer at its start to dev_buf (uint64[1 + 65536], [0] = count;
  * NULL = off); the launch log records kernel names and grids on the host in enqueue order */
 int keepop_kernel_stamps(unsigned long long* dev_buf);

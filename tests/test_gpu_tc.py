@@ -238,6 +238,48 @@ def test_conv_epilogue_groupnorm_statistics(lib, case):
     assert float((out.permute(0, 3, 1, 2) - want).abs().max()) < 2e-4 * max(1.0, float(want.abs().max()))
 
 
+# ---- LayerNorm of a split-K linear's output rows, written by its reduce kernel (code transformer, keep_arch.py:423-440) ------
+LN_CASES = [
+    # name, rows, cin, cout, res, add2_rows
+    ("out_proj_256x512", 256, 512, 512, True, 0),
+    ("linear2_256x1024_512_pos", 256, 1024, 512, True, 256),
+    ("feat_emb_256x256_512_pos", 256, 256, 512, False, 256),
+    ("lockstep4_1024x512_pos", 1024, 512, 512, True, 256),
+    ("narrow_512x512_128", 512, 512, 128, False, 0),
+]
+
+
+@pytest.mark.parametrize("case", LN_CASES, ids=[c[0] for c in LN_CASES])
+def test_linear_with_layernorm_in_the_splitk_reduce(lib, case):
+    from test_gpu_ops import _p, _rc
+    name, rows, cin, cout, res, add2_rows = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) & 0xFFFF)
+    x = (torch.randn((rows, cin), generator=g) * 2 + 0.3).cuda()
+    wt = (torch.randn((cout, cin), generator=g) / math.sqrt(cin))
+    b = torch.randn((cout,), generator=g)
+    r = (torch.randn((rows, cout), generator=g) * 3).cuda() if res else None
+    lg, lb = (1 + 0.3 * torch.randn((cout,), generator=g)).cuda(), (0.3 * torch.randn((cout,), generator=g)).cuda()
+    pos = torch.randn((add2_rows, cout), generator=g).cuda() if add2_rows else None
+    out = torch.full((rows, cout), float("nan"), device="cuda")
+    ln_out, ln_out2 = torch.full_like(out, float("nan")), torch.full_like(out, float("nan"))
+    wt_h, b_h = wt.contiguous(), b.contiguous()
+    _rc(lib, lib.keepop_linear_ln(_p(x), rows, cin, _p(wt_h), _p(b_h), cout, _p(r), _p(lg), _p(lb), 1e-5, _p(pos), add2_rows,
+                                  _p(out), _p(ln_out), _p(ln_out2) if add2_rows else None, None))
+    torch.cuda.synchronize()
+    want = x.double() @ wt.double().cuda().t() + b.double().cuda()
+    if res:
+        want = want + r.double()
+    e_y = float((out.double() - want).abs().max())
+    assert e_y < 2e-4 * max(1.0, float(want.abs().max())), "%s: linear err %g" % (name, e_y)
+    # the normalisation is checked against torch on the very rows the kernel wrote
+    want_ln = torch.nn.functional.layer_norm(out.double(), (cout,), lg.double(), lb.double(), 1e-5)
+    e_ln = float((ln_out.double() - want_ln).abs().max())
+    assert e_ln < 5e-6 * max(1.0, float(want_ln.abs().max())), "%s: LayerNorm err %g" % (name, e_ln)
+    if add2_rows:
+        want2 = want_ln + pos.double().repeat(rows // add2_rows, 1)
+        assert float((ln_out2.double() - want2).abs().max()) < 5e-6 * max(1.0, float(want2.abs().max()))
+
+
 # ---- fused attention on tcgen05 (attn_tcgen05.cu): QK^T -> softmax -> PV in one kernel ------------------------------------
 def _swin_regions(L_side=32, shift=16, n_win=4):
     """region ids of GMFlow's shifted 2x2 windows on a 64x64 map (gmflow/transformer.py:19-43), as the engine builds them"""

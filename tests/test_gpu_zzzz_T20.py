@@ -80,9 +80,9 @@ def test_T20_batched_stages_match_reference(net, gold, clip):
         if bool(flips.any()):
             worst = float(margin[i][flips].max())
             _report("T20_free[tc3].first_flip", frame=i, flips=int(flips.sum()), worst_margin=worst)
-            # the logit noise grows along the recurrence (the reference's own fp32-vs-fp64 spread is 5.8e-3 after 3
-            # frames), so the tie threshold is the T = 3 one for early frames and widens later
-            assert worst < (2e-2 if i < 4 else 1e-1), "frame %d: code index flipped at a non-tie (margin %g)" % (i, worst)
+            # one near-tie threshold for every frame (the reference's own fp32-vs-fp64 logit spread is 5.8e-3 after
+            # 3 frames; the engine's measured first flip on this clip sits at a 2.7e-3 margin)
+            assert worst < 2e-2, "frame %d: code index flipped at a non-tie (margin %g)" % (i, worst)
             break
         a, b = out[:, i, :, ::8, ::8], ref_sub[:, i]
         e = float((a.clamp(-1, 1) - b.clamp(-1, 1)).abs().max())
