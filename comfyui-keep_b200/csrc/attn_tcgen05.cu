@@ -47,6 +47,15 @@ __device__ __forceinline__ void at_mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void at_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D TMA: `bytes` (multiple of 16) global -> shared, completion counted on the mbarrier
+__device__ __forceinline__ void at_tma_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void at_fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void at_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void at_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -98,6 +107,10 @@ struct AttnTcArgs {
     int win_side, wsz_log2, map_w, shift;
     // multi-head mode (heads > 1, plain rows only): batch z = b * heads + h, head h = columns [h * dh, (h + 1) * dh) of the rows
     int heads;
+    // K / V already converted by attn_pack_kv_kernel (null: the producers convert them, once per query tile): per batch z and
+    // key block j the byte image of one K stage (NCB x 64 rows x 128 B) and one V^T stage (2 x DH rows x 128 B) -- a query tile's
+    // stages then arrive by 1-D TMA instead of being re-derived from fp32 by every one of the window's Lq / 128 query tiles
+    const uint8_t* kpack; const uint8_t* vpack;
     long long* trace;   // debug (keepop_attn_trace): 8 x 40 clock64 stamps of CTA 0, or null
 };
 #define AT_TRACE(slot, idx)                                                                       \
@@ -183,8 +196,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
     if (threadIdx.x == 0) {
         at_mbar_init(Q_FULL, AT_PROD);
         for (int s = 0; s < 2; ++s) {
-            at_mbar_init(K_FULL(s), AT_PROD / 2); at_mbar_init(K_EMPTY(s), 1);     // K / V stages: one producer group each
-            at_mbar_init(V_FULL(s), AT_PROD / 2); at_mbar_init(V_EMPTY(s), 1);
+            // K / V stages: one producer group each, or (packed operands) one TMA-issuing thread
+            at_mbar_init(K_FULL(s), a.kpack ? 1 : AT_PROD / 2); at_mbar_init(K_EMPTY(s), 1);
+            at_mbar_init(V_FULL(s), a.kpack ? 1 : AT_PROD / 2); at_mbar_init(V_EMPTY(s), 1);
             at_mbar_init(S_FULL(s), 1); at_mbar_init(S_EMPTY(s), 128);
         }
         at_mbar_init(P_FULL, 128); at_mbar_init(P_EMPTY, 1); at_mbar_init(O_FULL, 1);
@@ -290,11 +304,34 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
             at_mbar_arrive(V_FULL(sv));
             if (gt == 0) AT_TRACE(1, j);                                // slot 1: V stage j produced
         };
+        if (a.kpack) {
+            // packed operands: thread 0 of group 0 streams the K stages of both passes, thread 0 of group 1 the V stages
+            if (gt == 0 && grp == 0) {
+                const uint8_t* src = a.kpack + (size_t)z * NKB * SM::K_STAGE;
+                for (int t = 0; t < 2 * NKB; ++t) {
+                    const int j = t < NKB ? t : t - NKB, st = t & 1;
+                    at_mbar_wait(K_EMPTY(st), (uint32_t)(((t >> 1) & 1) ^ 1));
+                    at_mbar_arrive_expect_tx(K_FULL(st), (uint32_t)SM::K_STAGE);
+                    at_tma_g2s(at_smem_u32(sK + st * SM::K_STAGE), src + (size_t)j * SM::K_STAGE, (uint32_t)SM::K_STAGE, K_FULL(st));
+                    AT_TRACE(0, t);
+                }
+            } else if (gt == 0) {
+                const uint8_t* src = a.vpack + (size_t)z * NKB * SM::V_STAGE;
+                for (int j = 0; j < NKB; ++j) {
+                    const int sv = j & 1;
+                    at_mbar_wait(V_EMPTY(sv), (uint32_t)(((j >> 1) & 1) ^ 1));
+                    at_mbar_arrive_expect_tx(V_FULL(sv), (uint32_t)SM::V_STAGE);
+                    at_tma_g2s(at_smem_u32(sV + sv * SM::V_STAGE), src + (size_t)j * SM::V_STAGE, (uint32_t)SM::V_STAGE, V_FULL(sv));
+                    AT_TRACE(1, j);
+                }
+            }
+        } else {
         for (int t = grp; t < NKB; t += 2) produce_K(t);              // pass A: alternate stages (NKB is even or the tail is group 0's)
         if (grp == 0) {
             for (int t = NKB; t < 2 * NKB; ++t) produce_K(t);         // pass B: every K block
         } else {
             for (int j = 0; j < NKB; ++j) produce_V(j);               // pass B: every V block
+        }
         }
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
@@ -472,23 +509,93 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const AttnTcArgs
     }
 }
 
+// K / V of every batch element -> the (hi, lo) fp16 stage images the attention kernel's MMAs read (same layout produce_K /
+// produce_V build in shared memory), once per key block instead of once per (key block, query tile).  One block = one
+// (batch z, key block j): the two images are formed in shared memory, then copied out with coalesced 16-byte stores.
+template <int DH>
+__global__ void __launch_bounds__(256) attn_pack_kv_kernel(const AttnTcArgs a, uint8_t* __restrict__ kpack, uint8_t* __restrict__ vpack) {
+    using SM = AttnSmem<DH>;
+    constexpr int NCB = SM::NCB;
+    extern __shared__ __align__(16) uint8_t pk_smem[];
+    uint8_t* pK = pk_smem;
+    uint8_t* pV = pk_smem + SM::K_STAGE;
+    pdl_wait();
+    if (threadIdx.x == 0) keep_stamp_here();
+    const int NKB = a.Lk / AT_KB;
+    const int z = blockIdx.x / NKB, j = blockIdx.x - z * NKB;
+    const int nwin = a.win_side > 0 ? a.win_side * a.win_side : 1;
+    const int img = a.win_side > 0 ? z / nwin : (a.heads > 1 ? z / a.heads : z);
+    const int win = a.win_side > 0 ? z - img * nwin : 0;
+    const int hoff = a.heads > 1 ? (z - img * a.heads) * DH : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* kb = a.k + (size_t)img * a.k_bs + hoff;
+    const float* vb = a.v + (size_t)img * a.v_bs + hoff;
+    constexpr int UPR = NCB * 4;
+    constexpr int NU = (AT_KB * UPR) / 256;                    // K units per thread (4 at DH = 128)
+    constexpr int NCOMBO = 2 * (DH / 8), NC = NCOMBO / 8;      // V combos per warp (4 at DH = 128)
+    float kv[NU][8], vv[NC][8];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+        const int u = threadIdx.x + i * 256;
+        const int row = u / UPR, cu = u - row * UPR;
+        ldg256(kb + (size_t)at_token(a, win, j * AT_KB + row) * a.ldk + (cu >> 2) * 32 + (cu & 3) * 8, kv[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = warp + i * 8, kbk = c / (DH / 8), dg = c - kbk * (DH / 8);
+        ldg256(vb + (size_t)at_token(a, win, j * AT_KB + kbk * 32 + lane) * a.ldv + dg * 8, vv[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+        const int u = threadIdx.x + i * 256;
+        const int row = u / UPR, cu = u - row * UPR, cb = cu >> 2, pl = cu & 3;
+        uint4 hi, lo;
+        at_split8(kv[i], hi, lo);
+        const int off = cb * (AT_KB * 128) + row * 128 + ((pl ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(pK + off) = hi;
+        *reinterpret_cast<uint4*>(pK + (off ^ 64)) = lo;
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = warp + i * 8, kbk = c / (DH / 8), dg = c - kbk * (DH / 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int row = dg * 8 + e;
+            const __half h = __float2half_rn(vv[i][e]);
+            const __half l = __float2half_rn(vv[i][e] - __half2float(h));
+            uint8_t* rowp = pV + kbk * (DH * 128) + row * 128;
+            *reinterpret_cast<__half*>(rowp + ((((lane >> 3)) ^ (row & 7)) << 4) + (lane & 7) * 2) = h;
+            *reinterpret_cast<__half*>(rowp + ((((lane >> 3) + 4) ^ (row & 7)) << 4) + (lane & 7) * 2) = l;
+        }
+    }
+    __syncthreads();
+    uint4* kd = reinterpret_cast<uint4*>(kpack + ((size_t)z * NKB + j) * SM::K_STAGE);
+    uint4* vd = reinterpret_cast<uint4*>(vpack + ((size_t)z * NKB + j) * SM::V_STAGE);
+    for (int i = threadIdx.x; i < SM::K_STAGE / 16; i += 256) kd[i] = reinterpret_cast<const uint4*>(pK)[i];
+    for (int i = threadIdx.x; i < SM::V_STAGE / 16; i += 256) vd[i] = reinterpret_cast<const uint4*>(pV)[i];
+}
+
 }  // namespace
 
 long long* g_attn_trace = nullptr;   // debug: device buffer of 8 x 40 clock64 stamps (keepop_attn_trace)
 
 bool attention_tc_eligible(int Lq, int Lk, int dh) { return (dh == 128 || dh == 64) && Lq % 128 == 0 && Lk % AT_KB == 0 && Lk <= 1024 && Lq > 0 && Lk > 0; }
 
+size_t attention_tc_pack_bytes(int nb, int Lk, int dh) { return (size_t)2 * nb * Lk * dh * 4; }
+
 void attention_tc_configure_device() {
     static unsigned long long configured = 0;
     if (first_use_on_current_device(&configured)) {
         CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<128>::TOTAL));
         CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::TOTAL));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_pack_kv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<128>::K_STAGE + AttnSmem<128>::V_STAGE));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_pack_kv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::K_STAGE + AttnSmem<64>::V_STAGE));
     }
 }
 
 void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int ldk, long long k_bs, const float* v, int ldv, long long v_bs,
                   float* out, int ldo, long long o_bs, int nb, int Lq, int Lk, int dh, float scale, const unsigned char* region, int n_win,
-                  cudaStream_t s, int win_side, int wsz, int map_w, int shift, int heads) {
+                  cudaStream_t s, int win_side, int wsz, int map_w, int shift, int heads, void* kv_pack) {
     KEEP_CHECK(attention_tc_eligible(Lq, Lk, dh), "attention_tc: unsupported shape (Lq %d, Lk %d, dh %d)", Lq, Lk, dh);
     KEEP_CHECK(!region || (Lq == Lk && n_win > 0), "attention_tc: the region mask needs Lq == Lk");
     KEEP_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 && o_bs % 8 == 0 &&
@@ -508,6 +615,17 @@ void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int l
         KEEP_CHECK(wsz > 0 && (wsz & (wsz - 1)) == 0 && (map_w & (map_w - 1)) == 0 && win_side * wsz == map_w && Lq == wsz * wsz && Lk == Lq &&
                        nb % (win_side * win_side) == 0, "attention_tc: bad window geometry");
         while ((1 << a.wsz_log2) < wsz) ++a.wsz_log2;
+    }
+    a.kpack = a.vpack = nullptr;
+    if (kv_pack) {   // convert K / V once per key block (attention_tc_pack_bytes(nb, Lk, dh) bytes of scratch), then stream the stages by TMA
+        KEEP_CHECK((reinterpret_cast<uintptr_t>(kv_pack) & 127) == 0, "attention_tc: the K / V pack scratch must be 128-byte aligned");
+        uint8_t* kp = (uint8_t*)kv_pack;
+        uint8_t* vp = kp + (size_t)nb * Lk * dh * 4;
+        const unsigned blocks = (unsigned)(nb * (Lk / AT_KB));
+        if (dh == 128) launch_k(attn_pack_kv_kernel<128>, dim3(blocks), dim3(256), (size_t)(AttnSmem<128>::K_STAGE + AttnSmem<128>::V_STAGE), s, a, kp, vp);
+        else launch_k(attn_pack_kv_kernel<64>, dim3(blocks), dim3(256), (size_t)(AttnSmem<64>::K_STAGE + AttnSmem<64>::V_STAGE), s, a, kp, vp);
+        CUDA_CHECK(cudaGetLastError());
+        a.kpack = kp; a.vpack = vp;
     }
     if (dh == 128) launch_k(attn_tc_kernel<128>, dim3((unsigned)(nb * (Lq / 128))), dim3(AT_THREADS), (size_t)AttnSmem<128>::TOTAL, s, a);
     else launch_k(attn_tc_kernel<64>, dim3((unsigned)(nb * (Lq / 128))), dim3(AT_THREADS), (size_t)AttnSmem<64>::TOTAL, s, a);

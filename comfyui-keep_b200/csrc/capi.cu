@@ -314,11 +314,26 @@ int keepop_layernorm(const float* x_dev, int rows, int c, const float* g_dev, co
     KEEP_API_END
 }
 
+// op hooks: K / V pack scratch for attention_tc (mode -1: KEEP_ATTN_PACK from the environment, default on; 0 / 1: forced by the tests)
+static int g_attn_pack_mode = -1;
+int keepop_attention_pack_mode(int mode) { g_attn_pack_mode = mode; return 0; }
+namespace {
+struct AttnPack {
+    void* p = nullptr;
+    AttnPack(int nb, int Lk, int dh) {
+        const bool on = g_attn_pack_mode >= 0 ? g_attn_pack_mode != 0 : !(getenv("KEEP_ATTN_PACK") && getenv("KEEP_ATTN_PACK")[0] == '0');
+        if (on) CUDA_CHECK(cudaMalloc(&p, attention_tc_pack_bytes(nb, Lk, dh)));
+    }
+    ~AttnPack() { cudaFree(p); }
+};
+}  // namespace
+
 int keepop_attention_fused(const float* q, const float* k, const float* v, int nb, int Lq, int Lk, int dh, float scale,
                            const unsigned char* region_dev, int n_win, float* out_dev, void* stream) {
     KEEP_API_BEGIN
+    AttnPack pk(nb, Lk, dh);
     attention_tc(q, dh, (long long)Lq * dh, k, dh, (long long)Lk * dh, v, dh, (long long)Lk * dh, out_dev, dh, (long long)Lq * dh, nb, Lq, Lk, dh,
-                 scale, region_dev, n_win, (cudaStream_t)stream);
+                 scale, region_dev, n_win, (cudaStream_t)stream, 0, 0, 0, 0, 1, pk.p);
     CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
     KEEP_API_END
@@ -330,8 +345,9 @@ int keepop_attention_fused_heads(const float* q, const float* k, const float* v,
                                  float* out_dev, void* stream) {
     KEEP_API_BEGIN
     const int D = heads * dh;
+    AttnPack pk(nb * heads, Lk, dh);
     attention_tc(q, D, (long long)Lq * D, k, D, (long long)Lk * D, v, D, (long long)Lk * D, out_dev, D, (long long)Lq * D, nb * heads, Lq, Lk, dh, scale,
-                 nullptr, 1, (cudaStream_t)stream, 0, 0, 0, 0, heads);
+                 nullptr, 1, (cudaStream_t)stream, 0, 0, 0, 0, heads, pk.p);
     CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
     KEEP_API_END
@@ -343,8 +359,9 @@ int keepop_attention_window(const float* q, const float* k, const float* v, int 
     KEEP_CHECK(wsz > 0 && map_w % wsz == 0, "keepop_attention_window: bad geometry");
     const int side = map_w / wsz, L = wsz * wsz;
     const long long img = (long long)map_w * map_w * dh;
+    AttnPack pk(nimg * side * side, L, dh);
     attention_tc(q, dh, img, k, dh, img, v, dh, img, out_dev, dh, img, nimg * side * side, L, L, dh, scale, region_dev, side * side,
-                 (cudaStream_t)stream, side, wsz, map_w, shift);
+                 (cudaStream_t)stream, side, wsz, map_w, shift, 1, pk.p);
     CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
     KEEP_API_END

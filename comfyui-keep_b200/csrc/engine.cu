@@ -1040,11 +1040,16 @@ void Engine::gm_layer(Tensor& src, const Tensor& tgt, const std::string& p, int 
         if (plan_) plan_->push_back("attention nb=" + std::to_string(nimg * 4) + " Lq=" + std::to_string(L) + " Lk=" + std::to_string(L) +
                                     " heads=1 dh=" + std::to_string(C) + " kernel=tcgen05_fused");
         O = talloc(nimg, H * Wd, 1, C, F32);
+        // a window's 8 query tiles share its K / V: convert them once (pack kernel) and stream the stages by TMA (KEEP_ATTN_PACK=0:
+        // every query tile converts them itself)
+        static const bool attn_pack = !(getenv("KEEP_ATTN_PACK") && getenv("KEEP_ATTN_PACK")[0] == '0');
+        void* pack = attn_pack ? ar_->alloc(attention_tc_pack_bytes(nimg * 4, L, C)) : nullptr;
         if (!ar_->dry()) {
             attention_tc(qp, ldq, (long long)H * Wd * ldq, kp, ldkv, (long long)H * Wd * ldkv, vp, ldkv, (long long)H * Wd * ldkv, O.f(), C,
-                         (long long)H * Wd * C, nimg * 4, L, L, C, 1.0f / sqrtf((float)C), shift ? region8_ : nullptr, 4, s_, k, 32, Wd, sh);
-            launches_ += 1;
+                         (long long)H * Wd * C, nimg * 4, L, L, C, 1.0f / sqrtf((float)C), shift ? region8_ : nullptr, 4, s_, k, 32, Wd, sh, 1, pack);
+            launches_ += pack ? 2 : 1;
         }
+        if (pack) ar_->free(pack);
         tfree(q);
         if (kk.p) tfree(kk);
         if (v.p) tfree(v);

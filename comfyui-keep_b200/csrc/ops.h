@@ -82,7 +82,11 @@ bool attention_tc_eligible(int Lq, int Lk, int dh);
 void attention_tc_configure_device();
 void attention_tc(const float* q, int ldq, long long q_bs, const float* k, int ldk, long long k_bs, const float* v, int ldv, long long v_bs,
                   float* out, int ldo, long long o_bs, int nb, int Lq, int Lk, int dh, float scale, const unsigned char* region, int n_win,
-                  cudaStream_t s, int win_side = 0, int wsz = 0, int map_w = 0, int shift = 0, int heads = 1);
+                  cudaStream_t s, int win_side = 0, int wsz = 0, int map_w = 0, int shift = 0, int heads = 1, void* kv_pack = nullptr);
+// kv_pack != null (attention_tc_pack_bytes(nb, Lk, dh) bytes, 128-byte aligned): K / V are converted to the kernel's (hi, lo) fp16
+// stage images ONCE by a pack kernel and stream into the query tiles by 1-D TMA -- otherwise each of a batch element's Lq / 128
+// query tiles converts the whole K and V itself (worth it from ~4 query tiles per batch element on)
+size_t attention_tc_pack_bytes(int nb, int Lk, int dh);
 // (heads > 1: nb = batches * heads, head h of batch b reads / writes columns [h * dh, (h + 1) * dh) of batch b's rows)
 // (win_side > 0: swin window mode -- q / k / v / out are whole (map_w x map_w)-token maps, *_bs = image strides, nb = images *
 //  win_side^2, window partition + cyclic shift + merge are index math inside the kernel; wsz = window side, Lq = Lk = wsz^2)

@@ -91,6 +91,7 @@ def load_library():
     lib.keep_debug_read.restype = ctypes.c_longlong
     lib.keepop_conv2d.argtypes = [ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp, vp]
     lib.keepop_conv2d_gn.argtypes = [ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp]
+    lib.keepop_attention_pack_mode.argtypes = [ci]
     lib.keepop_linear_ln.argtypes = [vp, ci, ci, vp, vp, ci, vp, vp, vp, ctypes.c_float, vp, ci, vp, vp, vp, vp]
     lib.keepop_tc_trace.argtypes = [vp]
     lib.keepop_groupnorm_affine.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp]

@@ -148,6 +148,9 @@ int keepop_kernel_stamps(unsigned long long* dev_buf);
 int keepop_launch_log(int enable);
 int keepop_launch_log_dump(const char* path);
 int keepop_tc_trace(long long* dev_buf_160_i64); /* debug: per-role clock64 timeline of CTA 0 of the tcgen05 kernel */
+/* tests: 1 / 0 = the attention hooks below pre-convert K / V with the pack kernel (TMA-fed stages) or let every query tile convert
+ * them itself; -1 = follow KEEP_ATTN_PACK (default on) */
+int keepop_attention_pack_mode(int mode);
 int keepop_attn_trace(long long* dev_buf_320_i64); /* debug: the same for the fused attention kernel (8 roles x 40 stamps) */
 int keepop_groupnorm_affine(const float* x_dev, int n, int hw, int c, int groups, float eps, const float* gamma_dev,
                             const float* beta_dev, float* scale_dev, float* shift_dev, void* stream);

@@ -294,8 +294,17 @@ def _swin_regions(L_side=32, shift=16, n_win=4):
     return reg
 
 
+@pytest.fixture(params=[1, 0], ids=["kvpack", "convert_per_tile"])
+def attn_pack(lib, request):
+    """both operand paths of the fused attention kernel: K / V converted once by the pack kernel and streamed by TMA, or
+    converted by every query tile's producer warps"""
+    lib.keepop_attention_pack_mode(request.param)
+    yield request.param
+    lib.keepop_attention_pack_mode(-1)
+
+
 @pytest.mark.parametrize("nb,Lq,Lk,masked", [(8, 1024, 1024, False), (8, 1024, 1024, True), (3, 256, 512, False), (2, 128, 64, False)])
-def test_fused_attention_matches_torch(lib, nb, Lq, Lk, masked):
+def test_fused_attention_matches_torch(lib, attn_pack, nb, Lq, Lk, masked):
     """softmax(q k^T / sqrt(d) + mask) v against torch fp32 (TF32 off); the masked case is GMFlow's shifted-window layer (mask
     values 0 / -100).  Bar 5e-5 absolute on outputs of O(1): the split-precision operands are fp32-grade, what remains is the
     tensor core's fp32 accumulation over 1024 keys (192 accumulating MMAs per output; measured 2.1e-5 at 1024 keys, < 1e-5 at
@@ -320,7 +329,7 @@ def test_fused_attention_matches_torch(lib, nb, Lq, Lk, masked):
 
 
 @pytest.mark.parametrize("shift", [0, 16])
-def test_fused_window_attention_matches_torch(lib, shift):
+def test_fused_window_attention_matches_torch(lib, attn_pack, shift):
     """GMFlow's swin attention block (gmflow/transformer.py:78-103) with the partition / cyclic shift / merge done as index
     math inside the fused kernel: roll(-shift) -> split into 2x2 windows of 32x32 tokens -> masked attention -> merge ->
     roll(+shift), restated with torch ops."""
@@ -352,7 +361,7 @@ def test_fused_window_attention_matches_torch(lib, shift):
 
 
 @pytest.mark.parametrize("nb,L,heads,dh", [(1, 256, 8, 64), (3, 256, 8, 64), (2, 128, 2, 128)])
-def test_fused_multihead_attention_matches_torch(lib, nb, L, heads, dh):
+def test_fused_multihead_attention_matches_torch(lib, attn_pack, nb, L, heads, dh):
     """nn.MultiheadAttention's core on packed (tokens, heads * dh) operands (keep_arch.py:431-432: 8 x 64 over 256 tokens)."""
     from test_gpu_ops import _p, _rc
     g = torch.Generator(device="cpu").manual_seed(31)
