@@ -8,7 +8,7 @@
 //   warp  4     MMA issuer    one thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and tcgen05.commit
 //   warp  8     weight loader one thread streams pre-packed fp16 weight panels with 1-D TMA (cp.async.bulk), or
 //                             parks the layer's whole panel set in shared memory once when it fits
-//   16 warps    A producers   (two groups of 8 on alternate stages) coalesced NHWC loads of the (16+2)x(8+2) input halo,
+//   14 warps    A producers   (1x1 layers: two groups of 7 on alternate stages) coalesced NHWC loads of the (16+2)x(8+2) input halo,
 //                             GroupNorm/InstanceNorm apply + swish/ReLU in registers, fp16 (hi, lo) split,
 //                             st.shared into the UMMA SWIZZLE_128B K-major layout
 //
@@ -42,11 +42,18 @@ namespace {
 // Warp roles are laid out by SM sub-partition (warp % 4 picks the scheduler).  The MMA issuer needs ~90 instructions per
 // filter tap; sharing a scheduler with four busy producer warps stretched that to 350-550 cycles per tap, more than the
 // MMAs themselves take (measured: 88-105 clk per N=64 MMA in the kernel vs 55-64 in isolation, tools/ubench/umma_rate.cu).
-// So sub-partition 0 holds only the MMA issuer, the weight loader and one epilogue warp; the 15 producer warps live on
-// sub-partitions 1-3 next to the other three epilogue warps (tcgen05.ld ties epilogue warp w to TMEM lanes 32*(w%4)...).
-constexpr int kThreads = 704;                          // 22 warps
+// So sub-partition 0 holds the MMA issuer, the weight loader, one epilogue warp and only two producer warps (12, 16); the other
+// twelve producer warps live on sub-partitions 1-3 next to the other three epilogue warps (tcgen05.ld ties epilogue warp w to
+// TMEM lanes 32*(w%4)...).
+// 640 threads = 20 warps: the register file gives 65 536 / 640 -> 96 registers per thread.  With 22 warps (704 threads, 16
+// producer warps) ptxas is capped at 80 and every variant spilled a little; 14 producer warps without spills are faster
+// (measured 170.9 -> 175.8 frames/s; 64->64 3x3 @512^2 tile 6.9K -> 6.3K cycles; -DKEEP_TC_THREADS=704 restores the old shape)
+#ifndef KEEP_TC_THREADS
+#define KEEP_TC_THREADS 640
+#endif
+constexpr int kThreads = KEEP_TC_THREADS;
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 8;
-constexpr int kProdThreads = 512;                      // producers: the 16 warps >= 5 other than the loader (8)
+constexpr int kProdThreads = kThreads - 6 * 32;        // producers: the warps >= 5 other than the loader (8)
 constexpr int MAX_SA = 8, MAX_SB = 8;  // barrier slots (actual pipeline depths come from the launch arguments)
 // channels per A stage: 64 with fp16 operands (4 MMA K-steps of 16); 32 in the split-precision mode, whose 128-byte rows
 // hold [hi 32 ch | lo 32 ch] side by side (2 K-steps each), so a stage and a weight panel have the same geometry in both
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int CBK = cb_of(PASSES);                   // channels per A stage / weight panel
     constexpr int UPP = CBK / 8;                         // 8-channel producer units per pixel
-    // Producer groups: in the split-precision mode the 16 producer warps work as TWO groups of 8 that take alternate stages.
+    // Producer groups: in the split-precision mode the 14 producer warps work as TWO groups of 7 that take alternate stages.
     // A stage's critical path is load latency + convert + proxy fence (the fence -- MEMBAR.ALL.CTA -- also waits for any
     // prefetched global load of the same thread, which is why register double-buffering inside one thread bought nothing);
     // with two groups one stage's latency hides behind the other's conversion.
@@ -713,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
                     }
                 }
                 tmem_ld_wait();
-                if (stacked) {   // (warp-uniform) second half of the accumulator: the Ah * Wl term
+                if (stacked) {   // (warp-uniform) second half of the accumulator: the Ah * Wl term (both loads behind one wait: measured slower)
                     uint32_t r2[16];
                     tmem_ld16(t0 + 64u + (uint32_t)j, r2);
                     tmem_ld_wait();
