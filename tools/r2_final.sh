@@ -18,11 +18,11 @@ KEEP_DEBUG_SKIP_FLOW=1 timeout 300 python tools/timeline.py --frames 4 --out gpu
 KEEP_NO_SIDE=1 timeout 300 python tools/timeline.py --frames 5 --out gpurun_out/r2_final_tl_inline > gpurun_out/r2_final_timeline_gmflow_inline_T5.txt 2>&1
 grep -A12 "== last frame" gpurun_out/r2_final_timeline_noflow_T4.txt | head -16
 CMD="python tools/run_clip.py --frames 2 --clips 1 --mode tc3"
-timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:conv_tc_kernel<\(int\)3, \(bool\)0, \(int\)3, \(bool\)0>" -s 7 -c 8 \
+timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:conv_tc_kernel<\(int\)3, \(bool\)0, \(int\)3, \(bool\)0>" -s 11 -c 16 \
     -f -o gpurun_out/r2_ncu_full_conv3x3 $CMD > gpurun_out/r2_ncu_full_conv3x3.log 2>&1
 if [ -f gpurun_out/r2_ncu_full_conv3x3.ncu-rep ]; then
   ncu -i gpurun_out/r2_ncu_full_conv3x3.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_conv3x3.csv 2>/dev/null
-  python tools/ncu_summary.py gpurun_out/r2_ncu_full_conv3x3.csv "$CMD" "conv_tc_kernel<3,false,3,false>, 8 launches after the first 7, --set full" > gpurun_out/r2_ncu_full_conv3x3.json
+  python tools/ncu_summary.py gpurun_out/r2_ncu_full_conv3x3.csv "$CMD" "conv_tc_kernel<3,false,3,false>, 16 launches after the first 11, --set full" > gpurun_out/r2_ncu_full_conv3x3.json
   python - <<'P'
 import json
 d=json.load(open('gpurun_out/r2_ncu_full_conv3x3.json'))
