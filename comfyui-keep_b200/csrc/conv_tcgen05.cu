@@ -51,9 +51,11 @@ namespace {
 #ifndef KEEP_TC_THREADS
 #define KEEP_TC_THREADS 640
 #endif
-constexpr int kThreads = KEEP_TC_THREADS;
+#ifndef KEEP_TC_THREADS_1X1
+#define KEEP_TC_THREADS_1X1 KEEP_TC_THREADS            // (1x1 / linear variants can be built with their own CTA size: A/B)
+#endif
+constexpr int tc_threads(int win) { return win == 1 ? KEEP_TC_THREADS_1X1 : KEEP_TC_THREADS; }
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 8;
-constexpr int kProdThreads = kThreads - 6 * 32;        // producers: the warps >= 5 other than the loader (8)
 constexpr int MAX_SA = 8, MAX_SB = 8;  // barrier slots (actual pipeline depths come from the launch arguments)
 // channels per A stage: 64 with fp16 operands (4 MMA K-steps of 16); 32 in the split-precision mode, whose 128-byte rows
 // hold [hi 32 ch | lo 32 ch] side by side (2 K-steps each), so a stage and a weight panel have the same geometry in both
@@ -179,7 +181,7 @@ __device__ __noinline__ float act_slow(float v, int act) { return apply_act(v, a
 // range, 16 mantissa bits per pair instead of 22.  For layers whose input is a raw (un-normalised) feature map of
 // unbounded magnitude: fp16 overflows to inf beyond 65504 (KEEP_FLAG_TC_WIDE).
 template <int PASSES, bool IN_F16, int WIN, bool A_BF16 = false>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a) {
+__global__ void __launch_bounds__(tc_threads(WIN), 1) conv_tc_kernel(const TcConvArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms are 1024-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcConvArgs a
     // prefetched global load of the same thread, which is why register double-buffering inside one thread bought nothing);
     // with two groups one stage's latency hides behind the other's conversion.
     constexpr int NGROUPS = (PASSES == 3 && WIN == 1) ? 2 : 1;   // (3x3 layers: one group -- MAXIT 3 at 83 % fill and spills cost more than the overlap gives)
+    constexpr int kProdThreads = tc_threads(WIN) - 6 * 32;   // producers: the warps >= 5 other than the loader (8)
     constexpr int GT = kProdThreads / NGROUPS;           // threads per group = arrivals per stage
     constexpr int PPI = GT / UPP;                        // pixels per producer iteration
     constexpr int NPIX = WIN == 3 ? 18 * 10 : (WIN == 2 ? 17 * 9 : 128);   // pixels per stage (halo tile, or the 128 of a 1x1)
@@ -1281,11 +1284,11 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     const bool wide = a.a_wide && passes == 3 && !f16;
     const Kern kern = wide ? kerns_wide[t.win - 1] : kerns[passes == 3 ? 1 : 0][f16 ? 1 : 0][t.win - 1];
     if (t.cluster_k) {   // one work item per CTA, the splitk CTAs of a tile form one cluster
-        launch_k_cluster(kern, dim3((unsigned)total), dim3(kThreads), smem, s, splitk, t);
+        launch_k_cluster(kern, dim3((unsigned)total), dim3(tc_threads(t.win)), smem, s, splitk, t);
         CUDA_CHECK(cudaGetLastError());
         return 1;
     }
-    launch_k(kern, dim3(grid), dim3(kThreads), smem, s, t);
+    launch_k(kern, dim3(grid), dim3(tc_threads(t.win)), smem, s, t);
     CUDA_CHECK(cudaGetLastError());
     if (a.no_reduce) {
         KEEP_CHECK(splitk == a.splitk && !a.bias && !a.res && a.act == ACT_NONE, "conv2d_tc: no_reduce needs the K split as requested and a plain epilogue");
