@@ -29,6 +29,9 @@
 #ifndef KEEP_PDL_CONV_TRIGGER
 #define KEEP_PDL_CONV_TRIGGER 0
 #endif
+#ifndef KEEP_TC_PARTIAL32
+#define KEEP_TC_PARTIAL32 1   // split-K partial epilogue: 32 columns per TMEM round trip
+#endif
 #ifndef KEEP_TC_STACKED
 #define KEEP_TC_STACKED 1   // stacked [Wh ; Wl] weight panels for 64-wide N tiles in the split-precision mode (0: three N = 64 MMAs per K step)
 #endif
@@ -696,6 +699,31 @@ __global__ void __launch_bounds__(tc_threads(WIN), 1) conv_tc_kernel(const TcCon
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         *reinterpret_cast<uint4*>(dstrow + ((((j >> 2) + e) ^ (row & 7)) << 4)) = make_uint4(rr[4 * e], rr[4 * e + 1], rr[4 * e + 2], rr[4 * e + 3]);
+                }
+                tc_fence_before();
+                mbar_arrive(ACC_EMPTY(as));
+                if (threadIdx.x == 0) { TC_TRACE(7, trace_e); ++trace_e; }
+                if (++as == 2) { as = 0; pacc ^= 1; }
+                continue;
+            }
+            if (KEEP_TC_PARTIAL32 && partial_out && !stacked) {
+                // split-K partial tile: a plain TMEM -> partial-buffer copy, 32 columns (two loads in flight) per round trip --
+                // on the small layers of the per-frame chain the epilogue follows the CTA's only K loop, so its TMEM latency
+                // is on the layer's critical path
+                for (int j = 0; j < a.bn; j += 32) {
+                    uint32_t rr[32];
+                    __syncwarp();
+                    tmem_ld16(t0 + (uint32_t)j, rr);
+                    tmem_ld16(t0 + (uint32_t)j + 16u, rr + 16);
+                    tmem_ld_wait();
+                    const int nn = n0 + j;
+                    if (ok && nn < a.cout) {
+                        float* o = a.partial + (size_t)ks * a.M * a.cout + (size_t)pixel * a.cout + nn;
+                        const float* v = reinterpret_cast<const float*>(rr);
+                        stg256(o, v);
+                        stg256(o + 8, v + 8);
+                        if (nn + 16 < a.cout) { stg256(o + 16, v + 16); stg256(o + 24, v + 24); }
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(ACC_EMPTY(as));
