@@ -8,5 +8,5 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
 tail -c 1200 gpurun_out/r2_bench_n$N.json; tail -3 gpurun_out/r2_bench_n$N.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --config 5 --batch-clips 4 --steps 2 --warmup 3 > gpurun_out/r2_bench_config5_n$N.json 2> gpurun_out/r2_bench_config5_n$N.err
 cut -c1-400 gpurun_out/r2_bench_config5_n$N.json; tail -3 gpurun_out/r2_bench_config5_n$N.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus $N --steps 1 --warmup 1 > gpurun_out/r2_bench_reference_n$N.json 2> gpurun_out/r2_bench_reference_n$N.err
-cut -c1-300 gpurun_out/r2_bench_reference_n$N.json
+[ -n "$SKIP_REF" ] || python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus $N --steps 1 --warmup 1 > gpurun_out/r2_bench_reference_n$N.json 2> gpurun_out/r2_bench_reference_n$N.err
+[ -n "$SKIP_REF" ] || cut -c1-300 gpurun_out/r2_bench_reference_n$N.json
