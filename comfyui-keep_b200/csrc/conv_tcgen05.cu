@@ -32,6 +32,9 @@
 #ifndef KEEP_TC_PARTIAL32
 #define KEEP_TC_PARTIAL32 1   // split-K partial epilogue: 32 columns per TMEM round trip
 #endif
+#ifndef KEEP_TC_GROUPS_3X3
+#define KEEP_TC_GROUPS_3X3 1   // producer groups on 3x3 layers (split-precision mode): 2 = alternate stages, 1 = all warps on one stage
+#endif
 #ifndef KEEP_TC_STACKED
 #define KEEP_TC_STACKED 1   // stacked [Wh ; Wl] weight panels for 64-wide N tiles in the split-precision mode (0: three N = 64 MMAs per K step)
 #endif
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(tc_threads(WIN), 1) conv_tc_kernel(const TcCon
     // A stage's critical path is load latency + convert + proxy fence (the fence -- MEMBAR.ALL.CTA -- also waits for any
     // prefetched global load of the same thread, which is why register double-buffering inside one thread bought nothing);
     // with two groups one stage's latency hides behind the other's conversion.
-    constexpr int NGROUPS = (PASSES == 3 && WIN == 1) ? 2 : 1;   // (3x3 layers: one group -- MAXIT 3 at 83 % fill and spills cost more than the overlap gives)
+    constexpr int NGROUPS = (PASSES == 3 && (WIN == 1 || KEEP_TC_GROUPS_3X3 == 2)) ? 2 : 1;   // (3x3 layers: one group -- MAXIT 3 at 83 % fill and spills cost more than the overlap gives)
     constexpr int kProdThreads = tc_threads(WIN) - 6 * 32;   // producers: the warps >= 5 other than the loader (8)
     constexpr int GT = kProdThreads / NGROUPS;           // threads per group = arrivals per stage
     constexpr int PPI = GT / UPP;                        // pixels per producer iteration
