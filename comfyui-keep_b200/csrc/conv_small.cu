@@ -19,7 +19,13 @@ __global__ void __launch_bounds__(256) conv_cin3_kernel(const void* __restrict__
     pdl_prologue();
     constexpr int K = KS * KS * 3;
     __shared__ __align__(16) float sw[K * 64];
-    for (int i = threadIdx.x; i < K * 64; i += 256) sw[i] = wt[i];
+    // weights in shared memory as [k][q][grp][4]: the four channel groups' q-th float4 are 64 contiguous bytes, so the
+    // LDS.128 of a quarter-warp (2 pixel groups x 4 channel groups) hits 16 distinct banks (the plain [k][64] layout put groups
+    // 0 / 2 and 1 / 3 on the same banks: a 2-way conflict on every weight load -- ncu: 3.7M conflicts per frame)
+    for (int i = threadIdx.x; i < K * 64; i += 256) {
+        const int k = i >> 6, ch = i & 63;
+        sw[k * 64 + ((ch & 15) >> 2) * 16 + (ch >> 4) * 4 + (ch & 3)] = wt[i];
+    }
     __syncthreads();
     const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long pix = gid >> 2;
@@ -40,12 +46,12 @@ __global__ void __launch_bounds__(256) conv_cin3_kernel(const void* __restrict__
             if (ix < 0 || ix >= w) continue;
             const size_t base = (((size_t)img * h + iy) * w + ix) * 3;
             const float x0 = ld1(in, in_dt, base), x1 = ld1(in, in_dt, base + 1), x2 = ld1(in, in_dt, base + 2);
-            const float4* w0 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 0) * 64 + grp * 16);
-            const float4* w1 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 1) * 64 + grp * 16);
-            const float4* w2 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 2) * 64 + grp * 16);
+            const float4* w0 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 0) * 64 + grp * 4);
+            const float4* w1 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 1) * 64 + grp * 4);
+            const float4* w2 = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + 2) * 64 + grp * 4);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 a = w0[q], b = w1[q], c = w2[q];
+                const float4 a = w0[q * 4], b = w1[q * 4], c = w2[q * 4];
                 acc[4 * q + 0] = fmaf(x0, a.x, fmaf(x1, b.x, fmaf(x2, c.x, acc[4 * q + 0])));
                 acc[4 * q + 1] = fmaf(x0, a.y, fmaf(x1, b.y, fmaf(x2, c.y, acc[4 * q + 1])));
                 acc[4 * q + 2] = fmaf(x0, a.z, fmaf(x1, b.z, fmaf(x2, c.z, acc[4 * q + 2])));
@@ -75,7 +81,13 @@ __global__ void __launch_bounds__(256) conv_cin3_px4_kernel(const void* __restri
     pdl_prologue();
     constexpr int K = KS * KS * 3, PX = 4, SPAN = (PX - 1) * STRIDE + KS;
     __shared__ __align__(16) float sw[K * 64];
-    for (int i = threadIdx.x; i < K * 64; i += 256) sw[i] = wt[i];
+    // weights in shared memory as [k][q][grp][4]: the four channel groups' q-th float4 are 64 contiguous bytes, so the
+    // LDS.128 of a quarter-warp (2 pixel groups x 4 channel groups) hits 16 distinct banks (the plain [k][64] layout put groups
+    // 0 / 2 and 1 / 3 on the same banks: a 2-way conflict on every weight load -- ncu: 3.7M conflicts per frame)
+    for (int i = threadIdx.x; i < K * 64; i += 256) {
+        const int k = i >> 6, ch = i & 63;
+        sw[k * 64 + ((ch & 15) >> 2) * 16 + (ch >> 4) * 4 + (ch & 3)] = wt[i];
+    }
     __syncthreads();
     const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long pg = gid >> 2;                      // group of 4 output pixels
@@ -106,8 +118,8 @@ __global__ void __launch_bounds__(256) conv_cin3_px4_kernel(const void* __restri
         for (int kx = 0; kx < KS; ++kx) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + c) * 64 + grp * 16);
-                const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * KS + kx) * 3 + c) * 64 + grp * 4);
+                const float4 w0 = wp[0], w1 = wp[4], w2 = wp[8], w3 = wp[12];
 #pragma unroll
                 for (int p = 0; p < PX; ++p) {
                     const float x = xin[(p * STRIDE + kx) * 3 + c];
@@ -138,10 +150,13 @@ __global__ void __launch_bounds__(256) conv_cin3_px4_kernel(const void* __restri
     }
 }
 
-// ---- head: 3x3 s1 p1, Cin % 16 == 0, Cout <= 4.  Block = 32x8 output pixels, one thread per pixel; the input halo is
-// staged through shared memory 16 channels at a time with the GroupNorm affine applied; weights [9][cin][4] in smem.
-constexpr int HT_W = 32, HT_H = 8, HC = 16, HPITCH = 20;   // channel pitch 20 floats: conflict-free float4 reads
-__global__ void __launch_bounds__(256) conv_cout4_kernel(const void* __restrict__ in, int in_dt, int n, int h, int w, int cin,
+// ---- head: 3x3 s1 p1, Cin % 16 == 0, Cout <= 4.  Block = 32x32 output pixels, thread = 4 pixels of one column (rows ly, ly + 8,
+// ly + 16, ly + 24): every weight float4 fetched from shared memory (warp-uniform broadcast) feeds 4 pixels -- the first version
+// (one pixel per thread: 5 LDS.128 per 16 FMA) was bound by the shared-memory pipe (ncu: mio_throttle 5.2 stalls per issue,
+// 81 us per 512^2 frame).  The input halo is staged 8 channels at a time with the GroupNorm affine applied; pixel pitch 12
+// floats: the float4 reads of 8 consecutive pixels hit 8 distinct bank quads.  Weights [9][cin][4] in shared memory.
+constexpr int HT_W = 32, HT_H = 32, HROWS = 8, HPX = HT_H / HROWS, HC = 8, HPITCH = 12;
+__global__ void __launch_bounds__(256, 2) conv_cout4_kernel(const void* __restrict__ in, int in_dt, int n, int h, int w, int cin,
                                                          const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
                                                          const float* __restrict__ wt /*[9*cin][cout]*/, const float* __restrict__ bias,
                                                          int cout, float* __restrict__ out) {
@@ -158,46 +173,73 @@ __global__ void __launch_bounds__(256) conv_cout4_kernel(const void* __restrict_
     const int t = blockIdx.x - img * tiles_x * tiles_y;
     const int ty0 = (t / tiles_x) * HT_H, tx0 = (t % tiles_x) * HT_W;
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[HPX][4];
+#pragma unroll
+    for (int j = 0; j < HPX; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
     constexpr int HALO = (HT_H + 2) * (HT_W + 2);
     for (int c0 = 0; c0 < cin; c0 += HC) {
         __syncthreads();
-        for (int u = threadIdx.x; u < HALO * (HC / 4); u += 256) {
-            const int p = u >> 2, q = u & 3;
+        // every global load of the stage in flight before the first is used (a rolled loop paid one L2 round trip per iteration:
+        // ~7 of the 8.8 us a stage took)
+        constexpr int NU = (HALO * (HC / 4) + 255) / 256;
+        float4 v[NU];
+        unsigned inside = 0;                // bit i: unit i lies inside the image (zero padding is applied AFTER the normalisation)
+        const int q = threadIdx.x & 1;      // (256 is even: a thread's units all have the same channel quad)
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            const int u = threadIdx.x + i * 256, p = u >> 1;
             const int hy = p / (HT_W + 2), hx = p - hy * (HT_W + 2);
             const int iy = ty0 + hy - 1, ix = tx0 + hx - 1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (u < HALO * (HC / 4) && iy >= 0 && iy < h && ix >= 0 && ix < w) {
                 const size_t off = (((size_t)img * h + iy) * w + ix) * cin + c0 + q * 4;
-                v = in_dt == F32 ? ld4(reinterpret_cast<const float*>(in), off) : ld4(reinterpret_cast<const __half*>(in), off);
-                if (pre_scale) {
-                    const float4 s = *reinterpret_cast<const float4*>(pre_scale + (size_t)img * cin + c0 + q * 4);
-                    const float4 b = *reinterpret_cast<const float4*>(pre_shift + (size_t)img * cin + c0 + q * 4);
-                    v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
-                }
+                v[i] = in_dt == F32 ? ld4(reinterpret_cast<const float*>(in), off) : ld4(reinterpret_cast<const __half*>(in), off);
+                inside |= 1u << i;
             }
-            *reinterpret_cast<float4*>(sx + p * HPITCH + q * 4) = v;
+        }
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pre_scale) {
+            sc = *reinterpret_cast<const float4*>(pre_scale + (size_t)img * cin + c0 + q * 4);
+            sh = *reinterpret_cast<const float4*>(pre_shift + (size_t)img * cin + c0 + q * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            const int u = threadIdx.x + i * 256;
+            if (u >= HALO * (HC / 4)) continue;
+            float4 o = v[i];
+            if (pre_scale && ((inside >> i) & 1u)) {
+                o.x = fmaf(o.x, sc.x, sh.x); o.y = fmaf(o.y, sc.y, sh.y); o.z = fmaf(o.z, sc.z, sh.z); o.w = fmaf(o.w, sc.w, sh.w);
+            }
+            *reinterpret_cast<float4*>(sx + (u >> 1) * HPITCH + q * 4) = o;
         }
         __syncthreads();
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-            const float* xp = sx + ((ly + tap / 3) * (HT_W + 2) + lx + tap % 3) * HPITCH;
             const float4* wp = reinterpret_cast<const float4*>(sw + (tap * cin + c0) * 4);
 #pragma unroll
             for (int q = 0; q < HC / 4; ++q) {
-                const float4 x = *reinterpret_cast<const float4*>(xp + q * 4);
                 const float4 w0 = wp[q * 4 + 0], w1 = wp[q * 4 + 1], w2 = wp[q * 4 + 2], w3 = wp[q * 4 + 3];
-                acc[0] = fmaf(x.x, w0.x, fmaf(x.y, w1.x, fmaf(x.z, w2.x, fmaf(x.w, w3.x, acc[0]))));
-                acc[1] = fmaf(x.x, w0.y, fmaf(x.y, w1.y, fmaf(x.z, w2.y, fmaf(x.w, w3.y, acc[1]))));
-                acc[2] = fmaf(x.x, w0.z, fmaf(x.y, w1.z, fmaf(x.z, w2.z, fmaf(x.w, w3.z, acc[2]))));
-                acc[3] = fmaf(x.x, w0.w, fmaf(x.y, w1.w, fmaf(x.z, w2.w, fmaf(x.w, w3.w, acc[3]))));
+#pragma unroll
+                for (int j = 0; j < HPX; ++j) {
+                    const float4 x = *reinterpret_cast<const float4*>(sx + ((ly + j * HROWS + tap / 3) * (HT_W + 2) + lx + tap % 3) * HPITCH + q * 4);
+                    acc[j][0] = fmaf(x.x, w0.x, fmaf(x.y, w1.x, fmaf(x.z, w2.x, fmaf(x.w, w3.x, acc[j][0]))));
+                    acc[j][1] = fmaf(x.x, w0.y, fmaf(x.y, w1.y, fmaf(x.z, w2.y, fmaf(x.w, w3.y, acc[j][1]))));
+                    acc[j][2] = fmaf(x.x, w0.z, fmaf(x.y, w1.z, fmaf(x.z, w2.z, fmaf(x.w, w3.z, acc[j][2]))));
+                    acc[j][3] = fmaf(x.x, w0.w, fmaf(x.y, w1.w, fmaf(x.z, w2.w, fmaf(x.w, w3.w, acc[j][3]))));
+                }
             }
         }
     }
-    const int oy = ty0 + ly, ox = tx0 + lx;
-    if (oy < h && ox < w) {
-        const size_t o = (((size_t)img * h + oy) * w + ox) * cout;
-        for (int c = 0; c < cout; ++c) out[o + c] = acc[c] + (bias ? bias[c] : 0.0f);
+    const int ox = tx0 + lx;
+#pragma unroll
+    for (int j = 0; j < HPX; ++j) {
+        const int oy = ty0 + ly + j * HROWS;
+        if (oy < h && ox < w) {
+            const size_t o = (((size_t)img * h + oy) * w + ox) * cout;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)      // (compile-time indices: a run-time `c < cout` loop index would push acc[][] into local memory)
+                if (c < cout) out[o + c] = acc[j][c] + (bias ? bias[c] : 0.0f);
+        }
     }
 }
 }  // namespace
