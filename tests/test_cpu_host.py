@@ -268,6 +268,31 @@ def test_plan_per_frame_chain_and_kernel_choice(keep_mod, lib, state_dict, tmp_p
     assert {k: v - (12 if k == "attention" else 0) for k, v in k2.items() if k != "gemm"} == dict(kf) and not any("tcgen05" in l for l in lf)
 
 
+def test_plan_norms_ride_on_the_producing_kernels(keep_mod, lib, state_dict, tmp_path):
+    """GroupNorm statistics come from the producing conv / split-K reduce ('gnstats=1'), split-K layers with few slots also
+    finalize them inside the reduce ('gnstats=2' + 'groupnorm ... fused=2': no finalize launch), and every LayerNorm of the code
+    transformer is written by the preceding linear's reduce kernel ('layernorm ... fused=1') -- per additional frame of the chain."""
+    kn = keep_mod.keep_net
+    tc3 = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3
+    l2, _ = _plan(keep_mod, lib, state_dict, 1, 2, tc3, tmp_path)
+    l3, _ = _plan(keep_mod, lib, state_dict, 1, 3, tc3, tmp_path)
+
+    def count(lines, pred):
+        return sum(1 for l in lines if pred(l))
+
+    per_frame = lambda pred: count(l3, pred) - count(l2, pred)
+    gn_all = per_frame(lambda l: l.startswith("groupnorm"))
+    gn_fin_in_reduce = per_frame(lambda l: l.startswith("groupnorm") and l.endswith("fused=2"))
+    gn_fin_launch = per_frame(lambda l: l.startswith("groupnorm") and l.endswith("fused=1"))
+    assert per_frame(lambda l: l.startswith("conv") and l.endswith("gnstats=2")) == gn_fin_in_reduce
+    assert per_frame(lambda l: l.startswith("conv") and l.endswith("gnstats=1")) == gn_fin_launch
+    assert gn_fin_in_reduce >= 25 and gn_fin_in_reduce + gn_fin_launch >= 0.85 * gn_all
+    # code transformer: feat_emb -> norm1, 9 x norm2, 8 x the next layer's norm1, idx_pred_layer.0
+    assert per_frame(lambda l: l.startswith("layernorm") and "rows=256 c=512" in l and l.endswith("fused=1")) == 19
+    # (the only stand-alone LayerNorms of that shape left are the two post-norms of the 16^2 cross-frame attention block)
+    assert per_frame(lambda l: l.startswith("layernorm") and "rows=256 c=512" in l and not l.endswith("fused=1")) == 2
+
+
 def test_plan_lockstep_shares_the_chain_and_asian_adds_a_cft(keep_mod, lib, state_dict, state_dict_asian, tmp_path):
     kn = keep_mod.keep_net
     tc3 = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3
