@@ -1441,7 +1441,7 @@ Tensor Engine::cfa(const Tensor& cur, const Tensor& prev, const std::string& p) 
     pv.n = 1; pv.h = nbt * L; pv.w = 1;
     Tensor q = linear(x, p + ".attn.to_q"), k = linear(pv, p + ".attn.to_k"), v = linear(pv, p + ".attn.to_v");
     const long long bs = (long long)L * inner;
-    static const int tc_min_L = getenv("KEEP_MHA_TC_MIN_L") ? atoi(getenv("KEEP_MHA_TC_MIN_L")) : 1024;
+    static const int tc_min_L = getenv("KEEP_MHA_TC_MIN_L") ? atoi(getenv("KEEP_MHA_TC_MIN_L")) : 256;   // (1024: only the 32^2 block; both measured equal in time, profiles/r2_experiments.md)
     Tensor o = ((flags_ & KEEP_FLAG_TCGEN05) && nbt == 1 && L >= tc_min_L)
                    ? mha_tc(q.f(), k.f(), v.f(), L, L, heads, dh, 1.0f / sqrtf((float)dh))
                    : mha(q.f(), inner, bs, k.f(), inner, bs, v.f(), inner, bs, nbt, L, L, heads, dh, 1.0f / sqrtf((float)dh));
