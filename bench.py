@@ -476,7 +476,7 @@ def main():
         "other_family": prof["cuda_core" if fam == "tcgen05" else "tcgen05"],
         "whole_path_tflops_per_gpu": job_flops * args.steps / (ms * 1e-3) / 1e12 / world,
         "whole_path_frac_of_tensor_peak": job_flops * args.steps / (ms * 1e-3) / 1e12 / world / pk["tflops_sustained"],
-        "note": "per-launch events of ONE profiled 20-frame clip (eager, serialised by the events); the headline value is the graph replay",
+        "note": "per-launch events of ONE profiled 20-frame clip (eager, serialised by the events, GMFlow inline on the main stream so that every launch is timed alone); the headline value is the graph replay with the GMFlow side branch",
     }
 
     if world > 1:

@@ -1560,7 +1560,11 @@ void Engine::forward_clip(const float* x_dev, int T, void* out_dev, int out_dtyp
     } else {
         // fork: GMFlow for all pairs runs on the side stream / side arena, overlapping the LQ encoder, the gain
         // estimator and the serial per-frame chain (frame i only needs the flow of pair i-1).
-        static const bool no_side = getenv("KEEP_NO_SIDE") != nullptr;   // debug / timeline: GMFlow inline on the main stream
+        // GMFlow inline on the main stream: KEEP_NO_SIDE (debug / timeline), and the per-launch profiling pass -- its CUDA events
+        // must time every kernel ALONE (with the side branch running, a full-grid main-stream kernel shares the SMs with
+        // GMFlow's persistent CTAs and its event-to-event time is not the kernel's own: 84 us vs 62 us for the dominant conv shape)
+        static const bool env_no_side = getenv("KEEP_NO_SIDE") != nullptr;
+        const bool no_side = env_no_side || profile_;
         if (!dry && !no_side) {
             if (!side_) {
                 int lo = 0, hi = 0;
@@ -1728,7 +1732,8 @@ void Engine::forward_clips(const float* x_dev, int nb, int T, void* out_dev, int
     };
 
     // ---- optical flow of every clip on the side stream (low priority), overlapping everything below
-    static const bool no_side = getenv("KEEP_NO_SIDE") != nullptr;
+    static const bool env_no_side = getenv("KEEP_NO_SIDE") != nullptr;
+    const bool no_side = env_no_side || profile_;   // (profiling pass: every kernel timed alone, see forward_clip)
     static const bool skip_flow = getenv("KEEP_DEBUG_SKIP_FLOW") != nullptr;   // timing experiments only: zero flows, no GMFlow
     const int nchunk = (T - 1 + flow_chunk() - 1) / flow_chunk();
     const bool flows_async = !dry && !no_side && !skip_flow;
