@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(tc_threads(WIN), 1) conv_tc_kernel(const TcCon
                 const int ch = (a.s2d ? (cb - par * a.ncbr) : cb) * CBK + pl * 8;   // first of this thread's 8 real channels
                 const bool ch_ok = ch < cin;
                 const uint8_t* src; int sc_ch, cc;
-                if (ch < a.c0) { src = reinterpret_cast<const uint8_t*>(a.in0); sc_ch = a.c0; cc = ch; }
+                if (ch < a.c0) { src = reinterpret_cast<const uint8_t*>(a.in0); sc_ch = a.ld0; cc = ch; }
                 else { src = reinterpret_cast<const uint8_t*>(a.in1); sc_ch = a.c1; cc = ch - a.c0; }
                 constexpr int ESZ = IN_F16 ? 2 : 4;
                 if (!waited) {   // first activation load of this thread: the previous kernel must have completed (PDL)
@@ -1235,6 +1235,8 @@ int conv2d_tc(const ConvArgs& a, const __half* packed, int bn, int passes, int s
     const int cb = cb_of(passes);
     TcConvArgs t;
     t.in0 = a.in0; t.in1 = a.in1; t.in0_dt = a.in0_dt; t.in1_dt = a.in1_dt; t.c0 = a.c0; t.c1 = a.c1;
+    KEEP_CHECK(a.ld0 == 0 || (a.kh == 1 && a.c1 == 0 && a.ld0 >= a.c0 && a.ld0 % 8 == 0), "conv2d_tc: a strided A operand needs a 1x1 layer with one source and ld0 %% 8 == 0");
+    t.ld0 = a.ld0 > 0 ? a.ld0 : a.c0;
     t.n = a.n; t.h = a.h; t.w = a.w; t.up = a.up;
     t.pre_scale = a.pre_scale; t.pre_shift = a.pre_shift; t.pre_act = a.pre_act; t.pre_exact = a.pre_exact;
     t.wt = packed; t.bias = a.bias;

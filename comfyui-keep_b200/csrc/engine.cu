@@ -801,7 +801,7 @@ Tensor Engine::res_block(const Tensor& x, const std::string& p, const Tensor* x2
 // C[z] = alpha * A[z] (M x K) * B[z]^T, B[z] = (N x K) strided view, on the tcgen05 kernel: B is packed into per-batch
 // "weight" panel sets (tc_pack_matrix) and the batch rides on the kernel's image index.  fp32 in / out.
 Tensor Engine::gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, long long b_bstride, int ld_n, int ld_k, int N,
-                          float alpha) {
+                          float alpha, int lda) {
     const long long m_tiles = (long long)nb * cdiv(M, 128);
     const int bn = tc_pick_bn(N, m_tiles, tc_passes_);
     if (plan_) plan_->push_back("gemm nb=" + std::to_string(nb) + " M=" + std::to_string(M) + " K=" + std::to_string(K) + " N=" +
@@ -812,7 +812,7 @@ Tensor Engine::gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, 
     if (!ar_->dry()) {
         tc_pack_matrix(B, b_bstride, ld_n, ld_k, nb, N, K, bn, tc_passes_, alpha, panels, s_);
         ConvArgs a;
-        a.in0 = A; a.in0_dt = F32; a.c0 = K;
+        a.in0 = A; a.in0_dt = F32; a.c0 = K; a.ld0 = lda;   // (lda > 0: A[z] = M rows of a wider matrix, batch stride M * lda)
         a.n = nb; a.h = M; a.w = 1; a.up = 1;
         a.kh = 1; a.kw = 1; a.stride = 1; a.cout = N; a.ho = M; a.wo = 1;
         a.out = out.p; a.out_dt = F32;
@@ -913,8 +913,26 @@ Tensor Engine::attn_block(const Tensor& x, const std::string& p, bool out_stats,
     Tensor qkv = conv(x, p + ".qkv", o);
     afree(a);
     const int L = x.h * x.w, C = x.c;
-    Tensor O = mha(qkv.f(), 3 * C, (long long)L * 3 * C, qkv.f() + C, 3 * C, (long long)L * 3 * C, qkv.f() + 2 * C, 3 * C,
-                   (long long)L * 3 * C, x.n, L, L, 1, C, 1.0f / sqrtf((float)C));
+    // both contractions on the tcgen05 GEMM kernel (q / k / v are column slices of the fused qkv matrix: strided A operand, strided
+    // B packs), scores materialised (n x L x L fp32, 256 KB per image at 16^2).  KEEP_ATTNBLOCK_TC=0: the CUDA-core batched GEMMs of
+    // round 1 (measured equal in time: 177.3 vs 177.0 frames/s, profiles/r2_experiments.md)
+    static const bool attn_tc = !(getenv("KEEP_ATTNBLOCK_TC") && getenv("KEEP_ATTNBLOCK_TC")[0] == '0');
+    Tensor O;
+    if (attn_tc && (flags_ & KEEP_FLAG_TCGEN05) && tc_passes_ == 3 && L % 128 == 0 && C % 32 == 0) {
+        if (plan_) plan_->push_back("attention nb=" + std::to_string(x.n) + " Lq=" + std::to_string(L) + " Lk=" + std::to_string(L) +
+                                    " heads=1 dh=" + std::to_string(C) + " kernel=tcgen05");
+        std::vector<std::string>* plan_saved = plan_;
+        plan_ = nullptr;                                    // (the "attention" line covers both contractions)
+        const long long bs = (long long)L * 3 * C;
+        Tensor S = gemm_nt_tc(qkv.f(), x.n, L, C, qkv.f() + C, bs, 3 * C, 1, L, 1.0f / sqrtf((float)C), 3 * C);
+        if (!ar_->dry()) { softmax_rows(S.f(), (long long)x.n * L, L, nullptr, 1, L, s_); launches_ += 1; }
+        O = gemm_nt_tc(S.f(), x.n, L, L, qkv.f() + 2 * C, bs, 1, 3 * C, C, 1.0f);
+        plan_ = plan_saved;
+        tfree(S);
+    } else {
+        O = mha(qkv.f(), 3 * C, (long long)L * 3 * C, qkv.f() + C, 3 * C, (long long)L * 3 * C, qkv.f() + 2 * C, 3 * C,
+                (long long)L * 3 * C, x.n, L, L, 1, C, 1.0f / sqrtf((float)C));
+    }
     tfree(qkv);
     O.h = x.h; O.w = x.w;
     ConvOpt po;

@@ -97,7 +97,7 @@ class Engine {
     // multi-head attention on (rows, ld) matrices; writes (nb*Lq, heads*dh)
     Tensor mha(const float* q, int ldq, long long sq, const float* k, int ldk, long long sk, const float* v, int ldv, long long sv,
                int nb, int Lq, int Lk, int heads, int dh, float scale);
-    Tensor gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, long long b_bstride, int ld_n, int ld_k, int N, float alpha);
+    Tensor gemm_nt_tc(const float* A, int nb, int M, int K, const float* B, long long b_bstride, int ld_n, int ld_k, int N, float alpha, int lda = 0);
     // multi-head attention on token-major (L, heads * dh) fp32 matrices, all three contractions on the tcgen05 kernel
     Tensor mha_tc(const float* q, const float* k, const float* v, int Lq, int Lk, int heads, int dh, float scale);
     ConvW convw(const std::string& prefix) const;

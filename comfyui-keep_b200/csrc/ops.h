@@ -12,6 +12,7 @@ struct ConvArgs {
     // input: up to two NHWC sources concatenated along channels (torch.cat([enc, dec], 1) of the
     // CFT block, keep_arch.py:467, is never materialised)
     const void* in0 = nullptr; int in0_dt = F32; int c0 = 0;
+    int ld0 = 0;                   // tcgen05 path, 1x1 layers: row stride of in0 in elements (0: dense rows of c0) -- a column slice of a wider matrix
     const void* in1 = nullptr; int in1_dt = F32; int c1 = 0;
     int n = 0, h = 0, w = 0;     // physical input size
     int up = 1;                  // nearest-neighbour upsample factor applied on the fly (vqgan_arch.py:149)

@@ -6,6 +6,7 @@ namespace keep {
 
 struct TcConvArgs {
     const void* in0; const void* in1; int in0_dt, in1_dt; int c0, c1;
+    int ld0;            // row stride of in0 in elements (= c0 unless the A operand is a column slice of a wider matrix)
     int n, h, w, up;
     const float* pre_scale; const float* pre_shift; int pre_act; int pre_exact;
     const __half* wt; const float* bias;
