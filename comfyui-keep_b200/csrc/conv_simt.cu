@@ -276,7 +276,15 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
             const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
             const float2* base = reinterpret_cast<const float2*>(gn_part) + (size_t)(img * 32 + g) * gn_P;
             double sm = 0.0, sq = 0.0;
-            for (int k = l; k < gn_P; k += 8) {
+            int k = l;
+            for (; k + 24 < gn_P; k += 32) {   // four loads in flight per lane (a rolled loop paid one L2 round trip per slot); same order of additions
+                const float2 e0 = __ldcg(base + k), e1 = __ldcg(base + k + 8), e2 = __ldcg(base + k + 16), e3 = __ldcg(base + k + 24);
+                sm += (double)e0.x; sq += (double)e0.y;
+                sm += (double)e1.x; sq += (double)e1.y;
+                sm += (double)e2.x; sq += (double)e2.y;
+                sm += (double)e3.x; sq += (double)e3.y;
+            }
+            for (; k < gn_P; k += 8) {
                 const float2 e = __ldcg(base + k);
                 sm += (double)e.x; sq += (double)e.y;
             }

@@ -574,9 +574,10 @@ Tensor Engine::conv(const Tensor& x, const ConvW& cw, const ConvOpt& o) {
             out.gn_P = P;
             out.gn_part = (float*)ar_->alloc((size_t)x.n * P * 64 * sizeof(float));
             a.gn_part = out.gn_part; a.gn_P = P;
-            // few slots behind a split-K reduce: its last block per image finalizes them (no gn_finalize_parts launch);
-            // KEEP_GN_REDUCE_FINAL=0 keeps the separate launch
-            static const bool fin_en = !(getenv("KEEP_GN_REDUCE_FINAL") && getenv("KEEP_GN_REDUCE_FINAL")[0] == '0');
+            // KEEP_GN_REDUCE_FINAL=1 (opt-in): few slots behind a split-K reduce -> its last block per image finalizes them (ticket), no
+            // gn_finalize_parts launch.  Measured 0.6 % SLOWER than the separate launch (176.9 vs 177.9 frames/s): under graph + PDL
+            // the launch boundary costs less than the serial tail (fence, ticket, one block walking 32 x P slots)
+            static const bool fin_en = getenv("KEEP_GN_REDUCE_FINAL") && getenv("KEEP_GN_REDUCE_FINAL")[0] == '1';
             if (fin_en && a.splitk > 1 && P <= kGnReduceFinalMaxP && !o.stats_norm.empty() && x.n <= gn_ticket_count() &&
                 has(o.stats_norm + ".weight")) {
                 out.aff = (float*)ar_->alloc((size_t)2 * x.n * cw.cout * sizeof(float));

@@ -269,8 +269,8 @@ def test_plan_per_frame_chain_and_kernel_choice(keep_mod, lib, state_dict, tmp_p
 
 
 def test_plan_norms_ride_on_the_producing_kernels(keep_mod, lib, state_dict, tmp_path):
-    """GroupNorm statistics come from the producing conv / split-K reduce ('gnstats=1'), split-K layers with few slots also
-    finalize them inside the reduce ('gnstats=2' + 'groupnorm ... fused=2': no finalize launch), and every LayerNorm of the code
+    """GroupNorm statistics come from the producing conv / split-K reduce ('gnstats=1'; with KEEP_GN_REDUCE_FINAL=1 split-K layers
+    with few slots also finalize them inside the reduce: 'gnstats=2' + 'groupnorm ... fused=2', no finalize launch), and every LayerNorm of the code
     transformer is written by the preceding linear's reduce kernel ('layernorm ... fused=1') -- per additional frame of the chain."""
     kn = keep_mod.keep_net
     tc3 = kn.FLAG_TCGEN05 | kn.FLAG_TC_SPLIT3
@@ -286,7 +286,9 @@ def test_plan_norms_ride_on_the_producing_kernels(keep_mod, lib, state_dict, tmp
     gn_fin_launch = per_frame(lambda l: l.startswith("groupnorm") and l.endswith("fused=1"))
     assert per_frame(lambda l: l.startswith("conv") and l.endswith("gnstats=2")) == gn_fin_in_reduce
     assert per_frame(lambda l: l.startswith("conv") and l.endswith("gnstats=1")) == gn_fin_launch
-    assert gn_fin_in_reduce >= 25 and gn_fin_in_reduce + gn_fin_launch >= 0.85 * gn_all
+    # (finalize inside the reduce is opt-in -- KEEP_GN_REDUCE_FINAL=1 -- since the separate tiny launch measured 0.6 % faster)
+    assert gn_fin_in_reduce == (30 if os.environ.get("KEEP_GN_REDUCE_FINAL") == "1" else 0)
+    assert gn_fin_in_reduce + gn_fin_launch >= 0.85 * gn_all
     # code transformer: feat_emb -> norm1, 9 x norm2, 8 x the next layer's norm1, idx_pred_layer.0
     assert per_frame(lambda l: l.startswith("layernorm") and "rows=256 c=512" in l and l.endswith("fused=1")) == 19
     # (the only stand-alone LayerNorms of that shape left are the two post-norms of the 16^2 cross-frame attention block)
